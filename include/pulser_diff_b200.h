@@ -1,0 +1,165 @@
+/*
+ * pulser_diff_b200 C ABI  --  B200 (sm_100a) evolution engine behind pulser-diff's solver call.
+ *
+ * This is the drop-in boundary for the ONE hot path of pasqal-io/pulser-diff:
+ *
+ *     TorchEmulator.run._run_solver                  reference pulser_diff/backend.py:485-529
+ *       -> pyqtorch.sesolve(H, psi0, tsave, solver, options)      backend.py:488-494
+ *       -> pyqtorch.mesolve(H, rho0, L, tsave, solver, options)   backend.py:502-509
+ *     fed by Hamiltonian.build_ham_tensor / H_t       reference pulser_diff/hamiltonian.py:499-548
+ *     and differentiated by the autograd tape         reference pulser_diff/derivative.py:40,76
+ *
+ * The reference hands the solver an opaque closure H(t) -> sparse COO.  Here the same
+ * information crosses the boundary as STRUCTURE:
+ *
+ *   H(t) psi[s] = ( Dint[s] + sum_q d_q(t) r_q(s) ) psi[s]
+ *               + sum_q ( bit_q(s) ? g_q(t) : conj(g_q(t)) ) psi[s ^ m_q]
+ *
+ *   r_q(s) = 1 - bit_q(s)  (bit value 0 = Rydberg; |r> = e0, |g> = e1; hamiltonian.py:296-300)
+ *   m_q    = 1 << (N-1-q)  (qubit 0 is the most significant bit; hamiltonian.py:243-268)
+ *   Dint[s]= sum_{i<j} U_ij r_i r_j,  U_ij = C6 / r_ij^6   (hamiltonian.py:341-344, 536)
+ *   d_q(t) = 2 * sum_{det terms T containing q} interp(det_values[T], t)   (hamiltonian.py:537-540)
+ *   g_q(t) =     sum_{amp terms T containing q} interp(amp_values[T], t)   (hamiltonian.py:541-544)
+ *   interp(v,t): i1 = max(min(floor(t/dt), n-2), 0); i2 = min(i1+1, n-2);
+ *                v[i1] + (v[i2]-v[i1]) * (t - i1*dt) / dt                  (hamiltonian.py:532-542)
+ *
+ * det_values / amp_values are EXACTLY the reference's coefficient arrays
+ * (-0.5*det and 0.5*amp*exp(-i*phase), sub-sampled; hamiltonian.py:421-422, 432).
+ *
+ * All entry points: plain pointers and sizes, int status (0 = ok), message via
+ * pd_last_error().  "dev" pointers are CUDA device pointers on the plan's device,
+ * "host" pointers are ordinary host memory.  Complex numbers are interleaved
+ * (re, im) doubles.  State vectors cross the ABI batch-major: [batch][2^nbits].
+ * Work is queued on `stream` (a cudaStream_t passed as void*); calls that return
+ * host-side results synchronise that stream before returning.
+ */
+#ifndef PULSER_DIFF_B200_H
+#define PULSER_DIFF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PD_ABI_VERSION 1
+
+/* status codes */
+#define PD_OK 0
+#define PD_ERR_INVALID 1   /* bad argument            -> ValueError  */
+#define PD_ERR_CUDA 2      /* CUDA runtime failure    -> RuntimeError */
+#define PD_ERR_MAX_STEPS 3 /* adaptive solver gave up -> RuntimeError (pyqtorch max_steps) */
+#define PD_ERR_STATE 4     /* call order / missing setup -> RuntimeError */
+
+/* state kinds */
+#define PD_KET 0     /* psi in C^(2^N)              (sesolve, backend.py:488-494) */
+#define PD_DENSITY 1 /* vec(rho) in C^(4^N), row-major rho[r][c] (mesolve, backend.py:502-509) */
+
+/* solver ids, mirroring pyqtorch.utils.SolverType used at backend.py:434,483,487,495 */
+#define PD_SOLVER_DP5_SE 0
+#define PD_SOLVER_KRYLOV_SE 1
+#define PD_SOLVER_DP5_ME 2
+
+typedef struct pd_plan pd_plan; /* one register + pulse program + workspace */
+typedef struct pd_tape pd_tape; /* step log + checkpoints of one forward evolution */
+
+/* Solver options: the keys the reference forwards untouched through **options
+ * (backend.py:435,493,508); defaults are pyqtorch's. */
+typedef struct pd_options {
+  double atol;          /* 1e-8  */
+  double rtol;          /* 1e-6  */
+  int64_t max_steps;    /* 100000 */
+  double safety_factor; /* 0.9 */
+  double min_factor;    /* 0.2 */
+  double max_factor;    /* 5.0 */
+  int32_t max_krylov;   /* 80 */
+  double exp_tolerance; /* 1e-10 */
+  double norm_tolerance;/* 1e-10 */
+  /* additions (do not change defaults): */
+  int32_t n_replay;     /* >0: force this attempted-step sequence (shared-step parity protocol) */
+  const double* replay_dt;      /* host [n_replay] step sizes (ignored for clipped steps) */
+  const uint8_t* replay_clipped;/* host [n_replay] 1 = step lands on the next tsave point */
+  int32_t path;         /* 0 = auto, 1 = force generic gather kernels, 2 = force tiled kernels */
+} pd_options;
+
+typedef struct pd_step_record {
+  double t;        /* start time of the attempt (us) */
+  double dt;       /* step size used */
+  double error;    /* Hairer error norm (accepted iff <= 1) */
+  int32_t accepted;
+  int32_t clipped; /* dt was cut to land on tsave[interval] */
+  int32_t interval;/* index k of the tsave point being integrated towards */
+  int32_t _pad;
+} pd_step_record;
+
+int pd_abi_version(void);
+const char* pd_last_error(void);
+void pd_options_default(pd_options* o);
+
+/* ---- plan ------------------------------------------------------------------------------- */
+/* kind PD_KET: nbits = n_qubits.  PD_DENSITY: nbits = 2*n_qubits.  `device` = CUDA ordinal. */
+int pd_plan_create(pd_plan** out, int32_t n_qubits, int32_t batch, int32_t kind, int32_t device);
+int pd_plan_destroy(pd_plan* p);
+
+/* U_ij (host, row-major N*N, upper triangle used).  Builds Dint[2^N] on the device with a
+ * kernel.  Replaces 2*int_mat of hamiltonian.py:385-404,536. */
+int pd_plan_set_interaction(pd_plan* p, const double* pair_u_host, void* stream);
+
+/* Coefficient terms, the reference's qobj_list split (hamiltonian.py:506-520).
+ * det_values: host real [n_det][n_samples]; amp_values: host complex [n_amp][n_samples];
+ * masks: bit q set <=> the term's operator acts on qubit q (global channel = all bits).
+ * dt = 0.001 / sampling_rate (hamiltonian.py:523). */
+int pd_plan_set_terms(pd_plan* p, int32_t n_samples, double dt, int32_t n_det,
+                      const uint64_t* det_masks, const double* det_values, int32_t n_amp,
+                      const uint64_t* amp_masks, const double* amp_values);
+
+/* Lindblad collapse operators (PD_DENSITY only): n_ops single-qubit 2x2 complex operators,
+ * rate already folded in (sqrt(gamma)*op), each applied on EVERY qubit -- the shape produced
+ * by _build_collapse_operators (hamiltonian.py:98-143).  ops_host: [n_ops][2][2] complex,
+ * (r,g) basis.  n_ops = 0 reproduces backend.py:496-498 (single zero operator). */
+int pd_plan_set_collapse(pd_plan* p, int32_t n_ops, const double* ops_host);
+
+/* ---- single operator applications --------------------------------------------------------- */
+/* out = H(t) in   (ket plans; what `H(t) @ psi` does upstream) */
+int pd_hpsi(pd_plan* p, void* stream, double t, const void* in_dev, void* out_dev);
+/* out = d/dt state: -i H(t) psi  or the Lindblad right-hand side */
+int pd_rhs(pd_plan* p, void* stream, double t, const void* in_dev, void* out_dev);
+
+/* ---- evolution ---------------------------------------------------------------------------- */
+/* states_dev: [n_t][batch][dim] complex, states[0] = state0.  tsave host [n_t] (us, sorted,
+ * tsave[0] is the start time).  If tape_out != NULL a tape is created for pd_evolve_backward
+ * (caller destroys it).  n_steps_out/n_rejected_out may be NULL. */
+int pd_evolve_forward(pd_plan* p, void* stream, int32_t solver, const pd_options* opt,
+                      const void* state0_dev, const double* tsave_host, int32_t n_t,
+                      void* states_dev, pd_tape** tape_out);
+
+/* Adjoint sweep over the recorded step sequence (discretise-then-differentiate, like the
+ * reference's tape autograd, derivative.py:40,76).  grad_states_dev: cotangent of states
+ * [n_t][batch][dim].  Any output may be NULL.  Host outputs: grad_det [n_det][n_samples]
+ * real, grad_amp [n_amp][n_samples] complex (dL/dRe + i dL/dIm), grad_pair_u [N*N],
+ * grad_tsave [n_t].  grad_state0_dev: [batch][dim]. */
+int pd_evolve_backward(pd_plan* p, void* stream, pd_tape* tape, const void* states_dev,
+                       const void* grad_states_dev, double* grad_det_host, double* grad_amp_host,
+                       double* grad_pair_u_host, double* grad_tsave_host, void* grad_state0_dev);
+
+int64_t pd_tape_n_records(const pd_tape* t);
+int pd_tape_records(const pd_tape* t, pd_step_record* out, int64_t capacity);
+int pd_tape_destroy(pd_tape* t);
+
+/* ---- diagonal observables (utils.expect for diagonal O) --------------------- */
+/* out_host[n_t]: sum over batch columns of <psi|diag(obs)|psi>  (ket)  or  tr(diag(obs) rho)
+ * (density).  obs_dev: real [2^N]. */
+int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t,
+                   const double* obs_dev, double* out_host /* complex [n_t] */);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+/* number of CUDA kernels this plan has launched since creation (bench.py gpu_launches) */
+int64_t pd_plan_launch_count(const pd_plan* p);
+/* 1 if this library was built with the CUDA backend, 0 for the host stand-in used by tests */
+int pd_is_cuda(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PULSER_DIFF_B200_H */

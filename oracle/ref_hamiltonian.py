@@ -153,6 +153,7 @@ class RefHamiltonian:
             local += [c * _X, c * _Y, c * _Z]
         for rate, op in nz.get("eff_noise", []):
             local.append(torch.sqrt(torch.as_tensor(rate)) * torch.as_tensor(op, dtype=C128))
+        self.local_ops = local          # the single-qubit operators, rate folded in
         return [embed(self.n, {q: op}, dense=True) for op in local for q in range(self.n)]
 
     # -- reference hamiltonian.py:499-548 ------------------------------------------

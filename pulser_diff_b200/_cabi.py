@@ -1,0 +1,329 @@
+"""ctypes binding of ``include/pulser_diff_b200.h``.
+
+The product loads ``pulser_diff_b200/libpulser_diff_b200.so`` (built for sm_100a by
+``__graft_entry__.build()``) and nothing else: there is NO CPU fallback.  If the CUDA
+library is missing, or a tensor is not on a CUDA device, the call raises.
+
+Tests of the host-side logic may inject the host stand-in of the same ABI
+(``tests/emu/libpd_emu.so``) with :func:`use_library`; that is the only way a non-CUDA
+library is ever bound, and the package never does it by itself.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIBRARY = os.path.join(_HERE, "libpulser_diff_b200.so")
+
+PD_KET, PD_DENSITY = 0, 1
+SOLVER_DP5_SE, SOLVER_KRYLOV_SE, SOLVER_DP5_ME = 0, 1, 2
+_ERR_INVALID = 1
+
+
+class pd_options(C.Structure):
+    _fields_ = [
+        ("atol", C.c_double), ("rtol", C.c_double), ("max_steps", C.c_int64),
+        ("safety_factor", C.c_double), ("min_factor", C.c_double), ("max_factor", C.c_double),
+        ("max_krylov", C.c_int32), ("exp_tolerance", C.c_double), ("norm_tolerance", C.c_double),
+        ("n_replay", C.c_int32), ("replay_dt", C.POINTER(C.c_double)),
+        ("replay_clipped", C.POINTER(C.c_uint8)), ("path", C.c_int32),
+    ]
+
+
+class pd_step_record(C.Structure):
+    _fields_ = [("t", C.c_double), ("dt", C.c_double), ("error", C.c_double),
+                ("accepted", C.c_int32), ("clipped", C.c_int32), ("interval", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
+# every symbol include/pulser_diff_b200.h declares (checked by tests/test_cabi_symbols.py)
+EXPORTS = (
+    "pd_abi_version", "pd_last_error", "pd_options_default", "pd_plan_create", "pd_plan_destroy",
+    "pd_plan_set_interaction", "pd_plan_set_terms", "pd_plan_set_collapse", "pd_hpsi", "pd_rhs",
+    "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
+    "pd_tape_destroy", "pd_expect_diag", "pd_plan_launch_count", "pd_is_cuda",
+)
+
+_lib: Optional[C.CDLL] = None
+_lib_path: Optional[str] = None
+
+
+def _declare(lib: C.CDLL) -> None:
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    pdbl, pu64 = C.POINTER(C.c_double), C.POINTER(C.c_uint64)
+    lib.pd_abi_version.restype = C.c_int
+    lib.pd_last_error.restype = C.c_char_p
+    lib.pd_is_cuda.restype = C.c_int
+    lib.pd_options_default.argtypes = [C.POINTER(pd_options)]
+    lib.pd_options_default.restype = None
+    lib.pd_plan_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
+    lib.pd_plan_destroy.argtypes = [vp]
+    lib.pd_plan_set_interaction.argtypes = [vp, pdbl, vp]
+    lib.pd_plan_set_terms.argtypes = [vp, i32, dbl, i32, pu64, pdbl, i32, pu64, pdbl]
+    lib.pd_plan_set_collapse.argtypes = [vp, i32, pdbl]
+    lib.pd_hpsi.argtypes = [vp, vp, dbl, vp, vp]
+    lib.pd_rhs.argtypes = [vp, vp, dbl, vp, vp]
+    lib.pd_evolve_forward.argtypes = [vp, vp, i32, C.POINTER(pd_options), vp, pdbl, i32, vp,
+                                      C.POINTER(vp)]
+    lib.pd_evolve_backward.argtypes = [vp, vp, vp, vp, vp, pdbl, pdbl, pdbl, pdbl, vp]
+    lib.pd_tape_n_records.argtypes = [vp]
+    lib.pd_tape_n_records.restype = i64
+    lib.pd_tape_records.argtypes = [vp, C.POINTER(pd_step_record), i64]
+    lib.pd_tape_destroy.argtypes = [vp]
+    lib.pd_expect_diag.argtypes = [vp, vp, vp, i32, vp, pdbl]
+    lib.pd_plan_launch_count.argtypes = [vp]
+    lib.pd_plan_launch_count.restype = i64
+
+
+def use_library(path: Optional[str]) -> None:
+    """Bind an explicit library (tests only) or reset to the default with ``None``."""
+    global _lib, _lib_path
+    _lib, _lib_path = None, path
+
+
+def lib() -> C.CDLL:
+    global _lib, _lib_path
+    if _lib is None:
+        path = _lib_path or DEFAULT_LIBRARY
+        if not os.path.exists(path):
+            raise RuntimeError(
+                f"pulser_diff_b200: CUDA library not found at {path}. Build it with "
+                "`python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                "There is no CPU fallback.")
+        handle = C.CDLL(path)
+        _declare(handle)
+        if handle.pd_abi_version() != 1:
+            raise RuntimeError("pulser_diff_b200: ABI version mismatch")
+        _lib, _lib_path = handle, path
+    return _lib
+
+
+def is_cuda_library() -> bool:
+    return bool(lib().pd_is_cuda())
+
+
+def _check(status: int) -> None:
+    if status == 0:
+        return
+    msg = lib().pd_last_error().decode()
+    if status == _ERR_INVALID:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def _require_device(t: torch.Tensor, what: str) -> None:
+    if is_cuda_library():
+        if not t.is_cuda:
+            raise RuntimeError(
+                f"pulser_diff_b200: {what} must live on a CUDA device (got {t.device}); "
+                "this package has no CPU path.")
+    elif t.is_cuda:
+        raise RuntimeError("host stand-in library bound but tensor is on CUDA")
+
+
+def _stream(device: torch.device) -> C.c_void_p:
+    if device.type == "cuda":
+        return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+    return C.c_void_p(0)
+
+
+def _dptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _hdbl(t: Optional[torch.Tensor]):
+    if t is None:
+        return C.POINTER(C.c_double)()
+    return C.cast(C.c_void_p(t.data_ptr()), C.POINTER(C.c_double))
+
+
+@dataclass
+class Options:
+    """Solver options forwarded by ``TorchEmulator.run(**options)`` (reference backend.py:435)."""
+    atol: float = 1e-8
+    rtol: float = 1e-6
+    max_steps: int = 100_000
+    safety_factor: float = 0.9
+    min_factor: float = 0.2
+    max_factor: float = 5.0
+    max_krylov: int = 80
+    exp_tolerance: float = 1e-10
+    norm_tolerance: float = 1e-10
+    use_sparse: bool = False          # accepted for API parity; the path is matrix free
+    replay: Optional[Sequence] = None  # [(dt, clipped), ...] shared-step parity protocol
+    path: int = 0                     # 0 auto, 1 gather kernels, 2 tiled kernels
+
+    @classmethod
+    def from_dict(cls, d: Optional[dict]) -> "Options":
+        d = dict(d or {})
+        unknown = set(d) - set(cls.__dataclass_fields__)
+        if unknown:
+            raise TypeError(f"unknown solver option(s): {sorted(unknown)}")
+        return cls(**d)
+
+
+class Tape:
+    """Owner of a ``pd_tape*`` (step log of one forward evolution)."""
+
+    def __init__(self, ptr: int) -> None:
+        self._ptr = C.c_void_p(ptr)
+
+    @property
+    def ptr(self) -> C.c_void_p:
+        return self._ptr
+
+    def records(self) -> list[dict]:
+        n = lib().pd_tape_n_records(self._ptr)
+        buf = (pd_step_record * max(n, 1))()
+        _check(lib().pd_tape_records(self._ptr, buf, n))
+        return [dict(t=r.t, dt=r.dt, error=r.error, accepted=bool(r.accepted),
+                     clipped=bool(r.clipped), interval=r.interval) for r in buf[:n]]
+
+    def __del__(self) -> None:
+        try:
+            if self._ptr:
+                lib().pd_tape_destroy(self._ptr)
+                self._ptr = C.c_void_p(0)
+        except Exception:
+            pass
+
+
+class Plan:
+    """Owner of a ``pd_plan*``: one register geometry + workspace on one device."""
+
+    def __init__(self, n_qubits: int, batch: int, kind: int, device: torch.device) -> None:
+        self.n_qubits, self.batch, self.kind = int(n_qubits), int(batch), int(kind)
+        self.device = torch.device(device)
+        if is_cuda_library() and self.device.type != "cuda":
+            raise RuntimeError(
+                f"pulser_diff_b200 runs on CUDA devices only (asked for {self.device}); "
+                "there is no CPU fallback.")
+        ordinal = self.device.index if self.device.index is not None else (
+            torch.cuda.current_device() if self.device.type == "cuda" else 0)
+        p = C.c_void_p()
+        _check(lib().pd_plan_create(C.byref(p), self.n_qubits, self.batch, self.kind, ordinal))
+        self._ptr = p
+        self.dim = 2 ** (self.n_qubits if kind == PD_KET else 2 * self.n_qubits)
+        self.program_id = -1
+        self.n_det = self.n_amp = self.n_samples = 0
+
+    def __del__(self) -> None:
+        try:
+            if self._ptr:
+                lib().pd_plan_destroy(self._ptr)
+                self._ptr = C.c_void_p(0)
+        except Exception:
+            pass
+
+    # ---- setup -----------------------------------------------------------------------------
+    def set_interaction(self, pair_u: torch.Tensor) -> None:
+        u = pair_u.detach().to("cpu", torch.float64).contiguous()
+        if tuple(u.shape) != (self.n_qubits, self.n_qubits):
+            raise ValueError("pair_u must be (N, N)")
+        _check(lib().pd_plan_set_interaction(self._ptr, _hdbl(u), _stream(self.device)))
+
+    def set_terms(self, dt: float, det_masks: Sequence[int], det_values: torch.Tensor,
+                  amp_masks: Sequence[int], amp_values: torch.Tensor) -> None:
+        dv = det_values.detach().to("cpu", torch.float64).contiguous()
+        av = torch.view_as_real(amp_values.detach().to("cpu", torch.complex128).contiguous()).contiguous()
+        n_det, n_amp = len(det_masks), len(amp_masks)
+        n_samples = int(dv.shape[1]) if n_det else (int(av.shape[1]) if n_amp else 2)
+        if n_det and tuple(dv.shape) != (n_det, n_samples):
+            raise ValueError("det_values must be (n_det, n_samples)")
+        if n_amp and tuple(av.shape) != (n_amp, n_samples, 2):
+            raise ValueError("amp_values must be (n_amp, n_samples)")
+        dm = (C.c_uint64 * max(n_det, 1))(*det_masks)
+        am = (C.c_uint64 * max(n_amp, 1))(*amp_masks)
+        _check(lib().pd_plan_set_terms(self._ptr, n_samples, float(dt), n_det, dm, _hdbl(dv),
+                                       n_amp, am, _hdbl(av)))
+        self.n_det, self.n_amp, self.n_samples = n_det, n_amp, n_samples
+
+    def set_collapse(self, ops: Optional[torch.Tensor]) -> None:
+        if ops is None or ops.numel() == 0:
+            _check(lib().pd_plan_set_collapse(self._ptr, 0, C.POINTER(C.c_double)()))
+            return
+        o = torch.view_as_real(ops.detach().to("cpu", torch.complex128).contiguous()).contiguous()
+        if tuple(o.shape[1:]) != (2, 2, 2):
+            raise ValueError("collapse operators must be (n_ops, 2, 2) complex")
+        _check(lib().pd_plan_set_collapse(self._ptr, int(o.shape[0]), _hdbl(o)))
+
+    # ---- applications ------------------------------------------------------------------------
+    def _vec(self, t: torch.Tensor, what: str, lead: tuple = ()) -> torch.Tensor:
+        _require_device(t, what)
+        if t.dtype != torch.complex128:
+            raise TypeError(f"{what} must be complex128")
+        want = lead + (self.batch, self.dim)
+        if tuple(t.shape) != want:
+            raise ValueError(f"{what} must have shape {want}, got {tuple(t.shape)}")
+        return t.contiguous()
+
+    def hpsi(self, t: float, psi: torch.Tensor, rhs: bool = False) -> torch.Tensor:
+        psi = self._vec(psi, "psi")
+        out = torch.empty_like(psi)
+        fn = lib().pd_rhs if rhs else lib().pd_hpsi
+        _check(fn(self._ptr, _stream(self.device), float(t), _dptr(psi), _dptr(out)))
+        return out
+
+    def evolve_forward(self, solver: int, opt: Options, state0: torch.Tensor, tsave: torch.Tensor,
+                       want_tape: bool) -> tuple[torch.Tensor, Optional[Tape]]:
+        state0 = self._vec(state0, "state0")
+        ts = tsave.detach().to("cpu", torch.float64).contiguous()
+        n_t = int(ts.numel())
+        states = torch.empty((n_t, self.batch, self.dim), dtype=torch.complex128, device=state0.device)
+        o = pd_options()
+        lib().pd_options_default(C.byref(o))
+        for k in ("atol", "rtol", "max_steps", "safety_factor", "min_factor", "max_factor",
+                  "max_krylov", "exp_tolerance", "norm_tolerance", "path"):
+            setattr(o, k, getattr(opt, k))
+        keep = None
+        if opt.replay:
+            n = len(opt.replay)
+            dts = (C.c_double * n)(*[float(r[0]) for r in opt.replay])
+            cl = (C.c_uint8 * n)(*[1 if r[1] else 0 for r in opt.replay])
+            o.n_replay, o.replay_dt, o.replay_clipped = n, dts, cl
+            keep = (dts, cl)
+        tape_ptr = C.c_void_p()
+        _check(lib().pd_evolve_forward(self._ptr, _stream(self.device), int(solver), C.byref(o),
+                                       _dptr(state0), _hdbl(ts), n_t, _dptr(states),
+                                       C.byref(tape_ptr) if want_tape else None))
+        del keep
+        return states, (Tape(tape_ptr.value) if want_tape else None)
+
+    def evolve_backward(self, tape: Tape, states: torch.Tensor, grad_states: torch.Tensor,
+                        want_det: bool, want_amp: bool, want_pair: bool, want_tsave: bool,
+                        want_state0: bool):
+        n_t = int(states.shape[0])
+        states = self._vec(states, "states", (n_t,))
+        grad_states = self._vec(grad_states, "grad_states", (n_t,))
+        g_det = torch.zeros((self.n_det, self.n_samples), dtype=torch.float64) if want_det and self.n_det else None
+        g_amp = torch.zeros((self.n_amp, self.n_samples, 2), dtype=torch.float64) if want_amp and self.n_amp else None
+        g_pair = torch.zeros((self.n_qubits, self.n_qubits), dtype=torch.float64) if want_pair else None
+        g_ts = torch.zeros(n_t, dtype=torch.float64) if want_tsave else None
+        g_s0 = torch.empty((self.batch, self.dim), dtype=torch.complex128, device=states.device) if want_state0 else None
+        _check(lib().pd_evolve_backward(self._ptr, _stream(self.device), tape.ptr, _dptr(states),
+                                        _dptr(grad_states), _hdbl(g_det), _hdbl(g_amp), _hdbl(g_pair),
+                                        _hdbl(g_ts), _dptr(g_s0)))
+        if g_amp is not None:
+            g_amp = torch.view_as_complex(g_amp)
+        return g_det, g_amp, g_pair, g_ts, g_s0
+
+    def expect_diag(self, states: torch.Tensor, obs_diag: torch.Tensor) -> torch.Tensor:
+        n_t = int(states.shape[0])
+        states = self._vec(states, "states", (n_t,))
+        _require_device(obs_diag, "obs_diag")
+        obs = obs_diag.to(torch.float64).contiguous()
+        if obs.numel() != 2 ** self.n_qubits:
+            raise ValueError("diagonal observable must have 2**N entries")
+        out = torch.zeros(n_t, 2, dtype=torch.float64)
+        _check(lib().pd_expect_diag(self._ptr, _stream(self.device), _dptr(states), n_t, _dptr(obs),
+                                    _hdbl(out)))
+        return torch.view_as_complex(out)
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().pd_plan_launch_count(self._ptr))

@@ -1,0 +1,156 @@
+// C-ABI entry points (include/pulser_diff_b200.h), templated on the backend through PD_BACKEND.
+// Included by cabi.cu (CUDA, the product) and by tests/emu/emu_lib.cpp (host stand-in, tests only).
+#pragma once
+#include "engine.hpp"
+
+#ifndef PD_BACKEND
+#error "define PD_BACKEND before including cabi_impl.hpp"
+#endif
+
+using PdEngine = pd::Engine<PD_BACKEND>;
+
+struct pd_plan {
+  PdEngine eng;
+  pd_plan(int nq, int batch, int kind, int dev) : eng(nq, batch, kind, dev) {}
+};
+struct pd_tape {
+  pd::Tape tape;
+};
+
+namespace {
+thread_local std::string g_last_error;
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return PD_OK;
+  } catch (const pd::Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return PD_ERR_STATE;
+  }
+}
+void need(bool ok, const char* what) {
+  if (!ok) throw pd::Error(PD_ERR_INVALID, what);
+}
+}  // namespace
+
+extern "C" {
+
+int pd_abi_version(void) { return PD_ABI_VERSION; }
+const char* pd_last_error(void) { return g_last_error.c_str(); }
+int pd_is_cuda(void) { return PD_BACKEND::is_cuda ? 1 : 0; }
+
+void pd_options_default(pd_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof(*o));
+  o->atol = 1e-8;
+  o->rtol = 1e-6;
+  o->max_steps = 100000;
+  o->safety_factor = 0.9;
+  o->min_factor = 0.2;
+  o->max_factor = 5.0;
+  o->max_krylov = 80;
+  o->exp_tolerance = 1e-10;
+  o->norm_tolerance = 1e-10;
+}
+
+int pd_plan_create(pd_plan** out, int32_t n_qubits, int32_t batch, int32_t kind, int32_t device) {
+  return guarded([&] {
+    need(out != nullptr, "pd_plan_create: out is NULL");
+    *out = new pd_plan(n_qubits, batch, kind, device);
+  });
+}
+int pd_plan_destroy(pd_plan* p) {
+  return guarded([&] { delete p; });
+}
+int pd_plan_set_interaction(pd_plan* p, const double* pair_u_host, void* stream) {
+  return guarded([&] {
+    need(p && pair_u_host, "pd_plan_set_interaction: NULL argument");
+    p->eng.set_interaction(pair_u_host, stream);
+  });
+}
+int pd_plan_set_terms(pd_plan* p, int32_t n_samples, double dt, int32_t n_det,
+                      const uint64_t* det_masks, const double* det_values, int32_t n_amp,
+                      const uint64_t* amp_masks, const double* amp_values) {
+  return guarded([&] {
+    need(p != nullptr, "pd_plan_set_terms: plan is NULL");
+    need(n_det >= 0 && n_amp >= 0, "pd_plan_set_terms: negative term count");
+    need(n_det == 0 || (det_masks && det_values), "pd_plan_set_terms: det arrays missing");
+    need(n_amp == 0 || (amp_masks && amp_values), "pd_plan_set_terms: amp arrays missing");
+    p->eng.set_terms(n_samples, dt, n_det, det_masks, det_values, n_amp, amp_masks, amp_values);
+  });
+}
+int pd_plan_set_collapse(pd_plan* p, int32_t n_ops, const double* ops_host) {
+  return guarded([&] {
+    need(p != nullptr && n_ops >= 0 && (n_ops == 0 || ops_host), "pd_plan_set_collapse: bad argument");
+    p->eng.set_collapse(n_ops, ops_host);
+  });
+}
+int pd_hpsi(pd_plan* p, void* stream, double t, const void* in_dev, void* out_dev) {
+  return guarded([&] {
+    need(p && in_dev && out_dev, "pd_hpsi: NULL argument");
+    need(in_dev != out_dev, "pd_hpsi: in-place application is not supported");
+    p->eng.apply((pd::cplx*)out_dev, (const pd::cplx*)in_dev, t, 2, stream);
+  });
+}
+int pd_rhs(pd_plan* p, void* stream, double t, const void* in_dev, void* out_dev) {
+  return guarded([&] {
+    need(p && in_dev && out_dev, "pd_rhs: NULL argument");
+    need(in_dev != out_dev, "pd_rhs: in-place application is not supported");
+    p->eng.apply((pd::cplx*)out_dev, (const pd::cplx*)in_dev, t, 0, stream);
+  });
+}
+int pd_evolve_forward(pd_plan* p, void* stream, int32_t solver, const pd_options* opt,
+                      const void* state0_dev, const double* tsave_host, int32_t n_t,
+                      void* states_dev, pd_tape** tape_out) {
+  return guarded([&] {
+    need(p && state0_dev && tsave_host && states_dev, "pd_evolve_forward: NULL argument");
+    pd_options o;
+    if (opt) o = *opt; else pd_options_default(&o);
+    need(o.atol > 0 && o.rtol >= 0 && o.max_steps > 0, "pd_evolve_forward: bad tolerances");
+    p->eng.bk.path = o.path;
+    pd_tape* tp = tape_out ? new pd_tape() : nullptr;
+    try {
+      p->eng.forward(solver, o, (const pd::cplx*)state0_dev, tsave_host, n_t,
+                     (pd::cplx*)states_dev, tp ? &tp->tape : nullptr, stream);
+    } catch (...) {
+      delete tp;
+      throw;
+    }
+    if (tape_out) *tape_out = tp;
+  });
+}
+int pd_evolve_backward(pd_plan* p, void* stream, pd_tape* tape, const void* states_dev,
+                       const void* grad_states_dev, double* grad_det_host, double* grad_amp_host,
+                       double* grad_pair_u_host, double* grad_tsave_host, void* grad_state0_dev) {
+  return guarded([&] {
+    need(p && tape && states_dev, "pd_evolve_backward: NULL argument");
+    p->eng.backward(tape->tape, (const pd::cplx*)states_dev, (const pd::cplx*)grad_states_dev,
+                    grad_det_host, grad_amp_host, grad_pair_u_host, grad_tsave_host,
+                    (pd::cplx*)grad_state0_dev, stream);
+  });
+}
+int64_t pd_tape_n_records(const pd_tape* t) { return t ? (int64_t)t->tape.records.size() : 0; }
+int pd_tape_records(const pd_tape* t, pd_step_record* out, int64_t capacity) {
+  return guarded([&] {
+    need(t && out, "pd_tape_records: NULL argument");
+    int64_t n = std::min<int64_t>(capacity, (int64_t)t->tape.records.size());
+    std::copy(t->tape.records.begin(), t->tape.records.begin() + n, out);
+  });
+}
+int pd_tape_destroy(pd_tape* t) {
+  return guarded([&] { delete t; });
+}
+int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t,
+                   const double* obs_dev, double* out_host) {
+  return guarded([&] {
+    need(p && states_dev && obs_dev && out_host && n_t >= 1, "pd_expect_diag: bad argument");
+    p->eng.expect_diag((const pd::cplx*)states_dev, n_t, obs_dev, out_host, stream);
+  });
+}
+int64_t pd_plan_launch_count(const pd_plan* p) { return p ? p->eng.launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,166 @@
+// CUDA backend (sm_100a) for the evolution engine: memory plumbing + kernel launchers.
+//
+// Two kernel families implement every generator application:
+//   * "gather" kernels (this file): one thread per amplitude, bit-flip partners fetched
+//     through L1/L2.  Any N, any addressing, ket and density.  Correctness baseline and the
+//     path for small registers where the whole working set is cache resident.
+//   * "tiled" kernels (tiled_ket.cuh): shared-memory staged, TMA-bulk loaded tiles that close
+//     over a set of qubit bits on chip, fused with the Runge-Kutta stage combination.  The
+//     HBM-bound path for large registers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "pd_common.hpp"
+
+namespace pd {
+
+#define PD_CUDA_CHECK(expr)                                                              \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess)                                                               \
+      throw Error(PD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+  } while (0)
+
+constexpr int kThreads = 256;
+constexpr int kMaxReduceBlocks = 148 * 4;
+constexpr int kMaxR = 64;  // max doubles reduced per block in one pass
+
+struct DensityT {  // SiteOpsDensity without the by-value size limit worries: lives in a param
+  SiteOpsDensity so;
+};
+
+int launch_lincomb(const Geometry& g, cplx* out, int n_in, const cplx* const* ins, const double* w,
+                   cudaStream_t s);
+int launch_lincomb_c(size_t n, cplx* out, int m, const cplx* basis, size_t stride, const cplx* ws,
+                     cudaStream_t s);
+int launch_apply_ket(const Geometry& g, cplx* out, const cplx* in, const SiteOps& so, cudaStream_t s);
+int launch_apply_density(const Geometry& g, cplx* out, const cplx* in, const SiteOpsDensity& so,
+                         cudaStream_t s);
+int launch_build_diag(double* diag, int nq, const double* d_pair_u, cudaStream_t s);
+int launch_scaled_sumsq(const Geometry& g, double* out, const cplx* x, const cplx* xsub,
+                        const cplx* ref, double atol, double rtol, double* scratch, cudaStream_t s);
+int launch_err_sumsq(const Geometry& g, double* out, const cplx* const* k, const double* ew,
+                     const cplx* y0, const cplx* y1, double atol, double rtol, double* scratch,
+                     cudaStream_t s);
+int launch_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar,
+                const cplx* y, double* scratch, cudaStream_t s);
+int launch_re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, double* scratch,
+                  cudaStream_t s);
+int launch_pair_reduce(const Geometry& g, double* d_pair, const double* d_wacc, cudaStream_t s);
+int launch_expect_diag(const Geometry& g, const cplx* states, int n_t, const double* obs, cplx* out,
+                       double* scratch, cudaStream_t s);
+// tiled family (tiled_ket.cu); returns 0 launches if the shape is not supported
+bool tiled_ket_supported(const Geometry& g);
+int launch_tiled_stage_ket(const Geometry& g, cplx* out, cplx* comb, int n_in,
+                           const cplx* const* ins, const double* w, const SiteOps& so, cplx* tmp,
+                           cudaStream_t s);
+
+class CudaBackend {
+ public:
+  static constexpr bool is_cuda = true;
+  int device;
+  int path = 0;  // 0 auto, 1 gather, 2 tiled
+  explicit CudaBackend(int dev) : device(dev) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      throw Error(PD_ERR_CUDA, "pulser_diff_b200 needs a CUDA device (no CPU fallback): " +
+                                   std::string(cudaGetErrorString(e)));
+    if (dev < 0 || dev >= n) throw Error(PD_ERR_INVALID, "bad CUDA device ordinal");
+    PD_CUDA_CHECK(cudaSetDevice(dev));
+    PD_CUDA_CHECK(cudaMalloc(&d_pair_u_, sizeof(double) * kMaxQubits * kMaxQubits));
+  }
+  ~CudaBackend() { cudaFree(d_pair_u_); }
+  void* alloc(size_t bytes) {
+    void* p = nullptr;
+    PD_CUDA_CHECK(cudaSetDevice(device));
+    PD_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+    return p;
+  }
+  void free(void* p) { if (p) cudaFree(p); }
+  static cudaStream_t st(void* s) { return (cudaStream_t)s; }
+  void zero(void* p, size_t bytes, void* s) { PD_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, st(s))); }
+  void d2d(void* d, const void* sr, size_t b, void* s) {
+    PD_CUDA_CHECK(cudaMemcpyAsync(d, sr, b, cudaMemcpyDeviceToDevice, st(s)));
+  }
+  void d2h(void* d, const void* sr, size_t b, void* s) {
+    PD_CUDA_CHECK(cudaMemcpyAsync(d, sr, b, cudaMemcpyDeviceToHost, st(s)));
+  }
+  void sync(void* s) { PD_CUDA_CHECK(cudaStreamSynchronize(st(s))); }
+  size_t reduce_scratch_bytes(const Geometry&) { return sizeof(double) * kMaxReduceBlocks * kMaxR * 2; }
+  size_t segment_budget_bytes() {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) return (size_t)1 << 30;
+    return std::max<size_t>(fr / 3, (size_t)64 << 20);
+  }
+
+  void build_diag(double* diag, int nq, const double* pair_u_host, void* s) {
+    PD_CUDA_CHECK(cudaMemcpyAsync(d_pair_u_, pair_u_host, sizeof(double) * nq * nq,
+                                  cudaMemcpyHostToDevice, st(s)));
+    launch_build_diag(diag, nq, d_pair_u_, st(s));
+  }
+  int lincomb(const Geometry& g, cplx* out, int n_in, const cplx* const* ins, const double* w, void* s) {
+    return launch_lincomb(g, out, n_in, ins, w, st(s));
+  }
+  int lincomb_c(const Geometry& g, cplx* out, int m, const cplx* basis, size_t stride,
+                const cplx* ws_host, void* s) {
+    return launch_lincomb_c(g.dim * g.batch, out, m, basis, stride, ws_host, st(s));
+  }
+  int stage_ket(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
+                const double* w, const SiteOps& so, cplx* scratch, void* s) {
+    if (path != 1 && tiled_ket_supported(g))
+      return launch_tiled_stage_ket(g, out, comb, n_in, ins, w, so, scratch, st(s));
+    int n = 0;
+    const cplx* src = ins[0];
+    if (n_in > 1 || w[0] != 1.0) {
+      cplx* dst = comb ? comb : scratch;
+      n += launch_lincomb(g, dst, n_in, ins, w, st(s));
+      src = dst;
+    } else if (comb) {
+      d2d(comb, ins[0], sizeof(cplx) * g.dim * g.batch, s);
+    }
+    return n + launch_apply_ket(g, out, src, so, st(s));
+  }
+  int stage_density(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
+                    const double* w, const SiteOpsDensity& so, cplx* scratch, void* s) {
+    int n = 0;
+    const cplx* src = ins[0];
+    if (n_in > 1 || w[0] != 1.0) {
+      cplx* dst = comb ? comb : scratch;
+      n += launch_lincomb(g, dst, n_in, ins, w, st(s));
+      src = dst;
+    } else if (comb) {
+      d2d(comb, ins[0], sizeof(cplx) * g.dim * g.batch, s);
+    }
+    return n + launch_apply_density(g, out, src, so, st(s));
+  }
+  int scaled_sumsq(const Geometry& g, double* out, const cplx* x, const cplx* xsub, const cplx* ref,
+                   double atol, double rtol, double* scratch, void* s) {
+    return launch_scaled_sumsq(g, out, x, xsub, ref, atol, rtol, scratch, st(s));
+  }
+  int err_sumsq(const Geometry& g, double* out, const cplx* const* k, const double* ew,
+                const cplx* y0, const cplx* y1, double atol, double rtol, double* scratch, void* s) {
+    return launch_err_sumsq(g, out, k, ew, y0, y1, atol, rtol, scratch, st(s));
+  }
+  int corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar,
+           const cplx* y, double* scratch, void* s) {
+    return launch_corr(g, d_corr, d_wacc, wscale, kbar, y, scratch, st(s));
+  }
+  int re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, double* scratch, void* s) {
+    return launch_re_dot(g, out, a, b, scratch, st(s));
+  }
+  int pair_reduce(const Geometry& g, double* d_pair, const double* d_wacc, void* s) {
+    return launch_pair_reduce(g, d_pair, d_wacc, st(s));
+  }
+  int expect_diag(const Geometry& g, const cplx* states, int n_t, const double* obs, cplx* out,
+                  double* scratch, void* s) {
+    return launch_expect_diag(g, states, n_t, obs, out, scratch, st(s));
+  }
+
+ private:
+  double* d_pair_u_ = nullptr;
+};
+
+}  // namespace pd

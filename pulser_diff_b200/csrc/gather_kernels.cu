@@ -1,0 +1,479 @@
+// "Gather" kernel family: one thread per amplitude, bit-flip partners through L1/L2.
+// See cuda_backend.cuh for where this sits.  Everything here is the matrix-free form of
+//   H(t) psi = 2*int_mat psi + sum(det terms) + sum(amp terms)      (reference hamiltonian.py:536-544)
+// and of the Lindblad right-hand side, written as
+//   out[idx] = kappa*Dstat(idx)*v[idx] + sum_q sum_p' T_q[p(idx)][p'] v[idx with site q := p'].
+#include "cuda_backend.cuh"
+
+namespace pd {
+
+namespace {
+
+struct PtrW {
+  const cplx* p[8];
+  double w[8];
+  int n;
+};
+struct CW {
+  cplx w[128];
+  int m;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Deterministic block reduction of R per-thread accumulators -> partial[blockIdx][R]
+template <int R>
+__device__ __forceinline__ void block_reduce_write(double (&acc)[R], double* partial) {
+  __shared__ double sh[kThreads / 32][R];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    double v = warp_sum(acc[r]);
+    if (lane == 0) sh[warp][r] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < R) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; ++w) s += sh[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * R + threadIdx.x] = s;
+  }
+}
+
+// out[r] (= or +=) scale * sum_b partial[b][r]; one warp per r, fixed order
+__global__ void k_reduce_final(const double* __restrict__ partial, int nblocks, int R, int pstride,
+                               double* __restrict__ out, int out_stride, double scale, int accumulate) {
+  int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += partial[(size_t)b * pstride + r];
+  s = warp_sum(s);
+  if (lane == 0) {
+    if (accumulate) out[(size_t)r * out_stride] += scale * s;
+    else out[(size_t)r * out_stride] = scale * s;
+  }
+}
+
+int finalize(const double* partial, int nblocks, int R, double* out, int out_stride, double scale,
+             int accumulate, cudaStream_t s, int pstride = 0) {
+  int wpb = 4;
+  k_reduce_final<<<(R + wpb - 1) / wpb, wpb * 32, 0, s>>>(partial, nblocks, R, pstride ? pstride : R,
+                                                         out, out_stride, scale, accumulate);
+  return 1;
+}
+
+int grid_for(size_t n, int per_thread = 1) {
+  size_t b = (n + (size_t)kThreads * per_thread - 1) / ((size_t)kThreads * per_thread);
+  return (int)std::min<size_t>(std::max<size_t>(b, 1), (size_t)148 * 16);
+}
+int rgrid_for(size_t n, int R, int ny) {
+  size_t b = (n + kThreads - 1) / kThreads;
+  size_t cap = (size_t)kMaxReduceBlocks * kMaxR * 2 / ((size_t)R * ny);
+  cap = std::min<size_t>(cap, kMaxReduceBlocks);
+  return (int)std::max<size_t>(1, std::min(b, cap));
+}
+
+__global__ void __launch_bounds__(kThreads) k_lincomb(cplx* out, PtrW a, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    double re = 0.0, im = 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (j < a.n) {
+        cplx v = a.p[j][i];
+        re = fma(a.w[j], v.re, re);
+        im = fma(a.w[j], v.im, im);
+      }
+    out[i] = {re, im};
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_lincomb_c(cplx* out, const cplx* basis, size_t stride_v,
+                                                        const __grid_constant__ CW cw, size_t n) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    cplx acc{0.0, 0.0};
+    for (int j = 0; j < cw.m; ++j) fma_acc(acc, cw.w[j], basis[(size_t)j * stride_v + i]);
+    out[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_apply_ket(cplx* __restrict__ out, const cplx* __restrict__ in, const double* __restrict__ diag,
+            const __grid_constant__ SiteOps so, int nq, size_t dim, size_t total) {
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    size_t s = idx & (dim - 1);
+    cplx v = in[idx];
+    double dg = diag[s];
+    cplx dsum{so.kappa.re * dg, so.kappa.im * dg};
+    cplx acc{0.0, 0.0};
+    for (int q = 0; q < nq; ++q) {
+      size_t m = (size_t)1 << (nq - 1 - q);
+      bool a = (s & m) != 0;
+      cplx td = a ? so.T[q * 4 + 3] : so.T[q * 4 + 0];
+      cplx to = a ? so.T[q * 4 + 2] : so.T[q * 4 + 1];
+      dsum = dsum + td;
+      fma_acc(acc, to, in[idx ^ m]);
+    }
+    fma_acc(acc, dsum, v);
+    out[idx] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_apply_density(cplx* __restrict__ out, const cplx* __restrict__ in, const double* __restrict__ diag,
+                const __grid_constant__ SiteOpsDensity so, int nq, size_t total, int need_both) {
+  __shared__ cplx T[kMaxSitesDensity * 16];
+  for (int i = threadIdx.x; i < nq * 16; i += blockDim.x) T[i] = so.T[i];
+  __syncthreads();
+  size_t S = (size_t)1 << nq, dim = S * S;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    size_t e = idx & (dim - 1);
+    size_t r = e >> nq, c = e & (S - 1);
+    cplx v = in[idx];
+    double dg = diag[r] - diag[c];
+    cplx dsum{so.kappa.re * dg, so.kappa.im * dg};
+    cplx acc{0.0, 0.0};
+    for (int q = 0; q < nq; ++q) {
+      size_t mc = (size_t)1 << (nq - 1 - q), mr = mc << nq;
+      int p = ((e & mr) ? 2 : 0) | ((e & mc) ? 1 : 0);
+      const cplx* Tp = &T[q * 16 + p * 4];
+      dsum = dsum + Tp[p];
+      fma_acc(acc, Tp[p ^ 2], in[idx ^ mr]);
+      fma_acc(acc, Tp[p ^ 1], in[idx ^ mc]);
+      if (need_both) fma_acc(acc, Tp[p ^ 3], in[idx ^ mr ^ mc]);
+    }
+    fma_acc(acc, dsum, v);
+    out[idx] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) k_build_diag(double* diag, int nq, const double* __restrict__ u) {
+  __shared__ double su[kMaxQubits * kMaxQubits];
+  for (int i = threadIdx.x; i < nq * nq; i += blockDim.x) su[i] = u[i];
+  __syncthreads();
+  size_t dim = (size_t)1 << nq;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < dim; s += stride) {
+    double acc = 0.0;
+    for (int i = 0; i < nq; ++i) {
+      if (s >> (nq - 1 - i) & 1) continue;  // bit 1 = ground: r_i = 0
+      for (int j = i + 1; j < nq; ++j)
+        if (!(s >> (nq - 1 - j) & 1)) acc += su[i * nq + j];
+    }
+    diag[s] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_scaled_sumsq(const cplx* __restrict__ x, const cplx* __restrict__ xsub, const cplx* __restrict__ ref,
+               double atol, double rtol, size_t dim, double* partial) {
+  size_t base = (size_t)blockIdx.y * dim;
+  double acc[1] = {0.0};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+    cplx v = x[base + i];
+    if (xsub) v = v - xsub[base + i];
+    cplx rf = ref[base + i];
+    double sc = atol + rtol * hypot(rf.re, rf.im);
+    double a = v.re / sc, b = v.im / sc;
+    acc[0] += a * a + b * b;
+  }
+  block_reduce_write<1>(acc, partial + (size_t)blockIdx.y * gridDim.x);
+}
+
+struct KPtr7 {
+  const cplx* k[7];
+  double ew[7];
+};
+__global__ void __launch_bounds__(kThreads)
+k_err_sumsq(KPtr7 kp, const cplx* __restrict__ y0, const cplx* __restrict__ y1, double atol,
+            double rtol, size_t dim, double* partial) {
+  size_t base = (size_t)blockIdx.y * dim;
+  double acc[1] = {0.0};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += stride) {
+    double er = 0.0, ei = 0.0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+      if (kp.ew[j] != 0.0) {
+        cplx v = kp.k[j][base + i];
+        er = fma(kp.ew[j], v.re, er);
+        ei = fma(kp.ew[j], v.im, ei);
+      }
+    cplx a = y0[base + i], b = y1[base + i];
+    double sc = atol + rtol * fmax(hypot(a.re, a.im), hypot(b.re, b.im));
+    er /= sc; ei /= sc;
+    acc[0] += er * er + ei * ei;
+  }
+  block_reduce_write<1>(acc, partial + (size_t)blockIdx.y * gridDim.x);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_re_dot(const cplx* __restrict__ a, const cplx* __restrict__ b, size_t n, double* partial) {
+  double acc[1] = {0.0};
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    cplx u = a[i], v = b[i];
+    acc[0] += u.re * v.re + u.im * v.im;
+  }
+  block_reduce_write<1>(acc, partial);
+}
+
+// Site correlations for QC ket sites per blockIdx.y:
+//   C_q[a][a'] = sum_{b, s: bit_q(s)=a} conj(kbar[b,s]) * y[b, s with bit_q := a']
+constexpr int kQC = 4;
+__global__ void __launch_bounds__(kThreads)
+k_corr_ket(const cplx* __restrict__ kbar, const cplx* __restrict__ y, int nq, size_t dim, int batch,
+           double* partial, double* wacc, double wscale) {
+  int q0 = blockIdx.y * kQC;
+  double acc[kQC * 8];
+#pragma unroll
+  for (int i = 0; i < kQC * 8; ++i) acc[i] = 0.0;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x; s < dim; s += stride) {
+    double wsum = 0.0;
+    for (int b = 0; b < batch; ++b) {
+      size_t idx = (size_t)b * dim + s;
+      cplx kb = conj(kbar[idx]);
+      cplx ys = y[idx];
+      cplx self = kb * ys;
+      wsum += self.im;
+#pragma unroll
+      for (int j = 0; j < kQC; ++j) {
+        int q = q0 + j;
+        if (q < nq) {
+          size_t m = (size_t)1 << (nq - 1 - q);
+          bool a = (s & m) != 0;
+          cplx fl = kb * y[idx ^ m];
+          // T layout [a][a']: slot 0 = C[0][0], 1 = C[0][1], 2 = C[1][0], 3 = C[1][1]
+          acc[j * 8 + 0] += a ? 0.0 : self.re;
+          acc[j * 8 + 1] += a ? 0.0 : self.im;
+          acc[j * 8 + 2] += a ? 0.0 : fl.re;
+          acc[j * 8 + 3] += a ? 0.0 : fl.im;
+          acc[j * 8 + 4] += a ? fl.re : 0.0;
+          acc[j * 8 + 5] += a ? fl.im : 0.0;
+          acc[j * 8 + 6] += a ? self.re : 0.0;
+          acc[j * 8 + 7] += a ? self.im : 0.0;
+        }
+      }
+    }
+    if (wacc && blockIdx.y == 0) wacc[s] += wscale * wsum;
+  }
+  block_reduce_write<kQC * 8>(acc, partial + (size_t)blockIdx.y * gridDim.x * (kQC * 8));
+}
+
+// One density site per blockIdx.y: C_q[p][p'] = sum_{idx: p(idx)=p} conj(kbar) * y[idx with site := p']
+__global__ void __launch_bounds__(kThreads)
+k_corr_density(const cplx* __restrict__ kbar, const cplx* __restrict__ y, int nq, size_t total,
+               double* partial, double* wacc, double wscale) {
+  int q = blockIdx.y;
+  size_t S = (size_t)1 << nq, dim = S * S;
+  size_t mc = (size_t)1 << (nq - 1 - q), mr = mc << nq;
+  double acc[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.0;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    size_t e = idx & (dim - 1);
+    int p = ((e & mr) ? 2 : 0) | ((e & mc) ? 1 : 0);
+    cplx kb = conj(kbar[idx]);
+    cplx self = kb * y[idx], frow = kb * y[idx ^ mr], fcol = kb * y[idx ^ mc],
+         fboth = kb * y[idx ^ mr ^ mc];
+#pragma unroll
+    for (int pr = 0; pr < 4; ++pr)
+      if (pr == p) {
+        acc[(pr * 4 + pr) * 2 + 0] += self.re;        acc[(pr * 4 + pr) * 2 + 1] += self.im;
+        acc[(pr * 4 + (pr ^ 2)) * 2 + 0] += frow.re;  acc[(pr * 4 + (pr ^ 2)) * 2 + 1] += frow.im;
+        acc[(pr * 4 + (pr ^ 1)) * 2 + 0] += fcol.re;  acc[(pr * 4 + (pr ^ 1)) * 2 + 1] += fcol.im;
+        acc[(pr * 4 + (pr ^ 3)) * 2 + 0] += fboth.re; acc[(pr * 4 + (pr ^ 3)) * 2 + 1] += fboth.im;
+      }
+    if (wacc && q == 0) {
+      double w = wscale * self.im;
+      atomicAdd(&wacc[e >> nq], w);
+      atomicAdd(&wacc[e & (S - 1)], -w);
+    }
+  }
+  block_reduce_write<32>(acc, partial + (size_t)blockIdx.y * gridDim.x * 32);
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_pair_reduce(const double* __restrict__ wacc, int nq, double* out) {
+  int i = blockIdx.x / nq, j = blockIdx.x % nq;
+  __shared__ double sh[kThreads / 32];
+  double acc = 0.0;
+  if (i < j) {
+    size_t dim = (size_t)1 << nq;
+    size_t mi = (size_t)1 << (nq - 1 - i), mj = (size_t)1 << (nq - 1 - j);
+    for (size_t s = threadIdx.x; s < dim; s += blockDim.x)
+      if (!(s & mi) && !(s & mj)) acc += wacc[s];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kThreads / 32; ++w) s += sh[w];
+    out[blockIdx.x] = s;
+  }
+}
+
+// blockIdx.y = time index.  ket: sum_{b,s} obs[s] |psi|^2.  density: sum_r obs[r] rho[r][r].
+__global__ void __launch_bounds__(kThreads)
+k_expect_diag(const cplx* __restrict__ states, const double* __restrict__ obs, int kind, int nq,
+              size_t dim, int batch, double* partial) {
+  double acc[2] = {0.0, 0.0};
+  size_t base = (size_t)blockIdx.y * dim * batch;
+  size_t S = (size_t)1 << nq;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  if (kind == PD_KET) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < dim * batch; i += stride) {
+      cplx v = states[base + i];
+      acc[0] += obs[i & (dim - 1)] * (v.re * v.re + v.im * v.im);
+    }
+  } else {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < S * batch; i += stride) {
+      size_t b = i >> nq, r = i & (S - 1);
+      cplx v = states[base + b * dim + r * S + r];
+      acc[0] += obs[r] * v.re;
+      acc[1] += obs[r] * v.im;
+    }
+  }
+  block_reduce_write<2>(acc, partial + (size_t)blockIdx.y * gridDim.x * 2);
+}
+
+}  // namespace
+
+int launch_lincomb(const Geometry& g, cplx* out, int n_in, const cplx* const* ins, const double* w,
+                   cudaStream_t s) {
+  if (n_in < 1 || n_in > 8) throw Error(PD_ERR_INVALID, "lincomb takes 1..8 inputs");
+  PtrW a{};
+  a.n = n_in;
+  for (int i = 0; i < n_in; ++i) { a.p[i] = ins[i]; a.w[i] = w[i]; }
+  size_t n = g.dim * g.batch;
+  k_lincomb<<<grid_for(n, 2), kThreads, 0, s>>>(out, a, n);
+  return 1;
+}
+
+int launch_lincomb_c(size_t n, cplx* out, int m, const cplx* basis, size_t stride, const cplx* ws,
+                     cudaStream_t s) {
+  if (m < 1 || m > 128) throw Error(PD_ERR_INVALID, "lincomb_c takes 1..128 vectors");
+  CW cw{};
+  cw.m = m;
+  for (int i = 0; i < m; ++i) cw.w[i] = ws[i];
+  k_lincomb_c<<<grid_for(n, 2), kThreads, 0, s>>>(out, basis, stride, cw, n);
+  return 1;
+}
+
+int launch_apply_ket(const Geometry& g, cplx* out, const cplx* in, const SiteOps& so, cudaStream_t s) {
+  size_t total = g.dim * g.batch;
+  k_apply_ket<<<grid_for(total), kThreads, 0, s>>>(out, in, g.diag, so, g.nq, g.dim, total);
+  return 1;
+}
+
+int launch_apply_density(const Geometry& g, cplx* out, const cplx* in, const SiteOpsDensity& so,
+                         cudaStream_t s) {
+  size_t total = g.dim * g.batch;
+  int need_both = 0;
+  for (int q = 0; q < so.nsites; ++q)
+    for (int p = 0; p < 4; ++p)
+      if (so.nzmask[q] >> (p * 4 + (p ^ 3)) & 1) need_both = 1;
+  k_apply_density<<<grid_for(total), kThreads, 0, s>>>(out, in, g.diag, so, g.nq, total, need_both);
+  return 1;
+}
+
+int launch_build_diag(double* diag, int nq, const double* d_pair_u, cudaStream_t s) {
+  k_build_diag<<<grid_for((size_t)1 << nq), kThreads, 0, s>>>(diag, nq, d_pair_u);
+  return 1;
+}
+
+int launch_scaled_sumsq(const Geometry& g, double* out, const cplx* x, const cplx* xsub,
+                        const cplx* ref, double atol, double rtol, double* scratch, cudaStream_t s) {
+  int gx = rgrid_for(g.dim, 1, g.batch);
+  k_scaled_sumsq<<<dim3(gx, g.batch), kThreads, 0, s>>>(x, xsub, ref, atol, rtol, g.dim, scratch);
+  int n = 1;
+  for (int b = 0; b < g.batch; ++b) n += finalize(scratch + (size_t)b * gx, gx, 1, out + b, 1, 1.0, 0, s);
+  return n;
+}
+
+int launch_err_sumsq(const Geometry& g, double* out, const cplx* const* k, const double* ew,
+                     const cplx* y0, const cplx* y1, double atol, double rtol, double* scratch,
+                     cudaStream_t s) {
+  KPtr7 kp{};
+  for (int j = 0; j < 7; ++j) { kp.k[j] = k[j]; kp.ew[j] = ew[j]; }
+  int gx = rgrid_for(g.dim, 1, g.batch);
+  k_err_sumsq<<<dim3(gx, g.batch), kThreads, 0, s>>>(kp, y0, y1, atol, rtol, g.dim, scratch);
+  int n = 1;
+  for (int b = 0; b < g.batch; ++b) n += finalize(scratch + (size_t)b * gx, gx, 1, out + b, 1, 1.0, 0, s);
+  return n;
+}
+
+int launch_re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, double* scratch,
+                  cudaStream_t s) {
+  size_t n = g.dim * g.batch;
+  int gx = rgrid_for(n, 1, 1);
+  k_re_dot<<<gx, kThreads, 0, s>>>(a, b, n, scratch);
+  return 1 + finalize(scratch, gx, 1, out, 1, 1.0, 0, s);
+}
+
+int launch_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar,
+                const cplx* y, double* scratch, cudaStream_t s) {
+  int n = 0;
+  if (g.kind == PD_KET) {
+    int ny = (g.nq + kQC - 1) / kQC;
+    if (!d_corr) ny = 1;
+    int gx = rgrid_for(g.dim, kQC * 8, ny);
+    k_corr_ket<<<dim3(gx, ny), kThreads, 0, s>>>(kbar, y, g.nq, g.dim, g.batch, scratch, d_wacc, wscale);
+    ++n;
+    if (d_corr)
+      for (int c = 0; c < ny; ++c) {
+        int sites = std::min(kQC, g.nq - c * kQC);
+        n += finalize(scratch + (size_t)c * gx * (kQC * 8), gx, sites * 8,
+                      (double*)(d_corr + (size_t)c * kQC * 4), 1, 1.0, 0, s, kQC * 8);
+      }
+  } else {
+    int ny = d_corr ? g.nq : 1;
+    size_t total = g.dim * g.batch;
+    int gx = rgrid_for(total, 32, ny);
+    k_corr_density<<<dim3(gx, ny), kThreads, 0, s>>>(kbar, y, g.nq, total, scratch, d_wacc, wscale);
+    ++n;
+    if (d_corr)
+      for (int q = 0; q < ny; ++q)
+        n += finalize(scratch + (size_t)q * gx * 32, gx, 32, (double*)(d_corr + (size_t)q * 16), 1,
+                      1.0, 0, s);
+  }
+  return n;
+}
+
+int launch_pair_reduce(const Geometry& g, double* d_pair, const double* d_wacc, cudaStream_t s) {
+  k_pair_reduce<<<g.nq * g.nq, kThreads, 0, s>>>(d_wacc, g.nq, d_pair);
+  return 1;
+}
+
+int launch_expect_diag(const Geometry& g, const cplx* states, int n_t, const double* obs, cplx* out,
+                       double* scratch, cudaStream_t s) {
+  size_t work = g.kind == PD_KET ? g.dim * g.batch : ((size_t)1 << g.nq) * g.batch;
+  int n = 0;
+  // time indices in slabs so the partial buffer stays within the reduce scratch
+  int slab = std::max(1, std::min(n_t, kMaxReduceBlocks * kMaxR / (2 * 64)));
+  for (int t0 = 0; t0 < n_t; t0 += slab) {
+    int nt = std::min(slab, n_t - t0);
+    int gx = rgrid_for(work, 2, nt);
+    gx = std::min(gx, 64);
+    k_expect_diag<<<dim3(gx, nt), kThreads, 0, s>>>(states + (size_t)t0 * g.dim * g.batch, obs, g.kind,
+                                                    g.nq, g.dim, g.batch, scratch);
+    ++n;
+    for (int t = 0; t < nt; ++t)
+      n += finalize(scratch + (size_t)t * gx * 2, gx, 2, (double*)(out + t0 + t), 1, 1.0, 0, s);
+  }
+  return n;
+}
+
+}  // namespace pd

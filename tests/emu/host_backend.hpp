@@ -1,0 +1,211 @@
+// TEST INFRASTRUCTURE ONLY: a plain-C++ stand-in for the CUDA kernels so the host-side
+// orchestration of pulser_diff_b200/csrc/engine.hpp (step controller, tape, discrete adjoint,
+// gradient distribution, Krylov) and the Python layer above the C ABI can be exercised on a
+// box without a GPU.  It is compiled into tests/emu/libpd_emu.so, which the product package
+// never loads on its own (pulser_diff_b200/_cabi.py only accepts it when a test passes the
+// path explicitly).  "Device" pointers are host pointers here; streams are ignored.
+#pragma once
+#include <cstdlib>
+
+#include "../../pulser_diff_b200/csrc/pd_common.hpp"
+
+namespace pd {
+
+class HostBackend {
+ public:
+  static constexpr bool is_cuda = false;
+  int path = 0;
+  explicit HostBackend(int) {}
+  void* alloc(size_t bytes) {
+    void* p = nullptr;
+    if (posix_memalign(&p, 64, std::max<size_t>(bytes, 64)) != 0) throw Error(PD_ERR_STATE, "alloc");
+    return p;
+  }
+  void free(void* p) { std::free(p); }
+  void zero(void* p, size_t b, void*) { std::memset(p, 0, b); }
+  void d2d(void* d, const void* s, size_t b, void*) { std::memmove(d, s, b); }
+  void d2h(void* d, const void* s, size_t b, void*) { std::memmove(d, s, b); }
+  void sync(void*) {}
+  size_t reduce_scratch_bytes(const Geometry&) { return 64; }
+  size_t segment_budget_bytes() { return segment_budget; }
+  size_t segment_budget = (size_t)1 << 28;
+
+  void build_diag(double* diag, int nq, const double* u, void*) {
+    size_t dim = (size_t)1 << nq;
+    for (size_t s = 0; s < dim; ++s) {
+      double acc = 0.0;
+      for (int i = 0; i < nq; ++i) {
+        if (s >> (nq - 1 - i) & 1) continue;
+        for (int j = i + 1; j < nq; ++j)
+          if (!(s >> (nq - 1 - j) & 1)) acc += u[i * nq + j];
+      }
+      diag[s] = acc;
+    }
+  }
+  int lincomb(const Geometry& g, cplx* out, int n_in, const cplx* const* ins, const double* w, void*) {
+    size_t n = g.dim * g.batch;
+    for (size_t i = 0; i < n; ++i) {
+      double re = 0, im = 0;
+      for (int j = 0; j < n_in; ++j) { re += w[j] * ins[j][i].re; im += w[j] * ins[j][i].im; }
+      out[i] = {re, im};
+    }
+    return 1;
+  }
+  int lincomb_c(const Geometry& g, cplx* out, int m, const cplx* basis, size_t stride, const cplx* ws, void*) {
+    size_t n = g.dim * g.batch;
+    for (size_t i = 0; i < n; ++i) {
+      cplx acc{0, 0};
+      for (int j = 0; j < m; ++j) acc = acc + ws[j] * basis[(size_t)j * stride + i];
+      out[i] = acc;
+    }
+    return 1;
+  }
+  const cplx* combine(const Geometry& g, cplx* comb, int n_in, const cplx* const* ins, const double* w,
+                      cplx* scratch) {
+    if (n_in > 1 || w[0] != 1.0) {
+      cplx* dst = comb ? comb : scratch;
+      lincomb(g, dst, n_in, ins, w, nullptr);
+      return dst;
+    }
+    if (comb) std::memmove(comb, ins[0], sizeof(cplx) * g.dim * g.batch);
+    return ins[0];
+  }
+  int stage_ket(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
+                const double* w, const SiteOps& so, cplx* scratch, void*) {
+    const cplx* in = combine(g, comb, n_in, ins, w, scratch);
+    int nq = g.nq;
+    for (size_t idx = 0; idx < g.dim * g.batch; ++idx) {
+      size_t s = idx & (g.dim - 1);
+      cplx acc = (so.kappa * cplx{g.diag[s], 0}) * in[idx];
+      for (int q = 0; q < nq; ++q) {
+        size_t m = (size_t)1 << (nq - 1 - q);
+        int a = (s & m) ? 1 : 0;
+        acc = acc + so.T[q * 4 + a * 2 + a] * in[idx] + so.T[q * 4 + a * 2 + (1 - a)] * in[idx ^ m];
+      }
+      out[idx] = acc;
+    }
+    return 1;
+  }
+  int stage_density(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
+                    const double* w, const SiteOpsDensity& so, cplx* scratch, void*) {
+    const cplx* in = combine(g, comb, n_in, ins, w, scratch);
+    int nq = g.nq;
+    size_t S = (size_t)1 << nq;
+    for (size_t idx = 0; idx < g.dim * g.batch; ++idx) {
+      size_t e = idx & (g.dim - 1), r = e >> nq, c = e & (S - 1);
+      cplx acc = (so.kappa * cplx{g.diag[r] - g.diag[c], 0}) * in[idx];
+      for (int q = 0; q < nq; ++q) {
+        size_t mc = (size_t)1 << (nq - 1 - q), mr = mc << nq;
+        int p = ((e & mr) ? 2 : 0) | ((e & mc) ? 1 : 0);
+        const cplx* T = &so.T[q * 16 + p * 4];
+        acc = acc + T[p] * in[idx] + T[p ^ 2] * in[idx ^ mr] + T[p ^ 1] * in[idx ^ mc] +
+              T[p ^ 3] * in[idx ^ mr ^ mc];
+      }
+      out[idx] = acc;
+    }
+    return 1;
+  }
+  int scaled_sumsq(const Geometry& g, double* out, const cplx* x, const cplx* xsub, const cplx* ref,
+                   double atol, double rtol, double*, void*) {
+    for (int b = 0; b < g.batch; ++b) {
+      double acc = 0;
+      for (size_t i = 0; i < g.dim; ++i) {
+        size_t k = (size_t)b * g.dim + i;
+        cplx v = xsub ? x[k] - xsub[k] : x[k];
+        double sc = atol + rtol * std::hypot(ref[k].re, ref[k].im);
+        acc += (v.re / sc) * (v.re / sc) + (v.im / sc) * (v.im / sc);
+      }
+      out[b] = acc;
+    }
+    return 1;
+  }
+  int err_sumsq(const Geometry& g, double* out, const cplx* const* k, const double* ew,
+                const cplx* y0, const cplx* y1, double atol, double rtol, double*, void*) {
+    for (int b = 0; b < g.batch; ++b) {
+      double acc = 0;
+      for (size_t i = 0; i < g.dim; ++i) {
+        size_t x = (size_t)b * g.dim + i;
+        double er = 0, ei = 0;
+        for (int j = 0; j < 7; ++j)
+          if (ew[j] != 0.0) { er += ew[j] * k[j][x].re; ei += ew[j] * k[j][x].im; }
+        double sc = atol + rtol * std::max(std::hypot(y0[x].re, y0[x].im), std::hypot(y1[x].re, y1[x].im));
+        acc += (er / sc) * (er / sc) + (ei / sc) * (ei / sc);
+      }
+      out[b] = acc;
+    }
+    return 1;
+  }
+  int corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar,
+           const cplx* y, double*, void*) {
+    int nq = g.nq;
+    size_t S = (size_t)1 << nq;
+    int per = g.kind == PD_KET ? 4 : 16;
+    if (d_corr) for (int i = 0; i < nq * per; ++i) d_corr[i] = {0, 0};
+    for (size_t idx = 0; idx < g.dim * g.batch; ++idx) {
+      size_t e = idx & (g.dim - 1);
+      cplx kb = conj(kbar[idx]);
+      cplx self = kb * y[idx];
+      if (d_wacc) {
+        if (g.kind == PD_KET) d_wacc[e] += wscale * self.im;
+        else { d_wacc[e >> nq] += wscale * self.im; d_wacc[e & (S - 1)] -= wscale * self.im; }
+      }
+      if (!d_corr) continue;
+      for (int q = 0; q < nq; ++q) {
+        if (g.kind == PD_KET) {
+          size_t m = (size_t)1 << (nq - 1 - q);
+          int a = (e & m) ? 1 : 0;
+          d_corr[q * 4 + a * 2 + a] = d_corr[q * 4 + a * 2 + a] + self;
+          d_corr[q * 4 + a * 2 + (1 - a)] = d_corr[q * 4 + a * 2 + (1 - a)] + kb * y[idx ^ m];
+        } else {
+          size_t mc = (size_t)1 << (nq - 1 - q), mr = mc << nq;
+          int p = ((e & mr) ? 2 : 0) | ((e & mc) ? 1 : 0);
+          cplx* C = &d_corr[q * 16 + p * 4];
+          C[p] = C[p] + self;
+          C[p ^ 2] = C[p ^ 2] + kb * y[idx ^ mr];
+          C[p ^ 1] = C[p ^ 1] + kb * y[idx ^ mc];
+          C[p ^ 3] = C[p ^ 3] + kb * y[idx ^ mr ^ mc];
+        }
+      }
+    }
+    return 1;
+  }
+  int re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, double*, void*) {
+    double acc = 0;
+    for (size_t i = 0; i < g.dim * g.batch; ++i) acc += a[i].re * b[i].re + a[i].im * b[i].im;
+    *out = acc;
+    return 1;
+  }
+  int pair_reduce(const Geometry& g, double* d_pair, const double* d_wacc, void*) {
+    int nq = g.nq;
+    size_t S = (size_t)1 << nq;
+    for (int i = 0; i < nq; ++i)
+      for (int j = 0; j < nq; ++j) {
+        double acc = 0;
+        if (i < j)
+          for (size_t s = 0; s < S; ++s)
+            if (!(s >> (nq - 1 - i) & 1) && !(s >> (nq - 1 - j) & 1)) acc += d_wacc[s];
+        d_pair[i * nq + j] = acc;
+      }
+    return 1;
+  }
+  int expect_diag(const Geometry& g, const cplx* states, int n_t, const double* obs, cplx* out,
+                  double*, void*) {
+    size_t S = (size_t)1 << g.nq;
+    for (int t = 0; t < n_t; ++t) {
+      cplx acc{0, 0};
+      const cplx* st = states + (size_t)t * g.dim * g.batch;
+      for (int b = 0; b < g.batch; ++b)
+        if (g.kind == PD_KET)
+          for (size_t s = 0; s < g.dim; ++s) {
+            cplx v = st[(size_t)b * g.dim + s];
+            acc.re += obs[s] * (v.re * v.re + v.im * v.im);
+          }
+        else
+          for (size_t r = 0; r < S; ++r) acc = acc + obs[r] * st[(size_t)b * g.dim + r * S + r];
+      out[t] = acc;
+    }
+    return 1;
+  }
+};
+
+}  // namespace pd
