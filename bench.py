@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""Benchmark of the pulser-diff evolution hot path on B200 (driver contract: see README/DESIGN).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm
+    python bench.py --impl reference --gpus N --steps K ...   # reference CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): 12-atom 1-D chain, antiferromagnetic state preparation with
+parametrised Omega(t)/delta(t) (docs/state_preparation.ipynb parametrisation: 30+30 control
+points through interpolate_sine, 1100 ns, sampling_rate 0.05, DP5_SE), loss built from
+<n_i n_{i+1}> and <n_i>, gradient w.r.t. the 60 parameters.  One bench "step" = one forward +
+gradient pass.  Metric = DP5 evolution steps per second over forward+gradient.
+
+* ``value``  : passes with the register state and pulse coefficients already on the device.
+* ``e2e``    : the same pass through ``TorchEmulator.run`` from HOST tensors, loss and gradients
+               read back to the host, every step.
+* ``roofline``: the HBM-bound regime of the same kernels -- one fused DP5 step at N = 26
+               (north_star's target) timed with CUDA events inside the C ABI on the launching
+               stream; algorithmic bytes 576 B x 2^N per step, 40 B x 2^N per H.psi
+               (SURVEY.md 8d).  ``roofline_workload`` is the same figure for the N = 12 workload
+               itself (64 KiB state: launch/latency bound, reported for completeness).
+* ``cpu_baseline``: the oracle (restated reference CPU path: sparse-COO H(t) re-assembly, DP5,
+               tape autograd) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_QUBITS, DURATION, N_PARAM, GAMMA, RATE = 12, 1100, 30, 0.02, 0.05
+MAX_AMP, MAX_DET, SPACING, C6 = 12, 6, 7.0, 865723.02
+
+
+# ------------------------------------------------------------------------------------------------
+def workload_params(seed: int):
+    g = torch.Generator().manual_seed(seed)
+    ta = ((2 * torch.rand(N_PARAM, dtype=torch.float64, generator=g) - 1) * 50).requires_grad_(True)
+    td = ((2 * torch.rand(N_PARAM, dtype=torch.float64, generator=g) - 1) * 50).requires_grad_(True)
+    return ta, td
+
+
+def pulse_samples(ta, td, interp):
+    amp = interp @ (MAX_AMP * torch.sigmoid(GAMMA * ta))
+    det = interp @ (MAX_DET * torch.tanh(GAMMA * td))
+    return amp, det, torch.zeros(DURATION, dtype=torch.float64)
+
+
+def chain_coords(n):
+    return torch.stack([torch.arange(n, dtype=torch.float64) * SPACING,
+                        torch.zeros(n, dtype=torch.float64)], dim=1)
+
+
+def loss_diag(n, device):
+    from pulser_diff_b200.utils import occupation_diag
+    d = torch.zeros(2 ** n, dtype=torch.float64, device=device)
+    for i in range(n - 1):
+        d = d + occupation_diag(n, [i, i + 1], device)
+    for i in range(0, n, 2):
+        d = d - occupation_diag(n, [i], device)
+    return d
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def summary(self):
+        self._stop.set()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import pulser_diff_b200 as pdb
+    from pulser_diff_b200 import _cabi, ops
+    from pulser_diff_b200.samples import ChannelSamples, SequenceSamples
+    from pulser_diff_b200.utils import interpolate_sine
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    interp = interpolate_sine(N_PARAM, DURATION).to(torch.float64)
+    coords = chain_coords(N_QUBITS)
+    register = {f"q{i}": coords[i] for i in range(N_QUBITS)}
+    device_spec = pdb.DeviceSpec(C6)
+    diag_dev = loss_diag(N_QUBITS, dev)
+    ta, td = workload_params(args.seed + rank)           # one parameter set per rank (weak scaling)
+    plan = ops.get_plan(N_QUBITS, 1, _cabi.PD_KET, dev)
+
+    def e2e_pass():
+        """Public API from host tensors: samples -> TorchEmulator.run -> loss/grad on the host."""
+        amp, det, ph = pulse_samples(ta, td, interp)
+        em = pdb.TorchEmulator(SequenceSamples([ChannelSamples(amp, det, ph)]), register, device_spec,
+                               sampling_rate=RATE, torch_device=dev)
+        res = em.run(solver=pdb.SolverType.DP5_SE)
+        loss = res.expect([diag_dev])[0].real[-1]
+        ga, gd = torch.autograd.grad(loss, [ta, td])
+        steps = sum(1 for r in em._last_result.step_log() if r["accepted"])
+        return float(loss), ga, gd, steps, em
+
+    # device-resident variant: Hamiltonian structure + psi0 prepared once, outside the timed region
+    _, _, _, n_steps, em0 = e2e_pass()
+    H = em0._hamiltonian._hamiltonian
+    dm, dv, am, av = H.masks_and_values()
+    dv_d = dv.detach().clone().requires_grad_(True)
+    av_d = av.detach().clone().requires_grad_(True)
+    pair_u = H.pair_u.detach()
+    psi0_dev = em0.initial_state.to(dev).transpose(0, 1).contiguous()
+    tsave = em0.evaluation_times.detach()
+
+    def resident_pass():
+        st = ops.evolve(psi0_dev, tsave, dv_d, av_d, pair_u, n_qubits=N_QUBITS, kind=_cabi.PD_KET,
+                        dt=H.dt, det_masks=dm, amp_masks=am, solver=_cabi.SOLVER_DP5_SE)
+        loss = torch.ops.pulser_diff_b200.expect_diag  # noqa: F841 (op exists)
+        from pulser_diff_b200.utils import expect_diag
+        val = expect_diag(diag_dev, st.permute(0, 2, 1)).real[-1]
+        torch.autograd.grad(val, [dv_d, av_d])
+        return val
+
+    for _ in range(args.warmup):
+        resident_pass()
+        e2e_pass()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    # ---- timed region 1: device-resident passes ----
+    l0 = plan.launch_count
+    barrier()
+    t0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        resident_pass()
+    ev1.record()
+    barrier()
+    t_res = time.perf_counter() - t0
+    launches = plan.launch_count - l0
+    # ---- timed region 2: end-to-end passes from host tensors ----
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss_val, ga, gd, n_steps, _ = e2e_pass()
+    barrier()
+    t_e2e = time.perf_counter() - t0
+
+    # ---- roofline: the HBM-bound regime, N = roofline_n, CUDA events inside the C ABI ----
+    roof = roof_h = None
+    peak, peak_src = measured_peak()
+    if rank == 0 and args.roofline_n > 0:
+        nr = args.roofline_n
+        ops.clear_plan_cache()
+        big = _cabi.Plan(nr, 1, _cabi.PD_KET, dev)
+        cu = torch.zeros(nr, nr, dtype=torch.float64)
+        cc = chain_coords(nr)
+        for i in range(nr):
+            for j in range(i + 1, nr):
+                cu[i, j] = C6 / float(torch.linalg.norm(cc[i] - cc[j])) ** 6
+        big.set_interaction(cu)
+        big.set_terms(H.dt, dm, dv, am, av)
+        y = torch.zeros(1, 2 ** nr, dtype=torch.complex128, device=dev)
+        y[0, -1] = 1.0
+        ms_step = big.bench_dp5_steps(0.3, 1e-3, args.roofline_steps, y)
+        psi = torch.randn(1, 2 ** nr, dtype=torch.float64, device=dev).to(torch.complex128)
+        ms_h = big.bench_hpsi(0.3, psi, max(4, args.roofline_steps * 3))
+        s_amp = 2 ** nr
+        ach = 576.0 * s_amp / (ms_step * 1e-3) / 1e9
+        ach_h = 40.0 * s_amp / (ms_h * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": "fused DP5 step (6 generator applications + stage combines + error norm)",
+                "workload": f"chain_n{nr}_dp5_step", "ms_per_launch": ms_step,
+                "algorithmic_bytes": 576.0 * s_amp, "steps_per_s": 1e3 / ms_step}
+        roof_h = {"bound": "hbm", "achieved": ach_h, "peak": peak, "unit": "GB/s", "frac": ach_h / peak,
+                  "traffic": None, "kernel": "H(t) psi", "workload": f"chain_n{nr}_hpsi",
+                  "ms_per_launch": ms_h, "algorithmic_bytes": 40.0 * s_amp}
+        del big, y, psi
+        torch.cuda.empty_cache()
+    clocks = sampler.summary()
+
+    # max over ranks
+    t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device=dev)
+    steps_total = torch.tensor([float(n_steps)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(steps_total, op=dist.ReduceOp.SUM)
+    t_res, t_e2e = t.tolist()
+    total_steps = steps_total.item() * args.steps
+    value = total_steps / t_res
+    e2e_value = total_steps / t_e2e
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_sample(args.seed, budget_s=args.cpu_budget)
+
+    if rank == 0:
+        s12 = 2 ** N_QUBITS
+        h2d = int(s12 * 16 + N_QUBITS * N_QUBITS * 8)
+        d2h = int(n_steps * 6 * N_QUBITS * 4 * 16 + (n_steps + 8) * 8 + len(tsave) * 16)
+        line = {
+            "metric": "evolution steps/sec (DP5 steps, forward+gradient)", "value": value,
+            "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
+            "config": {"workload": "C2: 12-atom chain state preparation, DP5_SE fwd + gradient of "
+                                   "<n_i n_j> loss w.r.t. 60 pulse parameters",
+                       "n_qubits": N_QUBITS, "duration_ns": DURATION, "sampling_rate": RATE,
+                       "n_params": 2 * N_PARAM, "dp5_steps_per_pass": n_steps,
+                       "parameter_sets": world, "parallelism": f"independent parameter sets x{world}",
+                       "l2": "state (64 KiB) is smaller than L2 by construction of the workload; "
+                             "the roofline block uses N=26 (1 GiB vectors, >> 126 MB L2)"},
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_pass": 1e3 * t_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof, "roofline_hpsi": roof_h,
+            "roofline_workload": {"bound": "latency", "achieved": 576.0 * s12 * total_steps / world / t_res / 1e9 * 3,
+                                  "peak": peak, "unit": "GB/s",
+                                  "note": "N=12: 64 KiB vectors live in L2; 3x = fwd + recompute + adjoint"},
+            "cpu_baseline": cpu,
+            "loss": loss_val,
+        }
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(seed: int, budget_s: float = 20.0):
+    """The oracle on a bounded sample of the workload: forward + tape gradient over the first
+    tsave intervals, all host threads."""
+    from helpers import Channel, Problem
+    from oracle.ref_solvers import SolverType, sesolve
+    from pulser_diff_b200.utils import interpolate_sine
+    torch.set_num_threads(os.cpu_count() or 1)
+    interp = interpolate_sine(N_PARAM, DURATION).to(torch.float64)
+    ta, td = workload_params(seed)
+    amp, det, ph = pulse_samples(ta, td, interp)
+    p = Problem(chain_coords(N_QUBITS), C6, [Channel(amp, det, ph)], rate=RATE)
+    ref = p.ref()
+    n_int = 1
+    t0 = time.perf_counter()
+    ts = ref.evaluation_times[: n_int + 1].clone()
+    res = sesolve(ref.ham.H, ref.initial_state, ts, SolverType.DP5_SE, {})
+    d = loss_diag(N_QUBITS, "cpu")
+    loss = (d[:, None] * res.states[-1].abs() ** 2).sum()
+    torch.autograd.grad(loss, [ta, td])
+    dt = time.perf_counter() - t0
+    steps = sum(1 for r in res.steplog if r[2])
+    return {"value": steps / dt, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"first {n_int} of 55 tsave intervals of the same N=12 workload "
+                      f"({steps} DP5 steps forward + tape gradient, {dt:.1f} s)",
+            "seconds": dt, "dp5_steps": steps}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_sample(args.seed, budget_s=args.cpu_budget)
+        if i >= args.warmup:
+            vals.append(last)
+    tot_steps = sum(v["dp5_steps"] for v in vals)
+    tot_s = sum(v["seconds"] for v in vals)
+    value = tot_steps / tot_s
+    last = dict(last, value=value)
+    print(json.dumps({
+        "impl": "reference", "metric": "evolution steps/sec (DP5 steps, forward+gradient)",
+        "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_s / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "c128 (f64 arithmetic)", "data": "synthetic",
+        "config": {"workload": "C2: 12-atom chain state preparation, DP5_SE fwd + gradient "
+                               "(bounded sample: first tsave interval per step)",
+                   "n_qubits": N_QUBITS, "duration_ns": DURATION, "sampling_rate": RATE},
+        "cpu_baseline": last,
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference CPU path = oracle port (pyqtorch/pulser not installable: SURVEY.md 8c)",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--roofline-n", type=int, default=26)
+    ap.add_argument("--roofline-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

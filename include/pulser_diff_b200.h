@@ -153,6 +153,16 @@ int pd_tape_destroy(pd_tape* t);
 int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t,
                    const double* obs_dev, double* out_host /* complex [n_t] */);
 
+/* ---- measurement hooks (bench.py roofline) ------------------------------------------------- */
+/* Average device time (ms, CUDA events on `stream`) of `reps` back-to-back H(t)·psi
+ * applications in -> out. */
+int pd_bench_hpsi(pd_plan* p, void* stream, double t, int32_t reps, const void* in_dev,
+                  void* out_dev, double* ms_per_apply_host);
+/* Average device time (ms) of `steps` fixed-size DP5 steps from y_dev (6 generator
+ * applications with fused stage combination, y_new, error norm; every step accepted, FSAL). */
+int pd_bench_dp5_steps(pd_plan* p, void* stream, double t0, double dt, int32_t steps, void* y_dev,
+                       double* ms_per_step_host);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* number of CUDA kernels this plan has launched since creation (bench.py gpu_launches) */
 int64_t pd_plan_launch_count(const pd_plan* p);

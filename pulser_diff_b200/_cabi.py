@@ -46,7 +46,8 @@ EXPORTS = (
     "pd_abi_version", "pd_last_error", "pd_options_default", "pd_plan_create", "pd_plan_destroy",
     "pd_plan_set_interaction", "pd_plan_set_terms", "pd_plan_set_collapse", "pd_hpsi", "pd_rhs",
     "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
-    "pd_tape_destroy", "pd_expect_diag", "pd_plan_launch_count", "pd_is_cuda",
+    "pd_tape_destroy", "pd_expect_diag", "pd_bench_hpsi", "pd_bench_dp5_steps",
+    "pd_plan_launch_count", "pd_is_cuda",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -76,6 +77,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.pd_tape_records.argtypes = [vp, C.POINTER(pd_step_record), i64]
     lib.pd_tape_destroy.argtypes = [vp]
     lib.pd_expect_diag.argtypes = [vp, vp, vp, i32, vp, pdbl]
+    lib.pd_bench_hpsi.argtypes = [vp, vp, dbl, i32, vp, vp, pdbl]
+    lib.pd_bench_dp5_steps.argtypes = [vp, vp, dbl, dbl, i32, vp, pdbl]
     lib.pd_plan_launch_count.argtypes = [vp]
     lib.pd_plan_launch_count.restype = i64
 
@@ -323,6 +326,23 @@ class Plan:
         _check(lib().pd_expect_diag(self._ptr, _stream(self.device), _dptr(states), n_t, _dptr(obs),
                                     _hdbl(out)))
         return torch.view_as_complex(out)
+
+    def bench_hpsi(self, t: float, psi: torch.Tensor, reps: int) -> float:
+        """Average device ms of one H(t)·psi (CUDA events on the current stream)."""
+        psi = self._vec(psi, "psi")
+        out = torch.empty_like(psi)
+        ms = C.c_double()
+        _check(lib().pd_bench_hpsi(self._ptr, _stream(self.device), float(t), int(reps), _dptr(psi),
+                                   _dptr(out), C.byref(ms)))
+        return ms.value
+
+    def bench_dp5_steps(self, t0: float, dt: float, steps: int, y: torch.Tensor) -> float:
+        """Average device ms of one fixed-size DP5 step (updates ``y`` in place)."""
+        y = self._vec(y, "y")
+        ms = C.c_double()
+        _check(lib().pd_bench_dp5_steps(self._ptr, _stream(self.device), float(t0), float(dt),
+                                        int(steps), _dptr(y), C.byref(ms)))
+        return ms.value
 
     @property
     def launch_count(self) -> int:

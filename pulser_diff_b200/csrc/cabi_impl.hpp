@@ -151,6 +151,20 @@ int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t
     p->eng.expect_diag((const pd::cplx*)states_dev, n_t, obs_dev, out_host, stream);
   });
 }
+int pd_bench_hpsi(pd_plan* p, void* stream, double t, int32_t reps, const void* in_dev,
+                  void* out_dev, double* ms_per_apply_host) {
+  return guarded([&] {
+    need(p && in_dev && out_dev && ms_per_apply_host && reps > 0, "pd_bench_hpsi: bad argument");
+    *ms_per_apply_host = p->eng.bench_apply((const pd::cplx*)in_dev, (pd::cplx*)out_dev, t, reps, stream);
+  });
+}
+int pd_bench_dp5_steps(pd_plan* p, void* stream, double t0, double dt, int32_t steps, void* y_dev,
+                       double* ms_per_step_host) {
+  return guarded([&] {
+    need(p && y_dev && ms_per_step_host && steps > 0, "pd_bench_dp5_steps: bad argument");
+    *ms_per_step_host = p->eng.bench_dp5((pd::cplx*)y_dev, t0, dt, steps, stream);
+  });
+}
 int64_t pd_plan_launch_count(const pd_plan* p) { return p ? p->eng.launches : 0; }
 
 }  // extern "C"

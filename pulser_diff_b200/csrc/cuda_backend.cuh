@@ -89,6 +89,17 @@ class CudaBackend {
     PD_CUDA_CHECK(cudaMemcpyAsync(d, sr, b, cudaMemcpyDeviceToHost, st(s)));
   }
   void sync(void* s) { PD_CUDA_CHECK(cudaStreamSynchronize(st(s))); }
+  void timer_start(void* s) {
+    if (!ev0_) { PD_CUDA_CHECK(cudaEventCreate(&ev0_)); PD_CUDA_CHECK(cudaEventCreate(&ev1_)); }
+    PD_CUDA_CHECK(cudaEventRecord(ev0_, st(s)));
+  }
+  double timer_stop_ms(void* s) {
+    PD_CUDA_CHECK(cudaEventRecord(ev1_, st(s)));
+    PD_CUDA_CHECK(cudaEventSynchronize(ev1_));
+    float ms = 0.f;
+    PD_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0_, ev1_));
+    return (double)ms;
+  }
   size_t reduce_scratch_bytes(const Geometry&) { return sizeof(double) * kMaxReduceBlocks * kMaxR * 2; }
   size_t segment_budget_bytes() {
     size_t fr = 0, tot = 0;
@@ -161,6 +172,7 @@ class CudaBackend {
 
  private:
   double* d_pair_u_ = nullptr;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
 };
 
 }  // namespace pd

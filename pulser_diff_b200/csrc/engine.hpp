@@ -162,6 +162,42 @@ class Engine {
                    stream);
   }
 
+  // ---- measurement hooks ------------------------------------------------------------------
+  double bench_apply(const cplx* in, cplx* out, double t, int reps, void* stream) {
+    apply(out, in, t, 2, stream);
+    bk.sync(stream);
+    bk.timer_start(stream);
+    for (int r = 0; r < reps; ++r) apply(out, in, t, 2, stream);
+    return bk.timer_stop_ms(stream) / std::max(1, reps);
+  }
+  double bench_dp5(cplx* y_io, double t0, double dt, int steps, void* stream) {
+    vec y = vbuf("y"), ynew = vbuf("ynew");
+    vec k[7];
+    for (int i = 0; i < 7; ++i) k[i] = vbuf("k" + std::to_string(i));
+    double* d_err = (double*)buf("norm_out", sizeof(double) * geo.batch);
+    bk.d2d(y, y_io, sizeof(cplx) * L, stream);
+    double t = t0;
+    apply(k[0], y, t, 0, stream);
+    auto one = [&]() {
+      dp5_stages(t, dt, y, k, ynew, 7, stream);
+      double ew[7];
+      for (int j = 0; j < 7; ++j) ew[j] = dt * (tab.b5[j] - tab.b4[j]);
+      launches += bk.err_sumsq(geo, d_err, (const cplx* const*)k, ew, y, ynew, 1e-8, 1e-6,
+                               reduce_scratch(), stream);
+      t += dt;
+      std::swap(y, ynew);
+      std::swap(k[0], k[6]);
+    };
+    one();
+    bk.sync(stream);
+    bk.timer_start(stream);
+    for (int s = 0; s < steps; ++s) one();
+    double ms = bk.timer_stop_ms(stream) / std::max(1, steps);
+    bk.d2d(y_io, y, sizeof(cplx) * L, stream);
+    bk.sync(stream);
+    return ms;
+  }
+
   // ---- diagonal expectation --------------------------------------------------------------
   void expect_diag(const cplx* states, int n_t, const double* obs, double* out_host, void* stream) {
     cplx* d_out = (cplx*)buf("expect", sizeof(cplx) * (size_t)n_t);

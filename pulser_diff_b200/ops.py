@@ -1,0 +1,227 @@
+"""torch-facing operators of the B200 evolution engine.
+
+* :func:`evolve` - differentiable evolution (``torch.autograd.Function``) whose leaves are
+  exactly the tensors the reference's tape differentiates: the coefficient arrays captured by
+  ``H`` (``det_values`` / ``amp_values``, reference hamiltonian.py:506-520), the pair couplings
+  behind ``int_mat`` (hamiltonian.py:341-343), ``tsave`` (backend.py:453-455) and the initial
+  state.  Backward = adjoint sweep on the device; ``retain_graph`` / repeated
+  ``autograd.grad`` calls work because the step log is kept, not consumed
+  (reference derivative.py:40,76 call it 40x in docs/basic_usage.ipynb cell 26).
+* ``torch.ops.pulser_diff_b200.{hpsi, rhs, evolve_states, expect_diag}`` - ``torch.library``
+  custom ops over the same C ABI for non-differentiable use.
+
+Internal state layout is batch-major ``(batch, dim)``; the reference layout ``(dim, batch)``
+is converted in :mod:`pulser_diff_b200.solvers`.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import _cabi
+from ._cabi import PD_DENSITY, PD_KET, Options, Plan
+
+_program_ids = itertools.count()
+_PLAN_CACHE: dict[tuple, Plan] = {}
+
+
+@dataclass
+class Program:
+    """Everything that defines H(t) (and the dissipator) for one evolution, detached."""
+    n_qubits: int
+    kind: int
+    dt: float
+    det_masks: List[int]
+    det_values: Tensor            # (n_det, n_samples) float64, cpu
+    amp_masks: List[int]
+    amp_values: Tensor            # (n_amp, n_samples) complex128, cpu
+    pair_u: Tensor                # (N, N) float64, cpu
+    collapse: Optional[Tensor] = None   # (n_ops, 2, 2) complex128, cpu
+    id: int = field(default_factory=lambda: next(_program_ids))
+
+
+def clear_plan_cache() -> None:
+    """Drop cached plans (frees their device workspace)."""
+    _PLAN_CACHE.clear()
+
+
+def get_plan(n_qubits: int, batch: int, kind: int, device: torch.device) -> Plan:
+    device = torch.device(device)
+    if device.type == "cuda" and device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    key = (n_qubits, batch, kind, str(device), _cabi._lib_path)
+    plan = _PLAN_CACHE.get(key)
+    if plan is None:
+        plan = Plan(n_qubits, batch, kind, device)
+        _PLAN_CACHE[key] = plan
+    return plan
+
+
+def configure(plan: Plan, prog: Program) -> None:
+    if plan.program_id == prog.id:
+        return
+    plan.set_interaction(prog.pair_u)
+    plan.set_terms(prog.dt, prog.det_masks, prog.det_values, prog.amp_masks, prog.amp_values)
+    if plan.kind == PD_DENSITY:
+        plan.set_collapse(prog.collapse)
+    plan.program_id = prog.id
+
+
+def make_program(n_qubits: int, kind: int, dt: float, det_masks: Sequence[int], det_values: Tensor,
+                 amp_masks: Sequence[int], amp_values: Tensor, pair_u: Tensor,
+                 collapse: Optional[Tensor]) -> Program:
+    return Program(
+        n_qubits, kind, float(dt), [int(m) for m in det_masks],
+        det_values.detach().to("cpu", torch.float64).reshape(len(det_masks), -1).contiguous(),
+        [int(m) for m in amp_masks],
+        amp_values.detach().to("cpu", torch.complex128).reshape(len(amp_masks), -1).contiguous(),
+        pair_u.detach().to("cpu", torch.float64).contiguous(),
+        None if collapse is None else collapse.detach().to("cpu", torch.complex128).contiguous())
+
+
+class _EvolveFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, state0: Tensor, tsave: Tensor, det_values: Tensor, amp_values: Tensor,
+                pair_u: Tensor, n_qubits: int, kind: int, dt: float, det_masks, amp_masks,
+                collapse, solver: int, opt: Options):
+        batch = int(state0.shape[0])
+        plan = get_plan(n_qubits, batch, kind, state0.device)
+        prog = make_program(n_qubits, kind, dt, det_masks, det_values, amp_masks, amp_values,
+                            pair_u, collapse)
+        configure(plan, prog)
+        need = any(ctx.needs_input_grad[:5])
+        states, tape = plan.evolve_forward(solver, opt, state0.detach(), tsave, want_tape=need)
+        ctx.plan, ctx.prog, ctx.tape = plan, prog, tape
+        ctx.meta = (tsave.device, tsave.dtype, det_values.device, det_values.dtype,
+                    amp_values.device, amp_values.dtype, pair_u.device, pair_u.dtype,
+                    tuple(det_values.shape), tuple(amp_values.shape))
+        ctx.save_for_backward(states)
+        ctx.set_materialize_grads(False)
+        return states
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_states: Optional[Tensor]):
+        none = (None,) * 13
+        if grad_states is None or ctx.tape is None:
+            return none
+        (states,) = ctx.saved_tensors
+        plan, prog = ctx.plan, ctx.prog
+        configure(plan, prog)
+        w_s0, w_ts, w_det, w_amp, w_pair = ctx.needs_input_grad[:5]
+        g_det, g_amp, g_pair, g_ts, g_s0 = plan.evolve_backward(
+            ctx.tape, states, grad_states.to(torch.complex128).contiguous(),
+            want_det=w_det, want_amp=w_amp, want_pair=w_pair, want_tsave=w_ts, want_state0=w_s0)
+        (ts_dev, ts_dt, det_dev, det_dt, amp_dev, amp_dt, pu_dev, pu_dt, det_shape, amp_shape) = ctx.meta
+        if g_ts is not None:
+            g_ts = g_ts.to(device=ts_dev, dtype=ts_dt)
+        if g_det is not None:
+            g_det = g_det.reshape(det_shape).to(device=det_dev)
+            g_det = g_det.to(det_dt) if not det_dt.is_complex else g_det.to(det_dt)
+        elif w_det:
+            g_det = torch.zeros(det_shape, dtype=det_dt, device=det_dev)
+        if g_amp is not None:
+            g_amp = g_amp.reshape(amp_shape).to(device=amp_dev)
+            g_amp = g_amp.to(amp_dt) if amp_dt.is_complex else g_amp.real.to(amp_dt)
+        elif w_amp:
+            g_amp = torch.zeros(amp_shape, dtype=amp_dt, device=amp_dev)
+        if g_pair is not None:
+            g_pair = g_pair.to(device=pu_dev, dtype=pu_dt)
+        return (g_s0, g_ts, g_det, g_amp, g_pair) + (None,) * 8
+
+
+def evolve(state0: Tensor, tsave: Tensor, det_values: Tensor, amp_values: Tensor, pair_u: Tensor, *,
+           n_qubits: int, kind: int, dt: float, det_masks: Sequence[int], amp_masks: Sequence[int],
+           collapse: Optional[Tensor] = None, solver: int = _cabi.SOLVER_DP5_SE,
+           options: Optional[Options] = None) -> Tensor:
+    """states[k] = state at tsave[k]; shape (n_t, batch, dim), complex128, on state0's device."""
+    opt = options or Options()
+    return _EvolveFn.apply(state0, tsave, det_values, amp_values, pair_u, int(n_qubits), int(kind),
+                           float(dt), list(det_masks), list(amp_masks), collapse, int(solver), opt)
+
+
+def last_step_log(states: Tensor) -> list[dict]:
+    """Attempted-step records of the evolution that produced ``states`` (needs a grad graph)."""
+    fn = states.grad_fn
+    while fn is not None and not hasattr(fn, "tape"):
+        nxt = [f for f, _ in fn.next_functions if f is not None]
+        fn = nxt[0] if nxt else None
+    if fn is None or fn.tape is None:
+        raise RuntimeError("no step log: the evolution was run without gradient tracking")
+    return fn.tape.records()
+
+
+# ------------------------------------------------------------------------------------------
+# torch.library custom ops (non-differentiable entry points)
+# ------------------------------------------------------------------------------------------
+def _prog_from_args(n_qubits, kind, dt, det_masks, det_values, amp_masks, amp_values, pair_u, collapse):
+    coll = collapse if collapse is not None and collapse.numel() > 0 else None
+    return make_program(n_qubits, kind, dt, det_masks, det_values, amp_masks, amp_values, pair_u, coll)
+
+
+@torch.library.custom_op("pulser_diff_b200::hpsi", mutates_args=())
+def hpsi(psi: Tensor, t: float, det_values: Tensor, amp_values: Tensor, pair_u: Tensor,
+         det_masks: List[int], amp_masks: List[int], dt: float) -> Tensor:
+    """H(t) @ psi for psi of shape (batch, 2**N)."""
+    n = int(pair_u.shape[0])
+    plan = get_plan(n, int(psi.shape[0]), PD_KET, psi.device)
+    configure(plan, _prog_from_args(n, PD_KET, dt, det_masks, det_values, amp_masks, amp_values,
+                                    pair_u, None))
+    return plan.hpsi(t, psi)
+
+
+@hpsi.register_fake
+def _(psi, t, det_values, amp_values, pair_u, det_masks, amp_masks, dt):
+    return torch.empty_like(psi)
+
+
+@torch.library.custom_op("pulser_diff_b200::rhs", mutates_args=())
+def rhs(state: Tensor, t: float, det_values: Tensor, amp_values: Tensor, pair_u: Tensor,
+        collapse: Tensor, det_masks: List[int], amp_masks: List[int], dt: float, kind: int) -> Tensor:
+    """-i H(t) psi (kind 0) or the Lindblad right-hand side on vec(rho) (kind 1)."""
+    n = int(pair_u.shape[0])
+    plan = get_plan(n, int(state.shape[0]), kind, state.device)
+    configure(plan, _prog_from_args(n, kind, dt, det_masks, det_values, amp_masks, amp_values,
+                                    pair_u, collapse))
+    return plan.hpsi(t, state, rhs=True)
+
+
+@rhs.register_fake
+def _(state, t, det_values, amp_values, pair_u, collapse, det_masks, amp_masks, dt, kind):
+    return torch.empty_like(state)
+
+
+@torch.library.custom_op("pulser_diff_b200::evolve_states", mutates_args=())
+def evolve_states(state0: Tensor, tsave: Tensor, det_values: Tensor, amp_values: Tensor,
+                  pair_u: Tensor, collapse: Tensor, det_masks: List[int], amp_masks: List[int],
+                  dt: float, kind: int, solver: int, atol: float, rtol: float) -> Tensor:
+    """Forward-only evolution; returns (n_t, batch, dim)."""
+    n = int(pair_u.shape[0])
+    plan = get_plan(n, int(state0.shape[0]), kind, state0.device)
+    configure(plan, _prog_from_args(n, kind, dt, det_masks, det_values, amp_masks, amp_values,
+                                    pair_u, collapse))
+    states, _ = plan.evolve_forward(solver, Options(atol=atol, rtol=rtol), state0, tsave, False)
+    return states
+
+
+@evolve_states.register_fake
+def _(state0, tsave, det_values, amp_values, pair_u, collapse, det_masks, amp_masks, dt, kind,
+      solver, atol, rtol):
+    return state0.new_empty((tsave.numel(),) + tuple(state0.shape))
+
+
+@torch.library.custom_op("pulser_diff_b200::expect_diag", mutates_args=())
+def expect_diag(states: Tensor, obs_diag: Tensor, kind: int) -> Tensor:
+    """sum over batch of <psi|diag(obs)|psi> (kind 0) or tr(diag(obs) rho) (kind 1), per time."""
+    n = int(obs_diag.numel()).bit_length() - 1
+    plan = get_plan(n, int(states.shape[1]), kind, states.device)
+    return plan.expect_diag(states, obs_diag)
+
+
+@expect_diag.register_fake
+def _(states, obs_diag, kind):
+    return torch.empty(states.shape[0], dtype=torch.complex128)

@@ -5,6 +5,7 @@
 // never loads on its own (pulser_diff_b200/_cabi.py only accepts it when a test passes the
 // path explicitly).  "Device" pointers are host pointers here; streams are ignored.
 #pragma once
+#include <chrono>
 #include <cstdlib>
 
 #include "../../pulser_diff_b200/csrc/pd_common.hpp"
@@ -26,6 +27,11 @@ class HostBackend {
   void d2d(void* d, const void* s, size_t b, void*) { std::memmove(d, s, b); }
   void d2h(void* d, const void* s, size_t b, void*) { std::memmove(d, s, b); }
   void sync(void*) {}
+  std::chrono::steady_clock::time_point t0_;
+  void timer_start(void*) { t0_ = std::chrono::steady_clock::now(); }
+  double timer_stop_ms(void*) {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_).count();
+  }
   size_t reduce_scratch_bytes(const Geometry&) { return 64; }
   size_t segment_budget_bytes() { return segment_budget; }
   size_t segment_budget = (size_t)1 << 28;

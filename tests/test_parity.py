@@ -1,0 +1,217 @@
+"""Parity of the engine with the oracle on identical seeded inputs.
+
+Every test runs twice: against tests/emu (host stand-in; exercises the host-side engine and the
+Python layer on CPU) and, marked ``gpu``, against the CUDA library on cuda:0 -- the parity
+tests proper, which go through the C ABI.
+
+Tolerances (north_star): complex128 states / expectation values 1e-10 absolute, gradients 1e-8
+relative.  Both sides run the same adaptive controller from the same start, so their accepted
+step sequences coincide and the observed differences are round-off (~1e-13); the replay test
+additionally forces the oracle's recorded sequence (shared-step protocol).
+"""
+import math
+
+import pytest
+import torch
+
+from helpers import KAT_SOLVER, Problem, golden, kat_problem, random_problem
+from oracle.ref_emulator import expect as ref_expect, total_magnetization as ref_totmag
+from oracle.ref_solvers import SolverType as RefSolver
+import pulser_diff_b200 as pdb
+from pulser_diff_b200.utils import expect_diag, total_magnetization_diag
+
+ATOL_STATE = 1e-10
+RTOL_GRAD = 1e-8
+GOLD = golden("notebook_kats.json")
+
+
+def rel(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-300)).item()
+
+
+# ---------------------------------------------------------------------------------------------
+def test_hpsi_matches_sparse_matrix(engine_device):
+    p = random_problem(5, seed=3, local=True, grad=False)
+    ref = p.ref()
+    em = p.emulator(engine_device)
+    H = em._hamiltonian._hamiltonian
+    dm, dv, am, av = H.masks_and_values()
+    psi = torch.randn(3, 2 ** p.n, dtype=torch.complex128, generator=torch.Generator().manual_seed(1))
+    for t in (0.0, 0.0123, 0.1507, 0.3):
+        want = (ref.ham.H(torch.tensor(t, dtype=torch.float64)) @ psi.T).T
+        got = torch.ops.pulser_diff_b200.hpsi(psi.to(engine_device), t, dv, av, H.pair_u.detach(),
+                                              dm, am, H.dt).cpu()
+        assert (got - want).abs().max() < 1e-12 * want.abs().max()
+        # the compatibility closure builds the same matrix
+        assert (H(torch.tensor(t, dtype=torch.float64)).to_dense() - ref.ham.H(
+            torch.tensor(t, dtype=torch.float64)).to_dense()).abs().max() < 1e-12
+
+
+@pytest.mark.parametrize("name", ["K-A", "K-B", "K-C", "K-D", "K-E", "K-F", "K-G"])
+def test_notebook_kats_through_emulator(engine_device, name):
+    p = kat_problem(name)
+    em = p.emulator(engine_device)
+    ref = p.ref()
+    if name == "K-G":
+        em.set_initial_state(torch.eye(4))
+        ref.set_initial_state(torch.eye(4))
+    res = em.run(solver=pdb.SolverType(KAT_SOLVER[name]))
+    want = ref.run(solver=RefSolver(KAT_SOLVER[name])).states
+    assert (res.states.cpu() - want).abs().max() < ATOL_STATE
+    if name == "K-G":
+        h = torch.tensor([[1, 1], [1, -1]], dtype=torch.complex128) / math.sqrt(2)
+        infid = 1 - abs(torch.trace(torch.kron(h, h).mH @ res.states[-1].cpu())) / 4
+        assert abs(infid.item() - GOLD[name]["infidelity"]) < 6e-7
+        return
+    z = res.expect([total_magnetization_diag(p.n)])[0].real.cpu()
+    z_dense = res.expect([ref_totmag(p.n)])[0].real.cpu()
+    assert (z - z_dense).abs().max() < 1e-11
+    if name == "K-A":
+        assert (z - torch.tensor(GOLD[name]["sum_z"], dtype=torch.float64)).abs().max() < 6e-5
+    else:
+        assert abs(z[-1].item() - GOLD[name]["final_sum_z"]) < 6e-5
+
+
+def _loss_and_leaves(p: Problem, states, tsave, extra):
+    g = torch.Generator().manual_seed(7)
+    G = torch.randn(states.shape, dtype=torch.complex128, generator=g)
+    loss = (G.to(states.device).conj() * states).real.sum()
+    leaves = [p.coords] + [t for c in p.channels for t in (c.amp, c.det, c.phase)] + [tsave] + extra
+    return loss, leaves
+
+
+@pytest.mark.parametrize("solver", ["dp5_se", "krylov_se"])
+@pytest.mark.parametrize("local", [False, True])
+def test_ket_states_and_gradients(engine_device, solver, local):
+    p = random_problem(4, seed=11, local=local)
+    psi0 = torch.randn(2 ** p.n, 2, dtype=torch.complex128, generator=torch.Generator().manual_seed(2))
+    psi0 = (psi0 / psi0.norm(dim=0)).requires_grad_(True)
+    ref = p.ref()
+    ref.set_initial_state(psi0)
+    r = ref.run(time_grad=True, solver=RefSolver(solver))
+    loss_r, leaves_r = _loss_and_leaves(p, r.states, ref.evaluation_times, [psi0])
+    g_ref = torch.autograd.grad(loss_r, leaves_r)
+
+    em = p.emulator(engine_device)
+    em.set_initial_state(psi0)
+    res = em.run(time_grad=True, solver=pdb.SolverType(solver))
+    assert (res.states.detach().cpu() - r.states.detach()).abs().max() < ATOL_STATE
+    loss, leaves = _loss_and_leaves(p, res.states, em.evaluation_times, [psi0])
+    assert abs(loss.item() - loss_r.item()) < 1e-10 * max(1.0, abs(loss_r.item()))
+    g = torch.autograd.grad(loss, leaves, retain_graph=True)
+    for a, b in zip(g, g_ref):
+        assert rel(a.cpu(), b) < RTOL_GRAD
+    # the graph survives repeated one-hot cotangents (reference derivative.py:40,76)
+    g2 = torch.autograd.grad(loss, leaves)
+    for a, b in zip(g, g2):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("noise", [
+    {"dephasing_rate": 0.7, "relaxation_rate": 0.3},
+    {"depolarizing_rate": 0.4, "eff_noise": [(0.2, [[0, 1], [1, 0]]), (0.1, [[0.3, 0.5j], [0.2, -0.1]])]},
+])
+def test_lindblad_states_and_gradients(engine_device, noise):
+    p = random_problem(3, seed=5, noise=noise)
+    ref = p.ref()
+    r = ref.run(time_grad=True, solver=RefSolver.DP5_ME)
+    loss_r, leaves_r = _loss_and_leaves(p, r.states, ref.evaluation_times, [])
+    g_ref = torch.autograd.grad(loss_r, leaves_r)
+    em = p.emulator(engine_device)
+    res = em.run(time_grad=True)              # Lindblad noise forces DP5_ME (backend.py:477-483)
+    assert res.states.shape == r.states.shape
+    assert (res.states.detach().cpu() - r.states.detach()).abs().max() < ATOL_STATE
+    loss, leaves = _loss_and_leaves(p, res.states, em.evaluation_times, [])
+    g = torch.autograd.grad(loss, leaves)
+    for a, b in zip(g, g_ref):
+        assert rel(a.cpu(), b) < RTOL_GRAD
+    # trace and hermiticity survive
+    rho = res.states.detach()[-1, :, :, 0]
+    assert abs(torch.trace(rho).item() - 1) < 1e-7
+    assert (rho - rho.mH).abs().max() < 1e-12
+    # diagonal observable through the fused reduction == dense einsum
+    z = res.expect([total_magnetization_diag(p.n)])[0].cpu()
+    assert (z - ref_expect(ref_totmag(p.n), r.states.detach())).abs().max() < 1e-10
+
+
+def test_dist_grad_and_time_grad_helpers(engine_device):
+    """deriv_time / deriv_param / qq_distances as used in docs/basic_usage.ipynb cells 19, 26."""
+    p = random_problem(3, seed=9, T=200, rate=0.1, grad=True)
+    em = p.emulator(engine_device)
+    res = em.run(time_grad=True, dist_grad=True)
+    f = res.expect([total_magnetization_diag(p.n)])[0].real
+    ref = p.ref()
+    r = ref.run(time_grad=True)
+    f_ref = ref_expect(ref_totmag(p.n), r.states).real
+    assert (f.detach().cpu() - f_ref.detach()).abs().max() < ATOL_STATE
+    dt_ = pdb.deriv_time(f, em.evaluation_times)
+    dt_ref = torch.autograd.grad(f_ref, ref.evaluation_times, torch.ones_like(f_ref), retain_graph=True)[0]
+    assert rel(dt_.cpu(), dt_ref) < RTOL_GRAD
+    key = "q0-q2"
+    amp = p.channels[0].amp
+    got = pdb.deriv_param(f, [amp, em.qq_distances[key]], em.evaluation_times, t=100.0)
+    v = torch.zeros(len(f_ref), dtype=torch.float64)
+    v[torch.abs(ref.evaluation_times.detach() - 0.1).argmin()] = 1.0
+    want = torch.autograd.grad(f_ref, [amp, ref.ham.dist[(0, 2)]], v)
+    for a, b in zip(got, want):
+        assert rel(a.cpu(), b) < RTOL_GRAD
+
+
+def test_shared_step_sequence_replay(engine_device):
+    """Force the oracle's recorded attempted-step sequence (tight agreement by construction)."""
+    p = random_problem(4, seed=21, grad=False)
+    ref = p.ref()
+    r = ref.run()
+    em = p.emulator(engine_device)
+    replay = [(dt, clipped) for (_, dt, _, _, clipped) in r.steplog]
+    res = em.run(replay=replay)
+    assert (res.states.cpu() - r.states).abs().max() < 1e-12
+
+
+def test_default_controller_step_log_matches_oracle(engine_device):
+    p = random_problem(4, seed=22, grad=True)
+    ref = p.ref()
+    r = ref.run()
+    em = p.emulator(engine_device)
+    em.run()
+    log = em._last_result.step_log()
+    assert len(log) == len(r.steplog)
+    for a, b in zip(log, r.steplog):
+        assert a["accepted"] == b[2] and a["clipped"] == b[4]
+        assert abs(a["dt"] - b[1]) <= 1e-9 * abs(b[1])
+
+
+def test_tight_tolerance_protocol(engine_device):
+    p = random_problem(3, seed=4, grad=False, T=120)
+    opts = dict(atol=1e-13, rtol=1e-12)
+    r = p.ref().run(**opts)
+    res = p.emulator(engine_device).run(**opts)
+    assert (res.states.cpu() - r.states).abs().max() < ATOL_STATE
+
+
+def test_errors_and_edge_cases(engine_device):
+    p = random_problem(2, seed=1, grad=False, T=100)
+    em = p.emulator(engine_device)
+    with pytest.raises(ValueError):
+        em.set_initial_state(torch.zeros(3, 1))
+    with pytest.raises(ValueError):
+        em.set_evaluation_times("Sometimes")
+    with pytest.raises(ValueError):
+        em.set_evaluation_times([0.0, 5.0])
+    with pytest.raises(ValueError):
+        em.run(solver="not-a-solver")
+    with pytest.raises(TypeError):
+        pdb.sesolve(lambda t: None, em.initial_state, em.evaluation_times)
+    with pytest.raises(TypeError):
+        em.run(not_an_option=1)
+    with pytest.raises(RuntimeError):
+        em.run(max_steps=1)
+    em.set_evaluation_times("Minimal")
+    assert em.evaluation_times.tolist() == [0.0, 0.1]
+    res = em.run()
+    assert res.states.shape == (2, 4, 1)
+    assert abs(res.states[-1].norm().item() - 1) < 1e-6
+    # single-qubit register (reference hamiltonian.py:501-505)
+    p1 = random_problem(1, seed=1, grad=False, T=100)
+    r1 = p1.ref().run()
+    assert (p1.emulator(engine_device).run().states.cpu() - r1.states).abs().max() < ATOL_STATE
