@@ -120,6 +120,10 @@ int pd_plan_set_terms(pd_plan* p, int32_t n_samples, double dt, int32_t n_det,
  * (r,g) basis.  n_ops = 0 reproduces backend.py:496-498 (single zero operator). */
 int pd_plan_set_collapse(pd_plan* p, int32_t n_ops, const double* ops_host);
 
+/* Kernel family for the next calls on this plan: 0 = auto, 1 = gather kernels, 2 = tiled kernels
+ * where the shape allows (used by the tiled-vs-gather parity tests). */
+int pd_plan_set_path(pd_plan* p, int32_t path);
+
 /* ---- single operator applications --------------------------------------------------------- */
 /* out = H(t) in   (ket plans; what `H(t) @ psi` does upstream) */
 int pd_hpsi(pd_plan* p, void* stream, double t, const void* in_dev, void* out_dev);

@@ -44,7 +44,8 @@ class pd_step_record(C.Structure):
 # every symbol include/pulser_diff_b200.h declares (checked by tests/test_cabi_symbols.py)
 EXPORTS = (
     "pd_abi_version", "pd_last_error", "pd_options_default", "pd_plan_create", "pd_plan_destroy",
-    "pd_plan_set_interaction", "pd_plan_set_terms", "pd_plan_set_collapse", "pd_hpsi", "pd_rhs",
+    "pd_plan_set_interaction", "pd_plan_set_terms", "pd_plan_set_collapse", "pd_plan_set_path",
+    "pd_hpsi", "pd_rhs",
     "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
     "pd_tape_destroy", "pd_expect_diag", "pd_bench_hpsi", "pd_bench_dp5_steps",
     "pd_plan_launch_count", "pd_is_cuda",
@@ -67,6 +68,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.pd_plan_set_interaction.argtypes = [vp, pdbl, vp]
     lib.pd_plan_set_terms.argtypes = [vp, i32, dbl, i32, pu64, pdbl, i32, pu64, pdbl]
     lib.pd_plan_set_collapse.argtypes = [vp, i32, pdbl]
+    lib.pd_plan_set_path.argtypes = [vp, i32]
     lib.pd_hpsi.argtypes = [vp, vp, dbl, vp, vp]
     lib.pd_rhs.argtypes = [vp, vp, dbl, vp, vp]
     lib.pd_evolve_forward.argtypes = [vp, vp, i32, C.POINTER(pd_options), vp, pdbl, i32, vp,
@@ -254,6 +256,9 @@ class Plan:
         if tuple(o.shape[1:]) != (2, 2, 2):
             raise ValueError("collapse operators must be (n_ops, 2, 2) complex")
         _check(lib().pd_plan_set_collapse(self._ptr, int(o.shape[0]), _hdbl(o)))
+
+    def set_path(self, path: int) -> None:
+        _check(lib().pd_plan_set_path(self._ptr, int(path)))
 
     # ---- applications ------------------------------------------------------------------------
     def _vec(self, t: torch.Tensor, what: str, lead: tuple = ()) -> torch.Tensor:

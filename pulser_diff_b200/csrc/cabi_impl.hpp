@@ -89,6 +89,12 @@ int pd_plan_set_collapse(pd_plan* p, int32_t n_ops, const double* ops_host) {
     p->eng.set_collapse(n_ops, ops_host);
   });
 }
+int pd_plan_set_path(pd_plan* p, int32_t path) {
+  return guarded([&] {
+    need(p != nullptr && path >= 0 && path <= 2, "pd_plan_set_path: bad argument");
+    p->eng.bk.path = path;
+  });
+}
 int pd_hpsi(pd_plan* p, void* stream, double t, const void* in_dev, void* out_dev) {
   return guarded([&] {
     need(p && in_dev && out_dev, "pd_hpsi: NULL argument");

@@ -57,6 +57,13 @@ int launch_tiled_stage_ket(const Geometry& g, cplx* out, cplx* comb, int n_in,
                            const cplx* const* ins, const double* w, const SiteOps& so, cplx* tmp,
                            cudaStream_t s);
 
+int launch_tiled_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cplx* ynew,
+                          const SiteOps* stage_ops, const double* beta, const double* b5,
+                          const double* ew, double dt, double atol, double rtol, cplx* tmp_a,
+                          cplx* tmp_b, double* err_partial, double* err_out, cudaStream_t s);
+size_t tiled_err_partial_count(const Geometry& g);
+constexpr int kAutoTiledMinQubits = 18;   // below this the whole working set is L2 resident
+
 class CudaBackend {
  public:
   static constexpr bool is_cuda = true;
@@ -121,7 +128,7 @@ class CudaBackend {
   }
   int stage_ket(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
                 const double* w, const SiteOps& so, cplx* scratch, void* s) {
-    if (path != 1 && tiled_ket_supported(g))
+    if (use_tiled(g))
       return launch_tiled_stage_ket(g, out, comb, n_in, ins, w, so, scratch, st(s));
     int n = 0;
     const cplx* src = ins[0];
@@ -133,6 +140,20 @@ class CudaBackend {
       d2d(comb, ins[0], sizeof(cplx) * g.dim * g.batch, s);
     }
     return n + launch_apply_ket(g, out, src, so, st(s));
+  }
+  bool use_tiled(const Geometry& g) const {
+    if (path == 1 || !tiled_ket_supported(g)) return false;
+    return path == 2 || g.nq >= kAutoTiledMinQubits;
+  }
+  // One full Dormand-Prince step with the alternating tiled kernels; 0 = not handled here.
+  int dp5_step_ket(const Geometry& g, const cplx* y, cplx* const* k, cplx* ynew,
+                   const SiteOps* stage_ops, const Tableau& tab, const double* ew, double dt,
+                   double atol, double rtol, cplx* tmp_a, cplx* tmp_b, double* red_scratch,
+                   double* err_out, void* s) {
+    if (!use_tiled(g)) return 0;
+    if (tiled_err_partial_count(g) > (size_t)kMaxReduceBlocks * kMaxR * 2) return 0;
+    return launch_tiled_dp5_step(g, y, k, ynew, stage_ops, &tab.beta[0][0], tab.b5, ew, dt, atol,
+                                 rtol, tmp_a, tmp_b, red_scratch, err_out, st(s));
   }
   int stage_density(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
                     const double* w, const SiteOpsDensity& so, cplx* scratch, void* s) {

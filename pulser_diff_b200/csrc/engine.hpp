@@ -179,11 +179,7 @@ class Engine {
     double t = t0;
     apply(k[0], y, t, 0, stream);
     auto one = [&]() {
-      dp5_stages(t, dt, y, k, ynew, 7, stream);
-      double ew[7];
-      for (int j = 0; j < 7; ++j) ew[j] = dt * (tab.b5[j] - tab.b4[j]);
-      launches += bk.err_sumsq(geo, d_err, (const cplx* const*)k, ew, y, ynew, 1e-8, 1e-6,
-                               reduce_scratch(), stream);
+      dp5_step_with_error(t, dt, y, k, ynew, 1e-8, 1e-6, d_err, stream);
       t += dt;
       std::swap(y, ynew);
       std::swap(k[0], k[6]);
@@ -288,6 +284,24 @@ class Engine {
     }
   }
 
+  // stages 2..7, y_{n+1} and the per-column error sums of one step; fused tiled path if the
+  // backend offers one for this shape, stage by stage otherwise
+  void dp5_step_with_error(double t, double dt, const cplx* y, vec* k, vec ynew, double atol,
+                           double rtol, double* d_err, void* stream) {
+    double ew[7];
+    for (int j = 0; j < 7; ++j) ew[j] = dt * (tab.b5[j] - tab.b4[j]);
+    if (prog.kind == PD_KET) {
+      std::vector<SiteOps> so(7);
+      for (int i = 1; i < 7; ++i) prog.site_ops_ket(t + dt * tab.alpha[i - 1], 0, so[i]);
+      int nl = bk.dp5_step_ket(geo, y, k, ynew, so.data(), tab, ew, dt, atol, rtol, vbuf("scratch"),
+                               vbuf("scratch2"), reduce_scratch(), d_err, stream);
+      if (nl > 0) { launches += nl; return; }
+    }
+    dp5_stages(t, dt, y, k, ynew, 7, stream);
+    launches += bk.err_sumsq(geo, d_err, (const cplx* const*)k, ew, y, ynew, atol, rtol,
+                             reduce_scratch(), stream);
+  }
+
   void forward_dp5(const pd_options& o, const cplx* state0, const double* tsave, int n_t,
                    cplx* states, Tape* tape, void* stream) {
     vec y = vbuf("y"), ynew = vbuf("ynew");
@@ -318,11 +332,7 @@ class Engine {
           ++pos;
         }
         if (clipped) { cache_dt = dt; cache_err = error; dt = t_next - t; }
-        dp5_stages(t, dt, y, k, ynew, 7, stream);
-        double ew[7];
-        for (int j = 0; j < 7; ++j) ew[j] = dt * (tab.b5[j] - tab.b4[j]);
-        launches += bk.err_sumsq(geo, d_err, (const cplx* const*)k, ew, y, ynew, o.atol, o.rtol,
-                                 reduce_scratch(), stream);
+        dp5_step_with_error(t, dt, y, k, ynew, o.atol, o.rtol, d_err, stream);
         bk.d2h(h_err.data(), d_err, sizeof(double) * geo.batch, stream);
         bk.sync(stream);
         error = hairer_from_sumsq(h_err.data());

@@ -1,9 +1,367 @@
-// Tiled (shared-memory staged) ket kernels -- placeholder until the tiled family lands.
+// Tiled ket kernels: the HBM-bound path for large registers.
+//
+// H(t) = H_A(t) + H_B(t):
+//   H_A = static diagonal + detuning diagonal + sigma-x flips on the LOW  bits [0, LA)
+//   H_B =                                       sigma-x flips on the HIGH bits [LA, N)
+// A type-A tile is 2^TB contiguous amplitudes (closes over the low bits); a type-B tile is
+// 2^(N-LA) rows (stride 2^LA amplitudes) x 2^C contiguous columns (closes over the high bits).
+// Either tile lives in shared memory once; every bit flip is a shared-memory partner read.
+//
+// One kernel does TWO things on its tile, so that no stage input is ever materialised:
+//   finalise:  out_prev     = partial_prev + H_tau(t_prev) * Yprev,   Yprev = sum_j wprev_j v_j
+//   start:     partial_next =                H_tau(t_next) * Ynext,   Ynext = sum_j wnext_j v_j
+//                                                                            + wnext_out * out_prev
+// Alternating tile types A,B,A,B,... a Dormand-Prince step is 7 launches (K0 start-only ...
+// K6 finalise-only with the error norm in its epilogue) reading 34 and writing 13 vectors:
+// 784 B per amplitude against the 576 B algorithmic figure.
 #include "cuda_backend.cuh"
+
 namespace pd {
-bool tiled_ket_supported(const Geometry&) { return false; }
-int launch_tiled_stage_ket(const Geometry&, cplx*, cplx*, int, const cplx* const*, const double*,
-                           const SiteOps&, cplx*, cudaStream_t) {
-  throw Error(PD_ERR_STATE, "tiled ket kernels not built");
+
+namespace {
+
+constexpr int TB = 12;            // tile = 4096 amplitudes = 64 KiB of shared memory
+constexpr int TILE = 1 << TB;
+constexpr int NT = 256;           // threads per CTA; 2 CTAs per SM
+constexpr int EPT = TILE / NT;    // 16 amplitudes per thread
+constexpr int kMaxIn = 8;
+constexpr int kMinTiledQubits = 16;
+constexpr int kMaxTiledQubits = 2 * TB - 1;   // C >= 1 (32 B pieces); C >= 3 up to N = 21
+
+struct BitCoef {   // coefficients of one application for the bits this tile type handles
+  cplx kappa;                 // scale of the static diagonal (type A)
+  cplx t00[kMaxQubits];       // per GLOBAL bit position p: T[a=0][a=0]  (diagonal, a = 0)
+  cplx t11[kMaxQubits];
+  cplx t01[kMaxQubits];       // row a=0 <- a'=1
+  cplx t10[kMaxQubits];       // row a=1 <- a'=0
+};
+
+struct TiledParams {
+  int nq, type, C, n_in, do_prev, do_next, do_err;
+  size_t dim;
+  const cplx* v[kMaxIn];
+  double wprev[kMaxIn], wnext[kMaxIn], werr[kMaxIn];
+  double wnext_out, werr_out;
+  const cplx* partial_prev;
+  cplx* out_prev;
+  cplx* partial_next;
+  cplx* ynext_out;
+  const double* diag;
+  double atol, rtol;
+  double* err_partial;   // [gridDim.x] per-CTA sums of |err/scale|^2
+};
+
+__device__ __forceinline__ cplx ldg(const cplx* p) {
+  double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return {v.x, v.y};
 }
+
+// global amplitude index of local element e of tile `tile`
+__device__ __forceinline__ size_t gindex(int type, int C, size_t tile, int e) {
+  if (type == 0) return (tile << TB) + (size_t)e;
+  size_t row = (size_t)(e >> C), col = (size_t)(e & ((1 << C) - 1));
+  return (row << TB) + (tile << C) + col;
+}
+
+// own part of H applied to the tile in shared memory, at local element e
+template <int TYPE>
+__device__ __forceinline__ cplx apply_tile(const cplx* __restrict__ T, int e, const BitCoef& bc,
+                                           int nbits, int lb0, int gb0, cplx dsum) {
+  cplx acc{0.0, 0.0};
+  if (TYPE == 0) fma_acc(acc, dsum, T[e]);
+#pragma unroll 4
+  for (int b = 0; b < nbits; ++b) {
+    int lb = lb0 + b, gb = gb0 + b;
+    bool a = (e >> lb) & 1;
+    cplx c = a ? bc.t10[gb] : bc.t01[gb];
+    fma_acc(acc, c, T[e ^ (1 << lb)]);
+  }
+  return acc;
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(NT, 2)
+k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef cprev,
+        const __grid_constant__ BitCoef cnext) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  __shared__ cplx tab_prev[2][64], tab_next[2][64];   // detuning diagonal over local bits 0-5 / 6-11
+  __shared__ double red[NT / 32];
+
+  const int t = threadIdx.x;
+  const int nq = P.nq, C = P.C;
+  const size_t tiles_per_vec = P.dim >> TB;
+  const size_t tile = blockIdx.x % tiles_per_vec;
+  const size_t boff = (blockIdx.x / tiles_per_vec) * P.dim;     // batch column offset
+  // bits this tile closes over: type A local [0,TB) = global [0,TB); type B local [C,TB) = global [TB,nq)
+  const int nbits = TYPE == 0 ? (nq < TB ? nq : TB) : (nq - TB);
+  const int lb0 = TYPE == 0 ? 0 : C, gb0 = TYPE == 0 ? 0 : TB;
+
+  cplx z[EPT];
+  // ---- phase 1a: one pass over the input vectors builds Yprev (-> smem) and the v-part of Ynext
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) z[i] = {0.0, 0.0};
+  constexpr int QP = 4;   // elements per sub-pass: bounds registers (z + yp + x) under 128
+#pragma unroll
+  for (int q0 = 0; q0 < EPT; q0 += QP) {
+    cplx yp[QP];
+#pragma unroll
+    for (int i = 0; i < QP; ++i) yp[i] = {0.0, 0.0};
+    for (int j = 0; j < P.n_in; ++j) {
+      const cplx* vj = P.v[j] + boff;
+      const double wp = P.wprev[j], wn = P.wnext[j];
+      cplx x[QP];
+#pragma unroll
+      for (int i = 0; i < QP; ++i) x[i] = ldg(vj + gindex(TYPE, C, tile, t + NT * (q0 + i)));
+#pragma unroll
+      for (int i = 0; i < QP; ++i) {
+        yp[i].re = fma(wp, x[i].re, yp[i].re); yp[i].im = fma(wp, x[i].im, yp[i].im);
+        z[q0 + i].re = fma(wn, x[i].re, z[q0 + i].re);
+        z[q0 + i].im = fma(wn, x[i].im, z[q0 + i].im);
+      }
+    }
+    if (P.do_prev) {
+#pragma unroll
+      for (int i = 0; i < QP; ++i) T[t + NT * (q0 + i)] = yp[i];
+    }
+  }
+  // detuning-diagonal tables (type A): sum over local bits of (a ? t11 : t00), split 6 + 6 bits;
+  // the bits above the tile are constant per tile.
+  cplx hi_prev{0, 0}, hi_next{0, 0};
+  if (TYPE == 0) {
+    if (t < 128) {
+      int half = t >> 6, x = t & 63;
+      cplx sp{0, 0}, sn{0, 0};
+      for (int b = 0; b < 6; ++b) {
+        int gb = half * 6 + b;
+        if (gb < nq) {
+          bool a = (x >> b) & 1;
+          sp = sp + (a ? cprev.t11[gb] : cprev.t00[gb]);
+          sn = sn + (a ? cnext.t11[gb] : cnext.t00[gb]);
+        }
+      }
+      tab_prev[half][x] = sp;
+      tab_next[half][x] = sn;
+    }
+    for (int gb = TB; gb < nq; ++gb) {
+      bool a = (tile >> (gb - TB)) & 1;
+      hi_prev = hi_prev + (a ? cprev.t11[gb] : cprev.t00[gb]);
+      hi_next = hi_next + (a ? cnext.t11[gb] : cnext.t00[gb]);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1b: finalise the previous application
+  double err_acc = 0.0;
+  if (P.do_prev) {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const int e = t + NT * i;
+      const size_t g = boff + gindex(TYPE, C, tile, e);
+      cplx dsum{0, 0};
+      if (TYPE == 0) {
+        double dg = P.diag[g - boff];
+        dsum = cplx{cprev.kappa.re * dg, cprev.kappa.im * dg} + hi_prev + tab_prev[0][e & 63] +
+               tab_prev[1][(e >> 6) & 63];
+      }
+      cplx o = apply_tile<TYPE>(T, e, cprev, nbits, lb0, gb0, dsum);
+      if (P.partial_prev) o = o + ldg(P.partial_prev + g);
+      P.out_prev[g] = o;
+      z[i].re = fma(P.wnext_out, o.re, z[i].re);
+      z[i].im = fma(P.wnext_out, o.im, z[i].im);
+      if (P.do_err) {
+        // here z accumulates sum_j werr_j v_j (wnext := werr, wnext_out := werr_out)
+        cplx y0 = ldg(P.v[0] + g), y1 = T[e];
+        double sc = P.atol + P.rtol * fmax(hypot(y0.re, y0.im), hypot(y1.re, y1.im));
+        double er = z[i].re / sc, ei = z[i].im / sc;
+        err_acc += er * er + ei * ei;
+      }
+    }
+  }
+  if (P.do_err) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) err_acc += __shfl_xor_sync(0xffffffffu, err_acc, o);
+    if ((t & 31) == 0) red[t >> 5] = err_acc;
+    __syncthreads();
+    if (t == 0) {
+      double s = 0.0;
+      for (int w = 0; w < NT / 32; ++w) s += red[w];
+      P.err_partial[blockIdx.x] = s;
+    }
+  }
+  if (!P.do_next) return;
+
+  // ---- phase 2a: Ynext -> smem (and optionally to global: y_{n+1})
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int e = t + NT * i;
+    T[e] = z[i];
+    if (P.ynext_out) P.ynext_out[boff + gindex(TYPE, C, tile, e)] = z[i];
+  }
+  __syncthreads();
+  // ---- phase 2b: start the next application
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int e = t + NT * i;
+    const size_t g = boff + gindex(TYPE, C, tile, e);
+    cplx dsum{0, 0};
+    if (TYPE == 0) {
+      double dg = P.diag[g - boff];
+      dsum = cplx{cnext.kappa.re * dg, cnext.kappa.im * dg} + hi_next + tab_next[0][e & 63] +
+             tab_next[1][(e >> 6) & 63];
+    }
+    P.partial_next[g] = apply_tile<TYPE>(T, e, cnext, nbits, lb0, gb0, dsum);
+  }
+}
+
+void fill_coef(const SiteOps& so, int nq, BitCoef& bc) {
+  bc.kappa = so.kappa;
+  for (int q = 0; q < nq; ++q) {
+    int p = nq - 1 - q;   // global bit position of qubit q
+    bc.t00[p] = so.T[q * 4 + 0];
+    bc.t01[p] = so.T[q * 4 + 1];
+    bc.t10[p] = so.T[q * 4 + 2];
+    bc.t11[p] = so.T[q * 4 + 3];
+  }
+}
+
+bool g_attr_set = false;
+void launch(const TiledParams& P, const BitCoef& cp, const BitCoef& cn, int batch, cudaStream_t s) {
+  if (!g_attr_set) {
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+    g_attr_set = true;
+  }
+  unsigned grid = (unsigned)((P.dim >> TB) * (size_t)batch);
+  if (P.type == 0) k_tiled<0><<<grid, NT, TILE * 16, s>>>(P, cp, cn);
+  else k_tiled<1><<<grid, NT, TILE * 16, s>>>(P, cp, cn);
+  PD_CUDA_CHECK(cudaGetLastError());
+}
+
+__global__ void k_sum_partials(const double* __restrict__ partial, int per_col, double* out) {
+  __shared__ double sh[32];
+  int b = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < per_col; i += blockDim.x) s += partial[(size_t)b * per_col + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sh[w];
+    out[b] = tot;
+  }
+}
+
+TiledParams base_params(const Geometry& g) {
+  TiledParams P{};
+  P.nq = g.nq;
+  P.dim = g.dim;
+  P.C = 2 * TB - g.nq;   // type-B tile: 2^(nq-TB) rows x 2^C columns
+  P.diag = g.diag;
+  return P;
+}
+
+}  // namespace
+
+bool tiled_ket_supported(const Geometry& g) {
+  return g.kind == PD_KET && g.nq >= kMinTiledQubits && g.nq <= kMaxTiledQubits;
+}
+
+// out = G (sum_j w_j in_j); comb (nullable) = the combined input.  Two launches: type A starts
+// (diagonal + low bits), type B finalises (high bits).  `tmp` holds the partial in between.
+int launch_tiled_stage_ket(const Geometry& g, cplx* out, cplx* comb, int n_in,
+                           const cplx* const* ins, const double* w, const SiteOps& so, cplx* tmp,
+                           cudaStream_t s) {
+  if (n_in > kMaxIn) throw Error(PD_ERR_INVALID, "tiled stage takes at most 8 inputs");
+  BitCoef bc;
+  fill_coef(so, g.nq, bc);
+  TiledParams A = base_params(g);
+  A.type = 0; A.n_in = n_in; A.do_next = 1;
+  for (int j = 0; j < n_in; ++j) { A.v[j] = ins[j]; A.wnext[j] = w[j]; }
+  A.partial_next = tmp;
+  A.ynext_out = comb;
+  launch(A, bc, bc, g.batch, s);
+  TiledParams B = base_params(g);
+  B.type = 1; B.n_in = n_in; B.do_prev = 1;
+  for (int j = 0; j < n_in; ++j) { B.v[j] = ins[j]; B.wprev[j] = w[j]; }
+  B.partial_prev = tmp;
+  B.out_prev = out;
+  launch(B, bc, bc, g.batch, s);
+  return 2;
+}
+
+// One Dormand-Prince step as 7 alternating launches.  k[0] holds f(t, y) on entry (FSAL);
+// on exit k[1..6] are filled, ynew = y_{n+1}, err_out[b] = sum |err/scale|^2 per batch column.
+int launch_tiled_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cplx* ynew,
+                          const SiteOps* stage_ops /* [7], index i = stage i+1 */, const double* beta,
+                          const double* b5, const double* ew, double dt, double atol, double rtol,
+                          cplx* tmp_a, cplx* tmp_b, double* err_partial, double* err_out,
+                          cudaStream_t s) {
+  BitCoef bc[7];
+  for (int i = 1; i < 7; ++i) fill_coef(stage_ops[i], g.nq, bc[i]);
+  // launch m (0..6): tile type m%2; finalises stage m+1 (if m >= 1), starts stage m+2 (if m <= 5)
+  cplx* partial[2] = {tmp_a, tmp_b};
+  for (int m = 0; m < 7; ++m) {
+    TiledParams P = base_params(g);
+    P.type = m % 2;
+    int fin = m;        // k index finalised: k[fin] (stage fin+1), needs fin >= 1
+    int sta = m + 1;    // k index started:   k[sta] (stage sta+1), needs sta <= 6
+    P.do_prev = m >= 1;
+    P.do_next = m <= 5;
+    // inputs: y, k[0..m-1]
+    P.n_in = 1 + m;
+    if (P.n_in > kMaxIn) throw Error(PD_ERR_STATE, "dp5 tiled: too many inputs");
+    P.v[0] = y;
+    for (int j = 0; j < m; ++j) P.v[1 + j] = k[j];
+    if (P.do_prev) {
+      // Yprev = input of stage fin+1 = y + dt * sum_{j<fin} beta[fin-1][j] k[j]
+      P.wprev[0] = 1.0;
+      for (int j = 0; j < fin; ++j) P.wprev[1 + j] = dt * beta[(fin - 1) * 6 + j];
+      P.partial_prev = partial[(m + 1) % 2];
+      P.out_prev = k[fin];
+    }
+    if (P.do_next) {
+      // Ynext = input of stage sta+1 = y + dt * sum_{j<sta} beta[sta-1][j] k[j]; k[sta-1] = out_prev
+      P.wnext[0] = 1.0;
+      for (int j = 0; j < m; ++j) P.wnext[1 + j] = dt * beta[(sta - 1) * 6 + j];
+      P.wnext_out = m >= 1 ? dt * beta[(sta - 1) * 6 + (sta - 1)] : 0.0;
+      if (m == 0) { /* stage 2 input: y + dt*beta[0][0]*k[0]; k[0] is not an input yet */ }
+      P.partial_next = partial[m % 2];
+      if (sta == 6) P.ynext_out = ynew;
+    }
+    if (m == 0) {
+      // k[0] (FSAL) must be an explicit input of the first launch
+      P.n_in = 2;
+      P.v[1] = k[0];
+      P.wnext[1] = dt * beta[0];
+    } else {
+      // for m >= 1 the inputs are y, k[0..m-1]; out_prev = k[m] enters Ynext through wnext_out
+      P.wnext_out = dt * beta[(sta - 1) * 6 + m];
+      if (!P.do_next) P.wnext_out = 0.0;
+    }
+    if (m == 6) {
+      // error norm in the epilogue: err = sum_j ew_j k_j (k[6] = out_prev), y0 = v[0], y1 = Yprev
+      P.do_err = 1;
+      P.werr_out = ew[6];
+      for (int j = 0; j < 8; ++j) P.wnext[j] = 0.0;
+      for (int j = 0; j < 6; ++j) P.wnext[1 + j] = ew[j];
+      P.wnext_out = ew[6];
+      P.atol = atol; P.rtol = rtol;
+      P.err_partial = err_partial;
+    }
+    const BitCoef& cp = bc[P.do_prev ? fin : 1];
+    const BitCoef& cn = bc[P.do_next ? sta : 6];
+    launch(P, cp, cn, g.batch, s);
+  }
+  int per_col = (int)(g.dim >> TB);
+  k_sum_partials<<<g.batch, 256, 0, s>>>(err_partial, per_col, err_out);
+  (void)b5;
+  return 8;
+}
+
+size_t tiled_err_partial_count(const Geometry& g) { return (g.dim >> TB) * (size_t)g.batch; }
+
 }  // namespace pd

@@ -92,6 +92,10 @@ class HostBackend {
     }
     return 1;
   }
+  int dp5_step_ket(const Geometry&, const cplx*, cplx* const*, cplx*, const SiteOps*, const Tableau&,
+                   const double*, double, double, double, cplx*, cplx*, double*, double*, void*) {
+    return 0;   // no fused path in the stand-in: the engine falls back to stage-by-stage
+  }
   int stage_density(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
                     const double* w, const SiteOpsDensity& so, cplx* scratch, void*) {
     const cplx* in = combine(g, comb, n_in, ins, w, scratch);
