@@ -77,7 +77,8 @@ typedef struct pd_options {
   double exp_tolerance; /* 1e-10 */
   double norm_tolerance;/* 1e-10 */
   /* additions (do not change defaults): */
-  int32_t n_replay;     /* >0: force this attempted-step sequence (shared-step parity protocol) */
+  int32_t n_replay;     /* >0: force this ACCEPTED-step sequence, every step taken as accepted
+                           (shared-step parity protocol) */
   const double* replay_dt;      /* host [n_replay] step sizes (ignored for clipped steps) */
   const uint8_t* replay_clipped;/* host [n_replay] 1 = step lands on the next tsave point */
   int32_t path;         /* 0 = auto, 1 = force generic gather kernels, 2 = force tiled kernels */

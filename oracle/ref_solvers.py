@@ -13,9 +13,10 @@ are reference backend.py:488-494 (sesolve) and backend.py:502-509 (mesolve).
 * Krylov (H frozen at the interval END)      Appendix A.5
 * backward = plain autograd tape             Appendix A.6
 
-``record`` / ``replay`` are oracle-only additions for the shared-step-sequence
-parity protocol: ``record`` returns every attempted step
-``(t, dt, accepted, error)``; ``replay`` forces that sequence.
+``steplog`` / ``replay`` are oracle-only additions for the shared-step-sequence
+parity protocol: ``Result.steplog`` lists every attempted step
+``(t, dt, accepted, error, clipped)``; ``replay`` = the ACCEPTED entries of such a
+log, which are then taken verbatim (every replayed step counts as accepted).
 """
 from __future__ import annotations
 
@@ -155,7 +156,7 @@ def _integrate_adaptive(f, y0: Tensor, tsave: Tensor, opt: AdaptiveOptions,
                 dt_used = dt
             f_new, y_new, y_err = dp.step(t, y, ft, dt_used)
             error = dp.error(y_err, y, y_new)
-            accepted = error <= 1
+            accepted = True if replay is not None else error <= 1
             log.append((float(t), float(dt_used), bool(accepted), float(error), bool(clipped)))
             if accepted:
                 t = t_next if clipped else t + dt_used

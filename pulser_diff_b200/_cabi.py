@@ -160,7 +160,7 @@ class Options:
     exp_tolerance: float = 1e-10
     norm_tolerance: float = 1e-10
     use_sparse: bool = False          # accepted for API parity; the path is matrix free
-    replay: Optional[Sequence] = None  # [(dt, clipped), ...] shared-step parity protocol
+    replay: Optional[Sequence] = None  # accepted steps [(dt, clipped), ...]: shared-step protocol
     path: int = 0                     # 0 auto, 1 gather kernels, 2 tiled kernels
 
     @classmethod

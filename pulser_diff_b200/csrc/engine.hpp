@@ -336,7 +336,7 @@ class Engine {
         bk.d2h(h_err.data(), d_err, sizeof(double) * geo.batch, stream);
         bk.sync(stream);
         error = hairer_from_sumsq(h_err.data());
-        bool accepted = error <= 1.0;
+        bool accepted = replay ? true : error <= 1.0;   // a replayed sequence holds accepted steps only
         if (!(error == error)) throw Error(PD_ERR_STATE, "non-finite error norm in DP5 step");
         if (tape) {
           tape->records.push_back({t, dt, error, accepted ? 1 : 0, clipped ? 1 : 0, kk, 0});

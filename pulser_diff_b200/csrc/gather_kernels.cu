@@ -64,6 +64,7 @@ int finalize(const double* partial, int nblocks, int R, double* out, int out_str
   int wpb = 4;
   k_reduce_final<<<(R + wpb - 1) / wpb, wpb * 32, 0, s>>>(partial, nblocks, R, pstride ? pstride : R,
                                                          out, out_stride, scale, accumulate);
+  PD_CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
@@ -359,6 +360,7 @@ int launch_lincomb(const Geometry& g, cplx* out, int n_in, const cplx* const* in
   for (int i = 0; i < n_in; ++i) { a.p[i] = ins[i]; a.w[i] = w[i]; }
   size_t n = g.dim * g.batch;
   k_lincomb<<<grid_for(n, 2), kThreads, 0, s>>>(out, a, n);
+  PD_CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
@@ -369,12 +371,14 @@ int launch_lincomb_c(size_t n, cplx* out, int m, const cplx* basis, size_t strid
   cw.m = m;
   for (int i = 0; i < m; ++i) cw.w[i] = ws[i];
   k_lincomb_c<<<grid_for(n, 2), kThreads, 0, s>>>(out, basis, stride, cw, n);
+  PD_CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
 int launch_apply_ket(const Geometry& g, cplx* out, const cplx* in, const SiteOps& so, cudaStream_t s) {
   size_t total = g.dim * g.batch;
   k_apply_ket<<<grid_for(total), kThreads, 0, s>>>(out, in, g.diag, so, g.nq, g.dim, total);
+  PD_CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
@@ -386,11 +390,13 @@ int launch_apply_density(const Geometry& g, cplx* out, const cplx* in, const Sit
     for (int p = 0; p < 4; ++p)
       if (so.nzmask[q] >> (p * 4 + (p ^ 3)) & 1) need_both = 1;
   k_apply_density<<<grid_for(total), kThreads, 0, s>>>(out, in, g.diag, so, g.nq, total, need_both);
+  PD_CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
 int launch_build_diag(double* diag, int nq, const double* d_pair_u, cudaStream_t s) {
   k_build_diag<<<grid_for((size_t)1 << nq), kThreads, 0, s>>>(diag, nq, d_pair_u);
+  PD_CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
@@ -398,6 +404,7 @@ int launch_scaled_sumsq(const Geometry& g, double* out, const cplx* x, const cpl
                         const cplx* ref, double atol, double rtol, double* scratch, cudaStream_t s) {
   int gx = rgrid_for(g.dim, 1, g.batch);
   k_scaled_sumsq<<<dim3(gx, g.batch), kThreads, 0, s>>>(x, xsub, ref, atol, rtol, g.dim, scratch);
+  PD_CUDA_CHECK(cudaGetLastError());
   int n = 1;
   for (int b = 0; b < g.batch; ++b) n += finalize(scratch + (size_t)b * gx, gx, 1, out + b, 1, 1.0, 0, s);
   return n;
@@ -410,6 +417,7 @@ int launch_err_sumsq(const Geometry& g, double* out, const cplx* const* k, const
   for (int j = 0; j < 7; ++j) { kp.k[j] = k[j]; kp.ew[j] = ew[j]; }
   int gx = rgrid_for(g.dim, 1, g.batch);
   k_err_sumsq<<<dim3(gx, g.batch), kThreads, 0, s>>>(kp, y0, y1, atol, rtol, g.dim, scratch);
+  PD_CUDA_CHECK(cudaGetLastError());
   int n = 1;
   for (int b = 0; b < g.batch; ++b) n += finalize(scratch + (size_t)b * gx, gx, 1, out + b, 1, 1.0, 0, s);
   return n;
@@ -420,6 +428,7 @@ int launch_re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, 
   size_t n = g.dim * g.batch;
   int gx = rgrid_for(n, 1, 1);
   k_re_dot<<<gx, kThreads, 0, s>>>(a, b, n, scratch);
+  PD_CUDA_CHECK(cudaGetLastError());
   return 1 + finalize(scratch, gx, 1, out, 1, 1.0, 0, s);
 }
 
@@ -431,6 +440,7 @@ int launch_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, 
     if (!d_corr) ny = 1;
     int gx = rgrid_for(g.dim, kQC * 8, ny);
     k_corr_ket<<<dim3(gx, ny), kThreads, 0, s>>>(kbar, y, g.nq, g.dim, g.batch, scratch, d_wacc, wscale);
+  PD_CUDA_CHECK(cudaGetLastError());
     ++n;
     if (d_corr)
       for (int c = 0; c < ny; ++c) {
@@ -443,6 +453,7 @@ int launch_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, 
     size_t total = g.dim * g.batch;
     int gx = rgrid_for(total, 32, ny);
     k_corr_density<<<dim3(gx, ny), kThreads, 0, s>>>(kbar, y, g.nq, total, scratch, d_wacc, wscale);
+  PD_CUDA_CHECK(cudaGetLastError());
     ++n;
     if (d_corr)
       for (int q = 0; q < ny; ++q)
@@ -454,6 +465,7 @@ int launch_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, 
 
 int launch_pair_reduce(const Geometry& g, double* d_pair, const double* d_wacc, cudaStream_t s) {
   k_pair_reduce<<<g.nq * g.nq, kThreads, 0, s>>>(d_wacc, g.nq, d_pair);
+  PD_CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
@@ -469,6 +481,7 @@ int launch_expect_diag(const Geometry& g, const cplx* states, int n_t, const dou
     gx = std::min(gx, 64);
     k_expect_diag<<<dim3(gx, nt), kThreads, 0, s>>>(states + (size_t)t0 * g.dim * g.batch, obs, g.kind,
                                                     g.nq, g.dim, g.batch, scratch);
+  PD_CUDA_CHECK(cudaGetLastError());
     ++n;
     for (int t = 0; t < nt; ++t)
       n += finalize(scratch + (size_t)t * gx * 2, gx, 2, (double*)(out + t0 + t), 1, 1.0, 0, s);

@@ -53,7 +53,7 @@ def get_plan(n_qubits: int, batch: int, kind: int, device: torch.device) -> Plan
     device = torch.device(device)
     if device.type == "cuda" and device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    key = (n_qubits, batch, kind, str(device), _cabi._lib_path)
+    key = (n_qubits, batch, kind, str(device), _cabi._lib_path or _cabi.DEFAULT_LIBRARY)
     plan = _PLAN_CACHE.get(key)
     if plan is None:
         plan = Plan(n_qubits, batch, kind, device)

@@ -163,8 +163,8 @@ def test_shared_step_sequence_replay(engine_device):
     ref = p.ref()
     r = ref.run()
     em = p.emulator(engine_device)
-    replay = [(dt, clipped) for (_, dt, _, _, clipped) in r.steplog]
-    res = em.run(replay=replay)
+    accepted = [rec for rec in r.steplog if rec[2]]
+    res = em.run(replay=[(dt, clipped) for (_, dt, _, _, clipped) in accepted])
     assert (res.states.cpu() - r.states).abs().max() < 1e-12
 
 
@@ -186,7 +186,11 @@ def test_tight_tolerance_protocol(engine_device):
     opts = dict(atol=1e-13, rtol=1e-12)
     r = p.ref().run(**opts)
     res = p.emulator(engine_device).run(**opts)
-    assert (res.states.cpu() - r.states).abs().max() < ATOL_STATE
+    # Two free-running adaptive integrators agree to the solver's own global error: at these
+    # tolerances the embedded error estimate is a difference at round-off level, so a single
+    # accept/reject decision can flip between two correct implementations.  1e-10-level claims
+    # use the shared step sequence (test_shared_step_sequence_replay).
+    assert (res.states.cpu() - r.states).abs().max() < 1e-9
 
 
 def test_errors_and_edge_cases(engine_device):
