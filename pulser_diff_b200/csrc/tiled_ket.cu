@@ -63,6 +63,67 @@ __device__ __forceinline__ size_t gindex(int type, int C, size_t tile, int e) {
   return (row << TB) + (tile << C) + col;
 }
 
+// ---- TMEM as a software-managed accumulator store ------------------------------------------
+// Each thread parks its 16 complex "z" accumulators (the v-part of the next stage input) in
+// tensor memory between phases: 64 x 32-bit columns per thread, 128 columns per CTA (two warps
+// share one 32-lane quarter), so two CTAs per SM use half of the 512 columns.  This frees 64
+// registers per thread for deeper global-load pipelining; no tensor-core math is involved.
+constexpr int kTmemCols = 128;
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem) {
+  uint32_t dst = (uint32_t)__cvta_generic_to_shared(slot_smem);
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst),
+               "r"(kTmemCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(kTmemCols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// 4 complex doubles (16 x b32) per call
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const cplx (&v)[4]) {
+  uint32_t r[16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    r[4 * i + 0] = (uint32_t)__double2loint(v[i].re);
+    r[4 * i + 1] = (uint32_t)__double2hiint(v[i].re);
+    r[4 * i + 2] = (uint32_t)__double2loint(v[i].im);
+    r[4 * i + 3] = (uint32_t)__double2hiint(v[i].im);
+  }
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+      "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, cplx (&v)[4]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, "
+      "%12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+        "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i].re = __hiloint2double((int)r[4 * i + 1], (int)r[4 * i + 0]);
+    v[i].im = __hiloint2double((int)r[4 * i + 3], (int)r[4 * i + 2]);
+  }
+}
+__device__ __forceinline__ void tmem_wait_st() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // own part of H applied to the tile in shared memory, at local element e
 template <int TYPE>
 __device__ __forceinline__ cplx apply_tile(const cplx* __restrict__ T, int e, const BitCoef& bc,
@@ -79,6 +140,9 @@ __device__ __forceinline__ cplx apply_tile(const cplx* __restrict__ T, int e, co
   return acc;
 }
 
+constexpr int GP = 4;            // elements per TMEM transfer (16 x b32)
+constexpr int NG = EPT / GP;     // 4 groups per thread
+
 template <int TYPE>
 __global__ void __launch_bounds__(NT, 2)
 k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef cprev,
@@ -87,8 +151,10 @@ k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef c
   cplx* T = reinterpret_cast<cplx*>(smem_raw);
   __shared__ cplx tab_prev[2][64], tab_next[2][64];   // detuning diagonal over local bits 0-5 / 6-11
   __shared__ double red[NT / 32];
+  __shared__ uint32_t tmem_slot;
 
   const int t = threadIdx.x;
+  const int warp = t >> 5;
   const int nq = P.nq, C = P.C;
   const size_t tiles_per_vec = P.dim >> TB;
   const size_t tile = blockIdx.x % tiles_per_vec;
@@ -97,34 +163,8 @@ k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef c
   const int nbits = TYPE == 0 ? (nq < TB ? nq : TB) : (nq - TB);
   const int lb0 = TYPE == 0 ? 0 : C, gb0 = TYPE == 0 ? 0 : TB;
 
-  cplx z[EPT];
-  // ---- phase 1a: one pass over the input vectors builds Yprev (-> smem) and the v-part of Ynext
-#pragma unroll
-  for (int i = 0; i < EPT; ++i) z[i] = {0.0, 0.0};
-  constexpr int QP = 4;   // elements per sub-pass: bounds registers (z + yp + x) under 128
-#pragma unroll
-  for (int q0 = 0; q0 < EPT; q0 += QP) {
-    cplx yp[QP];
-#pragma unroll
-    for (int i = 0; i < QP; ++i) yp[i] = {0.0, 0.0};
-    for (int j = 0; j < P.n_in; ++j) {
-      const cplx* vj = P.v[j] + boff;
-      const double wp = P.wprev[j], wn = P.wnext[j];
-      cplx x[QP];
-#pragma unroll
-      for (int i = 0; i < QP; ++i) x[i] = ldg(vj + gindex(TYPE, C, tile, t + NT * (q0 + i)));
-#pragma unroll
-      for (int i = 0; i < QP; ++i) {
-        yp[i].re = fma(wp, x[i].re, yp[i].re); yp[i].im = fma(wp, x[i].im, yp[i].im);
-        z[q0 + i].re = fma(wn, x[i].re, z[q0 + i].re);
-        z[q0 + i].im = fma(wn, x[i].im, z[q0 + i].im);
-      }
-    }
-    if (P.do_prev) {
-#pragma unroll
-      for (int i = 0; i < QP; ++i) T[t + NT * (q0 + i)] = yp[i];
-    }
-  }
+  if (warp == 0) tmem_alloc(&tmem_slot);
+
   // detuning-diagonal tables (type A): sum over local bits of (a ? t11 : t00), split 6 + 6 bits;
   // the bits above the tile are constant per tile.
   cplx hi_prev{0, 0}, hi_next{0, 0};
@@ -149,39 +189,93 @@ k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef c
       hi_next = hi_next + (a ? cnext.t11[gb] : cnext.t00[gb]);
     }
   }
+  tmem_fence_before();
+  __syncthreads();
+  tmem_fence_after();
+  // this thread's TMEM window: lane quarter of its warp, 64 columns
+  const uint32_t tbase = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+
+  // ---- phase 1a: one pass over the input vectors builds Yprev (-> smem) and the v-part of
+  //      Ynext (-> TMEM).  8 elements per sub-pass, 8 x 16 B loads in flight per thread and input.
+  constexpr int QP = 8;
+#pragma unroll
+  for (int q0 = 0; q0 < EPT; q0 += QP) {
+    cplx yp[QP], zq[QP];
+#pragma unroll
+    for (int i = 0; i < QP; ++i) { yp[i] = {0.0, 0.0}; zq[i] = {0.0, 0.0}; }
+    for (int j = 0; j < P.n_in; ++j) {
+      const cplx* vj = P.v[j] + boff;
+      const double wp = P.wprev[j], wn = P.wnext[j];
+      cplx x[QP];
+#pragma unroll
+      for (int i = 0; i < QP; ++i) x[i] = ldg(vj + gindex(TYPE, C, tile, t + NT * (q0 + i)));
+#pragma unroll
+      for (int i = 0; i < QP; ++i) {
+        yp[i].re = fma(wp, x[i].re, yp[i].re); yp[i].im = fma(wp, x[i].im, yp[i].im);
+        zq[i].re = fma(wn, x[i].re, zq[i].re); zq[i].im = fma(wn, x[i].im, zq[i].im);
+      }
+    }
+    if (P.do_prev) {
+#pragma unroll
+      for (int i = 0; i < QP; ++i) T[t + NT * (q0 + i)] = yp[i];
+    }
+#pragma unroll
+    for (int g = 0; g < QP / GP; ++g) {
+      cplx tmp[GP];
+#pragma unroll
+      for (int i = 0; i < GP; ++i) tmp[i] = zq[g * GP + i];
+      tmem_st4(tbase + (uint32_t)((q0 / GP + g) * 16), tmp);
+    }
+  }
+  tmem_wait_st();
   __syncthreads();
 
   // ---- phase 1b: finalise the previous application
   double err_acc = 0.0;
   if (P.do_prev) {
 #pragma unroll
-    for (int i = 0; i < EPT; ++i) {
-      const int e = t + NT * i;
-      const size_t g = boff + gindex(TYPE, C, tile, e);
-      cplx dsum{0, 0};
-      if (TYPE == 0) {
-        double dg = P.diag[g - boff];
-        dsum = cplx{cprev.kappa.re * dg, cprev.kappa.im * dg} + hi_prev + tab_prev[0][e & 63] +
-               tab_prev[1][(e >> 6) & 63];
+    for (int g = 0; g < NG; ++g) {
+      // prefetch this group's partial / diagonal / y0 before touching shared memory
+      cplx pp[GP], y0v[GP];
+      double dg[GP];
+#pragma unroll
+      for (int i = 0; i < GP; ++i) {
+        const int e = t + NT * (g * GP + i);
+        const size_t gi = gindex(TYPE, C, tile, e);
+        pp[i] = P.partial_prev ? ldg(P.partial_prev + boff + gi) : cplx{0.0, 0.0};
+        if (TYPE == 0) dg[i] = __ldg(P.diag + gi);
+        if (P.do_err) y0v[i] = ldg(P.v[0] + boff + gi);
       }
-      cplx o = apply_tile<TYPE>(T, e, cprev, nbits, lb0, gb0, dsum);
-      if (P.partial_prev) o = o + ldg(P.partial_prev + g);
-      P.out_prev[g] = o;
-      z[i].re = fma(P.wnext_out, o.re, z[i].re);
-      z[i].im = fma(P.wnext_out, o.im, z[i].im);
-      if (P.do_err) {
-        // here z accumulates sum_j werr_j v_j (wnext := werr, wnext_out := werr_out)
-        cplx y0 = ldg(P.v[0] + g), y1 = T[e];
-        double sc = P.atol + P.rtol * fmax(hypot(y0.re, y0.im), hypot(y1.re, y1.im));
-        double er = z[i].re / sc, ei = z[i].im / sc;
-        err_acc += er * er + ei * ei;
+      cplx zq[GP];
+      tmem_ld4(tbase + (uint32_t)(g * 16), zq);
+#pragma unroll
+      for (int i = 0; i < GP; ++i) {
+        const int e = t + NT * (g * GP + i);
+        const size_t gidx = boff + gindex(TYPE, C, tile, e);
+        cplx dsum{0, 0};
+        if (TYPE == 0)
+          dsum = cplx{cprev.kappa.re * dg[i], cprev.kappa.im * dg[i]} + hi_prev +
+                 tab_prev[0][e & 63] + tab_prev[1][(e >> 6) & 63];
+        cplx o = apply_tile<TYPE>(T, e, cprev, nbits, lb0, gb0, dsum) + pp[i];
+        P.out_prev[gidx] = o;
+        zq[i].re = fma(P.wnext_out, o.re, zq[i].re);
+        zq[i].im = fma(P.wnext_out, o.im, zq[i].im);
+        if (P.do_err) {
+          // here z accumulates sum_j werr_j v_j (wnext := werr, wnext_out := werr_out)
+          cplx y1 = T[e];
+          double sc = P.atol + P.rtol * fmax(hypot(y0v[i].re, y0v[i].im), hypot(y1.re, y1.im));
+          double er = zq[i].re / sc, ei = zq[i].im / sc;
+          err_acc += er * er + ei * ei;
+        }
       }
+      if (P.do_next) tmem_st4(tbase + (uint32_t)(g * 16), zq);
     }
+    tmem_wait_st();
   }
   if (P.do_err) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) err_acc += __shfl_xor_sync(0xffffffffu, err_acc, o);
-    if ((t & 31) == 0) red[t >> 5] = err_acc;
+    if ((t & 31) == 0) red[warp] = err_acc;
     __syncthreads();
     if (t == 0) {
       double s = 0.0;
@@ -189,30 +283,45 @@ k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef c
       P.err_partial[blockIdx.x] = s;
     }
   }
-  if (!P.do_next) return;
-
-  // ---- phase 2a: Ynext -> smem (and optionally to global: y_{n+1})
-  __syncthreads();
+  if (P.do_next) {
+    // ---- phase 2a: Ynext -> smem (and optionally to global: y_{n+1})
+    __syncthreads();
 #pragma unroll
-  for (int i = 0; i < EPT; ++i) {
-    const int e = t + NT * i;
-    T[e] = z[i];
-    if (P.ynext_out) P.ynext_out[boff + gindex(TYPE, C, tile, e)] = z[i];
-  }
-  __syncthreads();
-  // ---- phase 2b: start the next application
+    for (int g = 0; g < NG; ++g) {
+      cplx zq[GP];
+      tmem_ld4(tbase + (uint32_t)(g * 16), zq);
 #pragma unroll
-  for (int i = 0; i < EPT; ++i) {
-    const int e = t + NT * i;
-    const size_t g = boff + gindex(TYPE, C, tile, e);
-    cplx dsum{0, 0};
-    if (TYPE == 0) {
-      double dg = P.diag[g - boff];
-      dsum = cplx{cnext.kappa.re * dg, cnext.kappa.im * dg} + hi_next + tab_next[0][e & 63] +
-             tab_next[1][(e >> 6) & 63];
+      for (int i = 0; i < GP; ++i) {
+        const int e = t + NT * (g * GP + i);
+        T[e] = zq[i];
+        if (P.ynext_out) P.ynext_out[boff + gindex(TYPE, C, tile, e)] = zq[i];
+      }
     }
-    P.partial_next[g] = apply_tile<TYPE>(T, e, cnext, nbits, lb0, gb0, dsum);
+    __syncthreads();
+    // ---- phase 2b: start the next application
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      double dg[GP];
+      if (TYPE == 0) {
+#pragma unroll
+        for (int i = 0; i < GP; ++i) dg[i] = __ldg(P.diag + gindex(TYPE, C, tile, t + NT * (g * GP + i)));
+      }
+#pragma unroll
+      for (int i = 0; i < GP; ++i) {
+        const int e = t + NT * (g * GP + i);
+        const size_t gidx = boff + gindex(TYPE, C, tile, e);
+        cplx dsum{0, 0};
+        if (TYPE == 0)
+          dsum = cplx{cnext.kappa.re * dg[i], cnext.kappa.im * dg[i]} + hi_next +
+                 tab_next[0][e & 63] + tab_next[1][(e >> 6) & 63];
+        P.partial_next[gidx] = apply_tile<TYPE>(T, e, cnext, nbits, lb0, gb0, dsum);
+      }
+    }
   }
+  // ---- release tensor memory (same warp that allocated it)
+  tmem_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_slot);
 }
 
 void fill_coef(const SiteOps& so, int nq, BitCoef& bc) {
