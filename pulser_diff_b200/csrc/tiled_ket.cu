@@ -124,26 +124,155 @@ __device__ __forceinline__ void tmem_wait_st() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// own part of H applied to the tile in shared memory, at local element e
-template <int TYPE>
-__device__ __forceinline__ cplx apply_tile(const cplx* __restrict__ T, int e, const BitCoef& bc,
-                                           int nbits, int lb0, int gb0, cplx dsum) {
-  cplx acc{0.0, 0.0};
-  if (TYPE == 0) fma_acc(acc, dsum, T[e]);
-#pragma unroll 4
-  for (int b = 0; b < nbits; ++b) {
-    int lb = lb0 + b, gb = gb0 + b;
-    bool a = (e >> lb) & 1;
-    cplx c = a ? bc.t10[gb] : bc.t01[gb];
-    fma_acc(acc, c, T[e ^ (1 << lb)]);
-  }
-  return acc;
-}
-
 constexpr int GP = 4;            // elements per TMEM transfer (16 x b32)
 constexpr int NG = EPT / GP;     // 4 groups per thread
 
-template <int TYPE>
+// Own part of H applied to the tile in shared memory for the GP elements e_i = t + NT*(GP*G + i).
+// Everything about the element index that is known at compile time after unrolling (its bits
+// 8..11 come from G and i) is resolved by the compiler: partner offsets and, for those bits, the
+// coefficient choice.  Bits 0..7 come from the thread id: one select per bit and group.
+//   UNI:  all qubits share one drive coefficient (global channel): out = c10*L + c01*(S-L) with
+//         S = sum of all partners, L = sum of partners seen from a set bit -- 2-4 DADD per flip.
+constexpr int NE = 2;   // elements per apply call (register pressure: S, L, out per element)
+template <int TYPE, bool UNI, int G, int I0>
+__device__ __forceinline__ void apply_group(const cplx* __restrict__ T, int t, const BitCoef& bc,
+                                            int lb0, const cplx* dsum, cplx* out) {
+  cplx S[NE], L[NE];
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    S[i] = {0.0, 0.0};
+    L[i] = {0.0, 0.0};
+    out[i] = {0.0, 0.0};
+  }
+#pragma unroll
+  for (int lb = 0; lb < TB; ++lb) {
+    if (TYPE == 1 && lb < lb0) continue;          // uniform: type-B tiles flip local bits [C, TB)
+    const int gb = TYPE == 0 ? lb : TB + lb - lb0;
+    if (lb < 8) {
+      const bool a = (t >> lb) & 1;
+      const int tp = t ^ (1 << lb);
+      cplx c{0.0, 0.0};
+      if (!UNI) c = a ? bc.t10[gb] : bc.t01[gb];
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const cplx pv = T[tp + NT * (GP * G + I0 + i)];
+        if (UNI) {
+          S[i].re += pv.re; S[i].im += pv.im;
+          L[i].re += a ? pv.re : 0.0; L[i].im += a ? pv.im : 0.0;
+        } else {
+          fma_acc(out[i], c, pv);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        constexpr int dummy = 0; (void)dummy;
+        const int idx = GP * G + I0 + i;
+        const bool a = (idx >> (lb - 8)) & 1;                 // compile-time after unrolling
+        const cplx pv = T[t + NT * (idx ^ (1 << (lb - 8)))];
+        if (UNI) {
+          S[i].re += pv.re; S[i].im += pv.im;
+          if (a) { L[i].re += pv.re; L[i].im += pv.im; }
+        } else {
+          fma_acc(out[i], a ? bc.t10[gb] : bc.t01[gb], pv);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    if (UNI) {
+      const cplx H{S[i].re - L[i].re, S[i].im - L[i].im};
+      fma_acc(out[i], bc.t10[TYPE == 0 ? 0 : TB], L[i]);
+      fma_acc(out[i], bc.t01[TYPE == 0 ? 0 : TB], H);
+    }
+    if (TYPE == 0) fma_acc(out[i], dsum[i], T[t + NT * (GP * G + I0 + i)]);
+  }
+}
+
+// Compile-time recursion over the NG groups of a thread (group index must be a constant so that
+// apply_group resolves element bits 8..11 at compile time).
+template <int TYPE, bool UNI, int G>
+struct Phase1b {
+  static __device__ __forceinline__ void run(const TiledParams& P, const BitCoef& cprev,
+                                             const cplx* __restrict__ T, int t, size_t tile,
+                                             size_t boff, int C, int lb0, cplx hi_prev,
+                                             const cplx (*tab)[64], uint32_t tbase, double& err_acc) {
+    // prefetch this group's partial / diagonal / y0 before touching shared memory
+    cplx pp[GP], dsum[GP], o[GP];
+    size_t gi[GP];
+#pragma unroll
+    for (int i = 0; i < GP; ++i) {
+      const int e = t + NT * (G * GP + i);
+      gi[i] = gindex(TYPE, C, tile, e);
+      pp[i] = P.partial_prev ? ldg(P.partial_prev + boff + gi[i]) : cplx{0.0, 0.0};
+      if (TYPE == 0) {
+        const double dg = __ldg(P.diag + gi[i]);
+        dsum[i] = cplx{cprev.kappa.re * dg, cprev.kappa.im * dg} + hi_prev + tab[0][e & 63] +
+                  tab[1][(e >> 6) & 63];
+      }
+    }
+    cplx zq[GP];
+    tmem_ld4(tbase + (uint32_t)(G * 16), zq);
+    apply_group<TYPE, UNI, G, 0>(T, t, cprev, lb0, dsum, o);
+    apply_group<TYPE, UNI, G, 2>(T, t, cprev, lb0, dsum + 2, o + 2);
+#pragma unroll
+    for (int i = 0; i < GP; ++i) {
+      o[i] = o[i] + pp[i];
+      P.out_prev[boff + gi[i]] = o[i];
+      zq[i].re = fma(P.wnext_out, o[i].re, zq[i].re);
+      zq[i].im = fma(P.wnext_out, o[i].im, zq[i].im);
+      if (P.do_err) {
+        // here z accumulates sum_j werr_j v_j (wnext := werr, wnext_out := werr_out)
+        const cplx y1 = T[t + NT * (G * GP + i)];
+        const cplx y0 = ldg(P.v[0] + boff + gi[i]);
+        const double sc = P.atol + P.rtol * fmax(hypot(y0.re, y0.im), hypot(y1.re, y1.im));
+        const double er = zq[i].re / sc, ei = zq[i].im / sc;
+        err_acc += er * er + ei * ei;
+      }
+    }
+    if (P.do_next) tmem_st4(tbase + (uint32_t)(G * 16), zq);
+    Phase1b<TYPE, UNI, G + 1>::run(P, cprev, T, t, tile, boff, C, lb0, hi_prev, tab, tbase, err_acc);
+  }
+};
+template <int TYPE, bool UNI>
+struct Phase1b<TYPE, UNI, NG> {
+  static __device__ __forceinline__ void run(const TiledParams&, const BitCoef&, const cplx*, int,
+                                             size_t, size_t, int, int, cplx, const cplx (*)[64],
+                                             uint32_t, double&) {}
+};
+template <int TYPE, bool UNI, int G>
+struct Phase2b {
+  static __device__ __forceinline__ void run(const TiledParams& P, const BitCoef& cnext,
+                                             const cplx* __restrict__ T, int t, size_t tile,
+                                             size_t boff, int C, int lb0, cplx hi_next,
+                                             const cplx (*tab)[64]) {
+    cplx dsum[GP], o[GP];
+    size_t gi[GP];
+#pragma unroll
+    for (int i = 0; i < GP; ++i) {
+      const int e = t + NT * (G * GP + i);
+      gi[i] = gindex(TYPE, C, tile, e);
+      if (TYPE == 0) {
+        const double dg = __ldg(P.diag + gi[i]);
+        dsum[i] = cplx{cnext.kappa.re * dg, cnext.kappa.im * dg} + hi_next + tab[0][e & 63] +
+                  tab[1][(e >> 6) & 63];
+      }
+    }
+    apply_group<TYPE, UNI, G, 0>(T, t, cnext, lb0, dsum, o);
+    apply_group<TYPE, UNI, G, 2>(T, t, cnext, lb0, dsum + 2, o + 2);
+#pragma unroll
+    for (int i = 0; i < GP; ++i) P.partial_next[boff + gi[i]] = o[i];
+    Phase2b<TYPE, UNI, G + 1>::run(P, cnext, T, t, tile, boff, C, lb0, hi_next, tab);
+  }
+};
+template <int TYPE, bool UNI>
+struct Phase2b<TYPE, UNI, NG> {
+  static __device__ __forceinline__ void run(const TiledParams&, const BitCoef&, const cplx*, int,
+                                             size_t, size_t, int, int, cplx, const cplx (*)[64]) {}
+};
+
+template <int TYPE, bool UNI>
 __global__ void __launch_bounds__(NT, 2)
 k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef cprev,
         const __grid_constant__ BitCoef cnext) {
@@ -160,8 +289,7 @@ k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef c
   const size_t tile = blockIdx.x % tiles_per_vec;
   const size_t boff = (blockIdx.x / tiles_per_vec) * P.dim;     // batch column offset
   // bits this tile closes over: type A local [0,TB) = global [0,TB); type B local [C,TB) = global [TB,nq)
-  const int nbits = TYPE == 0 ? (nq < TB ? nq : TB) : (nq - TB);
-  const int lb0 = TYPE == 0 ? 0 : C, gb0 = TYPE == 0 ? 0 : TB;
+  const int lb0 = TYPE == 0 ? 0 : C;
 
   if (warp == 0) tmem_alloc(&tmem_slot);
 
@@ -197,35 +325,38 @@ k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef c
 
   // ---- phase 1a: one pass over the input vectors builds Yprev (-> smem) and the v-part of
   //      Ynext (-> TMEM).  8 elements per sub-pass, 8 x 16 B loads in flight per thread and input.
-  constexpr int QP = 8;
+  constexpr int QP = 4;   // elements per sub-pass; two input vectors per iteration: 8 loads in flight
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += QP) {
     cplx yp[QP], zq[QP];
 #pragma unroll
     for (int i = 0; i < QP; ++i) { yp[i] = {0.0, 0.0}; zq[i] = {0.0, 0.0}; }
-    for (int j = 0; j < P.n_in; ++j) {
-      const cplx* vj = P.v[j] + boff;
-      const double wp = P.wprev[j], wn = P.wnext[j];
-      cplx x[QP];
-#pragma unroll
-      for (int i = 0; i < QP; ++i) x[i] = ldg(vj + gindex(TYPE, C, tile, t + NT * (q0 + i)));
+    for (int j = 0; j < P.n_in; j += 2) {
+      const bool two = j + 1 < P.n_in;
+      const cplx* va = P.v[j] + boff;
+      const cplx* vb = P.v[two ? j + 1 : j] + boff;
+      const double wpa = P.wprev[j], wna = P.wnext[j];
+      const double wpb = two ? P.wprev[j + 1] : 0.0, wnb = two ? P.wnext[j + 1] : 0.0;
+      cplx xa[QP], xb[QP];
 #pragma unroll
       for (int i = 0; i < QP; ++i) {
-        yp[i].re = fma(wp, x[i].re, yp[i].re); yp[i].im = fma(wp, x[i].im, yp[i].im);
-        zq[i].re = fma(wn, x[i].re, zq[i].re); zq[i].im = fma(wn, x[i].im, zq[i].im);
+        const size_t gi = gindex(TYPE, C, tile, t + NT * (q0 + i));
+        xa[i] = ldg(va + gi);
+        xb[i] = ldg(vb + gi);
+      }
+#pragma unroll
+      for (int i = 0; i < QP; ++i) {
+        yp[i].re = fma(wpb, xb[i].re, fma(wpa, xa[i].re, yp[i].re));
+        yp[i].im = fma(wpb, xb[i].im, fma(wpa, xa[i].im, yp[i].im));
+        zq[i].re = fma(wnb, xb[i].re, fma(wna, xa[i].re, zq[i].re));
+        zq[i].im = fma(wnb, xb[i].im, fma(wna, xa[i].im, zq[i].im));
       }
     }
     if (P.do_prev) {
 #pragma unroll
       for (int i = 0; i < QP; ++i) T[t + NT * (q0 + i)] = yp[i];
     }
-#pragma unroll
-    for (int g = 0; g < QP / GP; ++g) {
-      cplx tmp[GP];
-#pragma unroll
-      for (int i = 0; i < GP; ++i) tmp[i] = zq[g * GP + i];
-      tmem_st4(tbase + (uint32_t)((q0 / GP + g) * 16), tmp);
-    }
+    tmem_st4(tbase + (uint32_t)((q0 / GP) * 16), zq);
   }
   tmem_wait_st();
   __syncthreads();
@@ -233,43 +364,7 @@ k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef c
   // ---- phase 1b: finalise the previous application
   double err_acc = 0.0;
   if (P.do_prev) {
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      // prefetch this group's partial / diagonal / y0 before touching shared memory
-      cplx pp[GP], y0v[GP];
-      double dg[GP];
-#pragma unroll
-      for (int i = 0; i < GP; ++i) {
-        const int e = t + NT * (g * GP + i);
-        const size_t gi = gindex(TYPE, C, tile, e);
-        pp[i] = P.partial_prev ? ldg(P.partial_prev + boff + gi) : cplx{0.0, 0.0};
-        if (TYPE == 0) dg[i] = __ldg(P.diag + gi);
-        if (P.do_err) y0v[i] = ldg(P.v[0] + boff + gi);
-      }
-      cplx zq[GP];
-      tmem_ld4(tbase + (uint32_t)(g * 16), zq);
-#pragma unroll
-      for (int i = 0; i < GP; ++i) {
-        const int e = t + NT * (g * GP + i);
-        const size_t gidx = boff + gindex(TYPE, C, tile, e);
-        cplx dsum{0, 0};
-        if (TYPE == 0)
-          dsum = cplx{cprev.kappa.re * dg[i], cprev.kappa.im * dg[i]} + hi_prev +
-                 tab_prev[0][e & 63] + tab_prev[1][(e >> 6) & 63];
-        cplx o = apply_tile<TYPE>(T, e, cprev, nbits, lb0, gb0, dsum) + pp[i];
-        P.out_prev[gidx] = o;
-        zq[i].re = fma(P.wnext_out, o.re, zq[i].re);
-        zq[i].im = fma(P.wnext_out, o.im, zq[i].im);
-        if (P.do_err) {
-          // here z accumulates sum_j werr_j v_j (wnext := werr, wnext_out := werr_out)
-          cplx y1 = T[e];
-          double sc = P.atol + P.rtol * fmax(hypot(y0v[i].re, y0v[i].im), hypot(y1.re, y1.im));
-          double er = zq[i].re / sc, ei = zq[i].im / sc;
-          err_acc += er * er + ei * ei;
-        }
-      }
-      if (P.do_next) tmem_st4(tbase + (uint32_t)(g * 16), zq);
-    }
+    Phase1b<TYPE, UNI, 0>::run(P, cprev, T, t, tile, boff, C, lb0, hi_prev, tab_prev, tbase, err_acc);
     tmem_wait_st();
   }
   if (P.do_err) {
@@ -299,24 +394,7 @@ k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef c
     }
     __syncthreads();
     // ---- phase 2b: start the next application
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      double dg[GP];
-      if (TYPE == 0) {
-#pragma unroll
-        for (int i = 0; i < GP; ++i) dg[i] = __ldg(P.diag + gindex(TYPE, C, tile, t + NT * (g * GP + i)));
-      }
-#pragma unroll
-      for (int i = 0; i < GP; ++i) {
-        const int e = t + NT * (g * GP + i);
-        const size_t gidx = boff + gindex(TYPE, C, tile, e);
-        cplx dsum{0, 0};
-        if (TYPE == 0)
-          dsum = cplx{cnext.kappa.re * dg[i], cnext.kappa.im * dg[i]} + hi_next +
-                 tab_next[0][e & 63] + tab_next[1][(e >> 6) & 63];
-        P.partial_next[gidx] = apply_tile<TYPE>(T, e, cnext, nbits, lb0, gb0, dsum);
-      }
-    }
+    Phase2b<TYPE, UNI, 0>::run(P, cnext, T, t, tile, boff, C, lb0, hi_next, tab_next);
   }
   // ---- release tensor memory (same warp that allocated it)
   tmem_fence_before();
@@ -336,15 +414,30 @@ void fill_coef(const SiteOps& so, int nq, BitCoef& bc) {
 }
 
 bool g_attr_set = false;
+bool uniform_drive(const BitCoef& a, int nq) {
+  for (int p = 1; p < nq; ++p)
+    if (a.t01[p].re != a.t01[0].re || a.t01[p].im != a.t01[0].im || a.t10[p].re != a.t10[0].re ||
+        a.t10[p].im != a.t10[0].im)
+      return false;
+  return true;
+}
 void launch(const TiledParams& P, const BitCoef& cp, const BitCoef& cn, int batch, cudaStream_t s) {
   if (!g_attr_set) {
-    PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
-    PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
     g_attr_set = true;
   }
   unsigned grid = (unsigned)((P.dim >> TB) * (size_t)batch);
-  if (P.type == 0) k_tiled<0><<<grid, NT, TILE * 16, s>>>(P, cp, cn);
-  else k_tiled<1><<<grid, NT, TILE * 16, s>>>(P, cp, cn);
+  const bool uni = uniform_drive(cp, P.nq) && uniform_drive(cn, P.nq);
+  if (P.type == 0) {
+    if (uni) k_tiled<0, true><<<grid, NT, TILE * 16, s>>>(P, cp, cn);
+    else k_tiled<0, false><<<grid, NT, TILE * 16, s>>>(P, cp, cn);
+  } else {
+    if (uni) k_tiled<1, true><<<grid, NT, TILE * 16, s>>>(P, cp, cn);
+    else k_tiled<1, false><<<grid, NT, TILE * 16, s>>>(P, cp, cn);
+  }
   PD_CUDA_CHECK(cudaGetLastError());
 }
 
