@@ -22,7 +22,11 @@ namespace {
 
 constexpr int TB = 12;            // tile = 4096 amplitudes = 64 KiB of shared memory
 constexpr int TILE = 1 << TB;
-constexpr int NT = 256;           // threads per CTA; 2 CTAs per SM
+#ifndef PD_TILED_LNT
+#define PD_TILED_LNT 9
+#endif
+constexpr int LNT = PD_TILED_LNT;  // log2(threads per CTA)
+constexpr int NT = 1 << LNT;      // threads per CTA; 2 CTAs per SM
 constexpr int EPT = TILE / NT;    // 16 amplitudes per thread
 constexpr int kMaxIn = 8;
 constexpr int kMinTiledQubits = 16;
@@ -148,7 +152,7 @@ __device__ __forceinline__ void apply_group(const cplx* __restrict__ T, int t, c
   for (int lb = 0; lb < TB; ++lb) {
     if (TYPE == 1 && lb < lb0) continue;          // uniform: type-B tiles flip local bits [C, TB)
     const int gb = TYPE == 0 ? lb : TB + lb - lb0;
-    if (lb < 8) {
+    if (lb < LNT) {
       const bool a = (t >> lb) & 1;
       const int tp = t ^ (1 << lb);
       cplx c{0.0, 0.0};
@@ -168,8 +172,8 @@ __device__ __forceinline__ void apply_group(const cplx* __restrict__ T, int t, c
       for (int i = 0; i < NE; ++i) {
         constexpr int dummy = 0; (void)dummy;
         const int idx = GP * G + I0 + i;
-        const bool a = (idx >> (lb - 8)) & 1;                 // compile-time after unrolling
-        const cplx pv = T[t + NT * (idx ^ (1 << (lb - 8)))];
+        const bool a = (idx >> (lb - LNT)) & 1;               // compile-time after unrolling
+        const cplx pv = T[t + NT * (idx ^ (1 << (lb - LNT)))];
         if (UNI) {
           S[i].re += pv.re; S[i].im += pv.im;
           if (a) { L[i].re += pv.re; L[i].im += pv.im; }
@@ -186,60 +190,74 @@ __device__ __forceinline__ void apply_group(const cplx* __restrict__ T, int t, c
       fma_acc(out[i], bc.t10[TYPE == 0 ? 0 : TB], L[i]);
       fma_acc(out[i], bc.t01[TYPE == 0 ? 0 : TB], H);
     }
-    if (TYPE == 0) fma_acc(out[i], dsum[i], T[t + NT * (GP * G + I0 + i)]);
+    (void)dsum;
   }
 }
 
 // Compile-time recursion over the NG groups of a thread (group index must be a constant so that
 // apply_group resolves element bits 8..11 at compile time).
+template <int TYPE>
+struct Pref {          // partial + static diagonal of one group, fetched one group ahead
+  cplx pp[GP];
+  double dg[GP];
+};
+template <int TYPE>
+__device__ __forceinline__ void prefetch_group(const TiledParams& P, int t, size_t tile, size_t boff,
+                                               int C, int G, Pref<TYPE>& pf) {
+#pragma unroll
+  for (int i = 0; i < GP; ++i) {
+    const size_t gi = gindex(TYPE, C, tile, t + NT * (G * GP + i));
+    pf.pp[i] = P.partial_prev ? ldg(P.partial_prev + boff + gi) : cplx{0.0, 0.0};
+    pf.dg[i] = TYPE == 0 ? __ldg(P.diag + gi) : 0.0;
+  }
+}
 template <int TYPE, bool UNI, int G>
 struct Phase1b {
   static __device__ __forceinline__ void run(const TiledParams& P, const BitCoef& cprev,
                                              const cplx* __restrict__ T, int t, size_t tile,
                                              size_t boff, int C, int lb0, cplx hi_prev,
-                                             const cplx (*tab)[64], uint32_t tbase, double& err_acc) {
-    // prefetch this group's partial / diagonal / y0 before touching shared memory
-    cplx pp[GP], dsum[GP], o[GP];
-    size_t gi[GP];
+                                             const cplx (*tab)[64], uint32_t tbase, double& err_acc,
+                                             const Pref<TYPE>& cur) {
+    Pref<TYPE> nxt;
+    if (G + 1 < NG) prefetch_group<TYPE>(P, t, tile, boff, C, G + 1, nxt);
+    cplx dsum[GP], o[GP];
+#pragma unroll
+    for (int i = 0; i < GP; ++i) dsum[i] = {0.0, 0.0};
+    apply_group<TYPE, UNI, G, 0>(T, t, cprev, lb0, dsum, o);
+    apply_group<TYPE, UNI, G, 2>(T, t, cprev, lb0, dsum + 2, o + 2);
+    cplx zq[GP];
+    tmem_ld4(tbase + (uint32_t)(G * 16), zq);
 #pragma unroll
     for (int i = 0; i < GP; ++i) {
       const int e = t + NT * (G * GP + i);
-      gi[i] = gindex(TYPE, C, tile, e);
-      pp[i] = P.partial_prev ? ldg(P.partial_prev + boff + gi[i]) : cplx{0.0, 0.0};
+      const size_t gi = boff + gindex(TYPE, C, tile, e);
       if (TYPE == 0) {
-        const double dg = __ldg(P.diag + gi[i]);
-        dsum[i] = cplx{cprev.kappa.re * dg, cprev.kappa.im * dg} + hi_prev + tab[0][e & 63] +
-                  tab[1][(e >> 6) & 63];
+        const cplx ds = cplx{cprev.kappa.re * cur.dg[i], cprev.kappa.im * cur.dg[i]} + hi_prev +
+                        tab[0][e & 63] + tab[1][(e >> 6) & 63];
+        fma_acc(o[i], ds, T[e]);
       }
-    }
-    cplx zq[GP];
-    tmem_ld4(tbase + (uint32_t)(G * 16), zq);
-    apply_group<TYPE, UNI, G, 0>(T, t, cprev, lb0, dsum, o);
-    apply_group<TYPE, UNI, G, 2>(T, t, cprev, lb0, dsum + 2, o + 2);
-#pragma unroll
-    for (int i = 0; i < GP; ++i) {
-      o[i] = o[i] + pp[i];
-      P.out_prev[boff + gi[i]] = o[i];
+      o[i] = o[i] + cur.pp[i];
+      P.out_prev[gi] = o[i];
       zq[i].re = fma(P.wnext_out, o[i].re, zq[i].re);
       zq[i].im = fma(P.wnext_out, o[i].im, zq[i].im);
       if (P.do_err) {
         // here z accumulates sum_j werr_j v_j (wnext := werr, wnext_out := werr_out)
-        const cplx y1 = T[t + NT * (G * GP + i)];
-        const cplx y0 = ldg(P.v[0] + boff + gi[i]);
+        const cplx y1 = T[e];
+        const cplx y0 = ldg(P.v[0] + gi);
         const double sc = P.atol + P.rtol * fmax(hypot(y0.re, y0.im), hypot(y1.re, y1.im));
         const double er = zq[i].re / sc, ei = zq[i].im / sc;
         err_acc += er * er + ei * ei;
       }
     }
     if (P.do_next) tmem_st4(tbase + (uint32_t)(G * 16), zq);
-    Phase1b<TYPE, UNI, G + 1>::run(P, cprev, T, t, tile, boff, C, lb0, hi_prev, tab, tbase, err_acc);
+    Phase1b<TYPE, UNI, G + 1>::run(P, cprev, T, t, tile, boff, C, lb0, hi_prev, tab, tbase, err_acc, nxt);
   }
 };
 template <int TYPE, bool UNI>
 struct Phase1b<TYPE, UNI, NG> {
   static __device__ __forceinline__ void run(const TiledParams&, const BitCoef&, const cplx*, int,
                                              size_t, size_t, int, int, cplx, const cplx (*)[64],
-                                             uint32_t, double&) {}
+                                             uint32_t, double&, const Pref<TYPE>&) {}
 };
 template <int TYPE, bool UNI, int G>
 struct Phase2b {
@@ -248,21 +266,24 @@ struct Phase2b {
                                              size_t boff, int C, int lb0, cplx hi_next,
                                              const cplx (*tab)[64]) {
     cplx dsum[GP], o[GP];
-    size_t gi[GP];
+    double dg[GP];
 #pragma unroll
     for (int i = 0; i < GP; ++i) {
-      const int e = t + NT * (G * GP + i);
-      gi[i] = gindex(TYPE, C, tile, e);
-      if (TYPE == 0) {
-        const double dg = __ldg(P.diag + gi[i]);
-        dsum[i] = cplx{cnext.kappa.re * dg, cnext.kappa.im * dg} + hi_next + tab[0][e & 63] +
-                  tab[1][(e >> 6) & 63];
-      }
+      dsum[i] = {0.0, 0.0};
+      dg[i] = TYPE == 0 ? __ldg(P.diag + gindex(TYPE, C, tile, t + NT * (G * GP + i))) : 0.0;
     }
     apply_group<TYPE, UNI, G, 0>(T, t, cnext, lb0, dsum, o);
     apply_group<TYPE, UNI, G, 2>(T, t, cnext, lb0, dsum + 2, o + 2);
 #pragma unroll
-    for (int i = 0; i < GP; ++i) P.partial_next[boff + gi[i]] = o[i];
+    for (int i = 0; i < GP; ++i) {
+      const int e = t + NT * (G * GP + i);
+      if (TYPE == 0) {
+        const cplx ds = cplx{cnext.kappa.re * dg[i], cnext.kappa.im * dg[i]} + hi_next +
+                        tab[0][e & 63] + tab[1][(e >> 6) & 63];
+        fma_acc(o[i], ds, T[e]);
+      }
+      P.partial_next[boff + gindex(TYPE, C, tile, e)] = o[i];
+    }
     Phase2b<TYPE, UNI, G + 1>::run(P, cnext, T, t, tile, boff, C, lb0, hi_next, tab);
   }
 };
@@ -272,8 +293,11 @@ struct Phase2b<TYPE, UNI, NG> {
                                              size_t, size_t, int, int, cplx, const cplx (*)[64]) {}
 };
 
+#ifndef PD_TILED_MINB
+#define PD_TILED_MINB 2
+#endif
 template <int TYPE, bool UNI>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, PD_TILED_MINB)
 k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef cprev,
         const __grid_constant__ BitCoef cnext) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -321,36 +345,41 @@ k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef c
   __syncthreads();
   tmem_fence_after();
   // this thread's TMEM window: lane quarter of its warp, 64 columns
-  const uint32_t tbase = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+  const uint32_t tbase = tmem_slot + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * (EPT * 4));
 
   // ---- phase 1a: one pass over the input vectors builds Yprev (-> smem) and the v-part of
   //      Ynext (-> TMEM).  8 elements per sub-pass, 8 x 16 B loads in flight per thread and input.
-  constexpr int QP = 4;   // elements per sub-pass; two input vectors per iteration: 8 loads in flight
+  constexpr int QP = 4;   // elements per sub-pass; four input vectors per iteration: 16 loads in flight
+  constexpr int JU = 4;
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += QP) {
     cplx yp[QP], zq[QP];
+    size_t gi[QP];
 #pragma unroll
-    for (int i = 0; i < QP; ++i) { yp[i] = {0.0, 0.0}; zq[i] = {0.0, 0.0}; }
-    for (int j = 0; j < P.n_in; j += 2) {
-      const bool two = j + 1 < P.n_in;
-      const cplx* va = P.v[j] + boff;
-      const cplx* vb = P.v[two ? j + 1 : j] + boff;
-      const double wpa = P.wprev[j], wna = P.wnext[j];
-      const double wpb = two ? P.wprev[j + 1] : 0.0, wnb = two ? P.wnext[j + 1] : 0.0;
-      cplx xa[QP], xb[QP];
+    for (int i = 0; i < QP; ++i) {
+      yp[i] = {0.0, 0.0};
+      zq[i] = {0.0, 0.0};
+      gi[i] = boff + gindex(TYPE, C, tile, t + NT * (q0 + i));
+    }
+    for (int j = 0; j < P.n_in; j += JU) {
+      cplx x[JU][QP];
+      double wp[JU], wn[JU];
 #pragma unroll
-      for (int i = 0; i < QP; ++i) {
-        const size_t gi = gindex(TYPE, C, tile, t + NT * (q0 + i));
-        xa[i] = ldg(va + gi);
-        xb[i] = ldg(vb + gi);
+      for (int u = 0; u < JU; ++u) {
+        const bool on = j + u < P.n_in;                 // uniform
+        const cplx* vu = P.v[on ? j + u : j];
+        wp[u] = on ? P.wprev[j + u] : 0.0;
+        wn[u] = on ? P.wnext[j + u] : 0.0;
+#pragma unroll
+        for (int i = 0; i < QP; ++i) x[u][i] = ldg(vu + gi[i]);
       }
 #pragma unroll
-      for (int i = 0; i < QP; ++i) {
-        yp[i].re = fma(wpb, xb[i].re, fma(wpa, xa[i].re, yp[i].re));
-        yp[i].im = fma(wpb, xb[i].im, fma(wpa, xa[i].im, yp[i].im));
-        zq[i].re = fma(wnb, xb[i].re, fma(wna, xa[i].re, zq[i].re));
-        zq[i].im = fma(wnb, xb[i].im, fma(wna, xa[i].im, zq[i].im));
-      }
+      for (int u = 0; u < JU; ++u)
+#pragma unroll
+        for (int i = 0; i < QP; ++i) {
+          yp[i].re = fma(wp[u], x[u][i].re, yp[i].re); yp[i].im = fma(wp[u], x[u][i].im, yp[i].im);
+          zq[i].re = fma(wn[u], x[u][i].re, zq[i].re); zq[i].im = fma(wn[u], x[u][i].im, zq[i].im);
+        }
     }
     if (P.do_prev) {
 #pragma unroll
@@ -358,13 +387,15 @@ k_tiled(const __grid_constant__ TiledParams P, const __grid_constant__ BitCoef c
     }
     tmem_st4(tbase + (uint32_t)((q0 / GP) * 16), zq);
   }
+  Pref<TYPE> pf0;
+  if (P.do_prev) prefetch_group<TYPE>(P, t, tile, boff, C, 0, pf0);
   tmem_wait_st();
   __syncthreads();
 
   // ---- phase 1b: finalise the previous application
   double err_acc = 0.0;
   if (P.do_prev) {
-    Phase1b<TYPE, UNI, 0>::run(P, cprev, T, t, tile, boff, C, lb0, hi_prev, tab_prev, tbase, err_acc);
+    Phase1b<TYPE, UNI, 0>::run(P, cprev, T, t, tile, boff, C, lb0, hi_prev, tab_prev, tbase, err_acc, pf0);
     tmem_wait_st();
   }
   if (P.do_err) {
