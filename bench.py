@@ -13,11 +13,13 @@ gradient pass.  Metric = DP5 evolution steps per second over forward+gradient.
 * ``value``  : passes with the register state and pulse coefficients already on the device.
 * ``e2e``    : the same pass through ``TorchEmulator.run`` from HOST tensors, loss and gradients
                read back to the host, every step.
-* ``roofline``: the HBM-bound regime of the same kernels -- one fused DP5 step at N = 26
-               (north_star's target) timed with CUDA events inside the C ABI on the launching
-               stream; algorithmic bytes 576 B x 2^N per step, 40 B x 2^N per H.psi
-               (SURVEY.md 8d).  ``roofline_workload`` is the same figure for the N = 12 workload
-               itself (64 KiB state: launch/latency bound, reported for completeness).
+* ``roofline``: the HBM-bound regime of the same kernels -- one fused DP5 step at N = 23
+               (128 MiB vectors, the largest register the tiled kernel family covers today)
+               timed with CUDA events inside the C ABI on the launching stream; algorithmic
+               bytes 576 B x 2^N per step, 40 B x 2^N per H.psi.
+               ``roofline_n26`` is the same step at north_star's N = 26 (1 GiB vectors, gather
+               kernels); ``roofline_workload`` is the figure for the N = 12 workload itself
+               (64 KiB state: launch/latency bound, reported for completeness).
 * ``cpu_baseline``: the oracle (restated reference CPU path: sparse-COO H(t) re-assembly, DP5,
                tape autograd) on a bounded sample of the same workload.
 """
@@ -205,37 +207,41 @@ def run_b200(args):
     t_e2e = time.perf_counter() - t0
 
     # ---- roofline: the HBM-bound regime, N = roofline_n, CUDA events inside the C ABI ----
-    roof = roof_h = None
+    roof = roof_h = roof26 = None
     peak, peak_src = measured_peak()
     if rank == 0 and args.roofline_n > 0:
-        nr = args.roofline_n
-        ops.clear_plan_cache()
-        big = _cabi.Plan(nr, 1, _cabi.PD_KET, dev)
-        cu = torch.zeros(nr, nr, dtype=torch.float64)
-        cc = chain_coords(nr)
-        for i in range(nr):
-            for j in range(i + 1, nr):
-                cu[i, j] = C6 / float(torch.linalg.norm(cc[i] - cc[j])) ** 6
-        big.set_interaction(cu)
-        big.set_terms(H.dt, dm, dv, am, av)
-        y = torch.zeros(1, 2 ** nr, dtype=torch.complex128, device=dev)
-        y[0, -1] = 1.0
-        ms_step = big.bench_dp5_steps(0.3, 1e-3, args.roofline_steps, y)
-        psi = torch.randn(1, 2 ** nr, dtype=torch.float64, device=dev).to(torch.complex128)
-        ms_h = big.bench_hpsi(0.3, psi, max(4, args.roofline_steps * 3))
-        s_amp = 2 ** nr
-        ach = 576.0 * s_amp / (ms_step * 1e-3) / 1e9
-        ach_h = 40.0 * s_amp / (ms_h * 1e-3) / 1e9
-        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
-                "kernel": "fused DP5 step (6 generator applications + stage combines + error norm)",
-                "workload": f"chain_n{nr}_dp5_step", "ms_per_launch": ms_step,
-                "algorithmic_bytes": 576.0 * s_amp, "steps_per_s": 1e3 / ms_step}
-        roof_h = {"bound": "hbm", "achieved": ach_h, "peak": peak, "unit": "GB/s", "frac": ach_h / peak,
+        def measure(nr):
+            ops.clear_plan_cache()
+            big = _cabi.Plan(nr, 1, _cabi.PD_KET, dev)
+            cu = torch.zeros(nr, nr, dtype=torch.float64)
+            for i in range(nr):
+                for j in range(i + 1, nr):
+                    cu[i, j] = C6 / (SPACING * (j - i)) ** 6
+            big.set_interaction(cu)
+            big.set_terms(H.dt, dm, dv, am, av)
+            y = torch.zeros(1, 2 ** nr, dtype=torch.complex128, device=dev)
+            y[0, -1] = 1.0
+            ms_step = big.bench_dp5_steps(0.3, 1e-3, args.roofline_steps, y)
+            psi = torch.randn(1, 2 ** nr, dtype=torch.float64, device=dev).to(torch.complex128)
+            ms_h = big.bench_hpsi(0.3, psi, max(4, args.roofline_steps * 3))
+            s_amp = 2 ** nr
+            ach = 576.0 * s_amp / (ms_step * 1e-3) / 1e9
+            ach_h = 40.0 * s_amp / (ms_h * 1e-3) / 1e9
+            family = "tiled (smem + TMEM, alternating tile types)" if 18 <= nr <= 23 else "gather"
+            r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                 "traffic": None, "peak_source": peak_src,
+                 "kernel": "fused DP5 step (6 generator applications + stage combines + error norm)",
+                 "kernel_family": family, "workload": f"chain_n{nr}_dp5_step", "ms_per_launch": ms_step,
+                 "algorithmic_bytes": 576.0 * s_amp, "steps_per_s": 1e3 / ms_step}
+            rh = {"bound": "hbm", "achieved": ach_h, "peak": peak, "unit": "GB/s", "frac": ach_h / peak,
                   "traffic": None, "kernel": "H(t) psi", "workload": f"chain_n{nr}_hpsi",
                   "ms_per_launch": ms_h, "algorithmic_bytes": 40.0 * s_amp}
-        del big, y, psi
-        torch.cuda.empty_cache()
+            del big, y, psi
+            torch.cuda.empty_cache()
+            return r, rh
+        roof, roof_h = measure(args.roofline_n)
+        if args.roofline_n != 26 and not args.skip_n26:
+            roof26, _ = measure(26)
     clocks = sampler.summary()
 
     # max over ranks
@@ -268,12 +274,12 @@ def run_b200(args):
                        "n_params": 2 * N_PARAM, "dp5_steps_per_pass": n_steps,
                        "parameter_sets": world, "parallelism": f"independent parameter sets x{world}",
                        "l2": "state (64 KiB) is smaller than L2 by construction of the workload; "
-                             "the roofline block uses N=26 (1 GiB vectors, >> 126 MB L2)"},
+                             "the roofline blocks use N=23 / N=26 (128 MiB / 1 GiB vectors, >> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_pass": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": roof, "roofline_hpsi": roof_h,
+            "roofline": roof, "roofline_hpsi": roof_h, "roofline_n26": roof26,
             "roofline_workload": {"bound": "latency", "achieved": 576.0 * s12 * total_steps / world / t_res / 1e9 * 3,
                                   "peak": peak, "unit": "GB/s",
                                   "note": "N=12: 64 KiB vectors live in L2; 3x = fwd + recompute + adjoint"},
@@ -405,6 +411,7 @@ def main():
     ap.add_argument("--roofline-n", type=int, default=23)
     ap.add_argument("--roofline-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-n26", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--workload", default="c2", choices=["c2", "sharded"])
     ap.add_argument("--local-qubits", type=int, default=26)

@@ -219,3 +219,53 @@ def test_errors_and_edge_cases(engine_device):
     p1 = random_problem(1, seed=1, grad=False, T=100)
     r1 = p1.ref().run()
     assert (p1.emulator(engine_device).run().states.cpu() - r1.states).abs().max() < ATOL_STATE
+
+
+def test_quantum_model_training_step(engine_device):
+    """docs/basic_usage.ipynb section 2.1 in miniature: K-B sequence, train omega/area towards a
+    target <sum Z>; one optimiser step must match the same step taken with oracle gradients."""
+    from pulser_diff_b200.model import QuantumModel
+    from pulser_diff_b200.samples import (PulseBuilder, SequenceSamples, blackman_waveform,
+                                          constant_waveform, ramp_waveform)
+    from oracle import ref_pulses as RP
+
+    def sample_fn(p):
+        b = PulseBuilder()
+        b.add(constant_waveform(200, p["omega"]), constant_waveform(200, 0.0), 0.0)
+        b.add(blackman_waveform(160, p["area"]), ramp_waveform(160, 5.0, 0.0), 0.0)
+        return SequenceSamples([b.build()])
+
+    reg = {"q0": torch.tensor([-4.0, 0.0]), "q1": torch.tensor([4.0, 0.0])}
+    params = {"omega": torch.tensor(5.0, dtype=torch.float64), "area": torch.tensor(math.pi, dtype=torch.float64)}
+    model = QuantumModel(reg, pdb.MockDevice, sample_fn, params, {"omega": {"min": 4.5, "max": 5.5}},
+                         sampling_rate=0.5, solver=pdb.SolverType.DP5_SE, torch_device=engine_device)
+    assert sorted(n for n, _ in model.named_parameters()) == ["seq_param_values.area",
+                                                              "seq_param_values.omega"]
+    _, ev = model.expectation(total_magnetization_diag(2))
+    loss = (ev.real[-1] + 0.5) ** 2
+    loss.backward()
+    # oracle gradients of the same loss
+    om = torch.tensor(5.0, dtype=torch.float64, requires_grad=True)
+    ar = torch.tensor(math.pi, dtype=torch.float64, requires_grad=True)
+    ch = global_channel_ref(om, ar)
+    ref = Problem(torch.tensor([[-4.0, 0.0], [4.0, 0.0]], dtype=torch.float64), 5420158.53, [ch], rate=0.5).ref()
+    r = ref.run()
+    lr = (ref_expect(ref_totmag(2), r.states).real[-1] + 0.5) ** 2
+    g_om, g_ar = torch.autograd.grad(lr, [om, ar])
+    assert abs(loss.item() - lr.item()) < 1e-10
+    assert abs(model.seq_param_values["omega"].grad.item() - g_om.item()) < RTOL_GRAD * abs(g_om.item())
+    assert abs(model.seq_param_values["area"].grad.item() - g_ar.item()) < RTOL_GRAD * abs(g_ar.item())
+    with torch.no_grad():
+        model.seq_param_values["omega"] += 10.0
+    model.check_constraints()
+    assert model.seq_param_values["omega"].item() == 5.5
+    model.update_sequence()
+    assert abs(model.built_samples.channels[0].amp[0].item() - 5.5) < 1e-15
+
+
+def global_channel_ref(om, ar):
+    from helpers import Channel
+    from oracle import ref_pulses as RP
+    amp = torch.cat([RP.constant(200, om), RP.blackman(160, ar)])
+    det = torch.cat([RP.constant(200, 0.0), RP.ramp(160, 5.0, 0.0)])
+    return Channel(amp, det, torch.zeros(360, dtype=torch.float64))
