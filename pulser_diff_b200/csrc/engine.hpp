@@ -37,6 +37,8 @@ struct Tape {
   // Krylov: per interval and column, the Lanczos data needed by the adjoint
   struct KrylovSeg { int interval; double delta; double t_eval; };
   std::vector<KrylovSeg> ksegs;
+  // identity of the device-side stage tape recorded by the small-register forward sweep (0 = none)
+  uint64_t small_gen = 0;
 };
 
 template <class BK>
@@ -131,6 +133,7 @@ class Engine {
       throw Error(PD_ERR_INVALID, "solver does not match the plan kind (DP5_ME <=> density)");
     if (tape) {
       tape->records.clear(); tape->steps.clear(); tape->ksegs.clear();
+      tape->small_gen = 0;
       tape->tsave.assign(tsave, tsave + n_t);
       tape->solver = solver;
       tape->opt = opt;
@@ -313,6 +316,20 @@ class Engine {
     bool replay = o.n_replay > 0;
     double dt = replay ? 0.0 : init_tstep(t, y, k[0], o, stream);
     double error = 1.0;
+    if (use_small()) {
+      // whole evolution in one cluster kernel (small_ket.cu); the attempt log becomes the tape
+      std::vector<pd_step_record> recs;
+      uint64_t gen = 0;
+      launches += bk.small_forward(geo, prog, tab, o, y, k[0], dt, tsave, n_t, states, recs, tape != nullptr,
+                                   &gen, stream);
+      if (tape) {
+        tape->small_gen = gen;
+        for (const auto& r : recs)
+          if (r.accepted) tape->steps.push_back({r.t, r.dt, r.interval, r.clipped});
+        tape->records = std::move(recs);
+      }
+      return;
+    }
     int64_t pos = 0;
     double* d_err = (double*)buf("norm_out", sizeof(double) * geo.batch);
     std::vector<double> h_err(geo.batch);
@@ -364,6 +381,9 @@ class Engine {
     int n_t = (int)tape.tsave.size();
     size_t n_steps = tape.steps.size();
     vec lam = vbuf("lam");
+    if (use_small() &&
+        backward_dp5_small(tape, states, gstates, g_det, g_amp, g_pair, g_tsave, g_state0, want_coef, stream))
+      return;
     if (gstates) bk.d2d(lam, gstates + (size_t)(n_t - 1) * L, sizeof(cplx) * L, stream);
     else bk.zero(lam, sizeof(cplx) * L, stream);
     vec k[6], yb[6];
@@ -457,6 +477,96 @@ class Engine {
       bk.d2h(g_pair, d_pair, sizeof(double) * (size_t)prog.nq * prog.nq, stream);
     }
     bk.sync(stream);
+  }
+
+  // ---- small-register family (one cluster kernel per sweep) ----------------------------------
+  bool use_small() {
+    if (prog.kind != PD_KET || !(bk.path == 0 || bk.path == 3)) return false;
+    bool ok = bk.small_supported(geo, prog);
+    if (bk.path == 3 && !ok) throw Error(PD_ERR_INVALID, "path 3 (small-register kernels) does not fit this plan");
+    return ok;
+  }
+  bool backward_dp5_small(Tape& tape, const cplx* states, const cplx* gstates, double* g_det,
+                          double* g_amp, double* g_pair, double* g_tsave, cplx* g_state0,
+                          bool want_coef, void* stream) {
+    int n_t = (int)tape.tsave.size();
+    int n_steps = (int)tape.steps.size();
+    std::vector<double> st_t(n_steps), st_dt(n_steps);
+    std::vector<int> st_i(n_steps), st_c(n_steps);
+    for (int i = 0; i < n_steps; ++i) {
+      st_t[i] = tape.steps[i].t; st_dt[i] = tape.steps[i].dt;
+      st_i[i] = tape.steps[i].interval; st_c[i] = tape.steps[i].clipped;
+    }
+    vec lam = vbuf("lam");
+    double* d_wacc = nullptr;
+    if (g_pair) {
+      d_wacc = (double*)buf("wacc", sizeof(double) * ((size_t)1 << geo.nq));
+      bk.zero(d_wacc, sizeof(double) * ((size_t)1 << geo.nq), stream);
+    }
+    std::vector<double> sums;
+    int nl = bk.small_backward(geo, prog, tab, tape.tsave, st_t.data(), st_dt.data(), st_i.data(),
+                               st_c.data(), n_steps, tape.small_gen, gstates, want_coef, d_wacc, lam, sums,
+                               stream);
+    if (nl == 0) return false;
+    launches += nl;
+    if (g_state0) bk.d2d(g_state0, lam, sizeof(cplx) * L, stream);
+    if (want_coef && n_steps > 0) {
+      size_t nred = (size_t)prog.n_det() + 2 * (size_t)prog.n_amp() + 1;
+      std::vector<double> tbar_interval(n_t, 0.0), hbar_interval(n_t, 0.0);
+      for (int gi = 0; gi < n_steps; ++gi) {
+        const AcceptedStep& st = tape.steps[gi];
+        for (int i = 0; i < 6; ++i) {
+          double alpha = i == 0 ? 0.0 : tab.alpha[i - 1];
+          double ts = st.t + st.dt * alpha;
+          const double* sm = &sums[((size_t)gi * 6 + i) * nred];
+          double tbar = distribute_terms(ts, sm, g_det, g_amp);
+          tbar_interval[st.interval] += tbar;
+          if (st.clipped) hbar_interval[st.interval] += alpha * tbar + (g_tsave ? sm[nred - 1] / st.dt : 0.0);
+        }
+      }
+      if (g_tsave)
+        for (int kk = 1; kk < n_t; ++kk) {
+          g_tsave[kk] += hbar_interval[kk];
+          g_tsave[kk - 1] += tbar_interval[kk] - hbar_interval[kk];
+        }
+    }
+    if (g_pair) {
+      double* d_pair = (double*)buf("pair_out", sizeof(double) * (size_t)prog.nq * prog.nq);
+      launches += bk.pair_reduce(geo, d_pair, d_wacc, stream);
+      bk.d2h(g_pair, d_pair, sizeof(double) * (size_t)prog.nq * prog.nq, stream);
+    }
+    bk.sync(stream);
+    return true;
+  }
+  // Per-term sums of one slot (det: sum_q gd_q, amp: sum_q ga_q / gb_q) -> sample / time gradients.
+  double distribute_terms(double ts, const double* sums, double* g_det, double* g_amp) const {
+    int ns = prog.n_samples, n_det = prog.n_det();
+    if (ns < 2) return 0.0;
+    Interp ix = interp_index(ts, prog.dt, ns);
+    double x = (ts - ix.i1 * prog.dt) / prog.dt;
+    double tbar = 0.0;
+    for (int kdx = 0; kdx < n_det; ++kdx) {
+      double g = 2.0 * sums[kdx];
+      const double* v = &prog.det_values[(size_t)kdx * ns];
+      if (g_det) {
+        g_det[(size_t)kdx * ns + ix.i1] += g * (1.0 - x);
+        g_det[(size_t)kdx * ns + ix.i2] += g * x;
+      }
+      tbar += g * (v[ix.i2] - v[ix.i1]) / prog.dt;
+    }
+    for (int kdx = 0; kdx < prog.n_amp(); ++kdx) {
+      double gre = sums[n_det + 2 * kdx], gim = sums[n_det + 2 * kdx + 1];
+      const double* v = &prog.amp_values[(size_t)kdx * ns * 2];
+      if (g_amp) {
+        double* o1 = &g_amp[((size_t)kdx * ns + ix.i1) * 2];
+        double* o2 = &g_amp[((size_t)kdx * ns + ix.i2) * 2];
+        o1[0] += gre * (1.0 - x); o1[1] += gim * (1.0 - x);
+        o2[0] += gre * x;         o2[1] += gim * x;
+      }
+      tbar += gre * (v[2 * ix.i2] - v[2 * ix.i1]) / prog.dt +
+              gim * (v[2 * ix.i2 + 1] - v[2 * ix.i1 + 1]) / prog.dt;
+    }
+    return tbar;
   }
 
   // y_out = DP5 step from y_in (no error estimate); leaves k[0..5] filled

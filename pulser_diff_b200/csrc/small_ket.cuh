@@ -1,0 +1,655 @@
+// Small-register ket kernels: the launch-bound regime (N <= 15, state resident in registers/L2).
+//
+// For a 12-qubit register one state vector is 64 KiB: stage-by-stage launches spend their time in
+// launch latency and host round trips (98k launches / 90 ms for one forward+gradient pass of the
+// C2 workload, profiles/r01_launch_shares_bench.md).  Here the WHOLE adaptive Dormand-Prince
+// evolution (reference call: pyqtorch.sesolve behind backend.py:488-494; controller of SURVEY.md
+// Appendix A.3) and the WHOLE discrete-adjoint sweep (reference: the autograd tape,
+// derivative.py:40,76) each run as ONE cooperative kernel launch:
+//
+//   * a vector of L complex amplitudes is 2L real "lanes"; thread r owns double r of every vector
+//     (y, k1..k7 forward; lambda and the six stage adjoints backward) in REGISTERS across stages
+//     and steps, so every Runge-Kutta combination is a scalar FMA chain on private data;
+//   * a stage input is published to an L2-resident exchange buffer as flag-in-data lines and the
+//     N bit-flip partners are polled from it: no kernel boundary, no barrier and no memory fence
+//     between stages (a release fence alone costs ~2 us here); one exchange = one L2 round trip;
+//   * many small CTAs (128 threads, one warp per scheduler) spread the lanes over the chip: the
+//     per-stage critical path is one warp's ~100 instructions plus the L2 round trip;
+//   * the pulse coefficients d_q(t), g_q(t) are interpolated on the device at every stage time
+//     with the reference's rule (hamiltonian.py:532-542, quirk included);
+//   * the step controller runs redundantly in every thread on the same reduced error norm, so
+//     accept/reject decisions are uniform without a broadcast; the attempted-step log is written
+//     by one thread and becomes the host tape (pd_step_record);
+//   * the forward sweep records, per accepted step, the six stage inputs and slopes on a device
+//     tape (what the reference's autograd tape stores); the adjoint sweep reads it back instead of
+//     recomputing, and reduces per stage the per-term gradient sums for the host to scatter onto
+//     the sample arrays.
+#pragma once
+#include "cuda_backend.cuh"
+
+namespace pd {
+namespace sk {
+
+constexpr int SK_T = 128;          // threads per CTA: one warp per scheduler
+constexpr int SK_MAXQ = 16;        // qubits handled by this family
+constexpr int SK_MAXTERMS = 24;    // n_det, n_amp each
+constexpr int SK_MAXB = 32;        // batch columns
+constexpr int SK_MAXC = 296;       // co-resident CTAs of one cooperative launch (two per SM)
+
+struct SkProg {
+  int nq, n_samples, n_det, n_amp;
+  double dt;
+  const unsigned long long* det_masks;
+  const double* det_values;   // [n_det][n_samples]
+  const unsigned long long* amp_masks;
+  const double* amp_values;   // [n_amp][n_samples][2]
+  const double* diag;         // Dint[2^nq]
+};
+
+struct SkTab {
+  double alpha[6];
+  double beta[6][6];
+  double b5[7];
+  double eb[7];   // b5 - b4
+};
+
+// ---- flag-in-data exchange ("LL" lines) -----------------------------------------------------
+// Every published double travels as one 16-byte line {lo, seq, hi, seq}: the 32-bit sequence number
+// of the exchange phase is interleaved with the payload, each (payload, flag) pair is an aligned
+// 8-byte unit and therefore never torn, and a reader simply re-reads until both flags carry the
+// phase it waits for.  Lines are double-buffered by phase parity: a lane's slot is only read by
+// lanes of its partner elements, and when the element has received phase n+1 from all of them
+// they have all consumed its phase n line, so the slot can take phase n+2.
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned seq) {
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(lo), "r"(seq), "r"(hi), "r"(seq)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned ll_bad(const uint4& v, unsigned seq) { return (v.y ^ seq) | (v.w ^ seq); }
+__device__ __forceinline__ double ll_value(const uint4& v) { return __hiloint2double((int)v.z, (int)v.x); }
+
+// Bounded polling: a lane that waits longer than ~seconds raises the launch-wide abort flag, and
+// every poll loop leaves as soon as it sees the flag, so a protocol error surfaces as an error code
+// instead of a hung device.
+struct SkPoll {
+  int* abort_flag;
+  unsigned spins = 0;
+  __device__ __forceinline__ bool give_up() {
+    if ((++spins & 1023u) != 0) return false;
+    if (*(volatile int*)abort_flag) return true;
+    if (spins > (1u << 24)) { *(volatile int*)abort_flag = 1; return true; }
+    return false;
+  }
+};
+
+// per-bit coefficients of one stage time in shared memory (bit position p = nq-1-q)
+struct SkCoef {
+  double d[SK_MAXQ];
+  double gre[SK_MAXQ];
+  double gim[SK_MAXQ];
+  int uniform;      // every qubit carries the same d and g (global channels only)
+  int pad;
+};
+
+// Thread (stage i, qubit q) evaluates the reference interpolation rule (hamiltonian.py:532-542)
+// at that stage's time; all stage times of a step are known when the step starts.
+__device__ __forceinline__ void sk_eval_one(const SkProg& P, double t, SkCoef* c, int q) {
+  const int ns = P.n_samples;
+  double d = 0.0, gre = 0.0, gim = 0.0;
+  if (ns >= 2) {
+    const double fl = floor(t / P.dt);
+    long i1 = (long)fmin(fl, (double)(ns - 2));
+    if (i1 < 0) i1 = 0;
+    long i2 = i1 + 1 < (long)(ns - 2) ? i1 + 1 : (long)(ns - 2);
+    if (i2 < 0) i2 = 0;
+    const double x = (t - i1 * P.dt) / P.dt;
+    for (int k = 0; k < P.n_det; ++k)
+      if (P.det_masks[k] >> q & 1ull) {
+        const double* v = P.det_values + (size_t)k * ns;
+        const double cc = v[i1] + (v[i2] - v[i1]) * x;
+        d += cc + cc;
+      }
+    for (int k = 0; k < P.n_amp; ++k)
+      if (P.amp_masks[k] >> q & 1ull) {
+        const double* v = P.amp_values + (size_t)k * ns * 2;
+        gre += v[2 * i1] + (v[2 * i2] - v[2 * i1]) * x;
+        gim += v[2 * i1 + 1] + (v[2 * i2 + 1] - v[2 * i1 + 1]) * x;
+      }
+  }
+  const int p = P.nq - 1 - q;
+  c->d[p] = d;
+  c->gre[p] = gre;
+  c->gim[p] = gim;
+}
+// times[i] for i in [0, 6): coefficient set i.  Two __syncthreads inside.
+__device__ __forceinline__ void sk_eval_stages(const SkProg& P, const double* times, SkCoef* c, int tid) {
+  for (int w = tid; w < 6 * P.nq; w += SK_T) sk_eval_one(P, times[w / P.nq], &c[w / P.nq], w % P.nq);
+  __syncthreads();
+  if (tid < 6) {
+    int u = 1;
+    for (int p = 1; p < P.nq; ++p)
+      u &= (c[tid].d[p] == c[tid].d[0]) & (c[tid].gre[p] == c[tid].gre[0]) & (c[tid].gim[p] == c[tid].gim[0]);
+    c[tid].uniform = u;
+  }
+  __syncthreads();
+}
+
+// Copies the pulse tables into shared memory when they fit (the per-stage interpolation then costs
+// shared-memory latency instead of dependent L2 round trips) and repoints the program at them.
+constexpr int SK_TABLE_BYTES = 32 * 1024;
+__device__ __forceinline__ void sk_cache_tables(SkProg& P, unsigned char* tab_smem, int tid) {
+  const size_t ndv = (size_t)P.n_det * P.n_samples, nav = (size_t)P.n_amp * P.n_samples * 2;
+  const size_t need = (ndv + nav + P.n_det + P.n_amp) * 8;
+  if (need > SK_TABLE_BYTES) return;    // uniform
+  double* dv = reinterpret_cast<double*>(tab_smem);
+  double* av = dv + ndv;
+  unsigned long long* dm = reinterpret_cast<unsigned long long*>(av + nav);
+  unsigned long long* am = dm + P.n_det;
+  for (size_t i = tid; i < ndv; i += SK_T) dv[i] = P.det_values[i];
+  for (size_t i = tid; i < nav; i += SK_T) av[i] = P.amp_values[i];
+  for (int i = tid; i < P.n_det; i += SK_T) dm[i] = P.det_masks[i];
+  for (int i = tid; i < P.n_amp; i += SK_T) am[i] = P.amp_masks[i];
+  __syncthreads();
+  P.det_values = dv; P.amp_values = av; P.det_masks = dm; P.amp_masks = am;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- one lane of one application of H ---------------------------------------------------------
+// Lane r = 2*element + part (part 0 = real, 1 = imaginary).  The two lanes of an element split the
+// partners by parity of the bit position (NH = NQG/2 partners each): a lane polls its partner
+// lines, accumulates BOTH parts of H Y over them and the halves are combined with one shuffle.
+//
+//   part 0 gets (-i H Y).re =  (H Y).im ;  part 1 gets (-i H Y).im = -(H Y).re
+//   (+i H Y, the adjoint generator, is the negative of both.)
+//
+// Thread constants (SkLane): byte offsets of the partner lines and the bit pattern of the element.
+template <int NH>
+struct SkLane {
+  unsigned eoff;          // byte offset of the element's pair of lines (32 B per element)
+  unsigned xm[NH];        // XOR masks on eoff selecting partner j (bit position 2j + part)
+  unsigned bits;          // basis-state bits of the element
+  int part, jmax;         // jmax partners are real (bit position < nq)
+  int nzero;              // number of zero (Rydberg) bits: multiplies a uniform detuning
+  double dint;
+};
+template <int NH>
+__device__ __forceinline__ void sk_lane_init(SkLane<NH>& ln, size_t e, size_t dim, int nq, int part, double dint) {
+  ln.eoff = (unsigned)e * 32u;
+  ln.bits = (unsigned)(e & (dim - 1));
+  ln.part = part;
+  ln.jmax = nq > part ? (nq - part + 1) / 2 : 0;
+  if (ln.jmax > NH) ln.jmax = NH;
+#pragma unroll
+  for (int j = 0; j < NH; ++j) ln.xm[j] = 32u << (2 * j + part);
+  ln.nzero = nq - __popc(ln.bits);
+  ln.dint = dint;
+}
+template <int NH>
+struct SkStageCoef {
+  double dsum;
+  double gre[NH], gim[NH];   // gim carries the sign of the element's bit (conj for Rydberg)
+};
+template <int NH>
+__device__ __forceinline__ void sk_stage_coef(SkStageCoef<NH>& o, const SkLane<NH>& ln, const SkCoef& c, int nq) {
+  if (c.uniform) {
+    const double gre = c.gre[0], gim = c.gim[0];
+    o.dsum = fma(c.d[0], (double)ln.nzero, ln.dint);
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+      const bool a = (ln.bits >> (2 * j + ln.part)) & 1;
+      o.gre[j] = gre;
+      o.gim[j] = a ? gim : -gim;
+    }
+  } else {
+    double dsum = ln.dint;
+    for (int p = 0; p < nq; ++p) dsum += ((ln.bits >> p) & 1) ? 0.0 : c.d[p];
+    o.dsum = dsum;
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+      const int p = 2 * j + ln.part;
+      const bool a = (ln.bits >> p) & 1;
+      const double gim = p < nq ? c.gim[p] : 0.0;
+      o.gre[j] = p < nq ? c.gre[p] : 0.0;
+      o.gim[j] = a ? gim : -gim;
+    }
+  }
+}
+// value of the lane for -iH (negate for +iH); `other` = the element's other part of Y.
+// buf: LL lines of the published vector, two consecutive lines (re, im) per element.
+template <int NH>
+__device__ __forceinline__ double sk_apply_lane(const SkStageCoef<NH>& sc, const SkLane<NH>& ln, double other,
+                                                const uint4* __restrict__ buf, unsigned seq, bool active,
+                                                int* abort_flag) {
+  double sre0 = 0.0, sim0 = 0.0, sre1 = 0.0, sim1 = 0.0;
+  if (active) {
+    const char* base = reinterpret_cast<const char*>(buf);
+    uint4 lr[NH], li[NH];
+    unsigned bad;
+    SkPoll poll{abort_flag};
+    do {
+#pragma unroll
+      for (int j = 0; j < NH; ++j)
+        if (j < ln.jmax) {
+          const unsigned off = ln.eoff ^ ln.xm[j];
+          lr[j] = ll_load(base + off);
+          li[j] = ll_load(base + off + 16);
+        }
+      bad = 0;
+#pragma unroll
+      for (int j = 0; j < NH; ++j)
+        if (j < ln.jmax) bad |= ll_bad(lr[j], seq) | ll_bad(li[j], seq);
+    } while (bad != 0 && !poll.give_up());
+#pragma unroll
+    for (int j = 0; j < NH; ++j)
+      if (j < ln.jmax) {
+        const double pre = ll_value(lr[j]), pim = ll_value(li[j]);
+        // (H Y).re += g.re*pv.re - gim*pv.im ;  (H Y).im += g.re*pv.im + gim*pv.re
+        sre0 = fma(sc.gre[j], pre, sre0); sre1 = fma(-sc.gim[j], pim, sre1);
+        sim0 = fma(sc.gre[j], pim, sim0); sim1 = fma(sc.gim[j], pre, sim1);
+      }
+  }
+  const double sre = sre0 + sre1, sim = sim0 + sim1;
+  // part 0 needs (H Y).im, part 1 needs (H Y).re: hand the other lane the half it is missing
+  const double give = ln.part == 0 ? sre : sim;
+  const double recv = __shfl_xor_sync(0xffffffffu, give, 1);
+  const double mine = (ln.part == 0 ? sim : sre) + recv;
+  const double h = fma(sc.dsum, other, mine);
+  return ln.part == 0 ? h : -h;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward: whole adaptive evolution
+// ------------------------------------------------------------------------------------------
+struct SkResume {
+  double t, dt, error, cache_dt, cache_err;
+  long long steps_in_interval, pos;
+  int kk, in_interval, n_rec, status;   // status: 0 done, 1 log full (relaunch), 2 max_steps, 3 non-finite,
+                                        //         4 replay short, 5 exchange poll timed out
+  int n_acc, tape_ok;                   // accepted steps so far; 0 once the stage tape overflowed
+};
+
+struct SkFwd {
+  SkProg prog;
+  SkTab tab;
+  int batch, nC;
+  size_t dim, L;
+  double atol, rtol, safety, minf, maxf;
+  long long max_steps;
+  int n_replay;
+  const double* replay_dt;
+  const unsigned char* replay_clipped;
+  const double* tsave;
+  int n_t;
+  cplx* y_io;       // [L]   resume state
+  cplx* k0_io;      // [L]
+  cplx* states;     // [n_t][L]
+  uint4* YS;        // [2][2L] LL lines: stage exchange (zeroed by the host before each launch)
+  uint4* red;       // [2][nC][batch] LL lines: error-norm partial sums
+  pd_step_record* log;
+  int log_cap;
+  SkResume* resume;
+  // stage tape for the adjoint sweep (null = not recorded): per ACCEPTED step the six stage
+  // inputs Y_1..Y_6 (Y_1 = y_n) and the six slopes k_1..k_6, [step][6][2L] doubles each
+  double* tapeY;
+  double* tapeK;
+  int tape_cap;     // steps
+  int* abort_flag;  // zeroed by the host; set by a lane whose poll timed out
+};
+
+template <int NQG>
+__global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ SkFwd P) {
+  constexpr int NH = NQG / 2;
+  __shared__ SkCoef coef[6];
+  __shared__ double s_red[SK_T / 32][SK_MAXB];
+  __shared__ double s_err[SK_MAXB];
+  __shared__ double s_times[6];
+  __shared__ double s_fac;
+  __shared__ __align__(16) unsigned char s_tab[SK_TABLE_BYTES];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int part = tid & 1;
+  const unsigned cta = blockIdx.x;
+  const int nq = P.prog.nq;
+  const size_t dim = P.dim, L = P.L, L2 = 2 * P.L;
+  SkProg prog = P.prog;
+  sk_cache_tables(prog, s_tab, tid);
+
+  const size_t r = (size_t)cta * SK_T + tid;
+  const bool on = r < L2;
+  const size_t rr = on ? r : (size_t)part;
+  const size_t e = rr >> 1;
+  const int col = (int)(e / dim);
+  SkLane<NH> ln;
+  sk_lane_init<NH>(ln, e, dim, nq, part, prog.diag[e & (dim - 1)]);
+  double y, k[7], ynew = 0.0;
+  y = on ? reinterpret_cast<const double*>(P.y_io)[rr] : 0.0;
+  k[0] = on ? reinterpret_cast<const double*>(P.k0_io)[rr] : 0.0;
+
+  SkResume R = *P.resume;
+  double t = R.t, dt = R.dt, error = R.error, cache_dt = R.cache_dt, cache_err = R.cache_err;
+  long long steps = R.steps_in_interval, pos = R.pos;
+  int n_rec = 0, status = 0, par = 0, rpar = 0;
+  unsigned seq = 1, rseq = 1;
+  int n_acc = R.n_acc;
+  bool tape_ok = R.tape_ok != 0 && P.tapeY != nullptr;
+  bool in_interval = R.in_interval != 0;
+  const bool replay = P.n_replay > 0;
+  int kk = R.kk;
+
+  for (; kk < P.n_t && status == 0; ++kk) {
+    const double t_next = P.tsave[kk];
+    if (!in_interval) { cache_dt = dt; cache_err = error; steps = 0; }
+    in_interval = true;
+    while (t < t_next) {
+      if (n_rec >= P.log_cap) { status = 1; break; }
+      bool clipped;
+      if (!replay) {
+        // update_tstep; the pow is evaluated by one thread
+        if (tid == 0) s_fac = error == 0.0 ? 0.0 : P.safety * pow(error, -0.2);
+        __syncthreads();
+        const double fac = s_fac;
+        if (error == 0.0) dt = dt * P.maxf;
+        else dt = error <= 1.0 ? dt * fmax(1.0, fmin(P.maxf, fac)) : dt * fmin(0.9, fmax(P.minf, fac));
+        clipped = t + dt >= t_next;
+      } else {
+        if (pos >= P.n_replay) { status = 4; break; }
+        dt = P.replay_dt[pos];
+        clipped = P.replay_clipped[pos] != 0;
+        ++pos;
+      }
+      if (clipped) { cache_dt = dt; cache_err = error; dt = t_next - t; }
+      // coefficients of the six stage times
+      if (tid < 6) s_times[tid] = t + dt * P.tab.alpha[tid];
+      __syncthreads();
+      sk_eval_stages(prog, s_times, coef, tid);
+      if (tape_ok && n_acc >= P.tape_cap) tape_ok = false;
+      double* tY = tape_ok ? P.tapeY + (size_t)n_acc * 6 * L2 : nullptr;
+      double* tK = tape_ok ? P.tapeK + (size_t)n_acc * 6 * L2 : nullptr;
+      if (tY && on) { tY[r] = y; tK[r] = k[0]; }
+      // ---- stages 2..7 -------------------------------------------------------------------
+#pragma unroll
+      for (int i = 1; i < 7; ++i) {
+        uint4* buf = P.YS + (size_t)par * L2;
+        double v = y;
+#pragma unroll
+        for (int j = 0; j < i; ++j) v = fma(dt * P.tab.beta[i - 1][j], k[j], v);
+        if (on) ll_store(buf + r, v, seq);
+        if (i == 6) ynew = v;
+        if (tY && i < 6 && on) tY[(size_t)i * L2 + r] = v;
+        const double vo = __shfl_xor_sync(0xffffffffu, v, 1);
+        SkStageCoef<NH> sc;
+        sk_stage_coef<NH>(sc, ln, coef[i - 1], nq);
+        k[i] = sk_apply_lane<NH>(sc, ln, vo, buf, seq, on, P.abort_flag);
+        if (!on) k[i] = 0.0;
+        if (tK && i < 6 && on) tK[(size_t)i * L2 + r] = k[i];
+        par ^= 1; ++seq;
+      }
+      // ---- error norm ----------------------------------------------------------------------
+      double er = 0.0;
+#pragma unroll
+      for (int j = 0; j < 7; ++j) er = fma(dt * P.tab.eb[j], k[j], er);
+      {
+        const double yo = __shfl_xor_sync(0xffffffffu, y, 1);
+        const double yno = __shfl_xor_sync(0xffffffffu, ynew, 1);
+        const double m0 = fma(y, y, yo * yo), m1 = fma(ynew, ynew, yno * yno);
+        const double sc = P.atol + P.rtol * sqrt(fmax(m0, m1));
+        er /= sc;
+      }
+      const double sq = on ? er * er : 0.0;
+      for (int b = 0; b < P.batch; ++b) {
+        const double v = warp_sum_d(col == b ? sq : 0.0);
+        if (lane == 0) s_red[warp][b] = v;
+      }
+      __syncthreads();
+      if (tid < P.batch) {
+        double tot = 0.0;
+        for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w][tid];
+        ll_store(P.red + ((size_t)rpar * P.nC + cta) * P.batch + tid, tot, rseq);
+      }
+      // every CTA collects all partial sums: warp b (strided) polls the lines of column b, lane j
+      // those of CTAs j, j+32, ... and the warp sums them in a fixed order
+      for (int b = warp; b < P.batch; b += SK_T / 32) {
+        double tot = 0.0;
+        for (int c = lane; c < P.nC; c += 32) {
+          const uint4* src = P.red + ((size_t)rpar * P.nC + c) * P.batch + b;
+          uint4 v;
+          SkPoll poll{P.abort_flag};
+          do { v = ll_load(src); } while (ll_bad(v, rseq) != 0 && !poll.give_up());
+          tot += ll_value(v);
+        }
+        tot = warp_sum_d(tot);
+        if (lane == 0) s_err[b] = tot;
+      }
+      __syncthreads();
+      error = 0.0;
+      for (int b = 0; b < P.batch; ++b) error = fmax(error, sqrt(s_err[b] / (double)dim));
+      ++rseq;
+      rpar ^= 1;
+      if (*(volatile int*)P.abort_flag) { status = 5; break; }
+      if (!(error == error)) { status = 3; break; }
+      const bool accepted = replay ? true : error <= 1.0;
+      if (cta == 0 && tid == 0) {
+        pd_step_record rec;
+        rec.t = t; rec.dt = dt; rec.error = error; rec.accepted = accepted ? 1 : 0;
+        rec.clipped = clipped ? 1 : 0; rec.interval = kk; rec._pad = 0;
+        P.log[n_rec] = rec;
+      }
+      ++n_rec;
+      if (accepted) {
+        t = clipped ? t_next : t + dt;
+        ++n_acc;
+        y = ynew; k[0] = k[6];
+      }
+      if (++steps >= P.max_steps) { status = 2; break; }
+    }
+    if (status != 0) break;
+    dt = cache_dt; error = cache_err;
+    in_interval = false;
+    if (on) reinterpret_cast<double*>(P.states + (size_t)kk * L)[r] = y;
+  }
+  if (on) {
+    reinterpret_cast<double*>(P.y_io)[r] = y;
+    reinterpret_cast<double*>(P.k0_io)[r] = k[0];
+  }
+  if (cta == 0 && tid == 0) {
+    SkResume o;
+    o.t = t; o.dt = dt; o.error = error; o.cache_dt = cache_dt; o.cache_err = cache_err;
+    o.steps_in_interval = steps; o.pos = pos; o.kk = kk; o.in_interval = in_interval ? 1 : 0;
+    o.n_rec = n_rec; o.status = status; o.n_acc = n_acc; o.tape_ok = tape_ok ? 1 : 0;
+    *P.resume = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward: whole discrete-adjoint sweep over the accepted-step sequence, reading the stage tape
+// ------------------------------------------------------------------------------------------
+struct SkStep {
+  double t, dt;
+  int interval, clipped;
+};
+
+struct SkBwd {
+  SkProg prog;
+  SkTab tab;
+  int batch, nC;
+  size_t dim, L;
+  int n_t, n_steps;
+  const SkStep* steps;
+  const cplx* gstates;    // [n_t][L] or null
+  const double* tapeY;    // [n_steps][6][2L]
+  const double* tapeK;    // [n_steps][6][2L]
+  uint4* KB;              // [2][2L] LL lines: exchange of the adjoint stage inputs (zeroed by the host)
+  double* slotpart;       // [n_steps*6][nC][nred]  nred = n_det + 2 n_amp + 1
+  double* wacc_elem;      // [L] or null
+  cplx* lam_out;          // [L]
+  int want_coef;
+  int* abort_flag;
+};
+
+template <int NQG>
+__global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__ SkBwd P) {
+  constexpr int NH = NQG / 2;
+  __shared__ SkCoef coef[6];
+  __shared__ double s_red[SK_T / 32][2 * SK_MAXTERMS + SK_MAXTERMS + 1];
+  __shared__ unsigned long long s_dm[SK_MAXTERMS], s_am[SK_MAXTERMS];
+  __shared__ double s_times[6];
+  __shared__ __align__(16) unsigned char s_tab[SK_TABLE_BYTES];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int part = tid & 1;
+  const unsigned cta = blockIdx.x;
+  const int nq = P.prog.nq, n_det = P.prog.n_det, n_amp = P.prog.n_amp;
+  const int nred = n_det + 2 * n_amp + 1;
+  const size_t L = P.L, dim = P.dim, L2 = 2 * P.L;
+  if (tid < n_det) s_dm[tid] = P.prog.det_masks[tid];
+  if (tid < n_amp) s_am[tid] = P.prog.amp_masks[tid];
+  SkProg prog = P.prog;
+  sk_cache_tables(prog, s_tab, tid);
+  __syncthreads();
+
+  const size_t r = (size_t)cta * SK_T + tid;
+  const bool on = r < L2;
+  const size_t rr = on ? r : (size_t)part;
+  const size_t e = rr >> 1;
+  SkLane<NH> ln;
+  sk_lane_init<NH>(ln, e, dim, nq, part, prog.diag[e & (dim - 1)]);
+  const double* gst = reinterpret_cast<const double*>(P.gstates);
+  double wacc = 0.0;
+  double lam = (on && gst) ? gst[(size_t)(P.n_t - 1) * L2 + rr] : 0.0;
+  int bpar = 0;
+  unsigned seq = 1;
+  int hi = P.n_steps;
+  for (int kk = P.n_t - 1; kk >= 1; --kk) {
+    int lo = hi;
+    while (lo > 0 && P.steps[lo - 1].interval == kk) --lo;
+    for (int gi = hi - 1; gi >= lo; --gi) {
+      const SkStep st = P.steps[gi];
+      const double h = st.dt;
+      __syncthreads();
+      if (tid < 6) s_times[tid] = tid == 0 ? st.t : st.t + h * P.tab.alpha[tid - 1];
+      __syncthreads();
+      sk_eval_stages(prog, s_times, coef, tid);
+      const char* tY = reinterpret_cast<const char*>(P.tapeY + (size_t)gi * 6 * L2);
+      const double* tK = P.tapeK + (size_t)gi * 6 * L2;
+      double yb[6];
+#pragma unroll
+      for (int i = 5; i >= 0; --i) {
+        uint4* buf = P.KB + (size_t)bpar * L2;
+        double u = h * P.tab.b5[i] * lam;
+#pragma unroll
+        for (int j = i + 1; j < 6; ++j) u = fma(h * P.tab.beta[j - 1][i], yb[j], u);
+        if (on) ll_store(buf + r, u, seq);
+        const double uo = __shfl_xor_sync(0xffffffffu, u, 1);
+        SkStageCoef<NH> sc;
+        sk_stage_coef<NH>(sc, ln, coef[i], nq);
+        // tape values of this slot: element e of stage input i sits at byte offset e*16 (re, im)
+        const char* ysrc = tY + (size_t)i * L2 * 8;
+        const double kt = on ? tK[(size_t)i * L2 + r] : 0.0;
+        const double2 own = *reinterpret_cast<const double2*>(ysrc + (ln.eoff >> 1));
+        double2 pv[NH];
+        if (P.want_coef) {
+#pragma unroll
+          for (int j = 0; j < NH; ++j)
+            if (j < ln.jmax) pv[j] = *reinterpret_cast<const double2*>(ysrc + ((ln.eoff ^ ln.xm[j]) >> 1));
+        }
+        yb[i] = -sk_apply_lane<NH>(sc, ln, uo, buf, seq, on, P.abort_flag);
+        if (!on) yb[i] = 0.0;
+        bpar ^= 1; ++seq;
+        // ---- per-term gradient sums of this slot -----------------------------------------------
+        // kb = conj(u_e); self = kb*Y_e; fl_j = kb*Y_partner(j).  Everything stays in registers.
+        if (P.want_coef || P.wacc_elem) {
+          const double ure = part == 0 ? u : uo, uim = part == 0 ? uo : u;
+          const double self_im = on ? ure * own.y - uim * own.x : 0.0;
+          if (part == 0) wacc += self_im;
+          double hd = on ? u * kt : 0.0;
+          if (P.want_coef) {
+            double gd[NH], ga[NH], gb[NH];
+#pragma unroll
+            for (int j = 0; j < NH; ++j) {
+              gd[j] = 0.0; ga[j] = 0.0; gb[j] = 0.0;
+              if (j < ln.jmax && on) {
+                const bool a = (ln.bits >> (2 * j + part)) & 1;
+                const double fl_re = ure * pv[j].x + uim * pv[j].y;
+                const double fl_im = ure * pv[j].y - uim * pv[j].x;
+                gd[j] = a ? 0.0 : self_im;
+                ga[j] = fl_im;
+                gb[j] = a ? fl_re : -fl_re;
+              }
+            }
+            for (int kd = 0; kd < n_det; ++kd) {
+              const unsigned long long m = s_dm[kd];
+              double v = 0.0;
+#pragma unroll
+              for (int j = 0; j < NH; ++j)
+                if (j < ln.jmax && (m >> (nq - 1 - (2 * j + part)) & 1ull)) v += gd[j];
+              v = warp_sum_d(v);
+              if (lane == 0) s_red[warp][kd] = v;
+            }
+            for (int ka = 0; ka < n_amp; ++ka) {
+              const unsigned long long m = s_am[ka];
+              double va = 0.0, vb = 0.0;
+#pragma unroll
+              for (int j = 0; j < NH; ++j)
+                if (j < ln.jmax && (m >> (nq - 1 - (2 * j + part)) & 1ull)) { va += ga[j]; vb += gb[j]; }
+              va = warp_sum_d(va);
+              vb = warp_sum_d(vb);
+              if (lane == 0) { s_red[warp][n_det + 2 * ka] = va; s_red[warp][n_det + 2 * ka + 1] = vb; }
+            }
+          } else if (lane == 0) {
+            for (int q = 0; q < nred - 1; ++q) s_red[warp][q] = 0.0;
+          }
+          hd = warp_sum_d(hd);
+          if (lane == 0) s_red[warp][nred - 1] = hd;
+          __syncthreads();
+          if (tid < nred) {
+            double tot = 0.0;
+            for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w][tid];
+            P.slotpart[((size_t)gi * 6 + i) * P.nC * nred + (size_t)cta * nred + tid] = tot;
+          }
+          __syncthreads();
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) lam += yb[i];
+    }
+    hi = lo;
+    if (gst && on) lam += gst[(size_t)(kk - 1) * L2 + r];
+  }
+  if (on) {
+    reinterpret_cast<double*>(P.lam_out)[r] = lam;
+    if (P.wacc_elem && part == 0) P.wacc_elem[e] = wacc;
+  }
+}
+
+static __global__ void k_fold_columns(const double* __restrict__ in, double* __restrict__ out, size_t dim, int batch) {
+  size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= dim) return;
+  double v = 0.0;
+  for (int b = 0; b < batch; ++b) v += in[(size_t)b * dim + s];
+  out[s] += v;
+}
+
+inline void fill_tab(const Tableau& t, SkTab& o) {
+  for (int i = 0; i < 6; ++i) o.alpha[i] = t.alpha[i];
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 6; ++j) o.beta[i][j] = t.beta[i][j];
+  for (int j = 0; j < 7; ++j) { o.b5[j] = t.b5[j]; o.eb[j] = t.b5[j] - t.b4[j]; }
+}
+
+// Cooperative launch: all CTAs are guaranteed co-resident, which the polling exchange needs.
+template <class K, class PT>
+void launch_coop(K kern, const PT& P, int nC, cudaStream_t s) {
+  void* args[1] = {const_cast<PT*>(&P)};
+  PD_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nC), dim3(SK_T), args, 0, s));
+}
+
+}  // namespace sk
+}  // namespace pd

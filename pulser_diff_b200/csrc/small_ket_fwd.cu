@@ -1,0 +1,12 @@
+// Forward-evolution kernel variants of the small-register family (see small_ket.cuh):
+// partner arrays sized for registers of up to 8, 12 and 16 qubits.
+#include "small_ket.cuh"
+namespace pd {
+namespace sk {
+void launch_forward(int nq, const SkFwd& P, int nC, cudaStream_t st) {
+  if (nq <= 8) launch_coop(k_small_forward<8>, P, nC, st);
+  else if (nq <= 12) launch_coop(k_small_forward<12>, P, nC, st);
+  else launch_coop(k_small_forward<16>, P, nC, st);
+}
+}  // namespace sk
+}  // namespace pd

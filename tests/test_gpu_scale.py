@@ -107,3 +107,53 @@ def test_tiled_equals_gather(cuda_device, n):
     assert (hp[0] - hp[1]).abs().max() < 1e-12 * hp[0].abs().max()
     for a, b in zip(grads[0], grads[1]):
         assert (a - b).abs().max() < 1e-9 * max(1e-30, b.abs().max().item())
+
+
+@pytest.mark.parametrize("n,batch,local", [(3, 1, False), (6, 4, True), (10, 1, False), (12, 1, True),
+                                           (13, 1, False)])
+def test_small_cluster_kernels_equal_gather(cuda_device, n, batch, local):
+    """One-launch cluster kernels (csrc/small_ket.cu, path 3) against the stage-by-stage gather
+    kernels (path 1): states, attempted-step log, and every gradient (samples, times, pair
+    couplings, initial state)."""
+    pr = _program(n, T=16, seed=3)
+    dev = cuda_device
+    if local:   # per-qubit drive and detuning terms on two qubits + the global terms
+        g = torch.Generator().manual_seed(9)
+        pr["det_masks"] = pr["det_masks"] + [1 << 0, 1 << (n - 1)]
+        pr["amp_masks"] = pr["amp_masks"] + [1 << 1]
+        pr["det_values"] = torch.cat([pr["det_values"], torch.rand(2, 16, dtype=torch.float64, generator=g)])
+        pr["amp_values"] = torch.cat([pr["amp_values"],
+                                      torch.complex(torch.rand(1, 16, dtype=torch.float64, generator=g),
+                                                    torch.rand(1, 16, dtype=torch.float64, generator=g))])
+    psi0 = torch.randn(batch, 2 ** n, dtype=torch.complex128, generator=torch.Generator().manual_seed(5)).to(dev)
+    psi0 /= psi0.norm(dim=1, keepdim=True)
+    tsave0 = torch.tensor([0.0, 0.004, 0.0095, 0.013], dtype=torch.float64)
+    def run(path, replay=None):
+        av = pr["amp_values"].clone().requires_grad_(True)
+        dv = pr["det_values"].clone().requires_grad_(True)
+        pu = pr["pair_u"].clone().requires_grad_(True)
+        ts = tsave0.clone().requires_grad_(True)
+        p0 = psi0.clone().requires_grad_(True)
+        st = ops.evolve(p0, ts, dv, av, pu, n_qubits=n, kind=_cabi.PD_KET, dt=pr["dt"],
+                        det_masks=pr["det_masks"], amp_masks=pr["amp_masks"],
+                        options=_cabi.Options(path=path, replay=replay))
+        w = torch.arange(2 ** n, device=dev).remainder(5).to(torch.float64)
+        val = (w * st[-1].abs() ** 2).sum() + (w * st[1].abs() ** 2).sum() + (w * st[2].real).sum()
+        return st.detach(), ops.last_step_log(st), torch.autograd.grad(val, [av, dv, pu, ts, p0])
+
+    # free-running controllers: same decisions, step sizes equal up to the rounding of the
+    # error norm (a cancellation-prone quantity entering as error^(-1/5))
+    st_g, log_g, _ = run(1)
+    st_s, log_s, _ = run(3)
+    assert len(log_g) == len(log_s) and len(log_g) > 3
+    for a, b in zip(log_g, log_s):
+        assert a["accepted"] == b["accepted"] and a["clipped"] == b["clipped"]
+        assert abs(a["dt"] - b["dt"]) <= 1e-6 * abs(b["dt"])
+    assert (st_g - st_s).abs().max() < 1e-9
+    # shared step sequence: round-off agreement of states and of every gradient
+    frozen = [(r["dt"], r["clipped"]) for r in log_g if r["accepted"]]
+    st_g, _, g_g = run(1, frozen)
+    st_s, _, g_s = run(3, frozen)
+    assert (st_g - st_s).abs().max() < 1e-12
+    for a, b in zip(g_g, g_s):
+        assert (a - b).abs().max() < 1e-9 * max(1e-30, b.abs().max().item())

@@ -80,9 +80,14 @@ def _loss_and_leaves(p: Problem, states, tsave, extra):
     return loss, leaves
 
 
+@pytest.mark.parametrize("kpath", [0, 1], ids=["auto", "gather"])
 @pytest.mark.parametrize("solver", ["dp5_se", "krylov_se"])
 @pytest.mark.parametrize("local", [False, True])
-def test_ket_states_and_gradients(engine_device, solver, local):
+def test_ket_states_and_gradients(engine_device, solver, local, kpath):
+    """kpath 0 = automatic kernel choice (on CUDA: the one-launch cluster kernels of
+    csrc/small_ket.cu for DP5), 1 = stage-by-stage gather kernels."""
+    if kpath == 1 and solver != "dp5_se":
+        pytest.skip("kernel family only differs for DP5")
     p = random_problem(4, seed=11, local=local)
     psi0 = torch.randn(2 ** p.n, 2, dtype=torch.complex128, generator=torch.Generator().manual_seed(2))
     psi0 = (psi0 / psi0.norm(dim=0)).requires_grad_(True)
@@ -94,7 +99,7 @@ def test_ket_states_and_gradients(engine_device, solver, local):
 
     em = p.emulator(engine_device)
     em.set_initial_state(psi0)
-    res = em.run(time_grad=True, solver=pdb.SolverType(solver))
+    res = em.run(time_grad=True, solver=pdb.SolverType(solver), path=kpath)
     assert (res.states.detach().cpu() - r.states.detach()).abs().max() < ATOL_STATE
     loss, leaves = _loss_and_leaves(p, res.states, em.evaluation_times, [psi0])
     assert abs(loss.item() - loss_r.item()) < 1e-10 * max(1.0, abs(loss_r.item()))
