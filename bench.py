@@ -110,6 +110,14 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(key: str):
+    """dram bytes read+written per DP5 step from the committed ncu capture (profiles/r01_traffic.json)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]
+    except Exception:
+        return None
+
+
 def measured_peak():
     try:
         pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -207,7 +215,7 @@ def run_b200(args):
     t_e2e = time.perf_counter() - t0
 
     # ---- roofline: the HBM-bound regime, N = roofline_n, CUDA events inside the C ABI ----
-    roof = roof_h = roof26 = None
+    roof = roof_h = roof23 = None
     peak, peak_src = measured_peak()
     if rank == 0 and args.roofline_n > 0:
         def measure(nr):
@@ -227,10 +235,11 @@ def run_b200(args):
             s_amp = 2 ** nr
             ach = 576.0 * s_amp / (ms_step * 1e-3) / 1e9
             ach_h = 40.0 * s_amp / (ms_h * 1e-3) / 1e9
-            family = "tiled (smem + TMEM, alternating tile types)" if 18 <= nr <= 23 else "gather"
+            family = ("tiled (smem + TMEM, alternating tile types, fused DP5 step)" if 18 <= nr <= 23 else
+                      "stream (one bit-group of H per launch, >= 256 B pieces)" if nr >= 24 else "gather")
             r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                 "traffic": None, "peak_source": peak_src,
-                 "kernel": "fused DP5 step (6 generator applications + stage combines + error norm)",
+                 "traffic": measured_traffic(f"dp5_step_n{nr}"), "peak_source": peak_src,
+                 "kernel": "DP5 step kernel sequence (6 generator applications + stage combines + error norm)",
                  "kernel_family": family, "workload": f"chain_n{nr}_dp5_step", "ms_per_launch": ms_step,
                  "algorithmic_bytes": 576.0 * s_amp, "steps_per_s": 1e3 / ms_step}
             rh = {"bound": "hbm", "achieved": ach_h, "peak": peak, "unit": "GB/s", "frac": ach_h / peak,
@@ -240,8 +249,8 @@ def run_b200(args):
             torch.cuda.empty_cache()
             return r, rh
         roof, roof_h = measure(args.roofline_n)
-        if args.roofline_n != 26 and not args.skip_n26:
-            roof26, _ = measure(26)
+        if args.roofline_n != 23 and not args.skip_n23:
+            roof23, _ = measure(23)
     clocks = sampler.summary()
 
     # max over ranks
@@ -274,15 +283,16 @@ def run_b200(args):
                        "n_params": 2 * N_PARAM, "dp5_steps_per_pass": n_steps,
                        "parameter_sets": world, "parallelism": f"independent parameter sets x{world}",
                        "l2": "state (64 KiB) is smaller than L2 by construction of the workload; "
-                             "the roofline blocks use N=23 / N=26 (128 MiB / 1 GiB vectors, >> 126 MB L2)"},
+                             "the roofline blocks use N=26 / N=23 (1 GiB / 128 MiB vectors, >> 126 MB L2)"},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_pass": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": roof, "roofline_hpsi": roof_h, "roofline_n26": roof26,
-            "roofline_workload": {"bound": "latency", "achieved": 576.0 * s12 * total_steps / world / t_res / 1e9 * 3,
+            "roofline": roof, "roofline_hpsi": roof_h, "roofline_n23": roof23,
+            "roofline_workload": {"bound": "latency", "achieved": 576.0 * s12 * total_steps / world / t_res / 1e9 * 2,
                                   "peak": peak, "unit": "GB/s",
-                                  "note": "N=12: 64 KiB vectors live in L2; 3x = fwd + recompute + adjoint"},
+                                  "note": "N=12: 64 KiB vectors live in registers/L2 (one cooperative kernel per sweep); "
+                                          "2x = forward + adjoint"},
             "cpu_baseline": cpu,
             "loss": loss_val,
         }
@@ -408,10 +418,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--roofline-n", type=int, default=23)
+    ap.add_argument("--roofline-n", type=int, default=26)
     ap.add_argument("--roofline-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--skip-n26", action="store_true")
+    ap.add_argument("--skip-n23", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--workload", default="c2", choices=["c2", "sharded"])
     ap.add_argument("--local-qubits", type=int, default=26)

@@ -63,6 +63,10 @@ int launch_tiled_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cplx
                           cplx* tmp_b, double* err_partial, double* err_out, cudaStream_t s);
 size_t tiled_err_partial_count(const Geometry& g);
 constexpr int kAutoTiledMinQubits = 18;   // below this the whole working set is L2 resident
+// stream family (stream_ket.cu): one bit-group of H per launch, >= 256 B pieces, any N >= 16
+bool stream_ket_supported(const Geometry& g);
+int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, const cplx* const* ins,
+                            const double* w, const SiteOps& so, cudaStream_t s);
 // small-register family (small_ket.cu): whole forward / adjoint sweep in one cluster kernel
 struct SmallKetState;
 SmallKetState* small_ket_create();
@@ -162,6 +166,10 @@ class CudaBackend {
   }
   int stage_ket(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
                 const double* w, const SiteOps& so, cplx* scratch, void* s) {
+    if (use_stream(g)) {
+      const bool plain = n_in == 1 && w[0] == 1.0 && comb == nullptr;
+      return launch_stream_stage_ket(g, out, plain ? nullptr : (comb ? comb : scratch), n_in, ins, w, so, st(s));
+    }
     if (use_tiled(g))
       return launch_tiled_stage_ket(g, out, comb, n_in, ins, w, so, scratch, st(s));
     int n = 0;
@@ -176,8 +184,14 @@ class CudaBackend {
     return n + launch_apply_ket(g, out, src, so, st(s));
   }
   bool use_tiled(const Geometry& g) const {
-    if (path == 1 || !tiled_ket_supported(g)) return false;
+    if (path == 1 || path == 4 || !tiled_ket_supported(g)) return false;
     return path == 2 || g.nq >= kAutoTiledMinQubits;
+  }
+  // path 4 forces the stream family; automatic choice: registers too large for the two-type tiles
+  bool use_stream(const Geometry& g) const {
+    if (!stream_ket_supported(g)) return false;
+    if (path == 4) return true;
+    return path == 0 && !tiled_ket_supported(g) && g.nq >= kAutoTiledMinQubits;
   }
   // One full Dormand-Prince step with the alternating tiled kernels; 0 = not handled here.
   int dp5_step_ket(const Geometry& g, const cplx* y, cplx* const* k, cplx* ynew,

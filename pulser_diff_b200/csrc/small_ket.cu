@@ -224,15 +224,13 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
   }
   slot_sums.assign((size_t)n_steps * 6 * nred, 0.0);
   if (want_coef && n_steps > 0) {
-    std::vector<double> part(n_part);
-    PD_CUDA_CHECK(cudaMemcpyAsync(part.data(), P.slotpart, sizeof(double) * n_part, cudaMemcpyDeviceToHost, st));
-    PD_CUDA_CHECK(cudaStreamSynchronize(st));
-    for (size_t sl = 0; sl < (size_t)n_steps * 6; ++sl)
-      for (int c = 0; c < nC; ++c)
-        for (size_t r = 0; r < nred; ++r) slot_sums[sl * nred + r] += part[(sl * nC + c) * nred + r];
-  } else {
-    PD_CUDA_CHECK(cudaStreamSynchronize(st));
+    const size_t n_out = (size_t)n_steps * 6 * nred;
+    double* d_out = (double*)S.get(11, sizeof(double) * n_out);
+    k_sum_slots<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(P.slotpart, d_out, (size_t)n_steps * 6, nC, (int)nred);
+    ++launches;
+    PD_CUDA_CHECK(cudaMemcpyAsync(slot_sums.data(), d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
   }
+  PD_CUDA_CHECK(cudaStreamSynchronize(st));
   PD_CUDA_CHECK(cudaGetLastError());
   {
     int ab = 0;

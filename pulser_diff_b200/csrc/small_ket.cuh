@@ -637,6 +637,18 @@ static __global__ void k_fold_columns(const double* __restrict__ in, double* __r
   out[s] += v;
 }
 
+// out[slot][r] = sum over CTAs (fixed order) of the per-CTA partial sums of the adjoint sweep
+static __global__ void k_sum_slots(const double* __restrict__ part, double* __restrict__ out, size_t n_slots, int nC,
+                                   int nred) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_slots * nred) return;
+  const size_t sl = i / nred;
+  const int r = (int)(i % nred);
+  double v = 0.0;
+  for (int c = 0; c < nC; ++c) v += part[(sl * nC + c) * nred + r];
+  out[i] = v;
+}
+
 inline void fill_tab(const Tableau& t, SkTab& o) {
   for (int i = 0; i < 6; ++i) o.alpha[i] = t.alpha[i];
   for (int i = 0; i < 6; ++i)

@@ -1,0 +1,301 @@
+// Streaming tile kernels for large kets ("stream" family): one bit-group of H per launch.
+//
+// H(t) = H_A(t) + sum_g H_g(t):
+//   H_A = static diagonal + detuning diagonal + sigma-x flips on the LOW 12 bits (contiguous tile)
+//   H_g = sigma-x flips on a group of <= 8 higher bits (strided tile: 2^nb rows x 2^(12-nb) columns,
+//         so every global access is a contiguous piece of >= 256 B -- the size below which strided
+//         pieces lose bandwidth on B200, profiles/r01_membench.md)
+//
+// One launch streams one 4096-amplitude tile per CTA through 64 KiB of shared memory:
+//   A launch :  Y = sum_j w_j v_j  (stage combination on the fly, written once as Ymat)
+//               out = H_A Y
+//   g launch :  out += H_g Ymat      (in place)
+// A Dormand-Prince stage is 1 + G launches (G = ceil((N-12)/8) groups; G = 2 at N = 26).  Each
+// launch is a pure stream (a few coalesced vectors in, one or two out) with a single shared-memory
+// pass, small enough in registers and shared memory for three CTAs per SM, which is what keeps HBM
+// busy while other CTAs are in their shared-memory phase.
+//
+// Traffic of one DP5 step at N = 26: 84 vector passes + diagonal = 1392 B per amplitude against
+// the 576 B algorithmic figure.
+#include "cuda_backend.cuh"
+
+namespace pd {
+
+namespace {
+
+constexpr int TB = 12;
+constexpr int TILE = 1 << TB;
+constexpr int NT = 256;
+constexpr int EPT = TILE / NT;   // 16
+constexpr int kMaxIn = 8;
+constexpr int kMaxGroupBits = 8;
+
+struct StreamCoef {
+  cplx kappa;                 // scale of the static diagonal (A launch)
+  cplx t00[kMaxQubits];       // per GLOBAL bit position: diagonal entry for bit value 0 / 1
+  cplx t11[kMaxQubits];
+  cplx t01[kMaxQubits];       // row a=0 <- a'=1
+  cplx t10[kMaxQubits];       // row a=1 <- a'=0
+};
+
+struct StreamParams {
+  int nq;
+  int lo, nb, C;              // strided groups: row bits [lo, lo+nb), C = TB - nb column bits
+  int n_in;
+  size_t dim;
+  const cplx* v[kMaxIn];
+  double w[kMaxIn];
+  cplx* ymat;                 // A launch: combined input written here (nullable)
+  cplx* out;
+  const double* diag;
+};
+
+__device__ __forceinline__ cplx ldg(const cplx* p) {
+  double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return {v.x, v.y};
+}
+__device__ __forceinline__ cplx ldcs(const cplx* p) {
+  double2 v = __ldcs(reinterpret_cast<const double2*>(p));
+  return {v.x, v.y};
+}
+__device__ __forceinline__ void stcs(cplx* p, cplx v) {
+  __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im));
+}
+
+// ---- A launch: contiguous tile, combination + diagonal + low-bit flips ---------------------------
+template <bool UNI>
+__global__ void __launch_bounds__(NT, 3)
+k_stream_a(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  __shared__ cplx tab[2][64];
+  const int t = threadIdx.x;
+  const int nq = P.nq;
+  const size_t tiles_per_vec = P.dim >> TB;
+  const size_t tile = blockIdx.x % tiles_per_vec;
+  const size_t base = (blockIdx.x / tiles_per_vec) * P.dim + (tile << TB);   // batch column + tile
+
+  // detuning-diagonal tables over local bits 0-5 / 6-11; bits above the tile are constant per tile
+  if (t < 128) {
+    const int half = t >> 6, x = t & 63;
+    cplx s{0, 0};
+    for (int b = 0; b < 6; ++b) {
+      const int gb = half * 6 + b;
+      if (gb < nq) s = s + (((x >> b) & 1) ? cf.t11[gb] : cf.t00[gb]);
+    }
+    tab[half][x] = s;
+  }
+  cplx hi{0, 0};
+  for (int gb = TB; gb < nq; ++gb) hi = hi + (((tile >> (gb - TB)) & 1) ? cf.t11[gb] : cf.t00[gb]);
+
+  // ---- combination: Y = sum_j w_j v_j, 4 elements x 2 vectors in flight per thread
+  constexpr int QP = 4;
+#pragma unroll
+  for (int q0 = 0; q0 < EPT; q0 += QP) {
+    cplx y[QP];
+#pragma unroll
+    for (int i = 0; i < QP; ++i) y[i] = {0.0, 0.0};
+    for (int j = 0; j < P.n_in; j += 2) {
+      const bool two = j + 1 < P.n_in;               // uniform
+      const cplx* v0 = P.v[j] + base;
+      const double w0 = P.w[j];
+      cplx x0[QP], x1[QP];
+#pragma unroll
+      for (int i = 0; i < QP; ++i) x0[i] = ldcs(v0 + t + NT * (q0 + i));
+      if (two) {
+        const cplx* v1 = P.v[j + 1] + base;
+        const double w1 = P.w[j + 1];
+#pragma unroll
+        for (int i = 0; i < QP; ++i) x1[i] = ldcs(v1 + t + NT * (q0 + i));
+#pragma unroll
+        for (int i = 0; i < QP; ++i) {
+          y[i].re = fma(w1, x1[i].re, y[i].re); y[i].im = fma(w1, x1[i].im, y[i].im);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < QP; ++i) {
+        y[i].re = fma(w0, x0[i].re, y[i].re); y[i].im = fma(w0, x0[i].im, y[i].im);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < QP; ++i) {
+      T[t + NT * (q0 + i)] = y[i];
+      if (P.ymat) P.ymat[base + t + NT * (q0 + i)] = y[i];
+    }
+  }
+  __syncthreads();
+
+  // ---- out = (kappa*Dint + detuning diagonal) Y + low-bit flips
+  const int nl = nq < TB ? nq : TB;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int e = t + NT * i;
+    const double dg = __ldg(P.diag + (tile << TB) + e);
+    cplx o{0.0, 0.0};
+    if (UNI) {
+      cplx S{0.0, 0.0}, L{0.0, 0.0};
+#pragma unroll
+      for (int lb = 0; lb < TB; ++lb) {
+        if (lb >= nl) break;
+        const cplx pv = T[e ^ (1 << lb)];
+        const bool a = (e >> lb) & 1;
+        S.re += pv.re; S.im += pv.im;
+        L.re += a ? pv.re : 0.0; L.im += a ? pv.im : 0.0;
+      }
+      fma_acc(o, cf.t10[0], L);
+      fma_acc(o, cf.t01[0], cplx{S.re - L.re, S.im - L.im});
+    } else {
+#pragma unroll
+      for (int lb = 0; lb < TB; ++lb) {
+        if (lb >= nl) break;
+        const bool a = (e >> lb) & 1;
+        fma_acc(o, a ? cf.t10[lb] : cf.t01[lb], T[e ^ (1 << lb)]);
+      }
+    }
+    const cplx ds = cplx{cf.kappa.re * dg, cf.kappa.im * dg} + hi + tab[0][e & 63] + tab[1][(e >> 6) & 63];
+    fma_acc(o, ds, T[e]);
+    P.out[base + e] = o;
+  }
+}
+
+// ---- group launch: strided tile, out += H_g Ymat ---------------------------------------------------
+__device__ __forceinline__ size_t gindex(const StreamParams& P, size_t tile, int e) {
+  const size_t col = (size_t)(e & ((1 << P.C) - 1)), row = (size_t)(e >> P.C);
+  const int lw = P.lo - P.C;                       // tile-index bits placed below the row bits
+  const size_t ul = tile & (((size_t)1 << lw) - 1), uh = tile >> lw;
+  return col | (ul << P.C) | (row << P.lo) | (uh << (P.lo + P.nb));
+}
+
+template <bool UNI>
+__global__ void __launch_bounds__(NT, 3)
+k_stream_g(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  const int t = threadIdx.x;
+  const size_t tiles_per_vec = P.dim >> TB;
+  const size_t tile = blockIdx.x % tiles_per_vec;
+  const size_t boff = (blockIdx.x / tiles_per_vec) * P.dim;
+  const cplx* ym = P.v[0] + boff;
+  cplx* out = P.out + boff;
+  const int C = P.C, nb = P.nb;
+
+  // Ymat tile -> shared memory (8 x 16 B in flight per thread)
+#pragma unroll
+  for (int q0 = 0; q0 < EPT; q0 += 8) {
+    cplx x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = ldcs(ym + gindex(P, tile, t + NT * (q0 + i)));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) T[t + NT * (q0 + i)] = x[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q0 = 0; q0 < EPT; q0 += 4) {
+    size_t gi[4];
+    cplx acc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      gi[i] = gindex(P, tile, t + NT * (q0 + i));
+      acc[i] = ldcs(out + gi[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int e = t + NT * (q0 + i);
+      if (UNI) {
+        cplx S{0.0, 0.0}, L{0.0, 0.0};
+        for (int b = 0; b < nb; ++b) {
+          const int lb = C + b;
+          const cplx pv = T[e ^ (1 << lb)];
+          const bool a = (e >> lb) & 1;
+          S.re += pv.re; S.im += pv.im;
+          L.re += a ? pv.re : 0.0; L.im += a ? pv.im : 0.0;
+        }
+        fma_acc(acc[i], cf.t10[P.lo], L);
+        fma_acc(acc[i], cf.t01[P.lo], cplx{S.re - L.re, S.im - L.im});
+      } else {
+        for (int b = 0; b < nb; ++b) {
+          const int lb = C + b;
+          const bool a = (e >> lb) & 1;
+          fma_acc(acc[i], a ? cf.t10[P.lo + b] : cf.t01[P.lo + b], T[e ^ (1 << lb)]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[gi[i]] = acc[i];
+  }
+}
+
+void fill_coef(const SiteOps& so, int nq, StreamCoef& c) {
+  c.kappa = so.kappa;
+  for (int q = 0; q < nq; ++q) {
+    const int p = nq - 1 - q;   // global bit position of qubit q
+    c.t00[p] = so.T[q * 4 + 0];
+    c.t01[p] = so.T[q * 4 + 1];
+    c.t10[p] = so.T[q * 4 + 2];
+    c.t11[p] = so.T[q * 4 + 3];
+  }
+}
+bool uniform_drive(const StreamCoef& a, int nq) {
+  for (int p = 1; p < nq; ++p)
+    if (a.t01[p].re != a.t01[0].re || a.t01[p].im != a.t01[0].im || a.t10[p].re != a.t10[0].re ||
+        a.t10[p].im != a.t10[0].im)
+      return false;
+  return true;
+}
+
+bool g_attr_set = false;
+void set_attrs() {
+  if (g_attr_set) return;
+  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+  g_attr_set = true;
+}
+
+}  // namespace
+
+constexpr int kMinStreamQubits = 16;   // below this the gather kernels run out of L2 anyway
+
+bool stream_ket_supported(const Geometry& g) {
+  // the strided groups take the bits above 12 in chunks of <= 8; every chunk needs >= 1 bit
+  return g.kind == PD_KET && g.nq >= kMinStreamQubits && g.nq <= kMaxQubits - 1 && (g.dim >> TB) * (size_t)g.batch < ((size_t)1 << 31);
+}
+
+// out = G (sum_j w_j in_j); ymat receives the combined input (required: the group launches read it).
+int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, const cplx* const* ins,
+                            const double* w, const SiteOps& so, cudaStream_t s) {
+  if (n_in > kMaxIn) throw Error(PD_ERR_INVALID, "stream stage takes at most 8 inputs");
+  set_attrs();
+  StreamCoef cf;
+  fill_coef(so, g.nq, cf);
+  const bool uni = uniform_drive(cf, g.nq);
+  const unsigned grid = (unsigned)((g.dim >> TB) * (size_t)g.batch);
+  // a plain application (one input, weight 1) needs no materialised combination
+  const bool plain = n_in == 1 && w[0] == 1.0 && ymat == nullptr;
+  const cplx* ysrc = plain ? ins[0] : ymat;
+  if (!plain && ymat == nullptr) throw Error(PD_ERR_STATE, "stream stage needs a buffer for the combined input");
+  StreamParams A{};
+  A.nq = g.nq; A.dim = g.dim; A.n_in = n_in; A.diag = g.diag; A.ymat = plain ? nullptr : ymat; A.out = out;
+  for (int j = 0; j < n_in; ++j) { A.v[j] = ins[j]; A.w[j] = w[j]; }
+  if (uni) k_stream_a<true><<<grid, NT, TILE * 16, s>>>(A, cf);
+  else k_stream_a<false><<<grid, NT, TILE * 16, s>>>(A, cf);
+  int n = 1;
+  const int rest = g.nq - TB;
+  const int G = (rest + kMaxGroupBits - 1) / kMaxGroupBits;
+  int lo = TB;
+  for (int gi = 0; gi < G; ++gi) {
+    const int nb = rest / G + (gi < rest % G ? 1 : 0);
+    StreamParams B{};
+    B.nq = g.nq; B.dim = g.dim; B.n_in = 1; B.v[0] = ysrc; B.w[0] = 1.0; B.out = out;
+    B.lo = lo; B.nb = nb; B.C = TB - nb;
+    if (uni) k_stream_g<true><<<grid, NT, TILE * 16, s>>>(B, cf);
+    else k_stream_g<false><<<grid, NT, TILE * 16, s>>>(B, cf);
+    lo += nb;
+    ++n;
+  }
+  PD_CUDA_CHECK(cudaGetLastError());
+  return n;
+}
+
+}  // namespace pd

@@ -262,18 +262,16 @@ class Hamiltonian:
         """(N, N) upper triangle of C6 / r_ij^6 from the CURRENT ``_dist_dict`` tensors, so that
         ``dist_grad`` (reference backend.py:456-460) differentiates the same handles."""
         n = self._size
-        rows = []
-        for i in range(n):
-            row = []
-            for j in range(n):
-                key = next((k for k, ij in self._pair_index.items() if ij == (i, j)), None)
-                if key is None:
-                    row.append(torch.zeros((), dtype=torch.float64))
-                else:
-                    # 2 * (0.5 * C6 / r^6): hamiltonian.py:343 and the factor 2 of :536
-                    row.append(2 * (0.5 * self._device.interaction_coeff / self._dist_dict[key] ** 6))
-            rows.append(torch.stack(row))
-        return torch.stack(rows) if n > 0 else torch.zeros(0, 0, dtype=torch.float64)
+        out = torch.zeros(n, n, dtype=torch.float64)
+        if not self._pair_index:
+            return out
+        keys = list(self._pair_index)
+        dists = torch.stack([self._dist_dict[k] for k in keys])
+        # 2 * (0.5 * C6 / r^6): hamiltonian.py:343 and the factor 2 of :536
+        vals = 2 * (0.5 * self._device.interaction_coeff / dists ** 6)
+        ii = torch.tensor([self._pair_index[k][0] for k in keys])
+        jj = torch.tensor([self._pair_index[k][1] for k in keys])
+        return out.index_put((ii, jj), vals.to(torch.float64))
 
     def refresh_couplings(self) -> None:
         self._hamiltonian.pair_u = self._pair_couplings()

@@ -79,17 +79,20 @@ def test_norm_conservation_and_fd_gradient(cuda_device, n):
         assert abs(fd.item() - g[0, idx].real.item()) < 1e-6 * abs(fd.item()) + 1e-9
 
 
-@pytest.mark.parametrize("n", [16, 18, 21, 22, 23])
-def test_tiled_equals_gather(cuda_device, n):
-    """The tiled kernels (fused DP5 step, two-launch stage, adjoint sweep) against the gather
-    kernels on the same inputs: states, H.psi and gradients."""
+@pytest.mark.parametrize("n,other", [(16, 2), (18, 2), (21, 2), (22, 2), (23, 2),
+                                     (16, 4), (19, 4), (21, 4), (24, 4), (26, 4)])
+def test_tiled_equals_gather(cuda_device, n, other):
+    """The tiled kernels (path 2: fused DP5 step, two-launch stage, adjoint sweep) and the stream
+    kernels (path 4: one bit-group of H per launch) against the gather kernels (path 1) on the same
+    inputs: states, H.psi and gradients."""
     pr = _program(n, T=16)
     dev = cuda_device
-    psi0 = torch.randn(2, 2 ** n, dtype=torch.complex128, generator=torch.Generator().manual_seed(5)).to(dev)
+    nb = 2 if n <= 23 else 1
+    psi0 = torch.randn(nb, 2 ** n, dtype=torch.complex128, generator=torch.Generator().manual_seed(5)).to(dev)
     psi0 /= psi0.norm(dim=1, keepdim=True)
     tsave = torch.tensor([0.0, 0.004, 0.008], dtype=torch.float64)
     outs, grads, hp = [], [], []
-    for path in (1, 2):
+    for path in (1, other):
         av = pr["amp_values"].clone().requires_grad_(True)
         dv = pr["det_values"].clone().requires_grad_(True)
         st = ops.evolve(psi0, tsave, dv, av, pr["pair_u"], n_qubits=n, kind=_cabi.PD_KET,
@@ -99,7 +102,7 @@ def test_tiled_equals_gather(cuda_device, n):
         w = torch.arange(2 ** n, device=dev).remainder(5).to(torch.float64)
         val = (w * st[-1].abs() ** 2).sum() + (w * st[1].abs() ** 2).sum()
         grads.append(torch.autograd.grad(val, [av, dv]))
-        plan = ops.get_plan(n, 2, _cabi.PD_KET, dev)
+        plan = ops.get_plan(n, nb, _cabi.PD_KET, dev)
         plan.set_path(path)
         hp.append(plan.hpsi(0.0051, psi0))
         plan.set_path(0)
