@@ -305,6 +305,60 @@ k_corr_density(const cplx* __restrict__ kbar, const cplx* __restrict__ y, int nq
   block_reduce_write<32>(acc, partial + (size_t)blockIdx.y * gridDim.x * 32);
 }
 
+// All density sites in ONE pass: per site only the three real sums the gradient distribution reads
+// (engine.hpp::distribute, density branch) are accumulated,
+//   gd_q = sum_idx ((a==0) - (b==0)) Im(self),  ga_q = sum_idx Im(frow) - Im(fcol),
+//   gb_q = sum_idx (a ? 1 : -1) Re(frow) + (b ? 1 : -1) Re(fcol)
+// with a / b the row / column bit of site q, self = conj(kbar) y, frow / fcol = conj(kbar) times y
+// with the row / column bit flipped.  (The per-site 4x4 correlation of k_corr_density costs one
+// pass over the 4^N vector per site.)
+constexpr int kDF = 3 * kMaxSitesDensity;
+__global__ void __launch_bounds__(kThreads)
+k_corr_density_fused(const cplx* __restrict__ kbar, const cplx* __restrict__ y, int nq, size_t total,
+                     double* partial, double* wacc, double wscale) {
+  size_t S = (size_t)1 << nq, dim = S * S;
+  double acc[kDF];
+#pragma unroll
+  for (int i = 0; i < kDF; ++i) acc[i] = 0.0;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    size_t e = idx & (dim - 1);
+    cplx kb = conj(kbar[idx]);
+    cplx self = kb * y[idx];
+#pragma unroll
+    for (int q = 0; q < kMaxSitesDensity; ++q) {
+      if (q < nq) {
+        size_t mc = (size_t)1 << (nq - 1 - q), mr = mc << nq;
+        bool a = (e & mr) != 0, b = (e & mc) != 0;
+        cplx frow = kb * y[idx ^ mr], fcol = kb * y[idx ^ mc];
+        acc[q * 3 + 0] += ((a ? 0.0 : 1.0) - (b ? 0.0 : 1.0)) * self.im;
+        acc[q * 3 + 1] += frow.im - fcol.im;
+        acc[q * 3 + 2] += (a ? frow.re : -frow.re) + (b ? fcol.re : -fcol.re);
+      }
+    }
+    if (wacc) {
+      double w = wscale * self.im;
+      atomicAdd(&wacc[e >> nq], w);
+      atomicAdd(&wacc[e & (S - 1)], -w);
+    }
+  }
+  block_reduce_write<kDF>(acc, partial);
+}
+// d_corr[q][16]: zero except the three entries engine.hpp::distribute turns back into (gd, ga, gb)
+__global__ void k_corr_density_scatter(const double* __restrict__ partial, int nblocks, int nq, cplx* d_corr) {
+  int q = blockIdx.x, lane = threadIdx.x;   // one warp per site
+  double v[3] = {0.0, 0.0, 0.0};
+  for (int b = lane; b < nblocks; b += 32)
+    for (int k = 0; k < 3; ++k) v[k] += partial[(size_t)b * kDF + q * 3 + k];
+  for (int k = 0; k < 3; ++k) v[k] = warp_sum(v[k]);
+  if (lane < 16) d_corr[q * 16 + lane] = cplx{0.0, 0.0};
+  __syncwarp();
+  if (lane == 0) {
+    d_corr[q * 16 + 5] = cplx{0.0, v[0]};      // p = (a=0,b=1): weight +1 on Im C[p][p]
+    d_corr[q * 16 + 2] = cplx{-v[2], v[1]};    // p = 0, prow = 2: ga = +Im, gb = -Re
+  }
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_pair_reduce(const double* __restrict__ wacc, int nq, double* out) {
   int i = blockIdx.x / nq, j = blockIdx.x % nq;
@@ -449,16 +503,16 @@ int launch_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, 
                       (double*)(d_corr + (size_t)c * kQC * 4), 1, 1.0, 0, s, kQC * 8);
       }
   } else {
-    int ny = d_corr ? g.nq : 1;
     size_t total = g.dim * g.batch;
-    int gx = rgrid_for(total, 32, ny);
-    k_corr_density<<<dim3(gx, ny), kThreads, 0, s>>>(kbar, y, g.nq, total, scratch, d_wacc, wscale);
-  PD_CUDA_CHECK(cudaGetLastError());
+    int gx = rgrid_for(total, kDF, 1);
+    k_corr_density_fused<<<gx, kThreads, 0, s>>>(kbar, y, g.nq, total, scratch, d_wacc, wscale);
+    PD_CUDA_CHECK(cudaGetLastError());
     ++n;
-    if (d_corr)
-      for (int q = 0; q < ny; ++q)
-        n += finalize(scratch + (size_t)q * gx * 32, gx, 32, (double*)(d_corr + (size_t)q * 16), 1,
-                      1.0, 0, s);
+    if (d_corr) {
+      k_corr_density_scatter<<<g.nq, 32, 0, s>>>(scratch, gx, g.nq, d_corr);
+      PD_CUDA_CHECK(cudaGetLastError());
+      ++n;
+    }
   }
   return n;
 }
