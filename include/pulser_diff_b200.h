@@ -81,7 +81,8 @@ typedef struct pd_options {
                            (shared-step parity protocol) */
   const double* replay_dt;      /* host [n_replay] step sizes (ignored for clipped steps) */
   const uint8_t* replay_clipped;/* host [n_replay] 1 = step lands on the next tsave point */
-  int32_t path;         /* 0 = auto, 1 = force generic gather kernels, 2 = force tiled kernels */
+  int32_t path;         /* kernel family: 0 = auto, 1 = gather, 2 = tiled (18<=N<=23), 3 = small-register
+                           cooperative kernels (N<=14), 4 = stream (N>=16) */
 } pd_options;
 
 typedef struct pd_step_record {
@@ -121,8 +122,8 @@ int pd_plan_set_terms(pd_plan* p, int32_t n_samples, double dt, int32_t n_det,
  * (r,g) basis.  n_ops = 0 reproduces backend.py:496-498 (single zero operator). */
 int pd_plan_set_collapse(pd_plan* p, int32_t n_ops, const double* ops_host);
 
-/* Kernel family for the next calls on this plan: 0 = auto, 1 = gather kernels, 2 = tiled kernels
- * where the shape allows (used by the tiled-vs-gather parity tests). */
+/* Kernel family for the next calls on this plan: 0 = auto, 1 = gather, 2 = tiled, 3 = small-register,
+ * 4 = stream kernels where the shape allows (used by the family-vs-gather parity tests). */
 int pd_plan_set_path(pd_plan* p, int32_t path);
 
 /* ---- single operator applications --------------------------------------------------------- */
@@ -147,6 +148,26 @@ int pd_evolve_forward(pd_plan* p, void* stream, int32_t solver, const pd_options
 int pd_evolve_backward(pd_plan* p, void* stream, pd_tape* tape, const void* states_dev,
                        const void* grad_states_dev, double* grad_det_host, double* grad_amp_host,
                        double* grad_pair_u_host, double* grad_tsave_host, void* grad_state0_dev);
+
+/* ---- batches of independent parameter sets (BASELINE configs[2]; reference: the user-level loop
+ * over QuantumModel parameter sets, docs/gate_optimization.ipynb) ------------------------------
+ * n_units evolutions of the SAME register, masks, time grid and options; unit u has its own
+ * initial state state0[u] ([batch][dim]) and coefficient tables det_values[u] ([n_det][n_samples])
+ * / amp_values[u] ([n_amp][n_samples] complex), laid out unit-major on the host.  states_dev:
+ * [n_units][n_t][batch][dim].  Kets with 2*batch*2^N <= 128 run all units in one launch (one CTA
+ * per unit); larger units run one after the other.  DP5_SE only. */
+int pd_evolve_forward_units(pd_plan* p, void* stream, const pd_options* opt, int32_t n_units,
+                            const void* state0_dev, const double* tsave_host, int32_t n_t,
+                            const double* det_values_host, const double* amp_values_host,
+                            void* states_dev, pd_tape** tape_out);
+/* grad_det_host: [n_units][n_det][n_samples], grad_amp_host: [n_units][n_amp][n_samples] complex,
+ * grad_state0_dev: [n_units][batch][dim]; any may be NULL. */
+int pd_evolve_backward_units(pd_plan* p, void* stream, pd_tape* tape, const void* states_dev,
+                             const void* grad_states_dev, const double* det_values_host,
+                             const double* amp_values_host, double* grad_det_host, double* grad_amp_host,
+                             void* grad_state0_dev);
+/* accepted steps of one unit (and its attempted steps), -1 if out of range */
+int64_t pd_tape_unit_steps(const pd_tape* t, int32_t unit, int32_t* attempts_out);
 
 int64_t pd_tape_n_records(const pd_tape* t);
 int pd_tape_records(const pd_tape* t, pd_step_record* out, int64_t capacity);

@@ -47,6 +47,7 @@ EXPORTS = (
     "pd_plan_set_interaction", "pd_plan_set_terms", "pd_plan_set_collapse", "pd_plan_set_path",
     "pd_hpsi", "pd_rhs",
     "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
+    "pd_evolve_forward_units", "pd_evolve_backward_units", "pd_tape_unit_steps",
     "pd_tape_destroy", "pd_expect_diag", "pd_bench_hpsi", "pd_bench_dp5_steps",
     "pd_plan_launch_count", "pd_is_cuda",
 )
@@ -74,6 +75,11 @@ def _declare(lib: C.CDLL) -> None:
     lib.pd_evolve_forward.argtypes = [vp, vp, i32, C.POINTER(pd_options), vp, pdbl, i32, vp,
                                       C.POINTER(vp)]
     lib.pd_evolve_backward.argtypes = [vp, vp, vp, vp, vp, pdbl, pdbl, pdbl, pdbl, vp]
+    lib.pd_evolve_forward_units.argtypes = [vp, vp, C.POINTER(pd_options), i32, vp, pdbl, i32, pdbl, pdbl, vp,
+                                            C.POINTER(vp)]
+    lib.pd_evolve_backward_units.argtypes = [vp, vp, vp, vp, vp, pdbl, pdbl, pdbl, pdbl, vp]
+    lib.pd_tape_unit_steps.argtypes = [vp, i32, C.POINTER(i32)]
+    lib.pd_tape_unit_steps.restype = i64
     lib.pd_tape_n_records.argtypes = [vp]
     lib.pd_tape_n_records.restype = i64
     lib.pd_tape_records.argtypes = [vp, C.POINTER(pd_step_record), i64]
@@ -161,7 +167,7 @@ class Options:
     norm_tolerance: float = 1e-10
     use_sparse: bool = False          # accepted for API parity; the path is matrix free
     replay: Optional[Sequence] = None  # accepted steps [(dt, clipped), ...]: shared-step protocol
-    path: int = 0                     # 0 auto, 1 gather kernels, 2 tiled kernels
+    path: int = 0                     # 0 auto, 1 gather, 2 tiled, 3 small-register, 4 stream kernels
 
     @classmethod
     def from_dict(cls, d: Optional[dict]) -> "Options":
@@ -301,6 +307,60 @@ class Plan:
                                        C.byref(tape_ptr) if want_tape else None))
         del keep
         return states, (Tape(tape_ptr.value) if want_tape else None)
+
+    def _options_struct(self, opt: Options):
+        o = pd_options()
+        lib().pd_options_default(C.byref(o))
+        for k in ("atol", "rtol", "max_steps", "safety_factor", "min_factor", "max_factor",
+                  "max_krylov", "exp_tolerance", "norm_tolerance", "path"):
+            setattr(o, k, getattr(opt, k))
+        return o
+
+    def evolve_forward_units(self, opt: Options, state0: torch.Tensor, tsave: torch.Tensor,
+                             det_values: torch.Tensor, amp_values: torch.Tensor,
+                             want_tape: bool) -> tuple[torch.Tensor, Optional[Tape]]:
+        """Batch of parameter sets: ``state0`` (U, batch, dim) on the device, ``det_values``
+        (U, n_det, n_samples) float64 / ``amp_values`` (U, n_amp, n_samples) complex128 on the
+        host.  Returns states (U, n_t, batch, dim)."""
+        n_units = int(state0.shape[0])
+        state0 = self._vec(state0, "state0", (n_units,))
+        ts = tsave.detach().to("cpu", torch.float64).contiguous()
+        n_t = int(ts.numel())
+        dv = det_values.detach().to("cpu", torch.float64).contiguous()
+        av = torch.view_as_real(amp_values.detach().to("cpu", torch.complex128).contiguous()).contiguous()
+        if tuple(dv.shape) != (n_units, self.n_det, self.n_samples) or \
+                tuple(av.shape) != (n_units, self.n_amp, self.n_samples, 2):
+            raise ValueError("per-unit coefficient tables must be (U, n_terms, n_samples) matching the plan")
+        states = torch.empty((n_units, n_t, self.batch, self.dim), dtype=torch.complex128, device=state0.device)
+        o = self._options_struct(opt)
+        tape_ptr = C.c_void_p()
+        _check(lib().pd_evolve_forward_units(self._ptr, _stream(self.device), C.byref(o), n_units,
+                                             _dptr(state0), _hdbl(ts), n_t, _hdbl(dv), _hdbl(av),
+                                             _dptr(states), C.byref(tape_ptr) if want_tape else None))
+        return states, (Tape(tape_ptr.value) if want_tape else None)
+
+    def evolve_backward_units(self, tape: Tape, states: torch.Tensor, grad_states: torch.Tensor,
+                              det_values: torch.Tensor, amp_values: torch.Tensor, want_state0: bool):
+        n_units, n_t = int(states.shape[0]), int(states.shape[1])
+        states = self._vec(states, "states", (n_units, n_t))
+        grad_states = self._vec(grad_states, "grad_states", (n_units, n_t))
+        dv = det_values.detach().to("cpu", torch.float64).contiguous()
+        av = torch.view_as_real(amp_values.detach().to("cpu", torch.complex128).contiguous()).contiguous()
+        g_det = torch.zeros((n_units, self.n_det, self.n_samples), dtype=torch.float64) if self.n_det else None
+        g_amp = torch.zeros((n_units, self.n_amp, self.n_samples, 2), dtype=torch.float64) if self.n_amp else None
+        g_s0 = torch.empty((n_units, self.batch, self.dim), dtype=torch.complex128,
+                           device=states.device) if want_state0 else None
+        _check(lib().pd_evolve_backward_units(self._ptr, _stream(self.device), tape.ptr, _dptr(states),
+                                              _dptr(grad_states), _hdbl(dv), _hdbl(av), _hdbl(g_det),
+                                              _hdbl(g_amp), _dptr(g_s0)))
+        if g_amp is not None:
+            g_amp = torch.view_as_complex(g_amp)
+        return g_det, g_amp, g_s0
+
+    def unit_steps(self, tape: Tape, unit: int) -> tuple[int, int]:
+        att = C.c_int32(0)
+        acc = lib().pd_tape_unit_steps(tape.ptr, int(unit), C.byref(att))
+        return int(acc), int(att.value)
 
     def evolve_backward(self, tape: Tape, states: torch.Tensor, grad_states: torch.Tensor,
                         want_det: bool, want_amp: bool, want_pair: bool, want_tsave: bool,

@@ -15,6 +15,7 @@ struct pd_plan {
 };
 struct pd_tape {
   pd::Tape tape;
+  std::vector<pd::Tape> units;   // pd_evolve_forward_units: one per parameter set
 };
 
 namespace {
@@ -138,6 +139,50 @@ int pd_evolve_backward(pd_plan* p, void* stream, pd_tape* tape, const void* stat
                     grad_det_host, grad_amp_host, grad_pair_u_host, grad_tsave_host,
                     (pd::cplx*)grad_state0_dev, stream);
   });
+}
+int pd_evolve_forward_units(pd_plan* p, void* stream, const pd_options* opt, int32_t n_units,
+                            const void* state0_dev, const double* tsave_host, int32_t n_t,
+                            const double* det_values_host, const double* amp_values_host,
+                            void* states_dev, pd_tape** tape_out) {
+  return guarded([&] {
+    need(p && state0_dev && tsave_host && states_dev && n_units >= 1, "pd_evolve_forward_units: bad argument");
+    need((det_values_host || p->eng.prog.n_det() == 0) && (amp_values_host || p->eng.prog.n_amp() == 0),
+         "pd_evolve_forward_units: missing coefficient tables");
+    pd_options o;
+    if (opt) o = *opt; else pd_options_default(&o);
+    p->eng.bk.path = o.path;
+    pd_tape* tp = tape_out ? new pd_tape() : nullptr;
+    try {
+      p->eng.forward_units(o, n_units, (const pd::cplx*)state0_dev, tsave_host, n_t, det_values_host,
+                           amp_values_host, (pd::cplx*)states_dev, tp ? &tp->units : nullptr, nullptr, stream);
+    } catch (...) {
+      delete tp;
+      throw;
+    }
+    if (tape_out) *tape_out = tp;
+  });
+}
+int pd_evolve_backward_units(pd_plan* p, void* stream, pd_tape* tape, const void* states_dev,
+                             const void* grad_states_dev, const double* det_values_host,
+                             const double* amp_values_host, double* grad_det_host, double* grad_amp_host,
+                             void* grad_state0_dev) {
+  return guarded([&] {
+    need(p && tape && states_dev && !tape->units.empty(), "pd_evolve_backward_units: bad argument");
+    p->eng.states_for_fallback_ = (const pd::cplx*)states_dev;
+    try {
+      p->eng.backward_units(tape->units, det_values_host, amp_values_host, (const pd::cplx*)grad_states_dev,
+                            grad_det_host, grad_amp_host, (pd::cplx*)grad_state0_dev, stream);
+    } catch (...) {
+      p->eng.states_for_fallback_ = nullptr;
+      throw;
+    }
+    p->eng.states_for_fallback_ = nullptr;
+  });
+}
+int64_t pd_tape_unit_steps(const pd_tape* t, int32_t unit, int32_t* attempts_out) {
+  if (!t || unit < 0 || (size_t)unit >= t->units.size()) return -1;
+  if (attempts_out) *attempts_out = (int32_t)t->units[unit].records.size();
+  return (int64_t)t->units[unit].steps.size();
 }
 int64_t pd_tape_n_records(const pd_tape* t) { return t ? (int64_t)t->tape.records.size() : 0; }
 int pd_tape_records(const pd_tape* t, pd_step_record* out, int64_t capacity) {

@@ -72,15 +72,17 @@ struct SmallKetState;
 SmallKetState* small_ket_create();
 void small_ket_destroy(SmallKetState*);
 bool small_ket_supported(const Geometry& g, const Program& prog);
+bool small_ket_units_supported(const Geometry& g, const Program& prog);
 int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, const Tableau& tab,
-                      const pd_options& o, const cplx* y0, const cplx* k0, double dt0,
-                      const double* tsave, int n_t, cplx* states, std::vector<pd_step_record>& records,
-                      bool want_tape, uint64_t* tape_gen_out, cudaStream_t st);
+                      const pd_options& o, int n_units, const cplx* y0, const double* dv, const double* av,
+                      const double* tsave, int n_t, cplx* states,
+                      std::vector<std::vector<pd_step_record>>& records, bool want_tape,
+                      uint64_t* tape_gen_out, cudaStream_t st);
 int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog, const Tableau& tab,
-                       const std::vector<double>& tsave, const double* step_t, const double* step_dt,
-                       const int* step_interval, const int* step_clipped, int n_steps, uint64_t tape_gen,
+                       const std::vector<double>& tsave, int n_units, const double* dv, const double* av,
+                       const std::vector<std::vector<SkStepHost>>& steps, uint64_t tape_gen,
                        const cplx* gstates, bool want_coef, double* d_wacc, cplx* lam_out,
-                       std::vector<double>& slot_sums, cudaStream_t st);
+                       std::vector<std::vector<double>>& slot_sums, cudaStream_t st);
 
 class CudaBackend {
  public:
@@ -102,21 +104,23 @@ class CudaBackend {
     if (small_) small_ket_destroy(small_);
   }
   bool small_supported(const Geometry& g, const Program& prog) { return small_ket_supported(g, prog); }
+  bool small_units_supported(const Geometry& g, const Program& prog) { return small_ket_units_supported(g, prog); }
   int small_forward(const Geometry& g, const Program& prog, const Tableau& tab, const pd_options& o,
-                    const cplx* y0, const cplx* k0, double dt0, const double* tsave, int n_t,
-                    cplx* states, std::vector<pd_step_record>& recs, bool want_tape, uint64_t* gen, void* s) {
+                    int n_units, const cplx* y0, const double* dv, const double* av, const double* tsave,
+                    int n_t, cplx* states, std::vector<std::vector<pd_step_record>>& recs, bool want_tape,
+                    uint64_t* gen, void* s) {
     if (!small_) small_ = small_ket_create();
-    return small_ket_forward(*small_, g, prog, tab, o, y0, k0, dt0, tsave, n_t, states, recs, want_tape, gen,
-                             st(s));
+    return small_ket_forward(*small_, g, prog, tab, o, n_units, y0, dv, av, tsave, n_t, states, recs,
+                             want_tape, gen, st(s));
   }
   int small_backward(const Geometry& g, const Program& prog, const Tableau& tab,
-                     const std::vector<double>& tsave, const double* st_t, const double* st_dt,
-                     const int* st_i, const int* st_c, int n_steps, uint64_t tape_gen,
+                     const std::vector<double>& tsave, int n_units, const double* dv, const double* av,
+                     const std::vector<std::vector<SkStepHost>>& steps, uint64_t tape_gen,
                      const cplx* gstates, bool want_coef, double* d_wacc, cplx* lam_out,
-                     std::vector<double>& sums, void* s) {
+                     std::vector<std::vector<double>>& sums, void* s) {
     if (!small_) small_ = small_ket_create();
-    return small_ket_backward(*small_, g, prog, tab, tsave, st_t, st_dt, st_i, st_c, n_steps, tape_gen,
-                              gstates, want_coef, d_wacc, lam_out, sums, st(s));
+    return small_ket_backward(*small_, g, prog, tab, tsave, n_units, dv, av, steps, tape_gen, gstates,
+                              want_coef, d_wacc, lam_out, sums, st(s));
   }
   void* alloc(size_t bytes) {
     void* p = nullptr;

@@ -165,6 +165,105 @@ class Engine {
                    stream);
   }
 
+  // ---- batches of independent parameter sets (configs[2]) -------------------------------------
+  // Same register, masks, time grid and options; unit u has its own coefficient tables
+  // dv[u] ([n_det][n_samples]) / av[u] ([n_amp][n_samples] complex) and initial state.  One launch
+  // evolves all units (one CTA per unit, small_ket*.cu); states: [U][n_t][batch][dim].
+  void forward_units(const pd_options& o, int n_units, const cplx* state0, const double* tsave, int n_t,
+                     const double* dv, const double* av, cplx* states, std::vector<Tape>* tapes,
+                     uint64_t* gen_out, void* stream) {
+    if (n_t < 1) throw Error(PD_ERR_INVALID, "tsave must hold at least one time");
+    for (int k = 1; k < n_t; ++k)
+      if (tsave[k] < tsave[k - 1]) throw Error(PD_ERR_INVALID, "tsave must be sorted");
+    if (gen_out) *gen_out = 0;
+    if (prog.kind != PD_KET) throw Error(PD_ERR_INVALID, "batches of parameter sets need a ket plan");
+    if (!use_small() || !bk.small_units_supported(geo, prog)) {
+      // units too large for one CTA each (or no cooperative kernels in this build): one after the
+      // other through the single-problem path, each with its own coefficient tables
+      size_t nd = (size_t)prog.n_det() * prog.n_samples, na = (size_t)prog.n_amp() * prog.n_samples * 2;
+      if (tapes) tapes->assign(n_units, Tape{});
+      for (int u = 0; u < n_units; ++u) {
+        std::copy(dv + u * nd, dv + (u + 1) * nd, prog.det_values.begin());
+        std::copy(av + u * na, av + (u + 1) * na, prog.amp_values.begin());
+        forward(PD_SOLVER_DP5_SE, o, state0 + (size_t)u * L, tsave, n_t, states + (size_t)u * n_t * L,
+                tapes ? &(*tapes)[u] : nullptr, stream);
+        if (tapes) (*tapes)[u].small_gen = 0;      // the device tape is overwritten by the next unit
+      }
+      return;
+    }
+    std::vector<std::vector<pd_step_record>> recs;
+    uint64_t gen = 0;
+    launches += bk.small_forward(geo, prog, tab, o, n_units, state0, dv, av, tsave, n_t, states, recs,
+                                 tapes != nullptr, &gen, stream);
+    if (gen_out) *gen_out = gen;
+    if (tapes) {
+      tapes->assign(n_units, Tape{});
+      for (int u = 0; u < n_units; ++u) {
+        Tape& t = (*tapes)[u];
+        t.tsave.assign(tsave, tsave + n_t);
+        t.solver = PD_SOLVER_DP5_SE;
+        t.opt = o;
+        t.opt.replay_dt = nullptr; t.opt.replay_clipped = nullptr; t.opt.n_replay = 0;
+        t.small_gen = gen;
+        for (const auto& r : recs[u])
+          if (r.accepted) t.steps.push_back({r.t, r.dt, r.interval, r.clipped});
+        t.records = std::move(recs[u]);
+      }
+    }
+  }
+  // g_det: [U][n_det][n_samples], g_amp: [U][n_amp][n_samples][2], g_state0: [U][batch][dim] (device)
+  const cplx* states_for_fallback_ = nullptr;   // set by the C ABI around backward_units
+  void backward_units(std::vector<Tape>& tapes, const double* dv, const double* av, const cplx* gstates,
+                      double* g_det, double* g_amp, cplx* g_state0, void* stream) {
+    int n_units = (int)tapes.size();
+    if (n_units == 0) return;
+    int ns = prog.n_samples, n_det = prog.n_det(), n_amp = prog.n_amp();
+    size_t nred = (size_t)n_det + 2 * (size_t)n_amp + 1;
+    std::vector<std::vector<SkStepHost>> st(n_units);
+    for (int u = 0; u < n_units; ++u)
+      for (const auto& a : tapes[u].steps) st[u].push_back({a.t, a.dt, a.interval, a.clipped});
+    cplx* lam = (cplx*)buf("lam_units", sizeof(cplx) * L * (size_t)n_units);
+    std::vector<std::vector<double>> sums;
+    bool want_coef = g_det || g_amp;
+    int nl = 0;
+    if (tapes[0].small_gen != 0)
+      nl = bk.small_backward(geo, prog, tab, tapes[0].tsave, n_units, dv, av, st, tapes[0].small_gen, gstates,
+                             want_coef, nullptr, lam, sums, stream);
+    if (nl == 0) {
+      // no device tape (large units, another evolution ran since, or a build without the cooperative
+      // kernels): stage-by-stage adjoint per unit, recomputing from the saved states
+      if (!states_for_fallback_)
+        throw Error(PD_ERR_STATE, "backward_units: the forward states are needed for the per-unit adjoint");
+      size_t nd = (size_t)n_det * ns, na = (size_t)n_amp * ns * 2;
+      int n_t = (int)tapes[0].tsave.size();
+      for (int u = 0; u < n_units; ++u) {
+        std::copy(dv + u * nd, dv + (u + 1) * nd, prog.det_values.begin());
+        std::copy(av + u * na, av + (u + 1) * na, prog.amp_values.begin());
+        backward(tapes[u], states_for_fallback_ + (size_t)u * n_t * L,
+                 gstates ? gstates + (size_t)u * n_t * L : nullptr, g_det ? g_det + u * nd : nullptr,
+                 g_amp ? g_amp + u * na : nullptr, nullptr, nullptr,
+                 g_state0 ? g_state0 + (size_t)u * L : nullptr, stream);
+      }
+      return;
+    }
+    launches += nl;
+    if (g_state0) bk.d2d(g_state0, lam, sizeof(cplx) * L * (size_t)n_units, stream);
+    if (g_det) std::fill(g_det, g_det + (size_t)n_units * n_det * ns, 0.0);
+    if (g_amp) std::fill(g_amp, g_amp + (size_t)n_units * n_amp * ns * 2, 0.0);
+    if (want_coef)
+      for (int u = 0; u < n_units; ++u)
+        for (size_t gi = 0; gi < tapes[u].steps.size(); ++gi) {
+          const AcceptedStep& s = tapes[u].steps[gi];
+          for (int i = 0; i < 6; ++i) {
+            double alpha = i == 0 ? 0.0 : tab.alpha[i - 1];
+            distribute_terms(s.t + s.dt * alpha, &sums[u][(gi * 6 + i) * nred],
+                             g_det ? g_det + (size_t)u * n_det * ns : nullptr,
+                             g_amp ? g_amp + (size_t)u * n_amp * ns * 2 : nullptr);
+          }
+        }
+    bk.sync(stream);
+  }
+
   // ---- measurement hooks ------------------------------------------------------------------
   double bench_apply(const cplx* in, cplx* out, double t, int reps, void* stream) {
     apply(out, in, t, 2, stream);
@@ -310,26 +409,27 @@ class Engine {
     vec y = vbuf("y"), ynew = vbuf("ynew");
     vec k[7];
     for (int i = 0; i < 7; ++i) k[i] = vbuf("k" + std::to_string(i));
+    if (use_small()) {
+      // whole evolution in one cooperative kernel (small_ket*.cu), initial slope and step included;
+      // the attempt log becomes the tape
+      std::vector<std::vector<pd_step_record>> recs;
+      uint64_t gen = 0;
+      launches += bk.small_forward(geo, prog, tab, o, 1, state0, nullptr, nullptr, tsave, n_t, states, recs,
+                                   tape != nullptr, &gen, stream);
+      if (tape) {
+        tape->small_gen = gen;
+        for (const auto& r : recs[0])
+          if (r.accepted) tape->steps.push_back({r.t, r.dt, r.interval, r.clipped});
+        tape->records = std::move(recs[0]);
+      }
+      return;
+    }
     bk.d2d(y, state0, sizeof(cplx) * L, stream);
     double t = tsave[0];
     apply(k[0], y, t, 0, stream);
     bool replay = o.n_replay > 0;
     double dt = replay ? 0.0 : init_tstep(t, y, k[0], o, stream);
     double error = 1.0;
-    if (use_small()) {
-      // whole evolution in one cluster kernel (small_ket.cu); the attempt log becomes the tape
-      std::vector<pd_step_record> recs;
-      uint64_t gen = 0;
-      launches += bk.small_forward(geo, prog, tab, o, y, k[0], dt, tsave, n_t, states, recs, tape != nullptr,
-                                   &gen, stream);
-      if (tape) {
-        tape->small_gen = gen;
-        for (const auto& r : recs)
-          if (r.accepted) tape->steps.push_back({r.t, r.dt, r.interval, r.clipped});
-        tape->records = std::move(recs);
-      }
-      return;
-    }
     int64_t pos = 0;
     double* d_err = (double*)buf("norm_out", sizeof(double) * geo.batch);
     std::vector<double> h_err(geo.batch);
@@ -491,26 +591,22 @@ class Engine {
                           bool want_coef, void* stream) {
     int n_t = (int)tape.tsave.size();
     int n_steps = (int)tape.steps.size();
-    std::vector<double> st_t(n_steps), st_dt(n_steps);
-    std::vector<int> st_i(n_steps), st_c(n_steps);
-    for (int i = 0; i < n_steps; ++i) {
-      st_t[i] = tape.steps[i].t; st_dt[i] = tape.steps[i].dt;
-      st_i[i] = tape.steps[i].interval; st_c[i] = tape.steps[i].clipped;
-    }
+    std::vector<std::vector<SkStepHost>> st(1);
+    for (const auto& a : tape.steps) st[0].push_back({a.t, a.dt, a.interval, a.clipped});
     vec lam = vbuf("lam");
     double* d_wacc = nullptr;
     if (g_pair) {
       d_wacc = (double*)buf("wacc", sizeof(double) * ((size_t)1 << geo.nq));
       bk.zero(d_wacc, sizeof(double) * ((size_t)1 << geo.nq), stream);
     }
-    std::vector<double> sums;
-    int nl = bk.small_backward(geo, prog, tab, tape.tsave, st_t.data(), st_dt.data(), st_i.data(),
-                               st_c.data(), n_steps, tape.small_gen, gstates, want_coef, d_wacc, lam, sums,
-                               stream);
+    std::vector<std::vector<double>> sums_u;
+    int nl = bk.small_backward(geo, prog, tab, tape.tsave, 1, nullptr, nullptr, st, tape.small_gen, gstates,
+                               want_coef, d_wacc, lam, sums_u, stream);
     if (nl == 0) return false;
     launches += nl;
     if (g_state0) bk.d2d(g_state0, lam, sizeof(cplx) * L, stream);
     if (want_coef && n_steps > 0) {
+      const std::vector<double>& sums = sums_u[0];
       size_t nred = (size_t)prog.n_det() + 2 * (size_t)prog.n_amp() + 1;
       std::vector<double> tbar_interval(n_t, 0.0), hbar_interval(n_t, 0.0);
       for (int gi = 0; gi < n_steps; ++gi) {

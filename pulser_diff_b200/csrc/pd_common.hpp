@@ -86,6 +86,12 @@ struct Geometry {
   const double* diag;  // device Dint[2^nq]
 };
 
+// one accepted step as handed to the small-register adjoint sweep
+struct SkStepHost {
+  double t, dt;
+  int interval, clipped;
+};
+
 // Interpolation rule of the reference closure H_t, quirk included
 // (reference pulser_diff/hamiltonian.py:532-542).
 struct Interp {

@@ -20,7 +20,7 @@ struct SmallKetState {
   size_t ws_cap[16] = {};
   // stage tape of the most recent recorded forward sweep (slots 14/15) and its identity
   uint64_t tape_gen = 0;
-  int tape_steps = -1;
+  std::vector<int> tape_steps;   // accepted steps per unit of that sweep
   int tape_cap = 0;
   ~SmallKetState() {
     cudaFree(d_dm); cudaFree(d_am); cudaFree(d_dv); cudaFree(d_av);
@@ -63,7 +63,9 @@ bool small_ket_supported(const Geometry& g, const Program& prog) {
   return small_shape(g.dim * (size_t)g.batch, g.batch, nC);
 }
 
-static void upload_prog(SmallKetState& S, const Program& prog, const Geometry& g, SkProg& o, cudaStream_t st) {
+// Uploads masks and the coefficient tables of n_units units (dv: [U][n_det][ns], av: [U][n_amp][ns][2]).
+static void upload_prog(SmallKetState& S, const Program& prog, const Geometry& g, int n_units, const double* dv,
+                        const double* av, SkProg& o, cudaStream_t st) {
   auto up = [&](auto*& dptr, size_t& cap, const void* src, size_t bytes) {
     if (cap < bytes) {
       cudaFree(dptr);
@@ -74,48 +76,63 @@ static void upload_prog(SmallKetState& S, const Program& prog, const Geometry& g
     if (bytes) PD_CUDA_CHECK(cudaMemcpyAsync(dptr, src, bytes, cudaMemcpyHostToDevice, st));
   };
   static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "mask width");
+  const size_t ns = (size_t)prog.n_samples;
   up(S.d_dm, S.cap_dm, prog.det_masks.data(), prog.det_masks.size() * 8);
   up(S.d_am, S.cap_am, prog.amp_masks.data(), prog.amp_masks.size() * 8);
-  up(S.d_dv, S.cap_dv, prog.det_values.data(), prog.det_values.size() * 8);
-  up(S.d_av, S.cap_av, prog.amp_values.data(), prog.amp_values.size() * 8);
+  up(S.d_dv, S.cap_dv, dv, (size_t)n_units * prog.n_det() * ns * 8);
+  up(S.d_av, S.cap_av, av, (size_t)n_units * prog.n_amp() * ns * 16);
   o.nq = prog.nq; o.n_samples = prog.n_samples; o.n_det = prog.n_det(); o.n_amp = prog.n_amp();
   o.dt = prog.dt;
   o.det_masks = S.d_dm; o.det_values = S.d_dv; o.amp_masks = S.d_am; o.amp_values = S.d_av;
   o.diag = g.diag;
 }
 
-// Whole forward evolution.  y0 = state at tsave[0], k0 = f(tsave[0], y0), dt0 = initial step.
-// Appends every attempt to `records`.  Returns the number of kernel launches.
+bool small_ket_units_supported(const Geometry& g, const Program& prog) {
+  int nC;
+  return small_ket_supported(g, prog) && small_shape(g.dim * (size_t)g.batch, g.batch, nC) && nC == 1;
+}
+
+// Whole forward evolution of n_units independent parameter sets (same register, masks and time
+// grid; per-unit coefficient tables dv/av on the host, null = the plan's own for a single unit).
+// y0: [U][L] states at tsave[0]; states: [U][n_t][L].  k1 = f(t0, y0) and the initial step are
+// computed on the device.  Appends every attempt of unit u to records[u].  Returns the launches.
 int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, const Tableau& tab,
-                      const pd_options& o, const cplx* y0, const cplx* k0, double dt0,
-                      const double* tsave, int n_t, cplx* states, std::vector<pd_step_record>& records,
-                      bool want_tape, uint64_t* tape_gen_out, cudaStream_t st) {
+                      const pd_options& o, int n_units, const cplx* y0, const double* dv, const double* av,
+                      const double* tsave, int n_t, cplx* states,
+                      std::vector<std::vector<pd_step_record>>& records, bool want_tape,
+                      uint64_t* tape_gen_out, cudaStream_t st) {
   const size_t L = g.dim * (size_t)g.batch;
+  const size_t U = (size_t)n_units;
   int nC;
   if (!small_shape(L, g.batch, nC)) throw Error(PD_ERR_STATE, "small_ket_forward: unsupported shape");
+  if (n_units > 1 && nC != 1)
+    throw Error(PD_ERR_INVALID, "batches of parameter sets need 2 * batch * 2^N <= 128 (one CTA per set)");
   if (tape_gen_out) *tape_gen_out = 0;
+  records.assign(U, {});
   SkFwd P{};
-  upload_prog(S, prog, g, P.prog, st);
+  upload_prog(S, prog, g, n_units, dv ? dv : prog.det_values.data(), av ? av : prog.amp_values.data(), P.prog, st);
   fill_tab(tab, P.tab);
   P.batch = g.batch; P.nC = nC; P.dim = g.dim; P.L = L;
+  P.n_units = n_units;
+  P.det_stride = (size_t)prog.n_det() * prog.n_samples;
+  P.amp_stride = (size_t)prog.n_amp() * prog.n_samples * 2;
   P.atol = o.atol; P.rtol = o.rtol; P.safety = o.safety_factor; P.minf = o.min_factor; P.maxf = o.max_factor;
   P.max_steps = o.max_steps;
   P.n_replay = o.n_replay;
-  const int log_cap = 1 << 15;
+  const int log_cap = n_units == 1 ? (1 << 15) : (int)std::max<size_t>(256, std::min<size_t>(1 << 15, ((size_t)64 << 20) / 40 / U));
   double* d_ts = (double*)S.get(0, sizeof(double) * n_t);
   PD_CUDA_CHECK(cudaMemcpyAsync(d_ts, tsave, sizeof(double) * n_t, cudaMemcpyHostToDevice, st));
   P.tsave = d_ts; P.n_t = n_t;
-  P.y_io = (cplx*)S.get(1, sizeof(cplx) * L);
-  P.k0_io = (cplx*)S.get(2, sizeof(cplx) * L);
-  PD_CUDA_CHECK(cudaMemcpyAsync(P.y_io, y0, sizeof(cplx) * L, cudaMemcpyDeviceToDevice, st));
-  PD_CUDA_CHECK(cudaMemcpyAsync(P.k0_io, k0, sizeof(cplx) * L, cudaMemcpyDeviceToDevice, st));
+  P.y_io = (cplx*)S.get(1, sizeof(cplx) * L * U);
+  P.k0_io = (cplx*)S.get(2, sizeof(cplx) * L * U);
+  PD_CUDA_CHECK(cudaMemcpyAsync(P.y_io, y0, sizeof(cplx) * L * U, cudaMemcpyDeviceToDevice, st));
   P.states = states;
-  const size_t ys_bytes = sizeof(uint4) * 2 * (2 * L), red_bytes = sizeof(uint4) * 2 * nC * g.batch;
+  const size_t ys_bytes = sizeof(uint4) * 2 * (2 * L) * U, red_bytes = sizeof(uint4) * 2 * nC * g.batch * U;
   P.YS = (uint4*)S.get(3, ys_bytes);
   P.red = (uint4*)S.get(4, red_bytes);
-  P.log = (pd_step_record*)S.get(5, sizeof(pd_step_record) * log_cap);
+  P.log = (pd_step_record*)S.get(5, sizeof(pd_step_record) * log_cap * U);
   P.log_cap = log_cap;
-  P.resume = (SkResume*)S.get(6, sizeof(SkResume));
+  P.resume = (SkResume*)S.get(6, sizeof(SkResume) * U);
   P.abort_flag = (int*)S.get(10, 64);
   if (o.n_replay > 0) {
     double* d_rd = (double*)S.get(7, sizeof(double) * o.n_replay);
@@ -126,23 +143,27 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
   }
   if (want_tape) {
     // per accepted step: 6 stage inputs + 6 slopes; sized from the time grid, bounded by memory
-    const size_t per_step = 6 * L * sizeof(cplx);
+    const size_t per_step = 6 * L * sizeof(cplx) * U;
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) fr = (size_t)4 << 30;
-    const size_t budget = std::min<size_t>((size_t)3 << 29, fr / 8 + S.ws_cap[14]);
+    const size_t budget = std::max<size_t>((size_t)3 << 29, fr / 8) + S.ws_cap[14];
     size_t steps_cap = std::min<size_t>((size_t)16 * n_t + 256, budget / per_step);
-    steps_cap = std::max<size_t>(steps_cap, S.ws_cap[14] / per_step);
+    if (S.ws_cap[14] / per_step > steps_cap) steps_cap = S.ws_cap[14] / per_step;
     if (steps_cap >= 1) {
       P.tapeY = (double*)S.get(14, steps_cap * per_step);
       P.tapeK = (double*)S.get(15, steps_cap * per_step);
       P.tape_cap = (int)std::min<size_t>(steps_cap, (size_t)1 << 30);
     }
-    S.tape_steps = -1;
+    S.tape_steps.clear();
+    S.tape_cap = P.tape_cap;
   }
-  SkResume r{};
-  r.t = tsave[0]; r.dt = dt0; r.error = 1.0; r.cache_dt = dt0; r.cache_err = 1.0;
-  r.kk = 0; r.n_acc = 0; r.tape_ok = P.tapeY ? 1 : 0;
-  PD_CUDA_CHECK(cudaMemcpyAsync(P.resume, &r, sizeof(r), cudaMemcpyHostToDevice, st));
+  std::vector<SkResume> rs(U);
+  for (auto& r : rs) {
+    r = SkResume{};
+    r.t = tsave[0]; r.error = 1.0; r.cache_err = 1.0;
+    r.kk = -1; r.n_acc = 0; r.tape_ok = P.tapeY ? 1 : 0;
+  }
+  PD_CUDA_CHECK(cudaMemcpyAsync(P.resume, rs.data(), sizeof(SkResume) * U, cudaMemcpyHostToDevice, st));
   int launches = 0;
   std::vector<pd_step_record> chunk;
   for (;;) {
@@ -152,65 +173,102 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
     PD_CUDA_CHECK(cudaMemsetAsync(P.abort_flag, 0, 64, st));
     sk::launch_forward(prog.nq, P, nC, st);
     ++launches;
-    PD_CUDA_CHECK(cudaMemcpyAsync(&r, P.resume, sizeof(r), cudaMemcpyDeviceToHost, st));
+    PD_CUDA_CHECK(cudaMemcpyAsync(rs.data(), P.resume, sizeof(SkResume) * U, cudaMemcpyDeviceToHost, st));
     PD_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (r.n_rec > 0) {
-      chunk.resize(r.n_rec);
-      PD_CUDA_CHECK(cudaMemcpyAsync(chunk.data(), P.log, sizeof(pd_step_record) * r.n_rec, cudaMemcpyDeviceToHost, st));
-      PD_CUDA_CHECK(cudaStreamSynchronize(st));
-      records.insert(records.end(), chunk.begin(), chunk.end());
+    size_t max_rec = 0;
+    for (auto& r : rs) max_rec = std::max<size_t>(max_rec, (size_t)r.n_rec);
+    if (max_rec > 0) {
+      if (U == 1) {
+        chunk.resize(rs[0].n_rec);
+        PD_CUDA_CHECK(cudaMemcpyAsync(chunk.data(), P.log, sizeof(pd_step_record) * rs[0].n_rec, cudaMemcpyDeviceToHost, st));
+        PD_CUDA_CHECK(cudaStreamSynchronize(st));
+        records[0].insert(records[0].end(), chunk.begin(), chunk.end());
+      } else {
+        chunk.resize((size_t)log_cap * U);
+        PD_CUDA_CHECK(cudaMemcpyAsync(chunk.data(), P.log, sizeof(pd_step_record) * log_cap * U, cudaMemcpyDeviceToHost, st));
+        PD_CUDA_CHECK(cudaStreamSynchronize(st));
+        for (size_t u = 0; u < U; ++u)
+          records[u].insert(records[u].end(), chunk.begin() + u * log_cap, chunk.begin() + u * log_cap + rs[u].n_rec);
+      }
     }
-    if (r.status == 1) continue;
-    if (r.status == 2) throw Error(PD_ERR_MAX_STEPS, "max_steps reached");
-    if (r.status == 3) throw Error(PD_ERR_STATE, "non-finite error norm in DP5 step");
-    if (r.status == 4) throw Error(PD_ERR_INVALID, "replay sequence too short");
-    if (r.status == 5) throw Error(PD_ERR_STATE, "small_ket_forward: exchange poll timed out");
-    break;
+    bool again = false;
+    for (auto& r : rs) {
+      if (r.status == 1) again = true;
+      if (r.status == 2) throw Error(PD_ERR_MAX_STEPS, "max_steps reached");
+      if (r.status == 3) throw Error(PD_ERR_STATE, "non-finite error norm in DP5 step");
+      if (r.status == 4) throw Error(PD_ERR_INVALID, "replay sequence too short");
+      if (r.status == 5) throw Error(PD_ERR_STATE, "small_ket_forward: exchange poll timed out");
+    }
+    if (!again) break;
   }
-  if (P.tapeY && r.tape_ok) {
-    S.tape_steps = r.n_acc;
-    ++S.tape_gen;
-    if (tape_gen_out) *tape_gen_out = S.tape_gen;
+  if (P.tapeY) {
+    bool ok = true;
+    for (auto& r : rs) ok = ok && r.tape_ok;
+    if (ok) {
+      S.tape_steps.resize(U);
+      for (size_t u = 0; u < U; ++u) S.tape_steps[u] = rs[u].n_acc;
+      ++S.tape_gen;
+      if (tape_gen_out) *tape_gen_out = S.tape_gen;
+    }
   }
   return launches;
 }
 
 size_t small_ket_nred(const Program& prog) { return (size_t)prog.n_det() + 2 * (size_t)prog.n_amp() + 1; }
 
-// Whole adjoint sweep over the stage tape recorded by the forward sweep `tape_gen`.
-// slot_sums (host, [n_steps*6][nred]) receives per slot the per-term sums (det terms: sum_q gd_q;
-// amp terms: sum_q ga_q, sum_q gb_q; last: Re<kbar, k_i>).  Returns the number of launches, or 0
-// if that tape is gone (another forward sweep ran on the plan since) or was incomplete: the
-// caller then falls back to the stage-by-stage adjoint, which recomputes instead.
+// Whole adjoint sweep of n_units units over the stage tape recorded by the forward sweep `tape_gen`.
+// steps[u] = accepted steps of unit u.  slot_sums[u] (host, [n_steps_u*6][nred]) receives per slot
+// the per-term sums (det terms: sum_q gd_q; amp terms: sum_q ga_q, sum_q gb_q; last: Re<kbar, k_i>).
+// gstates: [U][n_t][L] or null; lam_out: [U][L]; d_wacc only for a single unit.
+// Returns the number of launches, or 0 if that tape is gone (another forward sweep ran on the plan
+// since) or was incomplete: the caller then falls back to the stage-by-stage adjoint.
 int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog, const Tableau& tab,
-                       const std::vector<double>& tsave, const double* step_t, const double* step_dt,
-                       const int* step_interval, const int* step_clipped, int n_steps, uint64_t tape_gen,
+                       const std::vector<double>& tsave, int n_units, const double* dv, const double* av,
+                       const std::vector<std::vector<SkStepHost>>& steps, uint64_t tape_gen,
                        const cplx* gstates, bool want_coef, double* d_wacc, cplx* lam_out,
-                       std::vector<double>& slot_sums, cudaStream_t st) {
+                       std::vector<std::vector<double>>& slot_sums, cudaStream_t st) {
   const size_t L = g.dim * (size_t)g.batch;
+  const size_t U = (size_t)n_units;
   int nC;
   if (!small_shape(L, g.batch, nC)) throw Error(PD_ERR_STATE, "small_ket_backward: unsupported shape");
   const int n_t = (int)tsave.size();
   const size_t nred = small_ket_nred(prog);
-  if (tape_gen == 0 || tape_gen != S.tape_gen || S.tape_steps != n_steps) return 0;
-  if ((size_t)n_steps * 6 * nC * nred * sizeof(double) > ((size_t)1 << 30)) return 0;
+  if (tape_gen == 0 || tape_gen != S.tape_gen || S.tape_steps.size() != U) return 0;
+  size_t max_steps = 1;
+  for (size_t u = 0; u < U; ++u) {
+    if (S.tape_steps[u] != (int)steps[u].size()) return 0;
+    max_steps = std::max(max_steps, steps[u].size());
+  }
+  if (U * max_steps * 6 * nC * nred * sizeof(double) > ((size_t)2 << 30)) return 0;
   SkBwd P{};
-  upload_prog(S, prog, g, P.prog, st);
+  upload_prog(S, prog, g, n_units, dv ? dv : prog.det_values.data(), av ? av : prog.amp_values.data(), P.prog, st);
   fill_tab(tab, P.tab);
-  P.batch = g.batch; P.nC = nC; P.dim = g.dim; P.L = L; P.n_t = n_t; P.n_steps = n_steps;
-  std::vector<SkStep> hs(std::max(1, n_steps));
-  for (int i = 0; i < n_steps; ++i) hs[i] = {step_t[i], step_dt[i], step_interval[i], step_clipped[i]};
+  P.batch = g.batch; P.nC = nC; P.dim = g.dim; P.L = L; P.n_t = n_t;
+  P.n_units = n_units; P.max_steps = (int)max_steps; P.tape_cap = S.tape_cap;
+  P.det_stride = (size_t)prog.n_det() * prog.n_samples;
+  P.amp_stride = (size_t)prog.n_amp() * prog.n_samples * 2;
+  std::vector<SkStep> hs(U * max_steps);
+  std::vector<int> hn(U);
+  for (size_t u = 0; u < U; ++u) {
+    hn[u] = (int)steps[u].size();
+    for (size_t i = 0; i < steps[u].size(); ++i)
+      hs[u * max_steps + i] = {steps[u][i].t, steps[u][i].dt, steps[u][i].interval, steps[u][i].clipped};
+  }
   SkStep* d_steps = (SkStep*)S.get(9, sizeof(SkStep) * hs.size());
+  int* d_n = (int*)S.get(7, sizeof(int) * U);
   PD_CUDA_CHECK(cudaMemcpyAsync(d_steps, hs.data(), sizeof(SkStep) * hs.size(), cudaMemcpyHostToDevice, st));
-  P.steps = d_steps;
+  PD_CUDA_CHECK(cudaMemcpyAsync(d_n, hn.data(), sizeof(int) * U, cudaMemcpyHostToDevice, st));
+  P.steps = d_steps; P.unit_steps = d_n; P.n_steps = (int)steps[0].size();
   P.gstates = gstates;
   P.tapeY = (const double*)S.ws[14];
   P.tapeK = (const double*)S.ws[15];
-  P.KB = (uint4*)S.get(3, sizeof(uint4) * 2 * (2 * L));
-  PD_CUDA_CHECK(cudaMemsetAsync(P.KB, 0, sizeof(uint4) * 2 * (2 * L), st));
-  const size_t n_part = std::max<size_t>(1, (size_t)n_steps * 6 * nC * nred);
+  const size_t kb_bytes = sizeof(uint4) * 2 * (2 * L) * U;
+  P.KB = (uint4*)S.get(3, kb_bytes);
+  PD_CUDA_CHECK(cudaMemsetAsync(P.KB, 0, kb_bytes, st));
+  const size_t n_part = U * max_steps * 6 * nC * nred;
   P.slotpart = (double*)S.get(12, sizeof(double) * n_part);
-  double* d_we = d_wacc ? (double*)S.get(13, sizeof(double) * L) : nullptr;
+  double* d_we = d_wacc ? (double*)S.get(13, sizeof(double) * L * U) : nullptr;
+  if (d_wacc && U != 1) throw Error(PD_ERR_INVALID, "pair-coupling gradients are not available for batches of parameter sets");
   P.wacc_elem = d_we;
   P.lam_out = lam_out;
   P.want_coef = want_coef ? 1 : 0;
@@ -222,13 +280,22 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
     k_fold_columns<<<(unsigned)((g.dim + 255) / 256), 256, 0, st>>>(d_we, d_wacc, g.dim, g.batch);
     ++launches;
   }
-  slot_sums.assign((size_t)n_steps * 6 * nred, 0.0);
-  if (want_coef && n_steps > 0) {
-    const size_t n_out = (size_t)n_steps * 6 * nred;
-    double* d_out = (double*)S.get(11, sizeof(double) * n_out);
-    k_sum_slots<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(P.slotpart, d_out, (size_t)n_steps * 6, nC, (int)nred);
-    ++launches;
-    PD_CUDA_CHECK(cudaMemcpyAsync(slot_sums.data(), d_out, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+  slot_sums.assign(U, {});
+  if (want_coef) {
+    const size_t n_out = U * max_steps * 6 * nred;
+    const double* d_src = P.slotpart;
+    if (nC > 1) {
+      double* d_out = (double*)S.get(11, sizeof(double) * n_out);
+      k_sum_slots<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(P.slotpart, d_out, U * max_steps * 6, nC, (int)nred);
+      ++launches;
+      d_src = d_out;
+    }
+    std::vector<double> all(n_out);
+    PD_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_src, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+    PD_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (size_t u = 0; u < U; ++u)
+      slot_sums[u].assign(all.begin() + u * max_steps * 6 * nred,
+                          all.begin() + u * max_steps * 6 * nred + steps[u].size() * 6 * nred);
   }
   PD_CUDA_CHECK(cudaStreamSynchronize(st));
   PD_CUDA_CHECK(cudaGetLastError());

@@ -304,6 +304,11 @@ struct SkFwd {
   double* tapeK;
   int tape_cap;     // steps
   int* abort_flag;  // zeroed by the host; set by a lane whose poll timed out
+  // independent parameter sets ("units", blockIdx.y): same register and masks, own coefficient
+  // values, own controller, own buffers.  n_units > 1 requires nC == 1 (a unit never waits for
+  // another CTA, so the launch needs no co-residency).
+  int n_units;
+  size_t det_stride, amp_stride;   // doubles per unit in prog.det_values / prog.amp_values
 };
 
 template <int NQG>
@@ -321,7 +326,20 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
   const int nq = P.prog.nq;
   const size_t dim = P.dim, L = P.L, L2 = 2 * P.L;
   SkProg prog = P.prog;
+  const size_t unit = blockIdx.y;
+  prog.det_values += unit * P.det_stride;
+  prog.amp_values += unit * P.amp_stride;
   sk_cache_tables(prog, s_tab, tid);
+  // this unit's buffers
+  cplx* const y_io = P.y_io + unit * L;
+  cplx* const k0_io = P.k0_io + unit * L;
+  cplx* const states = P.states + unit * (size_t)P.n_t * L;
+  uint4* const YS = P.YS + unit * 2 * L2;
+  uint4* const red = P.red + unit * 2 * (size_t)P.nC * P.batch;
+  pd_step_record* const log = P.log + unit * (size_t)P.log_cap;
+  SkResume* const resume = P.resume + unit;
+  double* const tapeY = P.tapeY ? P.tapeY + unit * (size_t)P.tape_cap * 6 * L2 : nullptr;
+  double* const tapeK = P.tapeK ? P.tapeK + unit * (size_t)P.tape_cap * 6 * L2 : nullptr;
 
   const size_t r = (size_t)cta * SK_T + tid;
   const bool on = r < L2;
@@ -331,19 +349,99 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
   SkLane<NH> ln;
   sk_lane_init<NH>(ln, e, dim, nq, part, prog.diag[e & (dim - 1)]);
   double y, k[7], ynew = 0.0;
-  y = on ? reinterpret_cast<const double*>(P.y_io)[rr] : 0.0;
-  k[0] = on ? reinterpret_cast<const double*>(P.k0_io)[rr] : 0.0;
+  y = on ? reinterpret_cast<const double*>(y_io)[rr] : 0.0;
+  k[0] = on ? reinterpret_cast<const double*>(k0_io)[rr] : 0.0;
 
-  SkResume R = *P.resume;
+  SkResume R = *resume;
+  if (R.status == 0 && R.kk >= P.n_t) {               // this unit finished in an earlier launch (uniform per CTA)
+    if (cta == 0 && tid == 0) resume->n_rec = 0;
+    return;
+  }
   double t = R.t, dt = R.dt, error = R.error, cache_dt = R.cache_dt, cache_err = R.cache_err;
   long long steps = R.steps_in_interval, pos = R.pos;
   int n_rec = 0, status = 0, par = 0, rpar = 0;
   unsigned seq = 1, rseq = 1;
   int n_acc = R.n_acc;
-  bool tape_ok = R.tape_ok != 0 && P.tapeY != nullptr;
+  bool tape_ok = R.tape_ok != 0 && tapeY != nullptr;
   bool in_interval = R.in_interval != 0;
   const bool replay = P.n_replay > 0;
   int kk = R.kk;
+
+  // max over batch columns of sqrt(mean(sq)) (Hairer norm), identical in every thread of the unit
+  auto col_norm = [&](double sq) -> double {
+    for (int b = 0; b < P.batch; ++b) {
+      const double v = warp_sum_d(col == b ? sq : 0.0);
+      if (lane == 0) s_red[warp][b] = v;
+    }
+    __syncthreads();
+    if (tid < P.batch) {
+      double tot = 0.0;
+      for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w][tid];
+      ll_store(red + ((size_t)rpar * P.nC + cta) * P.batch + tid, tot, rseq);
+    }
+    // every CTA collects all partial sums: warp b (strided) polls the lines of column b, lane j
+    // those of CTAs j, j+32, ... and the warp sums them in a fixed order
+    for (int b = warp; b < P.batch; b += SK_T / 32) {
+      double tot = 0.0;
+      for (int c = lane; c < P.nC; c += 32) {
+        const uint4* src = red + ((size_t)rpar * P.nC + c) * P.batch + b;
+        uint4 v;
+        SkPoll poll{P.abort_flag};
+        do { v = ll_load(src); } while (ll_bad(v, rseq) != 0 && !poll.give_up());
+        tot += ll_value(v);
+      }
+      tot = warp_sum_d(tot);
+      if (lane == 0) s_err[b] = tot;
+    }
+    __syncthreads();
+    double nrm = 0.0;
+    for (int b = 0; b < P.batch; ++b) nrm = fmax(nrm, sqrt(s_err[b] / (double)dim));
+    __syncthreads();          // s_red / s_err are reused by the next reduction
+    ++rseq;
+    rpar ^= 1;
+    return nrm;
+  };
+  // one application of -iH(t_idx) on the lane value v (publishes it, polls the partners)
+  auto apply_at = [&](int cidx, double v) -> double {
+    uint4* buf = YS + (size_t)par * L2;
+    if (on) ll_store(buf + r, v, seq);
+    const double vo = __shfl_xor_sync(0xffffffffu, v, 1);
+    SkStageCoef<NH> sc;
+    sk_stage_coef<NH>(sc, ln, coef[cidx], nq);
+    double out = sk_apply_lane<NH>(sc, ln, vo, buf, seq, on, P.abort_flag);
+    par ^= 1; ++seq;
+    return on ? out : 0.0;
+  };
+
+  if (kk < 0) {
+    // ---- fresh start: k1 = f(t0, y0) and Hairer's initial step ----------
+    t = P.tsave[0];
+    if (tid < 6) s_times[tid] = t;
+    __syncthreads();
+    sk_eval_stages(prog, s_times, coef, tid);
+    k[0] = apply_at(0, y);
+    dt = 0.0;
+    if (!replay) {
+      const double yo = __shfl_xor_sync(0xffffffffu, y, 1);
+      const double sc0 = P.atol + P.rtol * hypot(y, yo);
+      const double a0 = y / sc0, a1 = k[0] / sc0;
+      const double d0 = col_norm(on ? a0 * a0 : 0.0);
+      const double d1 = col_norm(on ? a1 * a1 : 0.0);
+      const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+      __syncthreads();
+      if (tid < 6) s_times[tid] = t + h0;
+      __syncthreads();
+      sk_eval_stages(prog, s_times, coef, tid);
+      const double f1 = apply_at(0, fma(h0, k[0], y));
+      const double a2 = (f1 - k[0]) / sc0;
+      const double d2 = col_norm(on ? a2 * a2 : 0.0) / h0;
+      const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 1.0 / 6.0);
+      dt = fmin(100 * h0, h1);
+    }
+    error = 1.0; cache_dt = dt; cache_err = 1.0;
+    kk = 0;
+    __syncthreads();
+  }
 
   for (; kk < P.n_t && status == 0; ++kk) {
     const double t_next = P.tsave[kk];
@@ -372,13 +470,13 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
       __syncthreads();
       sk_eval_stages(prog, s_times, coef, tid);
       if (tape_ok && n_acc >= P.tape_cap) tape_ok = false;
-      double* tY = tape_ok ? P.tapeY + (size_t)n_acc * 6 * L2 : nullptr;
-      double* tK = tape_ok ? P.tapeK + (size_t)n_acc * 6 * L2 : nullptr;
+      double* tY = tape_ok ? tapeY + (size_t)n_acc * 6 * L2 : nullptr;
+      double* tK = tape_ok ? tapeK + (size_t)n_acc * 6 * L2 : nullptr;
       if (tY && on) { tY[r] = y; tK[r] = k[0]; }
       // ---- stages 2..7 -------------------------------------------------------------------
 #pragma unroll
       for (int i = 1; i < 7; ++i) {
-        uint4* buf = P.YS + (size_t)par * L2;
+        uint4* buf = YS + (size_t)par * L2;
         double v = y;
 #pragma unroll
         for (int j = 0; j < i; ++j) v = fma(dt * P.tab.beta[i - 1][j], k[j], v);
@@ -404,36 +502,7 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
         const double sc = P.atol + P.rtol * sqrt(fmax(m0, m1));
         er /= sc;
       }
-      const double sq = on ? er * er : 0.0;
-      for (int b = 0; b < P.batch; ++b) {
-        const double v = warp_sum_d(col == b ? sq : 0.0);
-        if (lane == 0) s_red[warp][b] = v;
-      }
-      __syncthreads();
-      if (tid < P.batch) {
-        double tot = 0.0;
-        for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w][tid];
-        ll_store(P.red + ((size_t)rpar * P.nC + cta) * P.batch + tid, tot, rseq);
-      }
-      // every CTA collects all partial sums: warp b (strided) polls the lines of column b, lane j
-      // those of CTAs j, j+32, ... and the warp sums them in a fixed order
-      for (int b = warp; b < P.batch; b += SK_T / 32) {
-        double tot = 0.0;
-        for (int c = lane; c < P.nC; c += 32) {
-          const uint4* src = P.red + ((size_t)rpar * P.nC + c) * P.batch + b;
-          uint4 v;
-          SkPoll poll{P.abort_flag};
-          do { v = ll_load(src); } while (ll_bad(v, rseq) != 0 && !poll.give_up());
-          tot += ll_value(v);
-        }
-        tot = warp_sum_d(tot);
-        if (lane == 0) s_err[b] = tot;
-      }
-      __syncthreads();
-      error = 0.0;
-      for (int b = 0; b < P.batch; ++b) error = fmax(error, sqrt(s_err[b] / (double)dim));
-      ++rseq;
-      rpar ^= 1;
+      error = col_norm(on ? er * er : 0.0);
       if (*(volatile int*)P.abort_flag) { status = 5; break; }
       if (!(error == error)) { status = 3; break; }
       const bool accepted = replay ? true : error <= 1.0;
@@ -441,7 +510,7 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
         pd_step_record rec;
         rec.t = t; rec.dt = dt; rec.error = error; rec.accepted = accepted ? 1 : 0;
         rec.clipped = clipped ? 1 : 0; rec.interval = kk; rec._pad = 0;
-        P.log[n_rec] = rec;
+        log[n_rec] = rec;
       }
       ++n_rec;
       if (accepted) {
@@ -454,18 +523,18 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
     if (status != 0) break;
     dt = cache_dt; error = cache_err;
     in_interval = false;
-    if (on) reinterpret_cast<double*>(P.states + (size_t)kk * L)[r] = y;
+    if (on) reinterpret_cast<double*>(states + (size_t)kk * L)[r] = y;
   }
   if (on) {
-    reinterpret_cast<double*>(P.y_io)[r] = y;
-    reinterpret_cast<double*>(P.k0_io)[r] = k[0];
+    reinterpret_cast<double*>(y_io)[r] = y;
+    reinterpret_cast<double*>(k0_io)[r] = k[0];
   }
   if (cta == 0 && tid == 0) {
     SkResume o;
     o.t = t; o.dt = dt; o.error = error; o.cache_dt = cache_dt; o.cache_err = cache_err;
     o.steps_in_interval = steps; o.pos = pos; o.kk = kk; o.in_interval = in_interval ? 1 : 0;
     o.n_rec = n_rec; o.status = status; o.n_acc = n_acc; o.tape_ok = tape_ok ? 1 : 0;
-    *P.resume = o;
+    *resume = o;
   }
 }
 
@@ -493,6 +562,11 @@ struct SkBwd {
   cplx* lam_out;          // [L]
   int want_coef;
   int* abort_flag;
+  // independent units (blockIdx.y), see SkFwd: per-unit step lists (stride max_steps), tapes
+  // (stride tape_cap steps), cotangents, slot sums (stride max_steps*6*nC*nred) and outputs
+  int n_units, max_steps, tape_cap;
+  const int* unit_steps;      // [n_units] accepted steps of each unit (null: n_steps for all)
+  size_t det_stride, amp_stride;
 };
 
 template <int NQG>
@@ -512,8 +586,17 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
   if (tid < n_det) s_dm[tid] = P.prog.det_masks[tid];
   if (tid < n_amp) s_am[tid] = P.prog.amp_masks[tid];
   SkProg prog = P.prog;
+  const size_t unit = blockIdx.y;
+  prog.det_values += unit * P.det_stride;
+  prog.amp_values += unit * P.amp_stride;
   sk_cache_tables(prog, s_tab, tid);
   __syncthreads();
+  const int n_steps = P.unit_steps ? P.unit_steps[unit] : P.n_steps;
+  const SkStep* const steps = P.steps + unit * (size_t)P.max_steps;
+  const double* const tapeY = P.tapeY + unit * (size_t)P.tape_cap * 6 * L2;
+  const double* const tapeK = P.tapeK + unit * (size_t)P.tape_cap * 6 * L2;
+  uint4* const KB = P.KB + unit * 2 * L2;
+  double* const slotpart = P.slotpart + unit * (size_t)P.max_steps * 6 * P.nC * nred;
 
   const size_t r = (size_t)cta * SK_T + tid;
   const bool on = r < L2;
@@ -521,28 +604,28 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
   const size_t e = rr >> 1;
   SkLane<NH> ln;
   sk_lane_init<NH>(ln, e, dim, nq, part, prog.diag[e & (dim - 1)]);
-  const double* gst = reinterpret_cast<const double*>(P.gstates);
+  const double* gst = P.gstates ? reinterpret_cast<const double*>(P.gstates + unit * (size_t)P.n_t * L) : nullptr;
   double wacc = 0.0;
   double lam = (on && gst) ? gst[(size_t)(P.n_t - 1) * L2 + rr] : 0.0;
   int bpar = 0;
   unsigned seq = 1;
-  int hi = P.n_steps;
+  int hi = n_steps;
   for (int kk = P.n_t - 1; kk >= 1; --kk) {
     int lo = hi;
-    while (lo > 0 && P.steps[lo - 1].interval == kk) --lo;
+    while (lo > 0 && steps[lo - 1].interval == kk) --lo;
     for (int gi = hi - 1; gi >= lo; --gi) {
-      const SkStep st = P.steps[gi];
+      const SkStep st = steps[gi];
       const double h = st.dt;
       __syncthreads();
       if (tid < 6) s_times[tid] = tid == 0 ? st.t : st.t + h * P.tab.alpha[tid - 1];
       __syncthreads();
       sk_eval_stages(prog, s_times, coef, tid);
-      const char* tY = reinterpret_cast<const char*>(P.tapeY + (size_t)gi * 6 * L2);
-      const double* tK = P.tapeK + (size_t)gi * 6 * L2;
+      const char* tY = reinterpret_cast<const char*>(tapeY + (size_t)gi * 6 * L2);
+      const double* tK = tapeK + (size_t)gi * 6 * L2;
       double yb[6];
 #pragma unroll
       for (int i = 5; i >= 0; --i) {
-        uint4* buf = P.KB + (size_t)bpar * L2;
+        uint4* buf = KB + (size_t)bpar * L2;
         double u = h * P.tab.b5[i] * lam;
 #pragma unroll
         for (int j = i + 1; j < 6; ++j) u = fma(h * P.tab.beta[j - 1][i], yb[j], u);
@@ -612,7 +695,7 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
           if (tid < nred) {
             double tot = 0.0;
             for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w][tid];
-            P.slotpart[((size_t)gi * 6 + i) * P.nC * nred + (size_t)cta * nred + tid] = tot;
+            slotpart[((size_t)gi * 6 + i) * P.nC * nred + (size_t)cta * nred + tid] = tot;
           }
           __syncthreads();
         }
@@ -624,8 +707,8 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
     if (gst && on) lam += gst[(size_t)(kk - 1) * L2 + r];
   }
   if (on) {
-    reinterpret_cast<double*>(P.lam_out)[r] = lam;
-    if (P.wacc_elem && part == 0) P.wacc_elem[e] = wacc;
+    reinterpret_cast<double*>(P.lam_out + unit * L)[r] = lam;
+    if (P.wacc_elem && part == 0) P.wacc_elem[unit * L + e] = wacc;
   }
 }
 
@@ -656,11 +739,18 @@ inline void fill_tab(const Tableau& t, SkTab& o) {
   for (int j = 0; j < 7; ++j) { o.b5[j] = t.b5[j]; o.eb[j] = t.b5[j] - t.b4[j]; }
 }
 
-// Cooperative launch: all CTAs are guaranteed co-resident, which the polling exchange needs.
+// A unit that spans several CTAs polls lines written by its other CTAs: cooperative launch (all
+// CTAs co-resident).  Units of one CTA never wait for another CTA: plain launch, any grid size.
 template <class K, class PT>
-void launch_coop(K kern, const PT& P, int nC, cudaStream_t s) {
-  void* args[1] = {const_cast<PT*>(&P)};
-  PD_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nC), dim3(SK_T), args, 0, s));
+void launch_units(K kern, const PT& P, int nC, int n_units, cudaStream_t s) {
+  if (nC > 1) {
+    if (n_units != 1) throw Error(PD_ERR_STATE, "small_ket: multi-unit launches need single-CTA units");
+    void* args[1] = {const_cast<PT*>(&P)};
+    PD_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nC), dim3(SK_T), args, 0, s));
+  } else {
+    kern<<<dim3(1, (unsigned)n_units), SK_T, 0, s>>>(P);
+    PD_CUDA_CHECK(cudaGetLastError());
+  }
 }
 
 }  // namespace sk

@@ -4,9 +4,9 @@
 namespace pd {
 namespace sk {
 void launch_forward(int nq, const SkFwd& P, int nC, cudaStream_t st) {
-  if (nq <= 8) launch_coop(k_small_forward<8>, P, nC, st);
-  else if (nq <= 12) launch_coop(k_small_forward<12>, P, nC, st);
-  else launch_coop(k_small_forward<16>, P, nC, st);
+  if (nq <= 8) launch_units(k_small_forward<8>, P, nC, P.n_units, st);
+  else if (nq <= 12) launch_units(k_small_forward<12>, P, nC, P.n_units, st);
+  else launch_units(k_small_forward<16>, P, nC, P.n_units, st);
 }
 }  // namespace sk
 }  // namespace pd

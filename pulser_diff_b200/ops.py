@@ -144,6 +144,64 @@ def evolve(state0: Tensor, tsave: Tensor, det_values: Tensor, amp_values: Tensor
                            float(dt), list(det_masks), list(amp_masks), collapse, int(solver), opt)
 
 
+class _EvolveUnitsFn(torch.autograd.Function):
+    """Batch of independent parameter sets of ONE register (BASELINE configs[2]): unit u evolves
+    ``state0[u]`` under its own coefficient tables ``det_values[u]`` / ``amp_values[u]``.  Kets with
+    ``2*batch*2^N <= 128`` run all units in a single kernel launch (csrc/small_ket.cuh)."""
+
+    @staticmethod
+    def forward(ctx, state0: Tensor, tsave: Tensor, det_values: Tensor, amp_values: Tensor,
+                pair_u: Tensor, n_qubits: int, dt: float, det_masks, amp_masks, opt: Options):
+        n_units, batch = int(state0.shape[0]), int(state0.shape[1])
+        plan = get_plan(n_qubits, batch, PD_KET, state0.device)
+        # the plan carries the masks, dt and sample count; its own tables are those of unit 0
+        prog = make_program(n_qubits, PD_KET, dt, det_masks, det_values[0], amp_masks, amp_values[0],
+                            pair_u, None)
+        configure(plan, prog)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        states, tape = plan.evolve_forward_units(opt, state0.detach(), tsave, det_values, amp_values,
+                                                 want_tape=need)
+        ctx.plan, ctx.prog, ctx.tape = plan, prog, tape
+        ctx.tables = (det_values.detach(), amp_values.detach())
+        ctx.meta = (det_values.device, det_values.dtype, amp_values.device, amp_values.dtype)
+        ctx.save_for_backward(states)
+        ctx.set_materialize_grads(False)
+        return states
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_states: Optional[Tensor]):
+        none = (None,) * 10
+        if grad_states is None or ctx.tape is None:
+            return none
+        (states,) = ctx.saved_tensors
+        configure(ctx.plan, ctx.prog)
+        dv, av = ctx.tables
+        g_det, g_amp, g_s0 = ctx.plan.evolve_backward_units(
+            ctx.tape, states, grad_states.to(torch.complex128).contiguous(), dv, av,
+            want_state0=ctx.needs_input_grad[0])
+        det_dev, det_dt, amp_dev, amp_dt = ctx.meta
+        if g_det is not None:
+            g_det = g_det.to(device=det_dev, dtype=det_dt)
+        if g_amp is not None:
+            g_amp = g_amp.to(device=amp_dev)
+            g_amp = g_amp.to(amp_dt) if amp_dt.is_complex else g_amp.real.to(amp_dt)
+        return (g_s0, None, g_det, g_amp) + (None,) * 6
+
+
+def evolve_units(state0: Tensor, tsave: Tensor, det_values: Tensor, amp_values: Tensor, pair_u: Tensor, *,
+                 n_qubits: int, dt: float, det_masks: Sequence[int], amp_masks: Sequence[int],
+                 options: Optional[Options] = None) -> Tensor:
+    """DP5_SE evolution of ``U`` independent parameter sets of one register.
+
+    ``state0`` (U, batch, 2^N) on the device; ``det_values`` (U, n_det, n_samples) float64 and
+    ``amp_values`` (U, n_amp, n_samples) complex128 (the reference's coefficient arrays, one set per
+    unit); returns states (U, n_t, batch, 2^N).  Differentiable w.r.t. ``state0``, ``det_values`` and
+    ``amp_values`` (not ``tsave`` / ``pair_u``: use :func:`evolve` per unit for those)."""
+    return _EvolveUnitsFn.apply(state0, tsave, det_values, amp_values, pair_u, int(n_qubits), float(dt),
+                                list(det_masks), list(amp_masks), options or Options())
+
+
 def last_step_log(states: Tensor) -> list[dict]:
     """Attempted-step records of the evolution that produced ``states`` (needs a grad graph)."""
     fn = states.grad_fn

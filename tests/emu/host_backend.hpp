@@ -33,16 +33,17 @@ class HostBackend {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_).count();
   }
   size_t reduce_scratch_bytes(const Geometry&) { return 64; }
-  // the small-register cluster kernels exist only in the CUDA build
+  // the small-register cooperative kernels exist only in the CUDA build
   bool small_supported(const Geometry&, const Program&) { return false; }
-  int small_forward(const Geometry&, const Program&, const Tableau&, const pd_options&, const cplx*,
-                    const cplx*, double, const double*, int, cplx*, std::vector<pd_step_record>&, bool,
-                    uint64_t*, void*) {
+  bool small_units_supported(const Geometry&, const Program&) { return false; }
+  int small_forward(const Geometry&, const Program&, const Tableau&, const pd_options&, int, const cplx*,
+                    const double*, const double*, const double*, int, cplx*,
+                    std::vector<std::vector<pd_step_record>>&, bool, uint64_t*, void*) {
     throw Error(PD_ERR_STATE, "small-register kernels need the CUDA build");
   }
-  int small_backward(const Geometry&, const Program&, const Tableau&, const std::vector<double>&,
-                     const double*, const double*, const int*, const int*, int, uint64_t, const cplx*,
-                     bool, double*, cplx*, std::vector<double>&, void*) {
+  int small_backward(const Geometry&, const Program&, const Tableau&, const std::vector<double>&, int,
+                     const double*, const double*, const std::vector<std::vector<SkStepHost>>&, uint64_t,
+                     const cplx*, bool, double*, cplx*, std::vector<std::vector<double>>&, void*) {
     return 0;
   }
   size_t segment_budget_bytes() { return segment_budget; }

@@ -274,3 +274,44 @@ def global_channel_ref(om, ar):
     amp = torch.cat([RP.constant(200, om), RP.blackman(160, ar)])
     det = torch.cat([RP.constant(200, 0.0), RP.ramp(160, 5.0, 0.0)])
     return Channel(amp, det, torch.zeros(360, dtype=torch.float64))
+
+
+@pytest.mark.parametrize("n,batch", [(2, 4), (3, 1), (4, 16)])
+def test_parameter_set_batches(engine_device, n, batch):
+    """BASELINE configs[2]: a batch of pulse-parameter sets of ONE register in one call
+    (ops.evolve_units; on CUDA one CTA per set for 2*batch*2^N <= 128, otherwise set after set)
+    equals evolving every set on its own, states and gradients."""
+    from pulser_diff_b200 import _cabi, ops
+    dev = engine_device
+    U, T = 5, 20
+    g = torch.Generator().manual_seed(7)
+    full = (1 << n) - 1
+    dv = (torch.rand(U, 2, T, dtype=torch.float64, generator=g) - 0.5) * 3
+    av = torch.complex(torch.rand(U, 1, T, dtype=torch.float64, generator=g) * 4,
+                       torch.rand(U, 1, T, dtype=torch.float64, generator=g) - 0.5)
+    det_masks, amp_masks = [full, 1], [full]
+    x = torch.arange(n, dtype=torch.float64) * 6.5
+    pu = torch.zeros(n, n, dtype=torch.float64)
+    for i in range(n):
+        for j in range(i + 1, n):
+            pu[i, j] = 865723.02 / float(abs(x[i] - x[j])) ** 6
+    psi0 = torch.eye(2 ** n, dtype=torch.complex128)[:batch].repeat(U, 1, 1).to(dev)
+    tsave = torch.tensor([0.0, 0.003, 0.0071, 0.012], dtype=torch.float64)
+    w = torch.arange(2 ** n, dtype=torch.float64, device=dev).remainder(3) + 0.5
+
+    def loss_of(st):          # st: (..., n_t, batch, dim)
+        return (w * st[..., -1, :, :].abs() ** 2).sum() + (w * st[..., 1, :, :].real).sum()
+
+    dvb, avb, p0b = (t.clone().requires_grad_(True) for t in (dv, av, psi0))
+    st_b = ops.evolve_units(p0b, tsave, dvb, avb, pu, n_qubits=n, dt=0.001, det_masks=det_masks,
+                            amp_masks=amp_masks)
+    assert st_b.shape == (U, 4, batch, 2 ** n)
+    gb = torch.autograd.grad(loss_of(st_b), [dvb, avb, p0b])
+    for u in range(U):
+        dvu, avu, p0u = (t[u].clone().requires_grad_(True) for t in (dv, av, psi0))
+        st_u = ops.evolve(p0u, tsave, dvu, avu, pu, n_qubits=n, kind=_cabi.PD_KET, dt=0.001,
+                          det_masks=det_masks, amp_masks=amp_masks)
+        assert (st_u.detach() - st_b.detach()[u]).abs().max() < 1e-12
+        gu = torch.autograd.grad(loss_of(st_u), [dvu, avu, p0u])
+        for a, b in zip(gu, gb):
+            assert (a - b[u]).abs().max() < 1e-10 * max(1.0, a.abs().max().item())
