@@ -160,3 +160,46 @@ def test_small_cluster_kernels_equal_gather(cuda_device, n, batch, local):
     assert (st_g - st_s).abs().max() < 1e-12
     for a, b in zip(g_g, g_s):
         assert (a - b).abs().max() < 1e-9 * max(1e-30, b.abs().max().item())
+
+
+def test_c2_workload_vs_oracle_first_intervals(cuda_device):
+    """BASELINE configs[1] at FULL size (12-atom chain, the bench workload): the first two tsave
+    intervals against the oracle on the same seeded inputs -- states to 1e-10 and the gradient
+    w.r.t. the 60 pulse parameters to 1e-8 relative (shared accepted-step sequence), plus the
+    free-running controller taking the same decisions."""
+    import os, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench as B
+    from helpers import Channel, Problem
+    from oracle.ref_solvers import SolverType as RefSolver, sesolve as ref_sesolve
+    from pulser_diff_b200.utils import interpolate_sine
+
+    dev = cuda_device
+    interp = interpolate_sine(B.N_PARAM, B.DURATION).to(torch.float64)
+    ta, td = B.workload_params(0)
+    amp, det, ph = B.pulse_samples(ta, td, interp)
+    p = Problem(B.chain_coords(B.N_QUBITS), B.C6, [Channel(amp, det, ph)], rate=B.RATE)
+    ref = p.ref()
+    ts = ref.evaluation_times[:3].clone()
+    r = ref_sesolve(ref.ham.H, ref.initial_state, ts, RefSolver.DP5_SE, {})
+    d = B.loss_diag(B.N_QUBITS, "cpu")
+    loss_r = (d[:, None] * r.states[-1].abs() ** 2).sum()
+    g_ref = torch.autograd.grad(loss_r, [ta, td], retain_graph=True)
+
+    em = p.emulator(dev)
+    H = em._hamiltonian._hamiltonian
+    accepted = [rec for rec in r.steplog if rec[2]]
+    res = pdb.sesolve(H, em.initial_state, ts, pdb.SolverType.DP5_SE,
+                      options={"replay": [(dt, clipped) for (_, dt, _, _, clipped) in accepted]})
+    assert (res.states.detach().cpu() - r.states.detach()).abs().max() < 1e-10
+    loss = (d.to(dev)[:, None] * res.states[-1].abs() ** 2).sum()
+    assert abs(loss.item() - loss_r.item()) < 1e-10
+    g = torch.autograd.grad(loss, [ta, td], retain_graph=True)
+    for a, b in zip(g, g_ref):
+        assert (a.cpu() - b).abs().max() < 1e-8 * b.abs().max()
+    # free-running controller: same accept/reject pattern as the oracle's
+    res2 = pdb.sesolve(H, em.initial_state, ts, pdb.SolverType.DP5_SE)
+    log = res2.step_log()
+    assert [bool(a["accepted"]) for a in log] == [bool(b[2]) for b in r.steplog]
+    assert (res2.states.detach().cpu() - r.states.detach()).abs().max() < 1e-7
