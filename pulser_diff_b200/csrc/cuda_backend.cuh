@@ -67,6 +67,10 @@ constexpr int kAutoTiledMinQubits = 18;   // below this the whole working set is
 bool stream_ket_supported(const Geometry& g);
 int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, const cplx* const* ins,
                             const double* w, const SiteOps& so, cudaStream_t s);
+int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cplx* ynew, cplx* ymat, cplx* aux,
+                           const SiteOps* stage_ops, const double* beta, const double* ew, double dt,
+                           double atol, double rtol, double* err_partial, double* err_out, cudaStream_t s);
+size_t stream_err_partial_count(const Geometry& g);
 // small-register family (small_ket.cu): whole forward / adjoint sweep in one cluster kernel
 struct SmallKetState;
 SmallKetState* small_ket_create();
@@ -202,6 +206,12 @@ class CudaBackend {
                    const SiteOps* stage_ops, const Tableau& tab, const double* ew, double dt,
                    double atol, double rtol, cplx* tmp_a, cplx* tmp_b, double* red_scratch,
                    double* err_out, void* s) {
+    if (use_stream(g)) {
+      // ew holds dt*(b5-b4); the stream step wants the weights of the slopes directly
+      if (stream_err_partial_count(g) > (size_t)kMaxReduceBlocks * kMaxR * 2) return 0;
+      return launch_stream_dp5_step(g, y, k, ynew, tmp_a, tmp_b, stage_ops, &tab.beta[0][0], ew, dt, atol, rtol,
+                                    red_scratch, err_out, st(s));
+    }
     if (!use_tiled(g)) return 0;
     if (tiled_err_partial_count(g) > (size_t)kMaxReduceBlocks * kMaxR * 2) return 0;
     return launch_tiled_dp5_step(g, y, k, ynew, stage_ops, &tab.beta[0][0], tab.b5, ew, dt, atol,

@@ -48,6 +48,14 @@ struct StreamParams {
   cplx* ymat;                 // A launch: combined input written here (nullable)
   cplx* out;
   const double* diag;
+  // embedded error estimate of the Dormand-Prince step (last stage only):
+  //   A launch:      aux = sum_j w2_j v_j                  (partial error vector, w2 = dt*(b5-b4))
+  //   last g launch: err = aux + werr*out;  sum |err / (atol + rtol*max(|y0|,|Ymat|))|^2 per CTA
+  double w2[kMaxIn];
+  cplx* aux;                  // A: written (nullable);  g: read when err_partial != null
+  const cplx* y0;
+  double werr, atol, rtol;
+  double* err_partial;        // [gridDim.x] (g launch, nullable)
 };
 
 __device__ __forceinline__ cplx ldg(const cplx* p) {
@@ -90,11 +98,12 @@ k_stream_a(const __grid_constant__ StreamParams P, const __grid_constant__ Strea
 
   // ---- combination: Y = sum_j w_j v_j, 4 elements x 2 vectors in flight per thread
   constexpr int QP = 4;
+  const bool want_aux = P.aux != nullptr;          // uniform
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += QP) {
-    cplx y[QP];
+    cplx y[QP], z[QP];
 #pragma unroll
-    for (int i = 0; i < QP; ++i) y[i] = {0.0, 0.0};
+    for (int i = 0; i < QP; ++i) { y[i] = {0.0, 0.0}; z[i] = {0.0, 0.0}; }
     for (int j = 0; j < P.n_in; j += 2) {
       const bool two = j + 1 < P.n_in;               // uniform
       const cplx* v0 = P.v[j] + base;
@@ -111,16 +120,31 @@ k_stream_a(const __grid_constant__ StreamParams P, const __grid_constant__ Strea
         for (int i = 0; i < QP; ++i) {
           y[i].re = fma(w1, x1[i].re, y[i].re); y[i].im = fma(w1, x1[i].im, y[i].im);
         }
+        if (want_aux) {
+          const double u1 = P.w2[j + 1];
+#pragma unroll
+          for (int i = 0; i < QP; ++i) {
+            z[i].re = fma(u1, x1[i].re, z[i].re); z[i].im = fma(u1, x1[i].im, z[i].im);
+          }
+        }
       }
 #pragma unroll
       for (int i = 0; i < QP; ++i) {
         y[i].re = fma(w0, x0[i].re, y[i].re); y[i].im = fma(w0, x0[i].im, y[i].im);
+      }
+      if (want_aux) {
+        const double u0 = P.w2[j];
+#pragma unroll
+        for (int i = 0; i < QP; ++i) {
+          z[i].re = fma(u0, x0[i].re, z[i].re); z[i].im = fma(u0, x0[i].im, z[i].im);
+        }
       }
     }
 #pragma unroll
     for (int i = 0; i < QP; ++i) {
       T[t + NT * (q0 + i)] = y[i];
       if (P.ymat) P.ymat[base + t + NT * (q0 + i)] = y[i];
+      if (want_aux) P.aux[base + t + NT * (q0 + i)] = z[i];
     }
   }
   __syncthreads();
@@ -189,6 +213,7 @@ k_stream_g(const __grid_constant__ StreamParams P, const __grid_constant__ Strea
     for (int i = 0; i < 8; ++i) T[t + NT * (q0 + i)] = x[i];
   }
   __syncthreads();
+  double err_acc = 0.0;
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += 4) {
     size_t gi[4];
@@ -222,6 +247,29 @@ k_stream_g(const __grid_constant__ StreamParams P, const __grid_constant__ Strea
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) out[gi[i]] = acc[i];
+    if (P.err_partial) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const cplx ep = ldcs(P.aux + boff + gi[i]);
+        const cplx y0 = ldcs(P.y0 + boff + gi[i]);
+        const cplx y1 = T[t + NT * (q0 + i)];
+        const double sc = P.atol + P.rtol * fmax(hypot(y0.re, y0.im), hypot(y1.re, y1.im));
+        const double er = fma(P.werr, acc[i].re, ep.re) / sc, ei = fma(P.werr, acc[i].im, ep.im) / sc;
+        err_acc += er * er + ei * ei;
+      }
+    }
+  }
+  if (P.err_partial) {
+    __shared__ double red[NT / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) err_acc += __shfl_xor_sync(0xffffffffu, err_acc, o);
+    if ((t & 31) == 0) red[t >> 5] = err_acc;
+    __syncthreads();
+    if (t == 0) {
+      double sacc = 0.0;
+      for (int w = 0; w < NT / 32; ++w) sacc += red[w];
+      P.err_partial[blockIdx.x] = sacc;
+    }
   }
 }
 
@@ -296,6 +344,79 @@ int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, 
   }
   PD_CUDA_CHECK(cudaGetLastError());
   return n;
+}
+
+
+namespace {
+__global__ void k_stream_sum_partials(const double* __restrict__ partial, int per_col, double* out) {
+  __shared__ double sh[32];
+  const int b = blockIdx.x;
+  double s = 0.0;
+  for (int i = threadIdx.x; i < per_col; i += blockDim.x) s += partial[(size_t)b * per_col + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += sh[w];
+    out[b] = tot;
+  }
+}
+}  // namespace
+
+size_t stream_err_partial_count(const Geometry& g) { return (g.dim >> TB) * (size_t)g.batch; }
+
+// One Dormand-Prince step with the stream kernels: stages 2..7 (k[0] = f(t, y) on entry, FSAL),
+// ynew = y_{n+1}, and the embedded error estimate folded into the stage-7 launches (the A launch
+// forms the partial error vector from the slopes it reads anyway, the last group launch finishes
+// it): err_out[b] = sum |err/scale|^2 per batch column.  aux: scratch vector.
+int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cplx* ynew, cplx* ymat, cplx* aux,
+                           const SiteOps* stage_ops /* [7], index i = stage i+1 */, const double* beta,
+                           const double* ew, double dt, double atol, double rtol, double* err_partial,
+                           double* err_out, cudaStream_t s) {
+  set_attrs();
+  const unsigned grid = (unsigned)((g.dim >> TB) * (size_t)g.batch);
+  const int rest = g.nq - TB;
+  const int G = (rest + kMaxGroupBits - 1) / kMaxGroupBits;
+  int n = 0;
+  for (int i = 1; i < 7; ++i) {
+    StreamCoef cf;
+    fill_coef(stage_ops[i], g.nq, cf);
+    const bool uni = uniform_drive(cf, g.nq);
+    const bool last = i == 6;
+    cplx* ym = last ? ynew : ymat;
+    StreamParams A{};
+    A.nq = g.nq; A.dim = g.dim; A.diag = g.diag; A.ymat = ym; A.out = k[i];
+    int m = 0;
+    A.v[m] = y; A.w[m] = 1.0; A.w2[m] = 0.0; ++m;
+    for (int j = 0; j < i; ++j) {
+      const double b = beta[(i - 1) * 6 + j];
+      if (b != 0.0 || (last && ew[j] != 0.0)) { A.v[m] = k[j]; A.w[m] = dt * b; A.w2[m] = last ? ew[j] : 0.0; ++m; }
+    }
+    A.n_in = m;
+    A.aux = last ? aux : nullptr;
+    if (uni) k_stream_a<true><<<grid, NT, TILE * 16, s>>>(A, cf);
+    else k_stream_a<false><<<grid, NT, TILE * 16, s>>>(A, cf);
+    ++n;
+    int lo = TB;
+    for (int gi = 0; gi < G; ++gi) {
+      const int nb = rest / G + (gi < rest % G ? 1 : 0);
+      StreamParams B{};
+      B.nq = g.nq; B.dim = g.dim; B.n_in = 1; B.v[0] = ym; B.w[0] = 1.0; B.out = k[i];
+      B.lo = lo; B.nb = nb; B.C = TB - nb;
+      if (last && gi == G - 1) {
+        B.aux = aux; B.y0 = y; B.werr = ew[6]; B.atol = atol; B.rtol = rtol; B.err_partial = err_partial;
+      }
+      if (uni) k_stream_g<true><<<grid, NT, TILE * 16, s>>>(B, cf);
+      else k_stream_g<false><<<grid, NT, TILE * 16, s>>>(B, cf);
+      lo += nb;
+      ++n;
+    }
+  }
+  k_stream_sum_partials<<<g.batch, 256, 0, s>>>(err_partial, (int)(g.dim >> TB), err_out);
+  PD_CUDA_CHECK(cudaGetLastError());
+  return n + 1;
 }
 
 }  // namespace pd
