@@ -74,29 +74,55 @@ def loss_diag(n, device):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons DURING the timed region.  NVML in-process (nvidia_ml_py): spawning
+    `nvidia-smi` every 200 ms takes driver locks that stall the launches of a 10-ms timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = pynvml
+            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+        except Exception:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        flags = ["Active" if mask & bits[n] else "Not Active" for n in self.NAMES]
+        self.rows.append([str(sm), str(self._max), "0"] + flags)
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(",")])
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([x.strip() for x in out.strip().split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05 if self._nvml is not None else 0.2)
 
     def summary(self):
         self._halt.set()
         self.join(timeout=2)
         sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        names = self.NAMES
         for r in self.rows:
             try:
                 sm.append(float(r[0])); mx = max(mx, float(r[1]))
@@ -107,7 +133,8 @@ class ClockSampler(threading.Thread):
                 continue
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def measured_traffic(key: str):
