@@ -127,7 +127,7 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
   P.k0_io = (cplx*)S.get(2, sizeof(cplx) * L * U);
   PD_CUDA_CHECK(cudaMemcpyAsync(P.y_io, y0, sizeof(cplx) * L * U, cudaMemcpyDeviceToDevice, st));
   P.states = states;
-  const size_t ys_bytes = sizeof(uint4) * 2 * (2 * L) * U, red_bytes = sizeof(uint4) * 2 * (nC * (SK_T / 32)) * g.batch * U;
+  const size_t ys_bytes = sizeof(uint4) * 2 * (2 * L) * U, red_bytes = sizeof(uint4) * 2 * nC * g.batch * U;
   P.YS = (uint4*)S.get(3, ys_bytes);
   P.red = (uint4*)S.get(4, red_bytes);
   P.log = (pd_step_record*)S.get(5, sizeof(pd_step_record) * log_cap * U);
@@ -239,8 +239,7 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
     if (S.tape_steps[u] != (int)steps[u].size()) return 0;
     max_steps = std::max(max_steps, steps[u].size());
   }
-  const int nW = nC * (SK_T / 32);     // every warp writes its own partial sums
-  if (U * max_steps * 6 * nW * nred * sizeof(double) > ((size_t)4 << 30)) return 0;
+  if (U * max_steps * 6 * nC * nred * sizeof(double) > ((size_t)2 << 30)) return 0;
   SkBwd P{};
   upload_prog(S, prog, g, n_units, dv ? dv : prog.det_values.data(), av ? av : prog.amp_values.data(), P.prog, st);
   fill_tab(tab, P.tab);
@@ -266,7 +265,7 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
   const size_t kb_bytes = sizeof(uint4) * 2 * (2 * L) * U;
   P.KB = (uint4*)S.get(3, kb_bytes);
   PD_CUDA_CHECK(cudaMemsetAsync(P.KB, 0, kb_bytes, st));
-  const size_t n_part = U * max_steps * 6 * nW * nred;
+  const size_t n_part = U * max_steps * 6 * nC * nred;
   P.slotpart = (double*)S.get(12, sizeof(double) * n_part);
   double* d_we = d_wacc ? (double*)S.get(13, sizeof(double) * L * U) : nullptr;
   if (d_wacc && U != 1) throw Error(PD_ERR_INVALID, "pair-coupling gradients are not available for batches of parameter sets");
@@ -284,10 +283,13 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
   slot_sums.assign(U, {});
   if (want_coef) {
     const size_t n_out = U * max_steps * 6 * nred;
-    double* d_out = (double*)S.get(11, sizeof(double) * n_out);
-    k_sum_slots<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(P.slotpart, d_out, U * max_steps * 6, nW, (int)nred);
-    ++launches;
-    const double* d_src = d_out;
+    const double* d_src = P.slotpart;
+    if (nC > 1) {
+      double* d_out = (double*)S.get(11, sizeof(double) * n_out);
+      k_sum_slots<<<(unsigned)((n_out + 255) / 256), 256, 0, st>>>(P.slotpart, d_out, U * max_steps * 6, nC, (int)nred);
+      ++launches;
+      d_src = d_out;
+    }
     std::vector<double> all(n_out);
     PD_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_src, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
     PD_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -96,12 +96,18 @@ struct SkCoef {
   int pad;
 };
 
-// Reference interpolation rule (hamiltonian.py:532-542) for qubit q given the sample pair (i1, i2)
-// and the fraction x = (t - i1*dt)/dt of the stage time.
-__device__ __forceinline__ void sk_eval_one(const SkProg& P, int i1, int i2, double x, SkCoef* c, int q) {
+// Thread (stage i, qubit q) evaluates the reference interpolation rule (hamiltonian.py:532-542)
+// at that stage's time; all stage times of a step are known when the step starts.
+__device__ __forceinline__ void sk_eval_one(const SkProg& P, double t, SkCoef* c, int q) {
   const int ns = P.n_samples;
   double d = 0.0, gre = 0.0, gim = 0.0;
   if (ns >= 2) {
+    const double fl = floor(t / P.dt);
+    long i1 = (long)fmin(fl, (double)(ns - 2));
+    if (i1 < 0) i1 = 0;
+    long i2 = i1 + 1 < (long)(ns - 2) ? i1 + 1 : (long)(ns - 2);
+    if (i2 < 0) i2 = 0;
+    const double x = (t - i1 * P.dt) / P.dt;
     for (int k = 0; k < P.n_det; ++k)
       if (P.det_masks[k] >> q & 1ull) {
         const double* v = P.det_values + (size_t)k * ns;
@@ -120,41 +126,17 @@ __device__ __forceinline__ void sk_eval_one(const SkProg& P, int i1, int i2, dou
   c->gre[p] = gre;
   c->gim[p] = gim;
 }
-// Coefficient sets of the six stage times t0 + al[i]*h (al[i] < 0: the time t0 itself), evaluated
-// by every warp for itself into its own shared-memory slice: warps never wait for each other.
-// Lane i < 6 finds the sample pair of stage i once; the (stage, qubit) entries are spread over the lanes.
-__device__ __forceinline__ void sk_eval_stages(const SkProg& P, double t0, double h, const double* al6, SkCoef* c,
-                                               int lane) {
-  __syncwarp();
-  int i1 = 0, i2 = 0;
-  double x = 0.0;
-  if (lane < 6 && P.n_samples >= 2) {
-    const double a = al6[lane];
-    const double t = a < 0.0 ? t0 : t0 + h * a;
-    const int ns = P.n_samples;
-    const double fl = floor(t / P.dt);
-    long j1 = (long)fmin(fl, (double)(ns - 2));
-    if (j1 < 0) j1 = 0;
-    long j2 = j1 + 1 < (long)(ns - 2) ? j1 + 1 : (long)(ns - 2);
-    if (j2 < 0) j2 = 0;
-    i1 = (int)j1; i2 = (int)j2;
-    x = (t - j1 * P.dt) / P.dt;
-  }
-  for (int w0 = 0; w0 < 6 * P.nq; w0 += 32) {
-    const int w = w0 + lane;
-    const int i = w < 6 * P.nq ? w / P.nq : 0;
-    const int a1 = __shfl_sync(0xffffffffu, i1, i), a2 = __shfl_sync(0xffffffffu, i2, i);
-    const double xx = __shfl_sync(0xffffffffu, x, i);
-    if (w < 6 * P.nq) sk_eval_one(P, a1, a2, xx, &c[i], w % P.nq);
-  }
-  __syncwarp();
-  if (lane < 6) {
+// times[i] for i in [0, 6): coefficient set i.  Two __syncthreads inside.
+__device__ __forceinline__ void sk_eval_stages(const SkProg& P, const double* times, SkCoef* c, int tid) {
+  for (int w = tid; w < 6 * P.nq; w += SK_T) sk_eval_one(P, times[w / P.nq], &c[w / P.nq], w % P.nq);
+  __syncthreads();
+  if (tid < 6) {
     int u = 1;
     for (int p = 1; p < P.nq; ++p)
-      u &= (c[lane].d[p] == c[lane].d[0]) & (c[lane].gre[p] == c[lane].gre[0]) & (c[lane].gim[p] == c[lane].gim[0]);
-    c[lane].uniform = u;
+      u &= (c[tid].d[p] == c[tid].d[0]) & (c[tid].gre[p] == c[tid].gre[0]) & (c[tid].gim[p] == c[tid].gim[0]);
+    c[tid].uniform = u;
   }
-  __syncwarp();
+  __syncthreads();
 }
 
 // Copies the pulse tables into shared memory when they fit (the per-stage interpolation then costs
@@ -332,16 +314,15 @@ struct SkFwd {
 template <int NQG>
 __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ SkFwd P) {
   constexpr int NH = NQG / 2;
-  __shared__ SkCoef coef_all[SK_T / 32][6];
-  __shared__ double s_al[2][6];
+  __shared__ SkCoef coef[6];
+  __shared__ double s_red[SK_T / 32][SK_MAXB];
+  __shared__ double s_err[SK_MAXB];
+  __shared__ double s_times[6];
+  __shared__ double s_fac;
   __shared__ __align__(16) unsigned char s_tab[SK_TABLE_BYTES];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int part = tid & 1;
   const unsigned cta = blockIdx.x;
-  SkCoef* const coef = coef_all[warp];
-  const int nW = P.nC * (SK_T / 32), gw = (int)cta * (SK_T / 32) + warp;   // warps of the unit, own index
-  if (tid < 6) { s_al[0][tid] = P.tab.alpha[tid]; s_al[1][tid] = -1.0; }
-  __syncthreads();
   const int nq = P.prog.nq;
   const size_t dim = P.dim, L = P.L, L2 = 2 * P.L;
   SkProg prog = P.prog;
@@ -354,7 +335,7 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
   cplx* const k0_io = P.k0_io + unit * L;
   cplx* const states = P.states + unit * (size_t)P.n_t * L;
   uint4* const YS = P.YS + unit * 2 * L2;
-  uint4* const red = P.red + unit * 2 * (size_t)nW * P.batch;
+  uint4* const red = P.red + unit * 2 * (size_t)P.nC * P.batch;
   pd_step_record* const log = P.log + unit * (size_t)P.log_cap;
   SkResume* const resume = P.resume + unit;
   double* const tapeY = P.tapeY ? P.tapeY + unit * (size_t)P.tape_cap * 6 * L2 : nullptr;
@@ -388,38 +369,34 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
 
   // max over batch columns of sqrt(mean(sq)) (Hairer norm), identical in every thread of the unit
   auto col_norm = [&](double sq) -> double {
-    // every warp publishes its per-column partial sums as flag-in-data lines and collects those of
-    // all warps of the unit (lane j polls warps j, j+32, ...; fixed summation order, so every warp
-    // obtains bitwise the same norm): no block-level barrier
     for (int b = 0; b < P.batch; ++b) {
       const double v = warp_sum_d(col == b ? sq : 0.0);
-      if (lane == 0) ll_store(red + ((size_t)rpar * nW + gw) * P.batch + b, v, rseq);
+      if (lane == 0) s_red[warp][b] = v;
     }
-    double nrm = 0.0;
-    for (int b = 0; b < P.batch; ++b) {
+    __syncthreads();
+    if (tid < P.batch) {
       double tot = 0.0;
-      for (int c0 = 0; c0 < nW; c0 += 32 * 8) {          // up to 8 lines in flight per lane
-        uint4 v[8];
-        unsigned bad;
+      for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w][tid];
+      ll_store(red + ((size_t)rpar * P.nC + cta) * P.batch + tid, tot, rseq);
+    }
+    // every CTA collects all partial sums: warp b (strided) polls the lines of column b, lane j
+    // those of CTAs j, j+32, ... and the warp sums them in a fixed order
+    for (int b = warp; b < P.batch; b += SK_T / 32) {
+      double tot = 0.0;
+      for (int c = lane; c < P.nC; c += 32) {
+        const uint4* src = red + ((size_t)rpar * P.nC + c) * P.batch + b;
+        uint4 v;
         SkPoll poll{P.abort_flag};
-        do {
-          bad = 0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j * 32 + lane;
-            if (c < nW) {
-              v[j] = ll_load(red + ((size_t)rpar * nW + c) * P.batch + b);
-              bad |= ll_bad(v[j], rseq);
-            }
-          }
-        } while (bad != 0 && !poll.give_up());
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (c0 + j * 32 + lane < nW) tot += ll_value(v[j]);
+        do { v = ll_load(src); } while (ll_bad(v, rseq) != 0 && !poll.give_up());
+        tot += ll_value(v);
       }
       tot = warp_sum_d(tot);
-      nrm = fmax(nrm, sqrt(tot / (double)dim));
+      if (lane == 0) s_err[b] = tot;
     }
+    __syncthreads();
+    double nrm = 0.0;
+    for (int b = 0; b < P.batch; ++b) nrm = fmax(nrm, sqrt(s_err[b] / (double)dim));
+    __syncthreads();          // s_red / s_err are reused by the next reduction
     ++rseq;
     rpar ^= 1;
     return nrm;
@@ -439,7 +416,9 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
   if (kk < 0) {
     // ---- fresh start: k1 = f(t0, y0) and Hairer's initial step ----------
     t = P.tsave[0];
-    sk_eval_stages(prog, t, 0.0, s_al[1], coef, lane);
+    if (tid < 6) s_times[tid] = t;
+    __syncthreads();
+    sk_eval_stages(prog, s_times, coef, tid);
     k[0] = apply_at(0, y);
     dt = 0.0;
     if (!replay) {
@@ -449,7 +428,10 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
       const double d0 = col_norm(on ? a0 * a0 : 0.0);
       const double d1 = col_norm(on ? a1 * a1 : 0.0);
       const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-      sk_eval_stages(prog, t + h0, 0.0, s_al[1], coef, lane);
+      __syncthreads();
+      if (tid < 6) s_times[tid] = t + h0;
+      __syncthreads();
+      sk_eval_stages(prog, s_times, coef, tid);
       const double f1 = apply_at(0, fma(h0, k[0], y));
       const double a2 = (f1 - k[0]) / sc0;
       const double d2 = col_norm(on ? a2 * a2 : 0.0) / h0;
@@ -458,6 +440,7 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
     }
     error = 1.0; cache_dt = dt; cache_err = 1.0;
     kk = 0;
+    __syncthreads();
   }
 
   for (; kk < P.n_t && status == 0; ++kk) {
@@ -468,8 +451,10 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
       if (n_rec >= P.log_cap) { status = 1; break; }
       bool clipped;
       if (!replay) {
-        // update_tstep
-        const double fac = error == 0.0 ? 0.0 : P.safety * pow(error, -0.2);
+        // update_tstep; the pow is evaluated by one thread
+        if (tid == 0) s_fac = error == 0.0 ? 0.0 : P.safety * pow(error, -0.2);
+        __syncthreads();
+        const double fac = s_fac;
         if (error == 0.0) dt = dt * P.maxf;
         else dt = error <= 1.0 ? dt * fmax(1.0, fmin(P.maxf, fac)) : dt * fmin(0.9, fmax(P.minf, fac));
         clipped = t + dt >= t_next;
@@ -481,7 +466,9 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
       }
       if (clipped) { cache_dt = dt; cache_err = error; dt = t_next - t; }
       // coefficients of the six stage times
-      sk_eval_stages(prog, t, dt, s_al[0], coef, lane);
+      if (tid < 6) s_times[tid] = t + dt * P.tab.alpha[tid];
+      __syncthreads();
+      sk_eval_stages(prog, s_times, coef, tid);
       if (tape_ok && n_acc >= P.tape_cap) tape_ok = false;
       double* tY = tape_ok ? tapeY + (size_t)n_acc * 6 * L2 : nullptr;
       double* tK = tape_ok ? tapeK + (size_t)n_acc * 6 * L2 : nullptr;
@@ -585,16 +572,14 @@ struct SkBwd {
 template <int NQG>
 __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__ SkBwd P) {
   constexpr int NH = NQG / 2;
-  __shared__ SkCoef coef_all[SK_T / 32][6];
+  __shared__ SkCoef coef[6];
+  __shared__ double s_red[SK_T / 32][2 * SK_MAXTERMS + SK_MAXTERMS + 1];
   __shared__ unsigned long long s_dm[SK_MAXTERMS], s_am[SK_MAXTERMS];
-  __shared__ double s_al[6];
+  __shared__ double s_times[6];
   __shared__ __align__(16) unsigned char s_tab[SK_TABLE_BYTES];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int part = tid & 1;
   const unsigned cta = blockIdx.x;
-  SkCoef* const coef = coef_all[warp];
-  const int nW = P.nC * (SK_T / 32), gw = (int)cta * (SK_T / 32) + warp;   // warps of the unit, own index
-  if (tid < 6) s_al[tid] = tid == 0 ? -1.0 : P.tab.alpha[tid - 1];
   const int nq = P.prog.nq, n_det = P.prog.n_det, n_amp = P.prog.n_amp;
   const int nred = n_det + 2 * n_amp + 1;
   const size_t L = P.L, dim = P.dim, L2 = 2 * P.L;
@@ -611,7 +596,7 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
   const double* const tapeY = P.tapeY + unit * (size_t)P.tape_cap * 6 * L2;
   const double* const tapeK = P.tapeK + unit * (size_t)P.tape_cap * 6 * L2;
   uint4* const KB = P.KB + unit * 2 * L2;
-  double* const slotpart = P.slotpart + unit * (size_t)P.max_steps * 6 * nW * nred;
+  double* const slotpart = P.slotpart + unit * (size_t)P.max_steps * 6 * P.nC * nred;
 
   const size_t r = (size_t)cta * SK_T + tid;
   const bool on = r < L2;
@@ -631,7 +616,10 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
     for (int gi = hi - 1; gi >= lo; --gi) {
       const SkStep st = steps[gi];
       const double h = st.dt;
-      sk_eval_stages(prog, st.t, h, s_al, coef, lane);
+      __syncthreads();
+      if (tid < 6) s_times[tid] = tid == 0 ? st.t : st.t + h * P.tab.alpha[tid - 1];
+      __syncthreads();
+      sk_eval_stages(prog, s_times, coef, tid);
       const char* tY = reinterpret_cast<const char*>(tapeY + (size_t)gi * 6 * L2);
       const double* tK = tapeK + (size_t)gi * 6 * L2;
       double yb[6];
@@ -679,8 +667,6 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
                 gb[j] = a ? fl_re : -fl_re;
               }
             }
-            // every warp writes its own partial sums (summed over the warps of the unit afterwards)
-            double* dst = slotpart + (((size_t)gi * 6 + i) * nW + gw) * nred;
             for (int kd = 0; kd < n_det; ++kd) {
               const unsigned long long m = s_dm[kd];
               double v = 0.0;
@@ -688,7 +674,7 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
               for (int j = 0; j < NH; ++j)
                 if (j < ln.jmax && (m >> (nq - 1 - (2 * j + part)) & 1ull)) v += gd[j];
               v = warp_sum_d(v);
-              if (lane == 0) dst[kd] = v;
+              if (lane == 0) s_red[warp][kd] = v;
             }
             for (int ka = 0; ka < n_amp; ++ka) {
               const unsigned long long m = s_am[ka];
@@ -698,11 +684,20 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
                 if (j < ln.jmax && (m >> (nq - 1 - (2 * j + part)) & 1ull)) { va += ga[j]; vb += gb[j]; }
               va = warp_sum_d(va);
               vb = warp_sum_d(vb);
-              if (lane == 0) { dst[n_det + 2 * ka] = va; dst[n_det + 2 * ka + 1] = vb; }
+              if (lane == 0) { s_red[warp][n_det + 2 * ka] = va; s_red[warp][n_det + 2 * ka + 1] = vb; }
             }
+          } else if (lane == 0) {
+            for (int q = 0; q < nred - 1; ++q) s_red[warp][q] = 0.0;
           }
           hd = warp_sum_d(hd);
-          if (lane == 0) slotpart[(((size_t)gi * 6 + i) * nW + gw) * nred + nred - 1] = hd;
+          if (lane == 0) s_red[warp][nred - 1] = hd;
+          __syncthreads();
+          if (tid < nred) {
+            double tot = 0.0;
+            for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w][tid];
+            slotpart[((size_t)gi * 6 + i) * P.nC * nred + (size_t)cta * nred + tid] = tot;
+          }
+          __syncthreads();
         }
       }
 #pragma unroll

@@ -9,6 +9,8 @@ from pulser_diff_b200 import _cabi, ops
 from pulser_diff_b200.samples import ChannelSamples, SequenceSamples
 from pulser_diff_b200.utils import interpolate_sine, expect_diag
 
+if os.environ.get("PD_LIB"):
+    _cabi.use_library(os.environ["PD_LIB"])
 dev = torch.device("cuda", 0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 12
 B.N_QUBITS = n
