@@ -27,16 +27,17 @@ dv_d = dv.detach().clone().requires_grad_(True); av_d = av.detach().clone().requ
 psi0 = em.initial_state.to(dev).transpose(0, 1).contiguous()
 tsave = em.evaluation_times.detach()
 diag = B.loss_diag(n, dev)
+solver = _cabi.SOLVER_KRYLOV_SE if os.environ.get("PD_SOLVER", "dp5") == "krylov" else _cabi.SOLVER_DP5_SE
 for path in [int(p) for p in (sys.argv[2:] or ["0", "1"])]:
     for rep in range(3):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         st = ops.evolve(psi0, tsave, dv_d, av_d, H.pair_u.detach(), n_qubits=n, kind=_cabi.PD_KET, dt=H.dt,
-                        det_masks=dm, amp_masks=am, solver=_cabi.SOLVER_DP5_SE, options=_cabi.Options(path=path))
+                        det_masks=dm, amp_masks=am, solver=solver, options=_cabi.Options(path=path))
         torch.cuda.synchronize(); t1 = time.perf_counter()
         val = expect_diag(diag, st.permute(0, 2, 1)).real[-1]
         torch.autograd.grad(val, [dv_d, av_d])
         torch.cuda.synchronize(); t2 = time.perf_counter()
-    log = ops.last_step_log(st)
-    print(json.dumps({"n": n, "path": path, "fwd_ms": (t1 - t0) * 1e3, "bwd_ms": (t2 - t1) * 1e3,
+    log = ops.last_step_log(st) if solver == _cabi.SOLVER_DP5_SE else []
+    print(json.dumps({"n": n, "path": path, "solver": "krylov_se" if solver == _cabi.SOLVER_KRYLOV_SE else "dp5_se", "fwd_ms": (t1 - t0) * 1e3, "bwd_ms": (t2 - t1) * 1e3,
                       "attempts": len(log), "accepted": sum(1 for r in log if r["accepted"]),
                       "E": os.environ.get("PD_SMALL_E", "auto")}), flush=True)
