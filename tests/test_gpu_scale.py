@@ -203,3 +203,50 @@ def test_c2_workload_vs_oracle_first_intervals(cuda_device):
     log = res2.step_log()
     assert [bool(a["accepted"]) for a in log] == [bool(b[2]) for b in r.steplog]
     assert (res2.states.detach().cpu() - r.states.detach()).abs().max() < 1e-7
+
+
+def test_small_tape_overwritten_falls_back(cuda_device):
+    """Two evolutions on the same plan, then the gradient of the FIRST: its device-side stage tape
+    has been overwritten by the second, so the adjoint must fall back to the recomputing sweep and
+    still return the same gradient as an undisturbed run."""
+    n = 10
+    pr = _program(n, T=16, seed=5)
+    dev = cuda_device
+    psi0 = torch.zeros(1, 2 ** n, dtype=torch.complex128, device=dev)
+    psi0[0, -1] = 1.0
+    tsave = torch.tensor([0.0, 0.005, 0.011], dtype=torch.float64)
+    w = torch.arange(2 ** n, device=dev).remainder(3).to(torch.float64)
+
+    def run(av):
+        st = ops.evolve(psi0, tsave, pr["det_values"], av, pr["pair_u"], n_qubits=n, kind=_cabi.PD_KET,
+                        dt=pr["dt"], det_masks=pr["det_masks"], amp_masks=pr["amp_masks"])
+        return st, (w * st[-1, 0].abs() ** 2).sum()
+
+    av1 = pr["amp_values"].clone().requires_grad_(True)
+    _, val = run(av1)
+    (g_clean,) = torch.autograd.grad(val, [av1])
+    av2 = pr["amp_values"].clone().requires_grad_(True)
+    _, val2 = run(av2)
+    av3 = (pr["amp_values"] * 1.3).clone().requires_grad_(True)
+    run(av3)                                   # overwrites the plan's stage tape
+    (g_late,) = torch.autograd.grad(val2, [av2])
+    assert (g_late - g_clean).abs().max() < 1e-9 * g_clean.abs().max()
+
+
+@pytest.mark.parametrize("n,batch", [(15, 1), (16, 1), (17, 2)])
+def test_family_boundaries_norm_and_replay(cuda_device, n, batch):
+    """Register sizes between the kernel families (small-register <= 14 < gather < tiled >= 18):
+    unitarity and agreement of the automatic choice with the forced gather kernels."""
+    pr = _program(n, T=16)
+    dev = cuda_device
+    psi0 = torch.randn(batch, 2 ** n, dtype=torch.complex128, generator=torch.Generator().manual_seed(1)).to(dev)
+    psi0 /= psi0.norm(dim=1, keepdim=True)
+    tsave = torch.tensor([0.0, 0.004, 0.009], dtype=torch.float64)
+    outs = []
+    for path in (0, 1):
+        st = ops.evolve(psi0, tsave, pr["det_values"], pr["amp_values"], pr["pair_u"], n_qubits=n,
+                        kind=_cabi.PD_KET, dt=pr["dt"], det_masks=pr["det_masks"], amp_masks=pr["amp_masks"],
+                        options=_cabi.Options(path=path))
+        outs.append(st)
+    assert (outs[0].norm(dim=-1) - 1).abs().max() < 1e-6
+    assert (outs[0] - outs[1]).abs().max() < 1e-9
