@@ -181,8 +181,13 @@ int pd_evolve_backward_units(pd_plan* p, void* stream, pd_tape* tape, const void
 }
 int64_t pd_tape_unit_steps(const pd_tape* t, int32_t unit, int32_t* attempts_out) {
   if (!t || unit < 0 || (size_t)unit >= t->units.size()) return -1;
-  if (attempts_out) *attempts_out = (int32_t)t->units[unit].records.size();
-  return (int64_t)t->units[unit].steps.size();
+  const pd::Tape& u = t->units[unit];
+  if (u.n_acc_dev >= 0) {
+    if (attempts_out) *attempts_out = u.n_att_dev;
+    return u.n_acc_dev;
+  }
+  if (attempts_out) *attempts_out = (int32_t)u.records.size();
+  return (int64_t)u.steps.size();
 }
 int64_t pd_tape_n_records(const pd_tape* t) { return t ? (int64_t)t->tape.records.size() : 0; }
 int pd_tape_records(const pd_tape* t, pd_step_record* out, int64_t capacity) {

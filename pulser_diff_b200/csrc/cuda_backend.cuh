@@ -77,6 +77,11 @@ SmallKetState* small_ket_create();
 void small_ket_destroy(SmallKetState*);
 bool small_ket_supported(const Geometry& g, const Program& prog);
 bool small_ket_units_supported(const Geometry& g, const Program& prog);
+void small_ket_unit_counts(SmallKetState& S, uint64_t tape_gen, int unit, int* accepted, int* attempts);
+int small_ket_backward_units(SmallKetState& S, const Geometry& g, const Program& prog, const Tableau& tab,
+                             const std::vector<double>& tsave, int n_units, const double* dv, const double* av,
+                             uint64_t tape_gen, const cplx* gstates, cplx* lam_out, double* g_det, double* g_amp,
+                             cudaStream_t st);
 int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, const Tableau& tab,
                       const pd_options& o, int n_units, const cplx* y0, const double* dv, const double* av,
                       const double* tsave, int n_t, cplx* states,
@@ -116,6 +121,18 @@ class CudaBackend {
     if (!small_) small_ = small_ket_create();
     return small_ket_forward(*small_, g, prog, tab, o, n_units, y0, dv, av, tsave, n_t, states, recs,
                              want_tape, gen, st(s));
+  }
+  int small_backward_units(const Geometry& g, const Program& prog, const Tableau& tab,
+                           const std::vector<double>& tsave, int n_units, const double* dv, const double* av,
+                           uint64_t tape_gen, const cplx* gstates, cplx* lam_out, double* g_det, double* g_amp,
+                           void* s) {
+    if (!small_) small_ = small_ket_create();
+    return small_ket_backward_units(*small_, g, prog, tab, tsave, n_units, dv, av, tape_gen, gstates, lam_out,
+                                    g_det, g_amp, st(s));
+  }
+  void small_unit_counts(uint64_t tape_gen, int unit, int* acc, int* att) {
+    *acc = *att = -1;
+    if (small_) small_ket_unit_counts(*small_, tape_gen, unit, acc, att);
   }
   int small_backward(const Geometry& g, const Program& prog, const Tableau& tab,
                      const std::vector<double>& tsave, int n_units, const double* dv, const double* av,

@@ -39,6 +39,8 @@ struct Tape {
   std::vector<KrylovSeg> ksegs;
   // identity of the device-side stage tape recorded by the small-register forward sweep (0 = none)
   uint64_t small_gen = 0;
+  int unit_index = 0;   // position in a batch of parameter sets
+  int n_acc_dev = -1, n_att_dev = -1;   // batch whose step list stayed on the device: its counts
 };
 
 template <class BK>
@@ -205,9 +207,11 @@ class Engine {
         t.opt = o;
         t.opt.replay_dt = nullptr; t.opt.replay_clipped = nullptr; t.opt.n_replay = 0;
         t.small_gen = gen;
+        t.unit_index = u;
         for (const auto& r : recs[u])
           if (r.accepted) t.steps.push_back({r.t, r.dt, r.interval, r.clipped});
-        t.records = std::move(recs[u]);
+        t.records = std::move(recs[u]);   // empty for batches: their step lists stay on the device
+        if (n_units > 1) bk.small_unit_counts(gen, u, &t.n_acc_dev, &t.n_att_dev);
       }
     }
   }
@@ -224,11 +228,25 @@ class Engine {
       for (const auto& a : tapes[u].steps) st[u].push_back({a.t, a.dt, a.interval, a.clipped});
     cplx* lam = (cplx*)buf("lam_units", sizeof(cplx) * L * (size_t)n_units);
     std::vector<std::vector<double>> sums;
-    bool want_coef = g_det || g_amp;
     int nl = 0;
-    if (tapes[0].small_gen != 0)
+    bool want_coef = g_det || g_amp;
+    if (tapes[0].small_gen != 0 && n_units > 1) {
+      // step lists and gradient scatter on the device; only the sample gradients come back
+      nl = bk.small_backward_units(geo, prog, tab, tapes[0].tsave, n_units, dv, av, tapes[0].small_gen, gstates,
+                                   lam, g_det, g_amp, stream);
+      if (nl > 0) {
+        launches += nl;
+        if (g_state0) bk.d2d(g_state0, lam, sizeof(cplx) * L * (size_t)n_units, stream);
+        bk.sync(stream);
+        return;
+      }
+    }
+    if (tapes[0].small_gen != 0 && !tapes[0].steps.empty())
       nl = bk.small_backward(geo, prog, tab, tapes[0].tsave, n_units, dv, av, st, tapes[0].small_gen, gstates,
                              want_coef, nullptr, lam, sums, stream);
+    if (nl == 0 && tapes[0].small_gen != 0 && n_units > 1)
+      throw Error(PD_ERR_STATE, "the device-side tape of this batch was overwritten by a later evolution on the "
+                                "same plan; run the batch forward again before its backward");
     if (nl == 0) {
       // no device tape (large units, another evolution ran since, or a build without the cooperative
       // kernels): stage-by-stage adjoint per unit, recomputing from the saved states

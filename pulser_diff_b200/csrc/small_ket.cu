@@ -16,12 +16,14 @@ struct SmallKetState {
   double *d_dv = nullptr, *d_av = nullptr;
   size_t cap_dm = 0, cap_am = 0, cap_dv = 0, cap_av = 0;
   // workspace
-  void* ws[16] = {};
-  size_t ws_cap[16] = {};
+  void* ws[20] = {};
+  size_t ws_cap[20] = {};
   // stage tape of the most recent recorded forward sweep (slots 14/15) and its identity
   uint64_t tape_gen = 0;
   std::vector<int> tape_steps;   // accepted steps per unit of that sweep
+  std::vector<int> tape_attempts;
   int tape_cap = 0;
+  bool steps_on_device = false;  // batches: step lists live in ws[16] / ws[17] (k_compact_log)
   ~SmallKetState() {
     cudaFree(d_dm); cudaFree(d_am); cudaFree(d_dv); cudaFree(d_av);
     for (auto p : ws) cudaFree(p);
@@ -48,9 +50,18 @@ static int small_env(const char* name, int dflt) {
 // choose elements per thread and cluster size; false if the register does not fit one cluster
 // number of CTAs (SK_T real lanes each); false if the register does not fit one cooperative launch
 static bool small_shape(size_t L, int batch, int& nC) {
-  size_t c = (2 * L + SK_T - 1) / SK_T;
   (void)batch;
-  if (c > (size_t)SK_MAXC) return false;
+  // a unit that spans several CTAs needs them all co-resident (cooperative launch): two CTAs of
+  // 128 threads fit an SM with this kernel's registers and shared memory
+  static int max_coresident = 0;
+  if (max_coresident == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 0;
+    max_coresident = std::min(SK_MAXC, 2 * sms);
+  }
+  size_t c = (2 * L + SK_T - 1) / SK_T;
+  if (c > 1 && c > (size_t)max_coresident) return false;
   nC = (int)c;
   return true;
 }
@@ -134,6 +145,7 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
   P.log_cap = log_cap;
   P.resume = (SkResume*)S.get(6, sizeof(SkResume) * U);
   P.abort_flag = (int*)S.get(10, 64);
+  if (o.n_replay > 0 && n_units > 1) throw Error(PD_ERR_INVALID, "replayed step sequences are per evolution: not available for batches");
   if (o.n_replay > 0) {
     double* d_rd = (double*)S.get(7, sizeof(double) * o.n_replay);
     unsigned char* d_rc = (unsigned char*)S.get(8, (size_t)o.n_replay);
@@ -157,6 +169,16 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
     S.tape_steps.clear();
     S.tape_cap = P.tape_cap;
   }
+  // batches keep their step lists on the device (ws[16]: steps, ws[17]: accepted / attempted counts)
+  const bool dev_steps = U > 1 && P.tapeY != nullptr;
+  SkStep* d_steps = nullptr;
+  int *d_nsteps = nullptr, *d_natt = nullptr;
+  if (dev_steps) {
+    d_steps = (SkStep*)S.get(16, sizeof(SkStep) * U * (size_t)P.tape_cap);
+    d_nsteps = (int*)S.get(17, sizeof(int) * U * 2);
+    d_natt = d_nsteps + U;
+    PD_CUDA_CHECK(cudaMemsetAsync(d_nsteps, 0, sizeof(int) * U * 2, st));
+  }
   std::vector<SkResume> rs(U);
   for (auto& r : rs) {
     r = SkResume{};
@@ -177,7 +199,12 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
     PD_CUDA_CHECK(cudaStreamSynchronize(st));
     size_t max_rec = 0;
     for (auto& r : rs) max_rec = std::max<size_t>(max_rec, (size_t)r.n_rec);
-    if (max_rec > 0) {
+    if (max_rec > 0 && dev_steps) {
+      k_compact_log<<<(unsigned)((U + 127) / 128), 128, 0, st>>>(P.log, log_cap, P.resume, d_steps, P.tape_cap,
+                                                                 d_nsteps, d_natt, (int)U);
+      PD_CUDA_CHECK(cudaGetLastError());
+      ++launches;
+    } else if (max_rec > 0) {
       if (U == 1) {
         chunk.resize(rs[0].n_rec);
         PD_CUDA_CHECK(cudaMemcpyAsync(chunk.data(), P.log, sizeof(pd_step_record) * rs[0].n_rec, cudaMemcpyDeviceToHost, st));
@@ -207,6 +234,12 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
     if (ok) {
       S.tape_steps.resize(U);
       for (size_t u = 0; u < U; ++u) S.tape_steps[u] = rs[u].n_acc;
+      S.steps_on_device = dev_steps;
+      if (dev_steps) {
+        S.tape_attempts.resize(U);
+        PD_CUDA_CHECK(cudaMemcpyAsync(S.tape_attempts.data(), d_natt, sizeof(int) * U, cudaMemcpyDeviceToHost, st));
+        PD_CUDA_CHECK(cudaStreamSynchronize(st));
+      }
       ++S.tape_gen;
       if (tape_gen_out) *tape_gen_out = S.tape_gen;
     }
@@ -305,6 +338,81 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
     PD_CUDA_CHECK(cudaStreamSynchronize(st));
     if (ab) throw Error(PD_ERR_STATE, "small_ket_backward: exchange poll timed out");
   }
+  return launches;
+}
+
+
+// accepted / attempted steps of unit u of the batch recorded by forward sweep `tape_gen` (-1: unknown)
+void small_ket_unit_counts(SmallKetState& S, uint64_t tape_gen, int unit, int* accepted, int* attempts) {
+  *accepted = *attempts = -1;
+  if (tape_gen == 0 || tape_gen != S.tape_gen || unit < 0 || (size_t)unit >= S.tape_steps.size()) return;
+  *accepted = S.tape_steps[unit];
+  if ((size_t)unit < S.tape_attempts.size()) *attempts = S.tape_attempts[unit];
+}
+
+// Adjoint sweep of a batch whose step lists stayed on the device: kernel, then the gradient scatter
+// on the device; only the sample gradients come back.  g_det: [U][n_det][ns], g_amp: [U][n_amp][ns][2]
+// (host, nullable).  Returns launches, 0 if that tape is gone.
+int small_ket_backward_units(SmallKetState& S, const Geometry& g, const Program& prog, const Tableau& tab,
+                             const std::vector<double>& tsave, int n_units, const double* dv, const double* av,
+                             uint64_t tape_gen, const cplx* gstates, cplx* lam_out, double* g_det, double* g_amp,
+                             cudaStream_t st) {
+  const size_t L = g.dim * (size_t)g.batch;
+  const size_t U = (size_t)n_units;
+  int nC;
+  if (!small_shape(L, g.batch, nC) || nC != 1) throw Error(PD_ERR_STATE, "small_ket_backward_units: unsupported shape");
+  if (tape_gen == 0 || tape_gen != S.tape_gen || S.tape_steps.size() != U || !S.steps_on_device) return 0;
+  const int n_t = (int)tsave.size();
+  const size_t nred = small_ket_nred(prog);
+  const int ns = prog.n_samples, n_det = prog.n_det(), n_amp = prog.n_amp();
+  size_t max_steps = 1;
+  for (size_t u = 0; u < U; ++u) max_steps = std::max<size_t>(max_steps, (size_t)S.tape_steps[u]);
+  const size_t acc_bytes = sizeof(double) * (size_t)(n_det + 2 * n_amp) * ns;
+  if (acc_bytes > 40 * 1024) return 0;
+  SkBwd P{};
+  upload_prog(S, prog, g, n_units, dv ? dv : prog.det_values.data(), av ? av : prog.amp_values.data(), P.prog, st);
+  fill_tab(tab, P.tab);
+  P.batch = g.batch; P.nC = nC; P.dim = g.dim; P.L = L; P.n_t = n_t;
+  P.n_units = n_units; P.tape_cap = S.tape_cap;
+  P.max_steps = S.tape_cap;                 // stride of the device step lists
+  P.det_stride = (size_t)n_det * ns;
+  P.amp_stride = (size_t)n_amp * ns * 2;
+  P.steps = (const SkStep*)S.ws[16];
+  P.unit_steps = (const int*)S.ws[17];
+  P.n_steps = 0;
+  P.gstates = gstates;
+  P.tapeY = (const double*)S.ws[14];
+  P.tapeK = (const double*)S.ws[15];
+  const size_t kb_bytes = sizeof(uint4) * 2 * (2 * L) * U;
+  P.KB = (uint4*)S.get(3, kb_bytes);
+  PD_CUDA_CHECK(cudaMemsetAsync(P.KB, 0, kb_bytes, st));
+  // slot sums: stride tape_cap steps per unit (the kernel indexes with max_steps = tape_cap)
+  const size_t n_part = U * (size_t)S.tape_cap * 6 * nC * nred;
+  if (n_part * sizeof(double) > ((size_t)8 << 30)) return 0;
+  P.slotpart = (double*)S.get(12, sizeof(double) * n_part);
+  P.wacc_elem = nullptr;
+  P.lam_out = lam_out;
+  const bool want_coef = g_det || g_amp;
+  P.want_coef = want_coef ? 1 : 0;
+  P.abort_flag = (int*)S.get(10, 64);
+  PD_CUDA_CHECK(cudaMemsetAsync(P.abort_flag, 0, 64, st));
+  sk::launch_backward(prog.nq, P, nC, st);
+  int launches = 1;
+  if (want_coef) {
+    double* d_gd = (double*)S.get(11, sizeof(double) * U * (size_t)(n_det + 2 * n_amp) * ns);
+    double* d_ga = d_gd + U * (size_t)n_det * ns;
+    k_distribute_units<<<(unsigned)U, 128, acc_bytes, st>>>(P.slotpart, P.steps, P.unit_steps, S.tape_cap, nC, (int)nred,
+                                                          P.tab, prog.dt, ns, n_det, n_amp, d_gd, d_ga);
+    PD_CUDA_CHECK(cudaGetLastError());
+    ++launches;
+    if (g_det && n_det) PD_CUDA_CHECK(cudaMemcpyAsync(g_det, d_gd, sizeof(double) * U * n_det * ns, cudaMemcpyDeviceToHost, st));
+    if (g_amp && n_amp) PD_CUDA_CHECK(cudaMemcpyAsync(g_amp, d_ga, sizeof(double) * U * 2 * n_amp * ns, cudaMemcpyDeviceToHost, st));
+  }
+  int ab = 0;
+  PD_CUDA_CHECK(cudaMemcpyAsync(&ab, P.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PD_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (ab) throw Error(PD_ERR_STATE, "small_ket_backward_units: exchange poll timed out");
+  (void)max_steps;
   return launches;
 }
 

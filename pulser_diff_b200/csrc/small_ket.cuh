@@ -732,6 +732,72 @@ static __global__ void k_sum_slots(const double* __restrict__ part, double* __re
   out[i] = v;
 }
 
+// ---- batches of units: step lists and gradient scatter stay on the device --------------------------
+// appends the accepted records of the last launch of every unit to its device step list
+static __global__ void k_compact_log(const pd_step_record* __restrict__ log, int log_cap, const SkResume* __restrict__ resume,
+                                     SkStep* __restrict__ steps, int max_steps, int* __restrict__ n_steps,
+                                     int* __restrict__ n_attempts, int n_units) {
+  const int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_units) return;
+  int n = n_steps[u];
+  const int nr = resume[u].n_rec;
+  for (int r = 0; r < nr; ++r) {
+    const pd_step_record rec = log[(size_t)u * log_cap + r];
+    if (rec.accepted && n < max_steps) {
+      steps[(size_t)u * max_steps + n] = SkStep{rec.t, rec.dt, rec.interval, rec.clipped};
+      ++n;
+    }
+  }
+  n_steps[u] = n;
+  n_attempts[u] += nr;
+}
+// scatters the per-slot term sums of every unit onto its sample-gradient arrays with the
+// reference interpolation weights (engine.hpp::distribute_terms); one CTA per unit
+static __global__ void k_distribute_units(const double* __restrict__ slot, const SkStep* __restrict__ steps,
+                                          const int* __restrict__ n_steps, int max_steps, int nparts, int nred,
+                                          SkTab tab, double dt, int ns, int n_det, int n_amp,
+                                          double* __restrict__ g_det, double* __restrict__ g_amp) {
+  extern __shared__ double acc[];      // [n_det][ns] then [n_amp][ns][2]
+  const int u = blockIdx.x;
+  const int n_acc = (n_det + 2 * n_amp) * ns;
+  for (int i = threadIdx.x; i < n_acc; i += blockDim.x) acc[i] = 0.0;
+  __syncthreads();
+  const int nslots = n_steps[u] * 6;
+  for (int sl = threadIdx.x; sl < nslots; sl += blockDim.x) {
+    const SkStep st = steps[(size_t)u * max_steps + sl / 6];
+    const int i = sl % 6;
+    const double ts = st.t + st.dt * (i == 0 ? 0.0 : tab.alpha[i - 1]);
+    const double fl = floor(ts / dt);
+    long i1 = (long)fmin(fl, (double)(ns - 2));
+    if (i1 < 0) i1 = 0;
+    long i2 = i1 + 1 < (long)(ns - 2) ? i1 + 1 : (long)(ns - 2);
+    if (i2 < 0) i2 = 0;
+    const double x = (ts - i1 * dt) / dt;
+    double sums[2 * SK_MAXTERMS + SK_MAXTERMS];
+    for (int r = 0; r < nred - 1; ++r) {
+      double v = 0.0;
+      for (int c = 0; c < nparts; ++c) v += slot[(((size_t)u * max_steps * 6 + sl) * nparts + c) * nred + r];
+      sums[r] = v;
+    }
+    for (int kd = 0; kd < n_det; ++kd) {
+      const double g = 2.0 * sums[kd];
+      atomicAdd(&acc[kd * ns + i1], g * (1.0 - x));
+      atomicAdd(&acc[kd * ns + i2], g * x);
+    }
+    double* ga = acc + n_det * ns;
+    for (int ka = 0; ka < n_amp; ++ka) {
+      const double gre = sums[n_det + 2 * ka], gim = sums[n_det + 2 * ka + 1];
+      atomicAdd(&ga[(ka * ns + i1) * 2], gre * (1.0 - x));
+      atomicAdd(&ga[(ka * ns + i1) * 2 + 1], gim * (1.0 - x));
+      atomicAdd(&ga[(ka * ns + i2) * 2], gre * x);
+      atomicAdd(&ga[(ka * ns + i2) * 2 + 1], gim * x);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_det * ns; i += blockDim.x) g_det[(size_t)u * n_det * ns + i] = acc[i];
+  for (int i = threadIdx.x; i < 2 * n_amp * ns; i += blockDim.x) g_amp[(size_t)u * 2 * n_amp * ns + i] = acc[n_det * ns + i];
+}
+
 inline void fill_tab(const Tableau& t, SkTab& o) {
   for (int i = 0; i < 6; ++i) o.alpha[i] = t.alpha[i];
   for (int i = 0; i < 6; ++i)

@@ -52,13 +52,21 @@ params = params_all[mine].clone().requires_grad_(True)
 U = len(mine)
 psi0 = torch.eye(4, dtype=torch.complex128, device=dev).repeat(U, 1, 1)     # rows = initial states
 
+phase_ms = {}
+
+
 def run():
+    torch.cuda.synchronize(); t0 = time.perf_counter()
     dv, av = tables(params)
+    t1 = time.perf_counter()
     st = ops.evolve_units(psi0, tsave, dv, av, pair_u, n_qubits=N, dt=dt, det_masks=[full], amp_masks=[full])
+    torch.cuda.synchronize(); t2 = time.perf_counter()
     Uf = st[:, -1].transpose(1, 2)                       # column b = evolved basis state b
     fid = (target.conj().T @ Uf).diagonal(dim1=1, dim2=2).sum(-1).abs() / 4
     loss = 1 - fid
     (gp,) = torch.autograd.grad(loss.sum(), [params])
+    torch.cuda.synchronize(); t3 = time.perf_counter()
+    phase_ms.update(tables=(t1 - t0) * 1e3, forward=(t2 - t1) * 1e3, loss_and_backward=(t3 - t2) * 1e3)
     return loss.detach(), gp
 
 for _ in range(2):
@@ -91,6 +99,7 @@ if rank == 0:
     print(json.dumps({"config": "C3 parameter-set batch", "n_sets": n_sets, "n_gpus": world, "n_qubits": N,
                       "columns": 4, "n_t": int(tsave.numel()), "s_per_sweep": dt_s,
                       "sets_per_s": n_sets / dt_s, "mean_loss": losses.mean().item(),
-                      "first_loss": losses[0].item(), "max_abs_diff_vs_single": max(errs) if errs else None}))
+                      "first_loss": losses[0].item(), "max_abs_diff_vs_single": max(errs) if errs else None,
+                      "phase_ms_rank0": {k: round(v, 2) for k, v in phase_ms.items()}}))
 if world > 1:
     dist.destroy_process_group()

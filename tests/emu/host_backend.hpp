@@ -41,6 +41,11 @@ class HostBackend {
                     std::vector<std::vector<pd_step_record>>&, bool, uint64_t*, void*) {
     throw Error(PD_ERR_STATE, "small-register kernels need the CUDA build");
   }
+  int small_backward_units(const Geometry&, const Program&, const Tableau&, const std::vector<double>&, int,
+                           const double*, const double*, uint64_t, const cplx*, cplx*, double*, double*, void*) {
+    return 0;
+  }
+  void small_unit_counts(uint64_t, int, int* acc, int* att) { *acc = *att = -1; }
   int small_backward(const Geometry&, const Program&, const Tableau&, const std::vector<double>&, int,
                      const double*, const double*, const std::vector<std::vector<SkStepHost>>&, uint64_t,
                      const cplx*, bool, double*, cplx*, std::vector<std::vector<double>>&, void*) {
