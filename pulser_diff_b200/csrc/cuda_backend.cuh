@@ -1,12 +1,13 @@
 // CUDA backend (sm_100a) for the evolution engine: memory plumbing + kernel launchers.
 //
-// Two kernel families implement every generator application:
-//   * "gather" kernels (this file): one thread per amplitude, bit-flip partners fetched
-//     through L1/L2.  Any N, any addressing, ket and density.  Correctness baseline and the
-//     path for small registers where the whole working set is cache resident.
-//   * "tiled" kernels (tiled_ket.cuh): shared-memory staged, TMA-bulk loaded tiles that close
-//     over a set of qubit bits on chip, fused with the Runge-Kutta stage combination.  The
-//     HBM-bound path for large registers.
+// Kernel families:
+//   * "gather" (gather_kernels.cu): one thread per amplitude, bit-flip partners fetched through
+//     L1/L2.  Any N, any addressing, ket and density.  Correctness baseline; the path while the
+//     working set is cache resident, and the Lindblad path.
+//   * "small" (small_ket*.cu): kets of N <= 14 -- the whole adaptive evolution / adjoint sweep as one
+//     cooperative kernel with register-resident lanes and a flag-in-data exchange through L2.
+//   * "tiled" (tiled_ket.cu): kets of 18 <= N <= 23 -- two tile types, fused finalise/start launches.
+//   * "stream" (stream_ket.cu): kets of N >= 24 -- one bit-group of H per launch, >= 256 B pieces.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -71,7 +72,7 @@ int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cpl
                            const SiteOps* stage_ops, const double* beta, const double* ew, double dt,
                            double atol, double rtol, double* err_partial, double* err_out, cudaStream_t s);
 size_t stream_err_partial_count(const Geometry& g);
-// small-register family (small_ket.cu): whole forward / adjoint sweep in one cluster kernel
+// small-register family (small_ket*.cu): whole forward / adjoint sweep in one cooperative kernel
 struct SmallKetState;
 SmallKetState* small_ket_create();
 void small_ket_destroy(SmallKetState*);

@@ -597,7 +597,7 @@ class Engine {
     bk.sync(stream);
   }
 
-  // ---- small-register family (one cluster kernel per sweep) ----------------------------------
+  // ---- small-register family (one cooperative kernel per sweep) -------------------------------
   bool use_small() {
     if (prog.kind != PD_KET || !(bk.path == 0 || bk.path == 3)) return false;
     bool ok = bk.small_supported(geo, prog);

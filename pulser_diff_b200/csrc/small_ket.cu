@@ -47,7 +47,6 @@ static int small_env(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-// choose elements per thread and cluster size; false if the register does not fit one cluster
 // number of CTAs (SK_T real lanes each); false if the register does not fit one cooperative launch
 static bool small_shape(size_t L, int batch, int& nC) {
   (void)batch;

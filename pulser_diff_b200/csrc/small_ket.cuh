@@ -1,4 +1,4 @@
-// Small-register ket kernels: the launch-bound regime (N <= 15, state resident in registers/L2).
+// Small-register ket kernels: the launch-bound regime (N <= 14, state resident in registers/L2).
 //
 // For a 12-qubit register one state vector is 64 KiB: stage-by-stage launches spend their time in
 // launch latency and host round trips (98k launches / 90 ms for one forward+gradient pass of the

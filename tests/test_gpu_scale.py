@@ -114,8 +114,8 @@ def test_tiled_equals_gather(cuda_device, n, other):
 
 @pytest.mark.parametrize("n,batch,local", [(3, 1, False), (6, 4, True), (10, 1, False), (12, 1, True),
                                            (13, 1, False)])
-def test_small_cluster_kernels_equal_gather(cuda_device, n, batch, local):
-    """One-launch cluster kernels (csrc/small_ket.cu, path 3) against the stage-by-stage gather
+def test_small_register_kernels_equal_gather(cuda_device, n, batch, local):
+    """One-launch cooperative kernels (csrc/small_ket.cuh, path 3) against the stage-by-stage gather
     kernels (path 1): states, attempted-step log, and every gradient (samples, times, pair
     couplings, initial state)."""
     pr = _program(n, T=16, seed=3)

@@ -84,7 +84,7 @@ def _loss_and_leaves(p: Problem, states, tsave, extra):
 @pytest.mark.parametrize("solver", ["dp5_se", "krylov_se"])
 @pytest.mark.parametrize("local", [False, True])
 def test_ket_states_and_gradients(engine_device, solver, local, kpath):
-    """kpath 0 = automatic kernel choice (on CUDA: the one-launch cluster kernels of
+    """kpath 0 = automatic kernel choice (on CUDA: the one-launch cooperative kernels of
     csrc/small_ket.cu for DP5), 1 = stage-by-stage gather kernels."""
     if kpath == 1 and solver != "dp5_se":
         pytest.skip("kernel family only differs for DP5")
