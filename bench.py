@@ -298,8 +298,12 @@ def run_b200(args):
 
     if rank == 0:
         s12 = 2 ** N_QUBITS
-        h2d = int(s12 * 16 + N_QUBITS * N_QUBITS * 8)
-        d2h = int(n_steps * 6 * N_QUBITS * 4 * 16 + (n_steps + 8) * 8 + len(tsave) * 16)
+        n_s, n_tp = int(dv.shape[-1]), len(tsave)
+        # bytes that cross PCIe in one e2e pass (counted from the buffers the C ABI copies):
+        # in : psi0, pair couplings, coefficient tables (forward and adjoint launch), time grid, step list
+        # out: controller state + attempted-step log, per-slot gradient sums, expectation values, loss
+        h2d = int(s12 * 16 + N_QUBITS * N_QUBITS * 8 + 2 * (n_s * 8 + n_s * 16 + 16) + n_tp * 8 + n_steps * 24)
+        d2h = int(96 + 2 * n_steps * 40 + n_steps * 6 * 4 * 8 + n_tp * 16 + 8)
         line = {
             "metric": "evolution steps/sec (DP5 steps, forward+gradient)", "value": value,
             "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -1,5 +1,7 @@
 // Host side of the small-register ket family (kernels: small_ket.cuh, instantiated in
 // small_ket_fwd.cu / small_ket_bwd1.cu / small_ket_bwd2.cu so that they compile in parallel).
+#include <chrono>
+
 #include "small_ket.cuh"
 
 namespace pd {
@@ -115,6 +117,11 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
   const size_t U = (size_t)n_units;
   int nC;
   if (!small_shape(L, g.batch, nC)) throw Error(PD_ERR_STATE, "small_ket_forward: unsupported shape");
+  // PD_TIMING=1: host-side phase times of this call on stderr
+  static const bool timing = getenv("PD_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_in = timing ? now() : 0.0;
+  double t_tape = 0.0, t_launch = 0.0, t_done = 0.0;
   if (n_units > 1 && nC != 1)
     throw Error(PD_ERR_INVALID, "batches of parameter sets need 2 * batch * 2^N <= 128 (one CTA per set)");
   if (tape_gen_out) *tape_gen_out = 0;
@@ -152,6 +159,7 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
     PD_CUDA_CHECK(cudaMemcpyAsync(d_rc, o.replay_clipped, (size_t)o.n_replay, cudaMemcpyHostToDevice, st));
     P.replay_dt = d_rd; P.replay_clipped = d_rc;
   }
+  if (timing) t_tape = now();
   if (want_tape) {
     // per accepted step: 6 stage inputs + 6 slopes; sized from the time grid, bounded by memory
     const size_t per_step = 6 * L * sizeof(cplx) * U;
@@ -192,10 +200,12 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
     PD_CUDA_CHECK(cudaMemsetAsync(P.YS, 0, ys_bytes, st));
     PD_CUDA_CHECK(cudaMemsetAsync(P.red, 0, red_bytes, st));
     PD_CUDA_CHECK(cudaMemsetAsync(P.abort_flag, 0, 64, st));
+    if (timing) t_launch = now();
     sk::launch_forward(prog.nq, P, nC, st);
     ++launches;
     PD_CUDA_CHECK(cudaMemcpyAsync(rs.data(), P.resume, sizeof(SkResume) * U, cudaMemcpyDeviceToHost, st));
     PD_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (timing) t_done = now();
     size_t max_rec = 0;
     for (auto& r : rs) max_rec = std::max<size_t>(max_rec, (size_t)r.n_rec);
     if (max_rec > 0 && dev_steps) {
@@ -227,6 +237,9 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
     }
     if (!again) break;
   }
+  if (timing)
+    fprintf(stderr, "[pd] small forward: setup %.3f ms, tape sizing+rest %.3f ms, last launch->sync %.3f ms, logs %.3f ms\n",
+            t_tape - t_in, t_launch - t_tape, t_done - t_launch, now() - t_done);
   if (P.tapeY) {
     bool ok = true;
     for (auto& r : rs) ok = ok && r.tape_ok;

@@ -30,7 +30,7 @@
 namespace pd {
 namespace sk {
 
-constexpr int SK_T = 128;          // threads per CTA: one warp per scheduler
+constexpr int SK_T = 128;          // threads per CTA: one warp per scheduler (64 and 256 measured slower)
 constexpr int SK_MAXQ = 16;        // qubits handled by this family
 constexpr int SK_MAXTERMS = 24;    // n_det, n_amp each
 constexpr int SK_MAXB = 32;        // batch columns

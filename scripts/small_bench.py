@@ -29,7 +29,8 @@ tsave = em.evaluation_times.detach()
 diag = B.loss_diag(n, dev)
 solver = _cabi.SOLVER_KRYLOV_SE if os.environ.get("PD_SOLVER", "dp5") == "krylov" else _cabi.SOLVER_DP5_SE
 for path in [int(p) for p in (sys.argv[2:] or ["0", "1"])]:
-    for rep in range(3):
+    for rep in range(int(os.environ.get("PD_REPS", "3"))):
+        print("rep", rep, file=sys.stderr)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         st = ops.evolve(psi0, tsave, dv_d, av_d, H.pair_u.detach(), n_qubits=n, kind=_cabi.PD_KET, dt=H.dt,
                         det_masks=dm, amp_masks=am, solver=solver, options=_cabi.Options(path=path))
