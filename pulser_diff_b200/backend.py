@@ -120,6 +120,8 @@ class TorchEmulator:
         if isinstance(state, str) and state == "all-ground":
             psi = torch.zeros(2 ** n, 1, dtype=C128)
             psi[-1] = 1.0                       # kron(|g>, ..., |g>) with |g> = e1
+            if self._hamiltonian.torch_device.type == "cuda" and torch.cuda.is_available():
+                psi = psi.pin_memory()          # staged for the host->device copy of every run
             self._initial_state = psi
         else:
             legal = self._hamiltonian.dim ** n

@@ -72,6 +72,8 @@ int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cpl
                            const SiteOps* stage_ops, const double* beta, const double* ew, double dt,
                            double atol, double rtol, double* err_partial, double* err_out, cudaStream_t s);
 size_t stream_err_partial_count(const Geometry& g);
+int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar, int n_in,
+                       const cplx* const* ins, const double* w, cplx* ymat, cudaStream_t s);
 // small-register family (small_ket*.cu): whole forward / adjoint sweep in one cooperative kernel
 struct SmallKetState;
 SmallKetState* small_ket_create();
@@ -259,6 +261,18 @@ class CudaBackend {
   int corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar,
            const cplx* y, double* scratch, void* s) {
     return launch_corr(g, d_corr, d_wacc, wscale, kbar, y, scratch, st(s));
+  }
+  // correlations of kbar with the stage input y = sum_j w_j in_j; ybuf receives y when it has to be formed
+  int corr_combo(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar, int n_in,
+                 const cplx* const* ins, const double* w, cplx* ybuf, double* scratch, void* s) {
+    if (use_stream(g)) return launch_stream_corr(g, d_corr, d_wacc, wscale, kbar, n_in, ins, w, ybuf, st(s));
+    int n = 0;
+    const cplx* ysrc = ins[0];
+    if (n_in > 1 || w[0] != 1.0) {
+      n += launch_lincomb(g, ybuf, n_in, ins, w, st(s));
+      ysrc = ybuf;
+    }
+    return n + launch_corr(g, d_corr, d_wacc, wscale, kbar, ysrc, scratch, st(s));
   }
   int re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, double* scratch, void* s) {
     return launch_re_dot(g, out, a, b, scratch, st(s));

@@ -718,21 +718,17 @@ class Engine {
       size_t slot = (size_t)step_index * 6 + i;
       slots[slot] = {ts, alpha, st.interval, step_index};
       if (want_coef || d_wacc) {
-        const cplx* ysrc = y_n;
-        if (i > 0) {
-          const cplx* yi[8];
-          double yw[8];
-          int m = 0;
-          yi[m] = y_n; yw[m++] = 1.0;
-          for (int j = 0; j < i; ++j) {
-            double b = tab.beta[i - 1][j];
-            if (b != 0.0) { yi[m] = k[j]; yw[m++] = h * b; }
-          }
-          launches += bk.lincomb(geo, ystage, m, yi, yw, stream);
-          ysrc = ystage;
+        // stage input Y_i = y_n + h sum_j beta_ij k_j, formed by the correlation launch itself
+        const cplx* yi[8];
+        double yw[8];
+        int m = 0;
+        yi[m] = y_n; yw[m++] = 1.0;
+        for (int j = 0; j < i; ++j) {
+          double b = tab.beta[i - 1][j];
+          if (b != 0.0) { yi[m] = k[j]; yw[m++] = h * b; }
         }
-        launches += bk.corr(geo, want_coef ? d_corr + slot * cs : nullptr, d_wacc, 1.0, kbar, ysrc,
-                            reduce_scratch(), stream);
+        launches += bk.corr_combo(geo, want_coef ? d_corr + slot * cs : nullptr, d_wacc, 1.0, kbar, m, yi, yw,
+                                  ystage, reduce_scratch(), stream);
       }
       if (d_hdot && st.clipped)
         launches += bk.re_dot(geo, d_hdot + slot, kbar, k[i], reduce_scratch(), stream);

@@ -365,6 +365,250 @@ __global__ void k_stream_sum_partials(const double* __restrict__ partial, int pe
 }
 }  // namespace
 
+// ---- adjoint site correlations on tiles ---------------------------------------------------------------
+// Per qubit q the gradient distribution (engine.hpp::distribute) needs three real sums over the state index,
+//   gd_q = sum_{s: bit_q(s)=0} Im(conj(kbar[s]) y[s]),   ga_q = sum_s Im(conj(kbar[s]) y[s ^ m_q]),
+//   gb_q = sum_s (bit_q(s) ? 1 : -1) Re(conj(kbar[s]) y[s ^ m_q]),
+// with y the stage input (a combination of y_n and the slopes, formed on the fly like in k_stream_a and
+// written once as Ymat for the group launches).  The contiguous launch covers the low 12 qubits' bits and
+// every self term; each group launch its own bits.  Partners come from shared memory, not through L2 as in
+// the gather kernel k_corr_ket.
+namespace {
+constexpr int kCA = 3 * TB + 1;          // per-CTA partial sums of the contiguous launch: 12 x (gd, ga, gb) + self
+constexpr int kCG = 2 * kMaxGroupBits;   // per-CTA partial sums of a group launch: nb x (ga, gb)
+
+struct CorrParams {
+  int nq, lo, nb, C, n_in;
+  size_t dim;
+  const cplx* v[kMaxIn];
+  double w[kMaxIn];
+  cplx* ymat;              // contiguous launch: combined stage input written here (nullable)
+  const cplx* ysrc;        // group launches
+  const cplx* kbar;
+  double* wacc;            // [2^nq] += wscale * Im(conj(kbar) y)   (nullable; contiguous launch)
+  double wscale;
+  double* partial;         // [gridDim.x][kCA or kCG]
+};
+
+template <int R>
+__device__ __forceinline__ void corr_block_reduce(double (&acc)[R], double* partial) {
+  __shared__ double sh[NT / 32][R];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    double v = acc[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) sh[warp][r] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < R) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) s += sh[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * R + threadIdx.x] = s;
+  }
+}
+
+__global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__ CorrParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  const int t = threadIdx.x;
+  const size_t tiles_per_vec = P.dim >> TB;
+  const size_t tile = blockIdx.x % tiles_per_vec;
+  const size_t base = (blockIdx.x / tiles_per_vec) * P.dim + (tile << TB);
+  constexpr int QP = 4;
+#pragma unroll
+  for (int q0 = 0; q0 < EPT; q0 += QP) {
+    cplx y[QP];
+#pragma unroll
+    for (int i = 0; i < QP; ++i) y[i] = {0.0, 0.0};
+    for (int j = 0; j < P.n_in; ++j) {
+      const cplx* vj = P.v[j] + base;
+      const double wj = P.w[j];
+      cplx x[QP];
+#pragma unroll
+      for (int i = 0; i < QP; ++i) x[i] = ldcs(vj + t + NT * (q0 + i));
+#pragma unroll
+      for (int i = 0; i < QP; ++i) { y[i].re = fma(wj, x[i].re, y[i].re); y[i].im = fma(wj, x[i].im, y[i].im); }
+    }
+#pragma unroll
+    for (int i = 0; i < QP; ++i) {
+      T[t + NT * (q0 + i)] = y[i];
+      if (P.ymat) P.ymat[base + t + NT * (q0 + i)] = y[i];
+    }
+  }
+  __syncthreads();
+  double acc[kCA];
+#pragma unroll
+  for (int r = 0; r < kCA; ++r) acc[r] = 0.0;
+  const int nl = P.nq < TB ? P.nq : TB;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int e = t + NT * i;
+    const cplx kbv = ldcs(P.kbar + base + e);
+    const cplx kb{kbv.re, -kbv.im};
+    const cplx self = kb * T[e];
+    acc[kCA - 1] += self.im;
+    if (P.wacc) atomicAdd(P.wacc + (tile << TB) + e, P.wscale * self.im);
+#pragma unroll
+    for (int lb = 0; lb < TB; ++lb) {
+      if (lb >= nl) break;
+      const bool a = (e >> lb) & 1;
+      const cplx fl = kb * T[e ^ (1 << lb)];
+      acc[lb * 3 + 0] += a ? 0.0 : self.im;
+      acc[lb * 3 + 1] += fl.im;
+      acc[lb * 3 + 2] += a ? fl.re : -fl.re;
+    }
+  }
+  corr_block_reduce<kCA>(acc, P.partial);
+}
+
+__device__ __forceinline__ size_t cindex(const CorrParams& P, size_t tile, int e) {
+  const size_t col = (size_t)(e & ((1 << P.C) - 1)), row = (size_t)(e >> P.C);
+  const int lw = P.lo - P.C;
+  const size_t ul = tile & (((size_t)1 << lw) - 1), uh = tile >> lw;
+  return col | (ul << P.C) | (row << P.lo) | (uh << (P.lo + P.nb));
+}
+
+__global__ void __launch_bounds__(NT, 3) k_stream_corr_g(const __grid_constant__ CorrParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  const int t = threadIdx.x;
+  const size_t tiles_per_vec = P.dim >> TB;
+  const size_t tile = blockIdx.x % tiles_per_vec;
+  const size_t boff = (blockIdx.x / tiles_per_vec) * P.dim;
+#pragma unroll
+  for (int q0 = 0; q0 < EPT; q0 += 8) {
+    cplx x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = ldcs(P.ysrc + boff + cindex(P, tile, t + NT * (q0 + i)));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) T[t + NT * (q0 + i)] = x[i];
+  }
+  __syncthreads();
+  double acc[kCG];
+#pragma unroll
+  for (int r = 0; r < kCG; ++r) acc[r] = 0.0;
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const int e = t + NT * i;
+    const cplx kbv = ldcs(P.kbar + boff + cindex(P, tile, e));
+    const cplx kb{kbv.re, -kbv.im};
+#pragma unroll
+    for (int b = 0; b < kMaxGroupBits; ++b) {
+      if (b >= P.nb) break;
+      const int lb = P.C + b;
+      const bool a = (e >> lb) & 1;
+      const cplx fl = kb * T[e ^ (1 << lb)];
+      acc[b * 2 + 0] += fl.im;
+      acc[b * 2 + 1] += a ? fl.re : -fl.re;
+    }
+  }
+  corr_block_reduce<kCG>(acc, P.partial);
+}
+
+// One warp per qubit bit position p: sums the per-CTA partials in a fixed order and writes the 2x2 block
+// d_corr[q][a][a'] that engine.hpp::distribute reads: c[0] = (0, gd), c[2] = (gb, ga), c[1] = c[3] = 0.
+struct CorrFinal {
+  int nq, n_groups;
+  int lo[8], nb[8];
+  const double* part_a;
+  const double* part_g[8];
+  unsigned nblocks;
+  unsigned tiles_per_vec;
+  cplx* d_corr;
+};
+__global__ void k_stream_corr_final(const __grid_constant__ CorrFinal F) {
+  const int p = blockIdx.x, lane = threadIdx.x;
+  double gd = 0.0, ga = 0.0, gb = 0.0;
+  if (p < TB) {
+    for (unsigned b = lane; b < F.nblocks; b += 32) {
+      const double* r = F.part_a + (size_t)b * kCA + p * 3;
+      gd += r[0]; ga += r[1]; gb += r[2];
+    }
+  } else {
+    // self terms: CTAs whose tile index has bit (p - TB) clear
+    for (unsigned b = lane; b < F.nblocks; b += 32)
+      if (!(((b % F.tiles_per_vec) >> (p - TB)) & 1u)) gd += F.part_a[(size_t)b * kCA + kCA - 1];
+    for (int g = 0; g < F.n_groups; ++g)
+      if (p >= F.lo[g] && p < F.lo[g] + F.nb[g]) {
+        const int j = p - F.lo[g];
+        for (unsigned b = lane; b < F.nblocks; b += 32) {
+          const double* r = F.part_g[g] + (size_t)b * kCG + j * 2;
+          ga += r[0]; gb += r[1];
+        }
+      }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    gd += __shfl_xor_sync(0xffffffffu, gd, o);
+    ga += __shfl_xor_sync(0xffffffffu, ga, o);
+    gb += __shfl_xor_sync(0xffffffffu, gb, o);
+  }
+  if (lane == 0) {
+    const int q = F.nq - 1 - p;
+    F.d_corr[q * 4 + 0] = cplx{0.0, gd};
+    F.d_corr[q * 4 + 1] = cplx{0.0, 0.0};
+    F.d_corr[q * 4 + 2] = cplx{gb, ga};
+    F.d_corr[q * 4 + 3] = cplx{0.0, 0.0};
+  }
+}
+}  // namespace
+
+// Site correlations of kbar with the stage input y = sum_j w_j in_j (ymat: buffer for y, required unless the
+// input is plain).  d_corr (nullable): [nq][4] complex; d_wacc (nullable): [2^nq] += wscale * Im(conj(kbar) y).
+int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar, int n_in,
+                       const cplx* const* ins, const double* w, cplx* ymat, cudaStream_t s) {
+  if (n_in > kMaxIn) throw Error(PD_ERR_INVALID, "stream corr takes at most 8 inputs");
+  static bool attr = false;
+  if (!attr) {
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_a, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_g, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+    attr = true;
+  }
+  const unsigned grid = (unsigned)((g.dim >> TB) * (size_t)g.batch);
+  const int rest = g.nq - TB;
+  const int G = d_corr ? (rest + kMaxGroupBits - 1) / kMaxGroupBits : 0;
+  static double* d_part = nullptr;
+  static size_t cap = 0;
+  const size_t need = (size_t)grid * (kCA + (size_t)G * kCG);
+  if (cap < need) {
+    if (d_part) cudaFree(d_part);
+    PD_CUDA_CHECK(cudaMalloc(&d_part, sizeof(double) * need));
+    cap = need;
+  }
+  const bool plain = n_in == 1 && w[0] == 1.0;
+  const cplx* ysrc = plain ? ins[0] : ymat;
+  if (!plain && G > 0 && ymat == nullptr) throw Error(PD_ERR_STATE, "stream corr needs a buffer for the stage input");
+  CorrParams A{};
+  A.nq = g.nq; A.dim = g.dim; A.n_in = n_in; A.kbar = kbar; A.wacc = d_wacc; A.wscale = wscale; A.partial = d_part;
+  for (int j = 0; j < n_in; ++j) { A.v[j] = ins[j]; A.w[j] = w[j]; }
+  A.ymat = (plain || G == 0) ? nullptr : ymat;
+  k_stream_corr_a<<<grid, NT, TILE * 16, s>>>(A);
+  int n = 1;
+  if (d_corr) {
+    CorrFinal F{};
+    F.nq = g.nq; F.n_groups = G; F.part_a = d_part; F.nblocks = grid; F.tiles_per_vec = (unsigned)(g.dim >> TB);
+    F.d_corr = d_corr;
+    int lo = TB;
+    for (int gi = 0; gi < G; ++gi) {
+      const int nb = rest / G + (gi < rest % G ? 1 : 0);
+      CorrParams B{};
+      B.nq = g.nq; B.dim = g.dim; B.ysrc = ysrc; B.kbar = kbar; B.lo = lo; B.nb = nb; B.C = TB - nb;
+      B.partial = d_part + (size_t)grid * (kCA + (size_t)gi * kCG);
+      k_stream_corr_g<<<grid, NT, TILE * 16, s>>>(B);
+      F.lo[gi] = lo; F.nb[gi] = nb; F.part_g[gi] = B.partial;
+      lo += nb;
+      ++n;
+    }
+    k_stream_corr_final<<<g.nq, 32, 0, s>>>(F);
+    ++n;
+  }
+  PD_CUDA_CHECK(cudaGetLastError());
+  return n;
+}
+
 size_t stream_err_partial_count(const Geometry& g) { return (g.dim >> TB) * (size_t)g.batch; }
 
 // One Dormand-Prince step with the stream kernels: stages 2..7 (k[0] = f(t, y) on entry, FSAL),

@@ -197,6 +197,16 @@ class HostBackend {
     }
     return 1;
   }
+  int corr_combo(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar, int n_in,
+                 const cplx* const* ins, const double* w, cplx* ybuf, double* scratch, void* s) {
+    int n = 0;
+    const cplx* ysrc = ins[0];
+    if (n_in > 1 || w[0] != 1.0) {
+      n += lincomb(g, ybuf, n_in, ins, w, s);
+      ysrc = ybuf;
+    }
+    return n + corr(g, d_corr, d_wacc, wscale, kbar, ysrc, scratch, s);
+  }
   int re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, double*, void*) {
     double acc = 0;
     for (size_t i = 0; i < g.dim * g.batch; ++i) acc += a[i].re * b[i].re + a[i].im * b[i].im;

@@ -95,13 +95,14 @@ def test_tiled_equals_gather(cuda_device, n, other):
     for path in (1, other):
         av = pr["amp_values"].clone().requires_grad_(True)
         dv = pr["det_values"].clone().requires_grad_(True)
-        st = ops.evolve(psi0, tsave, dv, av, pr["pair_u"], n_qubits=n, kind=_cabi.PD_KET,
+        pu = pr["pair_u"].clone().requires_grad_(True)
+        st = ops.evolve(psi0, tsave, dv, av, pu, n_qubits=n, kind=_cabi.PD_KET,
                         dt=pr["dt"], det_masks=pr["det_masks"], amp_masks=pr["amp_masks"],
                         options=_cabi.Options(path=path))
         outs.append(st.detach())
         w = torch.arange(2 ** n, device=dev).remainder(5).to(torch.float64)
         val = (w * st[-1].abs() ** 2).sum() + (w * st[1].abs() ** 2).sum()
-        grads.append(torch.autograd.grad(val, [av, dv]))
+        grads.append(torch.autograd.grad(val, [av, dv, pu]))
         plan = ops.get_plan(n, nb, _cabi.PD_KET, dev)
         plan.set_path(path)
         hp.append(plan.hpsi(0.0051, psi0))
