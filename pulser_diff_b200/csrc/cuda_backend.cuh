@@ -265,7 +265,9 @@ class CudaBackend {
   // correlations of kbar with the stage input y = sum_j w_j in_j; ybuf receives y when it has to be formed
   int corr_combo(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar, int n_in,
                  const cplx* const* ins, const double* w, cplx* ybuf, double* scratch, void* s) {
-    if (use_stream(g)) return launch_stream_corr(g, d_corr, d_wacc, wscale, kbar, n_in, ins, w, ybuf, st(s));
+    // the tiled correlation kernels serve both large-register families (any N >= 16)
+    if ((use_stream(g) || use_tiled(g)) && stream_ket_supported(g))
+      return launch_stream_corr(g, d_corr, d_wacc, wscale, kbar, n_in, ins, w, ybuf, st(s));
     int n = 0;
     const cplx* ysrc = ins[0];
     if (n_in > 1 || w[0] != 1.0) {
