@@ -251,3 +251,29 @@ def test_family_boundaries_norm_and_replay(cuda_device, n, batch):
         outs.append(st)
     assert (outs[0].norm(dim=-1) - 1).abs().max() < 1e-6
     assert (outs[0] - outs[1]).abs().max() < 1e-9
+
+
+@pytest.mark.parametrize("n,other", [(18, 2), (20, 4)])
+def test_krylov_on_tiled_and_stream_kernels(cuda_device, n, other):
+    """KRYLOV_SE (Lanczos propagation, adjoint by Krylov-space quadrature) runs its H.psi through the
+    same kernel families: tiled (path 2) and stream (path 4) against gather (path 1)."""
+    pr = _program(n, T=16)
+    dev = cuda_device
+    psi0 = torch.zeros(1, 2 ** n, dtype=torch.complex128, device=dev)
+    psi0[0, -1] = 1.0
+    tsave = torch.tensor([0.0, 0.003, 0.006], dtype=torch.float64)
+    w = torch.arange(2 ** n, device=dev).remainder(5).to(torch.float64)
+    outs, grads = [], []
+    for path in (1, other):
+        av = pr["amp_values"].clone().requires_grad_(True)
+        dv = pr["det_values"].clone().requires_grad_(True)
+        st = ops.evolve(psi0, tsave, dv, av, pr["pair_u"], n_qubits=n, kind=_cabi.PD_KET, dt=pr["dt"],
+                        det_masks=pr["det_masks"], amp_masks=pr["amp_masks"], solver=_cabi.SOLVER_KRYLOV_SE,
+                        options=_cabi.Options(path=path))
+        outs.append(st.detach())
+        val = (w * st[-1, 0].abs() ** 2).sum()
+        grads.append(torch.autograd.grad(val, [av, dv]))
+    assert (outs[0].norm(dim=-1) - 1).abs().max() < 1e-9
+    assert (outs[0] - outs[1]).abs().max() < 1e-10
+    for a, b in zip(grads[0], grads[1]):
+        assert (a - b).abs().max() < 1e-8 * max(1e-30, b.abs().max().item())
