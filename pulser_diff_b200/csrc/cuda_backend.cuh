@@ -80,6 +80,9 @@ SmallKetState* small_ket_create();
 void small_ket_destroy(SmallKetState*);
 bool small_ket_supported(const Geometry& g, const Program& prog);
 bool small_ket_units_supported(const Geometry& g, const Program& prog);
+int small_ket_lanczos(SmallKetState& S, const Geometry& g1, const Program& prog, const cplx* v0, cplx* basis,
+                      int max_m, double t_eval, int j0, int j1, double beta_prev, double* alpha_host,
+                      double* beta_host, double* nrm, cudaStream_t st);
 void small_ket_unit_counts(SmallKetState& S, uint64_t tape_gen, int unit, int* accepted, int* attempts);
 int small_ket_backward_units(SmallKetState& S, const Geometry& g, const Program& prog, const Tableau& tab,
                              const std::vector<double>& tsave, int n_units, const double* dv, const double* av,
@@ -117,6 +120,12 @@ class CudaBackend {
   }
   bool small_supported(const Geometry& g, const Program& prog) { return small_ket_supported(g, prog); }
   bool small_units_supported(const Geometry& g, const Program& prog) { return small_ket_units_supported(g, prog); }
+  int small_lanczos(const Geometry& g1, const Program& prog, const cplx* v0, cplx* basis, int max_m, double t_eval,
+                    int j0, int j1, double beta_prev, double* alpha_host, double* beta_host, double* nrm, void* s) {
+    if (!small_) small_ = small_ket_create();
+    return small_ket_lanczos(*small_, g1, prog, v0, basis, max_m, t_eval, j0, j1, beta_prev, alpha_host, beta_host,
+                             nrm, st(s));
+  }
   int small_forward(const Geometry& g, const Program& prog, const Tableau& tab, const pd_options& o,
                     int n_units, const cplx* y0, const double* dv, const double* av, const double* tsave,
                     int n_t, cplx* states, std::vector<std::vector<pd_step_record>>& recs, bool want_tape,

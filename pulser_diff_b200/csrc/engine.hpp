@@ -812,6 +812,42 @@ class Engine {
     Lanczos lz;
     Geometry g1 = geo;
     g1.batch = 1;
+    if ((bk.path == 0 || bk.path == 3) && bk.small_supported(g1, prog)) {
+      // small registers: the recurrence runs on the device in chunks of iterations (small_ket.cuh,
+      // k_small_lanczos); the stopping rule below is the same as in the launch-per-operation loop,
+      // applied to the returned (alpha, beta)
+      std::vector<double> al(max_m), be(max_m);
+      const int chunk = 12;
+      int done = 0;
+      bool stop = false;
+      while (!stop) {
+        int j1 = std::min(max_m, done + chunk);
+        launches += bk.small_lanczos(g1, prog, v0, basis, max_m, t_eval, done, j1, done > 0 ? be[done - 1] : 0.0,
+                                     al.data(), be.data(), &lz.nrm, stream);
+        if (done == 0 && lz.nrm == 0.0) {
+          if (out) bk.zero(out, sizeof(cplx) * n, stream);
+          return lz;
+        }
+        for (int j = done; j < j1 && !stop; ++j) {
+          lz.alpha.push_back(al[j]);
+          double beta = be[j];
+          lz.w = tridiag_expm_e1(lz.alpha, lz.beta, sign * delta);
+          lz.m = j + 1;
+          if (beta < o.norm_tolerance) { stop = true; break; }
+          if (j >= 1) {
+            const cplx& a = lz.w[j];
+            const cplx& b = lz.w[j - 1];
+            double est = (std::hypot(a.re, a.im) + std::hypot(b.re, b.im)) * beta * std::fabs(delta);
+            if (est < o.exp_tolerance) { stop = true; break; }
+          }
+          if (j + 1 == max_m) { stop = true; break; }
+          lz.beta.push_back(beta);
+        }
+        done = j1;
+      }
+      if (out) combine_basis(out, basis, lz.w, lz.m, lz.nrm, stream);
+      return lz;
+    }
     double* d_s = (double*)buf("kry_scal", sizeof(double) * 4);
     double hs[4];
     launches += bk.re_dot(g1, d_s, v0, v0, reduce_scratch(), stream);

@@ -8,6 +8,7 @@ namespace pd {
 namespace sk {
 void launch_forward(int nq, const SkFwd& P, int nC, cudaStream_t st);
 void launch_backward(int nq, const SkBwd& P, int nC, cudaStream_t st);
+void launch_lanczos(int nq, const SkLanczos& P, int nC, cudaStream_t st);
 }  // namespace sk
 using namespace sk;
 
@@ -353,6 +354,38 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
   return launches;
 }
 
+
+// Lanczos iterations [j0, j1) of one column vector on the device (KRYLOV_SE); fills basis[j0+1..j1]
+// (capped at max_m - 1), and alpha[j0..j1) / beta[j0..j1) on the host.  j0 = 0 normalises v0 into
+// basis[0] and returns |v0| in *nrm.  One launch.
+int small_ket_lanczos(SmallKetState& S, const Geometry& g1, const Program& prog, const cplx* v0, cplx* basis,
+                      int max_m, double t_eval, int j0, int j1, double beta_prev, double* alpha_host,
+                      double* beta_host, double* nrm, cudaStream_t st) {
+  int nC;
+  if (!small_shape(g1.dim, 1, nC)) throw Error(PD_ERR_STATE, "small_ket_lanczos: unsupported shape");
+  SkLanczos P{};
+  upload_prog(S, prog, g1, 1, prog.det_values.data(), prog.amp_values.data(), P.prog, st);
+  P.nC = nC; P.dim = g1.dim; P.t_eval = t_eval; P.j0 = j0; P.j1 = j1; P.max_m = max_m; P.beta_prev = beta_prev;
+  P.basis = basis; P.v0 = v0;
+  double* d_ab = (double*)S.get(18, sizeof(double) * (2 * (size_t)max_m + 1));
+  P.alpha = d_ab; P.beta = d_ab + max_m; P.nrm_out = d_ab + 2 * max_m;
+  const size_t ys_bytes = sizeof(uint4) * 2 * (2 * g1.dim), red_bytes = sizeof(uint4) * 2 * nC;
+  P.YS = (uint4*)S.get(3, ys_bytes);
+  P.red = (uint4*)S.get(4, red_bytes);
+  P.abort_flag = (int*)S.get(10, 64);
+  PD_CUDA_CHECK(cudaMemsetAsync(P.YS, 0, ys_bytes, st));
+  PD_CUDA_CHECK(cudaMemsetAsync(P.red, 0, red_bytes, st));
+  PD_CUDA_CHECK(cudaMemsetAsync(P.abort_flag, 0, 64, st));
+  sk::launch_lanczos(prog.nq, P, nC, st);
+  PD_CUDA_CHECK(cudaMemcpyAsync(alpha_host + j0, P.alpha + j0, sizeof(double) * (j1 - j0), cudaMemcpyDeviceToHost, st));
+  PD_CUDA_CHECK(cudaMemcpyAsync(beta_host + j0, P.beta + j0, sizeof(double) * (j1 - j0), cudaMemcpyDeviceToHost, st));
+  if (j0 == 0) PD_CUDA_CHECK(cudaMemcpyAsync(nrm, P.nrm_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+  int ab = 0;
+  PD_CUDA_CHECK(cudaMemcpyAsync(&ab, P.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PD_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (ab) throw Error(PD_ERR_STATE, "small_ket_lanczos: exchange poll timed out");
+  return 1;
+}
 
 // accepted / attempted steps of unit u of the batch recorded by forward sweep `tape_gen` (-1: unknown)
 void small_ket_unit_counts(SmallKetState& S, uint64_t tape_gen, int unit, int* accepted, int* attempts) {

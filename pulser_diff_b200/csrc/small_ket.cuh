@@ -712,6 +712,123 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Lanczos recurrence of KRYLOV_SE for one column vector: iterations
+// [j0, j1) of   r = H v_j;  alpha_j = <v_j, r>;  r -= alpha_j v_j + beta_{j-1} v_{j-1};
+// beta_j = |r|;  v_{j+1} = r / beta_j   in one cooperative launch.  The recurrence does not depend
+// on where the host stops it (exponential-error / breakdown tests on the tridiagonal matrix), so
+// the host applies the reference's stopping rule a posteriori to the returned (alpha, beta) and
+// uses the first m basis vectors.  H is frozen at t_eval (the interval end).
+// ------------------------------------------------------------------------------------------
+struct SkLanczos {
+  SkProg prog;
+  int nC;
+  size_t dim;
+  double t_eval;
+  int j0, j1, max_m;   // iterations of this launch; basis[j0] (and basis[j0-1]) are already in place
+  double beta_prev;    // beta_{j0-1} (0 for j0 = 0)
+  cplx* basis;         // [max_m][dim]; j0 = 0: basis[0] receives v0 / |v0|
+  const cplx* v0;      // j0 = 0 only
+  double* alpha;       // [max_m] device
+  double* beta;        // [max_m] device
+  double* nrm_out;     // |v0| (j0 = 0)
+  uint4* YS;           // [2][2 dim] LL lines (zeroed by the host)
+  uint4* red;          // [2][nC] LL lines
+  int* abort_flag;
+};
+
+template <int NQG>
+__global__ void __launch_bounds__(SK_T) k_small_lanczos(const __grid_constant__ SkLanczos P) {
+  constexpr int NH = NQG / 2;
+  __shared__ SkCoef coef[6];
+  __shared__ double s_red[SK_T / 32];
+  __shared__ double s_tot;
+  __shared__ double s_times[6];
+  __shared__ __align__(16) unsigned char s_tab[SK_TABLE_BYTES];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int part = tid & 1;
+  const unsigned cta = blockIdx.x;
+  const int nq = P.prog.nq;
+  const size_t dim = P.dim, L2 = 2 * P.dim;
+  SkProg prog = P.prog;
+  sk_cache_tables(prog, s_tab, tid);
+  const size_t r = (size_t)cta * SK_T + tid;
+  const bool on = r < L2;
+  const size_t rr = on ? r : (size_t)part;
+  const size_t e = rr >> 1;
+  SkLane<NH> ln;
+  sk_lane_init<NH>(ln, e, dim, nq, part, prog.diag[e & (dim - 1)]);
+  if (tid < 6) s_times[tid] = P.t_eval;
+  __syncthreads();
+  sk_eval_stages(prog, s_times, coef, tid);
+  SkStageCoef<NH> sc;
+  sk_stage_coef<NH>(sc, ln, coef[0], nq);
+  int par = 0, rpar = 0;
+  unsigned seq = 1, rseq = 1;
+
+  // sum over all lanes of the unit, identical in every thread (fixed summation order)
+  auto all_sum = [&](double x) -> double {
+    const double v = warp_sum_d(x);
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w];
+      ll_store(P.red + (size_t)rpar * P.nC + cta, tot, rseq);
+    }
+    if (warp == 0) {
+      double tot = 0.0;
+      for (int c = lane; c < P.nC; c += 32) {
+        uint4 v4;
+        SkPoll poll{P.abort_flag};
+        do { v4 = ll_load(P.red + (size_t)rpar * P.nC + c); } while (ll_bad(v4, rseq) != 0 && !poll.give_up());
+        tot += ll_value(v4);
+      }
+      tot = warp_sum_d(tot);
+      if (lane == 0) s_tot = tot;
+    }
+    __syncthreads();
+    const double out = s_tot;
+    __syncthreads();
+    ++rseq; rpar ^= 1;
+    return out;
+  };
+
+  double* basis = reinterpret_cast<double*>(P.basis);
+  double vj, vprev = 0.0, beta_prev = P.beta_prev;
+  if (P.j0 == 0) {
+    const double x = on ? reinterpret_cast<const double*>(P.v0)[rr] : 0.0;
+    const double nrm = sqrt(all_sum(x * x));
+    if (cta == 0 && tid == 0) *P.nrm_out = nrm;
+    vj = nrm > 0.0 ? x / nrm : 0.0;
+    if (on) basis[rr] = vj;
+  } else {
+    vj = on ? basis[(size_t)P.j0 * L2 + rr] : 0.0;
+    vprev = on ? basis[(size_t)(P.j0 - 1) * L2 + rr] : 0.0;
+  }
+  for (int j = P.j0; j < P.j1; ++j) {
+    // r = H v_j: publish the lane, poll the partners; plain H (no factor -i):
+    //   part 0 needs (H v).re, part 1 needs (H v).im; sk_apply_lane returns -iH v, i.e.
+    //   part 0 -> (H v).im, part 1 -> -(H v).re, so swap the parts back through the sibling lane
+    uint4* buf = P.YS + (size_t)par * L2;
+    if (on) ll_store(buf + r, vj, seq);
+    const double vo = __shfl_xor_sync(0xffffffffu, vj, 1);
+    const double mih = sk_apply_lane<NH>(sc, ln, vo, buf, seq, on, P.abort_flag);   // lane's part of -i H v
+    par ^= 1; ++seq;
+    const double other = __shfl_xor_sync(0xffffffffu, mih, 1);
+    // (-iHv).re = (Hv).im (held by part 0), (-iHv).im = -(Hv).re (held by part 1)
+    double rl = part == 0 ? -other : other;      // part 0: (Hv).re = -(-iHv).im ; part 1: (Hv).im = (-iHv).re
+    if (!on) rl = 0.0;
+    const double a = all_sum(vj * rl);
+    rl = rl - a * vj - beta_prev * vprev;
+    const double b = sqrt(all_sum(rl * rl));
+    if (cta == 0 && tid == 0) { P.alpha[j] = a; P.beta[j] = b; }
+    const double vnext = b > 0.0 ? rl / b : 0.0;
+    if (on && j + 1 < P.max_m) basis[(size_t)(j + 1) * L2 + rr] = vnext;
+    vprev = vj; vj = vnext; beta_prev = b;
+  }
+}
+
 static __global__ void k_fold_columns(const double* __restrict__ in, double* __restrict__ out, size_t dim, int batch) {
   size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= dim) return;

@@ -36,6 +36,10 @@ class HostBackend {
   // the small-register cooperative kernels exist only in the CUDA build
   bool small_supported(const Geometry&, const Program&) { return false; }
   bool small_units_supported(const Geometry&, const Program&) { return false; }
+  int small_lanczos(const Geometry&, const Program&, const cplx*, cplx*, int, double, int, int, double, double*,
+                    double*, double*, void*) {
+    throw Error(PD_ERR_STATE, "small-register kernels need the CUDA build");
+  }
   int small_forward(const Geometry&, const Program&, const Tableau&, const pd_options&, int, const cplx*,
                     const double*, const double*, const double*, int, cplx*,
                     std::vector<std::vector<pd_step_record>>&, bool, uint64_t*, void*) {
