@@ -73,68 +73,56 @@ def loss_diag(n, device):
 
 
 # ------------------------------------------------------------------------------------------------
-class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons DURING the timed region.  NVML in-process (nvidia_ml_py): spawning
-    `nvidia-smi` every 200 ms takes driver locks that stall the launches of a 10-ms timed region."""
+class ClockSampler:
+    """SM clock and throttle reasons DURING the timed regions: one in-process NVML query after every timed
+    pass, from the timing thread itself.  (A background sampler -- `nvidia-smi` every 200 ms, or NVML from
+    a second thread -- contends for driver locks with the cooperative launches and stalled single passes
+    of this 10-ms workload by 20-200 ms; the query below costs ~0.1 ms and is inside the timed region.)"""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
-    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.index, self.sm, self.reasons, self.max = index, [], set(), 0.0
         self._nvml = None
         try:
             import pynvml
             pynvml.nvmlInit()
             self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self._nvml = pynvml
-            self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self.max = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
         except Exception:
             self._nvml = None
 
-    def _sample_nvml(self):
-        nv = self._nvml
-        sm = float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
-        try:
-            mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
-        except Exception:
-            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
-        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
-        flags = ["Active" if mask & bits[n] else "Not Active" for n in self.NAMES]
-        self.rows.append([str(sm), str(self._max), "0"] + flags)
+    def start(self):
+        self.sample()
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                if self._nvml is not None:
-                    self._sample_nvml()
-                else:
-                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                    self.rows.append([x.strip() for x in out.strip().split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.05 if self._nvml is not None else 0.2)
+    def sample(self):
+        try:
+            if self._nvml is not None:
+                nv = self._nvml
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self._h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+                self.reasons |= {n for n in self.NAMES if mask & self.BITS[n]}
+            else:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                r = [x.strip() for x in out.strip().split(",")]
+                self.sm.append(float(r[0])); self.max = max(self.max, float(r[1]))
+                self.reasons |= {n for n, v in zip(self.NAMES, r[3:7]) if v.lower().startswith("active")}
+        except Exception:
+            pass
 
     def summary(self):
-        self._halt.set()
-        self.join(timeout=2)
-        sm, mx, reasons = [], 0.0, set()
-        names = self.NAMES
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for nme, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nme)
-            except Exception:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm),
-                "source": "nvml" if self._nvml is not None else "nvidia-smi"}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max or None,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml (one query per timed pass)" if self._nvml is not None else "nvidia-smi"}
 
 
 def measured_traffic(key: str):
@@ -230,6 +218,7 @@ def run_b200(args):
     ev0.record()
     for _ in range(args.steps):
         resident_pass()
+        sampler.sample()
     ev1.record()
     barrier()
     t_res = time.perf_counter() - t0
@@ -239,6 +228,7 @@ def run_b200(args):
     t0 = time.perf_counter()
     for _ in range(args.steps):
         loss_val, ga, gd, _, _ = e2e_pass()
+        sampler.sample()
     barrier()
     t_e2e = time.perf_counter() - t0
 

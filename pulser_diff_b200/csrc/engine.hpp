@@ -94,6 +94,7 @@ class Engine {
     prog.amp_masks.assign(am, am + n_amp);
     prog.det_values.assign(dv, dv + (size_t)n_det * n_samples);
     prog.amp_values.assign(av, av + (size_t)n_amp * n_samples * 2);
+    ++prog.version;
   }
   void set_collapse(int n_ops, const double* ops) {
     if (prog.kind != PD_DENSITY) throw Error(PD_ERR_INVALID, "collapse operators need a density plan");
@@ -187,6 +188,7 @@ class Engine {
       for (int u = 0; u < n_units; ++u) {
         std::copy(dv + u * nd, dv + (u + 1) * nd, prog.det_values.begin());
         std::copy(av + u * na, av + (u + 1) * na, prog.amp_values.begin());
+        ++prog.version;
         forward(PD_SOLVER_DP5_SE, o, state0 + (size_t)u * L, tsave, n_t, states + (size_t)u * n_t * L,
                 tapes ? &(*tapes)[u] : nullptr, stream);
         if (tapes) (*tapes)[u].small_gen = 0;      // the device tape is overwritten by the next unit
@@ -257,6 +259,7 @@ class Engine {
       for (int u = 0; u < n_units; ++u) {
         std::copy(dv + u * nd, dv + (u + 1) * nd, prog.det_values.begin());
         std::copy(av + u * na, av + (u + 1) * na, prog.amp_values.begin());
+        ++prog.version;
         backward(tapes[u], states_for_fallback_ + (size_t)u * n_t * L,
                  gstates ? gstates + (size_t)u * n_t * L : nullptr, g_det ? g_det + u * nd : nullptr,
                  g_amp ? g_amp + u * na : nullptr, nullptr, nullptr,

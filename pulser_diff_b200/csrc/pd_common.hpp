@@ -120,6 +120,7 @@ struct Program {
   std::vector<double> det_values;  // [n_det][n_samples]
   std::vector<double> amp_values;  // [n_amp][n_samples][2]
   std::vector<double> pair_u;      // [nq*nq]
+  uint64_t version = 0;            // bumped whenever the coefficient tables change (device-side caches)
   int n_collapse = 0;
   std::vector<cplx> collapse;      // [n_ops][2][2]
   cplx dsup[16];                   // static dissipator on the (row,col) pair space, [p][p']

@@ -18,6 +18,7 @@ struct SmallKetState {
   unsigned long long *d_dm = nullptr, *d_am = nullptr;
   double *d_dv = nullptr, *d_av = nullptr;
   size_t cap_dm = 0, cap_am = 0, cap_dv = 0, cap_av = 0;
+  uint64_t uploaded_version = 0;   // Program::version of the single-unit tables currently on the device
   // workspace
   void* ws[20] = {};
   size_t ws_cap[20] = {};
@@ -90,10 +91,15 @@ static void upload_prog(SmallKetState& S, const Program& prog, const Geometry& g
   };
   static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "mask width");
   const size_t ns = (size_t)prog.n_samples;
-  up(S.d_dm, S.cap_dm, prog.det_masks.data(), prog.det_masks.size() * 8);
-  up(S.d_am, S.cap_am, prog.amp_masks.data(), prog.amp_masks.size() * 8);
-  up(S.d_dv, S.cap_dv, dv, (size_t)n_units * prog.n_det() * ns * 8);
-  up(S.d_av, S.cap_av, av, (size_t)n_units * prog.n_amp() * ns * 16);
+  // the plan's own tables stay on the device until the program changes (Program::version)
+  const bool own = n_units == 1 && dv == prog.det_values.data() && av == prog.amp_values.data();
+  if (!(own && S.uploaded_version == prog.version && prog.version != 0)) {
+    up(S.d_dm, S.cap_dm, prog.det_masks.data(), prog.det_masks.size() * 8);
+    up(S.d_am, S.cap_am, prog.amp_masks.data(), prog.amp_masks.size() * 8);
+    up(S.d_dv, S.cap_dv, dv, (size_t)n_units * prog.n_det() * ns * 8);
+    up(S.d_av, S.cap_av, av, (size_t)n_units * prog.n_amp() * ns * 16);
+    S.uploaded_version = own ? prog.version : 0;
+  }
   o.nq = prog.nq; o.n_samples = prog.n_samples; o.n_det = prog.n_det(); o.n_amp = prog.n_amp();
   o.dt = prog.dt;
   o.det_masks = S.d_dm; o.det_values = S.d_dv; o.amp_masks = S.d_am; o.amp_values = S.d_av;
@@ -164,11 +170,16 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
   if (want_tape) {
     // per accepted step: 6 stage inputs + 6 slopes; sized from the time grid, bounded by memory
     const size_t per_step = 6 * L * sizeof(cplx) * U;
-    size_t fr = 0, tot = 0;
-    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) fr = (size_t)4 << 30;
-    const size_t budget = std::max<size_t>((size_t)3 << 29, fr / 8) + S.ws_cap[14];
-    size_t steps_cap = std::min<size_t>((size_t)16 * n_t + 256, budget / per_step);
-    if (S.ws_cap[14] / per_step > steps_cap) steps_cap = S.ws_cap[14] / per_step;
+    const size_t want_steps = (size_t)16 * n_t + 256;
+    size_t steps_cap = S.ws_cap[14] / per_step;            // what the plan already owns
+    if (steps_cap < want_steps) {
+      // grow (rare): only now ask the driver how much is free -- cudaMemGetInfo stalls for tens of
+      // milliseconds every so often and must stay out of the steady state
+      size_t fr = 0, tot = 0;
+      if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) fr = (size_t)4 << 30;
+      const size_t budget = std::max<size_t>((size_t)3 << 29, fr / 8) + S.ws_cap[14];
+      steps_cap = std::max(steps_cap, std::min(want_steps, budget / per_step));
+    }
     if (steps_cap >= 1) {
       P.tapeY = (double*)S.get(14, steps_cap * per_step);
       P.tapeK = (double*)S.get(15, steps_cap * per_step);
