@@ -176,9 +176,11 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 template <int NH>
 struct SkLane {
   unsigned eoff;          // byte offset of the element's pair of lines (32 B per element)
-  unsigned xm[NH];        // XOR masks on eoff selecting partner j (bit position 2j + part)
+  unsigned xm[NH];        // XOR masks on eoff selecting partner j (bit position 2j + part); 0 = no such qubit
+  double wv[NH];          // 1 for a real partner, 0 for a padding slot (which re-reads the own lines)
+  double sg[NH];          // +1 if the element's bit is set (ground), -1 if clear (Rydberg), 0 for padding
   unsigned bits;          // basis-state bits of the element
-  int part, jmax;         // jmax partners are real (bit position < nq)
+  int part;
   int nzero;              // number of zero (Rydberg) bits: multiplies a uniform detuning
   double dint;
 };
@@ -187,29 +189,44 @@ __device__ __forceinline__ void sk_lane_init(SkLane<NH>& ln, size_t e, size_t di
   ln.eoff = (unsigned)e * 32u;
   ln.bits = (unsigned)(e & (dim - 1));
   ln.part = part;
-  ln.jmax = nq > part ? (nq - part + 1) / 2 : 0;
-  if (ln.jmax > NH) ln.jmax = NH;
 #pragma unroll
-  for (int j = 0; j < NH; ++j) ln.xm[j] = 32u << (2 * j + part);
+  for (int j = 0; j < NH; ++j) {
+    const int p = 2 * j + part;
+    const bool real = p < nq;
+    ln.xm[j] = real ? 32u << p : 0u;
+    ln.wv[j] = real ? 1.0 : 0.0;
+    ln.sg[j] = real ? (((ln.bits >> p) & 1) ? 1.0 : -1.0) : 0.0;
+  }
   ln.nzero = nq - __popc(ln.bits);
   ln.dint = dint;
+}
+// partner-line pointers of one exchange buffer (thread constants; the loads then need no address math)
+template <int NH>
+struct SkPtrs {
+  const char* p[NH];
+  uint4* own;
+};
+template <int NH>
+__device__ __forceinline__ void sk_ptrs_init(SkPtrs<NH>& o, const SkLane<NH>& ln, uint4* buf, size_t r) {
+  const char* base = reinterpret_cast<const char*>(buf);
+#pragma unroll
+  for (int j = 0; j < NH; ++j) o.p[j] = base + (ln.eoff ^ ln.xm[j]);
+  o.own = buf + r;
 }
 template <int NH>
 struct SkStageCoef {
   double dsum;
-  double gre[NH], gim[NH];   // gim carries the sign of the element's bit (conj for Rydberg)
+  int uniform;
+  double gre_u, gim_u;        // uniform drive: one coefficient for every qubit
+  double gre[NH], gim[NH];    // general: per partner, gim carries the sign of the element's bit
 };
 template <int NH>
 __device__ __forceinline__ void sk_stage_coef(SkStageCoef<NH>& o, const SkLane<NH>& ln, const SkCoef& c, int nq) {
+  o.uniform = c.uniform;
   if (c.uniform) {
-    const double gre = c.gre[0], gim = c.gim[0];
+    o.gre_u = c.gre[0];
+    o.gim_u = c.gim[0];
     o.dsum = fma(c.d[0], (double)ln.nzero, ln.dint);
-#pragma unroll
-    for (int j = 0; j < NH; ++j) {
-      const bool a = (ln.bits >> (2 * j + ln.part)) & 1;
-      o.gre[j] = gre;
-      o.gim[j] = a ? gim : -gim;
-    }
   } else {
     double dsum = ln.dint;
     for (int p = 0; p < nq; ++p) dsum += ((ln.bits >> p) & 1) ? 0.0 : c.d[p];
@@ -217,48 +234,53 @@ __device__ __forceinline__ void sk_stage_coef(SkStageCoef<NH>& o, const SkLane<N
 #pragma unroll
     for (int j = 0; j < NH; ++j) {
       const int p = 2 * j + ln.part;
-      const bool a = (ln.bits >> p) & 1;
-      const double gim = p < nq ? c.gim[p] : 0.0;
       o.gre[j] = p < nq ? c.gre[p] : 0.0;
-      o.gim[j] = a ? gim : -gim;
+      o.gim[j] = p < nq ? ln.sg[j] * c.gim[p] : 0.0;
     }
   }
 }
 // value of the lane for -iH (negate for +iH); `other` = the element's other part of Y.
-// buf: LL lines of the published vector, two consecutive lines (re, im) per element.
+// pp: LL lines of the published vector (two consecutive lines re, im per element).
 template <int NH>
 __device__ __forceinline__ double sk_apply_lane(const SkStageCoef<NH>& sc, const SkLane<NH>& ln, double other,
-                                                const uint4* __restrict__ buf, unsigned seq, bool active,
-                                                int* abort_flag) {
-  double sre0 = 0.0, sim0 = 0.0, sre1 = 0.0, sim1 = 0.0;
+                                                const SkPtrs<NH>& pp, unsigned seq, bool active, int* abort_flag) {
+  double sre = 0.0, sim = 0.0;
   if (active) {
-    const char* base = reinterpret_cast<const char*>(buf);
     uint4 lr[NH], li[NH];
     unsigned bad;
     SkPoll poll{abort_flag};
     do {
 #pragma unroll
-      for (int j = 0; j < NH; ++j)
-        if (j < ln.jmax) {
-          const unsigned off = ln.eoff ^ ln.xm[j];
-          lr[j] = ll_load(base + off);
-          li[j] = ll_load(base + off + 16);
-        }
+      for (int j = 0; j < NH; ++j) {
+        lr[j] = ll_load(pp.p[j]);
+        li[j] = ll_load(pp.p[j] + 16);
+      }
       bad = 0;
 #pragma unroll
-      for (int j = 0; j < NH; ++j)
-        if (j < ln.jmax) bad |= ll_bad(lr[j], seq) | ll_bad(li[j], seq);
+      for (int j = 0; j < NH; ++j) bad |= ll_bad(lr[j], seq) | ll_bad(li[j], seq);
     } while (bad != 0 && !poll.give_up());
+    // (H Y).re += g.re*pv.re - gim*pv.im ;  (H Y).im += g.re*pv.im + gim*pv.re   (gim signed by the own bit)
+    if (sc.uniform) {
+      double a0 = 0.0, c0 = 0.0, b0 = 0.0, d0 = 0.0;
 #pragma unroll
-    for (int j = 0; j < NH; ++j)
-      if (j < ln.jmax) {
+      for (int j = 0; j < NH; ++j) {
         const double pre = ll_value(lr[j]), pim = ll_value(li[j]);
-        // (H Y).re += g.re*pv.re - gim*pv.im ;  (H Y).im += g.re*pv.im + gim*pv.re
+        a0 = fma(ln.wv[j], pre, a0); c0 = fma(ln.wv[j], pim, c0);
+        b0 = fma(ln.sg[j], pim, b0); d0 = fma(ln.sg[j], pre, d0);
+      }
+      sre = fma(sc.gre_u, a0, -sc.gim_u * b0);
+      sim = fma(sc.gre_u, c0, sc.gim_u * d0);
+    } else {
+      double sre0 = 0.0, sim0 = 0.0, sre1 = 0.0, sim1 = 0.0;
+#pragma unroll
+      for (int j = 0; j < NH; ++j) {
+        const double pre = ll_value(lr[j]), pim = ll_value(li[j]);
         sre0 = fma(sc.gre[j], pre, sre0); sre1 = fma(-sc.gim[j], pim, sre1);
         sim0 = fma(sc.gre[j], pim, sim0); sim1 = fma(sc.gim[j], pre, sim1);
       }
+      sre = sre0 + sre1; sim = sim0 + sim1;
+    }
   }
-  const double sre = sre0 + sre1, sim = sim0 + sim1;
   // part 0 needs (H Y).im, part 1 needs (H Y).re: hand the other lane the half it is missing
   const double give = ln.part == 0 ? sre : sim;
   const double recv = __shfl_xor_sync(0xffffffffu, give, 1);
@@ -402,13 +424,17 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
     return nrm;
   };
   // one application of -iH(t_idx) on the lane value v (publishes it, polls the partners)
+  // partner / own line pointers of the two exchange buffers
+  SkPtrs<NH> pp[2];
+  sk_ptrs_init<NH>(pp[0], ln, YS, rr);
+  sk_ptrs_init<NH>(pp[1], ln, YS + L2, rr);
   auto apply_at = [&](int cidx, double v) -> double {
-    uint4* buf = YS + (size_t)par * L2;
-    if (on) ll_store(buf + r, v, seq);
+    const SkPtrs<NH>& q = par ? pp[1] : pp[0];
+    if (on) ll_store(q.own, v, seq);
     const double vo = __shfl_xor_sync(0xffffffffu, v, 1);
     SkStageCoef<NH> sc;
     sk_stage_coef<NH>(sc, ln, coef[cidx], nq);
-    double out = sk_apply_lane<NH>(sc, ln, vo, buf, seq, on, P.abort_flag);
+    double out = sk_apply_lane<NH>(sc, ln, vo, q, seq, on, P.abort_flag);
     par ^= 1; ++seq;
     return on ? out : 0.0;
   };
@@ -440,6 +466,9 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
     }
     error = 1.0; cache_dt = dt; cache_err = 1.0;
     kk = 0;
+    // the start-up used one (replay) or two exchanges; the stage loop below indexes the buffers
+    // statically, so hand it the buffer whose turn it is as pp[0]
+    if (par) { const SkPtrs<NH> tmp = pp[0]; pp[0] = pp[1]; pp[1] = tmp; par = 0; }
     __syncthreads();
   }
 
@@ -476,20 +505,21 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
       // ---- stages 2..7 -------------------------------------------------------------------
 #pragma unroll
       for (int i = 1; i < 7; ++i) {
-        uint4* buf = YS + (size_t)par * L2;
+        // six exchanges per attempt (and two in the start-up): the buffer parity of stage i is static
+        const SkPtrs<NH>& q = pp[(i - 1) & 1];
         double v = y;
 #pragma unroll
         for (int j = 0; j < i; ++j) v = fma(dt * P.tab.beta[i - 1][j], k[j], v);
-        if (on) ll_store(buf + r, v, seq);
+        if (on) ll_store(q.own, v, seq);
         if (i == 6) ynew = v;
         if (tY && i < 6 && on) tY[(size_t)i * L2 + r] = v;
         const double vo = __shfl_xor_sync(0xffffffffu, v, 1);
         SkStageCoef<NH> sc;
         sk_stage_coef<NH>(sc, ln, coef[i - 1], nq);
-        k[i] = sk_apply_lane<NH>(sc, ln, vo, buf, seq, on, P.abort_flag);
+        k[i] = sk_apply_lane<NH>(sc, ln, vo, q, seq, on, P.abort_flag);
         if (!on) k[i] = 0.0;
         if (tK && i < 6 && on) tK[(size_t)i * L2 + r] = k[i];
-        par ^= 1; ++seq;
+        ++seq;
       }
       // ---- error norm ----------------------------------------------------------------------
       double er = 0.0;
@@ -607,7 +637,9 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
   const double* gst = P.gstates ? reinterpret_cast<const double*>(P.gstates + unit * (size_t)P.n_t * L) : nullptr;
   double wacc = 0.0;
   double lam = (on && gst) ? gst[(size_t)(P.n_t - 1) * L2 + rr] : 0.0;
-  int bpar = 0;
+  SkPtrs<NH> pp[2];
+  sk_ptrs_init<NH>(pp[0], ln, KB, rr);
+  sk_ptrs_init<NH>(pp[1], ln, KB + L2, rr);
   unsigned seq = 1;
   int hi = n_steps;
   for (int kk = P.n_t - 1; kk >= 1; --kk) {
@@ -625,11 +657,11 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
       double yb[6];
 #pragma unroll
       for (int i = 5; i >= 0; --i) {
-        uint4* buf = KB + (size_t)bpar * L2;
+        const SkPtrs<NH>& q = pp[(5 - i) & 1];      // six exchanges per step: static buffer parity
         double u = h * P.tab.b5[i] * lam;
 #pragma unroll
         for (int j = i + 1; j < 6; ++j) u = fma(h * P.tab.beta[j - 1][i], yb[j], u);
-        if (on) ll_store(buf + r, u, seq);
+        if (on) ll_store(q.own, u, seq);
         const double uo = __shfl_xor_sync(0xffffffffu, u, 1);
         SkStageCoef<NH> sc;
         sk_stage_coef<NH>(sc, ln, coef[i], nq);
@@ -641,11 +673,11 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
         if (P.want_coef) {
 #pragma unroll
           for (int j = 0; j < NH; ++j)
-            if (j < ln.jmax) pv[j] = *reinterpret_cast<const double2*>(ysrc + ((ln.eoff ^ ln.xm[j]) >> 1));
+            pv[j] = *reinterpret_cast<const double2*>(ysrc + ((ln.eoff ^ ln.xm[j]) >> 1));
         }
-        yb[i] = -sk_apply_lane<NH>(sc, ln, uo, buf, seq, on, P.abort_flag);
+        yb[i] = -sk_apply_lane<NH>(sc, ln, uo, q, seq, on, P.abort_flag);
         if (!on) yb[i] = 0.0;
-        bpar ^= 1; ++seq;
+        ++seq;
         // ---- per-term gradient sums of this slot -----------------------------------------------
         // kb = conj(u_e); self = kb*Y_e; fl_j = kb*Y_partner(j).  Everything stays in registers.
         if (P.want_coef || P.wacc_elem) {
@@ -658,7 +690,7 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
 #pragma unroll
             for (int j = 0; j < NH; ++j) {
               gd[j] = 0.0; ga[j] = 0.0; gb[j] = 0.0;
-              if (j < ln.jmax && on) {
+              if (ln.wv[j] != 0.0 && on) {
                 const bool a = (ln.bits >> (2 * j + part)) & 1;
                 const double fl_re = ure * pv[j].x + uim * pv[j].y;
                 const double fl_im = ure * pv[j].y - uim * pv[j].x;
@@ -672,7 +704,7 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
               double v = 0.0;
 #pragma unroll
               for (int j = 0; j < NH; ++j)
-                if (j < ln.jmax && (m >> (nq - 1 - (2 * j + part)) & 1ull)) v += gd[j];
+                if (ln.wv[j] != 0.0 && (m >> (nq - 1 - (2 * j + part)) & 1ull)) v += gd[j];
               v = warp_sum_d(v);
               if (lane == 0) s_red[warp][kd] = v;
             }
@@ -681,7 +713,7 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
               double va = 0.0, vb = 0.0;
 #pragma unroll
               for (int j = 0; j < NH; ++j)
-                if (j < ln.jmax && (m >> (nq - 1 - (2 * j + part)) & 1ull)) { va += ga[j]; vb += gb[j]; }
+                if (ln.wv[j] != 0.0 && (m >> (nq - 1 - (2 * j + part)) & 1ull)) { va += ga[j]; vb += gb[j]; }
               va = warp_sum_d(va);
               vb = warp_sum_d(vb);
               if (lane == 0) { s_red[warp][n_det + 2 * ka] = va; s_red[warp][n_det + 2 * ka + 1] = vb; }
@@ -765,6 +797,9 @@ __global__ void __launch_bounds__(SK_T) k_small_lanczos(const __grid_constant__ 
   sk_stage_coef<NH>(sc, ln, coef[0], nq);
   int par = 0, rpar = 0;
   unsigned seq = 1, rseq = 1;
+  SkPtrs<NH> pp[2];
+  sk_ptrs_init<NH>(pp[0], ln, P.YS, rr);
+  sk_ptrs_init<NH>(pp[1], ln, P.YS + L2, rr);
 
   // sum over all lanes of the unit, identical in every thread (fixed summation order)
   auto all_sum = [&](double x) -> double {
@@ -810,10 +845,10 @@ __global__ void __launch_bounds__(SK_T) k_small_lanczos(const __grid_constant__ 
     // r = H v_j: publish the lane, poll the partners; plain H (no factor -i):
     //   part 0 needs (H v).re, part 1 needs (H v).im; sk_apply_lane returns -iH v, i.e.
     //   part 0 -> (H v).im, part 1 -> -(H v).re, so swap the parts back through the sibling lane
-    uint4* buf = P.YS + (size_t)par * L2;
-    if (on) ll_store(buf + r, vj, seq);
+    const SkPtrs<NH>& q = par ? pp[1] : pp[0];
+    if (on) ll_store(q.own, vj, seq);
     const double vo = __shfl_xor_sync(0xffffffffu, vj, 1);
-    const double mih = sk_apply_lane<NH>(sc, ln, vo, buf, seq, on, P.abort_flag);   // lane's part of -i H v
+    const double mih = sk_apply_lane<NH>(sc, ln, vo, q, seq, on, P.abort_flag);   // lane's part of -i H v
     par ^= 1; ++seq;
     const double other = __shfl_xor_sync(0xffffffffu, mih, 1);
     // (-iHv).re = (Hv).im (held by part 0), (-iHv).im = -(Hv).re (held by part 1)
