@@ -271,46 +271,12 @@ k_corr_ket(const cplx* __restrict__ kbar, const cplx* __restrict__ y, int nq, si
   block_reduce_write<kQC * 8>(acc, partial + (size_t)blockIdx.y * gridDim.x * (kQC * 8));
 }
 
-// One density site per blockIdx.y: C_q[p][p'] = sum_{idx: p(idx)=p} conj(kbar) * y[idx with site := p']
-__global__ void __launch_bounds__(kThreads)
-k_corr_density(const cplx* __restrict__ kbar, const cplx* __restrict__ y, int nq, size_t total,
-               double* partial, double* wacc, double wscale) {
-  int q = blockIdx.y;
-  size_t S = (size_t)1 << nq, dim = S * S;
-  size_t mc = (size_t)1 << (nq - 1 - q), mr = mc << nq;
-  double acc[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = 0.0;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    size_t e = idx & (dim - 1);
-    int p = ((e & mr) ? 2 : 0) | ((e & mc) ? 1 : 0);
-    cplx kb = conj(kbar[idx]);
-    cplx self = kb * y[idx], frow = kb * y[idx ^ mr], fcol = kb * y[idx ^ mc],
-         fboth = kb * y[idx ^ mr ^ mc];
-#pragma unroll
-    for (int pr = 0; pr < 4; ++pr)
-      if (pr == p) {
-        acc[(pr * 4 + pr) * 2 + 0] += self.re;        acc[(pr * 4 + pr) * 2 + 1] += self.im;
-        acc[(pr * 4 + (pr ^ 2)) * 2 + 0] += frow.re;  acc[(pr * 4 + (pr ^ 2)) * 2 + 1] += frow.im;
-        acc[(pr * 4 + (pr ^ 1)) * 2 + 0] += fcol.re;  acc[(pr * 4 + (pr ^ 1)) * 2 + 1] += fcol.im;
-        acc[(pr * 4 + (pr ^ 3)) * 2 + 0] += fboth.re; acc[(pr * 4 + (pr ^ 3)) * 2 + 1] += fboth.im;
-      }
-    if (wacc && q == 0) {
-      double w = wscale * self.im;
-      atomicAdd(&wacc[e >> nq], w);
-      atomicAdd(&wacc[e & (S - 1)], -w);
-    }
-  }
-  block_reduce_write<32>(acc, partial + (size_t)blockIdx.y * gridDim.x * 32);
-}
-
 // All density sites in ONE pass: per site only the three real sums the gradient distribution reads
 // (engine.hpp::distribute, density branch) are accumulated,
 //   gd_q = sum_idx ((a==0) - (b==0)) Im(self),  ga_q = sum_idx Im(frow) - Im(fcol),
 //   gb_q = sum_idx (a ? 1 : -1) Re(frow) + (b ? 1 : -1) Re(fcol)
 // with a / b the row / column bit of site q, self = conj(kbar) y, frow / fcol = conj(kbar) times y
-// with the row / column bit flipped.  (The per-site 4x4 correlation of k_corr_density costs one
+// with the row / column bit flipped.  (A per-site 4x4 correlation kernel, the first version, cost one
 // pass over the 4^N vector per site.)
 constexpr int kDF = 3 * kMaxSitesDensity;
 __global__ void __launch_bounds__(kThreads)

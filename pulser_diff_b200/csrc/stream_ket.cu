@@ -58,16 +58,9 @@ struct StreamParams {
   double* err_partial;        // [gridDim.x] (g launch, nullable)
 };
 
-__device__ __forceinline__ cplx ldg(const cplx* p) {
-  double2 v = __ldg(reinterpret_cast<const double2*>(p));
-  return {v.x, v.y};
-}
 __device__ __forceinline__ cplx ldcs(const cplx* p) {
   double2 v = __ldcs(reinterpret_cast<const double2*>(p));
   return {v.x, v.y};
-}
-__device__ __forceinline__ void stcs(cplx* p, cplx v) {
-  __stcs(reinterpret_cast<double2*>(p), make_double2(v.re, v.im));
 }
 
 // ---- A launch: contiguous tile, combination + diagonal + low-bit flips ---------------------------
