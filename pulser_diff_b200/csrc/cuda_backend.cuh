@@ -220,15 +220,18 @@ class CudaBackend {
     }
     return n + launch_apply_ket(g, out, src, so, st(s));
   }
+  // Automatic family for large kets, from the measured DP5 step times (profiles/r01_stream_n26.md):
+  // N = 18 and 21..23 tiled, N = 19, 20 and >= 24 stream.  path 2 / 4 force one of them.
+  static bool stream_preferred(int nq) { return nq == 19 || nq == 20 || nq >= 24; }
   bool use_tiled(const Geometry& g) const {
     if (path == 1 || path == 4 || !tiled_ket_supported(g)) return false;
-    return path == 2 || g.nq >= kAutoTiledMinQubits;
+    if (path == 2) return true;
+    return g.nq >= kAutoTiledMinQubits && !(stream_preferred(g.nq) && stream_ket_supported(g));
   }
-  // path 4 forces the stream family; automatic choice: registers too large for the two-type tiles
   bool use_stream(const Geometry& g) const {
     if (!stream_ket_supported(g)) return false;
     if (path == 4) return true;
-    return path == 0 && !tiled_ket_supported(g) && g.nq >= kAutoTiledMinQubits;
+    return path == 0 && g.nq >= kAutoTiledMinQubits && (stream_preferred(g.nq) || !tiled_ket_supported(g));
   }
   // One full Dormand-Prince step with the alternating tiled kernels; 0 = not handled here.
   int dp5_step_ket(const Geometry& g, const cplx* y, cplx* const* k, cplx* ynew,
