@@ -253,8 +253,8 @@ def run_b200(args):
             s_amp = 2 ** nr
             ach = 576.0 * s_amp / (ms_step * 1e-3) / 1e9
             ach_h = 40.0 * s_amp / (ms_h * 1e-3) / 1e9
-            family = ("tiled (smem + TMEM, alternating tile types, fused DP5 step)" if 18 <= nr <= 23 else
-                      "stream (one bit-group of H per launch, >= 256 B pieces)" if nr >= 24 else "gather")
+            family = ("stream (one bit-group of H per launch, >= 256 B pieces)" if nr in (19, 20) or nr >= 24 else
+                      "tiled (smem + TMEM, alternating tile types, fused DP5 step)" if 18 <= nr <= 23 else "gather")
             r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                  "traffic": measured_traffic(f"dp5_step_n{nr}"), "peak_source": peak_src,
                  "kernel": "DP5 step kernel sequence (6 generator applications + stage combines + error norm)",

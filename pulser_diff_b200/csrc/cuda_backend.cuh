@@ -6,8 +6,9 @@
 //     working set is cache resident, and the Lindblad path.
 //   * "small" (small_ket*.cu): kets of N <= 14 -- the whole adaptive evolution / adjoint sweep as one
 //     cooperative kernel with register-resident lanes and a flag-in-data exchange through L2.
-//   * "tiled" (tiled_ket.cu): kets of 18 <= N <= 23 -- two tile types, fused finalise/start launches.
-//   * "stream" (stream_ket.cu): kets of N >= 24 -- one bit-group of H per launch, >= 256 B pieces.
+//   * "tiled" (tiled_ket.cu): kets of N = 18, 21..23 -- two tile types, fused finalise/start launches.
+//   * "stream" (stream_ket.cu): kets of N = 19, 20 and N >= 24 -- one bit-group of H per launch, >= 256 B
+//     pieces; its tiled correlation kernels also serve the adjoint sweep of the tiled family.
 #pragma once
 #include <cuda_runtime.h>
 
