@@ -179,6 +179,16 @@ int pd_tape_destroy(pd_tape* t);
 int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t,
                    const double* obs_dev, double* out_host /* complex [n_t] */);
 
+/* ---- sharded register: flips of the qubits that index the GPU (the reference is
+ * single-process, SURVEY.md 5.8, so there is no reference site to cite) ----------------------- */
+/* out[i] += shift * psi[i] + sum_k coef_k * peer_slices[k][i]  over the plan's 2^N amplitudes
+ * (x batch).  peer_slices[k] are device pointers to the partner ranks' slices; they may be
+ * peer-mapped (NVLink) memory and are read in place -- no receive buffer.  coef_host: complex
+ * [n_peers] (re, im pairs).  The caller orders the launch after the partners' writes. */
+int pd_sharded_accumulate(pd_plan* p, void* stream, void* out_dev, const void* psi_dev, double shift,
+                          int32_t n_peers, const void* const* peer_slices,
+                          const double* coef_host);
+
 /* ---- measurement hooks (bench.py roofline) ------------------------------------------------- */
 /* Average device time (ms, CUDA events on `stream`) of `reps` back-to-back H(t)·psi
  * applications in -> out. */

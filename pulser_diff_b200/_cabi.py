@@ -48,7 +48,7 @@ EXPORTS = (
     "pd_hpsi", "pd_rhs",
     "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
     "pd_evolve_forward_units", "pd_evolve_backward_units", "pd_tape_unit_steps",
-    "pd_tape_destroy", "pd_expect_diag", "pd_bench_hpsi", "pd_bench_dp5_steps",
+    "pd_tape_destroy", "pd_expect_diag", "pd_sharded_accumulate", "pd_bench_hpsi", "pd_bench_dp5_steps",
     "pd_plan_launch_count", "pd_is_cuda",
 )
 
@@ -85,6 +85,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.pd_tape_records.argtypes = [vp, C.POINTER(pd_step_record), i64]
     lib.pd_tape_destroy.argtypes = [vp]
     lib.pd_expect_diag.argtypes = [vp, vp, vp, i32, vp, pdbl]
+    lib.pd_sharded_accumulate.argtypes = [vp, vp, vp, vp, dbl, i32, C.POINTER(vp), pdbl]
     lib.pd_bench_hpsi.argtypes = [vp, vp, dbl, i32, vp, vp, pdbl]
     lib.pd_bench_dp5_steps.argtypes = [vp, vp, dbl, dbl, i32, vp, pdbl]
     lib.pd_plan_launch_count.argtypes = [vp]
@@ -391,6 +392,26 @@ class Plan:
         _check(lib().pd_expect_diag(self._ptr, _stream(self.device), _dptr(states), n_t, _dptr(obs),
                                     _hdbl(out)))
         return torch.view_as_complex(out)
+
+    def sharded_accumulate(self, out: torch.Tensor, psi: torch.Tensor, shift: float,
+                           peer_ptrs: Sequence[int], coefs: Sequence[complex]) -> None:
+        """``out += shift*psi + sum_k coefs[k] * slice_at(peer_ptrs[k])`` (in place).
+
+        ``peer_ptrs`` are raw device addresses of the partner ranks' slices (peer-mapped memory
+        from ``torch.distributed._symmetric_memory``, or local tensors' ``data_ptr()``)."""
+        if not out.is_contiguous():
+            raise ValueError("out must be contiguous (it is updated in place)")
+        out = self._vec(out, "out")
+        psi = self._vec(psi, "psi")
+        k = len(peer_ptrs)
+        if k != len(coefs):
+            raise ValueError("one coefficient per peer slice")
+        ptrs = (C.c_void_p * max(k, 1))(*[C.c_void_p(int(a)) for a in peer_ptrs])
+        cf = (C.c_double * max(2 * k, 1))()
+        for i, c in enumerate(coefs):
+            cf[2 * i], cf[2 * i + 1] = complex(c).real, complex(c).imag
+        _check(lib().pd_sharded_accumulate(self._ptr, _stream(self.device), _dptr(out), _dptr(psi),
+                                           float(shift), k, ptrs, cf))
 
     def bench_hpsi(self, t: float, psi: torch.Tensor, reps: int) -> float:
         """Average device ms of one H(t)·psi (CUDA events on the current stream)."""

@@ -207,6 +207,18 @@ int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t
     p->eng.expect_diag((const pd::cplx*)states_dev, n_t, obs_dev, out_host, stream);
   });
 }
+int pd_sharded_accumulate(pd_plan* p, void* stream, void* out_dev, const void* psi_dev, double shift,
+                          int32_t n_peers, const void* const* peer_slices,
+                          const double* coef_host) {
+  return guarded([&] {
+    need(p && out_dev && psi_dev && n_peers >= 0 && n_peers <= 16, "pd_sharded_accumulate: bad argument");
+    need(n_peers == 0 || (peer_slices && coef_host), "pd_sharded_accumulate: NULL peer list");
+    for (int k = 0; k < n_peers; ++k)
+      need(peer_slices[k] != nullptr, "pd_sharded_accumulate: NULL peer slice");
+    p->eng.sharded_accumulate((pd::cplx*)out_dev, (const pd::cplx*)psi_dev, shift, n_peers,
+                              (const pd::cplx* const*)peer_slices, (const pd::cplx*)coef_host, stream);
+  });
+}
 int pd_bench_hpsi(pd_plan* p, void* stream, double t, int32_t reps, const void* in_dev,
                   void* out_dev, double* ms_per_apply_host) {
   return guarded([&] {

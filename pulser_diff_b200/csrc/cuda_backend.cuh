@@ -53,6 +53,10 @@ int launch_re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, 
 int launch_pair_reduce(const Geometry& g, double* d_pair, const double* d_wacc, cudaStream_t s);
 int launch_expect_diag(const Geometry& g, const cplx* states, int n_t, const double* obs, cplx* out,
                        double* scratch, cudaStream_t s);
+// sharded register (sharded_ket.cu): out += shift*psi + sum_k coef_k * peer_k, partner slices read
+// in place from peer memory
+int launch_sharded_accumulate(size_t n_amp, cplx* out, const cplx* psi, double shift, int n_peers,
+                              const cplx* const* peers, const cplx* coef, cudaStream_t s);
 // tiled family (tiled_ket.cu); returns 0 launches if the shape is not supported
 bool tiled_ket_supported(const Geometry& g);
 int launch_tiled_stage_ket(const Geometry& g, cplx* out, cplx* comb, int n_in,
@@ -298,6 +302,10 @@ class CudaBackend {
   int expect_diag(const Geometry& g, const cplx* states, int n_t, const double* obs, cplx* out,
                   double* scratch, void* s) {
     return launch_expect_diag(g, states, n_t, obs, out, scratch, st(s));
+  }
+  int sharded_accumulate(const Geometry& g, cplx* out, const cplx* psi, double shift, int n_peers,
+                         const cplx* const* peers, const cplx* coef, void* s) {
+    return launch_sharded_accumulate(g.dim * g.batch, out, psi, shift, n_peers, peers, coef, st(s));
   }
 
  private:

@@ -325,6 +325,13 @@ class Engine {
     bk.sync(stream);
   }
 
+  // ---- sharded register: flips of the qubits that index the rank -----------
+  // out += shift*psi + sum_k coef_k * peers[k]; peers[k] may be peer-mapped device memory.
+  void sharded_accumulate(cplx* out, const cplx* psi, double shift, int n_peers,
+                          const cplx* const* peers, const cplx* coef, void* stream) {
+    launches += bk.sharded_accumulate(geo, out, psi, shift, n_peers, peers, coef, stream);
+  }
+
  private:
   std::vector<std::pair<std::string, void*>> bufs_;
   std::vector<std::pair<std::string, size_t>> buf_sizes_;

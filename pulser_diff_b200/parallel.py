@@ -13,9 +13,13 @@ Two axes, exactly the two ``north_star`` names:
 
        local part   : the single-GPU kernels on the N-g local qubits, with the global qubits'
                       interaction folded into per-qubit detunings + one energy shift, and
-       global flips : one pairwise exchange of the local slice with rank ^ (1 << k) per global
-                      qubit (``torch.distributed`` P2P: NCCL over NVLink on GPUs, gloo in the
-                      CPU tests), posted BEFORE the local kernels so the transfer overlaps them.
+       global flips : the slice of rank ^ (1 << k) per global qubit.  On GPUs
+                      (``peer_memory=True``) every rank keeps its slice in a symmetric buffer the
+                      peers have mapped over NVLink, and ONE kernel (``pd_sharded_accumulate``)
+                      reads all partner slices in place while accumulating -- the transfer is
+                      the accumulation.  Otherwise (gloo in the CPU tests, or NCCL without peer
+                      mapping) one pairwise exchange per global qubit, posted BEFORE the local
+                      kernels so the transfer overlaps them.
 
    The reference has nothing to mirror here (single process, no collectives).
 """
@@ -86,11 +90,13 @@ class ShardedKet:
         dt, det_masks, det_values, amp_masks, amp_values: the term structure that crosses the
                   C ABI (same meaning as in :func:`pulser_diff_b200.ops.evolve`).
         device:   this rank's device.
+        peer_memory: read partner slices in place from NVLink peer memory (CUDA ranks of one
+                  node) instead of exchanging them through send/recv.
     """
 
     def __init__(self, n_qubits: int, pair_u: Tensor, dt: float, det_masks: Sequence[int],
                  det_values: Tensor, amp_masks: Sequence[int], amp_values: Tensor,
-                 device: torch.device, group=None) -> None:
+                 device: torch.device, group=None, peer_memory: bool = False) -> None:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -136,6 +142,22 @@ class ShardedKet:
         # energy shift from global-global interaction (static) -- detuning part is time dependent
         self.e_static = sum(float(u[p, q]) * self.r_glob[p] * self.r_glob[q]
                             for p in range(g) for q in range(p + 1, g))
+        self._sym = self._hdl = None
+        if peer_memory:
+            if self.device.type != "cuda":
+                raise ValueError("peer_memory needs CUDA ranks")
+            import torch.distributed._symmetric_memory as symm_mem
+            # float64 view of the complex slice: (re, im) pairs, the layout the kernels read
+            self._sym = symm_mem.empty((1, 2 << self.nl), dtype=torch.float64, device=self.device)
+            self._hdl = symm_mem.rendezvous(self._sym, group if group is not None else dist.group.WORLD)
+            self._peer_ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+
+    def state_buffer(self) -> Tensor:
+        """The peer-visible (1, 2^(N-g)) slice buffer.  A state kept here is read by the partner
+        ranks without the staging copy :meth:`hpsi` otherwise makes."""
+        if self._sym is None:
+            raise RuntimeError("state_buffer() needs peer_memory=True")
+        return torch.view_as_complex(self._sym.view(1, 1 << self.nl, 2))
 
     # -- scalar coefficients of the global qubits at time t (reference interpolation rule) -----
     def _interp(self, values: Tensor, t: float):
@@ -162,6 +184,8 @@ class ShardedKet:
     def hpsi(self, t: float, psi_local: Tensor) -> Tensor:
         """``(H(t) psi)`` restricted to this rank's slice.  ``psi_local``: (1, 2^(N-g))."""
         d, c = self._global_coefficients(t)
+        if self._hdl is not None:
+            return self._hpsi_peer(t, psi_local, d, c)
         # 1. post the pairwise exchanges (one per global qubit) before any local work
         recv = [torch.empty_like(psi_local) for _ in range(self.g)]
         reqs = []
@@ -184,6 +208,25 @@ class ShardedKet:
                 continue
             coef = c[q] if self.r_glob[q] == 0 else c[q].conjugate()
             out.add_(recv[q], alpha=coef)
+        return out
+
+    def _hpsi_peer(self, t: float, psi_local: Tensor, d, c) -> Tensor:
+        """Peer-memory variant: partner slices are read in place by one accumulation kernel."""
+        buf = self.state_buffer()
+        if psi_local.data_ptr() != buf.data_ptr():
+            buf.copy_(psi_local)
+        self._hdl.barrier(channel=0)                 # every slice published
+        ops.configure(self.plan, self._prog)
+        out = self.plan.hpsi(t, buf)
+        shift = self.e_static + sum(d[q] * self.r_glob[q] for q in range(self.g))
+        ptrs, coefs = [], []
+        for q in range(self.g):
+            if c[q] == 0:
+                continue
+            ptrs.append(self._peer_ptrs[self.rank ^ (1 << (self.g - 1 - q))])
+            coefs.append(c[q] if self.r_glob[q] == 0 else c[q].conjugate())
+        self.plan.sharded_accumulate(out, buf, shift, ptrs, coefs)
+        self._hdl.barrier(channel=1)                 # partners are done reading this slice
         return out
 
     def local_slice(self, full: Tensor) -> Tensor:

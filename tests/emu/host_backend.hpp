@@ -230,6 +230,19 @@ class HostBackend {
       }
     return 1;
   }
+  int sharded_accumulate(const Geometry& g, cplx* out, const cplx* psi, double shift, int n_peers,
+                         const cplx* const* peers, const cplx* coef, void*) {
+    size_t L = g.dim * g.batch;
+    for (size_t i = 0; i < L; ++i) {
+      double re = out[i].re + shift * psi[i].re, im = out[i].im + shift * psi[i].im;
+      for (int k = 0; k < n_peers; ++k) {
+        re += coef[k].re * peers[k][i].re - coef[k].im * peers[k][i].im;
+        im += coef[k].re * peers[k][i].im + coef[k].im * peers[k][i].re;
+      }
+      out[i] = cplx{re, im};
+    }
+    return 1;
+  }
   int expect_diag(const Geometry& g, const cplx* states, int n_t, const double* obs, cplx* out,
                   double*, void*) {
     size_t S = (size_t)1 << g.nq;

@@ -315,3 +315,27 @@ def test_parameter_set_batches(engine_device, n, batch):
         gu = torch.autograd.grad(loss_of(st_u), [dvu, avu, p0u])
         for a, b in zip(gu, gb):
             assert (a - b[u]).abs().max() < 1e-10 * max(1.0, a.abs().max().item())
+
+
+@pytest.mark.parametrize("n,batch,n_peers", [(3, 1, 0), (5, 1, 1), (11, 1, 3), (12, 2, 6)])
+def test_sharded_accumulate(engine_device, n, batch, n_peers):
+    """pd_sharded_accumulate: out += shift*psi + sum_k coef_k * slice_k, the kernel the sharded
+    register uses for the flips of the qubits that index the rank.  The slices
+    are addressed by raw device pointers (peer-mapped memory in the multi-GPU path; here plain
+    tensors of the same device).  Sizes cover the tail (2^3 < one thread chunk), more peers than
+    one launch takes (6 > 4) and a batch."""
+    from pulser_diff_b200 import _cabi
+    dev = engine_device
+    g = torch.Generator().manual_seed(11 + n)
+    plan = _cabi.Plan(n, batch, _cabi.PD_KET, dev)
+    rnd = lambda: torch.randn(batch, 2 ** n, dtype=torch.complex128, generator=g).to(dev)
+    out, psi = rnd(), rnd()
+    slices = [rnd() for _ in range(n_peers)]
+    coefs = [complex(0.3 * k - 0.5, 0.7 - 0.2 * k) for k in range(n_peers)]
+    want = out + 0.37 * psi
+    for c, s in zip(coefs, slices):
+        want = want + c * s
+    plan.sharded_accumulate(out, psi, 0.37, [s.data_ptr() for s in slices], coefs)
+    assert (out - want).abs().max().item() < 1e-13
+    with pytest.raises(ValueError):
+        plan.sharded_accumulate(out, psi, 0.0, [slices[0].data_ptr()] if slices else [0], [])
