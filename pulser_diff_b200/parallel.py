@@ -15,11 +15,13 @@ Two axes, exactly the two ``north_star`` names:
                       interaction folded into per-qubit detunings + one energy shift, and
        global flips : the slice of rank ^ (1 << k) per global qubit.  On GPUs
                       (``peer_memory=True``) every rank keeps its slice in a symmetric buffer the
-                      peers have mapped over NVLink, and ONE kernel (``pd_sharded_accumulate``)
-                      reads all partner slices in place while accumulating -- the transfer is
-                      the accumulation.  Otherwise (gloo in the CPU tests, or NCCL without peer
-                      mapping) one pairwise exchange per global qubit, posted BEFORE the local
-                      kernels so the transfer overlaps them.
+                      peers have mapped over NVLink.  The copy engines pull the partner slices
+                      on a second stream while the local kernels (HBM-bound, all SMs) run, then
+                      ONE kernel (``pd_sharded_accumulate``) folds every flip into the result.
+                      ``peer_memory="read"`` skips the local copies: the same kernel reads the
+                      partner slices in place over NVLink (no receive buffers; measured slower,
+                      profiles/r01_multi_gpu.md).  Otherwise (gloo in the CPU tests) one pairwise
+                      send/recv per global qubit, posted before the local kernels.
 
    The reference has nothing to mirror here (single process, no collectives).
 """
@@ -90,13 +92,14 @@ class ShardedKet:
         dt, det_masks, det_values, amp_masks, amp_values: the term structure that crosses the
                   C ABI (same meaning as in :func:`pulser_diff_b200.ops.evolve`).
         device:   this rank's device.
-        peer_memory: read partner slices in place from NVLink peer memory (CUDA ranks of one
-                  node) instead of exchanging them through send/recv.
+        peer_memory: ``True``/``"copy"``: partner slices come through NVLink peer memory (CUDA
+                  ranks of one node), pulled by the copy engines beside the local kernels;
+                  ``"read"``: read in place by the accumulation kernel; ``False``: send/recv.
     """
 
     def __init__(self, n_qubits: int, pair_u: Tensor, dt: float, det_masks: Sequence[int],
                  det_values: Tensor, amp_masks: Sequence[int], amp_values: Tensor,
-                 device: torch.device, group=None, peer_memory: bool = False) -> None:
+                 device: torch.device, group=None, peer_memory: bool | str = False) -> None:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -142,7 +145,8 @@ class ShardedKet:
         # energy shift from global-global interaction (static) -- detuning part is time dependent
         self.e_static = sum(float(u[p, q]) * self.r_glob[p] * self.r_glob[q]
                             for p in range(g) for q in range(p + 1, g))
-        self._sym = self._hdl = None
+        self._sym = self._hdl = self._side = None
+        self._mode = "read" if peer_memory == "read" else "copy"
         if peer_memory:
             if self.device.type != "cuda":
                 raise ValueError("peer_memory needs CUDA ranks")
@@ -211,20 +215,35 @@ class ShardedKet:
         return out
 
     def _hpsi_peer(self, t: float, psi_local: Tensor, d, c) -> Tensor:
-        """Peer-memory variant: partner slices are read in place by one accumulation kernel."""
+        """Peer-memory variants.  "read": one kernel accumulates the partner slices in place over
+        NVLink.  "copy": the copy engines pull the partner slices into local buffers on a second
+        stream while the local kernels run; the same kernel then accumulates them from HBM."""
         buf = self.state_buffer()
         if psi_local.data_ptr() != buf.data_ptr():
             buf.copy_(psi_local)
         self._hdl.barrier(channel=0)                 # every slice published
+        shift = self.e_static + sum(d[q] * self.r_glob[q] for q in range(self.g))
+        qs = [q for q in range(self.g) if c[q] != 0]
+        coefs = [c[q] if self.r_glob[q] == 0 else c[q].conjugate() for q in qs]
+        peers = [self.rank ^ (1 << (self.g - 1 - q)) for q in qs]
+        if self._mode == "copy":
+            main = torch.cuda.current_stream(self.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(self.device)
+                self._recv = [torch.empty_like(self._sym) for _ in range(self.g)]
+                self._peer_bufs = [self._hdl.get_buffer(r, self._sym.shape, self._sym.dtype)
+                                   for r in range(self.world)]
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                for k, r in enumerate(peers):
+                    self._recv[k].copy_(self._peer_bufs[r])
+            ptrs = [self._recv[k].data_ptr() for k in range(len(peers))]
+        else:
+            ptrs = [self._peer_ptrs[r] for r in peers]
         ops.configure(self.plan, self._prog)
         out = self.plan.hpsi(t, buf)
-        shift = self.e_static + sum(d[q] * self.r_glob[q] for q in range(self.g))
-        ptrs, coefs = [], []
-        for q in range(self.g):
-            if c[q] == 0:
-                continue
-            ptrs.append(self._peer_ptrs[self.rank ^ (1 << (self.g - 1 - q))])
-            coefs.append(c[q] if self.r_glob[q] == 0 else c[q].conjugate())
+        if self._mode == "copy":
+            main.wait_stream(self._side)
         self.plan.sharded_accumulate(out, buf, shift, ptrs, coefs)
         self._hdl.barrier(channel=1)                 # partners are done reading this slice
         return out

@@ -73,7 +73,7 @@ def timed(fn, reps=5):
 ms_local = timed(lambda: sk2.plan.hpsi(0.01, loc))
 # peer-memory variant: state kept in the peer-visible buffer, partner slices read in place
 sk3 = parallel.ShardedKet(n2, pr2["pair_u"], pr2["dt"], pr2["det_masks"], pr2["det_values"],
-                          pr2["amp_masks"], pr2["amp_values"], dev, peer_memory=True)
+                          pr2["amp_masks"], pr2["amp_values"], dev, peer_memory=os.environ.get("PD_PEER_MODE", "read"))
 sbuf = sk3.state_buffer(); sbuf.copy_(loc)
 ms_peer = timed(lambda: sk3.hpsi(0.01, sbuf))
 ms_peer_staged = timed(lambda: sk3.hpsi(0.01, loc))
