@@ -179,6 +179,19 @@ int pd_tape_destroy(pd_tape* t);
 int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t,
                    const double* obs_dev, double* out_host /* complex [n_t] */);
 
+/* ---- reverse mode of ONE generator application (the autograd node under `H_t(t) @ psi`,
+ * reference hamiltonian.py:526-546 recorded on torch's tape; derivative.py:40, 76) ------------ */
+/* For k = pd_rhs(t, state) and a cotangent cot on k (torch convention dL/dRe + i dL/dIm):
+ *   grad_state_dev [batch*dim] (nullable)  = G(t)^dagger cot,
+ *   grad_det_host [n_det*n_samples], grad_amp_host [n_amp*n_samples*2] (nullable): the gradient
+ *     w.r.t. the coefficient samples is ADDED (interpolation weights of the reference rule),
+ *   grad_pair_host [N*N] (nullable): overwritten with dL/dU_ij (upper triangle),
+ *   grad_t_host (nullable): dL/dt through the interpolation.
+ * H(t) psi = i * pd_rhs(t, psi) on ket plans, so the VJP of pd_hpsi is this call with cot' = -i cot. */
+int pd_rhs_vjp(pd_plan* p, void* stream, double t, const void* state_dev, const void* cot_dev,
+               void* grad_state_dev, double* grad_det_host, double* grad_amp_host,
+               double* grad_pair_host, double* grad_t_host);
+
 /* ---- sharded register: flips of the qubits that index the GPU (the reference is
  * single-process, SURVEY.md 5.8, so there is no reference site to cite) ----------------------- */
 /* out[i] += shift * psi[i] + sum_k coef_k * peer_slices[k][i]  over the plan's 2^N amplitudes

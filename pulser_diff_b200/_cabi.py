@@ -45,7 +45,7 @@ class pd_step_record(C.Structure):
 EXPORTS = (
     "pd_abi_version", "pd_last_error", "pd_options_default", "pd_plan_create", "pd_plan_destroy",
     "pd_plan_set_interaction", "pd_plan_set_terms", "pd_plan_set_collapse", "pd_plan_set_path",
-    "pd_hpsi", "pd_rhs",
+    "pd_hpsi", "pd_rhs", "pd_rhs_vjp",
     "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
     "pd_evolve_forward_units", "pd_evolve_backward_units", "pd_tape_unit_steps",
     "pd_tape_destroy", "pd_expect_diag", "pd_sharded_accumulate", "pd_bench_hpsi", "pd_bench_dp5_steps",
@@ -85,6 +85,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.pd_tape_records.argtypes = [vp, C.POINTER(pd_step_record), i64]
     lib.pd_tape_destroy.argtypes = [vp]
     lib.pd_expect_diag.argtypes = [vp, vp, vp, i32, vp, pdbl]
+    lib.pd_rhs_vjp.argtypes = [vp, vp, dbl, vp, vp, vp, pdbl, pdbl, pdbl, pdbl]
     lib.pd_sharded_accumulate.argtypes = [vp, vp, vp, vp, dbl, i32, C.POINTER(vp), pdbl]
     lib.pd_bench_hpsi.argtypes = [vp, vp, dbl, i32, vp, vp, pdbl]
     lib.pd_bench_dp5_steps.argtypes = [vp, vp, dbl, dbl, i32, vp, pdbl]
@@ -283,6 +284,23 @@ class Plan:
         fn = lib().pd_rhs if rhs else lib().pd_hpsi
         _check(fn(self._ptr, _stream(self.device), float(t), _dptr(psi), _dptr(out)))
         return out
+
+    def rhs_vjp(self, t: float, state: torch.Tensor, cot: torch.Tensor, want_state: bool = True,
+                want_det: bool = True, want_amp: bool = True, want_pair: bool = False):
+        """Reverse mode of ``k = rhs(t, state)``: returns ``(grad_state, g_det, g_amp, g_pair,
+        g_t)`` for the cotangent ``cot`` on ``k`` (entries not asked for are None)."""
+        state = self._vec(state, "state")
+        cot = self._vec(cot, "cot")
+        g_state = torch.empty_like(state) if want_state else None
+        g_det = torch.zeros((self.n_det, self.n_samples), dtype=torch.float64) if want_det and self.n_det else None
+        g_amp = torch.zeros((self.n_amp, self.n_samples, 2), dtype=torch.float64) if want_amp and self.n_amp else None
+        g_pair = torch.zeros((self.n_qubits, self.n_qubits), dtype=torch.float64) if want_pair else None
+        g_t = C.c_double(0.0)
+        _check(lib().pd_rhs_vjp(self._ptr, _stream(self.device), float(t), _dptr(state), _dptr(cot),
+                                _dptr(g_state), _hdbl(g_det), _hdbl(g_amp), _hdbl(g_pair), C.byref(g_t)))
+        if g_amp is not None:
+            g_amp = torch.view_as_complex(g_amp)
+        return g_state, g_det, g_amp, g_pair, float(g_t.value)
 
     def evolve_forward(self, solver: int, opt: Options, state0: torch.Tensor, tsave: torch.Tensor,
                        want_tape: bool) -> tuple[torch.Tensor, Optional[Tape]]:

@@ -207,6 +207,17 @@ int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t
     p->eng.expect_diag((const pd::cplx*)states_dev, n_t, obs_dev, out_host, stream);
   });
 }
+int pd_rhs_vjp(pd_plan* p, void* stream, double t, const void* state_dev, const void* cot_dev,
+               void* grad_state_dev, double* grad_det_host, double* grad_amp_host,
+               double* grad_pair_host, double* grad_t_host) {
+  return guarded([&] {
+    need(p && state_dev && cot_dev, "pd_rhs_vjp: NULL argument");
+    double tb = p->eng.rhs_vjp(t, (const pd::cplx*)state_dev, (const pd::cplx*)cot_dev,
+                               (pd::cplx*)grad_state_dev, grad_det_host, grad_amp_host,
+                               grad_pair_host, stream);
+    if (grad_t_host) *grad_t_host = tb;
+  });
+}
 int pd_sharded_accumulate(pd_plan* p, void* stream, void* out_dev, const void* psi_dev, double shift,
                           int32_t n_peers, const void* const* peer_slices,
                           const double* coef_host) {

@@ -325,6 +325,36 @@ class Engine {
     bk.sync(stream);
   }
 
+  // ---- vector-Jacobian product of ONE generator application ---------------------------------
+  // k = G(t) y with cotangent kbar:  grad_y = G(t)^dagger kbar; the coefficient-sample gradients
+  // are ADDED into g_det / g_amp, g_pair is overwritten; returns dL/dt.  Same reductions as one
+  // stage of the DP5 adjoint (adjoint_step), exposed so host-side integrators (the sharded
+  // register, user-written steppers) are differentiable too.
+  double rhs_vjp(double t, const cplx* y, const cplx* kbar, cplx* grad_y, double* g_det,
+                 double* g_amp, double* g_pair, void* stream) {
+    if (grad_y) apply(grad_y, kbar, t, 1, stream);
+    int cs = corr_stride();
+    cplx* d_corr = (cplx*)buf("corr", sizeof(cplx) * (size_t)cs);
+    double* d_wacc = nullptr;
+    if (g_pair) {
+      d_wacc = (double*)buf("wacc", sizeof(double) * ((size_t)1 << geo.nq));
+      bk.zero(d_wacc, sizeof(double) * ((size_t)1 << geo.nq), stream);
+    }
+    const cplx* yi[1] = {y};
+    double yw[1] = {1.0};
+    launches += bk.corr_combo(geo, d_corr, d_wacc, 1.0, kbar, 1, yi, yw, vbuf("ystage"),
+                              reduce_scratch(), stream);
+    std::vector<cplx> h_corr(cs);
+    bk.d2h(h_corr.data(), d_corr, sizeof(cplx) * (size_t)cs, stream);
+    if (g_pair) {
+      double* d_pair = (double*)buf("pair_out", sizeof(double) * (size_t)prog.nq * prog.nq);
+      launches += bk.pair_reduce(geo, d_pair, d_wacc, stream);
+      bk.d2h(g_pair, d_pair, sizeof(double) * (size_t)prog.nq * prog.nq, stream);
+    }
+    bk.sync(stream);
+    return distribute(t, h_corr.data(), g_det, g_amp);
+  }
+
   // ---- sharded register: flips of the qubits that index the rank -----------
   // out += shift*psi + sum_k coef_k * peers[k]; peers[k] may be peer-mapped device memory.
   void sharded_accumulate(cplx* out, const cplx* psi, double shift, int n_peers,

@@ -237,6 +237,44 @@ def _(psi, t, det_values, amp_values, pair_u, det_masks, amp_masks, dt):
     return torch.empty_like(psi)
 
 
+def _vjp_common(ctx, cot: Tensor, kind: int, collapse):
+    """Shared reverse mode of one generator application (C ABI pd_rhs_vjp)."""
+    state, det_values, amp_values, pair_u = ctx.saved_tensors
+    n = int(pair_u.shape[0])
+    plan = get_plan(n, int(state.shape[0]), kind, state.device)
+    configure(plan, _prog_from_args(n, kind, ctx.dt, ctx.det_masks, det_values, ctx.amp_masks,
+                                    amp_values, pair_u, collapse))
+    w_state, _, w_det, w_amp, w_pair = ctx.needs_input_grad[:5]
+    g_state, g_det, g_amp, g_pair, _ = plan.rhs_vjp(ctx.t, state, cot.to(torch.complex128).contiguous(),
+                                                    want_state=w_state, want_det=w_det, want_amp=w_amp,
+                                                    want_pair=w_pair)
+    if w_det:
+        g_det = (g_det if g_det is not None else torch.zeros(det_values.shape, dtype=torch.float64))
+        g_det = g_det.to(device=det_values.device, dtype=det_values.dtype)
+    if w_amp:
+        g_amp = (g_amp if g_amp is not None else torch.zeros(amp_values.shape, dtype=torch.complex128))
+        g_amp = g_amp.to(amp_values.device)
+        g_amp = g_amp.to(amp_values.dtype) if amp_values.dtype.is_complex else g_amp.real.to(amp_values.dtype)
+    if w_pair:
+        g_pair = g_pair.to(device=pair_u.device, dtype=pair_u.dtype)
+    return g_state, g_det, g_amp, g_pair
+
+
+def _hpsi_setup(ctx, inputs, output):
+    psi, t, det_values, amp_values, pair_u, det_masks, amp_masks, dt = inputs
+    ctx.save_for_backward(psi, det_values, amp_values, pair_u)
+    ctx.t, ctx.det_masks, ctx.amp_masks, ctx.dt = float(t), list(det_masks), list(amp_masks), float(dt)
+
+
+def _hpsi_backward(ctx, cot):
+    # H psi = i * (-i H psi): the cotangent on the right-hand side is -i * cot
+    g_state, g_det, g_amp, g_pair = _vjp_common(ctx, -1j * cot, PD_KET, None)
+    return g_state, None, g_det, g_amp, g_pair, None, None, None
+
+
+hpsi.register_autograd(_hpsi_backward, setup_context=_hpsi_setup)
+
+
 @torch.library.custom_op("pulser_diff_b200::rhs", mutates_args=())
 def rhs(state: Tensor, t: float, det_values: Tensor, amp_values: Tensor, pair_u: Tensor,
         collapse: Tensor, det_masks: List[int], amp_masks: List[int], dt: float, kind: int) -> Tensor:
@@ -251,6 +289,21 @@ def rhs(state: Tensor, t: float, det_values: Tensor, amp_values: Tensor, pair_u:
 @rhs.register_fake
 def _(state, t, det_values, amp_values, pair_u, collapse, det_masks, amp_masks, dt, kind):
     return torch.empty_like(state)
+
+
+def _rhs_setup(ctx, inputs, output):
+    state, t, det_values, amp_values, pair_u, collapse, det_masks, amp_masks, dt, kind = inputs
+    ctx.save_for_backward(state, det_values, amp_values, pair_u)
+    ctx.collapse, ctx.kind = collapse, int(kind)
+    ctx.t, ctx.det_masks, ctx.amp_masks, ctx.dt = float(t), list(det_masks), list(amp_masks), float(dt)
+
+
+def _rhs_backward(ctx, cot):
+    g_state, g_det, g_amp, g_pair = _vjp_common(ctx, cot, ctx.kind, ctx.collapse)
+    return g_state, None, g_det, g_amp, g_pair, None, None, None, None, None
+
+
+rhs.register_autograd(_rhs_backward, setup_context=_rhs_setup)
 
 
 @torch.library.custom_op("pulser_diff_b200::evolve_states", mutates_args=())

@@ -339,3 +339,55 @@ def test_sharded_accumulate(engine_device, n, batch, n_peers):
     assert (out - want).abs().max().item() < 1e-13
     with pytest.raises(ValueError):
         plan.sharded_accumulate(out, psi, 0.0, [slices[0].data_ptr()] if slices else [0], [])
+
+
+@pytest.mark.parametrize("kind", ["ket", "density"])
+def test_generator_vjp(engine_device, kind):
+    """Reverse mode of ONE generator application (C ABI pd_rhs_vjp behind the autograd formulas of
+    the custom ops hpsi / rhs): the node the reference gets from torch's tape under `H_t(t) @ psi`
+    (hamiltonian.py:526-546, derivative.py:40).  The generator is linear in the state, in every
+    coefficient sample and in U_ij, so central differences are exact up to rounding: tolerance
+    1e-9 relative (north_star asks 1e-8 on gradients)."""
+    dev = engine_device
+    n, ns, dt, t = 3, 9, 0.004, 0.0137
+    g = torch.Generator().manual_seed(5)
+    rnd = lambda *s: torch.randn(*s, dtype=torch.float64, generator=g)
+    dv, av = rnd(2, ns), torch.complex(rnd(2, ns), rnd(2, ns))
+    det_masks, amp_masks = [0b111, 0b010], [0b111, 0b100]
+    pu = torch.triu(rnd(n, n).abs() * 3, diagonal=1)
+    dens = kind == "density"
+    dim = 4 ** n if dens else 2 ** n
+    state = torch.complex(rnd(2 if not dens else 1, dim), rnd(2 if not dens else 1, dim)).to(dev)
+    w = torch.complex(rnd(*state.shape), rnd(*state.shape)).to(dev)
+    coll = torch.zeros(0, 2, 2, dtype=torch.complex128)
+    if dens:
+        z = torch.tensor([[1, 0], [0, -1]], dtype=torch.complex128)
+        lo = torch.tensor([[0, 0], [1, 0]], dtype=torch.complex128)
+        coll = torch.stack([0.6 * z, 0.4 * lo])
+
+    def f(state, dv, av, pu):
+        if dens:
+            out = torch.ops.pulser_diff_b200.rhs(state, t, dv, av, pu, coll, det_masks, amp_masks, dt, 1)
+        else:
+            out = torch.ops.pulser_diff_b200.hpsi(state, t, dv, av, pu, det_masks, amp_masks, dt)
+        return (w.conj() * out).real.sum() + (out.abs() ** 2).sum() * 0.1
+
+    leaves = [x.clone().requires_grad_(True) for x in (state, dv, av, pu)]
+    grads = torch.autograd.grad(f(*leaves), leaves)
+    eps = 1e-4   # f is quadratic in every argument: central differences have no truncation error
+    for idx, (x, gx) in enumerate(zip((state, dv, av, pu), grads)):
+        flat = x.reshape(-1)
+        picks = torch.randperm(flat.numel(), generator=g)[:6].tolist()
+        for i in picks:
+            if idx == 3 and not (i // n < i % n):
+                continue                      # only the upper triangle of U enters H
+            for unit in ((1.0, 1j) if x.is_complex() else (1.0,)):
+                xp, xm = flat.clone(), flat.clone()
+                xp[i] += eps * unit
+                xm[i] -= eps * unit
+                args_p = [a if k != idx else xp.reshape(x.shape) for k, a in enumerate((state, dv, av, pu))]
+                args_m = [a if k != idx else xm.reshape(x.shape) for k, a in enumerate((state, dv, av, pu))]
+                fd = (f(*args_p) - f(*args_m)).item() / (2 * eps)
+                got = gx.reshape(-1)[i]
+                got = (got.real if unit == 1.0 else got.imag).item() if x.is_complex() else got.item()
+                assert abs(got - fd) < 1e-9 * max(1.0, abs(fd)), (idx, i, unit, got, fd)
