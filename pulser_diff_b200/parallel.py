@@ -135,9 +135,11 @@ class ShardedKet:
                 extra_m.append(1 << j)
                 extra_v.append(torch.full((self.n_samples,), 0.5 * shift, dtype=torch.float64))
         keep = [k for k, m in enumerate(dm) if m]
+        self._keep_det, self._extra_qubits = keep, [m.bit_length() - 1 for m in extra_m]
         dm_all = [dm[k] for k in keep] + extra_m
         dv_all = torch.stack([dv[k] for k in keep] + extra_v) if dm_all else torch.zeros(0, self.n_samples)
         keep_a = [k for k, m in enumerate(am) if m]
+        self._keep_amp = keep_a
         am_all = [am[k] for k in keep_a]
         av_all = torch.stack([av[k] for k in keep_a]) if am_all else torch.zeros(0, self.n_samples, dtype=C128)
         self._prog = ops.make_program(self.nl, _cabi.PD_KET, self.dt, dm_all, dv_all, am_all, av_all,
@@ -185,11 +187,14 @@ class ShardedKet:
                     c[q] += val
         return d, c
 
-    def hpsi(self, t: float, psi_local: Tensor) -> Tensor:
-        """``(H(t) psi)`` restricted to this rank's slice.  ``psi_local``: (1, 2^(N-g))."""
+    def hpsi(self, t: float, psi_local: Tensor, keep_partners: bool = False):
+        """``(H(t) psi)`` restricted to this rank's slice.  ``psi_local``: (1, 2^(N-g)).
+
+        ``keep_partners``: also return the partner slices (one per global qubit, valid until the
+        next call) -- the adjoint sweep takes its drive correlations from them."""
         d, c = self._global_coefficients(t)
         if self._hdl is not None:
-            return self._hpsi_peer(t, psi_local, d, c)
+            return self._hpsi_peer(t, psi_local, d, c, keep_partners)
         # 1. post the pairwise exchanges (one per global qubit) before any local work
         recv = [torch.empty_like(psi_local) for _ in range(self.g)]
         reqs = []
@@ -202,19 +207,21 @@ class ShardedKet:
         ops.configure(self.plan, self._prog)
         out = self.plan.hpsi(t, psi_local)
         shift = self.e_static + sum(d[q] * self.r_glob[q] for q in range(self.g))
-        if shift != 0.0:
-            out.add_(psi_local, alpha=shift)
         # 3. global flips: this rank's bit for qubit q is 1 (ground) -> coefficient c, else conj(c)
         for r in reqs:
             r.wait()
-        for q in range(self.g):
-            if c[q] == 0:
-                continue
-            coef = c[q] if self.r_glob[q] == 0 else c[q].conjugate()
-            out.add_(recv[q], alpha=coef)
-        return out
+        coefs = [c[q] if self.r_glob[q] == 0 else c[q].conjugate() for q in range(self.g)]
+        if psi_local.device.type == "cuda":
+            self.plan.sharded_accumulate(out, psi_local, shift, [r.data_ptr() for r in recv], coefs)
+        else:
+            if shift != 0.0:
+                out.add_(psi_local, alpha=shift)
+            for q in range(self.g):
+                if coefs[q] != 0:
+                    out.add_(recv[q], alpha=coefs[q])
+        return (out, recv) if keep_partners else out
 
-    def _hpsi_peer(self, t: float, psi_local: Tensor, d, c) -> Tensor:
+    def _hpsi_peer(self, t: float, psi_local: Tensor, d, c, keep_partners: bool = False):
         """Peer-memory variants.  "read": one kernel accumulates the partner slices in place over
         NVLink.  "copy": the copy engines pull the partner slices into local buffers on a second
         stream while the local kernels run; the same kernel then accumulates them from HBM."""
@@ -223,10 +230,11 @@ class ShardedKet:
             buf.copy_(psi_local)
         self._hdl.barrier(channel=0)                 # every slice published
         shift = self.e_static + sum(d[q] * self.r_glob[q] for q in range(self.g))
-        qs = [q for q in range(self.g) if c[q] != 0]
+        qs = [q for q in range(self.g) if c[q] != 0 or keep_partners]
         coefs = [c[q] if self.r_glob[q] == 0 else c[q].conjugate() for q in qs]
         peers = [self.rank ^ (1 << (self.g - 1 - q)) for q in qs]
-        if self._mode == "copy":
+        copy = self._mode == "copy" or keep_partners
+        if copy:
             main = torch.cuda.current_stream(self.device)
             if self._side is None:
                 self._side = torch.cuda.Stream(self.device)
@@ -242,13 +250,226 @@ class ShardedKet:
             ptrs = [self._peer_ptrs[r] for r in peers]
         ops.configure(self.plan, self._prog)
         out = self.plan.hpsi(t, buf)
-        if self._mode == "copy":
+        if copy:
             main.wait_stream(self._side)
         self.plan.sharded_accumulate(out, buf, shift, ptrs, coefs)
         self._hdl.barrier(channel=1)                 # partners are done reading this slice
+        if keep_partners:
+            n_loc = 1 << self.nl
+            return out, [torch.view_as_complex(self._recv[k].view(1, n_loc, 2)) for k in range(self.g)]
         return out
 
     def local_slice(self, full: Tensor) -> Tensor:
         """This rank's (1, 2^(N-g)) slice of a full (1, 2^N) vector (tests)."""
         n_loc = 1 << self.nl
         return full[:, self.rank * n_loc:(self.rank + 1) * n_loc].contiguous()
+
+    # -- DP5 evolution of the sharded register (configs[4]: full pulse sequence + gradient) ------
+    # Same integrator, controller and discrete adjoint as the single-GPU engine
+    # (csrc/engine.hpp forward_dp5 / adjoint_step; reference call backend.py:488-494), driven
+    # from the host because every H.psi is one exchange step; the error norm is the only
+    # reduction on the forward path (one scalar all-reduce per attempted step).
+    def rhs(self, t: float, psi_local: Tensor) -> Tensor:
+        return self.hpsi(t, psi_local).mul_(-1j)
+
+    def _sum(self, x: float) -> float:
+        v = torch.tensor([x], dtype=torch.float64, device=self.device)
+        dist.all_reduce(v, group=self.group)
+        return float(v.item())
+
+    def _scaled_norm(self, x: Tensor, ref_abs: Tensor, atol: float, rtol: float) -> float:
+        loc = ((x.abs() / (atol + rtol * ref_abs)) ** 2).sum().item()
+        return math.sqrt(self._sum(loc) / float(1 << self.n))
+
+    def _stage_input(self, y: Tensor, k: list, i: int, h: float) -> Tensor:
+        Y = y.clone()
+        for j in range(i):
+            if _BETA[i - 1][j] != 0.0:
+                Y.add_(k[j], alpha=h * _BETA[i - 1][j])
+        return Y
+
+    def _dp5_step(self, t: float, h: float, y: Tensor, k0: Tensor):
+        """k[0..6], y_new of one step (stage 7's input is y_new: FSAL)."""
+        k = [k0]
+        y_new = None
+        for i in range(1, 7):
+            Y = self._stage_input(y, k, i, h)
+            k.append(self.rhs(t + h * _ALPHA[i - 1], Y))
+            if i == 6:
+                y_new = Y
+        return k, y_new
+
+    def evolve(self, psi0_local: Tensor, tsave: Sequence[float], atol: float = 1e-8, rtol: float = 1e-6,
+               safety_factor: float = 0.9, min_factor: float = 0.2, max_factor: float = 5.0,
+               max_steps: int = 100000, replay: Optional[Sequence[tuple]] = None):
+        """Adaptive DP5 from ``psi0_local`` over ``tsave``.  Returns ``(states, steps)``:
+        ``states`` (n_t, 1, 2^(N-g)) = this rank's slices at the save times, ``steps`` = the
+        accepted steps ``(t, dt, interval, clipped)`` (identical on every rank; the tape of
+        :meth:`evolve_backward`).  ``replay``: run exactly these steps instead of controlling."""
+        ts = [float(x) for x in tsave]
+        y = psi0_local.detach().clone()
+        t = ts[0]
+        k0 = self.rhs(t, y)
+        steps, states = [], []
+        if replay is None:
+            d0 = self._scaled_norm(y, y.abs(), atol, rtol)
+            d1 = self._scaled_norm(k0, y.abs(), atol, rtol)
+            h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+            f1 = self.rhs(t + h0, y + h0 * k0)
+            d2 = self._scaled_norm(f1 - k0, y.abs(), atol, rtol) / h0
+            h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / 6.0)
+            dt = min(100 * h0, h1)
+        else:
+            dt, replay = 0.0, list(replay)
+        error, pos = 1.0, 0
+        ew = [_B5[j] - _B4[j] for j in range(7)]
+        for kk, t_next in enumerate(ts):
+            cache_dt, cache_err, n_att = dt, error, 0
+            while t < t_next:
+                if replay is None:
+                    if error == 0.0:
+                        dt = dt * max_factor
+                    else:
+                        fac = safety_factor * error ** (-0.2)
+                        dt = dt * (max(1.0, min(max_factor, fac)) if error <= 1.0
+                                   else min(0.9, max(min_factor, fac)))
+                    clipped = t + dt >= t_next
+                else:
+                    _, dt, _, clipped = replay[pos]
+                    pos += 1
+                if clipped:
+                    cache_dt, cache_err, dt = dt, error, t_next - t
+                k, y_new = self._dp5_step(t, dt, y, k0)
+                err = torch.zeros_like(y)
+                for j in range(7):
+                    if ew[j] != 0.0:
+                        err.add_(k[j], alpha=dt * ew[j])
+                error = self._scaled_norm(err, torch.maximum(y.abs(), y_new.abs()), atol, rtol)
+                if error != error:
+                    raise RuntimeError("non-finite error norm in DP5 step")
+                if replay is not None or error <= 1.0:
+                    steps.append((t, dt, kk, bool(clipped)))
+                    t = t_next if clipped else t + dt
+                    y, k0 = y_new, k[6]
+                n_att += 1
+                if n_att >= max_steps:
+                    raise RuntimeError("max_steps reached")
+            dt, error = cache_dt, cache_err
+            states.append(y.clone())
+        return torch.stack(states), steps
+
+    def _vjp(self, t: float, Y: Tensor, kbar: Tensor, acc: dict) -> Tensor:
+        """Reverse mode of k = -i H(t) Y on the sharded register: returns this rank's slice of
+        ``(-i H)^dagger kbar`` and adds this rank's share of the parameter gradients to ``acc``
+        (summed over ranks by the caller)."""
+        g, n = self.g, self.n_samples
+        hk, partners = self.hpsi(t, kbar, keep_partners=True)
+        i1 = max(int(min(math.floor(t / self.dt), n - 2)), 0)
+        i2 = min(i1 + 1, n - 2)
+        x = (t - i1 * self.dt) / self.dt
+        # local qubits: the engine's own correlation kernels (C ABI pd_rhs_vjp)
+        ops.configure(self.plan, self._prog)
+        _, gl_det, gl_amp, gl_pair, _ = self.plan.rhs_vjp(t, Y, kbar, want_state=False, want_pair=True)
+        nk = len(self._keep_det)
+        if gl_det is None:
+            gl_det = torch.zeros(nk + len(self._extra_qubits), n, dtype=torch.float64)
+        if gl_amp is None:
+            gl_amp = torch.zeros(len(self._keep_amp), n, dtype=C128)
+        for j, kidx in enumerate(self._keep_det):
+            acc["det"][kidx] += gl_det[j]
+        for j, (q_loc) in enumerate(self._extra_qubits):      # static detuning = interaction with
+            tot = float(gl_det[nk + j].sum())                  # the occupied global qubits
+            for q in range(g):
+                acc["pair"][q, g + q_loc] += 0.5 * self.r_glob[q] * tot
+        for j, kidx in enumerate(self._keep_amp):
+            acc["amp"][kidx] += gl_amp[j]
+        acc["pair"][g:, g:] += gl_pair
+        # energy shift of the global qubits: k has -i * shift * Y
+        g_shift = torch.vdot(kbar.reshape(-1), Y.reshape(-1)).imag.item()
+        for p_ in range(g):
+            for q in range(p_ + 1, g):
+                acc["pair"][p_, q] += self.r_glob[p_] * self.r_glob[q] * g_shift
+        for kidx, m in enumerate(self.det_masks):
+            w = 2.0 * g_shift * sum(self.r_glob[q] for q in range(g) if m >> q & 1)
+            if w != 0.0:
+                acc["det"][kidx, i1] += w * (1.0 - x)
+                acc["det"][kidx, i2] += w * x
+        # flips of the global qubits: with the partner's kbar slice in hand this rank evaluates
+        # the PARTNER's drive correlation (its k has -i * coef * Y_mine); the sum over ranks is
+        # what the caller reduces, so every contribution is counted once.
+        for q in range(g):
+            zb = -1j * torch.vdot(partners[q].reshape(-1), Y.reshape(-1)).item()
+            gc = zb.conjugate() if (1 - self.r_glob[q]) == 0 else zb
+            for kidx, m in enumerate(self.amp_masks):
+                if m >> q & 1:
+                    acc["amp"][kidx, i1] += gc * (1.0 - x)
+                    acc["amp"][kidx, i2] += gc * x
+        return hk.mul_(1j)
+
+    def evolve_backward(self, states: Tensor, grad_states: Tensor, steps: Sequence[tuple]) -> dict:
+        """Discrete adjoint of :meth:`evolve` (the recorded step sequence, recomputed stage by
+        stage as in csrc/engine.hpp adjoint_step).  ``grad_states``: cotangents on this rank's
+        ``states``.  Returns ``{"det", "amp", "pair", "state0"}``: gradients w.r.t. the
+        coefficient samples and ``pair_u`` (complete, identical on every rank) and this rank's
+        slice of the gradient w.r.t. the initial state."""
+        acc = {"det": torch.zeros_like(self.det_values), "amp": torch.zeros_like(self.amp_values),
+               "pair": torch.zeros(self.n, self.n, dtype=torch.float64)}
+        n_t = int(states.shape[0])
+        lam = grad_states[n_t - 1].detach().clone()
+        hi = len(steps)
+        for kk in range(n_t - 1, 0, -1):
+            lo = hi
+            while lo > 0 and steps[lo - 1][2] == kk:
+                lo -= 1
+            # step-start states of the interval, recomputed from the saved state
+            ys = [states[kk - 1]]
+            for (t, h, _, _) in steps[lo:hi - 1]:
+                k, _ = self._dp5_step(t, h, ys[-1], self.rhs(t, ys[-1]))
+                y1 = ys[-1].clone()
+                for j in range(6):
+                    if _B5[j] != 0.0:
+                        y1.add_(k[j], alpha=h * _B5[j])
+                ys.append(y1)
+            for s_idx in range(hi - 1, lo - 1, -1):
+                t, h, _, _ = steps[s_idx]
+                y_n = ys[s_idx - lo]
+                k, _ = self._dp5_step(t, h, y_n, self.rhs(t, y_n))
+                yb = [None] * 6
+                for i in range(5, -1, -1):
+                    kbar = torch.zeros_like(lam)
+                    if _B5[i] != 0.0:
+                        kbar.add_(lam, alpha=h * _B5[i])
+                    for j in range(i + 1, 6):
+                        if _BETA[j - 1][i] != 0.0:
+                            kbar.add_(yb[j], alpha=h * _BETA[j - 1][i])
+                    ts_i = t + h * (0.0 if i == 0 else _ALPHA[i - 1])
+                    yb[i] = self._vjp(ts_i, self._stage_input(y_n, k, i, h), kbar, acc)
+                for i in range(6):
+                    lam.add_(yb[i])
+            hi = lo
+            lam.add_(grad_states[kk - 1])
+        for key in ("det", "amp", "pair"):
+            v = acc[key].to(self.device)
+            if v.is_complex():
+                v = torch.view_as_real(v).contiguous()
+                dist.all_reduce(v, group=self.group)
+                acc[key] = torch.view_as_complex(v).cpu()
+            else:
+                dist.all_reduce(v, group=self.group)
+                acc[key] = v.cpu()
+        acc["state0"] = lam
+        return acc
+
+
+# Dormand-Prince 5(4) tableau (the one csrc/pd_common.hpp holds for the device paths)
+_ALPHA = [1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0]
+_BETA = [
+    [1 / 5],
+    [3 / 40, 9 / 40],
+    [44 / 45, -56 / 15, 32 / 9],
+    [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+    [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+    [35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+]
+_B5 = [35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0.0]
+_B4 = [5179 / 57600, 0.0, 7571 / 16695, 393 / 640, -92097 / 339200, 187 / 2100, 1 / 40]

@@ -88,3 +88,76 @@ def test_sharded_paths_gloo(world, emu_library, tmp_path):
         assert res["gather_err"] == 0.0
         seen += res["units"]
     assert sorted(seen) == list(range(7))
+
+
+def _evolve_worker(rank, world, port, n, out_dir):
+    """configs[4] on the CPU tier: sharded DP5 evolution + discrete adjoint vs the single-process
+    engine on the full register (same library, so the comparison isolates the sharding)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sys
+    sys.path.insert(0, ROOT)
+    from pulser_diff_b200 import _cabi, ops, parallel
+    _cabi.use_library(EMU)
+    dev = torch.device("cpu")
+    pr = _program(n, T=40)
+    gen = torch.Generator().manual_seed(9)
+    psi0 = torch.randn(1, 2 ** n, dtype=torch.complex128, generator=gen)
+    psi0 = psi0 / psi0.norm()
+    tsave = torch.tensor([0.0, 0.011, 0.03, 0.0525], dtype=torch.float64)
+    w = torch.rand(len(tsave), 1, 2 ** n, dtype=torch.float64, generator=gen)
+    v = torch.randn(len(tsave), 1, 2 ** n, dtype=torch.complex128, generator=gen)
+
+    def loss_of(st):
+        return (w * st.abs() ** 2).sum() + (v.conj() * st).real.sum()
+
+    # single-process run of the full register
+    leaves = [x.clone().requires_grad_(True) for x in (psi0, pr["det_values"], pr["amp_values"], pr["pair_u"])]
+    st_full = ops.evolve(leaves[0], tsave, leaves[1], leaves[2], leaves[3], n_qubits=n, kind=_cabi.PD_KET,
+                         dt=pr["dt"], det_masks=pr["det_masks"], amp_masks=pr["amp_masks"])
+    g_full = torch.autograd.grad(loss_of(st_full), leaves)
+    log = [r for r in ops.last_step_log(st_full) if r["accepted"]]
+
+    sk = parallel.ShardedKet(n, pr["pair_u"], pr["dt"], pr["det_masks"], pr["det_values"],
+                             pr["amp_masks"], pr["amp_values"], dev)
+    n_loc = 2 ** sk.nl
+    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    res = {}
+    # free-running controller: the same first steps (the all-reduced error norm differs from the
+    # engine's by rounding, which the controller amplifies until an accept/reject decision
+    # flips -- hence the shared-step protocol below for the tight comparison)
+    st_free, steps_free = sk.evolve(sk.local_slice(psi0), tsave.tolist())
+    res["n_steps"] = (len(steps_free), len(log))
+    res["dt_err"] = max(abs(a[1] - b["dt"]) / b["dt"] for a, b in zip(steps_free[:3], log[:3]))
+    res["free_err"] = (st_free - st_full.detach()[:, :, sl]).abs().max().item()
+    # shared-step protocol (SURVEY.md 7 H1) for the tight comparison of states and gradients
+    replay = [(r["t"], r["dt"], r["interval"], bool(r["clipped"])) for r in log]
+    st, steps = sk.evolve(sk.local_slice(psi0), tsave.tolist(), replay=replay)
+    res["state_err"] = (st - st_full.detach()[:, :, sl]).abs().max().item()
+    st_leaf = st.clone().requires_grad_(True)
+    # this rank's share of the loss: its slices only
+    l_loc = (w[:, :, sl] * st_leaf.abs() ** 2).sum() + (v[:, :, sl].conj() * st_leaf).real.sum()
+    (g_st,) = torch.autograd.grad(l_loc, st_leaf)
+    out = sk.evolve_backward(st, g_st, steps)
+    relerr = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+    res["g_det"] = relerr(out["det"], g_full[1])
+    res["g_amp"] = relerr(out["amp"], g_full[2])
+    res["g_pair"] = relerr(out["pair"], g_full[3])
+    res["g_psi0"] = relerr(out["state0"], g_full[0][:, sl])
+    torch.save(res, os.path.join(out_dir, f"e{rank}.pt"))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_sharded_evolution_and_gradient_gloo(world, emu_library, tmp_path):
+    """Sharded register, full pulse sequence + gradient (BASELINE configs[4]): states to 1e-10,
+    gradients to 1e-8 relative (north_star's tolerances) against the unsharded engine."""
+    n = 6
+    mp.spawn(_evolve_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(os.path.join(tmp_path, f"e{r}.pt"))
+        assert abs(res["n_steps"][0] - res["n_steps"][1]) <= 0.1 * res["n_steps"][1], res
+        assert res["dt_err"] < 1e-9 and res["free_err"] < 1e-3, res
+        assert res["state_err"] < 1e-12, res
+        for key in ("g_det", "g_amp", "g_pair", "g_psi0"):
+            assert res[key] < 1e-8, (key, res)
