@@ -192,6 +192,19 @@ int pd_rhs_vjp(pd_plan* p, void* stream, double t, const void* state_dev, const 
                void* grad_state_dev, double* grad_det_host, double* grad_amp_host,
                double* grad_pair_host, double* grad_t_host);
 
+/* ---- pieces of one DP5 step for a host-driven stepper (the sharded register, where every
+ * generator application contains an exchange step; upstream solver) ------ */
+/* out = sum_j w_j * ins[j]  (1 <= n_in <= 8; element-wise, so out may be one of the inputs) */
+int pd_lincomb(pd_plan* p, void* stream, void* out_dev, int32_t n_in, const void* const* ins_dev,
+               const double* w_host);
+/* sumsq_host[batch] = sum over this plan's amplitudes of
+ *   |sum_j ew[j] k[j]|^2 / (atol + rtol * max(|y0|, |y1|))^2          (j = 0..6)
+ * -- the local share of the DP5 error norm; the caller adds the shares of all ranks and takes
+ * sqrt(sum / 2^N).  k_dev[j] may be NULL where ew[j] == 0. */
+int pd_dp5_error_sumsq(pd_plan* p, void* stream, const void* const* k_dev, const double* ew_host,
+                       const void* y0_dev, const void* y1_dev, double atol, double rtol,
+                       double* sumsq_host);
+
 /* ---- sharded register: flips of the qubits that index the GPU (the reference is
  * single-process, SURVEY.md 5.8, so there is no reference site to cite) ----------------------- */
 /* out[i] += shift * psi[i] + sum_k coef_k * peer_slices[k][i]  over the plan's 2^N amplitudes

@@ -48,7 +48,7 @@ EXPORTS = (
     "pd_hpsi", "pd_rhs", "pd_rhs_vjp",
     "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
     "pd_evolve_forward_units", "pd_evolve_backward_units", "pd_tape_unit_steps",
-    "pd_tape_destroy", "pd_expect_diag", "pd_sharded_accumulate", "pd_bench_hpsi", "pd_bench_dp5_steps",
+    "pd_tape_destroy", "pd_expect_diag", "pd_sharded_accumulate", "pd_lincomb", "pd_dp5_error_sumsq", "pd_bench_hpsi", "pd_bench_dp5_steps",
     "pd_plan_launch_count", "pd_is_cuda",
 )
 
@@ -86,6 +86,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.pd_tape_destroy.argtypes = [vp]
     lib.pd_expect_diag.argtypes = [vp, vp, vp, i32, vp, pdbl]
     lib.pd_rhs_vjp.argtypes = [vp, vp, dbl, vp, vp, vp, pdbl, pdbl, pdbl, pdbl]
+    lib.pd_lincomb.argtypes = [vp, vp, vp, i32, C.POINTER(vp), pdbl]
+    lib.pd_dp5_error_sumsq.argtypes = [vp, vp, C.POINTER(vp), pdbl, vp, vp, dbl, dbl, pdbl]
     lib.pd_sharded_accumulate.argtypes = [vp, vp, vp, vp, dbl, i32, C.POINTER(vp), pdbl]
     lib.pd_bench_hpsi.argtypes = [vp, vp, dbl, i32, vp, vp, pdbl]
     lib.pd_bench_dp5_steps.argtypes = [vp, vp, dbl, dbl, i32, vp, pdbl]
@@ -410,6 +412,33 @@ class Plan:
         _check(lib().pd_expect_diag(self._ptr, _stream(self.device), _dptr(states), n_t, _dptr(obs),
                                     _hdbl(out)))
         return torch.view_as_complex(out)
+
+    def lincomb(self, out: torch.Tensor, ins: Sequence[torch.Tensor], w: Sequence[float]) -> torch.Tensor:
+        """``out = sum_j w[j] * ins[j]`` in one pass (at most 8 inputs)."""
+        if not out.is_contiguous():
+            raise ValueError("out must be contiguous (it is written in place)")
+        self._vec(out, "out")
+        ins = [self._vec(x, "input") for x in ins]
+        if len(ins) != len(w) or not 1 <= len(ins) <= 8:
+            raise ValueError("1..8 inputs, one weight each")
+        ptrs = (C.c_void_p * len(ins))(*[C.c_void_p(x.data_ptr()) for x in ins])
+        ws = (C.c_double * len(ins))(*[float(x) for x in w])
+        _check(lib().pd_lincomb(self._ptr, _stream(self.device), _dptr(out), len(ins), ptrs, ws))
+        return out
+
+    def dp5_error_sumsq(self, k: Sequence[Optional[torch.Tensor]], ew: Sequence[float], y0: torch.Tensor,
+                        y1: torch.Tensor, atol: float, rtol: float) -> torch.Tensor:
+        """Per-column local share of the DP5 error norm (see include/pulser_diff_b200.h)."""
+        if len(k) != 7 or len(ew) != 7:
+            raise ValueError("seven slopes and seven weights")
+        ks = [None if x is None else self._vec(x, "k") for x in k]
+        ptrs = (C.c_void_p * 7)(*[C.c_void_p(0 if x is None else x.data_ptr()) for x in ks])
+        ws = (C.c_double * 7)(*[float(x) for x in ew])
+        out = torch.zeros(self.batch, dtype=torch.float64)
+        _check(lib().pd_dp5_error_sumsq(self._ptr, _stream(self.device), ptrs, ws,
+                                        _dptr(self._vec(y0, "y0")), _dptr(self._vec(y1, "y1")),
+                                        float(atol), float(rtol), _hdbl(out)))
+        return out
 
     def sharded_accumulate(self, out: torch.Tensor, psi: torch.Tensor, shift: float,
                            peer_ptrs: Sequence[int], coefs: Sequence[complex]) -> None:

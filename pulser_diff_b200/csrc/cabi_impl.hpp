@@ -218,6 +218,27 @@ int pd_rhs_vjp(pd_plan* p, void* stream, double t, const void* state_dev, const 
     if (grad_t_host) *grad_t_host = tb;
   });
 }
+int pd_lincomb(pd_plan* p, void* stream, void* out_dev, int32_t n_in, const void* const* ins_dev,
+               const double* w_host) {
+  return guarded([&] {
+    need(p && out_dev && ins_dev && w_host && n_in >= 1 && n_in <= 8, "pd_lincomb: bad argument");
+    for (int j = 0; j < n_in; ++j) need(ins_dev[j] != nullptr, "pd_lincomb: NULL input");
+    p->eng.lincomb((pd::cplx*)out_dev, n_in, (const pd::cplx* const*)ins_dev, w_host, stream);
+  });
+}
+int pd_dp5_error_sumsq(pd_plan* p, void* stream, const void* const* k_dev, const double* ew_host,
+                       const void* y0_dev, const void* y1_dev, double atol, double rtol,
+                       double* sumsq_host) {
+  return guarded([&] {
+    need(p && k_dev && ew_host && y0_dev && y1_dev && sumsq_host, "pd_dp5_error_sumsq: NULL argument");
+    for (int j = 0; j < 7; ++j)
+      need(k_dev[j] != nullptr || ew_host[j] == 0.0, "pd_dp5_error_sumsq: NULL slope with a non-zero weight");
+    const pd::cplx* k[7];
+    for (int j = 0; j < 7; ++j) k[j] = k_dev[j] ? (const pd::cplx*)k_dev[j] : (const pd::cplx*)y0_dev;
+    p->eng.error_sumsq(k, ew_host, (const pd::cplx*)y0_dev, (const pd::cplx*)y1_dev, atol, rtol,
+                       sumsq_host, stream);
+  });
+}
 int pd_sharded_accumulate(pd_plan* p, void* stream, void* out_dev, const void* psi_dev, double shift,
                           int32_t n_peers, const void* const* peer_slices,
                           const double* coef_host) {

@@ -355,6 +355,20 @@ class Engine {
     return distribute(t, h_corr.data(), g_det, g_amp);
   }
 
+  // ---- building blocks of a host-driven DP5 step (the sharded register) --------------------
+  // out = sum_j w_j in_j (one pass)
+  void lincomb(cplx* out, int n_in, const cplx* const* ins, const double* w, void* stream) {
+    launches += bk.lincomb(geo, out, n_in, ins, w, stream);
+  }
+  // per-column sum over this plan's amplitudes of |sum_j ew_j k_j / (atol + rtol max(|y0|,|y1|))|^2
+  void error_sumsq(const cplx* const* k, const double* ew, const cplx* y0, const cplx* y1,
+                   double atol, double rtol, double* out_host, void* stream) {
+    double* d_err = (double*)buf("norm_out", sizeof(double) * geo.batch);
+    launches += bk.err_sumsq(geo, d_err, k, ew, y0, y1, atol, rtol, reduce_scratch(), stream);
+    bk.d2h(out_host, d_err, sizeof(double) * geo.batch, stream);
+    bk.sync(stream);
+  }
+
   // ---- sharded register: flips of the qubits that index the rank -----------
   // out += shift*psi + sum_k coef_k * peers[k]; peers[k] may be peer-mapped device memory.
   void sharded_accumulate(cplx* out, const cplx* psi, double shift, int n_peers,

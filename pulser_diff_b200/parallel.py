@@ -187,14 +187,15 @@ class ShardedKet:
                     c[q] += val
         return d, c
 
-    def hpsi(self, t: float, psi_local: Tensor, keep_partners: bool = False):
-        """``(H(t) psi)`` restricted to this rank's slice.  ``psi_local``: (1, 2^(N-g)).
+    def hpsi(self, t: float, psi_local: Tensor, keep_partners: bool = False, rhs: bool = False):
+        """``(H(t) psi)`` restricted to this rank's slice (``rhs``: ``-i H(t) psi``, the factor
+        folded into the kernels' coefficients).  ``psi_local``: (1, 2^(N-g)).
 
         ``keep_partners``: also return the partner slices (one per global qubit, valid until the
         next call) -- the adjoint sweep takes its drive correlations from them."""
         d, c = self._global_coefficients(t)
         if self._hdl is not None:
-            return self._hpsi_peer(t, psi_local, d, c, keep_partners)
+            return self._hpsi_peer(t, psi_local, d, c, keep_partners, rhs)
         # 1. post the pairwise exchanges (one per global qubit) before any local work
         recv = [torch.empty_like(psi_local) for _ in range(self.g)]
         reqs = []
@@ -205,23 +206,19 @@ class ShardedKet:
             reqs += dist.batch_isend_irecv(ops_)
         # 2. local qubits: the single-GPU kernels (overlaps the transfers)
         ops.configure(self.plan, self._prog)
-        out = self.plan.hpsi(t, psi_local)
+        out = self.plan.hpsi(t, psi_local, rhs=rhs)
         shift = self.e_static + sum(d[q] * self.r_glob[q] for q in range(self.g))
         # 3. global flips: this rank's bit for qubit q is 1 (ground) -> coefficient c, else conj(c)
         for r in reqs:
             r.wait()
-        coefs = [c[q] if self.r_glob[q] == 0 else c[q].conjugate() for q in range(self.g)]
-        if psi_local.device.type == "cuda":
-            self.plan.sharded_accumulate(out, psi_local, shift, [r.data_ptr() for r in recv], coefs)
-        else:
-            if shift != 0.0:
-                out.add_(psi_local, alpha=shift)
-            for q in range(self.g):
-                if coefs[q] != 0:
-                    out.add_(recv[q], alpha=coefs[q])
+        f = -1j if rhs else 1.0
+        coefs = [f * shift] + [f * (c[q] if self.r_glob[q] == 0 else c[q].conjugate()) for q in range(self.g)]
+        self.plan.sharded_accumulate(out, psi_local, 0.0, [psi_local.data_ptr()] + [r.data_ptr() for r in recv],
+                                     coefs)
         return (out, recv) if keep_partners else out
 
-    def _hpsi_peer(self, t: float, psi_local: Tensor, d, c, keep_partners: bool = False):
+    def _hpsi_peer(self, t: float, psi_local: Tensor, d, c, keep_partners: bool = False,
+                   rhs: bool = False):
         """Peer-memory variants.  "read": one kernel accumulates the partner slices in place over
         NVLink.  "copy": the copy engines pull the partner slices into local buffers on a second
         stream while the local kernels run; the same kernel then accumulates them from HBM."""
@@ -231,7 +228,8 @@ class ShardedKet:
         self._hdl.barrier(channel=0)                 # every slice published
         shift = self.e_static + sum(d[q] * self.r_glob[q] for q in range(self.g))
         qs = [q for q in range(self.g) if c[q] != 0 or keep_partners]
-        coefs = [c[q] if self.r_glob[q] == 0 else c[q].conjugate() for q in qs]
+        f = -1j if rhs else 1.0
+        coefs = [f * shift] + [f * (c[q] if self.r_glob[q] == 0 else c[q].conjugate()) for q in qs]
         peers = [self.rank ^ (1 << (self.g - 1 - q)) for q in qs]
         copy = self._mode == "copy" or keep_partners
         if copy:
@@ -249,10 +247,10 @@ class ShardedKet:
         else:
             ptrs = [self._peer_ptrs[r] for r in peers]
         ops.configure(self.plan, self._prog)
-        out = self.plan.hpsi(t, buf)
+        out = self.plan.hpsi(t, buf, rhs=rhs)
         if copy:
             main.wait_stream(self._side)
-        self.plan.sharded_accumulate(out, buf, shift, ptrs, coefs)
+        self.plan.sharded_accumulate(out, buf, 0.0, [buf.data_ptr()] + ptrs, coefs)
         self._hdl.barrier(channel=1)                 # partners are done reading this slice
         if keep_partners:
             n_loc = 1 << self.nl
@@ -270,7 +268,7 @@ class ShardedKet:
     # from the host because every H.psi is one exchange step; the error norm is the only
     # reduction on the forward path (one scalar all-reduce per attempted step).
     def rhs(self, t: float, psi_local: Tensor) -> Tensor:
-        return self.hpsi(t, psi_local).mul_(-1j)
+        return self.hpsi(t, psi_local, rhs=True)
 
     def _sum(self, x: float) -> float:
         v = torch.tensor([x], dtype=torch.float64, device=self.device)
@@ -281,19 +279,23 @@ class ShardedKet:
         loc = ((x.abs() / (atol + rtol * ref_abs)) ** 2).sum().item()
         return math.sqrt(self._sum(loc) / float(1 << self.n))
 
-    def _stage_input(self, y: Tensor, k: list, i: int, h: float) -> Tensor:
-        Y = y.clone()
+    def _stage_input(self, y: Tensor, k: list, i: int, h: float, publish: bool = False) -> Tensor:
+        """Y_i = y + h sum_j beta_ij k_j in one pass; ``publish``: written straight into the
+        peer-visible buffer (valid until the next generator application)."""
+        ins, w = [y], [1.0]
         for j in range(i):
             if _BETA[i - 1][j] != 0.0:
-                Y.add_(k[j], alpha=h * _BETA[i - 1][j])
-        return Y
+                ins.append(k[j])
+                w.append(h * _BETA[i - 1][j])
+        out = self.state_buffer() if (publish and self._hdl is not None) else torch.empty_like(y)
+        return self.plan.lincomb(out, ins, w)
 
     def _dp5_step(self, t: float, h: float, y: Tensor, k0: Tensor):
         """k[0..6], y_new of one step (stage 7's input is y_new: FSAL)."""
         k = [k0]
         y_new = None
         for i in range(1, 7):
-            Y = self._stage_input(y, k, i, h)
+            Y = self._stage_input(y, k, i, h, publish=i < 6)
             k.append(self.rhs(t + h * _ALPHA[i - 1], Y))
             if i == 6:
                 y_new = Y
@@ -340,11 +342,8 @@ class ShardedKet:
                 if clipped:
                     cache_dt, cache_err, dt = dt, error, t_next - t
                 k, y_new = self._dp5_step(t, dt, y, k0)
-                err = torch.zeros_like(y)
-                for j in range(7):
-                    if ew[j] != 0.0:
-                        err.add_(k[j], alpha=dt * ew[j])
-                error = self._scaled_norm(err, torch.maximum(y.abs(), y_new.abs()), atol, rtol)
+                loc = self.plan.dp5_error_sumsq(k, [dt * e for e in ew], y, y_new, atol, rtol)
+                error = math.sqrt(self._sum(float(loc[0])) / float(1 << self.n))
                 if error != error:
                     raise RuntimeError("non-finite error norm in DP5 step")
                 if replay is not None or error <= 1.0:
@@ -363,7 +362,9 @@ class ShardedKet:
         ``(-i H)^dagger kbar`` and adds this rank's share of the parameter gradients to ``acc``
         (summed over ranks by the caller)."""
         g, n = self.g, self.n_samples
-        hk, partners = self.hpsi(t, kbar, keep_partners=True)
+        # (-i H)^dagger kbar = i H kbar = -(-i H kbar)
+        hk, partners = self.hpsi(t, kbar, keep_partners=True, rhs=True)
+        hk = hk.neg_()
         i1 = max(int(min(math.floor(t / self.dt), n - 2)), 0)
         i2 = min(i1 + 1, n - 2)
         x = (t - i1 * self.dt) / self.dt
@@ -404,7 +405,7 @@ class ShardedKet:
                 if m >> q & 1:
                     acc["amp"][kidx, i1] += gc * (1.0 - x)
                     acc["amp"][kidx, i2] += gc * x
-        return hk.mul_(1j)
+        return hk
 
     def evolve_backward(self, states: Tensor, grad_states: Tensor, steps: Sequence[tuple]) -> dict:
         """Discrete adjoint of :meth:`evolve` (the recorded step sequence, recomputed stage by
@@ -424,11 +425,7 @@ class ShardedKet:
             # step-start states of the interval, recomputed from the saved state
             ys = [states[kk - 1]]
             for (t, h, _, _) in steps[lo:hi - 1]:
-                k, _ = self._dp5_step(t, h, ys[-1], self.rhs(t, ys[-1]))
-                y1 = ys[-1].clone()
-                for j in range(6):
-                    if _B5[j] != 0.0:
-                        y1.add_(k[j], alpha=h * _B5[j])
+                _, y1 = self._dp5_step(t, h, ys[-1], self.rhs(t, ys[-1]))
                 ys.append(y1)
             for s_idx in range(hi - 1, lo - 1, -1):
                 t, h, _, _ = steps[s_idx]
@@ -436,16 +433,16 @@ class ShardedKet:
                 k, _ = self._dp5_step(t, h, y_n, self.rhs(t, y_n))
                 yb = [None] * 6
                 for i in range(5, -1, -1):
-                    kbar = torch.zeros_like(lam)
-                    if _B5[i] != 0.0:
-                        kbar.add_(lam, alpha=h * _B5[i])
+                    ins, w = ([lam], [h * _B5[i]]) if _B5[i] != 0.0 else ([], [])
                     for j in range(i + 1, 6):
                         if _BETA[j - 1][i] != 0.0:
-                            kbar.add_(yb[j], alpha=h * _BETA[j - 1][i])
+                            ins.append(yb[j])
+                            w.append(h * _BETA[j - 1][i])
+                    kbar = self.plan.lincomb(self.state_buffer() if self._hdl is not None
+                                             else torch.empty_like(lam), ins, w)
                     ts_i = t + h * (0.0 if i == 0 else _ALPHA[i - 1])
                     yb[i] = self._vjp(ts_i, self._stage_input(y_n, k, i, h), kbar, acc)
-                for i in range(6):
-                    lam.add_(yb[i])
+                self.plan.lincomb(lam, [lam] + yb, [1.0] * 7)
             hi = lo
             lam.add_(grad_states[kk - 1])
         for key in ("det", "amp", "pair"):
