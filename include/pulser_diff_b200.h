@@ -186,11 +186,17 @@ int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t
  *   grad_det_host [n_det*n_samples], grad_amp_host [n_amp*n_samples*2] (nullable): the gradient
  *     w.r.t. the coefficient samples is ADDED (interpolation weights of the reference rule),
  *   grad_pair_host [N*N] (nullable): overwritten with dL/dU_ij (upper triangle),
- *   grad_t_host (nullable): dL/dt through the interpolation.
+ *   grad_t_host (nullable): dL/dt through the interpolation,
+ *   defer_pair != 0: the per-amplitude interaction weights are accumulated inside the plan
+ *     instead (grad_pair_host untouched); pd_pair_gradient_flush reduces them once -- an adjoint
+ *     sweep calls this function thousands of times and needs dL/dU_ij only at the end.
  * H(t) psi = i * pd_rhs(t, psi) on ket plans, so the VJP of pd_hpsi is this call with cot' = -i cot. */
 int pd_rhs_vjp(pd_plan* p, void* stream, double t, const void* state_dev, const void* cot_dev,
                void* grad_state_dev, double* grad_det_host, double* grad_amp_host,
-               double* grad_pair_host, double* grad_t_host);
+               double* grad_pair_host, double* grad_t_host, int32_t defer_pair);
+/* grad_pair_host [N*N] = dL/dU_ij summed over every deferred pd_rhs_vjp since the last flush
+ * (zeros if there was none); clears the accumulator. */
+int pd_pair_gradient_flush(pd_plan* p, void* stream, double* grad_pair_host);
 
 /* ---- pieces of one DP5 step for a host-driven stepper (the sharded register, where every
  * generator application contains an exchange step; upstream solver) ------ */

@@ -45,7 +45,7 @@ class pd_step_record(C.Structure):
 EXPORTS = (
     "pd_abi_version", "pd_last_error", "pd_options_default", "pd_plan_create", "pd_plan_destroy",
     "pd_plan_set_interaction", "pd_plan_set_terms", "pd_plan_set_collapse", "pd_plan_set_path",
-    "pd_hpsi", "pd_rhs", "pd_rhs_vjp",
+    "pd_hpsi", "pd_rhs", "pd_rhs_vjp", "pd_pair_gradient_flush",
     "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
     "pd_evolve_forward_units", "pd_evolve_backward_units", "pd_tape_unit_steps",
     "pd_tape_destroy", "pd_expect_diag", "pd_sharded_accumulate", "pd_lincomb", "pd_dp5_error_sumsq", "pd_bench_hpsi", "pd_bench_dp5_steps",
@@ -85,7 +85,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.pd_tape_records.argtypes = [vp, C.POINTER(pd_step_record), i64]
     lib.pd_tape_destroy.argtypes = [vp]
     lib.pd_expect_diag.argtypes = [vp, vp, vp, i32, vp, pdbl]
-    lib.pd_rhs_vjp.argtypes = [vp, vp, dbl, vp, vp, vp, pdbl, pdbl, pdbl, pdbl]
+    lib.pd_rhs_vjp.argtypes = [vp, vp, dbl, vp, vp, vp, pdbl, pdbl, pdbl, pdbl, i32]
+    lib.pd_pair_gradient_flush.argtypes = [vp, vp, pdbl]
     lib.pd_lincomb.argtypes = [vp, vp, vp, i32, C.POINTER(vp), pdbl]
     lib.pd_dp5_error_sumsq.argtypes = [vp, vp, C.POINTER(vp), pdbl, vp, vp, dbl, dbl, pdbl]
     lib.pd_sharded_accumulate.argtypes = [vp, vp, vp, vp, dbl, i32, C.POINTER(vp), pdbl]
@@ -288,21 +289,31 @@ class Plan:
         return out
 
     def rhs_vjp(self, t: float, state: torch.Tensor, cot: torch.Tensor, want_state: bool = True,
-                want_det: bool = True, want_amp: bool = True, want_pair: bool = False):
+                want_det: bool = True, want_amp: bool = True, want_pair: bool = False,
+                defer_pair: bool = False):
         """Reverse mode of ``k = rhs(t, state)``: returns ``(grad_state, g_det, g_amp, g_pair,
-        g_t)`` for the cotangent ``cot`` on ``k`` (entries not asked for are None)."""
+        g_t)`` for the cotangent ``cot`` on ``k`` (entries not asked for are None).
+        ``defer_pair``: accumulate the interaction weights inside the plan; collect dL/dU_ij
+        once with :meth:`pair_gradient_flush`."""
         state = self._vec(state, "state")
         cot = self._vec(cot, "cot")
         g_state = torch.empty_like(state) if want_state else None
         g_det = torch.zeros((self.n_det, self.n_samples), dtype=torch.float64) if want_det and self.n_det else None
         g_amp = torch.zeros((self.n_amp, self.n_samples, 2), dtype=torch.float64) if want_amp and self.n_amp else None
-        g_pair = torch.zeros((self.n_qubits, self.n_qubits), dtype=torch.float64) if want_pair else None
+        g_pair = torch.zeros((self.n_qubits, self.n_qubits), dtype=torch.float64) if want_pair and not defer_pair else None
         g_t = C.c_double(0.0)
         _check(lib().pd_rhs_vjp(self._ptr, _stream(self.device), float(t), _dptr(state), _dptr(cot),
-                                _dptr(g_state), _hdbl(g_det), _hdbl(g_amp), _hdbl(g_pair), C.byref(g_t)))
+                                _dptr(g_state), _hdbl(g_det), _hdbl(g_amp), _hdbl(g_pair), C.byref(g_t),
+                                int(bool(defer_pair))))
         if g_amp is not None:
             g_amp = torch.view_as_complex(g_amp)
         return g_state, g_det, g_amp, g_pair, float(g_t.value)
+
+    def pair_gradient_flush(self) -> torch.Tensor:
+        """dL/dU_ij of every ``rhs_vjp(..., defer_pair=True)`` since the last flush."""
+        g_pair = torch.zeros((self.n_qubits, self.n_qubits), dtype=torch.float64)
+        _check(lib().pd_pair_gradient_flush(self._ptr, _stream(self.device), _hdbl(g_pair)))
+        return g_pair
 
     def evolve_forward(self, solver: int, opt: Options, state0: torch.Tensor, tsave: torch.Tensor,
                        want_tape: bool) -> tuple[torch.Tensor, Optional[Tape]]:

@@ -209,13 +209,19 @@ int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t
 }
 int pd_rhs_vjp(pd_plan* p, void* stream, double t, const void* state_dev, const void* cot_dev,
                void* grad_state_dev, double* grad_det_host, double* grad_amp_host,
-               double* grad_pair_host, double* grad_t_host) {
+               double* grad_pair_host, double* grad_t_host, int32_t defer_pair) {
   return guarded([&] {
     need(p && state_dev && cot_dev, "pd_rhs_vjp: NULL argument");
     double tb = p->eng.rhs_vjp(t, (const pd::cplx*)state_dev, (const pd::cplx*)cot_dev,
                                (pd::cplx*)grad_state_dev, grad_det_host, grad_amp_host,
-                               grad_pair_host, stream);
+                               grad_pair_host, defer_pair != 0, stream);
     if (grad_t_host) *grad_t_host = tb;
+  });
+}
+int pd_pair_gradient_flush(pd_plan* p, void* stream, double* grad_pair_host) {
+  return guarded([&] {
+    need(p && grad_pair_host, "pd_pair_gradient_flush: NULL argument");
+    p->eng.pair_gradient_flush(grad_pair_host, stream);
   });
 }
 int pd_lincomb(pd_plan* p, void* stream, void* out_dev, int32_t n_in, const void* const* ins_dev,

@@ -331,14 +331,19 @@ class Engine {
   // stage of the DP5 adjoint (adjoint_step), exposed so host-side integrators (the sharded
   // register, user-written steppers) are differentiable too.
   double rhs_vjp(double t, const cplx* y, const cplx* kbar, cplx* grad_y, double* g_det,
-                 double* g_amp, double* g_pair, void* stream) {
+                 double* g_amp, double* g_pair, bool defer_pair, void* stream) {
     if (grad_y) apply(grad_y, kbar, t, 1, stream);
     int cs = corr_stride();
     cplx* d_corr = (cplx*)buf("corr", sizeof(cplx) * (size_t)cs);
     double* d_wacc = nullptr;
-    if (g_pair) {
-      d_wacc = (double*)buf("wacc", sizeof(double) * ((size_t)1 << geo.nq));
-      bk.zero(d_wacc, sizeof(double) * ((size_t)1 << geo.nq), stream);
+    size_t wbytes = sizeof(double) * ((size_t)1 << geo.nq);
+    if (defer_pair) {
+      // per-amplitude weights keep accumulating inside the plan; pair_gradient_flush() reduces them
+      d_wacc = (double*)buf("wacc_vjp", wbytes);
+      if (!vjp_wacc_live_) { bk.zero(d_wacc, wbytes, stream); vjp_wacc_live_ = true; }
+    } else if (g_pair) {
+      d_wacc = (double*)buf("wacc", wbytes);
+      bk.zero(d_wacc, wbytes, stream);
     }
     const cplx* yi[1] = {y};
     double yw[1] = {1.0};
@@ -346,7 +351,7 @@ class Engine {
                               reduce_scratch(), stream);
     std::vector<cplx> h_corr(cs);
     bk.d2h(h_corr.data(), d_corr, sizeof(cplx) * (size_t)cs, stream);
-    if (g_pair) {
+    if (g_pair && !defer_pair) {
       double* d_pair = (double*)buf("pair_out", sizeof(double) * (size_t)prog.nq * prog.nq);
       launches += bk.pair_reduce(geo, d_pair, d_wacc, stream);
       bk.d2h(g_pair, d_pair, sizeof(double) * (size_t)prog.nq * prog.nq, stream);
@@ -354,6 +359,18 @@ class Engine {
     bk.sync(stream);
     return distribute(t, h_corr.data(), g_det, g_amp);
   }
+  // dL/dU_ij of every deferred rhs_vjp since the last flush; clears the accumulator
+  void pair_gradient_flush(double* g_pair, void* stream) {
+    size_t n2 = (size_t)prog.nq * prog.nq;
+    if (!vjp_wacc_live_) { std::fill(g_pair, g_pair + n2, 0.0); return; }
+    double* d_wacc = (double*)buf("wacc_vjp", sizeof(double) * ((size_t)1 << geo.nq));
+    double* d_pair = (double*)buf("pair_out", sizeof(double) * n2);
+    launches += bk.pair_reduce(geo, d_pair, d_wacc, stream);
+    bk.d2h(g_pair, d_pair, sizeof(double) * n2, stream);
+    bk.sync(stream);
+    vjp_wacc_live_ = false;
+  }
+  bool vjp_wacc_live_ = false;
 
   // ---- building blocks of a host-driven DP5 step (the sharded register) --------------------
   // out = sum_j w_j in_j (one pass)

@@ -370,7 +370,7 @@ class ShardedKet:
         x = (t - i1 * self.dt) / self.dt
         # local qubits: the engine's own correlation kernels (C ABI pd_rhs_vjp)
         ops.configure(self.plan, self._prog)
-        _, gl_det, gl_amp, gl_pair, _ = self.plan.rhs_vjp(t, Y, kbar, want_state=False, want_pair=True)
+        _, gl_det, gl_amp, _, _ = self.plan.rhs_vjp(t, Y, kbar, want_state=False, defer_pair=True)
         nk = len(self._keep_det)
         if gl_det is None:
             gl_det = torch.zeros(nk + len(self._extra_qubits), n, dtype=torch.float64)
@@ -384,7 +384,6 @@ class ShardedKet:
                 acc["pair"][q, g + q_loc] += 0.5 * self.r_glob[q] * tot
         for j, kidx in enumerate(self._keep_amp):
             acc["amp"][kidx] += gl_amp[j]
-        acc["pair"][g:, g:] += gl_pair
         # energy shift of the global qubits: k has -i * shift * Y
         g_shift = torch.vdot(kbar.reshape(-1), Y.reshape(-1)).imag.item()
         for p_ in range(g):
@@ -416,6 +415,8 @@ class ShardedKet:
         acc = {"det": torch.zeros_like(self.det_values), "amp": torch.zeros_like(self.amp_values),
                "pair": torch.zeros(self.n, self.n, dtype=torch.float64)}
         n_t = int(states.shape[0])
+        ops.configure(self.plan, self._prog)
+        self.plan.pair_gradient_flush()              # start from an empty accumulator
         lam = grad_states[n_t - 1].detach().clone()
         hi = len(steps)
         for kk in range(n_t - 1, 0, -1):
@@ -445,6 +446,8 @@ class ShardedKet:
                 self.plan.lincomb(lam, [lam] + yb, [1.0] * 7)
             hi = lo
             lam.add_(grad_states[kk - 1])
+        ops.configure(self.plan, self._prog)
+        acc["pair"][self.g:, self.g:] += self.plan.pair_gradient_flush()
         for key in ("det", "amp", "pair"):
             v = acc[key].to(self.device)
             if v.is_complex():
