@@ -101,8 +101,9 @@ class ShardedKet:
                  det_values: Tensor, amp_masks: Sequence[int], amp_values: Tensor,
                  device: torch.device, group=None, peer_memory: bool | str = False) -> None:
         self.group = group
-        self.world = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
+        # without a process group: one rank owning the whole register (no global qubits)
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         g = self.world.bit_length() - 1
         if 1 << g != self.world:
             raise ValueError("the number of ranks must be a power of two")
@@ -271,6 +272,8 @@ class ShardedKet:
         return self.hpsi(t, psi_local, rhs=True)
 
     def _sum(self, x: float) -> float:
+        if self.world == 1:
+            return x
         v = torch.tensor([x], dtype=torch.float64, device=self.device)
         dist.all_reduce(v, group=self.group)
         return float(v.item())
@@ -448,7 +451,7 @@ class ShardedKet:
             lam.add_(grad_states[kk - 1])
         ops.configure(self.plan, self._prog)
         acc["pair"][self.g:, self.g:] += self.plan.pair_gradient_flush()
-        for key in ("det", "amp", "pair"):
+        for key in ("det", "amp", "pair") if self.world > 1 else ():
             v = acc[key].to(self.device)
             if v.is_complex():
                 v = torch.view_as_real(v).contiguous()
