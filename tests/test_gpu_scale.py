@@ -318,3 +318,54 @@ def test_lindblad_midsize_invariants_and_fd_gradient(cuda_device):
         d[0, idx] = eps
         fd = (f(av.detach() + d, frozen)[1] - f(av.detach() - d, frozen)[1]) / (2 * eps)
         assert abs(fd.item() - g[0, idx].real.item()) < 1e-6 * abs(fd.item()) + 1e-9
+
+
+def test_c4_full_size_lindblad_invariants_and_fd_gradient(cuda_device):
+    """BASELINE configs[3] at its full size (N = 12: rho has 4^12 entries, 256 MiB per vector; the
+    dense-operator oracle cannot run this).  Size-independent properties of the Lindblad flow with
+    dephasing + amplitude damping: trace and hermiticity conserved, purity decays from 1, total
+    Rydberg population stays in [0, N]; and the adjoint gradient w.r.t. one drive sample and one
+    detuning sample equals a central difference on the frozen step sequence (1e-6 relative)."""
+    from pulser_diff_b200.utils import occupation_diag
+    n, T = 12, 24
+    dev = cuda_device
+    pr = _program(n, T=T, seed=12)
+    g_deph, g_damp = 0.5, 0.1                       # SURVEY.md 8d, C4
+    col = torch.tensor([[[(g_deph / 2) ** 0.5, 0], [0, -(g_deph / 2) ** 0.5]],
+                        [[0, 0], [g_damp ** 0.5, 0]]], dtype=torch.complex128)
+    rho0 = torch.zeros(1, 4 ** n, dtype=torch.complex128, device=dev)
+    rho0[0, -1] = 1.0
+    tsave = torch.tensor([0.0, 0.006], dtype=torch.float64)
+    obs = torch.zeros(2 ** n, dtype=torch.float64, device=dev)
+    for i in range(n):
+        obs = obs + occupation_diag(n, [i], dev)
+
+    def f(av_, dv_, opt):
+        st = ops.evolve(rho0, tsave, dv_, av_, pr["pair_u"], n_qubits=n, kind=_cabi.PD_DENSITY,
+                        dt=pr["dt"], det_masks=pr["det_masks"], amp_masks=pr["amp_masks"], collapse=col,
+                        solver=_cabi.SOLVER_DP5_ME, options=opt)
+        rho = st[-1, 0].reshape(2 ** n, 2 ** n)
+        return st, (obs * rho.diagonal().real).sum()
+
+    av = pr["amp_values"].clone().requires_grad_(True)
+    dv = pr["det_values"].clone().requires_grad_(True)
+    st, val = f(av, dv, _cabi.Options())
+    rho = st.detach()[-1, 0].reshape(2 ** n, 2 ** n)
+    assert abs(rho.diagonal().sum().item() - 1) < 1e-9
+    assert (rho - rho.mH).abs().max() < 1e-12
+    purity = (rho.abs() ** 2).sum().item()
+    assert 0.0 < purity < 1 - 1e-6
+    assert 0.0 < val.item() < n
+    log = [r for r in ops.last_step_log(st) if r["accepted"]]
+    assert len(log) >= 2
+    frozen = _cabi.Options(replay=[(r["dt"], r["clipped"]) for r in log])
+    del st, rho
+    _, val2 = f(av, dv, frozen)
+    g_av, g_dv = torch.autograd.grad(val2, [av, dv])
+    eps = 1e-4
+    d = torch.zeros_like(av.detach()); d[0, 1] = eps
+    fd = (f(av.detach() + d, dv.detach(), frozen)[1] - f(av.detach() - d, dv.detach(), frozen)[1]) / (2 * eps)
+    assert abs(fd.item() - g_av[0, 1].real.item()) < 1e-6 * abs(fd.item()) + 1e-9
+    d = torch.zeros_like(dv.detach()); d[0, 2] = eps
+    fd = (f(av.detach(), dv.detach() + d, frozen)[1] - f(av.detach(), dv.detach() - d, frozen)[1]) / (2 * eps)
+    assert abs(fd.item() - g_dv[0, 2].item()) < 1e-6 * abs(fd.item()) + 1e-9
