@@ -327,7 +327,7 @@ def test_c4_full_size_lindblad_invariants_and_fd_gradient(cuda_device):
     Rydberg population stays in [0, N]; and the adjoint gradient w.r.t. one drive sample and one
     detuning sample equals a central difference on the frozen step sequence (1e-6 relative)."""
     from pulser_diff_b200.utils import occupation_diag
-    n, T = 12, 24
+    n, T = 12, 64
     dev = cuda_device
     pr = _program(n, T=T, seed=12)
     g_deph, g_damp = 0.5, 0.1                       # SURVEY.md 8d, C4
@@ -335,7 +335,7 @@ def test_c4_full_size_lindblad_invariants_and_fd_gradient(cuda_device):
                         [[0, 0], [g_damp ** 0.5, 0]]], dtype=torch.complex128)
     rho0 = torch.zeros(1, 4 ** n, dtype=torch.complex128, device=dev)
     rho0[0, -1] = 1.0
-    tsave = torch.tensor([0.0, 0.006], dtype=torch.float64)
+    tsave = torch.tensor([0.0, 0.05], dtype=torch.float64)
     obs = torch.zeros(2 ** n, dtype=torch.float64, device=dev)
     for i in range(n):
         obs = obs + occupation_diag(n, [i], dev)
@@ -349,12 +349,12 @@ def test_c4_full_size_lindblad_invariants_and_fd_gradient(cuda_device):
 
     av = pr["amp_values"].clone().requires_grad_(True)
     dv = pr["det_values"].clone().requires_grad_(True)
-    st, val = f(av, dv, _cabi.Options())
+    st, val = f(av, dv, _cabi.Options(atol=1e-10, rtol=1e-8))
     rho = st.detach()[-1, 0].reshape(2 ** n, 2 ** n)
     assert abs(rho.diagonal().sum().item() - 1) < 1e-9
     assert (rho - rho.mH).abs().max() < 1e-12
     purity = (rho.abs() ** 2).sum().item()
-    assert 0.0 < purity < 1 - 1e-6
+    assert 0.0 < purity < 1 - 1e-4
     assert 0.0 < val.item() < n
     log = [r for r in ops.last_step_log(st) if r["accepted"]]
     assert len(log) >= 2
@@ -363,9 +363,9 @@ def test_c4_full_size_lindblad_invariants_and_fd_gradient(cuda_device):
     _, val2 = f(av, dv, frozen)
     g_av, g_dv = torch.autograd.grad(val2, [av, dv])
     eps = 1e-4
-    d = torch.zeros_like(av.detach()); d[0, 1] = eps
+    d = torch.zeros_like(av.detach()); d[0, 9] = eps
     fd = (f(av.detach() + d, dv.detach(), frozen)[1] - f(av.detach() - d, dv.detach(), frozen)[1]) / (2 * eps)
-    assert abs(fd.item() - g_av[0, 1].real.item()) < 1e-6 * abs(fd.item()) + 1e-9
-    d = torch.zeros_like(dv.detach()); d[0, 2] = eps
+    assert abs(fd.item() - g_av[0, 9].real.item()) < 1e-6 * abs(fd.item()) + 1e-9
+    d = torch.zeros_like(dv.detach()); d[0, 14] = eps
     fd = (f(av.detach(), dv.detach() + d, frozen)[1] - f(av.detach(), dv.detach() - d, frozen)[1]) / (2 * eps)
-    assert abs(fd.item() - g_dv[0, 2].item()) < 1e-6 * abs(fd.item()) + 1e-9
+    assert abs(fd.item() - g_dv[0, 14].item()) < 1e-6 * abs(fd.item()) + 1e-9
