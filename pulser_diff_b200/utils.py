@@ -163,3 +163,17 @@ def interpolate_sine(num_values: int, duration: int) -> Tensor:
     right = idx < num_values
     mat[rows[right], idx[right]] = s[right]
     return mat.to(torch.float32)
+
+
+def s(t: float) -> float:
+    """Sine ease between 0 and 1 for a normalised time ``t`` (reference utils.py:136-148)."""
+    import math
+    return 0.5 * (1.0 + math.sin(math.pi * (t - 0.5)))
+
+
+def vn_entropy(rho: Tensor) -> Tensor:
+    """Von Neumann entropy (base 2) of a density matrix (reference utils.py:97-105): only the
+    strictly positive eigenvalues contribute."""
+    ev = torch.linalg.eigvalsh(rho)
+    pos = ev[ev > 0]
+    return -(pos * torch.log2(pos)).sum()
