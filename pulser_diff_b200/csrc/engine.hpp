@@ -618,14 +618,23 @@ class Engine {
             ysrc = ycur;
           }
           bk.d2d(seg, ysrc, vec_bytes, stream);
+          // When the whole interval fits, the slopes of every step but the last are kept from the
+          // recomputation pass (6 vectors per step), so the sweep does not recompute them.
+          const bool keep_k = c_lo == 0 && cn >= 2 && (cn - 1) * 6 + cn <= cap;
+          vec segk = keep_k ? (vec)buf("segk", vec_bytes * 6 * (cn - 1)) : nullptr;
           for (size_t s = 0; s + 1 < cn; ++s) {
             const AcceptedStep& st = tape.steps[lo + c_lo + s];
-            advance(seg + s * L, seg + (s + 1) * L, st, k, stream);
+            vec ks[6];
+            for (int i = 0; i < 6; ++i) ks[i] = keep_k ? segk + (s * 6 + i) * L : k[i];
+            advance(seg + s * L, seg + (s + 1) * L, st, ks, stream);
           }
           for (size_t s = cn; s-- > 0;) {
             size_t gi = lo + c_lo + s;
-            adjoint_step(tape.steps[gi], (int)gi, seg + s * L, lam, k, yb, kbar, ystage, d_corr,
-                         d_hdot, d_wacc, slots, want_coef, stream);
+            const bool cached = keep_k && s + 1 < cn;
+            vec ks[6];
+            for (int i = 0; i < 6; ++i) ks[i] = cached ? segk + (s * 6 + i) * L : k[i];
+            adjoint_step(tape.steps[gi], (int)gi, seg + s * L, lam, ks, yb, kbar, ystage, d_corr,
+                         d_hdot, d_wacc, slots, want_coef, stream, cached);
           }
           done_hi = c_lo;
         }
@@ -769,10 +778,12 @@ class Engine {
 
   void adjoint_step(const AcceptedStep& st, int step_index, const cplx* y_n, vec lam, vec* k,
                     vec* yb, vec kbar, vec ystage, cplx* d_corr, double* d_hdot, double* d_wacc,
-                    std::vector<SlotInfo>& slots, bool want_coef, void* stream) {
+                    std::vector<SlotInfo>& slots, bool want_coef, void* stream, bool have_k = false) {
     double t = st.t, h = st.dt;
-    apply(k[0], y_n, t, 0, stream);
-    dp5_stages(t, h, y_n, k, nullptr, 6, stream);
+    if (!have_k) {
+      apply(k[0], y_n, t, 0, stream);
+      dp5_stages(t, h, y_n, k, nullptr, 6, stream);
+    }
     int cs = corr_stride();
     for (int i = 5; i >= 0; --i) {
       const cplx* ins[8];
