@@ -618,19 +618,19 @@ class Engine {
             ysrc = ycur;
           }
           bk.d2d(seg, ysrc, vec_bytes, stream);
-          // When the whole interval fits, the slopes of every step but the last are kept from the
-          // recomputation pass (6 vectors per step), so the sweep does not recompute them.
-          const bool keep_k = c_lo == 0 && cn >= 2 && (cn - 1) * 6 + cn <= cap;
-          vec segk = keep_k ? (vec)buf("segk", vec_bytes * 6 * (cn - 1)) : nullptr;
+          // Spare segment budget keeps the slopes of the recomputation pass (6 vectors per step) for
+          // as many steps as fit, so the sweep does not recompute them.
+          const size_t nk = cap > cn ? std::min(cn - 1, (cap - cn) / 6) : 0;
+          vec segk = nk ? (vec)buf("segk", vec_bytes * 6 * nk) : nullptr;
           for (size_t s = 0; s + 1 < cn; ++s) {
             const AcceptedStep& st = tape.steps[lo + c_lo + s];
             vec ks[6];
-            for (int i = 0; i < 6; ++i) ks[i] = keep_k ? segk + (s * 6 + i) * L : k[i];
+            for (int i = 0; i < 6; ++i) ks[i] = s < nk ? segk + (s * 6 + i) * L : k[i];
             advance(seg + s * L, seg + (s + 1) * L, st, ks, stream);
           }
           for (size_t s = cn; s-- > 0;) {
             size_t gi = lo + c_lo + s;
-            const bool cached = keep_k && s + 1 < cn;
+            const bool cached = s < nk;
             vec ks[6];
             for (int i = 0; i < 6; ++i) ks[i] = cached ? segk + (s * 6 + i) * L : k[i];
             adjoint_step(tape.steps[gi], (int)gi, seg + s * L, lam, ks, yb, kbar, ystage, d_corr,

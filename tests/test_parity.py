@@ -432,3 +432,36 @@ def test_host_driven_dp5_matches_engine(engine_device):
     for got, want in ((out["det"], g_full[1]), (out["amp"], g_full[2]), (out["pair"], g_full[3]),
                       (out["state0"], g_full[0])):
         assert rel(got.cpu(), want.cpu()) < 1e-8
+
+
+def test_adjoint_checkpoint_budgets(emu_library):
+    """The DP5 adjoint recomputes step-start states per tsave interval in chunks sized by a memory
+    budget and keeps the slopes of as many steps as the spare budget holds.  Every split (one
+    state per chunk, partial slope cache, everything cached) must give the same gradients."""
+    import ctypes as C
+    from pulser_diff_b200 import _cabi, ops
+    from test_parallel_gloo import _program
+    _cabi.use_library(emu_library)
+    n = 5
+    pr = _program(n, T=40)
+    psi0 = torch.zeros(1, 2 ** n, dtype=torch.complex128)
+    psi0[0, -1] = 1.0
+    tsave = torch.tensor([0.0, 0.02, 0.05], dtype=torch.float64)
+    w = torch.arange(2 ** n, dtype=torch.float64).remainder(5) + 0.5
+    plan = ops.get_plan(n, 1, _cabi.PD_KET, torch.device("cpu"))
+    vec_bytes = 16 * 2 ** n
+    grads = []
+    for n_vec in (1, 3, 9, 40, 10 ** 6):
+        ptr = plan._ptr.value if hasattr(plan._ptr, "value") else plan._ptr
+        assert _cabi.lib().pd_emu_set_segment_budget(C.c_void_p(ptr), C.c_uint64(n_vec * vec_bytes)) == 0
+        leaves = [x.clone().requires_grad_(True) for x in (psi0, pr["det_values"], pr["amp_values"], pr["pair_u"])]
+        ts = tsave.clone().requires_grad_(True)
+        st = ops.evolve(leaves[0], ts, leaves[1], leaves[2], leaves[3], n_qubits=n, kind=_cabi.PD_KET,
+                        dt=pr["dt"], det_masks=pr["det_masks"], amp_masks=pr["amp_masks"])
+        loss = (w * st[-1].abs() ** 2).sum() + (w * st[1].real).sum()
+        grads.append(torch.autograd.grad(loss, leaves + [ts]))
+        n_steps = sum(1 for r in ops.last_step_log(st) if r["accepted"])
+    assert n_steps > 12          # several chunks at the small budgets
+    for gset in grads[:-1]:
+        for a, b in zip(gset, grads[-1]):
+            assert (a - b).abs().max().item() <= 1e-12 * max(1.0, b.abs().max().item())
