@@ -371,6 +371,7 @@ class Engine {
     vjp_wacc_live_ = false;
   }
   bool vjp_wacc_live_ = false;
+  size_t n_backward_ = 0;   // DP5 adjoint sweeps this plan has run (slope-cache policy)
 
   // ---- building blocks of a host-driven DP5 step (the sharded register) --------------------
   // out = sum_j w_j in_j (one pass)
@@ -619,8 +620,10 @@ class Engine {
           }
           bk.d2d(seg, ysrc, vec_bytes, stream);
           // Spare segment budget keeps the slopes of the recomputation pass (6 vectors per step) for
-          // as many steps as fit, so the sweep does not recompute them.
-          const size_t nk = cap > cn ? std::min(cn - 1, (cap - cn) / 6) : 0;
+          // as many steps as fit, so the sweep does not recompute them.  Allocating that cache costs
+          // more than one sweep saves (cudaMalloc ~50 ms/GiB against ~3 ms/GiB of recomputation), so
+          // it is only set up once a plan is differentiated repeatedly (optimisation loops).
+          const size_t nk = (n_backward_ >= 1 && cap > cn) ? std::min(cn - 1, (cap - cn) / 6) : 0;
           vec segk = nk ? (vec)buf("segk", vec_bytes * 6 * nk) : nullptr;
           for (size_t s = 0; s + 1 < cn; ++s) {
             const AcceptedStep& st = tape.steps[lo + c_lo + s];
@@ -647,6 +650,7 @@ class Engine {
       }
     }
     if (g_state0) bk.d2d(g_state0, lam, vec_bytes, stream);
+    ++n_backward_;
 
     // ---- host post-processing of the per-slot reductions ----
     if (want_coef && n_slots > 0) {

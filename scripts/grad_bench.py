@@ -26,7 +26,7 @@ for n in [int(a) for a in (sys.argv[1:] or ["20"])]:
     replay = [(0.001, False)] * (n_steps - 1) + [(0.001, True)]
     w = torch.arange(2 ** n, device=dev).remainder(7).to(torch.float64)
     res = {}
-    for rep in range(2):
+    for rep in range(3):      # the third sweep runs with the slope cache set up by the second
         dv = dv0.clone().requires_grad_(True); av = av0.clone().requires_grad_(True)
         torch.cuda.synchronize(); t0 = time.perf_counter()
         st = ops.evolve(psi0, tsave, dv, av, u, n_qubits=n, kind=_cabi.PD_KET, dt=0.02, det_masks=[full],
