@@ -9,6 +9,9 @@
 //     discrete adjoint of the SAME accepted-step sequence, so gradients agree with the tape to
 //     round-off, not merely to solver tolerance.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 
 #include "pd_common.hpp"
@@ -574,6 +577,12 @@ class Engine {
     if (use_small() &&
         backward_dp5_small(tape, states, gstates, g_det, g_amp, g_pair, g_tsave, g_state0, want_coef, stream))
       return;
+    // PD_TIMING=1: host-side phase times of this sweep on stderr
+    static const bool timing = std::getenv("PD_TIMING") != nullptr;
+    auto now = [&] { if (timing) bk.sync(stream); return std::chrono::steady_clock::now(); };
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    auto t_begin = now();
+    double ms_alloc = 0, ms_recompute = 0, ms_sweep = 0;
     if (gstates) bk.d2d(lam, gstates + (size_t)(n_t - 1) * L, sizeof(cplx) * L, stream);
     else bk.zero(lam, sizeof(cplx) * L, stream);
     vec k[6], yb[6];
@@ -595,6 +604,7 @@ class Engine {
     // segment buffer for recomputed step-start states
     size_t vec_bytes = sizeof(cplx) * L;
     size_t cap = std::max<size_t>(1, bk.segment_budget_bytes() / vec_bytes);
+    auto t_setup = now();
 
     size_t hi = n_steps;  // steps [lo, hi) belong to the interval being processed
     for (int kk = n_t - 1; kk >= 1; --kk) {
@@ -609,6 +619,7 @@ class Engine {
           size_t c_lo = done_hi > cap ? done_hi - cap : 0;
           size_t cn = done_hi - c_lo;
           // y at the start of local step c_lo: recompute from the interval start
+          auto t0 = now();
           vec seg = (vec)buf("seg", vec_bytes * cn);
           vec ycur = vbuf("y"), ynext = vbuf("ynew");
           const cplx* ysrc = y_start;
@@ -625,12 +636,16 @@ class Engine {
           // it is only set up once a plan is differentiated repeatedly (optimisation loops).
           const size_t nk = (n_backward_ >= 1 && cap > cn) ? std::min(cn - 1, (cap - cn) / 6) : 0;
           vec segk = nk ? (vec)buf("segk", vec_bytes * 6 * nk) : nullptr;
+          auto t1 = now();
+          ms_alloc += ms(t0, t1);
           for (size_t s = 0; s + 1 < cn; ++s) {
             const AcceptedStep& st = tape.steps[lo + c_lo + s];
             vec ks[6];
             for (int i = 0; i < 6; ++i) ks[i] = s < nk ? segk + (s * 6 + i) * L : k[i];
             advance(seg + s * L, seg + (s + 1) * L, st, ks, stream);
           }
+          auto t2 = now();
+          ms_recompute += ms(t1, t2);
           for (size_t s = cn; s-- > 0;) {
             size_t gi = lo + c_lo + s;
             const bool cached = s < nk;
@@ -639,6 +654,7 @@ class Engine {
             adjoint_step(tape.steps[gi], (int)gi, seg + s * L, lam, ks, yb, kbar, ystage, d_corr,
                          d_hdot, d_wacc, slots, want_coef, stream, cached);
           }
+          ms_sweep += ms(t2, now());
           done_hi = c_lo;
         }
       }
@@ -651,6 +667,9 @@ class Engine {
     }
     if (g_state0) bk.d2d(g_state0, lam, vec_bytes, stream);
     ++n_backward_;
+    if (timing)
+      std::fprintf(stderr, "[pd] backward_dp5: setup %.1f ms, segment alloc %.1f ms, recompute %.1f ms, sweep %.1f ms "
+                   "(%zu steps, cap %zu vectors)\n", ms(t_begin, t_setup), ms_alloc, ms_recompute, ms_sweep, n_steps, cap);
 
     // ---- host post-processing of the per-slot reductions ----
     if (want_coef && n_slots > 0) {
