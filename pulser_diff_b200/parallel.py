@@ -409,6 +409,14 @@ class ShardedKet:
                     acc["amp"][kidx, i2] += gc * x
         return hk
 
+    def _slope_cache_steps(self, like: Tensor) -> int:
+        """How many steps' slopes (6 slices each) the adjoint sweep may keep."""
+        per_step = 6 * like.numel() * like.element_size()
+        if like.device.type != "cuda":
+            return (1 << 28) // per_step
+        free, _ = torch.cuda.mem_get_info(like.device)
+        return int(free // 3 // per_step)
+
     def evolve_backward(self, states: Tensor, grad_states: Tensor, steps: Sequence[tuple]) -> dict:
         """Discrete adjoint of :meth:`evolve` (the recorded step sequence, recomputed stage by
         stage as in csrc/engine.hpp adjoint_step).  ``grad_states``: cotangents on this rank's
@@ -426,15 +434,22 @@ class ShardedKet:
             lo = hi
             while lo > 0 and steps[lo - 1][2] == kk:
                 lo -= 1
-            # step-start states of the interval, recomputed from the saved state
-            ys = [states[kk - 1]]
+            # step-start states of the interval, recomputed from the saved state; the slopes of
+            # that pass are kept while they fit a third of the free memory (engine.hpp does the same)
+            ys, ks = [states[kk - 1]], []
+            room = self._slope_cache_steps(states[kk - 1])
+            k0 = None
             for (t, h, _, _) in steps[lo:hi - 1]:
-                _, y1 = self._dp5_step(t, h, ys[-1], self.rhs(t, ys[-1]))
+                k, y1 = self._dp5_step(t, h, ys[-1], k0 if k0 is not None else self.rhs(t, ys[-1]))
                 ys.append(y1)
+                ks.append(k[:6] if len(ks) < room else None)
+                k0 = k[6]                                   # FSAL: first slope of the next step
             for s_idx in range(hi - 1, lo - 1, -1):
                 t, h, _, _ = steps[s_idx]
                 y_n = ys[s_idx - lo]
-                k, _ = self._dp5_step(t, h, y_n, self.rhs(t, y_n))
+                k = ks.pop() if len(ks) > s_idx - lo else None
+                if k is None:
+                    k, _ = self._dp5_step(t, h, y_n, self.rhs(t, y_n))
                 yb = [None] * 6
                 for i in range(5, -1, -1):
                     ins, w = ([lam], [h * _B5[i]]) if _B5[i] != 0.0 else ([], [])
