@@ -293,11 +293,11 @@ class ShardedKet:
         out = self.state_buffer() if (publish and self._hdl is not None) else torch.empty_like(y)
         return self.plan.lincomb(out, ins, w)
 
-    def _dp5_step(self, t: float, h: float, y: Tensor, k0: Tensor):
-        """k[0..6], y_new of one step (stage 7's input is y_new: FSAL)."""
+    def _dp5_step(self, t: float, h: float, y: Tensor, k0: Tensor, upto: int = 6):
+        """k[0..upto], y_new of one step (stage 7's input is y_new: FSAL; ``upto=5`` stops before it)."""
         k = [k0]
         y_new = None
-        for i in range(1, 7):
+        for i in range(1, upto + 1):
             Y = self._stage_input(y, k, i, h, publish=i < 6)
             k.append(self.rhs(t + h * _ALPHA[i - 1], Y))
             if i == 6:
@@ -449,7 +449,7 @@ class ShardedKet:
                 y_n = ys[s_idx - lo]
                 k = ks.pop() if len(ks) > s_idx - lo else None
                 if k is None:
-                    k, _ = self._dp5_step(t, h, y_n, self.rhs(t, y_n))
+                    k, _ = self._dp5_step(t, h, y_n, self.rhs(t, y_n), upto=5)
                 yb = [None] * 6
                 for i in range(5, -1, -1):
                     ins, w = ([lam], [h * _B5[i]]) if _B5[i] != 0.0 else ([], [])
