@@ -7,8 +7,12 @@
   state.  Backward = adjoint sweep on the device; ``retain_graph`` / repeated
   ``autograd.grad`` calls work because the step log is kept, not consumed
   (reference derivative.py:40,76 call it 40x in docs/basic_usage.ipynb cell 26).
+* :func:`evolve_units` - the same for a batch of pulse-parameter sets of one register.
 * ``torch.ops.pulser_diff_b200.{hpsi, rhs, evolve_states, expect_diag}`` - ``torch.library``
-  custom ops over the same C ABI for non-differentiable use.
+  custom ops over the same C ABI.  ``hpsi`` and ``rhs`` (one generator application) are
+  differentiable w.r.t. the state, the coefficient arrays and the pair couplings (C ABI
+  ``pd_rhs_vjp``), so a stepper written in torch on top of them back-propagates like the
+  reference's ``H_t(t) @ psi`` (hamiltonian.py:526-546).
 
 Internal state layout is batch-major ``(batch, dim)``; the reference layout ``(dim, batch)``
 is converted in :mod:`pulser_diff_b200.solvers`.
@@ -214,7 +218,8 @@ def last_step_log(states: Tensor) -> list[dict]:
 
 
 # ------------------------------------------------------------------------------------------
-# torch.library custom ops (non-differentiable entry points)
+# torch.library custom ops (hpsi / rhs carry autograd formulas; evolve_states / expect_diag are
+# the non-differentiable entry points -- differentiable evolution is ops.evolve)
 # ------------------------------------------------------------------------------------------
 def _prog_from_args(n_qubits, kind, dt, det_masks, det_values, amp_masks, amp_values, pair_u, collapse):
     coll = collapse if collapse is not None and collapse.numel() > 0 else None
