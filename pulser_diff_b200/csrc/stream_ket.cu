@@ -284,14 +284,21 @@ bool uniform_drive(const StreamCoef& a, int nq) {
   return true;
 }
 
-bool g_attr_set = false;
+bool g_attr_set[64] = {};     // per device: function attributes belong to the device's context
+int current_device() {
+  int dev = 0;
+  PD_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) throw Error(PD_ERR_STATE, "device index out of range");
+  return dev;
+}
 void set_attrs() {
-  if (g_attr_set) return;
+  const int dev = current_device();
+  if (g_attr_set[dev]) return;
   PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
   PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
   PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
   PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
-  g_attr_set = true;
+  g_attr_set[dev] = true;
 }
 
 }  // namespace
@@ -554,23 +561,26 @@ __global__ void k_stream_corr_final(const __grid_constant__ CorrFinal F) {
 int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar, int n_in,
                        const cplx* const* ins, const double* w, cplx* ymat, cudaStream_t s) {
   if (n_in > kMaxIn) throw Error(PD_ERR_INVALID, "stream corr takes at most 8 inputs");
-  static bool attr = false;
-  if (!attr) {
+  static bool attr_set[64] = {};
+  const int dev = current_device();
+  if (!attr_set[dev]) {
     PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_a, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
     PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_g, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
-    attr = true;
+    attr_set[dev] = true;
   }
   const unsigned grid = (unsigned)((g.dim >> TB) * (size_t)g.batch);
   const int rest = g.nq - TB;
   const int G = d_corr ? (rest + kMaxGroupBits - 1) / kMaxGroupBits : 0;
-  static double* d_part = nullptr;
-  static size_t cap = 0;
+  // per-device scratch for the per-CTA partial sums (a process may drive several devices)
+  static double* parts[64] = {};
+  static size_t caps[64] = {};
   const size_t need = (size_t)grid * (kCA + (size_t)G * kCG);
-  if (cap < need) {
-    if (d_part) cudaFree(d_part);
-    PD_CUDA_CHECK(cudaMalloc(&d_part, sizeof(double) * need));
-    cap = need;
+  if (caps[dev] < need) {
+    if (parts[dev]) cudaFree(parts[dev]);
+    PD_CUDA_CHECK(cudaMalloc(&parts[dev], sizeof(double) * need));
+    caps[dev] = need;
   }
+  double* d_part = parts[dev];
   const bool plain = n_in == 1 && w[0] == 1.0;
   const cplx* ysrc = plain ? ins[0] : ymat;
   if (!plain && G > 0 && ymat == nullptr) throw Error(PD_ERR_STATE, "stream corr needs a buffer for the stage input");

@@ -444,7 +444,7 @@ void fill_coef(const SiteOps& so, int nq, BitCoef& bc) {
   }
 }
 
-bool g_attr_set = false;
+bool g_attr_set[64] = {};     // per device: function attributes belong to the device's context
 bool uniform_drive(const BitCoef& a, int nq) {
   for (int p = 1; p < nq; ++p)
     if (a.t01[p].re != a.t01[0].re || a.t01[p].im != a.t01[0].im || a.t10[p].re != a.t10[0].re ||
@@ -453,12 +453,15 @@ bool uniform_drive(const BitCoef& a, int nq) {
   return true;
 }
 void launch(const TiledParams& P, const BitCoef& cp, const BitCoef& cn, int batch, cudaStream_t s) {
-  if (!g_attr_set) {
+  int dev = 0;
+  PD_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) throw Error(PD_ERR_STATE, "device index out of range");
+  if (!g_attr_set[dev]) {
     PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
     PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
     PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
     PD_CUDA_CHECK(cudaFuncSetAttribute(k_tiled<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
-    g_attr_set = true;
+    g_attr_set[dev] = true;
   }
   unsigned grid = (unsigned)((P.dim >> TB) * (size_t)batch);
   const bool uni = uniform_drive(cp, P.nq) && uniform_drive(cn, P.nq);
