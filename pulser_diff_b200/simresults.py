@@ -1,11 +1,14 @@
 """Result container with the slice of the reference API that sits next to the hot path.
 
 Mirrors ``CoherentResults`` of reference ``pulser_diff/simresults.py`` (:81-129 ``expect``,
-:398-401 ``states``) without Pulser's ``Results`` base class.  Sampling, plotting and
-pseudo-density helpers are host statistics and out of scope.
+:131-157 ``sample_state`` / ``sample_final_state``, :398-401 ``states``) without Pulser's
+``Results`` base class.  Bitstring weights and the sampling itself stay on the device
+(reference result.py:71-120); plotting, measurement-error flips and the
+QuTiP pseudo-density are host statistics and out of scope.
 """
 from __future__ import annotations
 
+from collections import Counter
 from typing import Sequence
 
 import torch
@@ -35,10 +38,42 @@ class CoherentResults:
         return self._states[-1]
 
     def get_state(self, t: float, t_tol: float = 1.0e-3) -> Tensor:
+        return self._states[self._index_of(t, t_tol)]
+
+    def _index_of(self, t: float, t_tol: float) -> int:
         idx = int(torch.argmin(torch.abs(self._sim_times.detach() - t)))
         if abs(float(self._sim_times[idx]) - t) > t_tol:
             raise IndexError(f"Given time {t} is absent from the evaluation times within {t_tol}.")
-        return self._states[idx]
+        return idx
+
+    def _weights(self, idx: int) -> Tensor:
+        """Probabilities of the 2^N measured bitstrings at evaluation time ``idx`` (on the state's
+        device).  The state vector is ordered with r first ([rr, rg, gr, gg]) and r is measured as
+        1, so entry j of the result belongs to the bitstring ``binary_repr(j)``
+        (reference result.py:71-87)."""
+        st = self._states[idx].detach()
+        if st.dim() == 3:                                  # (S, S, 1) density matrix
+            probs = st[..., 0].diagonal().abs()
+        else:                                              # (S, B) kets; the reference takes B = 1
+            probs = (st.abs() ** 2).sum(dim=1)
+        weights = probs.flip(0) if self._meas_basis == "ground-rydberg" else probs
+        return weights / weights.sum()
+
+    def sample_state(self, t: float, n_samples: int = 1000, t_tol: float = 1.0e-3) -> Counter:
+        """Bitstring counts of ``n_samples`` projective measurements at time ``t``
+        (reference simresults.py:131-145).  Drawn on the device by inverting the cumulative
+        distribution, so the 2^N probabilities never travel to the host."""
+        w = self._weights(self._index_of(t, t_tol))
+        cdf = torch.cumsum(w, dim=0)
+        u = torch.rand(int(n_samples), dtype=cdf.dtype, device=cdf.device) * cdf[-1]
+        hits = torch.searchsorted(cdf, u, right=True).clamp_(max=w.numel() - 1)
+        values, counts = torch.unique(hits, return_counts=True)
+        n = self._size
+        return Counter({format(int(v), f"0{n}b"): int(c) for v, c in zip(values.tolist(), counts.tolist())})
+
+    def sample_final_state(self, N_samples: int = 1000) -> Counter:
+        """Bitstring counts of the final state (reference simresults.py:147-157)."""
+        return self.sample_state(float(self._sim_times[-1]), N_samples)
 
     def expect(self, obs_list: Sequence[Tensor]) -> list[Tensor]:
         """Expectation values of the operators in ``obs_list`` at every evaluation time.

@@ -465,3 +465,35 @@ def test_adjoint_checkpoint_budgets(emu_library):
     for gset in grads[:-1]:
         for a, b in zip(gset, grads[-1]):
             assert (a - b).abs().max().item() <= 1e-12 * max(1.0, b.abs().max().item())
+
+
+def test_bitstring_sampling_on_device(engine_device):
+    """CoherentResults.sample_state / sample_final_state (reference simresults.py:131-157,
+    result.py:71-87): r is measured as 1 and the register's first atom is the leftmost character;
+    frequencies follow |psi|^2 (4 sigma on 40 000 shots); density matrices use their diagonal."""
+    from pulser_diff_b200.simresults import CoherentResults
+    dev = engine_device
+    times = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    # basis state [rr, rg, gr, gg] index 1 = |r g>  ->  "10"
+    psi = torch.zeros(2, 4, 1, dtype=torch.complex128, device=dev)
+    psi[0, 1, 0] = 1.0
+    amp = torch.tensor([0.1, 0.5j, -0.7, 0.5], dtype=torch.complex128)
+    amp = amp / amp.norm()
+    psi[1, :, 0] = amp.to(dev)
+    res = CoherentResults(psi, 2, "ground-rydberg", times)
+    assert res.sample_state(0.0, 50) == {"10": 50}
+    torch.manual_seed(1)
+    shots = 40000
+    cnt = res.sample_final_state(shots)
+    assert sum(cnt.values()) == shots
+    want = {"11": abs(amp[0]) ** 2, "10": abs(amp[1]) ** 2, "01": abs(amp[2]) ** 2, "00": abs(amp[3]) ** 2}
+    for key, p in want.items():
+        p = float(p)
+        assert abs(cnt.get(key, 0) / shots - p) < 4 * (p * (1 - p) / shots) ** 0.5
+    with pytest.raises(IndexError):
+        res.sample_state(0.5)
+    rho = torch.zeros(1, 4, 4, 1, dtype=torch.complex128, device=dev)
+    rho[0, 3, 3, 0] = 0.25
+    rho[0, 0, 0, 0] = 0.75
+    cnt = CoherentResults(rho, 2, "ground-rydberg", times[:1]).sample_state(0.0, 4000)
+    assert set(cnt) == {"11", "00"} and abs(cnt["11"] / 4000 - 0.75) < 0.04
