@@ -497,3 +497,26 @@ def test_bitstring_sampling_on_device(engine_device):
     rho[0, 0, 0, 0] = 0.75
     cnt = CoherentResults(rho, 2, "ground-rydberg", times[:1]).sample_state(0.0, 4000)
     assert set(cnt) == {"11", "00"} and abs(cnt["11"] / 4000 - 0.75) < 0.04
+
+
+def test_generator_vjp_time_gradient(engine_device):
+    """dL/dt returned by pd_rhs_vjp (through the reference's interpolation rule,
+    hamiltonian.py:532-542): the coefficients are linear in t inside one sample interval, so a
+    central difference that stays inside the interval is exact."""
+    from pulser_diff_b200 import _cabi, ops
+    dev = engine_device
+    n, ns, dt, t = 3, 9, 0.004, 0.0137          # t / dt = 3.425: interval 3
+    g = torch.Generator().manual_seed(6)
+    rnd = lambda *s: torch.randn(*s, dtype=torch.float64, generator=g)
+    dv, av = rnd(2, ns), torch.complex(rnd(2, ns), rnd(2, ns))
+    det_masks, amp_masks = [0b111, 0b010], [0b111, 0b100]
+    pu = torch.triu(rnd(n, n).abs() * 3, diagonal=1)
+    state = torch.complex(rnd(1, 2 ** n), rnd(1, 2 ** n)).to(dev)
+    cot = torch.complex(rnd(1, 2 ** n), rnd(1, 2 ** n)).to(dev)
+    plan = ops.get_plan(n, 1, _cabi.PD_KET, torch.device(dev))
+    ops.configure(plan, ops.make_program(n, _cabi.PD_KET, dt, det_masks, dv, amp_masks, av, pu, None))
+    *_, g_t = plan.rhs_vjp(t, state, cot)
+    f = lambda tt: (cot.conj() * plan.hpsi(tt, state, rhs=True)).real.sum().item()
+    eps = 1e-4
+    fd = (f(t + eps) - f(t - eps)) / (2 * eps)
+    assert abs(g_t - fd) < 1e-9 * max(1.0, abs(fd))
