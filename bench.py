@@ -490,9 +490,6 @@ def run_sharded(args):
 
 
 def main():
-    # NCCL writes its banner ("NCCL version ...") to stdout when NCCL_DEBUG is set in the
-    # environment; stdout carries the ONE JSON line, so send NCCL's log to stderr.
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
