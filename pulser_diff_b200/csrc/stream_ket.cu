@@ -15,8 +15,17 @@
 // pass, small enough in registers and shared memory for three CTAs per SM, which is what keeps HBM
 // busy while other CTAs are in their shared-memory phase.
 //
-// Traffic of one DP5 step at N = 26: 84 vector passes + diagonal = 1392 B per amplitude against
-// the 576 B algorithmic figure.
+// L2 blocking (round 2).  B200's L2 serves hits at 15-19 TB/s against 6.5 TB/s from HBM
+// (profiles/r02_l2bench.md), so the A launch and the FIRST group launch of a stage run as ONE dataflow
+// launch, k_stream_ag: work items are handed out in ticket order, chunk by chunk (256 tiles = 16 MiB per
+// vector): the A tiles of chunk c, then the group tiles of chunk c - 1, which wait on a per-chunk
+// completion counter and find Ymat and the partial result in L2.  Per stage the HBM traffic falls from
+// n + 8.5 to n + 5.5 vector passes (n = vectors combined); a DP5 step at N = 26 moves 62 passes instead
+// of 80.
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
 #include "cuda_backend.cuh"
 
 namespace pd {
@@ -65,16 +74,13 @@ __device__ __forceinline__ cplx ldcs(const cplx* p) {
 
 // ---- A launch: contiguous tile, combination + diagonal + low-bit flips ---------------------------
 template <bool UNI>
-__global__ void __launch_bounds__(NT, 3)
-k_stream_a(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+__device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t lin_tile) {
   __shared__ cplx tab[2][64];
   const int t = threadIdx.x;
   const int nq = P.nq;
   const size_t tiles_per_vec = P.dim >> TB;
-  const size_t tile = blockIdx.x % tiles_per_vec;
-  const size_t base = (blockIdx.x / tiles_per_vec) * P.dim + (tile << TB);   // batch column + tile
+  const size_t tile = lin_tile % tiles_per_vec;
+  const size_t base = (lin_tile / tiles_per_vec) * P.dim + (tile << TB);   // batch column + tile
 
   // detuning-diagonal tables over local bits 0-5 / 6-11; bits above the tile are constant per tile
   if (t < 128) {
@@ -175,6 +181,13 @@ k_stream_a(const __grid_constant__ StreamParams P, const __grid_constant__ Strea
   }
 }
 
+template <bool UNI>
+__global__ void __launch_bounds__(NT, 3)
+k_stream_a(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  a_tile<UNI>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
+}
+
 // ---- group launch: strided tile, out += H_g Ymat ---------------------------------------------------
 __device__ __forceinline__ size_t gindex(const StreamParams& P, size_t tile, int e) {
   const size_t col = (size_t)(e & ((1 << P.C) - 1)), row = (size_t)(e >> P.C);
@@ -184,14 +197,11 @@ __device__ __forceinline__ size_t gindex(const StreamParams& P, size_t tile, int
 }
 
 template <bool UNI>
-__global__ void __launch_bounds__(NT, 3)
-k_stream_g(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+__device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t lin_tile) {
   const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
-  const size_t tile = blockIdx.x % tiles_per_vec;
-  const size_t boff = (blockIdx.x / tiles_per_vec) * P.dim;
+  const size_t tile = lin_tile % tiles_per_vec;
+  const size_t boff = (lin_tile / tiles_per_vec) * P.dim;
   const cplx* ym = P.v[0] + boff;
   cplx* out = P.out + boff;
   const int C = P.C, nb = P.nb;
@@ -261,8 +271,66 @@ k_stream_g(const __grid_constant__ StreamParams P, const __grid_constant__ Strea
     if (t == 0) {
       double sacc = 0.0;
       for (int w = 0; w < NT / 32; ++w) sacc += red[w];
-      P.err_partial[blockIdx.x] = sacc;
+      P.err_partial[lin_tile] = sacc;
     }
+  }
+}
+
+template <bool UNI>
+__global__ void __launch_bounds__(NT, 3)
+k_stream_g(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  g_tile<UNI>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
+}
+
+// ---- dataflow launch: A tiles and the first group's tiles, chunk by chunk through L2 --------------------
+// sync[0] = ticket dispenser, sync[1 + c] = finished A tiles of chunk c (zeroed by the host before the launch).
+// Tickets make the order of work items the order in which CTAs START, so a group tile only ever waits for A
+// tiles that are already running or done (no reliance on the block scheduler's dispatch order).
+struct AgCtl {
+  unsigned* sync;
+  unsigned chunk_log2;     // tiles per chunk = 1 << chunk_log2; the first group's row bits lie inside a chunk
+  unsigned n_chunks;
+  unsigned lag;            // group tiles of chunk c are handed out after the A tiles of chunk c + lag
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <bool UNI>
+__global__ void __launch_bounds__(NT, 3)
+k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ StreamParams PG,
+            const __grid_constant__ StreamCoef cf, const AgCtl ctl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  __shared__ unsigned s_item;
+  if (threadIdx.x == 0) s_item = atomicAdd(ctl.sync, 1u);
+  __syncthreads();
+  const unsigned item = s_item;
+  const unsigned CT = 1u << ctl.chunk_log2;
+  const unsigned blk = item >> (ctl.chunk_log2 + 1), r = item & (2 * CT - 1);
+  if (r < CT) {
+    if (blk >= ctl.n_chunks) return;
+    a_tile<UNI>(PA, cf, T, (size_t)blk * CT + r);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(ctl.sync + 1 + blk, 1u);
+  } else {
+    if (blk < ctl.lag) return;
+    const unsigned c = blk - ctl.lag;
+    if (threadIdx.x == 0) {
+      // bounded wait (~seconds): a lost producer must end as an error, never as a hung GPU
+      unsigned spins = 0;
+      while (ld_acquire_u32(ctl.sync + 1 + c) < CT) {
+        __nanosleep(128);
+        if (++spins > (1u << 24)) __trap();
+      }
+    }
+    __syncthreads();
+    g_tile<UNI>(PG, cf, T, (size_t)c * CT + (r - CT));
   }
 }
 
@@ -298,7 +366,101 @@ void set_attrs() {
   PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
   PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
   PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_ag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_ag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
   g_attr_set[dev] = true;
+}
+
+// Ticket + per-chunk counters of the dataflow launches, one buffer per (device, stream): launches on one
+// stream are ordered, launches on different streams must not share counters.
+constexpr unsigned kMaxChunks = 1u << 16;
+unsigned* ag_sync_buffer(cudaStream_t s) {
+  static std::mutex mu;
+  static std::map<std::pair<int, cudaStream_t>, unsigned*> bufs;
+  const int dev = current_device();
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = bufs.find({dev, s});
+  if (it != bufs.end()) return it->second;
+  unsigned* p = nullptr;
+  PD_CUDA_CHECK(cudaMalloc(&p, sizeof(unsigned) * (kMaxChunks + 1)));
+  bufs[{dev, s}] = p;
+  return p;
+}
+bool fuse_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("PD_STREAM_FUSE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
+// the strided groups of the bits above the contiguous tile: group gi takes bits [lo, lo + nb)
+struct Groups {
+  int G;
+  int lo[8], nb[8];
+};
+Groups make_groups(int nq) {
+  Groups gr{};
+  const int rest = nq - TB;
+  gr.G = (rest + kMaxGroupBits - 1) / kMaxGroupBits;
+  int lo = TB;
+  for (int gi = 0; gi < gr.G; ++gi) {
+    gr.lo[gi] = lo;
+    gr.nb[gi] = rest / gr.G + (gi < rest % gr.G ? 1 : 0);
+    lo += gr.nb[gi];
+  }
+  return gr;
+}
+
+struct ErrTail {   // embedded error estimate, finished by the LAST group launch of stage 7
+  cplx* aux;
+  const cplx* y0;
+  double werr, atol, rtol;
+  double* err_partial;
+};
+
+// One stage: out = H_A Y (A launch; Y formed from A.v / written to A.ymat) then out += H_g ysrc per group.
+// The A launch and the first group launch go out as one dataflow launch (see k_stream_ag).
+int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf, bool uni, const cplx* ysrc,
+                 const ErrTail* tail, cudaStream_t s) {
+  const size_t n_tiles = (g.dim >> TB) * (size_t)g.batch;
+  const unsigned grid = (unsigned)n_tiles;
+  const Groups gr = make_groups(g.nq);
+  StreamParams B[8];
+  for (int gi = 0; gi < gr.G; ++gi) {
+    StreamParams& b = B[gi];
+    b = StreamParams{};
+    b.nq = g.nq; b.dim = g.dim; b.n_in = 1; b.v[0] = ysrc; b.w[0] = 1.0; b.out = A.out;
+    b.lo = gr.lo[gi]; b.nb = gr.nb[gi]; b.C = TB - gr.nb[gi];
+    if (tail && gi == gr.G - 1) {
+      b.aux = tail->aux; b.y0 = tail->y0; b.werr = tail->werr; b.atol = tail->atol; b.rtol = tail->rtol;
+      b.err_partial = tail->err_partial;
+    }
+  }
+  int n = 0, first = 0;
+  const unsigned tiles_per_vec = (unsigned)(g.dim >> TB);
+  unsigned chunk_log2 = 0;
+  while ((1u << (chunk_log2 + 1)) <= tiles_per_vec && chunk_log2 < 8) ++chunk_log2;
+  const size_t n_chunks = n_tiles >> chunk_log2;
+  if (fuse_enabled() && gr.G >= 1 && (unsigned)gr.nb[0] <= chunk_log2 && n_chunks <= kMaxChunks) {
+    AgCtl ctl{ag_sync_buffer(s), chunk_log2, (unsigned)n_chunks, 1u};
+    PD_CUDA_CHECK(cudaMemsetAsync(ctl.sync, 0, sizeof(unsigned) * (n_chunks + 1), s));
+    const unsigned ag_grid = (unsigned)(2 * (n_tiles + ((size_t)ctl.lag << chunk_log2)));
+    if (uni) k_stream_ag<true><<<ag_grid, NT, TILE * 16, s>>>(A, B[0], cf, ctl);
+    else k_stream_ag<false><<<ag_grid, NT, TILE * 16, s>>>(A, B[0], cf, ctl);
+    n = 1;
+    first = 1;
+  } else {
+    if (uni) k_stream_a<true><<<grid, NT, TILE * 16, s>>>(A, cf);
+    else k_stream_a<false><<<grid, NT, TILE * 16, s>>>(A, cf);
+    n = 1;
+  }
+  for (int gi = first; gi < gr.G; ++gi) {
+    if (uni) k_stream_g<true><<<grid, NT, TILE * 16, s>>>(B[gi], cf);
+    else k_stream_g<false><<<grid, NT, TILE * 16, s>>>(B[gi], cf);
+    ++n;
+  }
+  return n;
 }
 
 }  // namespace
@@ -318,7 +480,6 @@ int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, 
   StreamCoef cf;
   fill_coef(so, g.nq, cf);
   const bool uni = uniform_drive(cf, g.nq);
-  const unsigned grid = (unsigned)((g.dim >> TB) * (size_t)g.batch);
   // a plain application (one input, weight 1) needs no materialised combination
   const bool plain = n_in == 1 && w[0] == 1.0 && ymat == nullptr;
   const cplx* ysrc = plain ? ins[0] : ymat;
@@ -326,22 +487,7 @@ int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, 
   StreamParams A{};
   A.nq = g.nq; A.dim = g.dim; A.n_in = n_in; A.diag = g.diag; A.ymat = plain ? nullptr : ymat; A.out = out;
   for (int j = 0; j < n_in; ++j) { A.v[j] = ins[j]; A.w[j] = w[j]; }
-  if (uni) k_stream_a<true><<<grid, NT, TILE * 16, s>>>(A, cf);
-  else k_stream_a<false><<<grid, NT, TILE * 16, s>>>(A, cf);
-  int n = 1;
-  const int rest = g.nq - TB;
-  const int G = (rest + kMaxGroupBits - 1) / kMaxGroupBits;
-  int lo = TB;
-  for (int gi = 0; gi < G; ++gi) {
-    const int nb = rest / G + (gi < rest % G ? 1 : 0);
-    StreamParams B{};
-    B.nq = g.nq; B.dim = g.dim; B.n_in = 1; B.v[0] = ysrc; B.w[0] = 1.0; B.out = out;
-    B.lo = lo; B.nb = nb; B.C = TB - nb;
-    if (uni) k_stream_g<true><<<grid, NT, TILE * 16, s>>>(B, cf);
-    else k_stream_g<false><<<grid, NT, TILE * 16, s>>>(B, cf);
-    lo += nb;
-    ++n;
-  }
+  const int n = launch_stage(g, A, cf, uni, ysrc, nullptr, s);
   PD_CUDA_CHECK(cudaGetLastError());
   return n;
 }
@@ -623,9 +769,6 @@ int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cpl
                            const double* ew, double dt, double atol, double rtol, double* err_partial,
                            double* err_out, cudaStream_t s) {
   set_attrs();
-  const unsigned grid = (unsigned)((g.dim >> TB) * (size_t)g.batch);
-  const int rest = g.nq - TB;
-  const int G = (rest + kMaxGroupBits - 1) / kMaxGroupBits;
   int n = 0;
   for (int i = 1; i < 7; ++i) {
     StreamCoef cf;
@@ -643,23 +786,8 @@ int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cpl
     }
     A.n_in = m;
     A.aux = last ? aux : nullptr;
-    if (uni) k_stream_a<true><<<grid, NT, TILE * 16, s>>>(A, cf);
-    else k_stream_a<false><<<grid, NT, TILE * 16, s>>>(A, cf);
-    ++n;
-    int lo = TB;
-    for (int gi = 0; gi < G; ++gi) {
-      const int nb = rest / G + (gi < rest % G ? 1 : 0);
-      StreamParams B{};
-      B.nq = g.nq; B.dim = g.dim; B.n_in = 1; B.v[0] = ym; B.w[0] = 1.0; B.out = k[i];
-      B.lo = lo; B.nb = nb; B.C = TB - nb;
-      if (last && gi == G - 1) {
-        B.aux = aux; B.y0 = y; B.werr = ew[6]; B.atol = atol; B.rtol = rtol; B.err_partial = err_partial;
-      }
-      if (uni) k_stream_g<true><<<grid, NT, TILE * 16, s>>>(B, cf);
-      else k_stream_g<false><<<grid, NT, TILE * 16, s>>>(B, cf);
-      lo += nb;
-      ++n;
-    }
+    const ErrTail tail{aux, y, ew[6], atol, rtol, err_partial};
+    n += launch_stage(g, A, cf, uni, ym, last ? &tail : nullptr, s);
   }
   k_stream_sum_partials<<<g.batch, 256, 0, s>>>(err_partial, (int)(g.dim >> TB), err_out);
   PD_CUDA_CHECK(cudaGetLastError());

@@ -163,26 +163,34 @@ class SequenceSamples:
         return SequenceSamples(out)
 
     def to_nested_dict(self, qubit_ids: Sequence, all_local: bool = False) -> dict:
-        """{"Global": {basis: {amp,det,phase}}, "Local": {basis: {qid: {...}}}} summed over
-        channels, as ``to_nested_dict(all_local, samples_type="tensor")`` gives the reference
-        (hamiltonian.py:177).  Any Local channel (or ``all_local``) expands Global ones."""
+        """{"Global": {basis: {amp,det,phase}}, "Local": {basis: {qid: {...}}}} as Pulser's
+        ``to_nested_dict(all_local, samples_type="tensor")`` gives the reference
+        (hamiltonian.py:177).  Global channels stay under "Global" (summed per basis) unless
+        ``all_local``; Local channels are accumulated per target qubit inside each pulse slot
+        ``[ti:tf]``.  The two groups are SEPARATE Hamiltonian terms (hamiltonian.py:478-481): a
+        qubit driven by both sees ``0.5 a_g e^{-i ph_g} + 0.5 a_l e^{-i ph_l}``."""
         d = self.max_duration
-        any_local = all_local or any(c.addressing == "Local" for c in self.channels)
         res: dict = {"Global": {}, "Local": {}}
 
         def zero():
             return {k: torch.zeros(d, dtype=F64) for k in ("amp", "det", "phase")}
 
+        def padded(x: Tensor) -> Tensor:
+            return x if x.numel() == d else torch.cat([x, torch.zeros(d - x.numel(), dtype=F64)])
+
         for c in self.channels:
-            if c.addressing == "Global" and not any_local:
+            if c.addressing == "Global" and not all_local:
                 dst = res["Global"].setdefault(c.basis, zero())
                 for k in ("amp", "det", "phase"):
-                    dst[k] = dst[k] + getattr(c, k)
-            else:
-                targets = list(qubit_ids) if c.addressing == "Global" else list(c.targets or [])
-                per = res["Local"].setdefault(c.basis, {})
-                for q in targets:
+                    dst[k] = dst[k] + padded(getattr(c, k))
+                continue
+            everyone = list(qubit_ids) if c.addressing == "Global" else list(c.targets or [])
+            per = res["Local"].setdefault(c.basis, {})
+            for slot in (c.slots or [Slot(0, c.duration, set(everyone))]):
+                window = torch.zeros(d, dtype=F64)
+                window[slot.ti:slot.tf] = 1.0
+                for q in (slot.targets or everyone):
                     dst = per.setdefault(q, zero())
                     for k in ("amp", "det", "phase"):
-                        dst[k] = dst[k] + getattr(c, k)
+                        dst[k] = dst[k] + padded(getattr(c, k)) * window
         return res

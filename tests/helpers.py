@@ -53,20 +53,17 @@ class Problem:
             return {"amp": torch.cat([c.amp, z]), "det": torch.cat([c.det, z]),
                     "phase": torch.cat([c.phase, c.phase[-1:].detach()])}
 
-        any_local = any(c.addressing == "Local" for c in self.channels)
+        # Global and Local channels are SEPARATE terms (reference hamiltonian.py:177, 478-481)
         samples: dict = {}
-        if not any_local:
-            acc = None
-            for c in self.channels:
-                e = ext(c)
-                acc = e if acc is None else {k: acc[k] + e[k] for k in e}
-            samples["Global"] = acc
-        else:
-            per: dict = {}
-            for c in self.channels:
-                e = ext(c)
-                for q in (range(self.n) if c.addressing == "Global" else [c.target]):
-                    per[q] = e if q not in per else {k: per[q][k] + e[k] for k in e}
+        per: dict = {}
+        for c in self.channels:
+            e = ext(c)
+            if c.addressing == "Global":
+                samples["Global"] = e if "Global" not in samples else \
+                    {k: samples["Global"][k] + e[k] for k in e}
+            else:
+                per[c.target] = e if c.target not in per else {k: per[c.target][k] + e[k] for k in e}
+        if per:
             samples["Local"] = per
         return RefEmulator(self.coords, self.c6, samples, rate=self.rate, noise=self.noise,
                            evaluation_times=self.evaluation_times)

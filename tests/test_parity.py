@@ -47,6 +47,42 @@ def test_hpsi_matches_sparse_matrix(engine_device):
             torch.tensor(t, dtype=torch.float64)).to_dense()).abs().max() < 1e-12
 
 
+def test_global_plus_local_channels_are_separate_terms(engine_device):
+    """A qubit addressed by a Global AND a Local channel sees the sum of the two drive terms,
+    0.5 a_g e^{-i ph_g} + 0.5 a_l e^{-i ph_l} (reference hamiltonian.py:177 keeps the two dicts apart
+    and :478-481 adds one term per dict), not one term with summed amplitudes and phases.
+    Checked against a dense H written out by hand, for the engine, its compatibility closure and the
+    oracle."""
+    from helpers import Channel, C6_60
+    T = 50
+    one = torch.ones(T, dtype=torch.float64)
+    coords = torch.tensor([[0.0, 0.0], [7.0, 0.0]], dtype=torch.float64)
+    p = Problem(coords, C6_60, [Channel(2.0 * one, 0.4 * one, 0.5 * one),
+                                Channel(1.0 * one, -0.7 * one, 0.3 * one, "Local", 0)], rate=1.0)
+    # by hand, basis (r, g), qubit 0 = most significant bit
+    n_op = torch.tensor([[1, 0], [0, 0]], dtype=torch.complex128)
+    sig_gr = torch.tensor([[0, 0], [1, 0]], dtype=torch.complex128)
+    eye = torch.eye(2, dtype=torch.complex128)
+    on = [lambda o: torch.kron(o, eye), lambda o: torch.kron(eye, o)]
+    u = C6_60 / 7.0 ** 6
+    H = u * torch.kron(n_op, n_op)
+    for q in range(2):
+        c = 0.5 * 2.0 * torch.exp(torch.tensor(-0.5j, dtype=torch.complex128))
+        H = H + c * on[q](sig_gr) + c.conj() * on[q](sig_gr).mH - 0.4 * on[q](n_op)
+    c = 0.5 * 1.0 * torch.exp(torch.tensor(-0.3j, dtype=torch.complex128))
+    H = H + c * on[0](sig_gr) + c.conj() * on[0](sig_gr).mH + 0.7 * on[0](n_op)
+    t = 0.0213
+    assert (p.ref().ham.H(torch.tensor(t, dtype=torch.float64)).to_dense() - H).abs().max() < 1e-12
+    em = p.emulator(engine_device)
+    Hs = em._hamiltonian._hamiltonian
+    assert (Hs(torch.tensor(t, dtype=torch.float64)).to_dense() - H).abs().max() < 1e-12
+    dm, dv, am, av = Hs.masks_and_values()
+    psi = torch.randn(2, 4, dtype=torch.complex128, generator=torch.Generator().manual_seed(4))
+    got = torch.ops.pulser_diff_b200.hpsi(psi.to(engine_device), t, dv, av, Hs.pair_u.detach(), dm, am,
+                                          Hs.dt).cpu()
+    assert (got - (H @ psi.T).T).abs().max() < 1e-12
+
+
 @pytest.mark.parametrize("name", ["K-A", "K-B", "K-C", "K-D", "K-E", "K-F", "K-G"])
 def test_notebook_kats_through_emulator(engine_device, name):
     p = kat_problem(name)
