@@ -39,12 +39,14 @@ constexpr int EPT = TILE / NT;   // 16
 constexpr int kMaxIn = 8;
 constexpr int kMaxGroupBits = 8;
 
+// Every generator the engine applies is kappa * H with H Hermitian (kappa = 1, -i or +i; pd_common.hpp
+// site_ops_ket), so the tiles accumulate h = H Y with a REAL diagonal and conjugate-paired flips and scale
+// once: per flip 2 FMAs when the drive has no phase (REAL), 4 otherwise.
 struct StreamCoef {
-  cplx kappa;                 // scale of the static diagonal (A launch)
-  cplx t00[kMaxQubits];       // per GLOBAL bit position: diagonal entry for bit value 0 / 1
-  cplx t11[kMaxQubits];
-  cplx t01[kMaxQubits];       // row a=0 <- a'=1
-  cplx t10[kMaxQubits];       // row a=1 <- a'=0
+  cplx kappa;
+  double d[kMaxQubits];       // per GLOBAL bit position p: diagonal entry of H for bit value 0 (|r>)
+  double gre[kMaxQubits];     // flip entry of H, row bit 1 <- partner bit 0: g = gre + i gim;
+  double gim[kMaxQubits];     //                  row bit 0 <- partner bit 1: conj(g)
 };
 
 struct StreamParams {
@@ -64,7 +66,7 @@ struct StreamParams {
   cplx* aux;                  // A: written (nullable);  g: read when err_partial != null
   const cplx* y0;
   double werr, atol, rtol;
-  double* err_partial;        // [gridDim.x] (g launch, nullable)
+  double* err_partial;        // [n_tiles] (g launch, nullable)
 };
 
 __device__ __forceinline__ cplx ldcs(const cplx* p) {
@@ -72,28 +74,29 @@ __device__ __forceinline__ cplx ldcs(const cplx* p) {
   return {v.x, v.y};
 }
 
-// ---- A launch: contiguous tile, combination + diagonal + low-bit flips ---------------------------
-template <bool UNI>
+// h += (gre + i*s) * pv  (REAL: s == 0)
+template <bool REAL>
+__device__ __forceinline__ void flip_acc(cplx& h, double gre, double s, cplx pv) {
+  h.re = fma(gre, pv.re, h.re);
+  h.im = fma(gre, pv.im, h.im);
+  if (!REAL) {
+    h.re = fma(-s, pv.im, h.re);
+    h.im = fma(s, pv.re, h.im);
+  }
+}
+
+// ---- A tile: contiguous 4096 amplitudes; combination + diagonal + flips of the low 12 bits -----------
+// Thread t owns elements e = t + 256 i (i < 16): tile bits 0-7 come from t, bits 8-11 from i.  The partner
+// of a flip on bit lb < 8 lives at a per-thread base pointer + a compile-time offset; on bit lb >= 8 it is
+// one of the thread's own elements; the sign of the flip's imaginary part (bit value of e) is per thread
+// (lb < 8) or a compile-time constant (lb >= 8): no per-element index arithmetic or selects.
+template <bool REAL>
 __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t lin_tile) {
-  __shared__ cplx tab[2][64];
   const int t = threadIdx.x;
   const int nq = P.nq;
   const size_t tiles_per_vec = P.dim >> TB;
   const size_t tile = lin_tile % tiles_per_vec;
   const size_t base = (lin_tile / tiles_per_vec) * P.dim + (tile << TB);   // batch column + tile
-
-  // detuning-diagonal tables over local bits 0-5 / 6-11; bits above the tile are constant per tile
-  if (t < 128) {
-    const int half = t >> 6, x = t & 63;
-    cplx s{0, 0};
-    for (int b = 0; b < 6; ++b) {
-      const int gb = half * 6 + b;
-      if (gb < nq) s = s + (((x >> b) & 1) ? cf.t11[gb] : cf.t00[gb]);
-    }
-    tab[half][x] = s;
-  }
-  cplx hi{0, 0};
-  for (int gb = TB; gb < nq; ++gb) hi = hi + (((tile >> (gb - TB)) & 1) ? cf.t11[gb] : cf.t00[gb]);
 
   // ---- combination: Y = sum_j w_j v_j, 4 elements x 2 vectors in flight per thread
   constexpr int QP = 4;
@@ -146,49 +149,58 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
       if (want_aux) P.aux[base + t + NT * (q0 + i)] = z[i];
     }
   }
+
+  // per-thread constants of the second phase (computed while the loads above drain)
+  const cplx* Tt = T + t;
+  const cplx* Tp[8];
+  double sg[8];
+  double dthr = 0.0;          // diagonal of the bits this thread's elements share: tile bits 0-7 and the bits above the tile
+#pragma unroll
+  for (int lb = 0; lb < 8; ++lb) {
+    const bool a = (t >> lb) & 1;
+    Tp[lb] = T + (t ^ (1 << lb));
+    sg[lb] = a ? cf.gim[lb] : -cf.gim[lb];
+    dthr += a ? 0.0 : cf.d[lb];
+  }
+  for (int gb = TB; gb < nq; ++gb) dthr += ((tile >> (gb - TB)) & 1) ? 0.0 : cf.d[gb];
+  const double* dg_ptr = P.diag + (tile << TB) + t;
   __syncthreads();
 
-  // ---- out = (kappa*Dint + detuning diagonal) Y + low-bit flips
-  const int nl = nq < TB ? nq : TB;
+  // ---- out = kappa * ( (Dint + detuning diagonal) Y + low-bit flips )
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
-    const int e = t + NT * i;
-    const double dg = __ldg(P.diag + (tile << TB) + e);
-    cplx o{0.0, 0.0};
-    if (UNI) {
-      cplx S{0.0, 0.0}, L{0.0, 0.0};
+    const double dg = __ldg(dg_ptr + NT * i);
+    cplx h{0.0, 0.0};
 #pragma unroll
-      for (int lb = 0; lb < TB; ++lb) {
-        if (lb >= nl) break;
-        const cplx pv = T[e ^ (1 << lb)];
-        const bool a = (e >> lb) & 1;
-        S.re += pv.re; S.im += pv.im;
-        L.re += a ? pv.re : 0.0; L.im += a ? pv.im : 0.0;
-      }
-      fma_acc(o, cf.t10[0], L);
-      fma_acc(o, cf.t01[0], cplx{S.re - L.re, S.im - L.im});
-    } else {
+    for (int lb = 0; lb < 8; ++lb) flip_acc<REAL>(h, cf.gre[lb], sg[lb], Tp[lb][NT * i]);
 #pragma unroll
-      for (int lb = 0; lb < TB; ++lb) {
-        if (lb >= nl) break;
-        const bool a = (e >> lb) & 1;
-        fma_acc(o, a ? cf.t10[lb] : cf.t01[lb], T[e ^ (1 << lb)]);
-      }
+    for (int k = 0; k < 4; ++k) {
+      const bool a = (i >> k) & 1;
+      flip_acc<REAL>(h, cf.gre[8 + k], a ? cf.gim[8 + k] : -cf.gim[8 + k], Tt[NT * (i ^ (1 << k))]);
     }
-    const cplx ds = cplx{cf.kappa.re * dg, cf.kappa.im * dg} + hi + tab[0][e & 63] + tab[1][(e >> 6) & 63];
-    fma_acc(o, ds, T[e]);
-    P.out[base + e] = o;
+    double dd = dthr + dg;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (!((i >> k) & 1)) dd += cf.d[8 + k];
+    const cplx own = Tt[NT * i];
+    h.re = fma(dd, own.re, h.re);
+    h.im = fma(dd, own.im, h.im);
+    P.out[base + t + NT * i] = cf.kappa * h;
   }
 }
 
-template <bool UNI>
-__global__ void __launch_bounds__(NT, 3)
+template <bool REAL>
+__global__ void __launch_bounds__(NT, REAL ? 3 : 2)
 k_stream_a(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  a_tile<UNI>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
+  a_tile<REAL>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
 }
 
-// ---- group launch: strided tile, out += H_g Ymat ---------------------------------------------------
+// ---- group tile: strided tile (2^nb rows x 2^C columns), out += kappa * H_g Ymat ------------------------
+// Tile element e = col | row << C; thread t owns e = t + 256 i, so consecutive elements of a thread are
+// 2^(8-C) rows apart: their global indices are g0 + i * stride.  The row bits split into tile bits [C, 8)
+// (partner = another thread's element, same i: per-thread pointer, runtime count 8 - C <= 4) and tile bits
+// 8-11 (partner = the thread's own element i ^ 2^k).
 __device__ __forceinline__ size_t gindex(const StreamParams& P, size_t tile, int e) {
   const size_t col = (size_t)(e & ((1 << P.C) - 1)), row = (size_t)(e >> P.C);
   const int lw = P.lo - P.C;                       // tile-index bits placed below the row bits
@@ -196,68 +208,73 @@ __device__ __forceinline__ size_t gindex(const StreamParams& P, size_t tile, int
   return col | (ul << P.C) | (row << P.lo) | (uh << (P.lo + P.nb));
 }
 
-template <bool UNI>
+template <bool REAL>
 __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t lin_tile) {
   const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
   const size_t tile = lin_tile % tiles_per_vec;
   const size_t boff = (lin_tile / tiles_per_vec) * P.dim;
-  const cplx* ym = P.v[0] + boff;
-  cplx* out = P.out + boff;
-  const int C = P.C, nb = P.nb;
+  const int C = P.C;
+  const size_t g0 = boff + gindex(P, tile, t);
+  const size_t stride = (size_t)1 << (P.lo + 8 - C);
+  const cplx* ym = P.v[0] + g0;
+  cplx* out = P.out + g0;
 
   // Ymat tile -> shared memory (8 x 16 B in flight per thread)
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += 8) {
     cplx x[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = ldcs(ym + gindex(P, tile, t + NT * (q0 + i)));
+    for (int i = 0; i < 8; ++i) x[i] = ldcs(ym + (size_t)(q0 + i) * stride);
 #pragma unroll
     for (int i = 0; i < 8; ++i) T[t + NT * (q0 + i)] = x[i];
   }
+  const cplx* Tt = T + t;
+  const int n_cross = 8 - C;                       // 0..4 row bits that live in t
+  const int p8 = P.lo + n_cross;                   // global bit position of tile bit 8
+  double gre8[4], gim8[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) { gre8[k] = cf.gre[p8 + k]; gim8[k] = cf.gim[p8 + k]; }
   __syncthreads();
   double err_acc = 0.0;
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += 4) {
-    size_t gi[4];
-    cplx acc[4];
+    cplx acc[4], h[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      gi[i] = gindex(P, tile, t + NT * (q0 + i));
-      acc[i] = ldcs(out + gi[i]);
+    for (int j = 0; j < 4; ++j) {
+      acc[j] = ldcs(out + (size_t)(q0 + j) * stride);
+      h[j] = {0.0, 0.0};
+    }
+    for (int b = 0; b < n_cross; ++b) {
+      const int lb = C + b;
+      const bool a = (t >> lb) & 1;
+      const cplx* Tq = T + (t ^ (1 << lb));
+      const double gr = cf.gre[P.lo + b];
+      const double s = a ? cf.gim[P.lo + b] : -cf.gim[P.lo + b];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) flip_acc<REAL>(h[j], gr, s, Tq[NT * (q0 + j)]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int e = t + NT * (q0 + i);
-      if (UNI) {
-        cplx S{0.0, 0.0}, L{0.0, 0.0};
-        for (int b = 0; b < nb; ++b) {
-          const int lb = C + b;
-          const cplx pv = T[e ^ (1 << lb)];
-          const bool a = (e >> lb) & 1;
-          S.re += pv.re; S.im += pv.im;
-          L.re += a ? pv.re : 0.0; L.im += a ? pv.im : 0.0;
-        }
-        fma_acc(acc[i], cf.t10[P.lo], L);
-        fma_acc(acc[i], cf.t01[P.lo], cplx{S.re - L.re, S.im - L.im});
-      } else {
-        for (int b = 0; b < nb; ++b) {
-          const int lb = C + b;
-          const bool a = (e >> lb) & 1;
-          fma_acc(acc[i], a ? cf.t10[P.lo + b] : cf.t01[P.lo + b], T[e ^ (1 << lb)]);
-        }
+    for (int j = 0; j < 4; ++j) {
+      const int i = q0 + j;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool a = (i >> k) & 1;
+        flip_acc<REAL>(h[j], gre8[k], a ? gim8[k] : -gim8[k], Tt[NT * (i ^ (1 << k))]);
       }
+      fma_acc(acc[j], cf.kappa, h[j]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) out[gi[i]] = acc[i];
+    for (int j = 0; j < 4; ++j) out[(size_t)(q0 + j) * stride] = acc[j];
     if (P.err_partial) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const cplx ep = ldcs(P.aux + boff + gi[i]);
-        const cplx y0 = ldcs(P.y0 + boff + gi[i]);
-        const cplx y1 = T[t + NT * (q0 + i)];
+      for (int j = 0; j < 4; ++j) {
+        const size_t gi = g0 + (size_t)(q0 + j) * stride;
+        const cplx ep = ldcs(P.aux + gi);
+        const cplx y0 = ldcs(P.y0 + gi);
+        const cplx y1 = Tt[NT * (q0 + j)];
         const double sc = P.atol + P.rtol * fmax(hypot(y0.re, y0.im), hypot(y1.re, y1.im));
-        const double er = fma(P.werr, acc[i].re, ep.re) / sc, ei = fma(P.werr, acc[i].im, ep.im) / sc;
+        const double er = fma(P.werr, acc[j].re, ep.re) / sc, ei = fma(P.werr, acc[j].im, ep.im) / sc;
         err_acc += er * er + ei * ei;
       }
     }
@@ -276,11 +293,11 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
   }
 }
 
-template <bool UNI>
-__global__ void __launch_bounds__(NT, 3)
+template <bool REAL>
+__global__ void __launch_bounds__(NT, REAL ? 3 : 2)
 k_stream_g(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  g_tile<UNI>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
+  g_tile<REAL>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
 }
 
 // ---- dataflow launch: A tiles and the first group's tiles, chunk by chunk through L2 --------------------
@@ -300,8 +317,8 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 
-template <bool UNI>
-__global__ void __launch_bounds__(NT, 3)
+template <bool REAL>
+__global__ void __launch_bounds__(NT, REAL ? 3 : 2)
 k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ StreamParams PG,
             const __grid_constant__ StreamCoef cf, const AgCtl ctl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -314,7 +331,7 @@ k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ Str
   const unsigned blk = item >> (ctl.chunk_log2 + 1), r = item & (2 * CT - 1);
   if (r < CT) {
     if (blk >= ctl.n_chunks) return;
-    a_tile<UNI>(PA, cf, T, (size_t)blk * CT + r);
+    a_tile<REAL>(PA, cf, T, (size_t)blk * CT + r);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicAdd(ctl.sync + 1 + blk, 1u);
@@ -330,25 +347,30 @@ k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ Str
       }
     }
     __syncthreads();
-    g_tile<UNI>(PG, cf, T, (size_t)c * CT + (r - CT));
+    g_tile<REAL>(PG, cf, T, (size_t)c * CT + (r - CT));
   }
 }
 
+// SiteOps holds kappa * H per qubit (pd_common.hpp site_ops_ket): recover the Hermitian entries.  kappa is
+// 1 or +-i, so multiplying by conj(kappa) is exact.
 void fill_coef(const SiteOps& so, int nq, StreamCoef& c) {
   c.kappa = so.kappa;
+  const cplx kc = conj(so.kappa);
+  const double k2 = so.kappa.re * so.kappa.re + so.kappa.im * so.kappa.im;
+  if (k2 != 1.0) throw Error(PD_ERR_STATE, "stream kernels expect a unit-modulus generator scale");
   for (int q = 0; q < nq; ++q) {
     const int p = nq - 1 - q;   // global bit position of qubit q
-    c.t00[p] = so.T[q * 4 + 0];
-    c.t01[p] = so.T[q * 4 + 1];
-    c.t10[p] = so.T[q * 4 + 2];
-    c.t11[p] = so.T[q * 4 + 3];
+    const cplx d = kc * so.T[q * 4 + 0], g = kc * so.T[q * 4 + 2], gc = kc * so.T[q * 4 + 1];
+    if (d.im != 0.0 || g.re != gc.re || g.im != -gc.im || so.T[q * 4 + 3].re != 0.0 || so.T[q * 4 + 3].im != 0.0)
+      throw Error(PD_ERR_STATE, "stream kernels expect kappa * (Hermitian site operators)");
+    c.d[p] = d.re;
+    c.gre[p] = g.re;
+    c.gim[p] = g.im;
   }
 }
-bool uniform_drive(const StreamCoef& a, int nq) {
-  for (int p = 1; p < nq; ++p)
-    if (a.t01[p].re != a.t01[0].re || a.t01[p].im != a.t01[0].im || a.t10[p].re != a.t10[0].re ||
-        a.t10[p].im != a.t10[0].im)
-      return false;
+bool real_drive(const StreamCoef& a, int nq) {
+  for (int p = 0; p < nq; ++p)
+    if (a.gim[p] != 0.0) return false;
   return true;
 }
 
@@ -479,7 +501,7 @@ int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, 
   set_attrs();
   StreamCoef cf;
   fill_coef(so, g.nq, cf);
-  const bool uni = uniform_drive(cf, g.nq);
+  const bool uni = real_drive(cf, g.nq);
   // a plain application (one input, weight 1) needs no materialised combination
   const bool plain = n_in == 1 && w[0] == 1.0 && ymat == nullptr;
   const cplx* ysrc = plain ? ins[0] : ymat;
@@ -773,7 +795,7 @@ int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cpl
   for (int i = 1; i < 7; ++i) {
     StreamCoef cf;
     fill_coef(stage_ops[i], g.nq, cf);
-    const bool uni = uniform_drive(cf, g.nq);
+    const bool uni = real_drive(cf, g.nq);
     const bool last = i == 6;
     cplx* ym = last ? ynew : ymat;
     StreamParams A{};

@@ -79,13 +79,36 @@ def test_norm_conservation_and_fd_gradient(cuda_device, n):
         assert abs(fd.item() - g[0, idx].real.item()) < 1e-6 * abs(fd.item()) + 1e-9
 
 
-@pytest.mark.parametrize("n,other", [(16, 2), (18, 2), (21, 2), (22, 2), (23, 2),
-                                     (16, 4), (19, 4), (21, 4), (24, 4), (26, 4)])
-def test_tiled_equals_gather(cuda_device, n, other):
+def _vary_drive(pr, n, drive):
+    """"complex": one global drive with a phase (general flip arithmetic); "real": phase-free global
+    drive (the two-FMA flip path); "local": global terms plus per-qubit drives / detunings on a few
+    qubits spread over the low, middle and high bit groups (non-uniform coefficients)."""
+    if drive == "real":
+        pr["amp_values"] = torch.complex(pr["amp_values"].real, torch.zeros_like(pr["amp_values"].real))
+    elif drive == "local":
+        g = torch.Generator().manual_seed(9)
+        T = pr["det_values"].shape[1]
+        qs = [0, n // 2, n - 1]
+        pr["det_masks"] = pr["det_masks"] + [1 << q for q in qs]
+        pr["amp_masks"] = pr["amp_masks"] + [1 << q for q in qs]
+        pr["det_values"] = torch.cat([pr["det_values"], torch.rand(3, T, dtype=torch.float64, generator=g)])
+        pr["amp_values"] = torch.cat([pr["amp_values"],
+                                      torch.complex(torch.rand(3, T, dtype=torch.float64, generator=g),
+                                                    torch.rand(3, T, dtype=torch.float64, generator=g) - 0.5)])
+    return pr
+
+
+@pytest.mark.parametrize("n,other,drive", [(16, 2, "complex"), (18, 2, "complex"), (21, 2, "complex"),
+                                           (22, 2, "complex"), (23, 2, "complex"),
+                                           (16, 4, "complex"), (19, 4, "complex"), (21, 4, "complex"),
+                                           (24, 4, "complex"), (26, 4, "complex"),
+                                           (16, 4, "real"), (17, 4, "local"), (20, 4, "real"), (21, 4, "local"),
+                                           (22, 4, "real"), (24, 4, "local"), (25, 4, "real")])
+def test_tiled_equals_gather(cuda_device, n, other, drive):
     """The tiled kernels (path 2: fused DP5 step, two-launch stage, adjoint sweep) and the stream
-    kernels (path 4: one bit-group of H per launch) against the gather kernels (path 1) on the same
-    inputs: states, H.psi and gradients."""
-    pr = _program(n, T=16)
+    kernels (path 4: one bit-group of H per launch, A + first group as one L2-blocked dataflow launch)
+    against the gather kernels (path 1) on the same inputs: states, H.psi and gradients."""
+    pr = _vary_drive(_program(n, T=16), n, drive)
     dev = cuda_device
     nb = 2 if n <= 23 else 1
     psi0 = torch.randn(nb, 2 ** n, dtype=torch.complex128, generator=torch.Generator().manual_seed(5)).to(dev)
