@@ -74,6 +74,14 @@ __device__ __forceinline__ cplx ldcs(const cplx* p) {
   return {v.x, v.y};
 }
 
+// CTA barrier of a tile routine: every thread of the CTA (NBAR = 0), or the NBAR consumer threads of the
+// persistent kernel (named barrier 1; its producer warp does not take part).
+template <int NBAR>
+__device__ __forceinline__ void tile_sync() {
+  if (NBAR == 0) __syncthreads();
+  else asm volatile("bar.sync 1, %0;" ::"n"(NBAR) : "memory");
+}
+
 // h += (gre + i*s) * pv  (REAL: s == 0)
 template <bool REAL>
 __device__ __forceinline__ void flip_acc(cplx& h, double gre, double s, cplx pv) {
@@ -90,17 +98,61 @@ __device__ __forceinline__ void flip_acc(cplx& h, double gre, double s, cplx pv)
 // of a flip on bit lb < 8 lives at a per-thread base pointer + a compile-time offset; on bit lb >= 8 it is
 // one of the thread's own elements; the sign of the flip's imaginary part (bit value of e) is per thread
 // (lb < 8) or a compile-time constant (lb >= 8): no per-element index arithmetic or selects.
-template <bool REAL>
-__device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t lin_tile) {
+// second phase of an A tile: T holds the combined input Y of the tile (written by this CTA, not yet synced)
+template <bool REAL, int NBAR>
+__device__ __forceinline__ void a_tile_flips(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t tile,
+                                             size_t base) {
   const int t = threadIdx.x;
   const int nq = P.nq;
+  // per-thread constants of the second phase (computed while the loads above drain)
+  const cplx* Tt = T + t;
+  const cplx* Tp[8];
+  double sg[8];
+  double dthr = 0.0;          // diagonal of the bits this thread's elements share: tile bits 0-7 and the bits above the tile
+#pragma unroll
+  for (int lb = 0; lb < 8; ++lb) {
+    const bool a = (t >> lb) & 1;
+    Tp[lb] = T + (t ^ (1 << lb));
+    sg[lb] = a ? cf.gim[lb] : -cf.gim[lb];
+    dthr += a ? 0.0 : cf.d[lb];
+  }
+  for (int gb = TB; gb < nq; ++gb) dthr += ((tile >> (gb - TB)) & 1) ? 0.0 : cf.d[gb];
+  const double* dg_ptr = P.diag + (tile << TB) + t;
+  tile_sync<NBAR>();
+
+  // ---- out = kappa * ( (Dint + detuning diagonal) Y + low-bit flips )
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) {
+    const double dg = __ldg(dg_ptr + NT * i);
+    cplx h{0.0, 0.0};
+#pragma unroll
+    for (int lb = 0; lb < 8; ++lb) flip_acc<REAL>(h, cf.gre[lb], sg[lb], Tp[lb][NT * i]);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const bool a = (i >> k) & 1;
+      flip_acc<REAL>(h, cf.gre[8 + k], a ? cf.gim[8 + k] : -cf.gim[8 + k], Tt[NT * (i ^ (1 << k))]);
+    }
+    double dd = dthr + dg;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (!((i >> k) & 1)) dd += cf.d[8 + k];
+    const cplx own = Tt[NT * i];
+    h.re = fma(dd, own.re, h.re);
+    h.im = fma(dd, own.im, h.im);
+    P.out[base + t + NT * i] = cf.kappa * h;
+  }
+}
+
+template <bool REAL, bool AUX>
+__device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t lin_tile) {
+  const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
   const size_t tile = lin_tile % tiles_per_vec;
   const size_t base = (lin_tile / tiles_per_vec) * P.dim + (tile << TB);   // batch column + tile
 
   // ---- combination: Y = sum_j w_j v_j, 4 elements x 2 vectors in flight per thread
   constexpr int QP = 4;
-  const bool want_aux = P.aux != nullptr;          // uniform
+  constexpr bool want_aux = AUX;                   // the error-estimate vector of the last stage
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += QP) {
     cplx y[QP], z[QP];
@@ -149,51 +201,14 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
       if (want_aux) P.aux[base + t + NT * (q0 + i)] = z[i];
     }
   }
-
-  // per-thread constants of the second phase (computed while the loads above drain)
-  const cplx* Tt = T + t;
-  const cplx* Tp[8];
-  double sg[8];
-  double dthr = 0.0;          // diagonal of the bits this thread's elements share: tile bits 0-7 and the bits above the tile
-#pragma unroll
-  for (int lb = 0; lb < 8; ++lb) {
-    const bool a = (t >> lb) & 1;
-    Tp[lb] = T + (t ^ (1 << lb));
-    sg[lb] = a ? cf.gim[lb] : -cf.gim[lb];
-    dthr += a ? 0.0 : cf.d[lb];
-  }
-  for (int gb = TB; gb < nq; ++gb) dthr += ((tile >> (gb - TB)) & 1) ? 0.0 : cf.d[gb];
-  const double* dg_ptr = P.diag + (tile << TB) + t;
-  __syncthreads();
-
-  // ---- out = kappa * ( (Dint + detuning diagonal) Y + low-bit flips )
-#pragma unroll
-  for (int i = 0; i < EPT; ++i) {
-    const double dg = __ldg(dg_ptr + NT * i);
-    cplx h{0.0, 0.0};
-#pragma unroll
-    for (int lb = 0; lb < 8; ++lb) flip_acc<REAL>(h, cf.gre[lb], sg[lb], Tp[lb][NT * i]);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const bool a = (i >> k) & 1;
-      flip_acc<REAL>(h, cf.gre[8 + k], a ? cf.gim[8 + k] : -cf.gim[8 + k], Tt[NT * (i ^ (1 << k))]);
-    }
-    double dd = dthr + dg;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (!((i >> k) & 1)) dd += cf.d[8 + k];
-    const cplx own = Tt[NT * i];
-    h.re = fma(dd, own.re, h.re);
-    h.im = fma(dd, own.im, h.im);
-    P.out[base + t + NT * i] = cf.kappa * h;
-  }
+  a_tile_flips<REAL, 0>(P, cf, T, tile, base);
 }
 
-template <bool REAL>
+template <bool REAL, bool AUX>
 __global__ void __launch_bounds__(NT, REAL ? 3 : 2)
 k_stream_a(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  a_tile<REAL>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
+  a_tile<REAL, AUX>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
 }
 
 // ---- group tile: strided tile (2^nb rows x 2^C columns), out += kappa * H_g Ymat ------------------------
@@ -208,7 +223,7 @@ __device__ __forceinline__ size_t gindex(const StreamParams& P, size_t tile, int
   return col | (ul << P.C) | (row << P.lo) | (uh << (P.lo + P.nb));
 }
 
-template <bool REAL>
+template <bool REAL, int NBAR>
 __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t lin_tile) {
   const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
@@ -220,30 +235,37 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
   const cplx* ym = P.v[0] + g0;
   cplx* out = P.out + g0;
 
-  // Ymat tile -> shared memory (8 x 16 B in flight per thread)
+  // Ymat tile -> shared memory with 16-byte asynchronous copies (LDGSTS): 16 in flight per thread, no
+  // registers; the first round of the partial result is fetched while they land
 #pragma unroll
-  for (int q0 = 0; q0 < EPT; q0 += 8) {
-    cplx x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = ldcs(ym + (size_t)(q0 + i) * stride);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) T[t + NT * (q0 + i)] = x[i];
+  for (int i = 0; i < EPT; ++i) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(T + t + NT * i);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(ym + (size_t)i * stride) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
   const cplx* Tt = T + t;
   const int n_cross = 8 - C;                       // 0..4 row bits that live in t
   const int p8 = P.lo + n_cross;                   // global bit position of tile bit 8
   double gre8[4], gim8[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) { gre8[k] = cf.gre[p8 + k]; gim8[k] = cf.gim[p8 + k]; }
-  __syncthreads();
+  cplx nxt[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) nxt[j] = ldcs(out + (size_t)j * stride);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  tile_sync<NBAR>();
   double err_acc = 0.0;
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += 4) {
     cplx acc[4], h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      acc[j] = ldcs(out + (size_t)(q0 + j) * stride);
+      acc[j] = nxt[j];
       h[j] = {0.0, 0.0};
+    }
+    if (q0 + 4 < EPT) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nxt[j] = ldcs(out + (size_t)(q0 + 4 + j) * stride);
     }
     for (int b = 0; b < n_cross; ++b) {
       const int lb = C + b;
@@ -284,7 +306,7 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) err_acc += __shfl_xor_sync(0xffffffffu, err_acc, o);
     if ((t & 31) == 0) red[t >> 5] = err_acc;
-    __syncthreads();
+    tile_sync<NBAR>();
     if (t == 0) {
       double sacc = 0.0;
       for (int w = 0; w < NT / 32; ++w) sacc += red[w];
@@ -297,7 +319,7 @@ template <bool REAL>
 __global__ void __launch_bounds__(NT, REAL ? 3 : 2)
 k_stream_g(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  g_tile<REAL>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
+  g_tile<REAL, 0>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
 }
 
 // ---- dataflow launch: A tiles and the first group's tiles, chunk by chunk through L2 --------------------
@@ -317,7 +339,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 
-template <bool REAL>
+template <bool REAL, bool AUX>
 __global__ void __launch_bounds__(NT, REAL ? 3 : 2)
 k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ StreamParams PG,
             const __grid_constant__ StreamCoef cf, const AgCtl ctl) {
@@ -331,7 +353,7 @@ k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ Str
   const unsigned blk = item >> (ctl.chunk_log2 + 1), r = item & (2 * CT - 1);
   if (r < CT) {
     if (blk >= ctl.n_chunks) return;
-    a_tile<REAL>(PA, cf, T, (size_t)blk * CT + r);
+    a_tile<REAL, AUX>(PA, cf, T, (size_t)blk * CT + r);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) atomicAdd(ctl.sync + 1 + blk, 1u);
@@ -347,7 +369,7 @@ k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ Str
       }
     }
     __syncthreads();
-    g_tile<REAL>(PG, cf, T, (size_t)c * CT + (r - CT));
+    g_tile<REAL, 0>(PG, cf, T, (size_t)c * CT + (r - CT));
   }
 }
 
@@ -384,12 +406,10 @@ int current_device() {
 void set_attrs() {
   const int dev = current_device();
   if (g_attr_set[dev]) return;
-  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_a<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
-  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_a<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
-  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_g<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
-  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_g<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
-  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_ag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
-  PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_ag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+  auto big = [](auto* f) { PD_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16)); };
+  big(k_stream_a<false, false>); big(k_stream_a<false, true>); big(k_stream_a<true, false>); big(k_stream_a<true, true>);
+  big(k_stream_ag<false, false>); big(k_stream_ag<false, true>); big(k_stream_ag<true, false>); big(k_stream_ag<true, true>);
+  big(k_stream_g<false>); big(k_stream_g<true>);
   g_attr_set[dev] = true;
 }
 
@@ -408,12 +428,17 @@ unsigned* ag_sync_buffer(cudaStream_t s) {
   bufs[{dev, s}] = p;
   return p;
 }
-bool fuse_enabled() {
-  static const bool on = [] {
+unsigned env_unsigned(const char* name, unsigned dflt) {
+  const char* e = std::getenv(name);
+  return e ? (unsigned)std::strtoul(e, nullptr, 10) : dflt;
+}
+// PD_STREAM_FUSE=0 keeps the A launch and the first group launch separate (for A/B measurements)
+int fuse_mode() {
+  static const int mode = [] {
     const char* e = std::getenv("PD_STREAM_FUSE");
-    return !(e && e[0] == '0');
+    return (e && e[0] == '0') ? 0 : 1;
   }();
-  return on;
+  return mode;
 }
 
 // the strided groups of the bits above the contiguous tile: group gi takes bits [lo, lo + nb)
@@ -461,20 +486,25 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
   }
   int n = 0, first = 0;
   const unsigned tiles_per_vec = (unsigned)(g.dim >> TB);
+  static const unsigned max_chunk_log2 = env_unsigned("PD_STREAM_CHUNK", 8), lag = env_unsigned("PD_STREAM_LAG", 1);
   unsigned chunk_log2 = 0;
-  while ((1u << (chunk_log2 + 1)) <= tiles_per_vec && chunk_log2 < 8) ++chunk_log2;
+  while ((1u << (chunk_log2 + 1)) <= tiles_per_vec && chunk_log2 < std::max<unsigned>(max_chunk_log2, gr.nb[0])) ++chunk_log2;
   const size_t n_chunks = n_tiles >> chunk_log2;
-  if (fuse_enabled() && gr.G >= 1 && (unsigned)gr.nb[0] <= chunk_log2 && n_chunks <= kMaxChunks) {
-    AgCtl ctl{ag_sync_buffer(s), chunk_log2, (unsigned)n_chunks, 1u};
+  if (fuse_mode() != 0 && gr.G >= 1 && (unsigned)gr.nb[0] <= chunk_log2 && n_chunks >= 8 && n_chunks <= kMaxChunks) {
+    AgCtl ctl{ag_sync_buffer(s), chunk_log2, (unsigned)n_chunks, std::max(1u, lag)};
     PD_CUDA_CHECK(cudaMemsetAsync(ctl.sync, 0, sizeof(unsigned) * (n_chunks + 1), s));
     const unsigned ag_grid = (unsigned)(2 * (n_tiles + ((size_t)ctl.lag << chunk_log2)));
-    if (uni) k_stream_ag<true><<<ag_grid, NT, TILE * 16, s>>>(A, B[0], cf, ctl);
-    else k_stream_ag<false><<<ag_grid, NT, TILE * 16, s>>>(A, B[0], cf, ctl);
+    const bool aux = A.aux != nullptr;
+    auto go = [&](auto* f) { f<<<ag_grid, NT, TILE * 16, s>>>(A, B[0], cf, ctl); };
+    if (uni) { if (aux) go(k_stream_ag<true, true>); else go(k_stream_ag<true, false>); }
+    else { if (aux) go(k_stream_ag<false, true>); else go(k_stream_ag<false, false>); }
     n = 1;
     first = 1;
   } else {
-    if (uni) k_stream_a<true><<<grid, NT, TILE * 16, s>>>(A, cf);
-    else k_stream_a<false><<<grid, NT, TILE * 16, s>>>(A, cf);
+    const bool aux = A.aux != nullptr;
+    auto go = [&](auto* f) { f<<<grid, NT, TILE * 16, s>>>(A, cf); };
+    if (uni) { if (aux) go(k_stream_a<true, true>); else go(k_stream_a<true, false>); }
+    else { if (aux) go(k_stream_a<false, true>); else go(k_stream_a<false, false>); }
     n = 1;
   }
   for (int gi = first; gi < gr.G; ++gi) {

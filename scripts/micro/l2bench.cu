@@ -58,6 +58,48 @@ k_ws(const double2* __restrict__ in, double2* __restrict__ out, size_t n_tiles, 
   if (acc == 1.2345e300) *sink = acc;
 }
 
+// ---- (a2) -------------------------------------------------------------------------------------------
+// Producer/consumer through L2 as in k_stream_ag: phase 0 writes a region (every CTA its own tiles), phase 1
+// (a second launch) reads tiles written by ANOTHER CTA (shift) with load policy POL (0 ld.cg, 1 ld.cs evict-first,
+// 2 default ld) and rewrites them: out[i] = in[i] + out[i] where `in` was just written and `out` is dirty.
+template <int POL>
+__device__ __forceinline__ double2 ldp(const double2* p) {
+  if (POL == 0) return __ldcg(p);
+  if (POL == 1) return __ldcs(p);
+  return *p;
+}
+__global__ void __launch_bounds__(256, 3) k_fill(double2* a, double2* b, size_t n_tiles) {
+  for (size_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      a[(tile << 12) + threadIdx.x + 256 * i] = make_double2(1.0, tile);
+      b[(tile << 12) + threadIdx.x + 256 * i] = make_double2(2.0, i);
+    }
+}
+template <int POL>
+__global__ void __launch_bounds__(256, 3) k_consume(const double2* __restrict__ in, double2* __restrict__ out, size_t n_tiles,
+                                                    size_t shift) {
+  const int t = threadIdx.x;
+  for (size_t tl = blockIdx.x; tl < n_tiles; tl += gridDim.x) {
+    const size_t tile = (tl + shift) % n_tiles;
+    const double2* p = in + (tile << 12);
+    double2* o = out + (tile << 12);
+#pragma unroll
+    for (int q0 = 0; q0 < 16; q0 += 8) {
+      double2 v[8], w[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ldp<POL>(p + t + 256 * (q0 + i));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) w[i] = ldp<POL>(o + t + 256 * (q0 + i));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        w[i].x += v[i].x; w[i].y += v[i].y;
+        o[t + 256 * (q0 + i)] = w[i];
+      }
+    }
+  }
+}
+
 // ---- (b) ---------------------------------------------------------------------------------------------
 // Cluster of CS CTAs, 64 KiB tile per CTA.  Per iteration a CTA (1) streams one 64 KiB tile from HBM into its
 // shared memory (WHAT & 1) and (2) reads `nbits` partner tiles through DSMEM (WHAT & 2).  Work of different
@@ -158,7 +200,7 @@ void run_cluster(const double2* in, size_t n_tiles, double* sink, unsigned* d_sm
   }
 }
 
-int main() {
+int main(int argc, char**) {
   const size_t dim = (size_t)1 << 26;
   double2 *in, *out;
   double* sink;
@@ -195,12 +237,38 @@ int main() {
              mode == 0 ? "read" : "rmw", mib, reps, best, bytes / best / 1e6);
       fflush(stdout);
     }
+  // (a2)
+  for (int mib : {16, 32}) {
+    const size_t nt = (size_t)mib * 16;
+    for (int pol = 0; pol < 3; ++pol)
+      for (size_t shift : {(size_t)0, (size_t)37}) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+          k_fill<<<148 * 3, 256>>>(in, out, nt);
+          CK(cudaEventRecord(e0));
+          if (pol == 0) k_consume<0><<<148 * 3, 256>>>(in, out, nt, shift);
+          if (pol == 1) k_consume<1><<<148 * 3, 256>>>(in, out, nt, shift);
+          if (pol == 2) k_consume<2><<<148 * 3, 256>>>(in, out, nt, shift);
+          CK(cudaEventRecord(e1));
+          CK(cudaEventSynchronize(e1));
+          float ms;
+          CK(cudaEventElapsedTime(&ms, e0, e1));
+          if (rep > 0 && ms < best) best = ms;
+        }
+        CK(cudaGetLastError());
+        printf("{\"bench\":\"produce_consume\",\"MiB_per_vector\":%d,\"policy\":\"%s\",\"shift\":%zu,\"ms\":%.4f,\"GBs\":%.1f}\n", mib,
+               pol == 0 ? "cg" : pol == 1 ? "cs" : "default", shift, best, 3.0 * nt * 65536 / best / 1e6);
+        fflush(stdout);
+      }
+  }
   // (b)
   const size_t n_tiles = dim >> 12;
   run_cluster<1>(in, n_tiles, sink, d_smid, e0, e1);
   run_cluster<2>(in, n_tiles, sink, d_smid, e0, e1);
-  run_cluster<4>(in, n_tiles, sink, d_smid, e0, e1);
-  run_cluster<8>(in, n_tiles, sink, d_smid, e0, e1);
-  run_cluster<16>(in, n_tiles, sink, d_smid, e0, e1);
+  if (argc > 1) {
+    run_cluster<4>(in, n_tiles, sink, d_smid, e0, e1);
+    run_cluster<8>(in, n_tiles, sink, d_smid, e0, e1);
+    run_cluster<16>(in, n_tiles, sink, d_smid, e0, e1);
+  }
   return 0;
 }
