@@ -33,6 +33,19 @@ int guarded(F&& f) {
     return PD_ERR_STATE;
   }
 }
+// Every entry point that launches or copies runs with the plan's device current and restores the caller's
+// device afterwards (a plan on cuda:k must not change the device torch sees, nor launch on a foreign one).
+struct DeviceScope {
+  int prev;
+  explicit DeviceScope(int dev) : prev(PD_BACKEND::push_device(dev)) {}
+  ~DeviceScope() { PD_BACKEND::pop_device(prev); }
+};
+template <class F>
+int guarded_on(const pd_plan* p, F&& f) {
+  if (!p) return guarded(f);
+  DeviceScope scope(p->eng.bk.device);
+  return guarded(f);
+}
 void need(bool ok, const char* what) {
   if (!ok) throw pd::Error(PD_ERR_INVALID, what);
 }
@@ -61,14 +74,15 @@ void pd_options_default(pd_options* o) {
 int pd_plan_create(pd_plan** out, int32_t n_qubits, int32_t batch, int32_t kind, int32_t device) {
   return guarded([&] {
     need(out != nullptr, "pd_plan_create: out is NULL");
+    DeviceScope scope(device);
     *out = new pd_plan(n_qubits, batch, kind, device);
   });
 }
 int pd_plan_destroy(pd_plan* p) {
-  return guarded([&] { delete p; });
+  return guarded_on(p, [&] { delete p; });
 }
 int pd_plan_set_interaction(pd_plan* p, const double* pair_u_host, void* stream) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && pair_u_host, "pd_plan_set_interaction: NULL argument");
     p->eng.set_interaction(pair_u_host, stream);
   });
@@ -76,7 +90,7 @@ int pd_plan_set_interaction(pd_plan* p, const double* pair_u_host, void* stream)
 int pd_plan_set_terms(pd_plan* p, int32_t n_samples, double dt, int32_t n_det,
                       const uint64_t* det_masks, const double* det_values, int32_t n_amp,
                       const uint64_t* amp_masks, const double* amp_values) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p != nullptr, "pd_plan_set_terms: plan is NULL");
     need(n_det >= 0 && n_amp >= 0, "pd_plan_set_terms: negative term count");
     need(n_det == 0 || (det_masks && det_values), "pd_plan_set_terms: det arrays missing");
@@ -85,26 +99,26 @@ int pd_plan_set_terms(pd_plan* p, int32_t n_samples, double dt, int32_t n_det,
   });
 }
 int pd_plan_set_collapse(pd_plan* p, int32_t n_ops, const double* ops_host) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p != nullptr && n_ops >= 0 && (n_ops == 0 || ops_host), "pd_plan_set_collapse: bad argument");
     p->eng.set_collapse(n_ops, ops_host);
   });
 }
 int pd_plan_set_path(pd_plan* p, int32_t path) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p != nullptr && path >= 0 && path <= 4, "pd_plan_set_path: bad argument");
     p->eng.bk.path = path;
   });
 }
 int pd_hpsi(pd_plan* p, void* stream, double t, const void* in_dev, void* out_dev) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && in_dev && out_dev, "pd_hpsi: NULL argument");
     need(in_dev != out_dev, "pd_hpsi: in-place application is not supported");
     p->eng.apply((pd::cplx*)out_dev, (const pd::cplx*)in_dev, t, 2, stream);
   });
 }
 int pd_rhs(pd_plan* p, void* stream, double t, const void* in_dev, void* out_dev) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && in_dev && out_dev, "pd_rhs: NULL argument");
     need(in_dev != out_dev, "pd_rhs: in-place application is not supported");
     p->eng.apply((pd::cplx*)out_dev, (const pd::cplx*)in_dev, t, 0, stream);
@@ -113,7 +127,7 @@ int pd_rhs(pd_plan* p, void* stream, double t, const void* in_dev, void* out_dev
 int pd_evolve_forward(pd_plan* p, void* stream, int32_t solver, const pd_options* opt,
                       const void* state0_dev, const double* tsave_host, int32_t n_t,
                       void* states_dev, pd_tape** tape_out) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && state0_dev && tsave_host && states_dev, "pd_evolve_forward: NULL argument");
     pd_options o;
     if (opt) o = *opt; else pd_options_default(&o);
@@ -133,7 +147,7 @@ int pd_evolve_forward(pd_plan* p, void* stream, int32_t solver, const pd_options
 int pd_evolve_backward(pd_plan* p, void* stream, pd_tape* tape, const void* states_dev,
                        const void* grad_states_dev, double* grad_det_host, double* grad_amp_host,
                        double* grad_pair_u_host, double* grad_tsave_host, void* grad_state0_dev) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && tape && states_dev, "pd_evolve_backward: NULL argument");
     p->eng.backward(tape->tape, (const pd::cplx*)states_dev, (const pd::cplx*)grad_states_dev,
                     grad_det_host, grad_amp_host, grad_pair_u_host, grad_tsave_host,
@@ -144,7 +158,7 @@ int pd_evolve_forward_units(pd_plan* p, void* stream, const pd_options* opt, int
                             const void* state0_dev, const double* tsave_host, int32_t n_t,
                             const double* det_values_host, const double* amp_values_host,
                             void* states_dev, pd_tape** tape_out) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && state0_dev && tsave_host && states_dev && n_units >= 1, "pd_evolve_forward_units: bad argument");
     need((det_values_host || p->eng.prog.n_det() == 0) && (amp_values_host || p->eng.prog.n_amp() == 0),
          "pd_evolve_forward_units: missing coefficient tables");
@@ -166,7 +180,7 @@ int pd_evolve_backward_units(pd_plan* p, void* stream, pd_tape* tape, const void
                              const void* grad_states_dev, const double* det_values_host,
                              const double* amp_values_host, double* grad_det_host, double* grad_amp_host,
                              void* grad_state0_dev) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && tape && states_dev && !tape->units.empty(), "pd_evolve_backward_units: bad argument");
     p->eng.states_for_fallback_ = (const pd::cplx*)states_dev;
     try {
@@ -202,7 +216,7 @@ int pd_tape_destroy(pd_tape* t) {
 }
 int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t,
                    const double* obs_dev, double* out_host) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && states_dev && obs_dev && out_host && n_t >= 1, "pd_expect_diag: bad argument");
     p->eng.expect_diag((const pd::cplx*)states_dev, n_t, obs_dev, out_host, stream);
   });
@@ -210,7 +224,7 @@ int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t
 int pd_rhs_vjp(pd_plan* p, void* stream, double t, const void* state_dev, const void* cot_dev,
                void* grad_state_dev, double* grad_det_host, double* grad_amp_host,
                double* grad_pair_host, double* grad_t_host, int32_t defer_pair) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && state_dev && cot_dev, "pd_rhs_vjp: NULL argument");
     double tb = p->eng.rhs_vjp(t, (const pd::cplx*)state_dev, (const pd::cplx*)cot_dev,
                                (pd::cplx*)grad_state_dev, grad_det_host, grad_amp_host,
@@ -219,14 +233,14 @@ int pd_rhs_vjp(pd_plan* p, void* stream, double t, const void* state_dev, const 
   });
 }
 int pd_pair_gradient_flush(pd_plan* p, void* stream, double* grad_pair_host) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && grad_pair_host, "pd_pair_gradient_flush: NULL argument");
     p->eng.pair_gradient_flush(grad_pair_host, stream);
   });
 }
 int pd_lincomb(pd_plan* p, void* stream, void* out_dev, int32_t n_in, const void* const* ins_dev,
                const double* w_host) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && out_dev && ins_dev && w_host && n_in >= 1 && n_in <= 8, "pd_lincomb: bad argument");
     for (int j = 0; j < n_in; ++j) need(ins_dev[j] != nullptr, "pd_lincomb: NULL input");
     p->eng.lincomb((pd::cplx*)out_dev, n_in, (const pd::cplx* const*)ins_dev, w_host, stream);
@@ -235,7 +249,7 @@ int pd_lincomb(pd_plan* p, void* stream, void* out_dev, int32_t n_in, const void
 int pd_dp5_error_sumsq(pd_plan* p, void* stream, const void* const* k_dev, const double* ew_host,
                        const void* y0_dev, const void* y1_dev, double atol, double rtol,
                        double* sumsq_host) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && k_dev && ew_host && y0_dev && y1_dev && sumsq_host, "pd_dp5_error_sumsq: NULL argument");
     for (int j = 0; j < 7; ++j)
       need(k_dev[j] != nullptr || ew_host[j] == 0.0, "pd_dp5_error_sumsq: NULL slope with a non-zero weight");
@@ -248,7 +262,7 @@ int pd_dp5_error_sumsq(pd_plan* p, void* stream, const void* const* k_dev, const
 int pd_sharded_accumulate(pd_plan* p, void* stream, void* out_dev, const void* psi_dev, double shift,
                           int32_t n_peers, const void* const* peer_slices,
                           const double* coef_host) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && out_dev && psi_dev && n_peers >= 0 && n_peers <= 16, "pd_sharded_accumulate: bad argument");
     need(n_peers == 0 || (peer_slices && coef_host), "pd_sharded_accumulate: NULL peer list");
     for (int k = 0; k < n_peers; ++k)
@@ -259,14 +273,14 @@ int pd_sharded_accumulate(pd_plan* p, void* stream, void* out_dev, const void* p
 }
 int pd_bench_hpsi(pd_plan* p, void* stream, double t, int32_t reps, const void* in_dev,
                   void* out_dev, double* ms_per_apply_host) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && in_dev && out_dev && ms_per_apply_host && reps > 0, "pd_bench_hpsi: bad argument");
     *ms_per_apply_host = p->eng.bench_apply((const pd::cplx*)in_dev, (pd::cplx*)out_dev, t, reps, stream);
   });
 }
 int pd_bench_dp5_steps(pd_plan* p, void* stream, double t0, double dt, int32_t steps, void* y_dev,
                        double* ms_per_step_host) {
-  return guarded([&] {
+  return guarded_on(p, [&] {
     need(p && y_dev && ms_per_step_host && steps > 0, "pd_bench_dp5_steps: bad argument");
     *ms_per_step_host = p->eng.bench_dp5((pd::cplx*)y_dev, t0, dt, steps, stream);
   });

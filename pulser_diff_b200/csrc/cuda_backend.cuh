@@ -107,6 +107,17 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
 class CudaBackend {
  public:
   static constexpr bool is_cuda = true;
+  // device guard of the C ABI (cabi_impl.hpp DeviceScope): make `dev` current, return the previous device
+  static int push_device(int dev) {
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+    return prev;
+  }
+  static void pop_device(int prev) {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
   int device;
   int path = 0;  // 0 auto, 1 gather, 2 tiled
   explicit CudaBackend(int dev) : device(dev) {
@@ -116,7 +127,6 @@ class CudaBackend {
       throw Error(PD_ERR_CUDA, "pulser_diff_b200 needs a CUDA device (no CPU fallback): " +
                                    std::string(cudaGetErrorString(e)));
     if (dev < 0 || dev >= n) throw Error(PD_ERR_INVALID, "bad CUDA device ordinal");
-    PD_CUDA_CHECK(cudaSetDevice(dev));
     PD_CUDA_CHECK(cudaMalloc(&d_pair_u_, sizeof(double) * kMaxQubits * kMaxQubits));
   }
   ~CudaBackend() {
@@ -161,8 +171,7 @@ class CudaBackend {
                               want_coef, d_wacc, lam_out, sums, st(s));
   }
   void* alloc(size_t bytes) {
-    void* p = nullptr;
-    PD_CUDA_CHECK(cudaSetDevice(device));
+    void* p = nullptr;   // the C ABI entry point has made `device` current (DeviceScope)
     PD_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
     return p;
   }

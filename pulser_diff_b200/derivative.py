@@ -10,20 +10,29 @@ import torch
 from torch import Tensor
 
 
+def _line_through(a: Tensor, b: Tensor) -> Tensor:
+    """Value two grid steps after ``a`` on the straight line through consecutive samples a, b."""
+    return a + 2 * (b - a)
+
+
 def _extrapolate_borders(deriv: Tensor, borders: list, dt: Tensor) -> Tensor:
-    """Replace derivative samples at pulse boundaries by linear extrapolation from their
-    neighbours (same rule as reference derivative.py:7-23)."""
-    prev = 0
+    """Derivative samples at pulse boundaries are artefacts of the piecewise pulse profile; each is
+    replaced, in order, by the straight line through two neighbouring samples (rule of reference
+    derivative.py:7-23; ``dt`` cancels out of it and is kept for signature compatibility).
+
+    An isolated boundary (or one too close to the end) is a pair (idx-1, idx) rebuilt from the
+    samples before it; a boundary directly following another one, and index 0, are rebuilt from
+    the two samples after it."""
+    n = len(deriv)
+    backward = [i != 0 and (i - p != 1 or i + 3 >= n)
+                for i, p in zip(borders, [0] + list(borders[:-1]))]
     with torch.no_grad():
-        for idx in borders:
-            if idx == 0:
-                deriv[0] = deriv[2] - ((deriv[2] - deriv[1]) / dt) * 2 * dt
-            elif (idx - prev) != 1 or idx + 3 >= len(deriv):
-                deriv[idx - 1] = deriv[idx - 3] + ((deriv[idx - 2] - deriv[idx - 3]) / dt) * 2 * dt
-                deriv[idx] = deriv[idx - 2] + ((deriv[idx - 1] - deriv[idx - 2]) / dt) * 2 * dt
+        for i, from_left in zip(borders, backward):
+            if from_left:
+                deriv[i - 1] = _line_through(deriv[i - 3], deriv[i - 2])
+                deriv[i] = _line_through(deriv[i - 2], deriv[i - 1])
             else:
-                deriv[idx] = deriv[idx + 2] - ((deriv[idx + 2] - deriv[idx + 1]) / dt) * 2 * dt
-            prev = idx
+                deriv[i] = _line_through(deriv[i + 2], deriv[i + 1])
     return deriv
 
 

@@ -145,9 +145,10 @@ class Hamiltonian:
         self.set_config(config)
 
     def _adapt_to_sampling_rate(self, full_array: Tensor) -> Tensor:
-        indices = torch.linspace(0, len(full_array) - 1, int(self._sampling_rate * self._duration),
-                                 dtype=torch.int)
-        return full_array[indices]
+        """Keep ``int(rate * duration)`` samples at integer positions spread evenly over the array,
+        end points included (sub-sampling rule of reference hamiltonian.py:83-91)."""
+        keep = int(self._sampling_rate * self._duration)
+        return full_array[torch.linspace(0, len(full_array) - 1, keep, dtype=torch.int)]
 
     @property
     def config(self) -> SimConfig:
@@ -186,31 +187,28 @@ class Hamiltonian:
         self._collapse_ops = CollapseOperators(local, self._size)
 
     def build_operator(self, operations: Union[list, tuple]) -> Tensor:
-        """``[(op, qubits), ...]`` -> tensor product with identities; ``(op, "global")`` sums the
-        operator over all qubits (same contract as reference hamiltonian.py:221-268)."""
-        op_list = [self.op_matrix["I"] for _ in range(self._size)]
-        if not isinstance(operations, list):
-            operations = [operations]
-        for operator, qubits in operations:
-            if qubits == "global":
-                total = None
-                for q_id in self._qdict:
-                    term = self.build_operator([(operator, [q_id])])
-                    total = term if total is None else total + term
-                return total
-            qubits_set = set(qubits)
-            if len(qubits_set) < len(qubits):
+        """Tensor-product operator from ``[(op, qubit ids), ...]`` (identity elsewhere); an entry
+        ``(op, "global")`` yields the sum of ``op`` over every qubit instead.  ``op`` is a 2x2
+        tensor or a key of ``op_matrix``.  Same contract and exceptions as reference
+        hamiltonian.py:221-268."""
+        entries = operations if isinstance(operations, list) else [operations]
+        placed: dict[int, Tensor] = {}
+        for op, where in entries:
+            if where == "global":
+                terms = [self.build_operator([(op, [qid])]) for qid in self._qdict]
+                return sum(terms[1:], terms[0])
+            ids = list(where)
+            if len(set(ids)) != len(ids):
                 raise ValueError("Duplicate atom ids in argument list.")
-            if not qubits_set.issubset(self._qdict.keys()):
-                raise ValueError("Invalid qubit names: " f"{qubits_set - self._qdict.keys()}")
-            if isinstance(operator, str):
-                try:
-                    operator = self.op_matrix[operator]
-                except KeyError:
-                    raise ValueError(f"{operator} is not a valid operator")
-            for qubit in qubits:
-                op_list[self._qid_index[qubit]] = operator
-        return kron(*op_list)
+            unknown = set(ids) - self._qdict.keys()
+            if unknown:
+                raise ValueError(f"Invalid qubit names: {unknown}")
+            if isinstance(op, str):
+                if op not in self.op_matrix:
+                    raise ValueError(f"{op} is not a valid operator")
+                op = self.op_matrix[op]
+            placed.update({self._qid_index[q]: op for q in ids})
+        return kron(*[placed.get(k, self.op_matrix["I"]) for k in range(self._size)])
 
     def _extract_samples(self) -> None:
         samples = self.samples_obj.to_nested_dict(list(self._qdict), all_local=False)

@@ -39,18 +39,17 @@ def kron(*args: Tensor) -> Tensor:
 
 
 def basis_state(dim, number) -> Tensor:
-    """(n, 1) ket of a (product of) Fock state(s) (reference utils.py:108-133)."""
-    dim = (dim,) if isinstance(dim, int) else tuple(dim)
-    number = (number,) if isinstance(number, int) else tuple(number)
-    if len(dim) != len(number):
+    """(prod(dim), 1) column with a single 1 at the row-major index of ``number`` in a register of
+    local dimensions ``dim`` (contract of reference utils.py:108-133)."""
+    dims = [dim] if isinstance(dim, int) else list(dim)
+    occ = [number] if isinstance(number, int) else list(number)
+    if len(dims) != len(occ):
         raise ValueError(
             "Arguments `number` must have the same length as `dim` of length"
-            f" {len(dim)}, but has length {len(number)}.")
-    n = 0
-    for d, s in zip(dim, number):
-        n = d * n + s
-    ket = torch.zeros(prod(dim), 1)
-    ket[n] = 1.0
+            f" {len(dims)}, but has length {len(occ)}.")
+    strides = [prod(dims[k + 1:]) for k in range(len(dims))]
+    ket = torch.zeros(prod(dims), 1)
+    ket[sum(o * st for o, st in zip(occ, strides))] = 1.0
     return ket
 
 

@@ -15,6 +15,9 @@ namespace pd {
 class HostBackend {
  public:
   static constexpr bool is_cuda = false;
+  int device = 0;
+  static int push_device(int) { return 0; }
+  static void pop_device(int) {}
   int path = 0;
   explicit HostBackend(int) {}
   void* alloc(size_t bytes) {
