@@ -78,11 +78,13 @@ def configure(plan: Plan, prog: Program) -> None:
 def make_program(n_qubits: int, kind: int, dt: float, det_masks: Sequence[int], det_values: Tensor,
                  amp_masks: Sequence[int], amp_values: Tensor, pair_u: Tensor,
                  collapse: Optional[Tensor]) -> Program:
+    # a program may have no detuning (or no drive) term at all: keep the sample axis explicit
+    n_s = int(det_values.shape[-1]) if len(det_masks) else (int(amp_values.shape[-1]) if len(amp_masks) else 0)
     return Program(
         n_qubits, kind, float(dt), [int(m) for m in det_masks],
-        det_values.detach().to("cpu", torch.float64).reshape(len(det_masks), -1).contiguous(),
+        det_values.detach().to("cpu", torch.float64).reshape(len(det_masks), n_s).contiguous(),
         [int(m) for m in amp_masks],
-        amp_values.detach().to("cpu", torch.complex128).reshape(len(amp_masks), -1).contiguous(),
+        amp_values.detach().to("cpu", torch.complex128).reshape(len(amp_masks), n_s).contiguous(),
         pair_u.detach().to("cpu", torch.float64).contiguous(),
         None if collapse is None else collapse.detach().to("cpu", torch.complex128).contiguous())
 

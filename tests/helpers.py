@@ -138,8 +138,33 @@ def kat_problem(name: str) -> Problem:
     raise KeyError(name)
 
 
+def independent_problem(name: str, theta: torch.Tensor) -> Problem:
+    """The cases of tests/golden/make_independent_kats.py, parametrised by the four scalars ``theta`` =
+    (amplitude scale, detuning scale, phase chirp, x shift of atom 1) so that gradients reach every
+    autograd leaf class of the path."""
+    if name == "C1":
+        base = Problem(torch.tensor([[0.0, 0.0], [8.0, 0.0]], dtype=torch.float64), C6_70,
+                       [global_channel((RP.constant(1000, 5.0), RP.constant(1000, 0.0), 0.0))], rate=1.0,
+                       evaluation_times="Minimal")
+    elif name == "C2-small":
+        k = torch.arange(1100, dtype=torch.float64) / 1100
+        base = Problem(chain(4, 7.0), C6_60,
+                       [Channel(6.0 * torch.sin(math.pi * k) ** 2, -8.0 + 16.0 * k, torch.zeros(1100, dtype=torch.float64))],
+                       rate=0.05)
+    else:
+        base = kat_problem(name)
+    ch = base.channels[0]
+    T = ch.amp.numel()
+    chirp = torch.arange(T, dtype=torch.float64) / T
+    shift = torch.zeros_like(base.coords)
+    shift[1, 0] = 1.0
+    return Problem(base.coords + theta[3] * shift, base.c6,
+                   [Channel(theta[0] * ch.amp, theta[1] * ch.det, ch.phase + theta[2] * chirp)],
+                   rate=base.rate, noise=base.noise, evaluation_times=base.evaluation_times)
+
+
 KAT_SOLVER = {"K-A": "dp5_se", "K-B": "krylov_se", "K-C": "krylov_se", "K-D": "krylov_se",
-              "K-E": "krylov_se", "K-F": "dp5_me", "K-G": "dp5_se"}
+              "K-E": "krylov_se", "K-F": "dp5_me", "K-G": "dp5_se", "C1": "dp5_se", "C2-small": "dp5_se"}
 
 
 def random_problem(n: int, seed: int = 0, T: int = 300, rate: float = 0.2, local: bool = False,
