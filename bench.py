@@ -13,13 +13,18 @@ gradient pass.  Metric = DP5 evolution steps per second over forward+gradient.
 * ``value``  : passes with the register state and pulse coefficients already on the device.
 * ``e2e``    : the same pass through ``TorchEmulator.run`` from HOST tensors, loss and gradients
                read back to the host, every step.
-* ``roofline``: the HBM-bound regime of the same kernels -- one fused DP5 step at N = 23
-               (128 MiB vectors, the largest register the tiled kernel family covers today)
-               timed with CUDA events inside the C ABI on the launching stream; algorithmic
-               bytes 576 B x 2^N per step, 40 B x 2^N per H.psi.
-               ``roofline_n26`` is the same step at north_star's N = 26 (1 GiB vectors, gather
-               kernels); ``roofline_workload`` is the figure for the N = 12 workload itself
-               (64 KiB state: launch/latency bound, reported for completeness).
+* ``roofline``: the HBM-bound regime of the same kernels -- one fused DP5 step at north_star's N = 26
+               (1 GiB vectors; stream family: A tiles + first bit group as one L2-blocked dataflow launch,
+               last bit group as a second launch) with a full-register global drive, timed with CUDA
+               events inside the C ABI on the launching stream; algorithmic bytes 576 B x 2^N per step,
+               40 B x 2^N per H.psi (``roofline_hpsi``), SURVEY.md 8d.  ``roofline_n23`` is the tiled
+               family at N = 23; ``fwd_grad_n26`` is forward + adjoint gradient wall time per DP5 step at
+               N = 26 (BASELINE metric "fwd+grad wall time at N qubits") with ``roofline_adjoint``.
+* ``c3_batch``: BASELINE configs[2] -- 4096 pulse-parameter sets of the 2-atom gate workload, forward +
+               gradient through ``ops.evolve_units``, sets dealt over the ranks (strong scaling, no
+               data-path collective); coefficient tables are built on the device.
+* ``c4_lindblad``: BASELINE configs[3] -- 12-atom Lindblad run (dephasing + relaxation, 4^12 density
+               matrix), forward + adjoint gradient seconds and the DP5_ME step roofline (528 B/entry).
 * ``cpu_baseline``: the oracle (restated reference CPU path: sparse-COO H(t) re-assembly, DP5,
                tape autograd) on a bounded sample of the same workload.
 """
@@ -126,9 +131,9 @@ class ClockSampler:
 
 
 def measured_traffic(key: str):
-    """dram bytes read+written per DP5 step from the committed ncu capture (profiles/r01_traffic.json)."""
+    """dram bytes read+written per DP5 step from the committed ncu capture (profiles/r02_traffic.json)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[key]
     except Exception:
         return None
 
@@ -139,6 +144,173 @@ def measured_peak():
         return float(pk["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def fwd_grad_large(dev, n, n_steps, peak):
+    """Forward + adjoint-gradient wall time of n_steps fixed DP5 steps at n qubits (BASELINE metric
+    "fwd+grad wall time at N qubits"), full-register global drive.  Algorithmic bytes of the adjoint of one
+    step: 576 B/amplitude to recompute the stage inputs + 576 B for the six
+    transposed generator applications with their stage combinations + 6 x 32 B for the site correlations
+    (each reads the stage adjoint and the stage input once) = 1344 B/amplitude."""
+    from pulser_diff_b200 import _cabi, ops
+    ops.clear_plan_cache()
+    torch.cuda.empty_cache()
+    T = 64
+    g = torch.Generator().manual_seed(0)
+    dv0 = (torch.rand(1, T, dtype=torch.float64, generator=g) - 0.5) * 4
+    av0 = torch.complex(torch.rand(1, T, dtype=torch.float64, generator=g) * 3, torch.zeros(1, T, dtype=torch.float64))
+    u = torch.zeros(n, n, dtype=torch.float64)
+    for i in range(n):
+        for j in range(i + 1, n):
+            u[i, j] = C6 / (SPACING * (j - i)) ** 6
+    full = (1 << n) - 1
+    psi0 = torch.zeros(1, 2 ** n, dtype=torch.complex128, device=dev)
+    psi0[0, -1] = 1.0
+    tsave = torch.tensor([0.0, 0.001 * n_steps], dtype=torch.float64)
+    replay = [(0.001, False)] * (n_steps - 1) + [(0.001, True)]
+    w = torch.arange(2 ** n, device=dev).remainder(7).to(torch.float64)
+    out = None
+    for _ in range(3):      # the last sweep runs warm (slope cache, allocations)
+        dv = dv0.clone().requires_grad_(True)
+        av = av0.clone().requires_grad_(True)
+        torch.cuda.synchronize(dev)
+        torch.cuda.nvtx.range_push("fwd_n%d" % n)
+        t0 = time.perf_counter()
+        st = ops.evolve(psi0, tsave, dv, av, u, n_qubits=n, kind=_cabi.PD_KET, dt=0.02, det_masks=[full],
+                        amp_masks=[full], options=_cabi.Options(replay=replay))
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        torch.cuda.nvtx.range_pop()
+        val = (w * st[-1, 0].abs() ** 2).sum()
+        torch.cuda.nvtx.range_push("adjoint_n%d" % n)
+        torch.autograd.grad(val, [dv, av])
+        torch.cuda.synchronize(dev)
+        t2 = time.perf_counter()
+        torch.cuda.nvtx.range_pop()
+        fwd, bwd = (t1 - t0) * 1e3 / n_steps, (t2 - t1) * 1e3 / n_steps
+        amps = 2.0 ** n
+        out = {"workload": f"chain_n{n}: {n_steps} fixed DP5 steps forward + adjoint gradient w.r.t. all samples",
+               "fwd_ms_per_step": fwd, "adjoint_ms_per_step": bwd, "fwd_grad_ms_per_step": fwd + bwd,
+               "adjoint_over_forward": bwd / fwd,
+               "roofline_adjoint": {"bound": "hbm", "achieved": 1344.0 * amps / (bwd * 1e-3) / 1e9, "peak": peak,
+                                    "unit": "GB/s", "frac": 1344.0 * amps / (bwd * 1e-3) / 1e9 / peak,
+                                    "algorithmic_bytes": 1344.0 * amps, "traffic": None}}
+        del st, val
+    ops.clear_plan_cache()
+    torch.cuda.empty_cache()
+    return out
+
+
+C3 = dict(n=2, pulses=8, dur=131, rate=0.05, c6=865723.02, spacing=6.5, n_sets=4096)
+
+
+def c3_tables(params, idx):
+    """params (U, 3, pulses) on any device -> the reference's coefficient arrays 0.5*amp*exp(-i phase) and
+    -0.5*det, sub-sampled (hamiltonian.py:83-91, 419-423), as (U, 1, n_samples)."""
+    U = params.shape[0]
+    z = torch.zeros(U, 1, dtype=torch.float64, device=params.device)
+    amp, det, ph = (torch.cat([params[:, k].repeat_interleave(C3["dur"], dim=1), z], dim=1)[:, idx] for k in range(3))
+    return (-0.5 * det)[:, None, :], (0.5 * amp * torch.exp(-1j * ph))[:, None, :]
+
+
+def c3_setup(dev):
+    import math
+    D = C3["pulses"] * C3["dur"] + 1                     # one extra sample (reference backend.py:114-115)
+    idx = torch.linspace(0, D - 1, int(C3["rate"] * D), dtype=torch.int).long()
+    tsave = torch.cat([(torch.arange(D, dtype=torch.float64) / 1000)[idx],
+                       torch.tensor([0.0, (D - 1) / 1000], dtype=torch.float64)]).unique()
+    pair_u = torch.zeros(2, 2, dtype=torch.float64)
+    pair_u[0, 1] = C3["c6"] / C3["spacing"] ** 6
+    had = torch.tensor([[1, 1], [1, -1]], dtype=torch.complex128) / math.sqrt(2)
+    return idx, tsave, pair_u, torch.kron(had, had)
+
+
+def c3_batch(dev, rank, world, reps, barrier):
+    """BASELINE configs[2]: 4096 parameter sets of the 2-atom gate workload (8 constant pulses x 131 ns,
+    psi0 = eye(4), rate 0.05, Hadamard x Hadamard infidelity, gradient w.r.t. the 24 parameters of every
+    set), dealt over the ranks; tables, evolution, loss and gradients stay on the device."""
+    import math
+    from pulser_diff_b200 import ops, parallel
+    idx, tsave, pair_u, target = c3_setup(dev)
+    target = target.to(dev)
+    g = torch.Generator().manual_seed(0)
+    params_all = torch.rand(C3["n_sets"], 3, C3["pulses"], dtype=torch.float64, generator=g) * 4 * math.pi
+    mine = parallel.shard_units(C3["n_sets"], rank, world) if world > 1 else list(range(C3["n_sets"]))
+    params = params_all[mine].to(dev).requires_grad_(True)
+    idx_d = idx.to(dev)
+    psi0 = torch.eye(4, dtype=torch.complex128, device=dev).repeat(len(mine), 1, 1)
+    dt = 0.001 / C3["rate"]
+
+    def sweep():
+        dv, av = c3_tables(params, idx_d)
+        st = ops.evolve_units(psi0, tsave, dv, av, pair_u, n_qubits=2, dt=dt, det_masks=[3], amp_masks=[3])
+        Uf = st[:, -1].transpose(1, 2)
+        loss = 1 - (target.conj().T @ Uf).diagonal(dim1=1, dim2=2).sum(-1).abs() / 4
+        (gp,) = torch.autograd.grad(loss.sum(), [params])
+        return loss.detach(), gp
+
+    for _ in range(2):
+        loss, gp = sweep()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        loss, gp = sweep()
+    barrier()
+    secs = (time.perf_counter() - t0) / reps
+    return secs, float(loss.sum()), float(gp.abs().sum()), len(mine)
+
+
+def c4_lindblad(dev, peak):
+    """BASELINE configs[3]: 12-atom chain, C2 pulses, dephasing 0.5 + relaxation 0.1, rho0 = |g..g><g..g|,
+    tsave Minimal, loss tr(rho sum n_i); forward + adjoint gradient through TorchEmulator, and one DP5_ME
+    step against the HBM roofline (528 B per density-matrix entry)."""
+    import pulser_diff_b200 as pdb
+    from pulser_diff_b200 import ops
+    from pulser_diff_b200.samples import ChannelSamples, SequenceSamples
+    from pulser_diff_b200.utils import interpolate_sine, occupation_diag
+    ops.clear_plan_cache()
+    torch.cuda.empty_cache()
+    n = N_QUBITS
+    interp = interpolate_sine(N_PARAM, DURATION).to(torch.float64)
+    coords = chain_coords(n)
+    register = {f"q{i}": coords[i] for i in range(n)}
+    obs = torch.zeros(2 ** n, dtype=torch.float64, device=dev)
+    for i in range(n):
+        obs = obs + occupation_diag(n, [i], dev)
+    cfg = pdb.SimConfig(noise=("dephasing", "relaxation"), dephasing_rate=0.5, relaxation_rate=0.1)
+    out = None
+    for _ in range(2):       # second pass warm (NVRTC compiles torch's complex element-wise kernels once)
+        ta, td = workload_params(0)
+        amp, det, ph = pulse_samples(ta, td, interp)
+        em = pdb.TorchEmulator(SequenceSamples([ChannelSamples(amp, det, ph)]), register, pdb.DeviceSpec(C6),
+                               sampling_rate=RATE, config=cfg, torch_device=dev)
+        em.set_evaluation_times("Minimal")
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        res = em.run()
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        loss = res.expect([obs])[0].real[-1]
+        ga, gd = torch.autograd.grad(loss, [ta, td])
+        torch.cuda.synchronize(dev)
+        t2 = time.perf_counter()
+        log = em._last_result.step_log()
+        entries = 4.0 ** n
+        ach = 528.0 * entries * len(log) / (t1 - t0) / 1e9
+        out = {"workload": "C4: 12-atom chain, dephasing 0.5 + relaxation 0.1, DP5_ME, 4^12 density matrix",
+               "attempted_steps": len(log), "accepted_steps": sum(1 for r in log if r["accepted"]),
+               "fwd_s": t1 - t0, "adjoint_s": t2 - t1, "fwd_grad_s": t2 - t0, "adjoint_over_forward": (t2 - t1) / (t1 - t0),
+               "steps_per_s_forward": len(log) / (t1 - t0), "loss": float(loss),
+               "trace": float(torch.trace(res.states.detach()[-1, :, :, 0]).real),
+               "roofline_c4": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                               "algorithmic_bytes": 528.0 * entries, "traffic": None,
+                               "kernel": "DP5_ME step (6 Lindblad applications on vec(rho) + stage combines + error norm), "
+                                         "whole forward run incl. the controller"}}
+        del res, em
+    ops.clear_plan_cache()
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -225,12 +397,14 @@ def run_b200(args):
     launches = plan.launch_count - l0
     # ---- timed region 2: end-to-end passes from host tensors ----
     barrier()
+    _cabi.transfer_counters(reset=True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         loss_val, ga, gd, _, _ = e2e_pass()
         sampler.sample()
     barrier()
     t_e2e = time.perf_counter() - t0
+    lib_h2d, lib_d2h = _cabi.transfer_counters()
 
     # ---- roofline: the HBM-bound regime, N = roofline_n, CUDA events inside the C ABI ----
     roof = roof_h = roof23 = None
@@ -244,7 +418,8 @@ def run_b200(args):
                 for j in range(i + 1, nr):
                     cu[i, j] = C6 / (SPACING * (j - i)) ** 6
             big.set_interaction(cu)
-            big.set_terms(H.dt, dm, dv, am, av)
+            full_mask = [(1 << nr) - 1]           # the global channel drives EVERY atom of the big register
+            big.set_terms(H.dt, full_mask, dv, full_mask, av)
             y = torch.zeros(1, 2 ** nr, dtype=torch.complex128, device=dev)
             y[0, -1] = 1.0
             ms_step = big.bench_dp5_steps(0.3, 1e-3, args.roofline_steps, y)
@@ -270,6 +445,33 @@ def run_b200(args):
         if args.roofline_n != 23 and not args.skip_n23:
             roof23, _ = measure(23)
     clocks = sampler.summary()
+    fwd_grad = c4 = None
+    if rank == 0 and world == 1 and args.roofline_n > 0 and not args.quick:
+        try:
+            fwd_grad = fwd_grad_large(dev, args.roofline_n, 4, peak)
+        except Exception as exc:           # the headline must survive an out-of-memory here
+            fwd_grad = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        try:
+            c4 = c4_lindblad(dev, peak)
+        except Exception as exc:
+            c4 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    c3 = None
+    if not args.quick:
+        try:
+            c3_s, c3_loss, c3_gsum, c3_mine = c3_batch(dev, rank, world, 3, barrier)
+            tt = torch.tensor([c3_s], dtype=torch.float64, device=dev)
+            chk = torch.tensor([c3_loss, c3_gsum], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+            c3 = {"workload": "C3: 4096 pulse-parameter sets, 2-atom gate (8 x 131 ns constant pulses, psi0 = eye(4), "
+                              "rate 0.05), forward + gradient w.r.t. 24 parameters per set",
+                  "n_sets": C3["n_sets"], "sets_per_rank": c3_mine, "scaling": "strong",
+                  "seconds_per_sweep": tt.item(), "sets_per_s": C3["n_sets"] / tt.item(),
+                  "sum_loss": chk[0].item(), "sum_abs_grad": chk[1].item(),
+                  "tables": "built on the device from the parameters (no host tables cross the ABI)"}
+        except Exception as exc:
+            c3 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     # max over ranks
     t = torch.tensor([t_res, t_e2e], dtype=torch.float64, device=dev)
@@ -285,15 +487,20 @@ def run_b200(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_sample(args.seed, budget_s=args.cpu_budget)
+        if not args.quick:
+            try:
+                cpu["extra"] = cpu_extras()
+            except Exception as exc:
+                cpu["extra"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     if rank == 0:
         s12 = 2 ** N_QUBITS
         n_s, n_tp = int(dv.shape[-1]), len(tsave)
-        # bytes that cross PCIe in one e2e pass (counted from the buffers the C ABI copies):
-        # in : psi0, pair couplings, coefficient tables (forward and adjoint launch), time grid, step list
-        # out: controller state + attempted-step log, per-slot gradient sums, expectation values, loss
-        h2d = int(s12 * 16 + N_QUBITS * N_QUBITS * 8 + 2 * (n_s * 8 + n_s * 16 + 16) + n_tp * 8 + n_steps * 24)
-        d2h = int(96 + 2 * n_steps * 40 + n_steps * 6 * 4 * 8 + n_tp * 16 + 8)
+        # bytes that cross PCIe in one e2e pass: every cudaMemcpyAsync call site of the library is counted
+        # (pd_transfer_counters, read around the timed region); torch adds the initial state (host -> device)
+        # and the loss scalar (device -> host)
+        h2d = int(lib_h2d // args.steps + s12 * 16)
+        d2h = int(lib_d2h // args.steps + 16)
         line = {
             "metric": "evolution steps/sec (DP5 steps, forward+gradient)", "value": value,
             "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -311,6 +518,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof, "roofline_hpsi": roof_h, "roofline_n23": roof23,
+            "fwd_grad_n26": fwd_grad, "c3_batch": c3, "c4_lindblad": c4,
             "roofline_workload": {"bound": "latency", "achieved": 576.0 * s12 * total_steps / world / t_res / 1e9 * 2,
                                   "peak": peak, "unit": "GB/s",
                                   "note": "N=12: 64 KiB vectors live in registers/L2 (one cooperative kernel per sweep); "
@@ -376,6 +584,46 @@ def cpu_sample(seed: int, budget_s: float = 20.0):
             "sample": f"first {n_int} of 55 tsave intervals of the same N=12 workload "
                       f"({steps} DP5 steps forward + tape gradient, {dt:.1f} s)",
             "seconds": dt, "dp5_steps": steps}
+
+
+def cpu_extras():
+    """the CPU path on C1 (2 atoms, forward + gradient) and the cost of one
+    H(t) re-assembly + sparse H.psi per register size (what every Runge-Kutta stage pays on the CPU)."""
+    import math
+    from helpers import Channel, Problem
+    from oracle.ref_solvers import SolverType
+    torch.set_num_threads(os.cpu_count() or 1)
+    amp = torch.full((1000,), 5.0, dtype=torch.float64, requires_grad=True)
+    z = torch.zeros(1000, dtype=torch.float64)
+    p = Problem(torch.tensor([[0.0, 0.0], [8.0, 0.0]], dtype=torch.float64), 5420158.53, [Channel(amp, z, z)],
+                rate=1.0, evaluation_times="Minimal")
+    ref = p.ref()
+    t0 = time.perf_counter()
+    res = ref.run(solver=SolverType.DP5_SE)
+    loss = (res.states[-1].abs() ** 2)[0].sum()
+    torch.autograd.grad(loss, [amp])
+    c1_s = time.perf_counter() - t0
+    c1_steps = sum(1 for r in res.steplog if r[2])
+    sweep = []
+    for n in (8, 10, 12):
+        zz = torch.zeros(201, dtype=torch.float64)
+        pr = Problem(chain_coords(n), C6, [Channel(zz + 3.0, zz - 1.0, zz)], rate=0.05).ref()
+        psi = torch.randn(2 ** n, 1, dtype=torch.complex128)
+        pr.ham.H(0.05) @ psi
+        reps = 5 if n < 12 else 2
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            Hm = pr.ham.H(0.05)
+        t1 = time.perf_counter()
+        for _ in range(reps):
+            Hm @ psi
+        t2 = time.perf_counter()
+        sweep.append({"n": n, "assemble_ms": (t1 - t0) * 1e3 / reps, "spmm_ms": (t2 - t1) * 1e3 / reps})
+    return {"c1": {"workload": "C1: 2 atoms, constant pulse 1000 ns, rate 1.0, DP5_SE forward + gradient",
+                   "seconds": c1_s, "dp5_steps": c1_steps, "steps_per_s": c1_steps / c1_s},
+            "hpsi_per_call_ms": sweep,
+            "infeasible": "N >= 18 on the CPU path: COO H(t) has ~2^N (N+1) entries of 32 B re-assembled at every "
+                          "stage (N=26: 58 GB per assembly) plus a tape of 7 stage vectors per step"}
 
 
 def run_reference(args):
@@ -500,6 +748,7 @@ def main():
     ap.add_argument("--roofline-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-n23", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline + roofline only (no fwd+grad N=26, C3, C4 legs)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--workload", default="c2", choices=["c2", "sharded"])
     ap.add_argument("--local-qubits", type=int, default=26)

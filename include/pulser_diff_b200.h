@@ -234,6 +234,10 @@ int pd_bench_dp5_steps(pd_plan* p, void* stream, double t0, double dt, int32_t s
 /* ---- introspection ------------------------------------------------------------------------ */
 /* number of CUDA kernels this plan has launched since creation (bench.py gpu_launches) */
 int64_t pd_plan_launch_count(const pd_plan* p);
+/* Bytes this library has copied host->device / device->host (every cudaMemcpyAsync call site of the
+ * library is counted) since the process started or since the last call with reset != 0.  bench.py
+ * reads it around the timed end-to-end region: e2e.h2d_bytes_per_step / d2h_bytes_per_step. */
+int pd_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int32_t reset);
 /* 1 if this library was built with the CUDA backend, 0 for the host stand-in used by tests */
 int pd_is_cuda(void);
 

@@ -49,7 +49,7 @@ EXPORTS = (
     "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
     "pd_evolve_forward_units", "pd_evolve_backward_units", "pd_tape_unit_steps",
     "pd_tape_destroy", "pd_expect_diag", "pd_sharded_accumulate", "pd_lincomb", "pd_dp5_error_sumsq", "pd_bench_hpsi", "pd_bench_dp5_steps",
-    "pd_plan_launch_count", "pd_is_cuda",
+    "pd_plan_launch_count", "pd_transfer_counters", "pd_is_cuda",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -94,6 +94,14 @@ def _declare(lib: C.CDLL) -> None:
     lib.pd_bench_dp5_steps.argtypes = [vp, vp, dbl, dbl, i32, vp, pdbl]
     lib.pd_plan_launch_count.argtypes = [vp]
     lib.pd_plan_launch_count.restype = i64
+    lib.pd_transfer_counters.argtypes = [C.POINTER(i64), C.POINTER(i64), i32]
+
+
+def transfer_counters(reset: bool = False) -> tuple[int, int]:
+    """(host->device, device->host) bytes copied by the library so far (see pd_transfer_counters)."""
+    a, b = C.c_int64(0), C.c_int64(0)
+    _check(lib().pd_transfer_counters(C.byref(a), C.byref(b), 1 if reset else 0))
+    return int(a.value), int(b.value)
 
 
 def use_library(path: Optional[str]) -> None:
@@ -358,33 +366,51 @@ class Plan:
         state0 = self._vec(state0, "state0", (n_units,))
         ts = tsave.detach().to("cpu", torch.float64).contiguous()
         n_t = int(ts.numel())
-        dv = det_values.detach().to("cpu", torch.float64).contiguous()
-        av = torch.view_as_real(amp_values.detach().to("cpu", torch.complex128).contiguous()).contiguous()
-        if tuple(dv.shape) != (n_units, self.n_det, self.n_samples) or \
-                tuple(av.shape) != (n_units, self.n_amp, self.n_samples, 2):
-            raise ValueError("per-unit coefficient tables must be (U, n_terms, n_samples) matching the plan")
+        dv, av, dvp, avp = self._unit_tables(det_values, amp_values, n_units)
         states = torch.empty((n_units, n_t, self.batch, self.dim), dtype=torch.complex128, device=state0.device)
         o = self._options_struct(opt)
         tape_ptr = C.c_void_p()
         _check(lib().pd_evolve_forward_units(self._ptr, _stream(self.device), C.byref(o), n_units,
-                                             _dptr(state0), _hdbl(ts), n_t, _hdbl(dv), _hdbl(av),
+                                             _dptr(state0), _hdbl(ts), n_t, dvp, avp,
                                              _dptr(states), C.byref(tape_ptr) if want_tape else None))
         return states, (Tape(tape_ptr.value) if want_tape else None)
+
+    def _unit_tables(self, det_values: torch.Tensor, amp_values: torch.Tensor, n_units: int):
+        """Per-unit coefficient tables as (tensors kept alive, double* det, double* amp).  Tables that
+        already live on the plan's device cross the ABI as device pointers (no host round trip); the
+        library tells the two apart (include/pulser_diff_b200.h, pd_evolve_forward_units)."""
+        on_dev = det_values.is_cuda and amp_values.is_cuda and det_values.device == amp_values.device
+        where = det_values.device if on_dev else "cpu"
+        dv = det_values.detach().to(where, torch.float64).contiguous()
+        av = torch.view_as_real(amp_values.detach().to(where, torch.complex128).contiguous()).contiguous()
+        if tuple(dv.shape) != (n_units, self.n_det, self.n_samples) or \
+                tuple(av.shape) != (n_units, self.n_amp, self.n_samples, 2):
+            raise ValueError("per-unit coefficient tables must be (U, n_terms, n_samples) matching the plan")
+        pd_ = C.POINTER(C.c_double)
+        if on_dev:
+            return dv, av, C.cast(C.c_void_p(dv.data_ptr()), pd_), C.cast(C.c_void_p(av.data_ptr()), pd_)
+        return dv, av, _hdbl(dv), _hdbl(av)
 
     def evolve_backward_units(self, tape: Tape, states: torch.Tensor, grad_states: torch.Tensor,
                               det_values: torch.Tensor, amp_values: torch.Tensor, want_state0: bool):
         n_units, n_t = int(states.shape[0]), int(states.shape[1])
         states = self._vec(states, "states", (n_units, n_t))
         grad_states = self._vec(grad_states, "grad_states", (n_units, n_t))
-        dv = det_values.detach().to("cpu", torch.float64).contiguous()
-        av = torch.view_as_real(amp_values.detach().to("cpu", torch.complex128).contiguous()).contiguous()
-        g_det = torch.zeros((n_units, self.n_det, self.n_samples), dtype=torch.float64) if self.n_det else None
-        g_amp = torch.zeros((n_units, self.n_amp, self.n_samples, 2), dtype=torch.float64) if self.n_amp else None
+        dv, av, dvp, avp = self._unit_tables(det_values, amp_values, n_units)
+        where = dv.device
+        g_det = torch.zeros((n_units, self.n_det, self.n_samples), dtype=torch.float64, device=where) if self.n_det else None
+        g_amp = torch.zeros((n_units, self.n_amp, self.n_samples, 2), dtype=torch.float64, device=where) if self.n_amp else None
         g_s0 = torch.empty((n_units, self.batch, self.dim), dtype=torch.complex128,
                            device=states.device) if want_state0 else None
+        pd_ = C.POINTER(C.c_double)
+
+        def ptr(x):
+            if x is None:
+                return None
+            return C.cast(C.c_void_p(x.data_ptr()), pd_) if x.is_cuda else _hdbl(x)
+
         _check(lib().pd_evolve_backward_units(self._ptr, _stream(self.device), tape.ptr, _dptr(states),
-                                              _dptr(grad_states), _hdbl(dv), _hdbl(av), _hdbl(g_det),
-                                              _hdbl(g_amp), _dptr(g_s0)))
+                                              _dptr(grad_states), dvp, avp, ptr(g_det), ptr(g_amp), _dptr(g_s0)))
         if g_amp is not None:
             g_amp = torch.view_as_complex(g_amp)
         return g_det, g_amp, g_s0

@@ -285,6 +285,14 @@ int pd_bench_dp5_steps(pd_plan* p, void* stream, double t0, double dt, int32_t s
     *ms_per_step_host = p->eng.bench_dp5((pd::cplx*)y_dev, t0, dt, steps, stream);
   });
 }
+int pd_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int32_t reset) {
+  return guarded([&] {
+    long long a = 0, b = 0;
+    PD_BACKEND::transfer_counters(&a, &b, reset != 0);
+    if (h2d_bytes) *h2d_bytes = a;
+    if (d2h_bytes) *d2h_bytes = b;
+  });
+}
 int64_t pd_plan_launch_count(const pd_plan* p) { return p ? p->eng.launches : 0; }
 
 }  // extern "C"

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdio>
 
 #include "pd_common.hpp"
@@ -24,6 +25,43 @@ namespace pd {
     if (_e != cudaSuccess)                                                               \
       throw Error(PD_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));      \
   } while (0)
+
+// Host<->device copies of the library go through these two wrappers, which count the bytes
+// (C ABI pd_transfer_counters; bench.py reports them as h2d/d2h bytes per step).
+struct XferCounters {
+  std::atomic<long long> h2d{0}, d2h{0};
+};
+inline XferCounters& xfer_counters() {
+  static XferCounters c;
+  return c;
+}
+inline cudaError_t copy_h2d(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  xfer_counters().h2d += (long long)bytes;
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s);
+}
+inline cudaError_t copy_d2h(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  xfer_counters().d2h += (long long)bytes;
+  return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+}
+
+// Buffers that may live on either side (the per-unit coefficient tables and their gradients of the
+// *_units entry points): only host<->device traffic is counted.
+inline bool is_device_pointer(const void* p) {
+  cudaPointerAttributes a;
+  if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+inline cudaError_t copy_in(void* dst_dev, const void* src, size_t bytes, cudaStream_t s) {
+  if (is_device_pointer(src)) return cudaMemcpyAsync(dst_dev, src, bytes, cudaMemcpyDeviceToDevice, s);
+  return copy_h2d(dst_dev, src, bytes, s);
+}
+inline cudaError_t copy_out(void* dst, const void* src_dev, size_t bytes, cudaStream_t s) {
+  if (is_device_pointer(dst)) return cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToDevice, s);
+  return copy_d2h(dst, src_dev, bytes, s);
+}
 
 constexpr int kThreads = 256;
 constexpr int kMaxReduceBlocks = 148 * 4;
@@ -107,6 +145,13 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
 class CudaBackend {
  public:
   static constexpr bool is_cuda = true;
+  static bool on_device(const void* p) { return is_device_pointer(p); }
+  static void transfer_counters(long long* h2d, long long* d2h, bool reset) {
+    XferCounters& c = xfer_counters();
+    if (h2d) *h2d = c.h2d.load();
+    if (d2h) *d2h = c.d2h.load();
+    if (reset) { c.h2d = 0; c.d2h = 0; }
+  }
   // device guard of the C ABI (cabi_impl.hpp DeviceScope): make `dev` current, return the previous device
   static int push_device(int dev) {
     int prev = -1;
@@ -182,7 +227,7 @@ class CudaBackend {
     PD_CUDA_CHECK(cudaMemcpyAsync(d, sr, b, cudaMemcpyDeviceToDevice, st(s)));
   }
   void d2h(void* d, const void* sr, size_t b, void* s) {
-    PD_CUDA_CHECK(cudaMemcpyAsync(d, sr, b, cudaMemcpyDeviceToHost, st(s)));
+    PD_CUDA_CHECK(copy_d2h(d, sr, b, st(s)));
   }
   void sync(void* s) { PD_CUDA_CHECK(cudaStreamSynchronize(st(s))); }
   void timer_start(void* s) {
@@ -204,8 +249,7 @@ class CudaBackend {
   }
 
   void build_diag(double* diag, int nq, const double* pair_u_host, void* s) {
-    PD_CUDA_CHECK(cudaMemcpyAsync(d_pair_u_, pair_u_host, sizeof(double) * nq * nq,
-                                  cudaMemcpyHostToDevice, st(s)));
+    PD_CUDA_CHECK(copy_h2d(d_pair_u_, pair_u_host, sizeof(double) * nq * nq, st(s)));
     launch_build_diag(diag, nq, d_pair_u_, st(s));
   }
   int lincomb(const Geometry& g, cplx* out, int n_in, const cplx* const* ins, const double* w, void* s) {

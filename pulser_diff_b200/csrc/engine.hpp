@@ -186,6 +186,8 @@ class Engine {
     if (!use_small() || !bk.small_units_supported(geo, prog)) {
       // units too large for one CTA each (or no cooperative kernels in this build): one after the
       // other through the single-problem path, each with its own coefficient tables
+      if (BK::on_device(dv) || BK::on_device(av))
+        throw Error(PD_ERR_INVALID, "device-resident coefficient tables need units that fit the one-launch kernels");
       size_t nd = (size_t)prog.n_det() * prog.n_samples, na = (size_t)prog.n_amp() * prog.n_samples * 2;
       if (tapes) tapes->assign(n_units, Tape{});
       for (int u = 0; u < n_units; ++u) {
@@ -246,6 +248,9 @@ class Engine {
         return;
       }
     }
+    if (BK::on_device(dv) || BK::on_device(av) || BK::on_device(g_det) || BK::on_device(g_amp))
+      throw Error(PD_ERR_INVALID, "device-resident coefficient tables / gradients need a batch (> 1 unit) whose "
+                                  "device-side tape is still current");
     if (tapes[0].small_gen != 0 && !tapes[0].steps.empty())
       nl = bk.small_backward(geo, prog, tab, tapes[0].tsave, n_units, dv, av, st, tapes[0].small_gen, gstates,
                              want_coef, nullptr, lam, sums, stream);

@@ -87,7 +87,7 @@ static void upload_prog(SmallKetState& S, const Program& prog, const Geometry& g
       PD_CUDA_CHECK(cudaMalloc((void**)&dptr, std::max<size_t>(bytes, 64)));
       cap = bytes;
     }
-    if (bytes) PD_CUDA_CHECK(cudaMemcpyAsync(dptr, src, bytes, cudaMemcpyHostToDevice, st));
+    if (bytes) PD_CUDA_CHECK(copy_in(dptr, src, bytes, st));   // tables may already be on the device
   };
   static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "mask width");
   const size_t ns = (size_t)prog.n_samples;
@@ -145,7 +145,7 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
   P.n_replay = o.n_replay;
   const int log_cap = n_units == 1 ? (1 << 15) : (int)std::max<size_t>(256, std::min<size_t>(1 << 15, ((size_t)64 << 20) / 40 / U));
   double* d_ts = (double*)S.get(0, sizeof(double) * n_t);
-  PD_CUDA_CHECK(cudaMemcpyAsync(d_ts, tsave, sizeof(double) * n_t, cudaMemcpyHostToDevice, st));
+  PD_CUDA_CHECK(copy_h2d(d_ts, tsave, sizeof(double) * n_t, st));
   P.tsave = d_ts; P.n_t = n_t;
   P.y_io = (cplx*)S.get(1, sizeof(cplx) * L * U);
   P.k0_io = (cplx*)S.get(2, sizeof(cplx) * L * U);
@@ -162,8 +162,8 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
   if (o.n_replay > 0) {
     double* d_rd = (double*)S.get(7, sizeof(double) * o.n_replay);
     unsigned char* d_rc = (unsigned char*)S.get(8, (size_t)o.n_replay);
-    PD_CUDA_CHECK(cudaMemcpyAsync(d_rd, o.replay_dt, sizeof(double) * o.n_replay, cudaMemcpyHostToDevice, st));
-    PD_CUDA_CHECK(cudaMemcpyAsync(d_rc, o.replay_clipped, (size_t)o.n_replay, cudaMemcpyHostToDevice, st));
+    PD_CUDA_CHECK(copy_h2d(d_rd, o.replay_dt, sizeof(double) * o.n_replay, st));
+    PD_CUDA_CHECK(copy_h2d(d_rc, o.replay_clipped, (size_t)o.n_replay, st));
     P.replay_dt = d_rd; P.replay_clipped = d_rc;
   }
   if (timing) t_tape = now();
@@ -204,7 +204,7 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
     r.t = tsave[0]; r.error = 1.0; r.cache_err = 1.0;
     r.kk = -1; r.n_acc = 0; r.tape_ok = P.tapeY ? 1 : 0;
   }
-  PD_CUDA_CHECK(cudaMemcpyAsync(P.resume, rs.data(), sizeof(SkResume) * U, cudaMemcpyHostToDevice, st));
+  PD_CUDA_CHECK(copy_h2d(P.resume, rs.data(), sizeof(SkResume) * U, st));
   int launches = 0;
   std::vector<pd_step_record> chunk;
   for (;;) {
@@ -215,7 +215,7 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
     if (timing) t_launch = now();
     sk::launch_forward(prog.nq, P, nC, st);
     ++launches;
-    PD_CUDA_CHECK(cudaMemcpyAsync(rs.data(), P.resume, sizeof(SkResume) * U, cudaMemcpyDeviceToHost, st));
+    PD_CUDA_CHECK(copy_d2h(rs.data(), P.resume, sizeof(SkResume) * U, st));
     PD_CUDA_CHECK(cudaStreamSynchronize(st));
     if (timing) t_done = now();
     size_t max_rec = 0;
@@ -228,12 +228,12 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
     } else if (max_rec > 0) {
       if (U == 1) {
         chunk.resize(rs[0].n_rec);
-        PD_CUDA_CHECK(cudaMemcpyAsync(chunk.data(), P.log, sizeof(pd_step_record) * rs[0].n_rec, cudaMemcpyDeviceToHost, st));
+        PD_CUDA_CHECK(copy_d2h(chunk.data(), P.log, sizeof(pd_step_record) * rs[0].n_rec, st));
         PD_CUDA_CHECK(cudaStreamSynchronize(st));
         records[0].insert(records[0].end(), chunk.begin(), chunk.end());
       } else {
         chunk.resize((size_t)log_cap * U);
-        PD_CUDA_CHECK(cudaMemcpyAsync(chunk.data(), P.log, sizeof(pd_step_record) * log_cap * U, cudaMemcpyDeviceToHost, st));
+        PD_CUDA_CHECK(copy_d2h(chunk.data(), P.log, sizeof(pd_step_record) * log_cap * U, st));
         PD_CUDA_CHECK(cudaStreamSynchronize(st));
         for (size_t u = 0; u < U; ++u)
           records[u].insert(records[u].end(), chunk.begin() + u * log_cap, chunk.begin() + u * log_cap + rs[u].n_rec);
@@ -261,7 +261,7 @@ int small_ket_forward(SmallKetState& S, const Geometry& g, const Program& prog, 
       S.steps_on_device = dev_steps;
       if (dev_steps) {
         S.tape_attempts.resize(U);
-        PD_CUDA_CHECK(cudaMemcpyAsync(S.tape_attempts.data(), d_natt, sizeof(int) * U, cudaMemcpyDeviceToHost, st));
+        PD_CUDA_CHECK(copy_d2h(S.tape_attempts.data(), d_natt, sizeof(int) * U, st));
         PD_CUDA_CHECK(cudaStreamSynchronize(st));
       }
       ++S.tape_gen;
@@ -313,8 +313,8 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
   }
   SkStep* d_steps = (SkStep*)S.get(9, sizeof(SkStep) * hs.size());
   int* d_n = (int*)S.get(7, sizeof(int) * U);
-  PD_CUDA_CHECK(cudaMemcpyAsync(d_steps, hs.data(), sizeof(SkStep) * hs.size(), cudaMemcpyHostToDevice, st));
-  PD_CUDA_CHECK(cudaMemcpyAsync(d_n, hn.data(), sizeof(int) * U, cudaMemcpyHostToDevice, st));
+  PD_CUDA_CHECK(copy_h2d(d_steps, hs.data(), sizeof(SkStep) * hs.size(), st));
+  PD_CUDA_CHECK(copy_h2d(d_n, hn.data(), sizeof(int) * U, st));
   P.steps = d_steps; P.unit_steps = d_n; P.n_steps = (int)steps[0].size();
   P.gstates = gstates;
   P.tapeY = (const double*)S.ws[14];
@@ -348,7 +348,7 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
       d_src = d_out;
     }
     std::vector<double> all(n_out);
-    PD_CUDA_CHECK(cudaMemcpyAsync(all.data(), d_src, sizeof(double) * n_out, cudaMemcpyDeviceToHost, st));
+    PD_CUDA_CHECK(copy_d2h(all.data(), d_src, sizeof(double) * n_out, st));
     PD_CUDA_CHECK(cudaStreamSynchronize(st));
     for (size_t u = 0; u < U; ++u)
       slot_sums[u].assign(all.begin() + u * max_steps * 6 * nred,
@@ -358,7 +358,7 @@ int small_ket_backward(SmallKetState& S, const Geometry& g, const Program& prog,
   PD_CUDA_CHECK(cudaGetLastError());
   {
     int ab = 0;
-    PD_CUDA_CHECK(cudaMemcpyAsync(&ab, P.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PD_CUDA_CHECK(copy_d2h(&ab, P.abort_flag, sizeof(int), st));
     PD_CUDA_CHECK(cudaStreamSynchronize(st));
     if (ab) throw Error(PD_ERR_STATE, "small_ket_backward: exchange poll timed out");
   }
@@ -388,11 +388,11 @@ int small_ket_lanczos(SmallKetState& S, const Geometry& g1, const Program& prog,
   PD_CUDA_CHECK(cudaMemsetAsync(P.red, 0, red_bytes, st));
   PD_CUDA_CHECK(cudaMemsetAsync(P.abort_flag, 0, 64, st));
   sk::launch_lanczos(prog.nq, P, nC, st);
-  PD_CUDA_CHECK(cudaMemcpyAsync(alpha_host + j0, P.alpha + j0, sizeof(double) * (j1 - j0), cudaMemcpyDeviceToHost, st));
-  PD_CUDA_CHECK(cudaMemcpyAsync(beta_host + j0, P.beta + j0, sizeof(double) * (j1 - j0), cudaMemcpyDeviceToHost, st));
-  if (j0 == 0) PD_CUDA_CHECK(cudaMemcpyAsync(nrm, P.nrm_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+  PD_CUDA_CHECK(copy_d2h(alpha_host + j0, P.alpha + j0, sizeof(double) * (j1 - j0), st));
+  PD_CUDA_CHECK(copy_d2h(beta_host + j0, P.beta + j0, sizeof(double) * (j1 - j0), st));
+  if (j0 == 0) PD_CUDA_CHECK(copy_d2h(nrm, P.nrm_out, sizeof(double), st));
   int ab = 0;
-  PD_CUDA_CHECK(cudaMemcpyAsync(&ab, P.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PD_CUDA_CHECK(copy_d2h(&ab, P.abort_flag, sizeof(int), st));
   PD_CUDA_CHECK(cudaStreamSynchronize(st));
   if (ab) throw Error(PD_ERR_STATE, "small_ket_lanczos: exchange poll timed out");
   return 1;
@@ -461,11 +461,11 @@ int small_ket_backward_units(SmallKetState& S, const Geometry& g, const Program&
                                                           P.tab, prog.dt, ns, n_det, n_amp, d_gd, d_ga);
     PD_CUDA_CHECK(cudaGetLastError());
     ++launches;
-    if (g_det && n_det) PD_CUDA_CHECK(cudaMemcpyAsync(g_det, d_gd, sizeof(double) * U * n_det * ns, cudaMemcpyDeviceToHost, st));
-    if (g_amp && n_amp) PD_CUDA_CHECK(cudaMemcpyAsync(g_amp, d_ga, sizeof(double) * U * 2 * n_amp * ns, cudaMemcpyDeviceToHost, st));
+    if (g_det && n_det) PD_CUDA_CHECK(copy_out(g_det, d_gd, sizeof(double) * U * n_det * ns, st));
+    if (g_amp && n_amp) PD_CUDA_CHECK(copy_out(g_amp, d_ga, sizeof(double) * U * 2 * n_amp * ns, st));
   }
   int ab = 0;
-  PD_CUDA_CHECK(cudaMemcpyAsync(&ab, P.abort_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PD_CUDA_CHECK(copy_d2h(&ab, P.abort_flag, sizeof(int), st));
   PD_CUDA_CHECK(cudaStreamSynchronize(st));
   if (ab) throw Error(PD_ERR_STATE, "small_ket_backward_units: exchange poll timed out");
   (void)max_steps;

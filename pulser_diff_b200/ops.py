@@ -31,6 +31,7 @@ from ._cabi import PD_DENSITY, PD_KET, Options, Plan
 
 _program_ids = itertools.count()
 _PLAN_CACHE: dict[tuple, Plan] = {}
+_UNIT_PROGRAMS: dict[tuple, "Program"] = {}
 
 
 @dataclass
@@ -51,6 +52,7 @@ class Program:
 def clear_plan_cache() -> None:
     """Drop cached plans (frees their device workspace)."""
     _PLAN_CACHE.clear()
+    _UNIT_PROGRAMS.clear()
 
 
 def get_plan(n_qubits: int, batch: int, kind: int, device: torch.device) -> Plan:
@@ -160,9 +162,20 @@ class _EvolveUnitsFn(torch.autograd.Function):
                 pair_u: Tensor, n_qubits: int, dt: float, det_masks, amp_masks, opt: Options):
         n_units, batch = int(state0.shape[0]), int(state0.shape[1])
         plan = get_plan(n_qubits, batch, PD_KET, state0.device)
-        # the plan carries the masks, dt and sample count; its own tables are those of unit 0
-        prog = make_program(n_qubits, PD_KET, dt, det_masks, det_values[0], amp_masks, amp_values[0],
-                            pair_u, None)
+        # the plan carries the register, masks, dt and sample count; every unit brings its own tables, so
+        # the plan's own are placeholders and one Program serves every call with the same structure
+        # (no per-call reconfiguration, no device->host copy of a table)
+        pu = pair_u.detach().to("cpu", torch.float64).contiguous()
+        key = (n_qubits, float(dt), tuple(int(m) for m in det_masks), tuple(int(m) for m in amp_masks),
+               int(det_values.shape[-1]), int(amp_values.shape[-1]), pu.numpy().tobytes())
+        prog = _UNIT_PROGRAMS.get(key)
+        if prog is None:
+            prog = make_program(n_qubits, PD_KET, dt, det_masks,
+                                torch.zeros(det_values.shape[1:], dtype=torch.float64), amp_masks,
+                                torch.zeros(amp_values.shape[1:], dtype=torch.complex128), pu, None)
+            if len(_UNIT_PROGRAMS) > 64:
+                _UNIT_PROGRAMS.clear()
+            _UNIT_PROGRAMS[key] = prog
         configure(plan, prog)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
         states, tape = plan.evolve_forward_units(opt, state0.detach(), tsave, det_values, amp_values,

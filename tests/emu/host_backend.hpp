@@ -18,6 +18,8 @@ class HostBackend {
   int device = 0;
   static int push_device(int) { return 0; }
   static void pop_device(int) {}
+  static bool on_device(const void*) { return false; }
+  static void transfer_counters(long long* h2d, long long* d2h, bool) { if (h2d) *h2d = 0; if (d2h) *d2h = 0; }
   int path = 0;
   explicit HostBackend(int) {}
   void* alloc(size_t bytes) {

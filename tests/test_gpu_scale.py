@@ -229,6 +229,48 @@ def test_c2_workload_vs_oracle_first_intervals(cuda_device):
     assert (res2.states.detach().cpu() - r.states.detach()).abs().max() < 1e-7
 
 
+def test_c2_full_workload_against_oracle_fixture(cuda_device):
+    """ALL 55 tsave intervals of the C2 workload (12 atoms, 406 attempted / 223 accepted DP5 steps) against
+    the oracle's full run, stored by tests/golden/make_c2_full.py (the oracle's tape gradient alone takes
+    five minutes on the CPU): loss at every evaluation time and the final state on the shared step
+    sequence (1e-10), the gradient w.r.t. the 60 pulse parameters (1e-8 relative), and the free-running
+    controller's accept/reject log."""
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench as B
+    from helpers import Channel, Problem, golden
+    from pulser_diff_b200.utils import interpolate_sine
+
+    gold = golden("c2_full.json")
+    dev = cuda_device
+    interp = interpolate_sine(B.N_PARAM, B.DURATION).to(torch.float64)
+    ta, td = B.workload_params(0)
+    amp, det, ph = B.pulse_samples(ta, td, interp)
+    p = Problem(B.chain_coords(B.N_QUBITS), B.C6, [Channel(amp, det, ph)], rate=B.RATE)
+    em = p.emulator(dev)
+    assert (em.evaluation_times.detach().cpu() - torch.tensor(gold["tsave"], dtype=torch.float64)).abs().max() < 1e-15
+    H = em._hamiltonian._hamiltonian
+    accepted = [rec for rec in gold["steplog"] if rec[2]]
+    res = pdb.sesolve(H, em.initial_state, em.evaluation_times, pdb.SolverType.DP5_SE,
+                      options={"replay": [(dt, clipped) for (_, dt, _, _, clipped) in accepted]})
+    d = B.loss_diag(B.N_QUBITS, dev)
+    series = (d[None, :, None] * res.states.abs() ** 2).sum(dim=(1, 2))
+    assert (series.detach().cpu() - torch.tensor(gold["loss_series"], dtype=torch.float64)).abs().max() < 1e-10
+    final = torch.complex(torch.tensor(gold["final_re"], dtype=torch.float64),
+                          torch.tensor(gold["final_im"], dtype=torch.float64))
+    assert (res.states[-1].detach().cpu().reshape(-1) - final).abs().max() < 1e-10
+    ga, gd = torch.autograd.grad(series[-1], [ta, td])
+    for got, want in ((ga, gold["grad_ta"]), (gd, gold["grad_td"])):
+        want = torch.tensor(want, dtype=torch.float64)
+        assert (got.cpu() - want).abs().max() < 1e-8 * want.abs().max()
+    res2 = pdb.sesolve(H, em.initial_state, em.evaluation_times, pdb.SolverType.DP5_SE)
+    log = res2.step_log()
+    assert [bool(a["accepted"]) for a in log] == [bool(b[2]) for b in gold["steplog"]]
+    assert (res2.states[-1].detach().cpu().reshape(-1) - final).abs().max() < 1e-7
+
+
 def test_small_tape_overwritten_falls_back(cuda_device):
     """Two evolutions on the same plan, then the gradient of the FIRST: its device-side stage tape
     has been overwritten by the second, so the adjoint must fall back to the recomputing sweep and
