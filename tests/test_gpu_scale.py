@@ -229,6 +229,46 @@ def test_c2_workload_vs_oracle_first_intervals(cuda_device):
     assert (res2.states.detach().cpu() - r.states.detach()).abs().max() < 1e-7
 
 
+@pytest.mark.parametrize("n", [16, 18])
+def test_large_register_families_against_oracle_sparse_h(cuda_device, n):
+    """Every kernel family of the large registers DIRECTLY against the oracle's sparse-COO H(t)
+    (reference hamiltonian.py:526-546 restated), not only against each other: H(t) psi at three times for
+    the gather (path 1), tiled (path 2) and stream (path 4) kernels, with a global drive that carries a
+    phase plus local drives / detunings on qubits of the low, middle and top bit groups; and, at N = 16, a
+    short DP5 evolution on the oracle's step sequence."""
+    from helpers import C6_60, Channel, Problem, chain
+    dev = cuda_device
+    T = 40
+    g = torch.Generator().manual_seed(n)
+    r = lambda: torch.rand(T, dtype=torch.float64, generator=g)
+    chans = [Channel(3 * r(), r() - 0.5, r())] + [Channel(r(), 2 * r() - 1, r(), "Local", q) for q in (1, n // 2, n - 2)]
+    p = Problem(chain(n), C6_60, chans, rate=1.0)
+    ref = p.ref()
+    em = p.emulator(dev)
+    H = em._hamiltonian._hamiltonian
+    dm, dv, am, av = H.masks_and_values()
+    psi = torch.randn(2 ** n, 1, dtype=torch.complex128, generator=g)
+    psi_d = psi.T.contiguous().to(dev)
+    plan = ops.get_plan(n, 1, _cabi.PD_KET, dev)
+    for t in (0.0, 0.0123, 0.0377):
+        want = (ref.ham.H(torch.tensor(t, dtype=torch.float64)) @ psi).T
+        for path in (1, 2, 4):
+            plan.set_path(path)
+            got = torch.ops.pulser_diff_b200.hpsi(psi_d, t, dv, av, H.pair_u.detach(), dm, am, H.dt).cpu()
+            assert (got - want).abs().max() < 1e-12 * want.abs().max(), (path, t)
+    plan.set_path(0)
+    if n > 16:
+        return
+    from oracle.ref_solvers import SolverType as RefSolver, sesolve as ref_sesolve
+    psi0 = psi / psi.norm()
+    ts = torch.tensor([0.0, 0.004, 0.009], dtype=torch.float64)
+    rr = ref_sesolve(ref.ham.H, psi0, ts, RefSolver.DP5_SE, {})
+    replay = [(dt, clipped) for (_, dt, acc, _, clipped) in rr.steplog if acc]
+    for path in (2, 4):
+        res = pdb.sesolve(H, psi0, ts, pdb.SolverType.DP5_SE, options={"replay": replay, "path": path})
+        assert (res.states.detach().cpu() - rr.states).abs().max() < 1e-12, path
+
+
 def test_c2_full_workload_against_oracle_fixture(cuda_device):
     """ALL 55 tsave intervals of the C2 workload (12 atoms, 406 attempted / 223 accepted DP5 steps) against
     the oracle's full run, stored by tests/golden/make_c2_full.py (the oracle's tape gradient alone takes

@@ -148,12 +148,19 @@ def test_ket_states_and_gradients(engine_device, solver, local, kpath):
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("noise", [
-    {"dephasing_rate": 0.7, "relaxation_rate": 0.3},
-    {"depolarizing_rate": 0.4, "eff_noise": [(0.2, [[0, 1], [1, 0]]), (0.1, [[0.3, 0.5j], [0.2, -0.1]])]},
+@pytest.mark.parametrize("n,noise", [
+    (3, {"dephasing_rate": 0.7, "relaxation_rate": 0.3}),
+    (3, {"depolarizing_rate": 0.4, "eff_noise": [(0.2, [[0, 1], [1, 0]]), (0.1, [[0.3, 0.5j], [0.2, -0.1]])]}),
+    # N = 5 (32 x 32 density matrix, 1024-entry vec(rho)): each noise kind on its own and all four together
+    (5, {"dephasing_rate": 0.5}),
+    (5, {"relaxation_rate": 0.1}),
+    (5, {"depolarizing_rate": 0.2}),
+    (5, {"eff_noise": [(0.15, [[0, 1], [1, 0]]), (0.05, [[0.3, 0.5j], [0.2, -0.1]])]}),
+    (5, {"dephasing_rate": 0.5, "relaxation_rate": 0.1, "depolarizing_rate": 0.2,
+         "eff_noise": [(0.15, [[0, -1j], [1j, 0]])]}),
 ])
-def test_lindblad_states_and_gradients(engine_device, noise):
-    p = random_problem(3, seed=5, noise=noise)
+def test_lindblad_states_and_gradients(engine_device, n, noise):
+    p = random_problem(n, seed=5, noise=noise, T=300 if n == 3 else 120)
     ref = p.ref()
     r = ref.run(time_grad=True, solver=RefSolver.DP5_ME)
     loss_r, leaves_r = _loss_and_leaves(p, r.states, ref.evaluation_times, [])
@@ -162,6 +169,13 @@ def test_lindblad_states_and_gradients(engine_device, noise):
     res = em.run(time_grad=True)              # Lindblad noise forces DP5_ME (backend.py:477-483)
     assert res.states.shape == r.states.shape
     assert (res.states.detach().cpu() - r.states.detach()).abs().max() < ATOL_STATE
+    if n > 3:
+        # gradients on the oracle's step sequence (shared-step protocol): two free-running
+        # controllers agree on every accept/reject but their step sizes differ by ~1e-5 relative through
+        # the rounding of the error norm, which moves these gradients by ~2e-8
+        em = p.emulator(engine_device)
+        res = em.run(time_grad=True, replay=[(dt, c) for (_, dt, acc, _, c) in r.steplog if acc])
+        assert (res.states.detach().cpu() - r.states.detach()).abs().max() < 1e-10
     loss, leaves = _loss_and_leaves(p, res.states, em.evaluation_times, [])
     g = torch.autograd.grad(loss, leaves)
     for a, b in zip(g, g_ref):
@@ -556,3 +570,45 @@ def test_generator_vjp_time_gradient(engine_device):
     eps = 1e-4
     fd = (f(t + eps) - f(t - eps)) / (2 * eps)
     assert abs(g_t - fd) < 1e-9 * max(1.0, abs(fd))
+
+
+@pytest.mark.parametrize("n_sets", [pytest.param(6, id="slice6"), pytest.param(64, id="slice64", marks=pytest.mark.gpu)])
+def test_parameter_set_batch_slice_against_oracle(engine_device, n_sets):
+    """A slice of the real C3 workload (BASELINE configs[2]: 2 atoms 6.5 um apart, 8 constant pulses x 131 ns
+    with their own amplitude / detuning / phase, psi0 = eye(4), rate 0.05, Hadamard x Hadamard infidelity)
+    through ``ops.evolve_units`` -- one launch for all sets, tables built on the engine's device -- against
+    the oracle run set by set: every set's infidelity and its gradient w.r.t. the 24 parameters.  Both
+    sides run their own default controller (pyqtorch's atol 1e-8 / rtol 1e-6); the step sequences
+    coincide, the step sizes up to the rounding of the error norm, hence 1e-9 / 1e-7 here (the
+    shared-step tests above hold 1e-10 / 1e-8)."""
+    import os
+    import sys
+    from pulser_diff_b200 import ops
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench as B
+    from helpers import C6_60, Channel
+    from oracle.ref_solvers import sesolve as ref_sesolve
+    if engine_device.type == "cpu" and n_sets > 8:
+        pytest.skip("the 64-set slice runs on the GPU tier")
+    idx, tsave, pair_u, target = B.c3_setup(engine_device)
+    g = torch.Generator().manual_seed(0)
+    params_all = torch.rand(B.C3["n_sets"], 3, B.C3["pulses"], dtype=torch.float64, generator=g) * 4 * math.pi
+    params = params_all[:n_sets].to(engine_device).requires_grad_(True)
+    dv, av = B.c3_tables(params, idx.to(engine_device))
+    psi0 = torch.eye(4, dtype=torch.complex128, device=engine_device).repeat(n_sets, 1, 1)
+    st = ops.evolve_units(psi0, tsave, dv, av, pair_u, n_qubits=2, dt=0.001 / B.C3["rate"], det_masks=[3], amp_masks=[3])
+    Uf = st[:, -1].transpose(1, 2)
+    loss = 1 - (target.to(engine_device).conj().T @ Uf).diagonal(dim1=1, dim2=2).sum(-1).abs() / 4
+    (gp,) = torch.autograd.grad(loss.sum(), [params])
+    coords = torch.tensor([[-3.25, 0.0], [3.25, 0.0]], dtype=torch.float64)
+    for u in range(n_sets):
+        pu = params_all[u].clone().requires_grad_(True)
+        amp, det, ph = (pu[k].repeat_interleave(B.C3["dur"]) for k in range(3))
+        ref = Problem(coords, C6_60, [Channel(amp, det, ph)], rate=B.C3["rate"]).ref()
+        ref.set_initial_state(torch.eye(4))
+        assert (ref.evaluation_times - tsave).abs().max() < 1e-15
+        r = ref_sesolve(ref.ham.H, ref.initial_state, ref.evaluation_times, RefSolver.DP5_SE, {})
+        l_ref = 1 - torch.abs(torch.trace(target.mH @ r.states[-1])) / 4
+        (g_ref,) = torch.autograd.grad(l_ref, [pu])
+        assert abs(loss[u].item() - l_ref.item()) < 1e-9, u
+        assert (gp[u].cpu() - g_ref).abs().max() < 1e-7 * g_ref.abs().max(), u
