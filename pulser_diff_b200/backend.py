@@ -20,7 +20,7 @@ from torch import Tensor
 from .hamiltonian import Hamiltonian
 from .samples import SequenceSamples
 from .simconfig import SimConfig
-from .simresults import CoherentResults
+from .simresults import CoherentResults, NoisyResults
 from .solvers import SolverType, mesolve, sesolve
 
 C128 = torch.complex128
@@ -189,6 +189,8 @@ class TorchEmulator:
             self._hamiltonian.refresh_couplings()
         if self.config.has_lindblad:
             solver = SolverType.DP5_ME
+        if self.config.needs_resampling:
+            return self._run_noisy(solver, options)
         ham = self._hamiltonian._hamiltonian
         if solver in (SolverType.DP5_SE, SolverType.KRYLOV_SE):
             result = sesolve(H=ham, psi0=self.initial_state, tsave=self._eval_times_array,
@@ -201,5 +203,68 @@ class TorchEmulator:
         else:
             raise ValueError(f"Solver {solver} not available.")
         self._last_result = result
+        meas = ({"epsilon": self.config.epsilon, "epsilon_prime": self.config.epsilon_prime}
+                if "SPAM" in self.config.noise else None)
         return CoherentResults(result.states, self._hamiltonian._size, self._hamiltonian.basis_name,
-                               self._eval_times_array, self._meas_basis)
+                               self._eval_times_array, self._meas_basis, meas)
+
+    def _run_noisy(self, solver: SolverType, options: dict,
+                   generator: Optional[torch.Generator] = None) -> NoisyResults:
+        """Averages over the random Hamiltonians of the stochastic noises (reference backend.py:568-611).
+
+        Where the reference loops ``runs`` times over ``_construct_hamiltonian`` + solver, the draws are
+        made up front and all runs that share a set of badly prepared atoms go to the device as ONE
+        batch of parameter sets (``ops.evolve_units``: a single launch for registers of <= 14 atoms);
+        Lindblad noise on top runs them one after the other through ``mesolve``.  Bitstring counts are
+        sampled on the device per run and evaluation time, ``samples_per_run`` shots each."""
+        from collections import Counter
+        from . import _cabi, ops
+        from .hamiltonian import StructuredHamiltonian
+        cfg, ham = self.config, self._hamiltonian
+        n, dev = ham._size, ham.torch_device
+        noise = set(cfg.noise)
+        generator = generator if generator is not None else getattr(self, "noise_generator", None)
+        resample = "doppler" in noise or ("amplitude" in noise and cfg.amp_sigma != 0.0)
+        if resample:
+            draws = [(ham.noise_realisation(generator), 1) for _ in range(cfg.runs)]
+        else:       # SPAM only: distinct preparation patterns with their multiplicities, nothing else random
+            pats = Counter(tuple((torch.rand(n, dtype=torch.float64, generator=generator) < cfg.eta).tolist())
+                           for _ in range(cfg.runs))
+            draws = [(ham.noise_realisation(generator, bad_atoms=torch.tensor(p), resample=False), reps)
+                     for p, reps in pats.most_common()]
+        self._last_noise_draws, self._last_noisy_states = draws, []
+        meas = ({"epsilon": cfg.epsilon, "epsilon_prime": cfg.epsilon_prime} if "SPAM" in noise else None)
+        times = self._eval_times_array
+        total = [Counter() for _ in range(len(times))]
+        groups: dict = {}
+        for d, reps in draws:
+            groups.setdefault(tuple(d["bad_atoms"].tolist()), []).append((d, reps))
+        psi0 = self.initial_state.to(device=dev, dtype=C128).transpose(0, 1).contiguous()
+        for members in groups.values():
+            d0 = members[0][0]
+            if solver == SolverType.DP5_SE:
+                dv = torch.stack([d["det_values"] for d, _ in members])
+                av = torch.stack([d["amp_values"] for d, _ in members])
+                st = ops.evolve_units(psi0.repeat(len(members), 1, 1), times.detach(), dv, av, d0["pair_u"],
+                                      n_qubits=n, dt=d0["dt"], det_masks=d0["det_masks"], amp_masks=d0["amp_masks"],
+                                      options=_cabi.Options.from_dict(options))
+                per_run = [st[u].permute(0, 2, 1) for u in range(len(members))]
+            else:
+                per_run = []
+                for d, _ in members:
+                    H = StructuredHamiltonian(n, d["pair_u"], d["dt"], d["n_samples"],
+                                              list(zip(d["det_masks"], d["det_values"])),
+                                              list(zip(d["amp_masks"], d["amp_values"])), dev)
+                    if solver == SolverType.DP5_ME:
+                        psi = self.initial_state
+                        per_run.append(mesolve(H, torch.matmul(psi, psi.mH).unsqueeze(-1), ham._collapse_ops,
+                                               times, solver, options).states)
+                    else:
+                        per_run.append(sesolve(H, self.initial_state, times, solver, options).states)
+            self._last_noisy_states = getattr(self, "_last_noisy_states", [])
+            self._last_noisy_states += [(d, st_) for st_, (d, _) in zip(per_run, members)]
+            for states, (_, reps) in zip(per_run, members):
+                res = CoherentResults(states, n, ham.basis_name, times, self._meas_basis, meas)
+                for k, t in enumerate(times.tolist()):
+                    total[k] += res.sample_state(t, n_samples=cfg.samples_per_run * reps)
+        return NoisyResults(total, n, ham.basis_name, times, cfg.runs * cfg.samples_per_run)

@@ -271,5 +271,72 @@ class Hamiltonian:
         jj = torch.tensor([self._pair_index[k][1] for k in keys])
         return out.index_put((ii, jj), vals.to(torch.float64))
 
+    # ---- stochastic noise (reference hamiltonian.py:179-219, 270-286; backend.py:568-611) ---------
+    def noise_realisation(self, generator: Optional[torch.Generator] = None,
+                          bad_atoms: Optional[Tensor] = None, resample: bool = True) -> dict:
+        """One random Hamiltonian of the noisy sequence, as structure: per-qubit coefficient tables
+        (``det_values`` (N, n_samples) float64, ``amp_values`` (N, n_samples) complex128 with masks
+        ``1 << q``), the pair couplings with badly prepared atoms removed, and the draws themselves.
+
+        Follows the reference's order of operations: every channel is expanded to per-qubit samples
+        (``to_nested_dict(all_local=True)``), then, channel by channel and pulse slot by pulse slot, the
+        Doppler offset of each targeted atom is added to its detuning inside the slot and -- for Global
+        channels -- the amplitude inside the slot is scaled by one Gaussian draw per slot times the beam
+        profile ``exp(-(r / w0)^2)``; samples of badly prepared atoms are zeroed and they drop out of
+        the interaction.  ``resample=False`` keeps the deterministic parts only (the reference's
+        ``update=False`` runs over SPAM configurations)."""
+        from .simconfig import doppler_sigma
+        cfg, n, D = self._config, self._size, self._duration
+        qids = list(self._qdict)
+        noise = set(cfg.noise_types)
+
+        def normal(mean: float, std: float, size: int) -> Tensor:
+            if std == 0.0:
+                return torch.full((size,), float(mean), dtype=torch.float64)
+            return mean + std * torch.randn(size, dtype=torch.float64, generator=generator)
+
+        if bad_atoms is None:
+            bad_atoms = (torch.rand(n, dtype=torch.float64, generator=generator) < cfg.eta
+                         if ("SPAM" in noise and cfg.eta > 0 and resample) else torch.zeros(n, dtype=torch.bool))
+        bad_atoms = torch.as_tensor(bad_atoms, dtype=torch.bool)
+        doppler = (normal(0.0, doppler_sigma(cfg.temperature * 1e-6), n) if ("doppler" in noise and resample)
+                   else torch.zeros(n, dtype=torch.float64))
+        arr = {k: torch.zeros(n, D, dtype=torch.float64) for k in ("amp", "det", "phase")}
+        plan = []
+        for c in self.samples_obj.channels:
+            everyone = qids if c.addressing == "Global" else list(c.targets or [])
+            from .samples import Slot
+            for slot in (c.slots or [Slot(0, c.duration, set(everyone))]):
+                rows = [self._qid_index[q] for q in (slot.targets or everyone)]
+                for k in ("amp", "det", "phase"):
+                    arr[k][rows, slot.ti:slot.tf] += getattr(c, k).detach()[slot.ti:slot.tf]
+                plan.append((c.addressing == "Global", slot.ti, slot.tf, rows))
+        amp_draws = []
+        for is_global, ti, tf, rows in plan:
+            base = max(0.0, float(normal(1.0, cfg.amp_sigma if resample else 0.0, 1)))
+            amp_draws.append(base)
+            if "doppler" in noise:
+                arr["det"][rows, ti:tf] += doppler[rows, None]
+            if "amplitude" in noise and is_global:
+                frac = torch.ones(len(rows), dtype=torch.float64)
+                if cfg.laser_waist is not None:
+                    r = torch.stack([torch.linalg.norm(self._qdict[qids[i]].detach()) for i in rows])
+                    frac = torch.exp(-((r / float(cfg.laser_waist)) ** 2))
+                arr["amp"][rows, ti:tf] *= (base * frac)[:, None]
+        for k in arr:
+            arr[k][bad_atoms] = 0.0
+        keep = torch.linspace(0, D - 1, int(self._sampling_rate * D), dtype=torch.int).long()
+        pair_u = self._pair_couplings().detach().clone()
+        pair_u[bad_atoms, :] = 0.0
+        pair_u[:, bad_atoms] = 0.0
+        if n - int(bad_atoms.sum()) <= 1:
+            pair_u.zero_()
+        return {"det_masks": [1 << q for q in range(n)], "amp_masks": [1 << q for q in range(n)],
+                "det_values": (-0.5 * arr["det"])[:, keep],
+                "amp_values": (0.5 * arr["amp"] * torch.exp(-1j * arr["phase"]))[:, keep],
+                "pair_u": pair_u, "bad_atoms": bad_atoms, "doppler": doppler, "amp_draws": amp_draws,
+                "samples": arr,                      # the (N, T+1) per-qubit arrays the tables were cut from
+                "dt": self._dt, "n_samples": self._n_samples}
+
     def refresh_couplings(self) -> None:
         self._hamiltonian.pair_u = self._pair_couplings()
