@@ -577,13 +577,15 @@ def test_parameter_set_batch_slice_against_oracle(engine_device, n_sets):
     """A slice of the real C3 workload (BASELINE configs[2]: 2 atoms 6.5 um apart, 8 constant pulses x 131 ns
     with their own amplitude / detuning / phase, psi0 = eye(4), rate 0.05, Hadamard x Hadamard infidelity)
     through ``ops.evolve_units`` -- one launch for all sets, tables built on the engine's device -- against
-    the oracle run set by set: every set's infidelity and its gradient w.r.t. the 24 parameters.  Both
-    sides run their own default controller (pyqtorch's atol 1e-8 / rtol 1e-6); the step sequences
-    coincide, the step sizes up to the rounding of the error norm, hence 1e-9 / 1e-7 here (the
-    shared-step tests above hold 1e-10 / 1e-8)."""
+    the oracle run set by set: every set's infidelity and its gradient w.r.t. the 24 parameters.
+
+    Two tiers (SURVEY.md 7 H1): the first sets with BOTH sides at tight solver tolerances (1e-9 / 1e-7);
+    the whole slice with pyqtorch's default controller on both sides (atol 1e-8, rtol 1e-6), where two
+    implementations agree only to the solver tolerance because a marginal accept/reject decision at a pulse
+    edge may fall differently (observed: 1e-6 on one set of 64)."""
     import os
     import sys
-    from pulser_diff_b200 import ops
+    from pulser_diff_b200 import _cabi, ops
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import bench as B
     from helpers import C6_60, Channel
@@ -593,22 +595,38 @@ def test_parameter_set_batch_slice_against_oracle(engine_device, n_sets):
     idx, tsave, pair_u, target = B.c3_setup(engine_device)
     g = torch.Generator().manual_seed(0)
     params_all = torch.rand(B.C3["n_sets"], 3, B.C3["pulses"], dtype=torch.float64, generator=g) * 4 * math.pi
-    params = params_all[:n_sets].to(engine_device).requires_grad_(True)
-    dv, av = B.c3_tables(params, idx.to(engine_device))
-    psi0 = torch.eye(4, dtype=torch.complex128, device=engine_device).repeat(n_sets, 1, 1)
-    st = ops.evolve_units(psi0, tsave, dv, av, pair_u, n_qubits=2, dt=0.001 / B.C3["rate"], det_masks=[3], amp_masks=[3])
-    Uf = st[:, -1].transpose(1, 2)
-    loss = 1 - (target.to(engine_device).conj().T @ Uf).diagonal(dim1=1, dim2=2).sum(-1).abs() / 4
-    (gp,) = torch.autograd.grad(loss.sum(), [params])
     coords = torch.tensor([[-3.25, 0.0], [3.25, 0.0]], dtype=torch.float64)
-    for u in range(n_sets):
+
+    def engine(n_units, options):
+        params = params_all[:n_units].to(engine_device).requires_grad_(True)
+        dv, av = B.c3_tables(params, idx.to(engine_device))
+        psi0 = torch.eye(4, dtype=torch.complex128, device=engine_device).repeat(n_units, 1, 1)
+        st = ops.evolve_units(psi0, tsave, dv, av, pair_u, n_qubits=2, dt=0.001 / B.C3["rate"], det_masks=[3],
+                              amp_masks=[3], options=options)
+        Uf = st[:, -1].transpose(1, 2)
+        loss = 1 - (target.to(engine_device).conj().T @ Uf).diagonal(dim1=1, dim2=2).sum(-1).abs() / 4
+        (gp,) = torch.autograd.grad(loss.sum(), [params])
+        return loss.detach().cpu(), gp.cpu()
+
+    def oracle(u, options):
         pu = params_all[u].clone().requires_grad_(True)
         amp, det, ph = (pu[k].repeat_interleave(B.C3["dur"]) for k in range(3))
         ref = Problem(coords, C6_60, [Channel(amp, det, ph)], rate=B.C3["rate"]).ref()
         ref.set_initial_state(torch.eye(4))
         assert (ref.evaluation_times - tsave).abs().max() < 1e-15
-        r = ref_sesolve(ref.ham.H, ref.initial_state, ref.evaluation_times, RefSolver.DP5_SE, {})
+        r = ref_sesolve(ref.ham.H, ref.initial_state, ref.evaluation_times, RefSolver.DP5_SE, options)
         l_ref = 1 - torch.abs(torch.trace(target.mH @ r.states[-1])) / 4
         (g_ref,) = torch.autograd.grad(l_ref, [pu])
-        assert abs(loss[u].item() - l_ref.item()) < 1e-9, u
-        assert (gp[u].cpu() - g_ref).abs().max() < 1e-7 * g_ref.abs().max(), u
+        return l_ref.item(), g_ref
+
+    n_tight = min(4, n_sets)
+    loss, gp = engine(n_tight, _cabi.Options(atol=1e-12, rtol=1e-11))
+    for u in range(n_tight):
+        l_ref, g_ref = oracle(u, {"atol": 1e-12, "rtol": 1e-11})
+        assert abs(loss[u].item() - l_ref) < 1e-9, u
+        assert (gp[u] - g_ref).abs().max() < 1e-7 * g_ref.abs().max(), u
+    loss, gp = engine(n_sets, None)
+    for u in range(n_sets):
+        l_ref, g_ref = oracle(u, {})
+        assert abs(loss[u].item() - l_ref) < 5e-6, u
+        assert (gp[u] - g_ref).abs().max() < 5e-5 * g_ref.abs().max(), u
