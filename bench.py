@@ -537,11 +537,11 @@ def run_b200(args):
             if done.is_set():
                 return
             if rank == 0:
-                line["sharded"] = {"error": "sharded leg did not finish within 150 s"}
+                line["sharded"] = {"error": "sharded leg did not finish within 300 s"}
                 print(json.dumps(line), flush=True)
             os._exit(0)
 
-        timer = threading.Timer(150.0, give_up)
+        timer = threading.Timer(300.0, give_up)
         timer.daemon = True
         timer.start()
         try:
@@ -654,16 +654,73 @@ def run_reference(args):
     }))
 
 
-NVLINK_PEER_GBS = 770.0     # measured peer copy per direction on this pool (profiles/r01_multi_gpu.md)
+NVLINK_PEER_GBS = 770.0     # fallback only: the peer-copy rate is measured in the same run (nvlink_measured)
+
+
+def sharded_parity(dev, rank, world, n=20):
+    """ShardedKet.evolve / evolve_backward over NVLink peer memory against the single-GPU engine on the
+    full register (N = 20, shared step sequence): max state difference and relative gradient differences,
+    max over ranks.  The driver's pytest box has one GPU, so this check lives in the bench."""
+    import torch.distributed as dist
+    from pulser_diff_b200 import _cabi, ops, parallel
+    gen = torch.Generator().manual_seed(9)
+    T = 40
+    dv = (torch.rand(2, T, dtype=torch.float64, generator=gen) - 0.5) * 4
+    av = torch.complex(torch.rand(2, T, dtype=torch.float64, generator=gen) * 3,
+                       torch.rand(2, T, dtype=torch.float64, generator=gen) - 0.5)
+    full = (1 << n) - 1
+    masks = [full, 0b101 | (1 << (n - 1))]            # a global term + one touching global AND local qubits
+    u = torch.zeros(n, n, dtype=torch.float64)
+    for i in range(n):
+        for j in range(i + 1, n):
+            u[i, j] = C6 / (SPACING * (j - i)) ** 6
+    psi0 = torch.randn(1, 2 ** n, dtype=torch.complex128, generator=gen)
+    psi0 = (psi0 / psi0.norm()).to(dev)
+    tsave = torch.tensor([0.0, 0.004, 0.009], dtype=torch.float64)
+    w = torch.rand(len(tsave), 1, 2 ** n, dtype=torch.float64, generator=gen).to(dev)
+    leaves = [x.clone().requires_grad_(True) for x in (psi0, dv, av, u)]
+    st_full = ops.evolve(leaves[0], tsave, leaves[1], leaves[2], leaves[3], n_qubits=n, kind=_cabi.PD_KET,
+                         dt=0.002, det_masks=masks, amp_masks=masks)
+    loss = (w * st_full.abs() ** 2).sum()
+    g_full = torch.autograd.grad(loss, leaves)
+    replay = [(r["t"], r["dt"], r["interval"], bool(r["clipped"])) for r in ops.last_step_log(st_full) if r["accepted"]]
+    sk = parallel.ShardedKet(n, u, 0.002, masks, dv, masks, av, dev, peer_memory=True)
+    n_loc = 2 ** sk.nl
+    sl = slice(rank * n_loc, (rank + 1) * n_loc)
+    st, steps = sk.evolve(sk.local_slice(psi0), tsave.tolist(), replay=replay)
+    state_err = (st - st_full.detach()[:, :, sl]).abs().max().item()
+    st_leaf = st.clone().requires_grad_(True)
+    (g_st,) = torch.autograd.grad((w[:, :, sl] * st_leaf.abs() ** 2).sum(), st_leaf)
+    out = sk.evolve_backward(st, g_st, steps)
+    rel = lambda a, b: ((a.cpu() - b.cpu()).abs().max() / b.abs().max().cpu()).item()
+    errs = torch.tensor([state_err, rel(out["det"], g_full[1]), rel(out["amp"], g_full[2]), rel(out["pair"], g_full[3]),
+                         rel(out["state0"], g_full[0][:, sl])], dtype=torch.float64, device=dev)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    del sk, st, st_full, st_leaf, out, w, leaves, g_full
+    ops.clear_plan_cache()
+    torch.cuda.empty_cache()
+    e = errs.tolist()
+    return {"n_qubits": n, "accepted_steps": len(replay), "state_max_abs_diff": e[0], "grad_det_rel": e[1],
+            "grad_amp_rel": e[2], "grad_pair_rel": e[3], "grad_psi0_rel": e[4],
+            "ok": bool(e[0] < 1e-10 and max(e[1:]) < 1e-8)}
 
 
 def sharded_measure(dev, rank, world, local_qubits, steps, warmup):
     """configs[4]-style leg: ONE register of local_qubits + log2(world) atoms sharded over the
     ranks by its top qubits (NVLink peer memory).  Times H.psi and fixed-size DP5 steps with CUDA
-    events (max over ranks) and sets them against max(HBM, NVLink) rooflines."""
+    events (max over ranks) and sets them against max(HBM, NVLink) rooflines; the NVLink rate is the
+    peer copy timed in the same run with every rank pulling at once."""
     import torch.distributed as dist
     from pulser_diff_b200 import parallel
     g = world.bit_length() - 1
+    parity = sharded_parity(dev, rank, world)
+    # largest slice that fits: the forward evolution holds y, 7 slopes, the next state, the peer-visible
+    # buffer, g receive buffers, 2 saved states and ~2 transients (16 B/amplitude each) + the 8 B diagonal
+    free = torch.tensor([torch.cuda.mem_get_info(dev)[0]], dtype=torch.float64, device=dev)
+    dist.all_reduce(free, op=dist.ReduceOp.MIN)
+    need = lambda nl: ((14 + g) * 16 + 8) * 2.0 ** nl * 1.08
+    while local_qubits > 20 and need(local_qubits) > free.item():
+        local_qubits -= 1
     n = local_qubits + g
     T = 64
     gen = torch.Generator().manual_seed(0)
@@ -676,7 +733,9 @@ def sharded_measure(dev, rank, world, local_qubits, steps, warmup):
     full = (1 << n) - 1
     sk = parallel.ShardedKet(n, u, 0.02, [full], dv, [full], av, dev, peer_memory=True)
     psi = sk.state_buffer()
-    psi.copy_(torch.randn(1, 2 ** local_qubits, dtype=torch.float64, device=dev).to(torch.complex128))
+    psi.zero_()
+    if rank == world - 1:
+        psi[0, -1] = 1.0
 
     def timed(fn, reps):
         dist.barrier(); torch.cuda.synchronize(dev)
@@ -692,6 +751,13 @@ def sharded_measure(dev, rank, world, local_qubits, steps, warmup):
 
     for _ in range(warmup):
         sk.hpsi(0.3, psi)
+    # NVLink rate of this box, this run: every rank pulls its g partner slices at once (what H.psi does)
+    def pull():
+        for k in range(g):
+            sk._recv[k].copy_(sk._peer_bufs[rank ^ (1 << k)])
+    pull()
+    ms_pull = timed(pull, 3)
+    nvlink = g * 16.0 * 2 ** local_qubits / (ms_pull * 1e-3) / 1e9
     ms_h = timed(lambda: sk.hpsi(0.3, psi), max(steps, 3))
     y0 = torch.zeros(1, 2 ** local_qubits, dtype=torch.complex128, device=dev)
     if rank == world - 1:
@@ -704,17 +770,22 @@ def sharded_measure(dev, rank, world, local_qubits, steps, warmup):
     amps = 2 ** local_qubits
 
     def roof(alg_bytes_hbm, link_bytes, ms):
-        hbm_t, link_t = alg_bytes_hbm / (peak * 1e9), link_bytes / (NVLINK_PEER_GBS * 1e9)
+        hbm_t, link_t = alg_bytes_hbm / (peak * 1e9), link_bytes / (nvlink * 1e9)
         return {"bound": "nvlink" if link_t > hbm_t else "hbm", "hbm_s": hbm_t, "nvlink_s": link_t,
                 "frac": max(hbm_t, link_t) / (ms * 1e-3)}
 
     return {"workload": f"single register N={n} sharded by its {g} top qubits (2^{local_qubits} amplitudes per GPU)",
             "exchange": "partner slices pulled by the copy engines from NVLink peer memory beside the local kernels; "
                         "one accumulate kernel (pd_sharded_accumulate)",
+            "local_qubits": local_qubits, "bytes_per_vector_per_gpu": 16 * amps,
             "ms_per_hpsi": ms_h, "hpsi_per_s": 1e3 / ms_h, "roofline_hpsi": roof(40.0 * amps, g * 16.0 * amps, ms_h),
             "ms_per_dp5_step": ms_e, "dp5_steps_per_s": 1e3 / ms_e,
             "roofline_dp5_step": roof(576.0 * amps, 6 * g * 16.0 * amps, ms_e),
-            "peak_hbm_GBs": peak, "peak_nvlink_GBs_per_dir": NVLINK_PEER_GBS}
+            "peak_hbm_GBs": peak,
+            "nvlink_measured": {"GBs_per_direction_per_gpu": nvlink, "how": f"{g} concurrent peer copies of one "
+                                f"{16 * amps / 2 ** 30:.2f} GiB slice per rank, CUDA events, max over ranks",
+                                "ms": ms_pull},
+            "parity_vs_single_gpu": parity}
 
 
 def run_sharded(args):
@@ -752,7 +823,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--workload", default="c2", choices=["c2", "sharded"])
     ap.add_argument("--local-qubits", type=int, default=26)
-    ap.add_argument("--sharded-local-qubits", type=int, default=26,
+    ap.add_argument("--sharded-local-qubits", type=int, default=29,
                     help="N > 1: also time one register of this many + log2(N) qubits sharded over the ranks (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
