@@ -718,7 +718,7 @@ def sharded_measure(dev, rank, world, local_qubits, steps, warmup):
     # buffer, g receive buffers, 2 saved states and ~2 transients (16 B/amplitude each) + the 8 B diagonal
     free = torch.tensor([torch.cuda.mem_get_info(dev)[0]], dtype=torch.float64, device=dev)
     dist.all_reduce(free, op=dist.ReduceOp.MIN)
-    need = lambda nl: ((14 + g) * 16 + 8) * 2.0 ** nl * 1.08
+    need = lambda nl: ((14 + g) * 16 + 8) * 2.0 ** nl * 1.12
     while local_qubits > 20 and need(local_qubits) > free.item():
         local_qubits -= 1
     n = local_qubits + g

@@ -608,6 +608,10 @@ __device__ __forceinline__ void corr_block_reduce(double (&acc)[R], double* part
   }
 }
 
+// Same thread <-> element map as a_tile (e = t + 256 i): for tile bits lb < 8 the bit value of e is a property
+// of the thread, so the sign of gb and the "bit clear" condition of gd are applied ONCE per thread after the
+// element loop; for lb >= 8 they are compile-time constants.  Per flip and element: one LDS.128 and four FMAs
+// straight into the two accumulators (ga += Im(conj(kb) y'), gb_raw += Re(conj(kb) y')).
 __global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__ CorrParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* T = reinterpret_cast<cplx*>(smem_raw);
@@ -636,29 +640,61 @@ __global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__
       if (P.ymat) P.ymat[base + t + NT * (q0 + i)] = y[i];
     }
   }
+  const cplx* Tt = T + t;
+  const cplx* Tp[8];
+#pragma unroll
+  for (int lb = 0; lb < 8; ++lb) Tp[lb] = T + (t ^ (1 << lb));
   __syncthreads();
-  double acc[kCA];
+  double ga[TB], gb[TB], self_lo[4] = {0.0, 0.0, 0.0, 0.0}, self_all = 0.0;
 #pragma unroll
-  for (int r = 0; r < kCA; ++r) acc[r] = 0.0;
-  const int nl = P.nq < TB ? P.nq : TB;
+  for (int lb = 0; lb < TB; ++lb) { ga[lb] = 0.0; gb[lb] = 0.0; }
+  // four elements at a time (i = 4 io + ii): bounds the loads in flight / registers; tile bits 8, 9 are
+  // compile-time inside the group, bits 10, 11 are uniform per group
+#pragma unroll 1
+  for (int io = 0; io < 4; ++io) {
+    cplx kb4[4];
 #pragma unroll
-  for (int i = 0; i < EPT; ++i) {
-    const int e = t + NT * i;
-    const cplx kbv = ldcs(P.kbar + base + e);
-    const cplx kb{kbv.re, -kbv.im};
-    const cplx self = kb * T[e];
-    acc[kCA - 1] += self.im;
-    if (P.wacc) atomicAdd(P.wacc + (tile << TB) + e, P.wscale * self.im);
+    for (int ii = 0; ii < 4; ++ii) kb4[ii] = ldcs(P.kbar + base + t + NT * (4 * io + ii));
 #pragma unroll
-    for (int lb = 0; lb < TB; ++lb) {
-      if (lb >= nl) break;
-      const bool a = (e >> lb) & 1;
-      const cplx fl = kb * T[e ^ (1 << lb)];
-      acc[lb * 3 + 0] += a ? 0.0 : self.im;
-      acc[lb * 3 + 1] += fl.im;
-      acc[lb * 3 + 2] += a ? fl.re : -fl.re;
+    for (int ii = 0; ii < 4; ++ii) {
+      const int i = 4 * io + ii;
+      const cplx kbv = kb4[ii];                                // conj(kbar) = (kbv.re, -kbv.im)
+      const cplx own = Tt[NT * i];
+      const double self_im = fma(kbv.re, own.im, -kbv.im * own.re);
+      self_all += self_im;
+      if (P.wacc) atomicAdd(P.wacc + (tile << TB) + t + NT * i, P.wscale * self_im);
+#pragma unroll
+      for (int lb = 0; lb < 8; ++lb) {
+        const cplx pv = Tp[lb][NT * i];
+        ga[lb] = fma(kbv.re, pv.im, fma(-kbv.im, pv.re, ga[lb]));
+        gb[lb] = fma(kbv.re, pv.re, fma(kbv.im, pv.im, gb[lb]));
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool a = k < 2 ? ((ii >> k) & 1) : ((io >> (k - 2)) & 1);
+        const cplx pv = Tt[NT * (i ^ (1 << k))];
+        const double re = fma(kbv.re, pv.re, kbv.im * pv.im);
+        ga[8 + k] = fma(kbv.re, pv.im, fma(-kbv.im, pv.re, ga[8 + k]));
+        gb[8 + k] += a ? re : -re;
+        self_lo[k] += a ? 0.0 : self_im;
+      }
     }
   }
+  double acc[kCA];
+#pragma unroll
+  for (int lb = 0; lb < 8; ++lb) {
+    const bool a = (t >> lb) & 1;
+    acc[lb * 3 + 0] = a ? 0.0 : self_all;
+    acc[lb * 3 + 1] = ga[lb];
+    acc[lb * 3 + 2] = a ? gb[lb] : -gb[lb];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    acc[(8 + k) * 3 + 0] = self_lo[k];
+    acc[(8 + k) * 3 + 1] = ga[8 + k];
+    acc[(8 + k) * 3 + 2] = gb[8 + k];
+  }
+  acc[kCA - 1] = self_all;
   corr_block_reduce<kCA>(acc, P.partial);
 }
 
@@ -669,39 +705,66 @@ __device__ __forceinline__ size_t cindex(const CorrParams& P, size_t tile, int e
   return col | (ul << P.C) | (row << P.lo) | (uh << (P.lo + P.nb));
 }
 
-__global__ void __launch_bounds__(NT, 3) k_stream_corr_g(const __grid_constant__ CorrParams P) {
+// group tile: element e = t + 256 i at global index g0 + i * stride (see g_tile); row bits [C, 8) live in t
+// (runtime count 8 - C <= 4), row bits 8-11 in i.
+__global__ void __launch_bounds__(NT, 2) k_stream_corr_g(const __grid_constant__ CorrParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* T = reinterpret_cast<cplx*>(smem_raw);
   const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
   const size_t tile = blockIdx.x % tiles_per_vec;
   const size_t boff = (blockIdx.x / tiles_per_vec) * P.dim;
+  const int C = P.C;
+  const size_t g0 = boff + cindex(P, tile, t);
+  const size_t stride = (size_t)1 << (P.lo + 8 - C);
 #pragma unroll
-  for (int q0 = 0; q0 < EPT; q0 += 8) {
-    cplx x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = ldcs(P.ysrc + boff + cindex(P, tile, t + NT * (q0 + i)));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) T[t + NT * (q0 + i)] = x[i];
+  for (int i = 0; i < EPT; ++i) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(T + t + NT * i);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(P.ysrc + g0 + (size_t)i * stride) : "memory");
   }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  cplx kb[EPT];
+#pragma unroll
+  for (int i = 0; i < EPT; ++i) kb[i] = ldcs(P.kbar + g0 + (size_t)i * stride);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
+  const cplx* Tt = T + t;
+  const int n_cross = 8 - C;
   double acc[kCG];
 #pragma unroll
   for (int r = 0; r < kCG; ++r) acc[r] = 0.0;
+  for (int b = 0; b < n_cross; ++b) {
+    const cplx* Tq = T + (t ^ (1 << (C + b)));
+    double a_im = 0.0, a_re = 0.0;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      const cplx pv = Tq[NT * i];
+      a_im = fma(kb[i].re, pv.im, fma(-kb[i].im, pv.re, a_im));
+      a_re = fma(kb[i].re, pv.re, fma(kb[i].im, pv.im, a_re));
+    }
+    const bool a = (t >> (C + b)) & 1;
+    // static index into acc: b is a runtime loop counter, so scatter with a compile-time unrolled select
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb)
+      if (bb == b) { acc[bb * 2 + 0] = a_im; acc[bb * 2 + 1] = a ? a_re : -a_re; }
+  }
+  // tile bits 8-11 are group bits n_cross .. n_cross + 3
+  double ga8[4] = {0.0, 0.0, 0.0, 0.0}, gb8[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
-    const int e = t + NT * i;
-    const cplx kbv = ldcs(P.kbar + boff + cindex(P, tile, e));
-    const cplx kb{kbv.re, -kbv.im};
 #pragma unroll
-    for (int b = 0; b < kMaxGroupBits; ++b) {
-      if (b >= P.nb) break;
-      const int lb = P.C + b;
-      const bool a = (e >> lb) & 1;
-      const cplx fl = kb * T[e ^ (1 << lb)];
-      acc[b * 2 + 0] += fl.im;
-      acc[b * 2 + 1] += a ? fl.re : -fl.re;
+    for (int k = 0; k < 4; ++k) {
+      const cplx pv = Tt[NT * (i ^ (1 << k))];
+      const double re = fma(kb[i].re, pv.re, kb[i].im * pv.im);
+      ga8[k] = fma(kb[i].re, pv.im, fma(-kb[i].im, pv.re, ga8[k]));
+      gb8[k] += ((i >> k) & 1) ? re : -re;
     }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+#pragma unroll
+    for (int bb = 0; bb < kMaxGroupBits; ++bb)
+      if (bb == n_cross + k) { acc[bb * 2 + 0] = ga8[k]; acc[bb * 2 + 1] = gb8[k]; }
   }
   corr_block_reduce<kCG>(acc, P.partial);
 }
@@ -717,34 +780,39 @@ struct CorrFinal {
   unsigned tiles_per_vec;
   cplx* d_corr;
 };
-__global__ void k_stream_corr_final(const __grid_constant__ CorrFinal F) {
-  const int p = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(256) k_stream_corr_final(const __grid_constant__ CorrFinal F) {
+  const int p = blockIdx.x, t = threadIdx.x;
   double gd = 0.0, ga = 0.0, gb = 0.0;
   if (p < TB) {
-    for (unsigned b = lane; b < F.nblocks; b += 32) {
+    for (unsigned b = t; b < F.nblocks; b += 256) {
       const double* r = F.part_a + (size_t)b * kCA + p * 3;
       gd += r[0]; ga += r[1]; gb += r[2];
     }
   } else {
     // self terms: CTAs whose tile index has bit (p - TB) clear
-    for (unsigned b = lane; b < F.nblocks; b += 32)
+    for (unsigned b = t; b < F.nblocks; b += 256)
       if (!(((b % F.tiles_per_vec) >> (p - TB)) & 1u)) gd += F.part_a[(size_t)b * kCA + kCA - 1];
     for (int g = 0; g < F.n_groups; ++g)
       if (p >= F.lo[g] && p < F.lo[g] + F.nb[g]) {
         const int j = p - F.lo[g];
-        for (unsigned b = lane; b < F.nblocks; b += 32) {
+        for (unsigned b = t; b < F.nblocks; b += 256) {
           const double* r = F.part_g[g] + (size_t)b * kCG + j * 2;
           ga += r[0]; gb += r[1];
         }
       }
   }
+  __shared__ double sh[8][3];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     gd += __shfl_xor_sync(0xffffffffu, gd, o);
     ga += __shfl_xor_sync(0xffffffffu, ga, o);
     gb += __shfl_xor_sync(0xffffffffu, gb, o);
   }
-  if (lane == 0) {
+  if ((t & 31) == 0) { sh[t >> 5][0] = gd; sh[t >> 5][1] = ga; sh[t >> 5][2] = gb; }
+  __syncthreads();
+  if (t == 0) {
+    gd = ga = gb = 0.0;
+    for (int w = 0; w < 8; ++w) { gd += sh[w][0]; ga += sh[w][1]; gb += sh[w][2]; }
     const int q = F.nq - 1 - p;
     F.d_corr[q * 4 + 0] = cplx{0.0, gd};
     F.d_corr[q * 4 + 1] = cplx{0.0, 0.0};
@@ -803,7 +871,7 @@ int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double w
       lo += nb;
       ++n;
     }
-    k_stream_corr_final<<<g.nq, 32, 0, s>>>(F);
+    k_stream_corr_final<<<g.nq, 256, 0, s>>>(F);
     ++n;
   }
   PD_CUDA_CHECK(cudaGetLastError());
