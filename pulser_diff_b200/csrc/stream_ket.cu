@@ -18,10 +18,13 @@
 // L2 blocking (round 2).  B200's L2 serves hits at 15-19 TB/s against 6.5 TB/s from HBM
 // (profiles/r02_l2bench.md), so the A launch and the FIRST group launch of a stage run as ONE dataflow
 // launch, k_stream_ag: work items are handed out in ticket order, chunk by chunk (256 tiles = 16 MiB per
-// vector): the A tiles of chunk c, then the group tiles of chunk c - 1, which wait on a per-chunk
-// completion counter and find Ymat and the partial result in L2.  Per stage the HBM traffic falls from
+// vector; 64 tiles = 4 MiB by default): A tiles of chunk c alternate, ticket by ticket, with the group tiles of
+// chunk c - lag, which wait on a per-chunk completion counter and find Ymat and the partial result in L2 (the A
+// tiles write them with an evict_last policy, inputs and final results stream with evict_first).  Per stage the HBM traffic falls from
 // n + 8.5 to n + 5.5 vector passes (n = vectors combined); a DP5 step at N = 26 moves 62 passes instead
 // of 80.
+#include <cuda.h>
+
 #include <cstdlib>
 #include <map>
 #include <mutex>
@@ -67,11 +70,32 @@ struct StreamParams {
   const cplx* y0;
   double werr, atol, rtol;
   double* err_partial;        // [n_tiles] (g launch, nullable)
+  int pol_st, pol_ld;         // L2 policy kinds (l2_policy) of this launch's result stores / tile loads
+  int via_ring;               // pipelined group items: tile data arrives as TMA boxes through the ring (else: loads)
 };
 
 __device__ __forceinline__ cplx ldcs(const cplx* p) {
   double2 v = __ldcs(reinterpret_cast<const double2*>(p));
   return {v.x, v.y};
+}
+
+// L2 residency control of the dataflow launch (k_stream_ag): what an A tile writes (Ymat, partial result) is
+// re-read by a group tile a few chunks later and should outlive the input vectors streaming through L2; what
+// a group tile writes is not touched again before the next launch.
+__device__ __forceinline__ unsigned long long l2_policy(int kind) {   // 0 normal, 1 evict_last, 2 evict_first
+  unsigned long long pol;
+  if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void st_pol(cplx* p, cplx v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.re), "d"(v.im), "l"(pol) : "memory");
+}
+__device__ __forceinline__ cplx ld_pol(const cplx* p, unsigned long long pol) {
+  cplx v;
+  asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.re), "=d"(v.im) : "l"(p), "l"(pol));
+  return v;
 }
 
 // CTA barrier of a tile routine: every thread of the CTA (NBAR = 0), or the NBAR consumer threads of the
@@ -118,6 +142,7 @@ __device__ __forceinline__ void a_tile_flips(const StreamParams& P, const Stream
   }
   for (int gb = TB; gb < nq; ++gb) dthr += ((tile >> (gb - TB)) & 1) ? 0.0 : cf.d[gb];
   const double* dg_ptr = P.diag + (tile << TB) + t;
+  const unsigned long long pol = l2_policy(P.pol_st);
   tile_sync<NBAR>();
 
   // ---- out = kappa * ( (Dint + detuning diagonal) Y + low-bit flips )
@@ -139,7 +164,7 @@ __device__ __forceinline__ void a_tile_flips(const StreamParams& P, const Stream
     const cplx own = Tt[NT * i];
     h.re = fma(dd, own.re, h.re);
     h.im = fma(dd, own.im, h.im);
-    P.out[base + t + NT * i] = cf.kappa * h;
+    st_pol(P.out + base + t + NT * i, cf.kappa * h, pol);
   }
 }
 
@@ -153,6 +178,7 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
   // ---- combination: Y = sum_j w_j v_j, 4 elements x 2 vectors in flight per thread
   constexpr int QP = 4;
   constexpr bool want_aux = AUX;                   // the error-estimate vector of the last stage
+  const unsigned long long pol = l2_policy(P.pol_st);
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += QP) {
     cplx y[QP], z[QP];
@@ -197,7 +223,7 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
 #pragma unroll
     for (int i = 0; i < QP; ++i) {
       T[t + NT * (q0 + i)] = y[i];
-      if (P.ymat) P.ymat[base + t + NT * (q0 + i)] = y[i];
+      if (P.ymat) st_pol(P.ymat + base + t + NT * (q0 + i), y[i], pol);
       if (want_aux) P.aux[base + t + NT * (q0 + i)] = z[i];
     }
   }
@@ -234,13 +260,14 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
   const size_t stride = (size_t)1 << (P.lo + 8 - C);
   const cplx* ym = P.v[0] + g0;
   cplx* out = P.out + g0;
+  const unsigned long long pol_ld = l2_policy(P.pol_ld), pol_st = l2_policy(P.pol_st);
 
   // Ymat tile -> shared memory with 16-byte asynchronous copies (LDGSTS): 16 in flight per thread, no
   // registers; the first round of the partial result is fetched while they land
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
     const unsigned dst = (unsigned)__cvta_generic_to_shared(T + t + NT * i);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(ym + (size_t)i * stride) : "memory");
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(ym + (size_t)i * stride), "l"(pol_ld) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
   const cplx* Tt = T + t;
@@ -251,7 +278,7 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
   for (int k = 0; k < 4; ++k) { gre8[k] = cf.gre[p8 + k]; gim8[k] = cf.gim[p8 + k]; }
   cplx nxt[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) nxt[j] = ldcs(out + (size_t)j * stride);
+  for (int j = 0; j < 4; ++j) nxt[j] = ld_pol(out + (size_t)j * stride, pol_ld);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   tile_sync<NBAR>();
   double err_acc = 0.0;
@@ -265,7 +292,7 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
     }
     if (q0 + 4 < EPT) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) nxt[j] = ldcs(out + (size_t)(q0 + 4 + j) * stride);
+      for (int j = 0; j < 4; ++j) nxt[j] = ld_pol(out + (size_t)(q0 + 4 + j) * stride, pol_ld);
     }
     for (int b = 0; b < n_cross; ++b) {
       const int lb = C + b;
@@ -287,7 +314,7 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
       fma_acc(acc[j], cf.kappa, h[j]);
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) out[(size_t)(q0 + j) * stride] = acc[j];
+    for (int j = 0; j < 4; ++j) st_pol(out + (size_t)(q0 + j) * stride, acc[j], pol_st);
     if (P.err_partial) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -331,6 +358,9 @@ struct AgCtl {
   unsigned chunk_log2;     // tiles per chunk = 1 << chunk_log2; the first group's row bits lie inside a chunk
   unsigned n_chunks;
   unsigned lag;            // group tiles of chunk c are handed out after the A tiles of chunk c + lag
+  unsigned mix;
+  unsigned done_per_tile;  // arrivals on a chunk counter per finished A tile (1: per CTA, 16: per consumer warp)
+  unsigned dbg;            // experiment switches (PD_STREAM_DBG)
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -350,8 +380,13 @@ k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ Str
   __syncthreads();
   const unsigned item = s_item;
   const unsigned CT = 1u << ctl.chunk_log2;
-  const unsigned blk = item >> (ctl.chunk_log2 + 1), r = item & (2 * CT - 1);
-  if (r < CT) {
+  const unsigned blk = item >> (ctl.chunk_log2 + 1);
+  unsigned r = item & (2 * CT - 1);
+  // ctl.mix: A and group items alternate ticket by ticket (a steady mix of HBM-bound and L2-bound CTAs on every
+  // SM) instead of CT A items followed by CT group items
+  bool is_a = r < CT;
+  if (ctl.mix) { is_a = !(r & 1u); r = (r >> 1) + (is_a ? 0u : CT); }
+  if (is_a) {
     if (blk >= ctl.n_chunks) return;
     a_tile<REAL, AUX>(PA, cf, T, (size_t)blk * CT + r);
     __threadfence();
@@ -370,6 +405,397 @@ k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ Str
     }
     __syncthreads();
     g_tile<REAL, 0>(PG, cf, T, (size_t)c * CT + (r - CT));
+  }
+}
+
+// ---- persistent dataflow launch with an asynchronous input pipeline (round 2) ----------------------------
+// Same work items, ticket order and chunk counters as k_stream_ag, but the CTAs are persistent (one per SM, 16
+// consumer warps + a producer warp) and warp-specialised:
+//   * the last warp (one elected lane) is the PRODUCER: it draws the tickets, waits for a group item's chunk, hands
+//     the item to the consumers through a small queue, and streams the input vectors of A items into a ring
+//     of 16 KiB shared-memory slots with cp.async.bulk (TMA bulk copies, completion counted in bytes on an
+//     mbarrier) -- it runs ahead of the consumers across item boundaries, so the HBM stream never waits for a
+//     tile's shared-memory phase; group tiles (strided rows) travel as TMA tensor boxes (cp.async.bulk.tensor);
+//   * warps 0-15 are CONSUMERS: they combine the staged inputs in registers (the thread keeps its 8 elements
+//     of Y, so the three highest tile bits flip in registers), park Y in the 64 KiB tile for the nine
+//     cross-thread bits, and write Ymat / the result with L2 policies.
+// Ring slots are recycled through full/empty mbarriers; only the tile buffer uses a (consumer-only) named
+// barrier.
+constexpr int kPipeCons = 512;                       // consumer threads (16 warps)
+constexpr int kPipeThreads = kPipeCons + 32;         // + the producer warp
+constexpr int PEPT = TILE / kPipeCons;               // 8 elements per consumer thread: e = t + 512 i
+constexpr int PXB = 9;                               // tile bits that live in the thread index (cross-thread flips)
+constexpr int PRB = TB - PXB;                        // tile bits that live in the element index (flips in registers)
+constexpr int kSub = 1024;                           // amplitudes per ring slot (16 KiB)
+constexpr int SPT = kSub / kPipeCons;                // 2 elements per thread and slot
+constexpr int NSUB = TILE / kSub;                    // 4 slots per tile and vector
+constexpr int kPipeSlots = 10;
+constexpr int kItemQ = 4;
+constexpr unsigned kSlotBytes = kSub * 16;
+struct PipeShared {
+  cplx T[TILE];
+  cplx ring[kPipeSlots][kSub];
+  unsigned long long full[kPipeSlots], empty[kPipeSlots], item_full[kItemQ], item_empty[kItemQ];
+  unsigned item_kind[kItemQ], item_tile[kItemQ];
+  double red[kPipeCons / 32];
+};
+constexpr size_t kPipeSmem = sizeof(PipeShared) + 128;   // + slack to align the base to 128 B (TMA destinations)
+static_assert(kPipeSmem <= 232448, "one pipeline CTA per SM");
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n}" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// bounded wait (seconds): a broken pipeline must end as an error, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+  const unsigned a = smem_u32(b);
+  unsigned ok = 0, spins = 0;
+  long long t0 = 0;
+  for (;;) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    if (ok) return;
+    if ((++spins & 1023u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000ll) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar,
+                                          unsigned long long pol) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+// one box of a strided group tile (cuTensorMapEncodeTiled view, see make_group_map): rows x contiguous piece
+__device__ __forceinline__ void tensor_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                               unsigned long long* bar, unsigned long long pol) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
+               " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+               ::"r"(smem_u32(dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void cons_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kPipeCons) : "memory"); }
+
+// ticket -> work item (shared with k_stream_ag): kind 0 = A tile, 1 = group tile, 2 = nothing, 3 = end
+struct PipeItem { unsigned kind, tile, chunk; };
+__device__ __forceinline__ PipeItem decode_item(const AgCtl& ctl, unsigned item, unsigned total) {
+  if (item >= total) return {3u, 0u, 0u};
+  const unsigned CT = 1u << ctl.chunk_log2;
+  const unsigned blk = item >> (ctl.chunk_log2 + 1);
+  unsigned r = item & (2 * CT - 1);
+  bool is_a = r < CT;
+  if (ctl.mix) { is_a = !(r & 1u); r = (r >> 1) + (is_a ? 0u : CT); }
+  if (is_a) {
+    if (blk >= ctl.n_chunks) return {2u, 0u, 0u};
+    return {0u, blk * CT + r, blk};
+  }
+  if (blk < ctl.lag) return {2u, 0u, 0u};
+  const unsigned c = blk - ctl.lag;
+  return {1u, c * CT + (r - CT), c};
+}
+
+// one ring slot -> this thread's SPT elements of sub-block `q` (waits for the copy, frees the slot)
+__device__ __forceinline__ void ring_take(PipeShared& S, unsigned& step, cplx (&x)[SPT]) {
+  const unsigned sl = step % kPipeSlots;
+  mbar_wait(&S.full[sl], (step / kPipeSlots) & 1u);
+  const cplx* src = S.ring[sl] + threadIdx.x;
+#pragma unroll
+  for (int ii = 0; ii < SPT; ++ii) x[ii] = src[kPipeCons * ii];
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(&S.empty[sl]);
+  ++step;
+}
+
+// A item: Y = sum_j w_j v_j from the staged inputs, Ymat, out = kappa (diagonal + flips of the low 12 bits) Y.
+// The thread keeps its 8 elements of Y: tile bits 9-11 flip in registers, bits 0-8 through the tile buffer.
+template <bool REAL, bool AUX>
+__device__ __forceinline__ void pipe_a_item(const StreamParams& P, const StreamCoef& cf, PipeShared& S, size_t lin_tile,
+                                            unsigned& step) {
+  const int t = threadIdx.x;
+  const size_t tiles_per_vec = P.dim >> TB;
+  const size_t tile = lin_tile % tiles_per_vec;
+  const size_t base = (lin_tile / tiles_per_vec) * P.dim + (tile << TB);
+  const unsigned long long pol = l2_policy(P.pol_st);
+  cplx y[PEPT];
+#pragma unroll
+  for (int q = 0; q < NSUB; ++q) {
+    cplx z[SPT];
+#pragma unroll
+    for (int ii = 0; ii < SPT; ++ii) { y[SPT * q + ii] = {0.0, 0.0}; z[ii] = {0.0, 0.0}; }
+    for (int j = 0; j < P.n_in; ++j) {
+      cplx x[SPT];
+      ring_take(S, step, x);
+      const double w = P.w[j];
+#pragma unroll
+      for (int ii = 0; ii < SPT; ++ii) {
+        y[SPT * q + ii].re = fma(w, x[ii].re, y[SPT * q + ii].re);
+        y[SPT * q + ii].im = fma(w, x[ii].im, y[SPT * q + ii].im);
+      }
+      if (AUX) {
+        const double u = P.w2[j];
+#pragma unroll
+        for (int ii = 0; ii < SPT; ++ii) { z[ii].re = fma(u, x[ii].re, z[ii].re); z[ii].im = fma(u, x[ii].im, z[ii].im); }
+      }
+    }
+    if (AUX) {
+#pragma unroll
+      for (int ii = 0; ii < SPT; ++ii) P.aux[base + t + kPipeCons * (SPT * q + ii)] = z[ii];
+    }
+  }
+  cplx* T = S.T;
+  const cplx* Tp[PXB];
+  double sg[PXB];
+  double dthr = 0.0;          // diagonal of the bits this thread's elements share: tile bits 0-8 and the bits above the tile
+#pragma unroll
+  for (int lb = 0; lb < PXB; ++lb) {
+    const bool a = (t >> lb) & 1;
+    Tp[lb] = T + (t ^ (1 << lb));
+    sg[lb] = a ? cf.gim[lb] : -cf.gim[lb];
+    dthr += a ? 0.0 : cf.d[lb];
+  }
+  for (int gb = TB; gb < P.nq; ++gb) dthr += ((tile >> (gb - TB)) & 1) ? 0.0 : cf.d[gb];
+  // static diagonal: all PEPT values are fetched before the tile exchange, so their latency hides behind it
+  const double* dg_ptr = P.diag + (tile << TB) + t;
+  double dg[PEPT];
+#pragma unroll
+  for (int i = 0; i < PEPT; ++i) dg[i] = __ldg(dg_ptr + kPipeCons * i);
+  cons_sync();                                       // every warp is done reading the previous item's tile
+#pragma unroll
+  for (int i = 0; i < PEPT; ++i) {
+    T[t + kPipeCons * i] = y[i];
+    if (P.ymat) st_pol(P.ymat + base + t + kPipeCons * i, y[i], pol);
+  }
+  cons_sync();
+#pragma unroll
+  for (int i = 0; i < PEPT; ++i) {
+    cplx h{0.0, 0.0};
+#pragma unroll
+    for (int lb = 0; lb < PXB; ++lb) flip_acc<REAL>(h, cf.gre[lb], sg[lb], Tp[lb][kPipeCons * i]);
+#pragma unroll
+    for (int k = 0; k < PRB; ++k) {
+      const bool a = (i >> k) & 1;
+      flip_acc<REAL>(h, cf.gre[PXB + k], a ? cf.gim[PXB + k] : -cf.gim[PXB + k], y[i ^ (1 << k)]);
+    }
+    double dd = dthr + dg[i];
+#pragma unroll
+    for (int k = 0; k < PRB; ++k)
+      if (!((i >> k) & 1)) dd += cf.d[PXB + k];
+    h.re = fma(dd, y[i].re, h.re);
+    h.im = fma(dd, y[i].im, h.im);
+    st_pol(P.out + base + t + kPipeCons * i, cf.kappa * h, pol);
+  }
+}
+
+// group item: the Ymat tile and the partial result arrive through the ring as boxes of 2^(10-C) rows (TMA tensor
+// copies issued by the producer).  Tile element e = col | row << C = t + 512 i: the row bits split into tile bits
+// [C, 9) (partner = another thread's element: tile buffer) and tile bits 9-11 (the thread's own elements:
+// registers).
+template <bool REAL>
+__device__ __forceinline__ void pipe_g_item(const StreamParams& P, const StreamCoef& cf, PipeShared& S, size_t lin_tile,
+                                            unsigned& step) {
+  const int t = threadIdx.x;
+  const size_t tiles_per_vec = P.dim >> TB;
+  const size_t tile = lin_tile % tiles_per_vec;
+  const size_t boff = (lin_tile / tiles_per_vec) * P.dim;
+  const int C = P.C;
+  const size_t g0 = boff + gindex(P, tile, t);
+  const size_t stride = (size_t)1 << (P.lo + PXB - C);
+  cplx* out = P.out + g0;
+  const unsigned long long pol_st = l2_policy(P.pol_st);
+  cplx y[PEPT];
+  const bool ring = P.via_ring != 0;                 // uniform
+  if (ring) {
+#pragma unroll
+    for (int q = 0; q < NSUB; ++q) {
+      cplx x[SPT];
+      ring_take(S, step, x);
+#pragma unroll
+      for (int ii = 0; ii < SPT; ++ii) y[SPT * q + ii] = x[ii];
+    }
+  } else {
+    const unsigned long long pol_ld = l2_policy(P.pol_ld);
+    const cplx* ym = P.v[0] + g0;
+#pragma unroll
+    for (int i = 0; i < PEPT; ++i) y[i] = ld_pol(ym + (size_t)i * stride, pol_ld);
+  }
+  cplx* T = S.T;
+  const int n_cross = PXB - C;                       // row bits that live in t
+  const int p9 = P.lo + n_cross;                     // global bit position of tile bit 9
+  double gre9[PRB], gim9[PRB];
+#pragma unroll
+  for (int k = 0; k < PRB; ++k) { gre9[k] = cf.gre[p9 + k]; gim9[k] = cf.gim[p9 + k]; }
+  // without the ring the partial result is fetched now, so that its latency hides behind the tile exchange
+  cplx accg[PEPT];
+  if (!ring) {
+    const unsigned long long pol_ld = l2_policy(P.pol_ld);
+#pragma unroll
+    for (int i = 0; i < PEPT; ++i) accg[i] = ld_pol(out + (size_t)i * stride, pol_ld);
+  }
+  cons_sync();
+#pragma unroll
+  for (int i = 0; i < PEPT; ++i) T[t + kPipeCons * i] = y[i];
+  cons_sync();
+  double err_acc = 0.0;
+#pragma unroll
+  for (int q = 0; q < NSUB; ++q) {
+    cplx acc[SPT], h[SPT];
+    if (ring) ring_take(S, step, acc);
+    else {
+#pragma unroll
+      for (int ii = 0; ii < SPT; ++ii) acc[ii] = accg[SPT * q + ii];
+    }
+#pragma unroll
+    for (int ii = 0; ii < SPT; ++ii) h[ii] = {0.0, 0.0};
+    for (int b = 0; b < n_cross; ++b) {
+      const int lb = C + b;
+      const bool a = (t >> lb) & 1;
+      const cplx* Tq = T + (t ^ (1 << lb));
+      const double gr = cf.gre[P.lo + b];
+      const double sgn = a ? cf.gim[P.lo + b] : -cf.gim[P.lo + b];
+#pragma unroll
+      for (int ii = 0; ii < SPT; ++ii) flip_acc<REAL>(h[ii], gr, sgn, Tq[kPipeCons * (SPT * q + ii)]);
+    }
+#pragma unroll
+    for (int ii = 0; ii < SPT; ++ii) {
+      const int i = SPT * q + ii;
+#pragma unroll
+      for (int k = 0; k < PRB; ++k) {
+        const bool a = (i >> k) & 1;
+        flip_acc<REAL>(h[ii], gre9[k], a ? gim9[k] : -gim9[k], y[i ^ (1 << k)]);
+      }
+      fma_acc(acc[ii], cf.kappa, h[ii]);
+      st_pol(out + (size_t)i * stride, acc[ii], pol_st);
+    }
+    if (P.err_partial) {
+#pragma unroll
+      for (int ii = 0; ii < SPT; ++ii) {
+        const int i = SPT * q + ii;
+        const size_t gi = g0 + (size_t)i * stride;
+        const cplx ep = ldcs(P.aux + gi);
+        const cplx y0 = ldcs(P.y0 + gi);
+        const double sc = P.atol + P.rtol * fmax(hypot(y0.re, y0.im), hypot(y[i].re, y[i].im));
+        const double er = fma(P.werr, acc[ii].re, ep.re) / sc, ei = fma(P.werr, acc[ii].im, ep.im) / sc;
+        err_acc += er * er + ei * ei;
+      }
+    }
+  }
+  if (P.err_partial) {
+    double* red = S.red;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) err_acc += __shfl_xor_sync(0xffffffffu, err_acc, o);
+    cons_sync();
+    if ((t & 31) == 0) red[t >> 5] = err_acc;
+    cons_sync();
+    if (t == 0) {
+      double sacc = 0.0;
+      for (int w = 0; w < kPipeCons / 32; ++w) sacc += red[w];
+      P.err_partial[lin_tile] = sacc;
+    }
+  }
+}
+
+template <bool REAL, bool AUX>
+__global__ void __launch_bounds__(kPipeThreads, 1)
+k_stream_pipe(const __grid_constant__ StreamParams PA, const __grid_constant__ StreamParams PG,
+              const __grid_constant__ StreamCoef cf, const AgCtl ctl, const unsigned total_items,
+              const __grid_constant__ CUtensorMap tm_y, const __grid_constant__ CUtensorMap tm_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PipeShared& S = *reinterpret_cast<PipeShared*>(smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kPipeSlots; ++i) { mbar_init(&S.full[i], 1); mbar_init(&S.empty[i], kPipeCons / 32); }
+    for (int i = 0; i < kItemQ; ++i) { mbar_init(&S.item_full[i], 1); mbar_init(&S.item_empty[i], kPipeCons / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+  const unsigned CT = 1u << ctl.chunk_log2;
+  if (warp == kPipeCons / 32) {
+    // ===== producer: one lane =====
+    if (lane != 0) return;
+    const unsigned long long pol_in = l2_policy(2);  // inputs stream through L2 once
+    const size_t tiles_per_vec = PA.dim >> TB;
+    unsigned step = 0, it = 0;
+    for (;;) {
+      const unsigned ticket = atomicAdd(ctl.sync, 1u);
+      const PipeItem w = decode_item(ctl, ticket, total_items);
+      if (w.kind == 2u) continue;
+      if (w.kind == 1u && ctl.done_per_tile) {
+        unsigned spins = 0;
+        while (ld_acquire_u32(ctl.sync + 1 + w.chunk) < CT * ctl.done_per_tile) {
+          __nanosleep(64);
+          if (++spins > (1u << 25)) __trap();
+        }
+        __threadfence();
+        if (!(ctl.dbg & 2u)) asm volatile("fence.proxy.async.global;" ::: "memory");   // the chunk was written through the generic proxy, TMA reads it
+      }
+      const unsigned q = it % kItemQ;
+      mbar_wait(&S.item_empty[q], ((it / kItemQ) & 1u) ^ 1u);
+      S.item_kind[q] = w.kind;
+      S.item_tile[q] = w.tile;
+      mbar_arrive(&S.item_full[q]);
+      ++it;
+      if (w.kind == 3u) break;
+      const size_t tile = (size_t)w.tile % tiles_per_vec;
+      const size_t col = (size_t)w.tile / tiles_per_vec;          // batch column
+      if (w.kind == 0u) {
+        const size_t base = col * PA.dim + (tile << TB);
+        for (int q4 = 0; q4 < NSUB; ++q4)
+          for (int j = 0; j < PA.n_in; ++j) {
+            const unsigned sl = step % kPipeSlots;
+            mbar_wait(&S.empty[sl], ((step / kPipeSlots) & 1u) ^ 1u);
+            mbar_expect_tx(&S.full[sl], kSlotBytes);
+            bulk_load(S.ring[sl], PA.v[j] + base + (size_t)q4 * kSub, kSlotBytes, &S.full[sl], pol_in);
+            ++step;
+          }
+      } else if (PG.via_ring) {
+        // tile index -> box coordinates (gindex): contiguous doubles, row, slab
+        const int C = PG.C, lw = PG.lo - C;
+        const int c0 = (int)((tile & (((size_t)1 << lw) - 1)) << (C + 1));
+        const int c2 = (int)((tile >> lw) + col * (PG.dim >> (PG.lo + PG.nb)));
+        const int rows = kSub >> C;
+        const unsigned long long pol_g = l2_policy(PG.pol_ld);
+        for (int v = 0; v < 2; ++v)
+          for (int q4 = 0; q4 < NSUB; ++q4) {
+            const unsigned sl = step % kPipeSlots;
+            mbar_wait(&S.empty[sl], ((step / kPipeSlots) & 1u) ^ 1u);
+            mbar_expect_tx(&S.full[sl], kSlotBytes);
+            if (v == 0) tensor_load_3d(S.ring[sl], &tm_y, c0, q4 * rows, c2, &S.full[sl], pol_g);
+            else tensor_load_3d(S.ring[sl], &tm_out, c0, q4 * rows, c2, &S.full[sl], pol_g);
+            ++step;
+          }
+      }
+    }
+    return;
+  }
+  // ===== consumers =====
+  unsigned step = 0, it = 0;
+  for (;;) {
+    const unsigned q = it % kItemQ;
+    mbar_wait(&S.item_full[q], (it / kItemQ) & 1u);
+    const unsigned kind = S.item_kind[q], tile = S.item_tile[q];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.item_empty[q]);
+    ++it;
+    if (kind == 3u) break;
+    if (kind == 0u) {
+      pipe_a_item<REAL, AUX>(PA, cf, S, tile, step);
+      // this warp's share of the tile is written: publish it to the group tiles of the chunk
+      // the group tiles read these lines through the async proxy (TMA): generic -> async proxy fence for
+      // global memory (the unqualified fence.proxy.async only covers shared memory), then the usual release
+      if (!(ctl.dbg & 1u)) asm volatile("fence.proxy.async.global;" ::: "memory");
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) atomicAdd(ctl.sync + 1 + (tile >> ctl.chunk_log2), 1u);
+    } else {
+      pipe_g_item<REAL>(PG, cf, S, tile, step);
+    }
   }
 }
 
@@ -403,6 +829,39 @@ int current_device() {
   if (dev < 0 || dev >= 64) throw Error(PD_ERR_STATE, "device index out of range");
   return dev;
 }
+// 3-D view of a vector for the strided tiles of the group on bits [lo, lo + nb), in doubles (2 per amplitude):
+// dim0 = 2^(lo+1) contiguous, dim1 = 2^nb rows (stride 2^lo amplitudes), dim2 = the slabs above (and the
+// batch columns, which continue the same stride); box = one ring slot = 2^(10-C) rows x 2^C amplitudes.
+CUtensorMap make_group_map(const cplx* base, size_t dim, int batch, int lo, int nb) {
+  using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PD_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) throw Error(PD_ERR_STATE, "cuTensorMapEncodeTiled is not available");
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  const int C = TB - nb;
+  CUtensorMap tm;
+  const cuuint64_t gdim[3] = {(cuuint64_t)2 << lo, (cuuint64_t)1 << nb, (cuuint64_t)(dim >> (lo + nb)) * (cuuint64_t)batch};
+  const cuuint64_t gstride[2] = {(cuuint64_t)16 << lo, (cuuint64_t)16 << (lo + nb)};
+  const cuuint32_t box[3] = {(cuuint32_t)2 << C, (cuuint32_t)1 << (10 - C), 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<cplx*>(base), gdim, gstride, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw Error(PD_ERR_STATE, "cuTensorMapEncodeTiled failed for a group tile view");
+  return tm;
+}
+
+int sm_count() {
+  static int n[64] = {};
+  const int dev = current_device();
+  if (!n[dev]) PD_CUDA_CHECK(cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev));
+  return n[dev];
+}
 void set_attrs() {
   const int dev = current_device();
   if (g_attr_set[dev]) return;
@@ -410,6 +869,9 @@ void set_attrs() {
   big(k_stream_a<false, false>); big(k_stream_a<false, true>); big(k_stream_a<true, false>); big(k_stream_a<true, true>);
   big(k_stream_ag<false, false>); big(k_stream_ag<false, true>); big(k_stream_ag<true, false>); big(k_stream_ag<true, true>);
   big(k_stream_g<false>); big(k_stream_g<true>);
+  auto pipe_attr = [](auto* f) { PD_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem)); };
+  pipe_attr(k_stream_pipe<false, false>); pipe_attr(k_stream_pipe<false, true>);
+  pipe_attr(k_stream_pipe<true, false>); pipe_attr(k_stream_pipe<true, true>);
   g_attr_set[dev] = true;
 }
 
@@ -436,7 +898,7 @@ unsigned env_unsigned(const char* name, unsigned dflt) {
 int fuse_mode() {
   static const int mode = [] {
     const char* e = std::getenv("PD_STREAM_FUSE");
-    return (e && e[0] == '0') ? 0 : 1;
+    return e ? (e[0] - '0') : 1;                    // 0: separate launches, 1: k_stream_ag, 2: k_stream_pipe
   }();
   return mode;
 }
@@ -451,11 +913,19 @@ Groups make_groups(int nq) {
   const int rest = nq - TB;
   gr.G = (rest + kMaxGroupBits - 1) / kMaxGroupBits;
   int lo = TB;
-  for (int gi = 0; gi < gr.G; ++gi) {
-    gr.lo[gi] = lo;
-    gr.nb[gi] = rest / gr.G + (gi < rest % gr.G ? 1 : 0);
-    lo += gr.nb[gi];
+  for (int gi = 0; gi < gr.G; ++gi) gr.nb[gi] = rest / gr.G + (gi < rest % gr.G ? 1 : 0);
+  // The FIRST group rides in the dataflow launch: its closure (2^nb tiles) is the L2 blocking unit.  With two
+  // groups PD_STREAM_G1BITS moves bits between them (a group tile needs 4 <= nb <= 8: 8 - C cross bits >= 0 and
+  // pieces of >= 256 B).
+  // Measured at N = 24, 26 (profiles/r02_stream_knobs.md): a 6-bit first group (4 MiB closure per vector) beats
+  // the even split by 3-4 %.
+  static const unsigned g1_env = env_unsigned("PD_STREAM_G1BITS", 0);
+  if (gr.G == 2) {
+    const int nb0 = g1_env ? (int)g1_env : (rest >= 12 ? std::max(rest - kMaxGroupBits, 6) : gr.nb[0]);
+    const int nb1 = rest - nb0;
+    if (nb0 >= 4 && nb0 <= kMaxGroupBits && nb1 >= 4 && nb1 <= kMaxGroupBits) { gr.nb[0] = nb0; gr.nb[1] = nb1; }
   }
+  for (int gi = 0; gi < gr.G; ++gi) { gr.lo[gi] = lo; lo += gr.nb[gi]; }
   return gr;
 }
 
@@ -474,11 +944,15 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
   const unsigned grid = (unsigned)n_tiles;
   const Groups gr = make_groups(g.nq);
   StreamParams B[8];
+  static const unsigned hints = env_unsigned("PD_STREAM_HINTS", 7);
   for (int gi = 0; gi < gr.G; ++gi) {
     StreamParams& b = B[gi];
     b = StreamParams{};
     b.nq = g.nq; b.dim = g.dim; b.n_in = 1; b.v[0] = ysrc; b.w[0] = 1.0; b.out = A.out;
     b.lo = gr.lo[gi]; b.nb = gr.nb[gi]; b.C = TB - gr.nb[gi];
+    b.via_ring = 1;
+    b.pol_st = hints & 2 ? 2 : 0;                    // group results: not re-read before the next launch
+    b.pol_ld = (hints & 4) && gi == 0 ? 2 : 0;       // fused group: last use of the A tiles' lines
     if (tail && gi == gr.G - 1) {
       b.aux = tail->aux; b.y0 = tail->y0; b.werr = tail->werr; b.atol = tail->atol; b.rtol = tail->rtol;
       b.err_partial = tail->err_partial;
@@ -486,18 +960,41 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
   }
   int n = 0, first = 0;
   const unsigned tiles_per_vec = (unsigned)(g.dim >> TB);
-  static const unsigned max_chunk_log2 = env_unsigned("PD_STREAM_CHUNK", 8), lag = env_unsigned("PD_STREAM_LAG", 1);
+  // defaults from the sweep in profiles/r02_stream_knobs.md (N=26: 14.25 ms with chunk 8 / lag 1 / no hints ->
+  // 13.0 ms with chunk 6 / lag 6 / alternating tickets / L2 policies)
+  static const unsigned max_chunk_log2 = env_unsigned("PD_STREAM_CHUNK", 6), lag = env_unsigned("PD_STREAM_LAG", 6);
   unsigned chunk_log2 = 0;
   while ((1u << (chunk_log2 + 1)) <= tiles_per_vec && chunk_log2 < std::max<unsigned>(max_chunk_log2, gr.nb[0])) ++chunk_log2;
   const size_t n_chunks = n_tiles >> chunk_log2;
-  if (fuse_mode() != 0 && gr.G >= 1 && (unsigned)gr.nb[0] <= chunk_log2 && n_chunks >= 8 && n_chunks <= kMaxChunks) {
-    AgCtl ctl{ag_sync_buffer(s), chunk_log2, (unsigned)n_chunks, std::max(1u, lag)};
+  if (fuse_mode() != 0 && gr.G >= 1 && (unsigned)gr.nb[0] <= chunk_log2 && n_chunks >= 16 && n_chunks <= kMaxChunks) {
+    static const unsigned mix = env_unsigned("PD_STREAM_MIX", 1);
+    // the pipelined launch moves group tiles as TMA boxes: inner extent 2^(C+1) doubles <= 256, i.e. nb >= 5
+    const bool pipe = fuse_mode() == 2 && gr.nb[0] >= 5;
+    static const unsigned dbg = env_unsigned("PD_STREAM_DBG", 0);
+    AgCtl ctl{ag_sync_buffer(s), chunk_log2, (unsigned)n_chunks, std::max(1u, lag), mix, pipe ? (unsigned)(kPipeCons / 32) : 1u, dbg};
+    StreamParams Af = A;
+    Af.pol_st = hints & 1 ? 1 : 0;                   // keep Ymat and the partial result in L2 for the group tiles
     PD_CUDA_CHECK(cudaMemsetAsync(ctl.sync, 0, sizeof(unsigned) * (n_chunks + 1), s));
     const unsigned ag_grid = (unsigned)(2 * (n_tiles + ((size_t)ctl.lag << chunk_log2)));
     const bool aux = A.aux != nullptr;
-    auto go = [&](auto* f) { f<<<ag_grid, NT, TILE * 16, s>>>(A, B[0], cf, ctl); };
-    if (uni) { if (aux) go(k_stream_ag<true, true>); else go(k_stream_ag<true, false>); }
-    else { if (aux) go(k_stream_ag<false, true>); else go(k_stream_ag<false, false>); }
+    if (pipe) {
+      const unsigned pgrid = (unsigned)std::min<size_t>((size_t)sm_count(), n_tiles);
+      // Group tiles of the dataflow launch read what A tiles of the SAME launch wrote a moment earlier.  Moving
+      // them as TMA boxes returned stale sectors now and then (N=22, batch 2, 8 chunks: 26 of 400 applications
+      // wrong in a few 32 B sectors of one piece, with generic->async proxy fences on both sides; profiles/
+      // r02_stream_pipe.md), so here they are fetched with ordinary loads; PD_STREAM_TMA_G=1 re-enables the boxes.
+      static const unsigned tma_g = env_unsigned("PD_STREAM_TMA_G", 0);
+      B[0].via_ring = tma_g ? 1 : 0;
+      const CUtensorMap tm_y = make_group_map(ysrc, g.dim, g.batch, gr.lo[0], gr.nb[0]);
+      const CUtensorMap tm_out = make_group_map(A.out, g.dim, g.batch, gr.lo[0], gr.nb[0]);
+      auto go = [&](auto* f) { f<<<pgrid, kPipeThreads, kPipeSmem, s>>>(Af, B[0], cf, ctl, ag_grid, tm_y, tm_out); };
+      if (uni) { if (aux) go(k_stream_pipe<true, true>); else go(k_stream_pipe<true, false>); }
+      else { if (aux) go(k_stream_pipe<false, true>); else go(k_stream_pipe<false, false>); }
+    } else {
+      auto go = [&](auto* f) { f<<<ag_grid, NT, TILE * 16, s>>>(Af, B[0], cf, ctl); };
+      if (uni) { if (aux) go(k_stream_ag<true, true>); else go(k_stream_ag<true, false>); }
+      else { if (aux) go(k_stream_ag<false, true>); else go(k_stream_ag<false, false>); }
+    }
     n = 1;
     first = 1;
   } else {
@@ -507,8 +1004,20 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
     else { if (aux) go(k_stream_a<false, true>); else go(k_stream_a<false, false>); }
     n = 1;
   }
+  // later groups: their inputs come from earlier LAUNCHES, so the tiles can travel as TMA boxes through the
+  // persistent pipeline (every ticket is a group item; PD_STREAM_GPIPE=0 keeps the plain kernel)
+  static const unsigned gpipe = env_unsigned("PD_STREAM_GPIPE", 1);
   for (int gi = first; gi < gr.G; ++gi) {
-    if (uni) k_stream_g<true><<<grid, NT, TILE * 16, s>>>(B[gi], cf);
+    if (gpipe && fuse_mode() == 2 && gr.nb[gi] >= 5 && n_tiles >= 2 * (size_t)sm_count()) {
+      AgCtl gctl{ag_sync_buffer(s), 0u, 0u, 0u, 0u, 0u, 0u};   // chunk = 1 tile, no A items, nothing to wait for
+      PD_CUDA_CHECK(cudaMemsetAsync(gctl.sync, 0, sizeof(unsigned) * 2, s));
+      const CUtensorMap tm_y = make_group_map(ysrc, g.dim, g.batch, gr.lo[gi], gr.nb[gi]);
+      const CUtensorMap tm_out = make_group_map(A.out, g.dim, g.batch, gr.lo[gi], gr.nb[gi]);
+      const unsigned pgrid = (unsigned)std::min<size_t>((size_t)sm_count(), n_tiles);
+      const unsigned total = (unsigned)(2 * n_tiles);
+      if (uni) k_stream_pipe<true, false><<<pgrid, kPipeThreads, kPipeSmem, s>>>(B[gi], B[gi], cf, gctl, total, tm_y, tm_out);
+      else k_stream_pipe<false, false><<<pgrid, kPipeThreads, kPipeSmem, s>>>(B[gi], B[gi], cf, gctl, total, tm_y, tm_out);
+    } else if (uni) k_stream_g<true><<<grid, NT, TILE * 16, s>>>(B[gi], cf);
     else k_stream_g<false><<<grid, NT, TILE * 16, s>>>(B[gi], cf);
     ++n;
   }
