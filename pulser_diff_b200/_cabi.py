@@ -289,9 +289,14 @@ class Plan:
             raise ValueError(f"{what} must have shape {want}, got {tuple(t.shape)}")
         return t.contiguous()
 
-    def hpsi(self, t: float, psi: torch.Tensor, rhs: bool = False) -> torch.Tensor:
+    def hpsi(self, t: float, psi: torch.Tensor, rhs: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         psi = self._vec(psi, "psi")
-        out = torch.empty_like(psi)
+        if out is None:
+            out = torch.empty_like(psi)
+        elif not out.is_contiguous() or out.data_ptr() == psi.data_ptr():
+            raise ValueError("out must be a contiguous buffer distinct from psi")
+        else:
+            self._vec(out, "out")
         fn = lib().pd_rhs if rhs else lib().pd_hpsi
         _check(fn(self._ptr, _stream(self.device), float(t), _dptr(psi), _dptr(out)))
         return out

@@ -188,7 +188,8 @@ class ShardedKet:
                     c[q] += val
         return d, c
 
-    def hpsi(self, t: float, psi_local: Tensor, keep_partners: bool = False, rhs: bool = False):
+    def hpsi(self, t: float, psi_local: Tensor, keep_partners: bool = False, rhs: bool = False,
+             out: Optional[Tensor] = None):
         """``(H(t) psi)`` restricted to this rank's slice (``rhs``: ``-i H(t) psi``, the factor
         folded into the kernels' coefficients).  ``psi_local``: (1, 2^(N-g)).
 
@@ -196,7 +197,7 @@ class ShardedKet:
         next call) -- the adjoint sweep takes its drive correlations from them."""
         d, c = self._global_coefficients(t)
         if self._hdl is not None:
-            return self._hpsi_peer(t, psi_local, d, c, keep_partners, rhs)
+            return self._hpsi_peer(t, psi_local, d, c, keep_partners, rhs, out)
         # 1. post the pairwise exchanges (one per global qubit) before any local work
         recv = [torch.empty_like(psi_local) for _ in range(self.g)]
         reqs = []
@@ -207,7 +208,7 @@ class ShardedKet:
             reqs += dist.batch_isend_irecv(ops_)
         # 2. local qubits: the single-GPU kernels (overlaps the transfers)
         ops.configure(self.plan, self._prog)
-        out = self.plan.hpsi(t, psi_local, rhs=rhs)
+        out = self.plan.hpsi(t, psi_local, rhs=rhs, out=out)
         shift = self.e_static + sum(d[q] * self.r_glob[q] for q in range(self.g))
         # 3. global flips: this rank's bit for qubit q is 1 (ground) -> coefficient c, else conj(c)
         for r in reqs:
@@ -219,7 +220,7 @@ class ShardedKet:
         return (out, recv) if keep_partners else out
 
     def _hpsi_peer(self, t: float, psi_local: Tensor, d, c, keep_partners: bool = False,
-                   rhs: bool = False):
+                   rhs: bool = False, out: Optional[Tensor] = None):
         """Peer-memory variants.  "read": one kernel accumulates the partner slices in place over
         NVLink.  "copy": the copy engines pull the partner slices into local buffers on a second
         stream while the local kernels run; the same kernel then accumulates them from HBM."""
@@ -248,7 +249,7 @@ class ShardedKet:
         else:
             ptrs = [self._peer_ptrs[r] for r in peers]
         ops.configure(self.plan, self._prog)
-        out = self.plan.hpsi(t, buf, rhs=rhs)
+        out = self.plan.hpsi(t, buf, rhs=rhs, out=out)
         if copy:
             main.wait_stream(self._side)
         self.plan.sharded_accumulate(out, buf, 0.0, [buf.data_ptr()] + ptrs, coefs)
@@ -268,8 +269,8 @@ class ShardedKet:
     # (csrc/engine.hpp forward_dp5 / adjoint_step; reference call backend.py:488-494), driven
     # from the host because every H.psi is one exchange step; the error norm is the only
     # reduction on the forward path (one scalar all-reduce per attempted step).
-    def rhs(self, t: float, psi_local: Tensor) -> Tensor:
-        return self.hpsi(t, psi_local, rhs=True)
+    def rhs(self, t: float, psi_local: Tensor, out: Optional[Tensor] = None) -> Tensor:
+        return self.hpsi(t, psi_local, rhs=True, out=out)
 
     def _sum(self, x: float) -> float:
         if self.world == 1:
@@ -282,7 +283,8 @@ class ShardedKet:
         loc = ((x.abs() / (atol + rtol * ref_abs)) ** 2).sum().item()
         return math.sqrt(self._sum(loc) / float(1 << self.n))
 
-    def _stage_input(self, y: Tensor, k: list, i: int, h: float, publish: bool = False) -> Tensor:
+    def _stage_input(self, y: Tensor, k: list, i: int, h: float, publish: bool = False,
+                     out: Optional[Tensor] = None) -> Tensor:
         """Y_i = y + h sum_j beta_ij k_j in one pass; ``publish``: written straight into the
         peer-visible buffer (valid until the next generator application)."""
         ins, w = [y], [1.0]
@@ -290,16 +292,23 @@ class ShardedKet:
             if _BETA[i - 1][j] != 0.0:
                 ins.append(k[j])
                 w.append(h * _BETA[i - 1][j])
-        out = self.state_buffer() if (publish and self._hdl is not None) else torch.empty_like(y)
+        if publish and self._hdl is not None:
+            out = self.state_buffer()
+        elif out is None:
+            out = torch.empty_like(y)
         return self.plan.lincomb(out, ins, w)
 
-    def _dp5_step(self, t: float, h: float, y: Tensor, k0: Tensor, upto: int = 6):
-        """k[0..upto], y_new of one step (stage 7's input is y_new: FSAL; ``upto=5`` stops before it)."""
+    def _dp5_step(self, t: float, h: float, y: Tensor, k0: Tensor, upto: int = 6, ring=None):
+        """k[0..upto], y_new of one step (stage 7's input is y_new: FSAL; ``upto=5`` stops before it).
+
+        ``ring``: ``(slopes, y_next)`` = seven preallocated slope vectors (``slopes[0] is k0``) and the
+        vector that receives y_new -- no allocation inside the step (the forward evolution; at 2^29
+        amplitudes per GPU a fresh 8 GiB tensor per stage costs more than the stage itself)."""
         k = [k0]
         y_new = None
         for i in range(1, upto + 1):
-            Y = self._stage_input(y, k, i, h, publish=i < 6)
-            k.append(self.rhs(t + h * _ALPHA[i - 1], Y))
+            Y = self._stage_input(y, k, i, h, publish=i < 6, out=None if ring is None or i < 6 else ring[1])
+            k.append(self.rhs(t + h * _ALPHA[i - 1], Y, out=None if ring is None else ring[0][i]))
             if i == 6:
                 y_new = Y
         return k, y_new
@@ -314,7 +323,11 @@ class ShardedKet:
         ts = [float(x) for x in tsave]
         y = psi0_local.detach().clone()
         t = ts[0]
-        k0 = self.rhs(t, y)
+        # the integrator's whole working set, allocated once: y, y_next and seven slopes (+ the
+        # peer-visible stage buffer and the g receive buffers of the exchange)
+        slopes = [torch.empty_like(y) for _ in range(7)]
+        y_next = torch.empty_like(y)
+        k0 = self.rhs(t, y, out=slopes[0])
         steps, states = [], []
         if replay is None:
             d0 = self._scaled_norm(y, y.abs(), atol, rtol)
@@ -344,7 +357,7 @@ class ShardedKet:
                     pos += 1
                 if clipped:
                     cache_dt, cache_err, dt = dt, error, t_next - t
-                k, y_new = self._dp5_step(t, dt, y, k0)
+                k, y_new = self._dp5_step(t, dt, y, k0, ring=(slopes, y_next))
                 loc = self.plan.dp5_error_sumsq(k, [dt * e for e in ew], y, y_new, atol, rtol)
                 error = math.sqrt(self._sum(float(loc[0])) / float(1 << self.n))
                 if error != error:
@@ -352,7 +365,9 @@ class ShardedKet:
                 if replay is not None or error <= 1.0:
                     steps.append((t, dt, kk, bool(clipped)))
                     t = t_next if clipped else t + dt
-                    y, k0 = y_new, k[6]
+                    y, y_next = y_new, y                 # FSAL: the last slope opens the next step
+                    slopes[0], slopes[6] = slopes[6], slopes[0]
+                    k0 = slopes[0]
                 n_att += 1
                 if n_att >= max_steps:
                     raise RuntimeError("max_steps reached")
