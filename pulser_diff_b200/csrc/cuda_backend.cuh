@@ -115,6 +115,10 @@ int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cpl
                            const SiteOps* stage_ops, const double* beta, const double* ew, double dt,
                            double atol, double rtol, double* err_partial, double* err_out, cudaStream_t s);
 size_t stream_err_partial_count(const Geometry& g);
+// density tiles (dens_tile.cu): both bits of up to six sites closed per launch, N = 8..13
+bool dens_tile_supported(const Geometry& g);
+int launch_dens_stage(const Geometry& g, cplx* out, cplx* ymat, int n_in, const cplx* const* ins, const double* w,
+                      const SiteOpsDensity& so, cudaStream_t s);
 int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar, int n_in,
                        const cplx* const* ins, const double* w, cplx* ymat, cudaStream_t s);
 // small-register family (small_ket*.cu): whole forward / adjoint sweep in one cooperative kernel
@@ -307,8 +311,14 @@ class CudaBackend {
     return launch_tiled_dp5_step(g, y, k, ynew, stage_ops, &tab.beta[0][0], tab.b5, ew, dt, atol,
                                  rtol, tmp_a, tmp_b, red_scratch, err_out, st(s));
   }
+  // path 1 keeps the gather kernel (the correctness baseline); otherwise registers of 8..13 sites take the tiles
+  bool use_dens_tiles(const Geometry& g) const { return path != 1 && dens_tile_supported(g); }
   int stage_density(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
                     const double* w, const SiteOpsDensity& so, cplx* scratch, void* s) {
+    if (use_dens_tiles(g)) {
+      const bool plain = n_in == 1 && w[0] == 1.0 && comb == nullptr;
+      return launch_dens_stage(g, out, plain ? nullptr : (comb ? comb : scratch), n_in, ins, w, so, st(s));
+    }
     int n = 0;
     const cplx* src = ins[0];
     if (n_in > 1 || w[0] != 1.0) {

@@ -12,8 +12,8 @@
 //     sites), the later types 4-8 passive low column bits plus the column and row bits of two to four sites;
 //   * a thread owns 16 entries whose index differs in the four bits of TWO complete sites: those sites are
 //     applied in registers (partners and the uniform 4x4 coefficients cost no shared-memory traffic); the
-//     other sites of the tile read their partners from the shared-memory copy of the tile, with the three
-//     off-diagonal coefficients of the thread's own (c, r) value held in registers;
+//     other sites of the tile read their partners, and the three off-diagonal coefficients of the thread's own
+//     (c, r) value, from shared memory;
 //   * the FIRST launch of a stage forms the stage combination Y = sum_j w_j v_j on the fly (written once as
 //     Ymat for the later launches) and carries every diagonal term; later launches do out += F_sites Ymat.
 // A stage is 2 launches at N <= 10 and 3 at N = 11..13, each a pure stream.
@@ -134,18 +134,18 @@ k_dens_tile(const __grid_constant__ DensParams P, const __grid_constant__ DensGe
   __syncthreads();
 
   // ---- per-thread constants: the off-diagonal coefficients of the sites on thread bits
-  cplx cs[4][3];
+  // (the coefficients themselves stay in shared memory: 24 more doubles per thread would spill)
+  int crow[4];                // offset of row p of the site's 4x4 block in Ts
+  int pk = 0;                 // the thread's (c, r) value per site, two bits each
   int xc[4], xr[4];
   cplx dthr{0.0, 0.0};
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     if (s < G.n_thr_sites) {
       const int p = ((t >> G.thr_c[s]) & 1) | (((t >> G.thr_r[s]) & 1) << 1);
-      const cplx* Tp = Ts + G.thr_q[s] * 16 + p * 4;
-      cs[s][0] = Tp[p ^ 1];
-      cs[s][1] = Tp[p ^ 2];
-      cs[s][2] = Tp[p ^ 3];
-      if (FIRST) dthr = dthr + Tp[p];
+      crow[s] = G.thr_q[s] * 16 + p * 4;
+      pk |= p << (2 * s);
+      if (FIRST) dthr = dthr + Ts[crow[s] + p];
       xc[s] = 1 << G.thr_tb[G.thr_c[s]];
       xr[s] = 1 << G.thr_tb[G.thr_r[s]];
     }
@@ -182,9 +182,10 @@ k_dens_tile(const __grid_constant__ DensParams P, const __grid_constant__ DensGe
 #pragma unroll
     for (int s = 0; s < 4; ++s) {
       if (s < G.n_thr_sites) {
-        fma_acc(acc, cs[s][0], Y[sb ^ xc[s]]);
-        fma_acc(acc, cs[s][1], Y[sb ^ xr[s]]);
-        if (both) fma_acc(acc, cs[s][2], Y[sb ^ xc[s] ^ xr[s]]);
+        const int p = (pk >> (2 * s)) & 3;
+        fma_acc(acc, Ts[crow[s] + (p ^ 1)], Y[sb ^ xc[s]]);
+        fma_acc(acc, Ts[crow[s] + (p ^ 2)], Y[sb ^ xr[s]]);
+        if (both) fma_acc(acc, Ts[crow[s] + (p ^ 3)], Y[sb ^ xc[s] ^ xr[s]]);
       }
     }
     if (FIRST) {
@@ -251,7 +252,11 @@ TileTypes make_tile_types(int nq) {
   for (int gi = 0; gi < 2 && sizes[gi] > 0; ++gi) {
     const int k = sizes[gi], C = DT_BITS - 2 * k;
     DensGeom& G = tt.g[tt.n++];
-    for (int j = 0; j < C; ++j) G.tile_gbit[j] = j;
+    // passive bits: the lowest C index bits that do not belong to the group's sites
+    for (int j = 0, b = 0; j < C; ++b) {
+      const bool own = (b >= p0 && b < p0 + k) || (b >= nq + p0 && b < nq + p0 + k);
+      if (!own) G.tile_gbit[j++] = b;
+    }
     for (int j = 0; j < k; ++j) { G.tile_gbit[C + j] = p0 + j; G.tile_gbit[C + k + j] = nq + p0 + j; }
     // the last two sites of the group sit on the register bits
     G.reg_tb[0] = C + k - 2; G.reg_tb[1] = C + 2 * k - 2; G.reg_tb[2] = C + k - 1; G.reg_tb[3] = C + 2 * k - 1;

@@ -474,3 +474,35 @@ def test_c4_full_size_lindblad_invariants_and_fd_gradient(cuda_device):
     d = torch.zeros_like(dv.detach()); d[0, 14] = eps
     fd = (f(av.detach(), dv.detach() + d, frozen)[1] - f(av.detach(), dv.detach() - d, frozen)[1]) / (2 * eps)
     assert abs(fd.item() - g_dv[0, 14].item()) < 1e-6 * abs(fd.item()) + 1e-9
+
+
+@pytest.mark.parametrize("n,noise", [(8, "both"), (9, "both"), (10, "dephasing"), (10, "both"), (11, "both")])
+def test_density_tiles_equal_gather(cuda_device, n, noise):
+    """The density tile kernels (both bits of up to six sites closed per launch, two of them in registers;
+    dens_tile.cu) against the gather kernel (path 1) on the same inputs: DP5_ME states and gradients with a
+    phase-carrying drive.  "dephasing": diagonal collapse operator only (no double flips); "both": dephasing +
+    relaxation (every entry of the 4x4 site super-operators in use)."""
+    dev = cuda_device
+    pr = _program(n, T=16, seed=3)
+    col = torch.tensor([[[0.5, 0], [0, -0.5]], [[0, 0], [0.3, 0]]], dtype=torch.complex128)
+    if noise == "dephasing":
+        col = col[:1]
+    g = torch.Generator().manual_seed(n)
+    a = torch.randn(2 ** n, 2 ** n, dtype=torch.complex128, generator=g)
+    rho = a @ a.mH
+    rho = (rho / torch.trace(rho)).reshape(1, 4 ** n).to(dev)
+    tsave = torch.tensor([0.0, 0.003, 0.006], dtype=torch.float64)
+    outs, grads = [], []
+    for path in (1, 0):
+        av = pr["amp_values"].clone().requires_grad_(True)
+        dv = pr["det_values"].clone().requires_grad_(True)
+        st = ops.evolve(rho, tsave, dv, av, pr["pair_u"], n_qubits=n, kind=_cabi.PD_DENSITY, dt=pr["dt"],
+                        det_masks=pr["det_masks"], amp_masks=pr["amp_masks"], collapse=col,
+                        solver=_cabi.SOLVER_DP5_ME, options=_cabi.Options(path=path))
+        outs.append(st.detach())
+        w = torch.arange(4 ** n, device=dev).remainder(7).to(torch.float64)
+        val = (w * st[-1].real).sum() + (w * st[1].imag).sum()
+        grads.append(torch.autograd.grad(val, [av, dv]))
+    assert (outs[0] - outs[1]).abs().max() < 1e-13
+    for x, y in zip(grads[0], grads[1]):
+        assert (x - y).abs().max() < 1e-9 * max(1e-30, y.abs().max().item())
