@@ -82,7 +82,8 @@ typedef struct pd_options {
   const double* replay_dt;      /* host [n_replay] step sizes (ignored for clipped steps) */
   const uint8_t* replay_clipped;/* host [n_replay] 1 = step lands on the next tsave point */
   int32_t path;         /* kernel family: 0 = auto, 1 = gather, 2 = tiled (18<=N<=23), 3 = small-register
-                           cooperative kernels (N<=14), 4 = stream (N>=16) */
+                           cooperative kernels (N<=14), 4 = stream (N>=16), 5 = density tiles (Lindblad,
+                           8<=N<=13; opt-in, slower than the gather kernel on B200) */
 } pd_options;
 
 typedef struct pd_step_record {

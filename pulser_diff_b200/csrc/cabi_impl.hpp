@@ -106,7 +106,7 @@ int pd_plan_set_collapse(pd_plan* p, int32_t n_ops, const double* ops_host) {
 }
 int pd_plan_set_path(pd_plan* p, int32_t path) {
   return guarded_on(p, [&] {
-    need(p != nullptr && path >= 0 && path <= 4, "pd_plan_set_path: bad argument");
+    need(p != nullptr && path >= 0 && path <= 5, "pd_plan_set_path: bad argument");
     p->eng.bk.path = path;
   });
 }

@@ -311,8 +311,12 @@ class CudaBackend {
     return launch_tiled_dp5_step(g, y, k, ynew, stage_ops, &tab.beta[0][0], tab.b5, ew, dt, atol,
                                  rtol, tmp_a, tmp_b, red_scratch, err_out, st(s));
   }
-  // path 1 keeps the gather kernel (the correctness baseline); otherwise registers of 8..13 sites take the tiles
-  bool use_dens_tiles(const Geometry& g) const { return path != 1 && dens_tile_supported(g); }
+  // The density tiles are opt-in (path 5): measured at N = 12 they are SLOWER than the gather kernel (DP5_ME
+  // step 6.3-6.7 ms with 2-3 tile launches per application, 7.5 ms with one launch that gathers the sites
+  // outside the tile, against 5.6 ms; profiles/r02_lindblad.md) -- the gather kernel runs at the L2 gather
+  // rate with full occupancy, the tile kernels serialise a load phase and an instruction-heavy compute phase
+  // at two CTAs per SM.
+  bool use_dens_tiles(const Geometry& g) const { return path == 5 && dens_tile_supported(g); }
   int stage_density(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
                     const double* w, const SiteOpsDensity& so, cplx* scratch, void* s) {
     if (use_dens_tiles(g)) {

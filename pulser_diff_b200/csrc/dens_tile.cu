@@ -17,6 +17,7 @@
 //   * the FIRST launch of a stage forms the stage combination Y = sum_j w_j v_j on the fly (written once as
 //     Ymat for the later launches) and carries every diagonal term; later launches do out += F_sites Ymat.
 // A stage is 2 launches at N <= 10 and 3 at N = 11..13, each a pure stream.
+#include <cstdlib>
 #include <cstring>
 
 #include "cuda_backend.cuh"
@@ -47,6 +48,8 @@ struct DensGeom {
 
 struct DensParams {
   int nq, n_in, need_both;
+  int gather_rest;       // FIRST launch also applies the sites outside the tile, partners fetched through L2 from
+                         // ysrc (one launch per application; needs the stage input materialised beforehand)
   size_t dim;
   unsigned tiles_per_vec;
   const cplx* v[DT_MAXIN];
@@ -188,6 +191,21 @@ k_dens_tile(const __grid_constant__ DensParams P, const __grid_constant__ DensGe
         if (both) fma_acc(acc, Ts[crow[s] + (p ^ 3)], Y[sb ^ xc[s] ^ xr[s]]);
       }
     }
+    if (FIRST && P.gather_rest) {
+      // sites outside the tile: their (c, r) value is the same for the whole CTA, so the coefficients are
+      // uniform; the partners are the same element of three other tiles
+      const cplx* src = P.ysrc + g0 + goff(i);
+      for (int s = 0; s < G.n_out_sites; ++s) {
+        const int pbit = G.out_p[s];
+        const int p = (int)((base >> pbit) & 1) | ((int)((base >> (P.nq + pbit)) & 1) << 1);
+        const cplx* Tp = Ts + G.out_q[s] * 16 + p * 4;
+        const long long dc = (p & 1) ? -((long long)1 << pbit) : ((long long)1 << pbit);
+        const long long dr = (p & 2) ? -((long long)1 << (P.nq + pbit)) : ((long long)1 << (P.nq + pbit));
+        fma_acc(acc, Tp[p ^ 1], ld_stream(src + dc));
+        fma_acc(acc, Tp[p ^ 2], ld_stream(src + dr));
+        if (both) fma_acc(acc, Tp[p ^ 3], ld_stream(src + dc + dr));
+      }
+    }
     if (FIRST) {
       const size_t e = e0 + goff(i);
       const double dg = __ldg(P.diag + (e >> P.nq)) - __ldg(P.diag + (e & cmask));
@@ -313,6 +331,9 @@ int launch_dens_stage(const Geometry& g, cplx* out, cplx* ymat, int n_in, const 
   }
   const TileTypes& tt = tile_types(g.nq);
   const bool plain = n_in == 1 && w[0] == 1.0;
+  // PD_DENS_MODE: 1 (default) = one launch per application: six sites inside the tile, the others gathered
+  // through L2 (the combination is formed by a separate pass when there is one); 2 = tiles only, 2-3 launches
+  static const int mode = [] { const char* e = std::getenv("PD_DENS_MODE"); return e ? std::atoi(e) : 1; }();
   if (!plain && ymat == nullptr) throw Error(PD_ERR_STATE, "density stage needs a buffer for the combined input");
   DensParams P{};
   P.nq = g.nq; P.n_in = n_in; P.need_both = any_double_flip(so, g.nq) ? 1 : 0; P.dim = g.dim;
@@ -323,6 +344,17 @@ int launch_dens_stage(const Geometry& g, cplx* out, cplx* ymat, int n_in, const 
   P.out = out;
   P.diag = g.diag;
   const unsigned grid = P.tiles_per_vec * (unsigned)g.batch;
+  if (mode == 1) {
+    int n = 0;
+    if (!plain) {
+      n += launch_lincomb(g, ymat, n_in, ins, w, s);
+      P.n_in = 1; P.v[0] = ymat; P.w[0] = 1.0; P.ymat = nullptr; P.ysrc = ymat;
+    }
+    P.gather_rest = 1;
+    k_dens_tile<true><<<grid, DT_NT, smem, s>>>(P, tt.g[0], so);
+    PD_CUDA_CHECK(cudaGetLastError());
+    return n + 1;
+  }
   k_dens_tile<true><<<grid, DT_NT, smem, s>>>(P, tt.g[0], so);
   for (int ti = 1; ti < tt.n; ++ti) k_dens_tile<false><<<grid, DT_NT, smem, s>>>(P, tt.g[ti], so);
   PD_CUDA_CHECK(cudaGetLastError());

@@ -478,8 +478,8 @@ def test_c4_full_size_lindblad_invariants_and_fd_gradient(cuda_device):
 
 @pytest.mark.parametrize("n,noise", [(8, "both"), (9, "both"), (10, "dephasing"), (10, "both"), (11, "both")])
 def test_density_tiles_equal_gather(cuda_device, n, noise):
-    """The density tile kernels (both bits of up to six sites closed per launch, two of them in registers;
-    dens_tile.cu) against the gather kernel (path 1) on the same inputs: DP5_ME states and gradients with a
+    """The opt-in density tile kernels (path 5: both bits of up to six sites closed per launch, two of them in
+    registers; dens_tile.cu) against the gather kernel (path 1) on the same inputs: DP5_ME states and gradients with a
     phase-carrying drive.  "dephasing": diagonal collapse operator only (no double flips); "both": dephasing +
     relaxation (every entry of the 4x4 site super-operators in use)."""
     dev = cuda_device
@@ -493,7 +493,7 @@ def test_density_tiles_equal_gather(cuda_device, n, noise):
     rho = (rho / torch.trace(rho)).reshape(1, 4 ** n).to(dev)
     tsave = torch.tensor([0.0, 0.003, 0.006], dtype=torch.float64)
     outs, grads = [], []
-    for path in (1, 0):
+    for path in (1, 5):
         av = pr["amp_values"].clone().requires_grad_(True)
         dv = pr["det_values"].clone().requires_grad_(True)
         st = ops.evolve(rho, tsave, dv, av, pr["pair_u"], n_qubits=n, kind=_cabi.PD_DENSITY, dt=pr["dt"],
