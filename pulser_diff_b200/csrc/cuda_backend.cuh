@@ -79,6 +79,7 @@ int launch_apply_ket(const Geometry& g, cplx* out, const cplx* in, const SiteOps
 int launch_apply_density(const Geometry& g, cplx* out, const cplx* in, const SiteOpsDensity& so,
                          cudaStream_t s);
 int launch_build_diag(double* diag, int nq, const double* d_pair_u, cudaStream_t s);
+int launch_build_diag_parts(double* parts, int nq, const double* diag, cudaStream_t s);
 int launch_scaled_sumsq(const Geometry& g, double* out, const cplx* x, const cplx* xsub,
                         const cplx* ref, double atol, double rtol, double* scratch, cudaStream_t s);
 int launch_err_sumsq(const Geometry& g, double* out, const cplx* const* k, const double* ew,
@@ -255,6 +256,9 @@ class CudaBackend {
   void build_diag(double* diag, int nq, const double* pair_u_host, void* s) {
     PD_CUDA_CHECK(copy_h2d(d_pair_u_, pair_u_host, sizeof(double) * nq * nq, st(s)));
     launch_build_diag(diag, nq, d_pair_u_, st(s));
+  }
+  void build_diag_parts(double* parts, int nq, const double* diag, void* s) {
+    launch_build_diag_parts(parts, nq, diag, st(s));
   }
   int lincomb(const Geometry& g, cplx* out, int n_in, const cplx* const* ins, const double* w, void* s) {
     return launch_lincomb(g, out, n_in, ins, w, st(s));

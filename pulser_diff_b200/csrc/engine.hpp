@@ -56,6 +56,7 @@ class Engine {
   Tableau tab;
   int64_t launches = 0;
   double* d_diag = nullptr;
+  double* d_diag_parts = nullptr;
   size_t L = 0;  // complex elements per state block = batch * dim
 
   Engine(int nq, int batch, int kind, int device) : bk(device) {
@@ -76,16 +77,24 @@ class Engine {
     d_diag = (double*)bk.alloc(sizeof(double) * ((size_t)1 << nq));
     bk.zero(d_diag, sizeof(double) * ((size_t)1 << nq), nullptr);
     geo.diag = d_diag;
+    if (kind == PD_KET && nq >= 16) {
+      const size_t tiles = (size_t)1 << (nq - 12);
+      d_diag_parts = (double*)bk.alloc(sizeof(double) * (4096 + 13 * tiles));
+      bk.zero(d_diag_parts, sizeof(double) * (4096 + 13 * tiles), nullptr);
+      geo.diag_parts = d_diag_parts;
+    }
   }
   ~Engine() {
     for (auto& kv : bufs_) bk.free(kv.second);
     bk.free(d_diag);
+    if (d_diag_parts) bk.free(d_diag_parts);
   }
 
   // ---- setup ----------------------------------------------------------------------------
   void set_interaction(const double* pair_u, void* stream) {
     std::copy(pair_u, pair_u + (size_t)prog.nq * prog.nq, prog.pair_u.begin());
     bk.build_diag(d_diag, prog.nq, prog.pair_u.data(), stream);
+    if (d_diag_parts) bk.build_diag_parts(d_diag_parts, prog.nq, d_diag, stream);
     bk.sync(stream);
   }
   void set_terms(int n_samples, double dt, int n_det, const uint64_t* dm, const double* dv,

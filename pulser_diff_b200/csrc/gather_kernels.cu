@@ -414,6 +414,28 @@ int launch_apply_density(const Geometry& g, cplx* out, const cplx* in, const Sit
   return 1;
 }
 
+// Dint split for 4096-amplitude tiles (layout: pd_common.hpp Geometry::diag_parts), read off the full diagonal:
+// bit value 1 = ground state = no interaction, so setting a group of bits switches its qubits off.
+__global__ void __launch_bounds__(kThreads) k_build_diag_parts(double* parts, int nq, const double* __restrict__ diag) {
+  const size_t T = (size_t)1 << (nq - 12), dim = (size_t)1 << nq;
+  const size_t total = 4096 + 13 * T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    if (i < 4096) parts[i] = diag[(dim - 4096) | i];
+    else if (i < 4096 + T) parts[i] = diag[((i - 4096) << 12) | 0xFFF];
+    else {
+      const size_t j = i - 4096 - T, h = j / 12;
+      const unsigned p = (unsigned)(j % 12);
+      parts[i] = diag[(h << 12) | (0xFFFu & ~(1u << p))] - diag[(h << 12) | 0xFFF];
+    }
+  }
+}
+int launch_build_diag_parts(double* parts, int nq, const double* diag, cudaStream_t s) {
+  const size_t total = 4096 + 13 * ((size_t)1 << (nq - 12));
+  k_build_diag_parts<<<grid_for(total), kThreads, 0, s>>>(parts, nq, diag);
+  PD_CUDA_CHECK(cudaGetLastError());
+  return 1;
+}
+
 int launch_build_diag(double* diag, int nq, const double* d_pair_u, cudaStream_t s) {
   k_build_diag<<<grid_for((size_t)1 << nq), kThreads, 0, s>>>(diag, nq, d_pair_u);
   PD_CUDA_CHECK(cudaGetLastError());

@@ -84,6 +84,12 @@ struct Geometry {
   size_t dim;    // 2^nbits
   int batch;
   const double* diag;  // device Dint[2^nq]
+  // kets of nq >= 16: Dint split for 4096-amplitude tiles (stream family), tile = index >> 12:
+  //   [0, 4096)            Dlow[l]   pairs inside the low 12 bits
+  //   [4096, 4096 + T)     Dhh[tile] pairs inside the bits above            (T = 2^(nq-12))
+  //   [4096 + T, ... 13T)  ch[tile][p] = sum over occupied high bits of U(p, .), p < 12
+  // so that Dint[s] = Dhh + Dlow + sum over occupied low bits of ch (nullptr: not built)
+  const double* diag_parts = nullptr;
 };
 
 // one accepted step as handed to the small-register adjoint sweep

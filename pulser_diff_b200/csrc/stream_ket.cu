@@ -61,7 +61,7 @@ struct StreamParams {
   double w[kMaxIn];
   cplx* ymat;                 // A launch: combined input written here (nullable)
   cplx* out;
-  const double* diag;
+  const double* diag;         // Dint split for tiles (Geometry::diag_parts): no 8 B/amplitude stream from HBM
   // embedded error estimate of the Dormand-Prince step (last stage only):
   //   A launch:      aux = sum_j w2_j v_j                  (partial error vector, w2 = dt*(b5-b4))
   //   last g launch: err = aux + werr*out;  sum |err / (atol + rtol*max(|y0|,|Ymat|))|^2 per CTA
@@ -132,16 +132,24 @@ __device__ __forceinline__ void a_tile_flips(const StreamParams& P, const Stream
   const cplx* Tt = T + t;
   const cplx* Tp[8];
   double sg[8];
-  double dthr = 0.0;          // diagonal of the bits this thread's elements share: tile bits 0-7 and the bits above the tile
+  // Diagonal = detunings + interaction.  The interaction of an occupied low bit p with the occupied bits above
+  // the tile, ch[tile][p], acts like one more detuning on p: 13 doubles per tile from a small table instead of
+  // 8 B per amplitude from HBM; the pairs inside the low 12 bits come from a 32 KiB table that lives in L1.
+  const size_t n_tiles = P.dim >> TB;
+  const double* ch = P.diag + TILE + n_tiles + tile * 12;
+  double dthr = __ldg(P.diag + TILE + tile);   // bits this thread's elements share: tile bits 0-7, bits above the tile
 #pragma unroll
   for (int lb = 0; lb < 8; ++lb) {
     const bool a = (t >> lb) & 1;
     Tp[lb] = T + (t ^ (1 << lb));
     sg[lb] = a ? cf.gim[lb] : -cf.gim[lb];
-    dthr += a ? 0.0 : cf.d[lb];
+    dthr += a ? 0.0 : (cf.d[lb] + __ldg(ch + lb));
   }
+  double d8[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) d8[k] = cf.d[8 + k] + __ldg(ch + 8 + k);
   for (int gb = TB; gb < nq; ++gb) dthr += ((tile >> (gb - TB)) & 1) ? 0.0 : cf.d[gb];
-  const double* dg_ptr = P.diag + (tile << TB) + t;
+  const double* dg_ptr = P.diag + t;
   const unsigned long long pol = l2_policy(P.pol_st);
   tile_sync<NBAR>();
 
@@ -160,7 +168,7 @@ __device__ __forceinline__ void a_tile_flips(const StreamParams& P, const Stream
     double dd = dthr + dg;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-      if (!((i >> k) & 1)) dd += cf.d[8 + k];
+      if (!((i >> k) & 1)) dd += d8[k];
     const cplx own = Tt[NT * i];
     h.re = fma(dd, own.re, h.re);
     h.im = fma(dd, own.im, h.im);
@@ -560,8 +568,15 @@ __device__ __forceinline__ void pipe_a_item(const StreamParams& P, const StreamC
     dthr += a ? 0.0 : cf.d[lb];
   }
   for (int gb = TB; gb < P.nq; ++gb) dthr += ((tile >> (gb - TB)) & 1) ? 0.0 : cf.d[gb];
-  // static diagonal: all PEPT values are fetched before the tile exchange, so their latency hides behind it
-  const double* dg_ptr = P.diag + (tile << TB) + t;
+  // interaction part of the diagonal from the tile tables (see a_tile_flips)
+  const double* ch = P.diag + TILE + (P.dim >> TB) + tile * 12;
+  dthr += __ldg(P.diag + TILE + tile);
+#pragma unroll
+  for (int lb = 0; lb < PXB; ++lb) dthr += ((t >> lb) & 1) ? 0.0 : __ldg(ch + lb);
+  double dr[PRB];
+#pragma unroll
+  for (int k = 0; k < PRB; ++k) dr[k] = cf.d[PXB + k] + __ldg(ch + PXB + k);
+  const double* dg_ptr = P.diag + t;
   double dg[PEPT];
 #pragma unroll
   for (int i = 0; i < PEPT; ++i) dg[i] = __ldg(dg_ptr + kPipeCons * i);
@@ -585,7 +600,7 @@ __device__ __forceinline__ void pipe_a_item(const StreamParams& P, const StreamC
     double dd = dthr + dg[i];
 #pragma unroll
     for (int k = 0; k < PRB; ++k)
-      if (!((i >> k) & 1)) dd += cf.d[PXB + k];
+      if (!((i >> k) & 1)) dd += dr[k];
     h.re = fma(dd, y[i].re, h.re);
     h.im = fma(dd, y[i].im, h.im);
     st_pol(P.out + base + t + kPipeCons * i, cf.kappa * h, pol);
@@ -1030,7 +1045,8 @@ constexpr int kMinStreamQubits = 16;   // below this the gather kernels run out 
 
 bool stream_ket_supported(const Geometry& g) {
   // the strided groups take the bits above 12 in chunks of <= 8; every chunk needs >= 1 bit
-  return g.kind == PD_KET && g.nq >= kMinStreamQubits && g.nq <= kMaxQubits - 1 && (g.dim >> TB) * (size_t)g.batch < ((size_t)1 << 31);
+  return g.kind == PD_KET && g.nq >= kMinStreamQubits && g.nq <= kMaxQubits - 1 && g.diag_parts != nullptr &&
+         (g.dim >> TB) * (size_t)g.batch < ((size_t)1 << 31);
 }
 
 // out = G (sum_j w_j in_j); ymat receives the combined input (required: the group launches read it).
@@ -1046,7 +1062,7 @@ int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, 
   const cplx* ysrc = plain ? ins[0] : ymat;
   if (!plain && ymat == nullptr) throw Error(PD_ERR_STATE, "stream stage needs a buffer for the combined input");
   StreamParams A{};
-  A.nq = g.nq; A.dim = g.dim; A.n_in = n_in; A.diag = g.diag; A.ymat = plain ? nullptr : ymat; A.out = out;
+  A.nq = g.nq; A.dim = g.dim; A.n_in = n_in; A.diag = g.diag_parts; A.ymat = plain ? nullptr : ymat; A.out = out;
   for (int j = 0; j < n_in; ++j) { A.v[j] = ins[j]; A.w[j] = w[j]; }
   const int n = launch_stage(g, A, cf, uni, ysrc, nullptr, s);
   PD_CUDA_CHECK(cudaGetLastError());
@@ -1406,7 +1422,7 @@ int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cpl
     const bool last = i == 6;
     cplx* ym = last ? ynew : ymat;
     StreamParams A{};
-    A.nq = g.nq; A.dim = g.dim; A.diag = g.diag; A.ymat = ym; A.out = k[i];
+    A.nq = g.nq; A.dim = g.dim; A.diag = g.diag_parts; A.ymat = ym; A.out = k[i];
     int m = 0;
     A.v[m] = y; A.w[m] = 1.0; A.w2[m] = 0.0; ++m;
     for (int j = 0; j < i; ++j) {

@@ -67,13 +67,16 @@ def duration_mode_samples(durations_us: Sequence, amps: Sequence, dets: Sequence
     (reference model.py:184-206, 301-322, 324-368): ``sum(int(d*1000)) + 5`` samples, each the
     sum of the pulses' tanh envelopes."""
     total = sum(int(float(d) * 1000) for d in durations_us) + 5
-    t = torch.arange(total, dtype=F64)
-    out = {k: torch.zeros(total, dtype=F64) for k in ("amp", "det", "phase")}
+    # built where the trainable parameters live: with pulse parameters on the GPU the envelopes (and their
+    # autograd graph) never touch the host (SURVEY.md 8f rank 4)
+    dev = next((x.device for x in (*durations_us, *amps, *dets, *phases) if isinstance(x, Tensor)), None)
+    t = torch.arange(total, dtype=F64, device=dev)
+    out = {k: torch.zeros(total, dtype=F64, device=dev) for k in ("amp", "det", "phase")}
     ti = 0
     for d, a, de, ph in zip(durations_us, amps, dets, phases):
-        tf = ti + _t(d).reshape(())
+        tf = ti + _t(d).reshape(()).to(t.device)
         for key, v in (("amp", a), ("det", de), ("phase", ph)):
-            out[key] = out[key] + tanh_envelope(t, ti, tf, v)
+            out[key] = out[key] + tanh_envelope(t, ti, tf, _t(v).to(t.device))
         ti = tf
     return out
 

@@ -63,6 +63,15 @@ class HostBackend {
   size_t segment_budget_bytes() { return segment_budget; }
   size_t segment_budget = (size_t)1 << 28;
 
+  void build_diag_parts(double* parts, int nq, const double* diag, void*) {
+    const size_t T = (size_t)1 << (nq - 12);
+    for (size_t l = 0; l < 4096; ++l) parts[l] = diag[(((size_t)1 << nq) - 4096) | l];
+    for (size_t h = 0; h < T; ++h) {
+      parts[4096 + h] = diag[(h << 12) | 0xFFF];
+      for (int p = 0; p < 12; ++p)
+        parts[4096 + T + h * 12 + p] = diag[(h << 12) | (0xFFF & ~(1u << p))] - diag[(h << 12) | 0xFFF];
+    }
+  }
   void build_diag(double* diag, int nq, const double* u, void*) {
     size_t dim = (size_t)1 << nq;
     for (size_t s = 0; s < dim; ++s) {
