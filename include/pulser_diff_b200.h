@@ -221,6 +221,12 @@ int pd_dp5_error_sumsq(pd_plan* p, void* stream, const void* const* k_dev, const
 int pd_sharded_accumulate(pd_plan* p, void* stream, void* out_dev, const void* psi_dev, double shift,
                           int32_t n_peers, const void* const* peer_slices,
                           const double* coef_host);
+/* Same on a range of the slice: every pointer already points at the first amplitude of the range,
+ * n_amp amplitudes are updated.  Lets the caller accumulate chunk c while the copy engines are still
+ * pulling chunk c + 1 of the partner slices. */
+int pd_sharded_accumulate_range(pd_plan* p, void* stream, void* out_dev, const void* psi_dev, double shift,
+                                int32_t n_peers, const void* const* peer_slices, const double* coef_host,
+                                uint64_t n_amp);
 
 /* ---- measurement hooks (bench.py roofline) ------------------------------------------------- */
 /* Average device time (ms, CUDA events on `stream`) of `reps` back-to-back H(t)·psi

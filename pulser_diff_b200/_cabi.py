@@ -48,7 +48,7 @@ EXPORTS = (
     "pd_hpsi", "pd_rhs", "pd_rhs_vjp", "pd_pair_gradient_flush",
     "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
     "pd_evolve_forward_units", "pd_evolve_backward_units", "pd_tape_unit_steps",
-    "pd_tape_destroy", "pd_expect_diag", "pd_sharded_accumulate", "pd_lincomb", "pd_dp5_error_sumsq", "pd_bench_hpsi", "pd_bench_dp5_steps",
+    "pd_tape_destroy", "pd_expect_diag", "pd_sharded_accumulate", "pd_sharded_accumulate_range", "pd_lincomb", "pd_dp5_error_sumsq", "pd_bench_hpsi", "pd_bench_dp5_steps",
     "pd_plan_launch_count", "pd_transfer_counters", "pd_is_cuda",
 )
 
@@ -90,6 +90,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.pd_lincomb.argtypes = [vp, vp, vp, i32, C.POINTER(vp), pdbl]
     lib.pd_dp5_error_sumsq.argtypes = [vp, vp, C.POINTER(vp), pdbl, vp, vp, dbl, dbl, pdbl]
     lib.pd_sharded_accumulate.argtypes = [vp, vp, vp, vp, dbl, i32, C.POINTER(vp), pdbl]
+    lib.pd_sharded_accumulate_range.argtypes = [vp, vp, vp, vp, dbl, i32, C.POINTER(vp), pdbl, C.c_uint64]
     lib.pd_bench_hpsi.argtypes = [vp, vp, dbl, i32, vp, vp, pdbl]
     lib.pd_bench_dp5_steps.argtypes = [vp, vp, dbl, dbl, i32, vp, pdbl]
     lib.pd_plan_launch_count.argtypes = [vp]
@@ -501,6 +502,21 @@ class Plan:
             cf[2 * i], cf[2 * i + 1] = complex(c).real, complex(c).imag
         _check(lib().pd_sharded_accumulate(self._ptr, _stream(self.device), _dptr(out), _dptr(psi),
                                            float(shift), k, ptrs, cf))
+
+    def sharded_accumulate_range(self, out_ptr: int, psi_ptr: int, shift: float, peer_ptrs: Sequence[int],
+                                 coefs: Sequence[complex], n_amp: int) -> None:
+        """:meth:`sharded_accumulate` on ``n_amp`` amplitudes starting at the given raw addresses (the
+        caller offsets every pointer to the start of the range)."""
+        k = len(peer_ptrs)
+        if k != len(coefs):
+            raise ValueError("one coefficient per peer slice")
+        ptrs = (C.c_void_p * max(k, 1))(*[C.c_void_p(int(a)) for a in peer_ptrs])
+        cf = (C.c_double * max(2 * k, 1))()
+        for i, c in enumerate(coefs):
+            cf[2 * i], cf[2 * i + 1] = complex(c).real, complex(c).imag
+        _check(lib().pd_sharded_accumulate_range(self._ptr, _stream(self.device), C.c_void_p(int(out_ptr)),
+                                                 C.c_void_p(int(psi_ptr)), float(shift), k, ptrs, cf,
+                                                 C.c_uint64(int(n_amp))))
 
     def bench_hpsi(self, t: float, psi: torch.Tensor, reps: int) -> float:
         """Average device ms of one H(t)·psi (CUDA events on the current stream)."""

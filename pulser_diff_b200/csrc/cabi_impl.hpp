@@ -271,6 +271,20 @@ int pd_sharded_accumulate(pd_plan* p, void* stream, void* out_dev, const void* p
                               (const pd::cplx* const*)peer_slices, (const pd::cplx*)coef_host, stream);
   });
 }
+int pd_sharded_accumulate_range(pd_plan* p, void* stream, void* out_dev, const void* psi_dev, double shift,
+                                int32_t n_peers, const void* const* peer_slices, const double* coef_host,
+                                uint64_t n_amp) {
+  return guarded_on(p, [&] {
+    need(p && out_dev && psi_dev && n_peers >= 0 && n_peers <= 16 && n_amp > 0,
+         "pd_sharded_accumulate_range: bad argument");
+    need(n_peers == 0 || (peer_slices && coef_host), "pd_sharded_accumulate_range: NULL peer list");
+    for (int k = 0; k < n_peers; ++k)
+      need(peer_slices[k] != nullptr, "pd_sharded_accumulate_range: NULL peer slice");
+    p->eng.sharded_accumulate_n((pd::cplx*)out_dev, (const pd::cplx*)psi_dev, shift, n_peers,
+                                (const pd::cplx* const*)peer_slices, (const pd::cplx*)coef_host, (size_t)n_amp,
+                                stream);
+  });
+}
 int pd_bench_hpsi(pd_plan* p, void* stream, double t, int32_t reps, const void* in_dev,
                   void* out_dev, double* ms_per_apply_host) {
   return guarded_on(p, [&] {

@@ -410,6 +410,14 @@ class Engine {
                           const cplx* const* peers, const cplx* coef, void* stream) {
     launches += bk.sharded_accumulate(geo, out, psi, shift, n_peers, peers, coef, stream);
   }
+  void sharded_accumulate_n(cplx* out, const cplx* psi, double shift, int n_peers, const cplx* const* peers,
+                            const cplx* coef, size_t n_amp, void* stream) {
+    if (n_amp > geo.dim * (size_t)geo.batch) throw Error(PD_ERR_INVALID, "range longer than the slice");
+    Geometry g1 = geo;
+    g1.batch = 1;
+    g1.dim = n_amp;
+    launches += bk.sharded_accumulate(g1, out, psi, shift, n_peers, peers, coef, stream);
+  }
 
  private:
   std::vector<std::pair<std::string, void*>> bufs_;

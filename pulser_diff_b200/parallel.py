@@ -148,7 +148,8 @@ class ShardedKet:
         # energy shift from global-global interaction (static) -- detuning part is time dependent
         self.e_static = sum(float(u[p, q]) * self.r_glob[p] * self.r_glob[q]
                             for p in range(g) for q in range(p + 1, g))
-        self._sym = self._hdl = self._side = None
+        self._sym = self._hdl = self._side = self._events = None
+        self._pull_chunks = 8
         self._mode = "read" if peer_memory == "read" else "copy"
         if peer_memory:
             if self.device.type != "cuda":
@@ -241,18 +242,35 @@ class ShardedKet:
                 self._recv = [torch.empty_like(self._sym) for _ in range(self.g)]
                 self._peer_bufs = [self._hdl.get_buffer(r, self._sym.shape, self._sym.dtype)
                                    for r in range(self.world)]
+            # the pulls go chunk by chunk (all partners' chunk 0 first) so that the accumulate of a chunk can
+            # run while the copy engines are still busy with the next ones
+            n_loc = 1 << self.nl
+            n_ch = max(1, min(self._pull_chunks, n_loc >> 20))
+            ch = n_loc // n_ch
+            if self._events is None or len(self._events) != n_ch:
+                self._events = [torch.cuda.Event() for _ in range(n_ch)]
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                for k, r in enumerate(peers):
-                    self._recv[k].copy_(self._peer_bufs[r])
+                for c_ in range(n_ch):
+                    a_, b_ = 2 * c_ * ch, 2 * (c_ + 1) * ch          # float64 view: (re, im) pairs
+                    for k, r in enumerate(peers):
+                        self._recv[k][:, a_:b_].copy_(self._peer_bufs[r][:, a_:b_])
+                    self._events[c_].record(self._side)
             ptrs = [self._recv[k].data_ptr() for k in range(len(peers))]
         else:
             ptrs = [self._peer_ptrs[r] for r in peers]
         ops.configure(self.plan, self._prog)
         out = self.plan.hpsi(t, buf, rhs=rhs, out=out)
-        if copy:
-            main.wait_stream(self._side)
-        self.plan.sharded_accumulate(out, buf, 0.0, [buf.data_ptr()] + ptrs, coefs)
+        if copy and n_ch > 1:
+            for c_ in range(n_ch):
+                main.wait_event(self._events[c_])
+                off = 16 * c_ * ch
+                self.plan.sharded_accumulate_range(out.data_ptr() + off, buf.data_ptr() + off, 0.0,
+                                                   [buf.data_ptr() + off] + [p_ + off for p_ in ptrs], coefs, ch)
+        else:
+            if copy:
+                main.wait_stream(self._side)
+            self.plan.sharded_accumulate(out, buf, 0.0, [buf.data_ptr()] + ptrs, coefs)
         self._hdl.barrier(channel=1)                 # partners are done reading this slice
         if keep_partners:
             n_loc = 1 << self.nl
