@@ -1129,7 +1129,7 @@ __device__ __forceinline__ void corr_block_reduce(double (&acc)[R], double* part
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < NT / 32; ++w) s += sh[w][threadIdx.x];
-    partial[(size_t)blockIdx.x * R + threadIdx.x] = s;
+    partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;   // [R][n_blocks]: the final pass reads rows
   }
 }
 
@@ -1308,21 +1308,23 @@ struct CorrFinal {
 __global__ void __launch_bounds__(256) k_stream_corr_final(const __grid_constant__ CorrFinal F) {
   const int p = blockIdx.x, t = threadIdx.x;
   double gd = 0.0, ga = 0.0, gb = 0.0;
+  const size_t nbk = F.nblocks;
   if (p < TB) {
+    const double* r0 = F.part_a + (size_t)(p * 3) * nbk;
     for (unsigned b = t; b < F.nblocks; b += 256) {
-      const double* r = F.part_a + (size_t)b * kCA + p * 3;
-      gd += r[0]; ga += r[1]; gb += r[2];
+      gd += r0[b]; ga += r0[nbk + b]; gb += r0[2 * nbk + b];
     }
   } else {
     // self terms: CTAs whose tile index has bit (p - TB) clear
+    const double* rs = F.part_a + (size_t)(kCA - 1) * nbk;
     for (unsigned b = t; b < F.nblocks; b += 256)
-      if (!(((b % F.tiles_per_vec) >> (p - TB)) & 1u)) gd += F.part_a[(size_t)b * kCA + kCA - 1];
+      if (!(((b % F.tiles_per_vec) >> (p - TB)) & 1u)) gd += rs[b];
     for (int g = 0; g < F.n_groups; ++g)
       if (p >= F.lo[g] && p < F.lo[g] + F.nb[g]) {
         const int j = p - F.lo[g];
+        const double* r0 = F.part_g[g] + (size_t)(j * 2) * nbk;
         for (unsigned b = t; b < F.nblocks; b += 256) {
-          const double* r = F.part_g[g] + (size_t)b * kCG + j * 2;
-          ga += r[0]; gb += r[1];
+          ga += r0[b]; gb += r0[nbk + b];
         }
       }
   }
