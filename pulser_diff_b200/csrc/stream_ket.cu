@@ -71,6 +71,8 @@ struct StreamParams {
   double werr, atol, rtol;
   double* err_partial;        // [n_tiles] (g launch, nullable)
   int pol_st, pol_ld;         // L2 policy kinds (l2_policy) of this launch's result stores / tile loads
+  int pol_in;                 // A launch: L2 policy of the input loads (a plain application re-reads its input
+                              // in the group tiles, a combination is read once)
   int via_ring;               // pipelined group items: tile data arrives as TMA boxes through the ring (else: loads)
 };
 
@@ -186,7 +188,7 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
   // ---- combination: Y = sum_j w_j v_j, 4 elements x 2 vectors in flight per thread
   constexpr int QP = 4;
   constexpr bool want_aux = AUX;                   // the error-estimate vector of the last stage
-  const unsigned long long pol = l2_policy(P.pol_st);
+  const unsigned long long pol = l2_policy(P.pol_st), pol_in = l2_policy(P.pol_in);
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += QP) {
     cplx y[QP], z[QP];
@@ -198,12 +200,12 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
       const double w0 = P.w[j];
       cplx x0[QP], x1[QP];
 #pragma unroll
-      for (int i = 0; i < QP; ++i) x0[i] = ldcs(v0 + t + NT * (q0 + i));
+      for (int i = 0; i < QP; ++i) x0[i] = ld_pol(v0 + t + NT * (q0 + i), pol_in);
       if (two) {
         const cplx* v1 = P.v[j + 1] + base;
         const double w1 = P.w[j + 1];
 #pragma unroll
-        for (int i = 0; i < QP; ++i) x1[i] = ldcs(v1 + t + NT * (q0 + i));
+        for (int i = 0; i < QP; ++i) x1[i] = ld_pol(v1 + t + NT * (q0 + i), pol_in);
 #pragma unroll
         for (int i = 0; i < QP; ++i) {
           y[i].re = fma(w1, x1[i].re, y[i].re); y[i].im = fma(w1, x1[i].im, y[i].im);
@@ -330,9 +332,12 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
         const cplx ep = ldcs(P.aux + gi);
         const cplx y0 = ldcs(P.y0 + gi);
         const cplx y1 = Tt[NT * (q0 + j)];
-        const double sc = P.atol + P.rtol * fmax(hypot(y0.re, y0.im), hypot(y1.re, y1.im));
-        const double er = fma(P.werr, acc[j].re, ep.re) / sc, ei = fma(P.werr, acc[j].im, ep.im) / sc;
-        err_acc += er * er + ei * ei;
+        // |err / (atol + rtol max(|y0|, |y1|))|^2 with one square root and one division (amplitudes are <= 1:
+        // the squares neither overflow nor matter when they underflow)
+        const double m2 = fmax(fma(y0.re, y0.re, y0.im * y0.im), fma(y1.re, y1.re, y1.im * y1.im));
+        const double sc = fma(P.rtol, sqrt(m2), P.atol);
+        const double er = fma(P.werr, acc[j].re, ep.re), ei = fma(P.werr, acc[j].im, ep.im);
+        err_acc += fma(er, er, ei * ei) / (sc * sc);
       }
     }
   }
@@ -694,9 +699,10 @@ __device__ __forceinline__ void pipe_g_item(const StreamParams& P, const StreamC
         const size_t gi = g0 + (size_t)i * stride;
         const cplx ep = ldcs(P.aux + gi);
         const cplx y0 = ldcs(P.y0 + gi);
-        const double sc = P.atol + P.rtol * fmax(hypot(y0.re, y0.im), hypot(y[i].re, y[i].im));
-        const double er = fma(P.werr, acc[ii].re, ep.re) / sc, ei = fma(P.werr, acc[ii].im, ep.im) / sc;
-        err_acc += er * er + ei * ei;
+        const double m2 = fmax(fma(y0.re, y0.re, y0.im * y0.im), fma(y[i].re, y[i].re, y[i].im * y[i].im));
+        const double sc = fma(P.rtol, sqrt(m2), P.atol);
+        const double er = fma(P.werr, acc[ii].re, ep.re), ei = fma(P.werr, acc[ii].im, ep.im);
+        err_acc += fma(er, er, ei * ei) / (sc * sc);
       }
     }
   }
@@ -989,6 +995,8 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
     AgCtl ctl{ag_sync_buffer(s), chunk_log2, (unsigned)n_chunks, std::max(1u, lag), mix, pipe ? (unsigned)(kPipeCons / 32) : 1u, dbg};
     StreamParams Af = A;
     Af.pol_st = hints & 1 ? 1 : 0;                   // keep Ymat and the partial result in L2 for the group tiles
+    static const unsigned plain_in = env_unsigned("PD_STREAM_PLAIN_IN", 0);
+    Af.pol_in = (A.ymat == nullptr && A.n_in == 1) ? (int)plain_in : 2;
     PD_CUDA_CHECK(cudaMemsetAsync(ctl.sync, 0, sizeof(unsigned) * (n_chunks + 1), s));
     const unsigned ag_grid = (unsigned)(2 * (n_tiles + ((size_t)ctl.lag << chunk_log2)));
     const bool aux = A.aux != nullptr;
@@ -1014,7 +1022,9 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
     first = 1;
   } else {
     const bool aux = A.aux != nullptr;
-    auto go = [&](auto* f) { f<<<grid, NT, TILE * 16, s>>>(A, cf); };
+    StreamParams An = A;
+    An.pol_in = 2;
+    auto go = [&](auto* f) { f<<<grid, NT, TILE * 16, s>>>(An, cf); };
     if (uni) { if (aux) go(k_stream_a<true, true>); else go(k_stream_a<true, false>); }
     else { if (aux) go(k_stream_a<false, true>); else go(k_stream_a<false, false>); }
     n = 1;
