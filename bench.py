@@ -17,8 +17,8 @@ gradient pass.  Metric = DP5 evolution steps per second over forward+gradient.
                (1 GiB vectors; stream family: A tiles + first bit group as one L2-blocked dataflow launch,
                last bit group as a second launch) with a full-register global drive, timed with CUDA
                events inside the C ABI on the launching stream; algorithmic bytes 576 B x 2^N per step,
-               40 B x 2^N per H.psi (``roofline_hpsi``), SURVEY.md 8d.  ``roofline_n23`` is the tiled
-               family at N = 23; ``fwd_grad_n26`` is forward + adjoint gradient wall time per DP5 step at
+               40 B x 2^N per H.psi (``roofline_hpsi``), SURVEY.md 8d.  ``roofline_n23`` is the same
+               family at N = 23 (128 MiB vectors); ``fwd_grad_n26`` is forward + adjoint gradient wall time per DP5 step at
                N = 26 (BASELINE metric "fwd+grad wall time at N qubits") with ``roofline_adjoint``.
 * ``c3_batch``: BASELINE configs[2] -- 4096 pulse-parameter sets of the 2-atom gate workload, forward +
                gradient through ``ops.evolve_units``, sets dealt over the ranks (strong scaling, no
@@ -428,8 +428,8 @@ def run_b200(args):
             s_amp = 2 ** nr
             ach = 576.0 * s_amp / (ms_step * 1e-3) / 1e9
             ach_h = 40.0 * s_amp / (ms_h * 1e-3) / 1e9
-            family = ("stream (one bit-group of H per launch, >= 256 B pieces)" if nr in (19, 20) or nr >= 24 else
-                      "tiled (smem + TMEM, alternating tile types, fused DP5 step)" if 18 <= nr <= 23 else "gather")
+            family = ("stream (one bit-group of H per tile type, >= 256 B pieces, A + first group as one "
+                      "L2-blocked dataflow launch)" if nr >= 19 else "gather")
             r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                  "traffic": measured_traffic(f"dp5_step_n{nr}"), "peak_source": peak_src,
                  "kernel": "DP5 step kernel sequence (6 generator applications + stage combines + error norm)",

@@ -6,9 +6,10 @@
 //     working set is cache resident, and the Lindblad path.
 //   * "small" (small_ket*.cu): kets of N <= 14 -- the whole adaptive evolution / adjoint sweep as one
 //     cooperative kernel with register-resident lanes and a flag-in-data exchange through L2.
-//   * "tiled" (tiled_ket.cu): kets of N = 18, 21..23 -- two tile types, fused finalise/start launches.
-//   * "stream" (stream_ket.cu): kets of N = 19, 20 and N >= 24 -- one bit-group of H per launch, >= 256 B
-//     pieces; its tiled correlation kernels also serve the adjoint sweep of the tiled family.
+//   * "tiled" (tiled_ket.cu): kets of N = 18..23 on request (path 2) -- two tile types, fused finalise/start
+//     launches; the default until the stream family overtook it in round 2.
+//   * "stream" (stream_ket.cu): kets of N >= 19 -- one bit-group of H per tile type, >= 256 B pieces, A tiles +
+//     first group as one L2-blocked dataflow launch; its tiled correlation kernels serve the adjoint sweep.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -107,7 +108,8 @@ int launch_tiled_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cplx
                           const double* ew, double dt, double atol, double rtol, cplx* tmp_a,
                           cplx* tmp_b, double* err_partial, double* err_out, cudaStream_t s);
 size_t tiled_err_partial_count(const Geometry& g);
-constexpr int kAutoTiledMinQubits = 18;   // below this the whole working set is L2 resident
+constexpr int kAutoTiledMinQubits = 19;   // up to N = 18 the working set is L2 resident and the gather kernels
+                                          // win (N = 18: 0.119 ms per DP5 step against 0.135 stream, 0.159 tiled)
 // stream family (stream_ket.cu): one bit-group of H per launch, >= 256 B pieces, any N >= 16
 bool stream_ket_supported(const Geometry& g);
 int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, const cplx* const* ins,
@@ -286,9 +288,10 @@ class CudaBackend {
     }
     return n + launch_apply_ket(g, out, src, so, st(s));
   }
-  // Automatic family for large kets, from the measured DP5 step times (profiles/r01_stream_n26.md):
-  // N = 18 and 21..23 tiled, N = 19, 20 and >= 24 stream.  path 2 / 4 force one of them.
-  static bool stream_preferred(int nq) { return nq == 19 || nq == 20 || nq >= 24; }
+  // Automatic family for large kets, from the measured DP5 step times: since round 2 the stream family wins
+  // at every N >= 19 (N = 21 / 22 / 23: 0.554 / 0.927 / 1.667 ms per step against 0.587 / 1.090 / 2.080 ms
+  // tiled; profiles/r02_stream_n26.md).  path 2 / 4 force one of them.
+  static bool stream_preferred(int nq) { return nq >= kAutoTiledMinQubits; }
   bool use_tiled(const Geometry& g) const {
     if (path == 1 || path == 4 || !tiled_ket_supported(g)) return false;
     if (path == 2) return true;
