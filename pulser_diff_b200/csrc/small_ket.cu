@@ -56,13 +56,15 @@ static bool small_shape(size_t L, int batch, int& nC) {
   (void)batch;
   // a unit that spans several CTAs needs them all co-resident (cooperative launch): two CTAs of
   // 128 threads fit an SM with this kernel's registers and shared memory
-  static int max_coresident = 0;
-  if (max_coresident == 0) {
-    int dev = 0, sms = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      sms = 0;
-    max_coresident = std::min(SK_MAXC, 2 * sms);
+  static int per_device[64] = {};          // a process may drive several devices
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  if (per_device[dev] == 0) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 0;
+    per_device[dev] = std::max(1, std::min(SK_MAXC, 2 * sms));
   }
+  const int max_coresident = per_device[dev];
   size_t c = (2 * L + SK_T - 1) / SK_T;
   if (c > 1 && c > (size_t)max_coresident) return false;
   nC = (int)c;

@@ -31,6 +31,8 @@ from ._cabi import PD_DENSITY, PD_KET, Options, Plan
 
 _program_ids = itertools.count()
 _PLAN_CACHE: dict[tuple, Plan] = {}
+_PLAN_CACHE_MAX_PLANS = 16                 # small registers: cheap to keep
+_PLAN_CACHE_MAX_AMPLITUDES = 1 << 27       # plans kept beside a new one hold at most this many amplitudes in total
 _UNIT_PROGRAMS: dict[tuple, "Program"] = {}
 
 
@@ -60,10 +62,18 @@ def get_plan(n_qubits: int, batch: int, kind: int, device: torch.device) -> Plan
     if device.type == "cuda" and device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
     key = (n_qubits, batch, kind, str(device), _cabi._lib_path or _cabi.DEFAULT_LIBRARY)
-    plan = _PLAN_CACHE.get(key)
+    plan = _PLAN_CACHE.pop(key, None)
     if plan is None:
+        # bounded, least recently used first out: a plan pins its whole workspace (tens of GiB at N >= 26),
+        # so sweeping N or the batch size must not pile plans up until the device is full
+        budget = _PLAN_CACHE_MAX_AMPLITUDES
+        kept = 0
+        for k in reversed(list(_PLAN_CACHE)):
+            kept += _PLAN_CACHE[k].dim * _PLAN_CACHE[k].batch
+            if kept > budget or len(_PLAN_CACHE) >= _PLAN_CACHE_MAX_PLANS:
+                del _PLAN_CACHE[k]
         plan = Plan(n_qubits, batch, kind, device)
-        _PLAN_CACHE[key] = plan
+    _PLAN_CACHE[key] = plan          # most recently used last
     return plan
 
 
