@@ -128,7 +128,8 @@ __device__ __forceinline__ void sk_eval_one(const SkProg& P, double t, SkCoef* c
 }
 // times[i] for i in [0, 6): coefficient set i.  Two __syncthreads inside.
 __device__ __forceinline__ void sk_eval_stages(const SkProg& P, const double* times, SkCoef* c, int tid) {
-  for (int w = tid; w < 6 * P.nq; w += SK_T) sk_eval_one(P, times[w / P.nq], &c[w / P.nq], w % P.nq);
+  const int nthr = blockDim.x;
+  for (int w = tid; w < 6 * P.nq; w += nthr) sk_eval_one(P, times[w / P.nq], &c[w / P.nq], w % P.nq);
   __syncthreads();
   if (tid < 6) {
     int u = 1;
@@ -142,18 +143,23 @@ __device__ __forceinline__ void sk_eval_stages(const SkProg& P, const double* ti
 // Copies the pulse tables into shared memory when they fit (the per-stage interpolation then costs
 // shared-memory latency instead of dependent L2 round trips) and repoints the program at them.
 constexpr int SK_TABLE_BYTES = 32 * 1024;
+// The table space is the launch's dynamic shared memory (sized by the host from the same formula, 0 when the
+// tables do not fit): a unit of a batch then costs a few KiB of shared memory instead of a fixed 32 KiB.
 __device__ __forceinline__ void sk_cache_tables(SkProg& P, unsigned char* tab_smem, int tid) {
   const size_t ndv = (size_t)P.n_det * P.n_samples, nav = (size_t)P.n_amp * P.n_samples * 2;
   const size_t need = (ndv + nav + P.n_det + P.n_amp) * 8;
-  if (need > SK_TABLE_BYTES) return;    // uniform
+  unsigned cap;
+  asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(cap));
+  if (need > SK_TABLE_BYTES || need > cap) return;    // uniform
+  const int SK_TN = blockDim.x;
   double* dv = reinterpret_cast<double*>(tab_smem);
   double* av = dv + ndv;
   unsigned long long* dm = reinterpret_cast<unsigned long long*>(av + nav);
   unsigned long long* am = dm + P.n_det;
-  for (size_t i = tid; i < ndv; i += SK_T) dv[i] = P.det_values[i];
-  for (size_t i = tid; i < nav; i += SK_T) av[i] = P.amp_values[i];
-  for (int i = tid; i < P.n_det; i += SK_T) dm[i] = P.det_masks[i];
-  for (int i = tid; i < P.n_amp; i += SK_T) am[i] = P.amp_masks[i];
+  for (size_t i = tid; i < ndv; i += SK_TN) dv[i] = P.det_values[i];
+  for (size_t i = tid; i < nav; i += SK_TN) av[i] = P.amp_values[i];
+  for (int i = tid; i < P.n_det; i += SK_TN) dm[i] = P.det_masks[i];
+  for (int i = tid; i < P.n_amp; i += SK_TN) am[i] = P.amp_masks[i];
   __syncthreads();
   P.det_values = dv; P.amp_values = av; P.det_masks = dm; P.amp_masks = am;
 }
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
   __shared__ double s_err[SK_MAXB];
   __shared__ double s_times[6];
   __shared__ double s_fac;
-  __shared__ __align__(16) unsigned char s_tab[SK_TABLE_BYTES];
+  extern __shared__ __align__(16) unsigned char s_tab[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int part = tid & 1;
   const unsigned cta = blockIdx.x;
@@ -363,7 +369,7 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
   double* const tapeY = P.tapeY ? P.tapeY + unit * (size_t)P.tape_cap * 6 * L2 : nullptr;
   double* const tapeK = P.tapeK ? P.tapeK + unit * (size_t)P.tape_cap * 6 * L2 : nullptr;
 
-  const size_t r = (size_t)cta * SK_T + tid;
+  const size_t r = (size_t)cta * blockDim.x + tid;
   const bool on = r < L2;
   const size_t rr = on ? r : (size_t)part;
   const size_t e = rr >> 1;
@@ -398,12 +404,12 @@ __global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ 
     __syncthreads();
     if (tid < P.batch) {
       double tot = 0.0;
-      for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w][tid];
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w][tid];
       ll_store(red + ((size_t)rpar * P.nC + cta) * P.batch + tid, tot, rseq);
     }
     // every CTA collects all partial sums: warp b (strided) polls the lines of column b, lane j
     // those of CTAs j, j+32, ... and the warp sums them in a fixed order
-    for (int b = warp; b < P.batch; b += SK_T / 32) {
+    for (int b = warp; b < P.batch; b += (int)(blockDim.x >> 5)) {
       double tot = 0.0;
       for (int c = lane; c < P.nC; c += 32) {
         const uint4* src = red + ((size_t)rpar * P.nC + c) * P.batch + b;
@@ -606,7 +612,7 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
   __shared__ double s_red[SK_T / 32][2 * SK_MAXTERMS + SK_MAXTERMS + 1];
   __shared__ unsigned long long s_dm[SK_MAXTERMS], s_am[SK_MAXTERMS];
   __shared__ double s_times[6];
-  __shared__ __align__(16) unsigned char s_tab[SK_TABLE_BYTES];
+  extern __shared__ __align__(16) unsigned char s_tab[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int part = tid & 1;
   const unsigned cta = blockIdx.x;
@@ -628,7 +634,7 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
   uint4* const KB = P.KB + unit * 2 * L2;
   double* const slotpart = P.slotpart + unit * (size_t)P.max_steps * 6 * P.nC * nred;
 
-  const size_t r = (size_t)cta * SK_T + tid;
+  const size_t r = (size_t)cta * blockDim.x + tid;
   const bool on = r < L2;
   const size_t rr = on ? r : (size_t)part;
   const size_t e = rr >> 1;
@@ -724,10 +730,10 @@ __global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__
           hd = warp_sum_d(hd);
           if (lane == 0) s_red[warp][nred - 1] = hd;
           __syncthreads();
-          if (tid < nred) {
+          for (int q = tid; q < nred; q += (int)blockDim.x) {   // nred can exceed a 32-thread CTA
             double tot = 0.0;
-            for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w][tid];
-            slotpart[((size_t)gi * 6 + i) * P.nC * nred + (size_t)cta * nred + tid] = tot;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w][q];
+            slotpart[((size_t)gi * 6 + i) * P.nC * nred + (size_t)cta * nred + q] = tot;
           }
           __syncthreads();
         }
@@ -776,7 +782,7 @@ __global__ void __launch_bounds__(SK_T) k_small_lanczos(const __grid_constant__ 
   __shared__ double s_red[SK_T / 32];
   __shared__ double s_tot;
   __shared__ double s_times[6];
-  __shared__ __align__(16) unsigned char s_tab[SK_TABLE_BYTES];
+  extern __shared__ __align__(16) unsigned char s_tab[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int part = tid & 1;
   const unsigned cta = blockIdx.x;
@@ -784,7 +790,7 @@ __global__ void __launch_bounds__(SK_T) k_small_lanczos(const __grid_constant__ 
   const size_t dim = P.dim, L2 = 2 * P.dim;
   SkProg prog = P.prog;
   sk_cache_tables(prog, s_tab, tid);
-  const size_t r = (size_t)cta * SK_T + tid;
+  const size_t r = (size_t)cta * blockDim.x + tid;
   const bool on = r < L2;
   const size_t rr = on ? r : (size_t)part;
   const size_t e = rr >> 1;
@@ -808,7 +814,7 @@ __global__ void __launch_bounds__(SK_T) k_small_lanczos(const __grid_constant__ 
     __syncthreads();
     if (tid == 0) {
       double tot = 0.0;
-      for (int w = 0; w < SK_T / 32; ++w) tot += s_red[w];
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += s_red[w];
       ll_store(P.red + (size_t)rpar * P.nC + cta, tot, rseq);
     }
     if (warp == 0) {
@@ -959,14 +965,23 @@ inline void fill_tab(const Tableau& t, SkTab& o) {
 
 // A unit that spans several CTAs polls lines written by its other CTAs: cooperative launch (all
 // CTAs co-resident).  Units of one CTA never wait for another CTA: plain launch, any grid size.
+// `lanes` = real lanes of one unit (2 x amplitudes x batch columns).  A single-CTA unit gets a CTA of just
+// enough warps (a 2-qubit unit with four initial states is ONE warp: up to ~12 units per SM are then co-resident
+// instead of 3, which is what bounds a batch of thousands of small parameter sets) and only the shared memory
+// its tables need.
 template <class K, class PT>
-void launch_units(K kern, const PT& P, int nC, int n_units, cudaStream_t s) {
+void launch_units(K kern, const PT& P, int nC, int n_units, size_t lanes, cudaStream_t s) {
+  const size_t need = ((size_t)P.prog.n_det * P.prog.n_samples + (size_t)P.prog.n_amp * P.prog.n_samples * 2 +
+                       P.prog.n_det + P.prog.n_amp) * 8;
+  const unsigned dyn = need <= (size_t)SK_TABLE_BYTES ? (unsigned)((need + 15) & ~(size_t)15) : 0u;
   if (nC > 1) {
     if (n_units != 1) throw Error(PD_ERR_STATE, "small_ket: multi-unit launches need single-CTA units");
     void* args[1] = {const_cast<PT*>(&P)};
-    PD_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nC), dim3(SK_T), args, 0, s));
+    PD_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kern, dim3((unsigned)nC), dim3(SK_T), args, dyn, s));
   } else {
-    kern<<<dim3(1, (unsigned)n_units), SK_T, 0, s>>>(P);
+    const unsigned nthr = n_units > 1 ? (unsigned)std::min<size_t>(SK_T, std::max<size_t>(32, (lanes + 31) & ~(size_t)31))
+                                      : (unsigned)SK_T;
+    kern<<<dim3(1, (unsigned)n_units), nthr, dyn, s>>>(P);
     PD_CUDA_CHECK(cudaGetLastError());
   }
 }

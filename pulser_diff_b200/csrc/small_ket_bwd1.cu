@@ -3,9 +3,9 @@
 namespace pd {
 namespace sk {
 void launch_backward(int nq, const SkBwd& P, int nC, cudaStream_t st) {
-  if (nq <= 8) launch_units(k_small_backward<8>, P, nC, P.n_units, st);
-  else if (nq <= 12) launch_units(k_small_backward<12>, P, nC, P.n_units, st);
-  else launch_units(k_small_backward<16>, P, nC, P.n_units, st);
+  if (nq <= 8) launch_units(k_small_backward<8>, P, nC, P.n_units, 2 * P.L, st);
+  else if (nq <= 12) launch_units(k_small_backward<12>, P, nC, P.n_units, 2 * P.L, st);
+  else launch_units(k_small_backward<16>, P, nC, P.n_units, 2 * P.L, st);
 }
 }  // namespace sk
 }  // namespace pd
