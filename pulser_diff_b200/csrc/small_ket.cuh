@@ -339,8 +339,9 @@ struct SkFwd {
   size_t det_stride, amp_stride;   // doubles per unit in prog.det_values / prog.amp_values
 };
 
+// NQG = 4 serves batches of tiny registers (one warp per unit): capped at 128 registers so that 16 units fit an SM
 template <int NQG>
-__global__ void __launch_bounds__(SK_T) k_small_forward(const __grid_constant__ SkFwd P) {
+__global__ void __launch_bounds__(SK_T) __maxnreg__(NQG <= 4 ? 128 : 255) k_small_forward(const __grid_constant__ SkFwd P) {
   constexpr int NH = NQG / 2;
   __shared__ SkCoef coef[6];
   __shared__ double s_red[SK_T / 32][SK_MAXB];
@@ -606,7 +607,7 @@ struct SkBwd {
 };
 
 template <int NQG>
-__global__ void __launch_bounds__(SK_T) k_small_backward(const __grid_constant__ SkBwd P) {
+__global__ void __launch_bounds__(SK_T) __maxnreg__(NQG <= 4 ? 128 : 255) k_small_backward(const __grid_constant__ SkBwd P) {
   constexpr int NH = NQG / 2;
   __shared__ SkCoef coef[6];
   __shared__ double s_red[SK_T / 32][2 * SK_MAXTERMS + SK_MAXTERMS + 1];

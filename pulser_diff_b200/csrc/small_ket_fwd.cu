@@ -4,7 +4,8 @@
 namespace pd {
 namespace sk {
 void launch_forward(int nq, const SkFwd& P, int nC, cudaStream_t st) {
-  if (nq <= 8) launch_units(k_small_forward<8>, P, nC, P.n_units, 2 * P.L, st);
+  if (nq <= 4) launch_units(k_small_forward<4>, P, nC, P.n_units, 2 * P.L, st);
+  else if (nq <= 8) launch_units(k_small_forward<8>, P, nC, P.n_units, 2 * P.L, st);
   else if (nq <= 12) launch_units(k_small_forward<12>, P, nC, P.n_units, 2 * P.L, st);
   else launch_units(k_small_forward<16>, P, nC, P.n_units, 2 * P.L, st);
 }
