@@ -205,6 +205,25 @@ def fwd_grad_large(dev, n, n_steps, peak):
 C3 = dict(n=2, pulses=8, dur=131, rate=0.05, c6=865723.02, spacing=6.5, n_sets=4096)
 
 
+def c64_hpsi_check(dev, H, dv, av, n):
+    """max |H psi (complex64 library) - H psi (complex128 library)| / max |H psi| on one random vector."""
+    from pulser_diff_b200 import _cabi
+    outs = []
+    psi = torch.randn(1, 2 ** n, dtype=torch.complex128, device=dev)
+    psi /= psi.norm()
+    for cd in (torch.complex128, torch.complex64):
+        plan = _cabi.Plan(n, 1, _cabi.PD_KET, dev, cd)
+        cu = torch.zeros(n, n, dtype=torch.float64)
+        for i in range(n):
+            for j in range(i + 1, n):
+                cu[i, j] = C6 / (SPACING * (j - i)) ** 6
+        plan.set_interaction(cu)
+        plan.set_terms(H.dt, [(1 << n) - 1], dv, [(1 << n) - 1], av)
+        outs.append(plan.hpsi(0.3, psi.to(cd)).to(torch.complex128))
+        del plan
+    return float((outs[1] - outs[0]).abs().max() / outs[0].abs().max())
+
+
 def c3_tables(params, idx):
     """params (U, 3, pulses) on any device -> the reference's coefficient arrays 0.5*amp*exp(-i phase) and
     -0.5*det, sub-sampled (hamiltonian.py:83-91, 419-423), as (U, 1, n_samples)."""
@@ -407,12 +426,16 @@ def run_b200(args):
     lib_h2d, lib_d2h = _cabi.transfer_counters()
 
     # ---- roofline: the HBM-bound regime, N = roofline_n, CUDA events inside the C ABI ----
-    roof = roof_h = roof23 = None
+    roof = roof_h = roof23 = roof_c64 = None
     peak, peak_src = measured_peak()
     if rank == 0 and args.roofline_n > 0:
-        def measure(nr):
+        def measure(nr, cdtype=torch.complex128):
+            # algorithmic bytes per amplitude: DP5 step = (26 reads + 7 writes) amplitudes + 6
+            # diagonal doubles; H.psi = read + write + one diagonal double
+            ab = 16.0 if cdtype == torch.complex128 else 8.0
+            b_step, b_h = 33.0 * ab + 48.0, 2.0 * ab + 8.0
             ops.clear_plan_cache()
-            big = _cabi.Plan(nr, 1, _cabi.PD_KET, dev)
+            big = _cabi.Plan(nr, 1, _cabi.PD_KET, dev, cdtype)
             cu = torch.zeros(nr, nr, dtype=torch.float64)
             for i in range(nr):
                 for j in range(i + 1, nr):
@@ -420,30 +443,40 @@ def run_b200(args):
             big.set_interaction(cu)
             full_mask = [(1 << nr) - 1]           # the global channel drives EVERY atom of the big register
             big.set_terms(H.dt, full_mask, dv, full_mask, av)
-            y = torch.zeros(1, 2 ** nr, dtype=torch.complex128, device=dev)
+            y = torch.zeros(1, 2 ** nr, dtype=cdtype, device=dev)
             y[0, -1] = 1.0
             ms_step = big.bench_dp5_steps(0.3, 1e-3, args.roofline_steps, y)
-            psi = torch.randn(1, 2 ** nr, dtype=torch.float64, device=dev).to(torch.complex128)
+            psi = torch.randn(1, 2 ** nr, dtype=torch.float64, device=dev).to(cdtype)
             ms_h = big.bench_hpsi(0.3, psi, max(4, args.roofline_steps * 3))
             s_amp = 2 ** nr
-            ach = 576.0 * s_amp / (ms_step * 1e-3) / 1e9
-            ach_h = 40.0 * s_amp / (ms_h * 1e-3) / 1e9
+            ach = b_step * s_amp / (ms_step * 1e-3) / 1e9
+            ach_h = b_h * s_amp / (ms_h * 1e-3) / 1e9
             family = ("stream (one bit-group of H per tile type, >= 256 B pieces, A + first group as one "
                       "L2-blocked dataflow launch)" if nr >= 19 else "gather")
             r = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                 "traffic": measured_traffic(f"dp5_step_n{nr}"), "peak_source": peak_src,
+                 "traffic": measured_traffic(f"dp5_step_n{nr}") if cdtype == torch.complex128 else None,
+                 "peak_source": peak_src, "state_dtype": str(cdtype).replace("torch.", ""),
                  "kernel": "DP5 step kernel sequence (6 generator applications + stage combines + error norm)",
                  "kernel_family": family, "workload": f"chain_n{nr}_dp5_step", "ms_per_launch": ms_step,
-                 "algorithmic_bytes": 576.0 * s_amp, "steps_per_s": 1e3 / ms_step}
+                 "algorithmic_bytes": b_step * s_amp, "steps_per_s": 1e3 / ms_step}
             rh = {"bound": "hbm", "achieved": ach_h, "peak": peak, "unit": "GB/s", "frac": ach_h / peak,
                   "traffic": None, "kernel": "H(t) psi", "workload": f"chain_n{nr}_hpsi",
-                  "ms_per_launch": ms_h, "algorithmic_bytes": 40.0 * s_amp}
+                  "ms_per_launch": ms_h, "algorithmic_bytes": b_h * s_amp}
             del big, y, psi
             torch.cuda.empty_cache()
             return r, rh
         roof, roof_h = measure(args.roofline_n)
         if args.roofline_n != 23 and not args.skip_n23:
             roof23, _ = measure(23)
+        if not args.quick:
+            # north_star's optional complex64 tier, reported BESIDE the complex128 numbers (never instead of):
+            # same kernels compiled for complex64 state vectors (libpulser_diff_b200_c64.so), half the bytes per pass
+            try:
+                r64, r64h = measure(args.roofline_n, torch.complex64)
+                roof_c64 = {"dp5_step": r64, "hpsi": r64h, "speedup_vs_c128_step": roof["ms_per_launch"] / r64["ms_per_launch"],
+                            "hpsi_rel_diff_vs_c128_n22": c64_hpsi_check(dev, H, dv, av, 22)}
+            except Exception as exc:
+                roof_c64 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     clocks = sampler.summary()
     fwd_grad = c4 = None
     if rank == 0 and world == 1 and args.roofline_n > 0 and not args.quick:
@@ -517,7 +550,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": d2h, "ms_per_pass": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": roof, "roofline_hpsi": roof_h, "roofline_n23": roof23,
+            "roofline": roof, "roofline_hpsi": roof_h, "roofline_n23": roof23, "roofline_c64": roof_c64,
             "fwd_grad_n26": fwd_grad, "c3_batch": c3, "c4_lindblad": c4,
             "roofline_workload": {"bound": "latency", "achieved": 576.0 * s12 * total_steps / world / t_res / 1e9 * 2,
                                   "peak": peak, "unit": "GB/s",

@@ -29,7 +29,8 @@
  * All entry points: plain pointers and sizes, int status (0 = ok), message via
  * pd_last_error().  "dev" pointers are CUDA device pointers on the plan's device,
  * "host" pointers are ordinary host memory.  Complex numbers are interleaved
- * (re, im) doubles.  State vectors cross the ABI batch-major: [batch][2^nbits].
+ * (re, im) doubles (state amplitudes: floats in the complex64 build, see pd_amplitude_bytes).
+ * State vectors cross the ABI batch-major: [batch][2^nbits].
  * Work is queued on `stream` (a cudaStream_t passed as void*); calls that return
  * host-side results synchronise that stream before returning.
  */
@@ -247,6 +248,15 @@ int64_t pd_plan_launch_count(const pd_plan* p);
 int pd_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int32_t reset);
 /* 1 if this library was built with the CUDA backend, 0 for the host stand-in used by tests */
 int pd_is_cuda(void);
+/* Bytes per state-vector amplitude of THIS library build: 16 (complex128, libpulser_diff_b200.so -- the
+ * precision the reference computes in, backend.py:271, 280) or 8 (complex64, libpulser_diff_b200_c64.so --
+ * north_star's optional 1e-5 tier: the same sources compiled with -DPD_C64, same symbols).  In the complex64
+ * build every "dev" pointer to amplitudes (states, cotangents, stage vectors, peer slices) holds interleaved
+ * (re, im) floats; everything else -- coefficient tables, times, tolerances, gradients w.r.t. samples /
+ * pair_u / tsave, expectation values, error norms -- stays double in both builds.  The complex64 build
+ * carries the bandwidth-bound kernel families (gather: any ket / density shape; stream: kets of N >= 19;
+ * sharded accumulate); registers of N <= 14 are served by the complex128 library (the Python host casts). */
+int pd_amplitude_bytes(void);
 
 #ifdef __cplusplus
 }

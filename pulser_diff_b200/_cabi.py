@@ -19,6 +19,9 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIBRARY = os.path.join(_HERE, "libpulser_diff_b200.so")
+# complex64 build of the same sources and symbols (north_star's optional 1e-5 tier): state vectors are
+# complex64 in device memory, the bandwidth-bound kernel families only (include/pulser_diff_b200.h)
+DEFAULT_LIBRARY_C64 = os.path.join(_HERE, "libpulser_diff_b200_c64.so")
 
 PD_KET, PD_DENSITY = 0, 1
 SOLVER_DP5_SE, SOLVER_KRYLOV_SE, SOLVER_DP5_ME = 0, 1, 2
@@ -49,11 +52,11 @@ EXPORTS = (
     "pd_evolve_forward", "pd_evolve_backward", "pd_tape_n_records", "pd_tape_records",
     "pd_evolve_forward_units", "pd_evolve_backward_units", "pd_tape_unit_steps",
     "pd_tape_destroy", "pd_expect_diag", "pd_sharded_accumulate", "pd_sharded_accumulate_range", "pd_lincomb", "pd_dp5_error_sumsq", "pd_bench_hpsi", "pd_bench_dp5_steps",
-    "pd_plan_launch_count", "pd_transfer_counters", "pd_is_cuda",
+    "pd_plan_launch_count", "pd_transfer_counters", "pd_is_cuda", "pd_amplitude_bytes",
 )
 
-_lib: Optional[C.CDLL] = None
-_lib_path: Optional[str] = None
+_libs: dict = {}                       # complex64? -> loaded library
+_lib_paths: dict = {False: None, True: None}
 
 
 def _declare(lib: C.CDLL) -> None:
@@ -62,6 +65,7 @@ def _declare(lib: C.CDLL) -> None:
     lib.pd_abi_version.restype = C.c_int
     lib.pd_last_error.restype = C.c_char_p
     lib.pd_is_cuda.restype = C.c_int
+    lib.pd_amplitude_bytes.restype = C.c_int
     lib.pd_options_default.argtypes = [C.POINTER(pd_options)]
     lib.pd_options_default.restype = None
     lib.pd_plan_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
@@ -105,16 +109,19 @@ def transfer_counters(reset: bool = False) -> tuple[int, int]:
     return int(a.value), int(b.value)
 
 
-def use_library(path: Optional[str]) -> None:
-    """Bind an explicit library (tests only) or reset to the default with ``None``."""
-    global _lib, _lib_path
-    _lib, _lib_path = None, path
+def use_library(path: Optional[str], path_c64: Optional[str] = None) -> None:
+    """Bind explicit libraries (tests only) or reset to the defaults with ``None``."""
+    _libs.clear()
+    _lib_paths[False], _lib_paths[True] = path, path_c64
 
 
-def lib() -> C.CDLL:
-    global _lib, _lib_path
-    if _lib is None:
-        path = _lib_path or DEFAULT_LIBRARY
+def lib(torch_complex64: bool = False) -> C.CDLL:
+    """The complex128 library (default) or the complex64 build of the same ABI."""
+    key = bool(torch_complex64)
+    if key not in _libs:
+        path = _lib_paths[key] or (DEFAULT_LIBRARY_C64 if key else DEFAULT_LIBRARY)
+        if key and _lib_paths[False] and not _lib_paths[True]:
+            raise RuntimeError("an explicit complex128 library is bound without its complex64 counterpart")
         if not os.path.exists(path):
             raise RuntimeError(
                 f"pulser_diff_b200: CUDA library not found at {path}. Build it with "
@@ -124,18 +131,21 @@ def lib() -> C.CDLL:
         _declare(handle)
         if handle.pd_abi_version() != 1:
             raise RuntimeError("pulser_diff_b200: ABI version mismatch")
-        _lib, _lib_path = handle, path
-    return _lib
+        if handle.pd_amplitude_bytes() != (8 if key else 16):
+            raise RuntimeError(f"pulser_diff_b200: {path} is not the "
+                               f"{'complex64' if key else 'complex128'} build")
+        _libs[key] = handle
+    return _libs[key]
 
 
 def is_cuda_library() -> bool:
     return bool(lib().pd_is_cuda())
 
 
-def _check(status: int) -> None:
+def _check(status: int, handle: Optional[C.CDLL] = None) -> None:
     if status == 0:
         return
-    msg = lib().pd_last_error().decode()
+    msg = (handle or lib()).pd_last_error().decode()
     if status == _ERR_INVALID:
         raise ValueError(msg)
     raise RuntimeError(msg)
@@ -182,6 +192,8 @@ class Options:
     use_sparse: bool = False          # accepted for API parity; the path is matrix free
     replay: Optional[Sequence] = None  # accepted steps [(dt, clipped), ...]: shared-step protocol
     path: int = 0                     # 0 auto, 1 gather, 2 tiled, 3 small-register, 4 stream kernels
+    dtype: str = "complex128"         # "complex64": north_star's optional 1e-5 tier (state vectors in complex64;
+                                      # the reference itself is complex128 only, backend.py:271, 280)
 
     @classmethod
     def from_dict(cls, d: Optional[dict]) -> "Options":
@@ -189,30 +201,39 @@ class Options:
         unknown = set(d) - set(cls.__dataclass_fields__)
         if unknown:
             raise TypeError(f"unknown solver option(s): {sorted(unknown)}")
+        if "dtype" in d:
+            d["dtype"] = str(d["dtype"]).replace("torch.", "")
+            if d["dtype"] not in ("complex128", "complex64"):
+                raise ValueError("dtype must be complex128 or complex64")
         return cls(**d)
+
+    @property
+    def state_dtype(self) -> torch.dtype:
+        return torch.complex64 if self.dtype == "complex64" else torch.complex128
 
 
 class Tape:
     """Owner of a ``pd_tape*`` (step log of one forward evolution)."""
 
-    def __init__(self, ptr: int) -> None:
+    def __init__(self, ptr: int, handle: Optional[C.CDLL] = None) -> None:
         self._ptr = C.c_void_p(ptr)
+        self._lib = handle or lib()
 
     @property
     def ptr(self) -> C.c_void_p:
         return self._ptr
 
     def records(self) -> list[dict]:
-        n = lib().pd_tape_n_records(self._ptr)
+        n = self._lib.pd_tape_n_records(self._ptr)
         buf = (pd_step_record * max(n, 1))()
-        _check(lib().pd_tape_records(self._ptr, buf, n))
+        _check(self._lib.pd_tape_records(self._ptr, buf, n), self._lib)
         return [dict(t=r.t, dt=r.dt, error=r.error, accepted=bool(r.accepted),
                      clipped=bool(r.clipped), interval=r.interval) for r in buf[:n]]
 
     def __del__(self) -> None:
         try:
             if self._ptr:
-                lib().pd_tape_destroy(self._ptr)
+                self._lib.pd_tape_destroy(self._ptr)
                 self._ptr = C.c_void_p(0)
         except Exception:
             pass
@@ -221,9 +242,14 @@ class Tape:
 class Plan:
     """Owner of a ``pd_plan*``: one register geometry + workspace on one device."""
 
-    def __init__(self, n_qubits: int, batch: int, kind: int, device: torch.device) -> None:
+    def __init__(self, n_qubits: int, batch: int, kind: int, device: torch.device,
+                 dtype: torch.dtype = torch.complex128) -> None:
         self.n_qubits, self.batch, self.kind = int(n_qubits), int(batch), int(kind)
         self.device = torch.device(device)
+        if dtype not in (torch.complex128, torch.complex64):
+            raise TypeError("state vectors are complex128 or complex64")
+        self.cdtype = dtype                       # dtype of every amplitude tensor of this plan
+        self._lib = lib(dtype == torch.complex64)
         if is_cuda_library() and self.device.type != "cuda":
             raise RuntimeError(
                 f"pulser_diff_b200 runs on CUDA devices only (asked for {self.device}); "
@@ -231,16 +257,19 @@ class Plan:
         ordinal = self.device.index if self.device.index is not None else (
             torch.cuda.current_device() if self.device.type == "cuda" else 0)
         p = C.c_void_p()
-        _check(lib().pd_plan_create(C.byref(p), self.n_qubits, self.batch, self.kind, ordinal))
+        self._ck(self._lib.pd_plan_create(C.byref(p), self.n_qubits, self.batch, self.kind, ordinal))
         self._ptr = p
         self.dim = 2 ** (self.n_qubits if kind == PD_KET else 2 * self.n_qubits)
         self.program_id = -1
         self.n_det = self.n_amp = self.n_samples = 0
 
+    def _ck(self, status: int) -> None:
+        _check(status, self._lib)
+
     def __del__(self) -> None:
         try:
             if self._ptr:
-                lib().pd_plan_destroy(self._ptr)
+                self._lib.pd_plan_destroy(self._ptr)
                 self._ptr = C.c_void_p(0)
         except Exception:
             pass
@@ -250,7 +279,7 @@ class Plan:
         u = pair_u.detach().to("cpu", torch.float64).contiguous()
         if tuple(u.shape) != (self.n_qubits, self.n_qubits):
             raise ValueError("pair_u must be (N, N)")
-        _check(lib().pd_plan_set_interaction(self._ptr, _hdbl(u), _stream(self.device)))
+        self._ck(self._lib.pd_plan_set_interaction(self._ptr, _hdbl(u), _stream(self.device)))
 
     def set_terms(self, dt: float, det_masks: Sequence[int], det_values: torch.Tensor,
                   amp_masks: Sequence[int], amp_values: torch.Tensor) -> None:
@@ -264,27 +293,27 @@ class Plan:
             raise ValueError("amp_values must be (n_amp, n_samples)")
         dm = (C.c_uint64 * max(n_det, 1))(*det_masks)
         am = (C.c_uint64 * max(n_amp, 1))(*amp_masks)
-        _check(lib().pd_plan_set_terms(self._ptr, n_samples, float(dt), n_det, dm, _hdbl(dv),
+        self._ck(self._lib.pd_plan_set_terms(self._ptr, n_samples, float(dt), n_det, dm, _hdbl(dv),
                                        n_amp, am, _hdbl(av)))
         self.n_det, self.n_amp, self.n_samples = n_det, n_amp, n_samples
 
     def set_collapse(self, ops: Optional[torch.Tensor]) -> None:
         if ops is None or ops.numel() == 0:
-            _check(lib().pd_plan_set_collapse(self._ptr, 0, C.POINTER(C.c_double)()))
+            self._ck(self._lib.pd_plan_set_collapse(self._ptr, 0, C.POINTER(C.c_double)()))
             return
         o = torch.view_as_real(ops.detach().to("cpu", torch.complex128).contiguous()).contiguous()
         if tuple(o.shape[1:]) != (2, 2, 2):
             raise ValueError("collapse operators must be (n_ops, 2, 2) complex")
-        _check(lib().pd_plan_set_collapse(self._ptr, int(o.shape[0]), _hdbl(o)))
+        self._ck(self._lib.pd_plan_set_collapse(self._ptr, int(o.shape[0]), _hdbl(o)))
 
     def set_path(self, path: int) -> None:
-        _check(lib().pd_plan_set_path(self._ptr, int(path)))
+        self._ck(self._lib.pd_plan_set_path(self._ptr, int(path)))
 
     # ---- applications ------------------------------------------------------------------------
     def _vec(self, t: torch.Tensor, what: str, lead: tuple = ()) -> torch.Tensor:
         _require_device(t, what)
-        if t.dtype != torch.complex128:
-            raise TypeError(f"{what} must be complex128")
+        if t.dtype != self.cdtype:
+            raise TypeError(f"{what} must be {str(self.cdtype).replace('torch.', '')}")
         want = lead + (self.batch, self.dim)
         if tuple(t.shape) != want:
             raise ValueError(f"{what} must have shape {want}, got {tuple(t.shape)}")
@@ -298,8 +327,8 @@ class Plan:
             raise ValueError("out must be a contiguous buffer distinct from psi")
         else:
             self._vec(out, "out")
-        fn = lib().pd_rhs if rhs else lib().pd_hpsi
-        _check(fn(self._ptr, _stream(self.device), float(t), _dptr(psi), _dptr(out)))
+        fn = self._lib.pd_rhs if rhs else self._lib.pd_hpsi
+        self._ck(fn(self._ptr, _stream(self.device), float(t), _dptr(psi), _dptr(out)))
         return out
 
     def rhs_vjp(self, t: float, state: torch.Tensor, cot: torch.Tensor, want_state: bool = True,
@@ -316,7 +345,7 @@ class Plan:
         g_amp = torch.zeros((self.n_amp, self.n_samples, 2), dtype=torch.float64) if want_amp and self.n_amp else None
         g_pair = torch.zeros((self.n_qubits, self.n_qubits), dtype=torch.float64) if want_pair and not defer_pair else None
         g_t = C.c_double(0.0)
-        _check(lib().pd_rhs_vjp(self._ptr, _stream(self.device), float(t), _dptr(state), _dptr(cot),
+        self._ck(self._lib.pd_rhs_vjp(self._ptr, _stream(self.device), float(t), _dptr(state), _dptr(cot),
                                 _dptr(g_state), _hdbl(g_det), _hdbl(g_amp), _hdbl(g_pair), C.byref(g_t),
                                 int(bool(defer_pair))))
         if g_amp is not None:
@@ -326,7 +355,7 @@ class Plan:
     def pair_gradient_flush(self) -> torch.Tensor:
         """dL/dU_ij of every ``rhs_vjp(..., defer_pair=True)`` since the last flush."""
         g_pair = torch.zeros((self.n_qubits, self.n_qubits), dtype=torch.float64)
-        _check(lib().pd_pair_gradient_flush(self._ptr, _stream(self.device), _hdbl(g_pair)))
+        self._ck(self._lib.pd_pair_gradient_flush(self._ptr, _stream(self.device), _hdbl(g_pair)))
         return g_pair
 
     def evolve_forward(self, solver: int, opt: Options, state0: torch.Tensor, tsave: torch.Tensor,
@@ -334,9 +363,9 @@ class Plan:
         state0 = self._vec(state0, "state0")
         ts = tsave.detach().to("cpu", torch.float64).contiguous()
         n_t = int(ts.numel())
-        states = torch.empty((n_t, self.batch, self.dim), dtype=torch.complex128, device=state0.device)
+        states = torch.empty((n_t, self.batch, self.dim), dtype=self.cdtype, device=state0.device)
         o = pd_options()
-        lib().pd_options_default(C.byref(o))
+        self._lib.pd_options_default(C.byref(o))
         for k in ("atol", "rtol", "max_steps", "safety_factor", "min_factor", "max_factor",
                   "max_krylov", "exp_tolerance", "norm_tolerance", "path"):
             setattr(o, k, getattr(opt, k))
@@ -348,15 +377,15 @@ class Plan:
             o.n_replay, o.replay_dt, o.replay_clipped = n, dts, cl
             keep = (dts, cl)
         tape_ptr = C.c_void_p()
-        _check(lib().pd_evolve_forward(self._ptr, _stream(self.device), int(solver), C.byref(o),
+        self._ck(self._lib.pd_evolve_forward(self._ptr, _stream(self.device), int(solver), C.byref(o),
                                        _dptr(state0), _hdbl(ts), n_t, _dptr(states),
                                        C.byref(tape_ptr) if want_tape else None))
         del keep
-        return states, (Tape(tape_ptr.value) if want_tape else None)
+        return states, (Tape(tape_ptr.value, self._lib) if want_tape else None)
 
     def _options_struct(self, opt: Options):
         o = pd_options()
-        lib().pd_options_default(C.byref(o))
+        self._lib.pd_options_default(C.byref(o))
         for k in ("atol", "rtol", "max_steps", "safety_factor", "min_factor", "max_factor",
                   "max_krylov", "exp_tolerance", "norm_tolerance", "path"):
             setattr(o, k, getattr(opt, k))
@@ -373,13 +402,13 @@ class Plan:
         ts = tsave.detach().to("cpu", torch.float64).contiguous()
         n_t = int(ts.numel())
         dv, av, dvp, avp = self._unit_tables(det_values, amp_values, n_units)
-        states = torch.empty((n_units, n_t, self.batch, self.dim), dtype=torch.complex128, device=state0.device)
+        states = torch.empty((n_units, n_t, self.batch, self.dim), dtype=self.cdtype, device=state0.device)
         o = self._options_struct(opt)
         tape_ptr = C.c_void_p()
-        _check(lib().pd_evolve_forward_units(self._ptr, _stream(self.device), C.byref(o), n_units,
+        self._ck(self._lib.pd_evolve_forward_units(self._ptr, _stream(self.device), C.byref(o), n_units,
                                              _dptr(state0), _hdbl(ts), n_t, dvp, avp,
                                              _dptr(states), C.byref(tape_ptr) if want_tape else None))
-        return states, (Tape(tape_ptr.value) if want_tape else None)
+        return states, (Tape(tape_ptr.value, self._lib) if want_tape else None)
 
     def _unit_tables(self, det_values: torch.Tensor, amp_values: torch.Tensor, n_units: int):
         """Per-unit coefficient tables as (tensors kept alive, double* det, double* amp).  Tables that
@@ -406,7 +435,7 @@ class Plan:
         where = dv.device
         g_det = torch.zeros((n_units, self.n_det, self.n_samples), dtype=torch.float64, device=where) if self.n_det else None
         g_amp = torch.zeros((n_units, self.n_amp, self.n_samples, 2), dtype=torch.float64, device=where) if self.n_amp else None
-        g_s0 = torch.empty((n_units, self.batch, self.dim), dtype=torch.complex128,
+        g_s0 = torch.empty((n_units, self.batch, self.dim), dtype=self.cdtype,
                            device=states.device) if want_state0 else None
         pd_ = C.POINTER(C.c_double)
 
@@ -415,7 +444,7 @@ class Plan:
                 return None
             return C.cast(C.c_void_p(x.data_ptr()), pd_) if x.is_cuda else _hdbl(x)
 
-        _check(lib().pd_evolve_backward_units(self._ptr, _stream(self.device), tape.ptr, _dptr(states),
+        self._ck(self._lib.pd_evolve_backward_units(self._ptr, _stream(self.device), tape.ptr, _dptr(states),
                                               _dptr(grad_states), dvp, avp, ptr(g_det), ptr(g_amp), _dptr(g_s0)))
         if g_amp is not None:
             g_amp = torch.view_as_complex(g_amp)
@@ -423,7 +452,7 @@ class Plan:
 
     def unit_steps(self, tape: Tape, unit: int) -> tuple[int, int]:
         att = C.c_int32(0)
-        acc = lib().pd_tape_unit_steps(tape.ptr, int(unit), C.byref(att))
+        acc = self._lib.pd_tape_unit_steps(tape.ptr, int(unit), C.byref(att))
         return int(acc), int(att.value)
 
     def evolve_backward(self, tape: Tape, states: torch.Tensor, grad_states: torch.Tensor,
@@ -436,8 +465,8 @@ class Plan:
         g_amp = torch.zeros((self.n_amp, self.n_samples, 2), dtype=torch.float64) if want_amp and self.n_amp else None
         g_pair = torch.zeros((self.n_qubits, self.n_qubits), dtype=torch.float64) if want_pair else None
         g_ts = torch.zeros(n_t, dtype=torch.float64) if want_tsave else None
-        g_s0 = torch.empty((self.batch, self.dim), dtype=torch.complex128, device=states.device) if want_state0 else None
-        _check(lib().pd_evolve_backward(self._ptr, _stream(self.device), tape.ptr, _dptr(states),
+        g_s0 = torch.empty((self.batch, self.dim), dtype=self.cdtype, device=states.device) if want_state0 else None
+        self._ck(self._lib.pd_evolve_backward(self._ptr, _stream(self.device), tape.ptr, _dptr(states),
                                         _dptr(grad_states), _hdbl(g_det), _hdbl(g_amp), _hdbl(g_pair),
                                         _hdbl(g_ts), _dptr(g_s0)))
         if g_amp is not None:
@@ -452,7 +481,7 @@ class Plan:
         if obs.numel() != 2 ** self.n_qubits:
             raise ValueError("diagonal observable must have 2**N entries")
         out = torch.zeros(n_t, 2, dtype=torch.float64)
-        _check(lib().pd_expect_diag(self._ptr, _stream(self.device), _dptr(states), n_t, _dptr(obs),
+        self._ck(self._lib.pd_expect_diag(self._ptr, _stream(self.device), _dptr(states), n_t, _dptr(obs),
                                     _hdbl(out)))
         return torch.view_as_complex(out)
 
@@ -466,7 +495,7 @@ class Plan:
             raise ValueError("1..8 inputs, one weight each")
         ptrs = (C.c_void_p * len(ins))(*[C.c_void_p(x.data_ptr()) for x in ins])
         ws = (C.c_double * len(ins))(*[float(x) for x in w])
-        _check(lib().pd_lincomb(self._ptr, _stream(self.device), _dptr(out), len(ins), ptrs, ws))
+        self._ck(self._lib.pd_lincomb(self._ptr, _stream(self.device), _dptr(out), len(ins), ptrs, ws))
         return out
 
     def dp5_error_sumsq(self, k: Sequence[Optional[torch.Tensor]], ew: Sequence[float], y0: torch.Tensor,
@@ -478,7 +507,7 @@ class Plan:
         ptrs = (C.c_void_p * 7)(*[C.c_void_p(0 if x is None else x.data_ptr()) for x in ks])
         ws = (C.c_double * 7)(*[float(x) for x in ew])
         out = torch.zeros(self.batch, dtype=torch.float64)
-        _check(lib().pd_dp5_error_sumsq(self._ptr, _stream(self.device), ptrs, ws,
+        self._ck(self._lib.pd_dp5_error_sumsq(self._ptr, _stream(self.device), ptrs, ws,
                                         _dptr(self._vec(y0, "y0")), _dptr(self._vec(y1, "y1")),
                                         float(atol), float(rtol), _hdbl(out)))
         return out
@@ -500,7 +529,7 @@ class Plan:
         cf = (C.c_double * max(2 * k, 1))()
         for i, c in enumerate(coefs):
             cf[2 * i], cf[2 * i + 1] = complex(c).real, complex(c).imag
-        _check(lib().pd_sharded_accumulate(self._ptr, _stream(self.device), _dptr(out), _dptr(psi),
+        self._ck(self._lib.pd_sharded_accumulate(self._ptr, _stream(self.device), _dptr(out), _dptr(psi),
                                            float(shift), k, ptrs, cf))
 
     def sharded_accumulate_range(self, out_ptr: int, psi_ptr: int, shift: float, peer_ptrs: Sequence[int],
@@ -514,7 +543,7 @@ class Plan:
         cf = (C.c_double * max(2 * k, 1))()
         for i, c in enumerate(coefs):
             cf[2 * i], cf[2 * i + 1] = complex(c).real, complex(c).imag
-        _check(lib().pd_sharded_accumulate_range(self._ptr, _stream(self.device), C.c_void_p(int(out_ptr)),
+        self._ck(self._lib.pd_sharded_accumulate_range(self._ptr, _stream(self.device), C.c_void_p(int(out_ptr)),
                                                  C.c_void_p(int(psi_ptr)), float(shift), k, ptrs, cf,
                                                  C.c_uint64(int(n_amp))))
 
@@ -523,7 +552,7 @@ class Plan:
         psi = self._vec(psi, "psi")
         out = torch.empty_like(psi)
         ms = C.c_double()
-        _check(lib().pd_bench_hpsi(self._ptr, _stream(self.device), float(t), int(reps), _dptr(psi),
+        self._ck(self._lib.pd_bench_hpsi(self._ptr, _stream(self.device), float(t), int(reps), _dptr(psi),
                                    _dptr(out), C.byref(ms)))
         return ms.value
 
@@ -531,10 +560,10 @@ class Plan:
         """Average device ms of one fixed-size DP5 step (updates ``y`` in place)."""
         y = self._vec(y, "y")
         ms = C.c_double()
-        _check(lib().pd_bench_dp5_steps(self._ptr, _stream(self.device), float(t0), float(dt),
+        self._ck(self._lib.pd_bench_dp5_steps(self._ptr, _stream(self.device), float(t0), float(dt),
                                         int(steps), _dptr(y), C.byref(ms)))
         return ms.value
 
     @property
     def launch_count(self) -> int:
-        return int(lib().pd_plan_launch_count(self._ptr))
+        return int(self._lib.pd_plan_launch_count(self._ptr))

@@ -239,7 +239,7 @@ class TorchEmulator:
         groups: dict = {}
         for d, reps in draws:
             groups.setdefault(tuple(d["bad_atoms"].tolist()), []).append((d, reps))
-        psi0 = self.initial_state.to(device=dev, dtype=C128).transpose(0, 1).contiguous()
+        psi0 = self.initial_state.to(device=dev, dtype=_cabi.Options.from_dict(options).state_dtype).transpose(0, 1).contiguous()
         for members in groups.values():
             d0 = members[0][0]
             if solver == SolverType.DP5_SE:

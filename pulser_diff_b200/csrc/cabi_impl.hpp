@@ -56,6 +56,7 @@ extern "C" {
 int pd_abi_version(void) { return PD_ABI_VERSION; }
 const char* pd_last_error(void) { return g_last_error.c_str(); }
 int pd_is_cuda(void) { return PD_BACKEND::is_cuda ? 1 : 0; }
+int pd_amplitude_bytes(void) { return (int)sizeof(pd::amp_t); }
 
 void pd_options_default(pd_options* o) {
   if (!o) return;
@@ -114,14 +115,14 @@ int pd_hpsi(pd_plan* p, void* stream, double t, const void* in_dev, void* out_de
   return guarded_on(p, [&] {
     need(p && in_dev && out_dev, "pd_hpsi: NULL argument");
     need(in_dev != out_dev, "pd_hpsi: in-place application is not supported");
-    p->eng.apply((pd::cplx*)out_dev, (const pd::cplx*)in_dev, t, 2, stream);
+    p->eng.apply((pd::amp_t*)out_dev, (const pd::amp_t*)in_dev, t, 2, stream);
   });
 }
 int pd_rhs(pd_plan* p, void* stream, double t, const void* in_dev, void* out_dev) {
   return guarded_on(p, [&] {
     need(p && in_dev && out_dev, "pd_rhs: NULL argument");
     need(in_dev != out_dev, "pd_rhs: in-place application is not supported");
-    p->eng.apply((pd::cplx*)out_dev, (const pd::cplx*)in_dev, t, 0, stream);
+    p->eng.apply((pd::amp_t*)out_dev, (const pd::amp_t*)in_dev, t, 0, stream);
   });
 }
 int pd_evolve_forward(pd_plan* p, void* stream, int32_t solver, const pd_options* opt,
@@ -135,8 +136,8 @@ int pd_evolve_forward(pd_plan* p, void* stream, int32_t solver, const pd_options
     p->eng.bk.path = o.path;
     pd_tape* tp = tape_out ? new pd_tape() : nullptr;
     try {
-      p->eng.forward(solver, o, (const pd::cplx*)state0_dev, tsave_host, n_t,
-                     (pd::cplx*)states_dev, tp ? &tp->tape : nullptr, stream);
+      p->eng.forward(solver, o, (const pd::amp_t*)state0_dev, tsave_host, n_t,
+                     (pd::amp_t*)states_dev, tp ? &tp->tape : nullptr, stream);
     } catch (...) {
       delete tp;
       throw;
@@ -149,9 +150,9 @@ int pd_evolve_backward(pd_plan* p, void* stream, pd_tape* tape, const void* stat
                        double* grad_pair_u_host, double* grad_tsave_host, void* grad_state0_dev) {
   return guarded_on(p, [&] {
     need(p && tape && states_dev, "pd_evolve_backward: NULL argument");
-    p->eng.backward(tape->tape, (const pd::cplx*)states_dev, (const pd::cplx*)grad_states_dev,
+    p->eng.backward(tape->tape, (const pd::amp_t*)states_dev, (const pd::amp_t*)grad_states_dev,
                     grad_det_host, grad_amp_host, grad_pair_u_host, grad_tsave_host,
-                    (pd::cplx*)grad_state0_dev, stream);
+                    (pd::amp_t*)grad_state0_dev, stream);
   });
 }
 int pd_evolve_forward_units(pd_plan* p, void* stream, const pd_options* opt, int32_t n_units,
@@ -167,8 +168,8 @@ int pd_evolve_forward_units(pd_plan* p, void* stream, const pd_options* opt, int
     p->eng.bk.path = o.path;
     pd_tape* tp = tape_out ? new pd_tape() : nullptr;
     try {
-      p->eng.forward_units(o, n_units, (const pd::cplx*)state0_dev, tsave_host, n_t, det_values_host,
-                           amp_values_host, (pd::cplx*)states_dev, tp ? &tp->units : nullptr, nullptr, stream);
+      p->eng.forward_units(o, n_units, (const pd::amp_t*)state0_dev, tsave_host, n_t, det_values_host,
+                           amp_values_host, (pd::amp_t*)states_dev, tp ? &tp->units : nullptr, nullptr, stream);
     } catch (...) {
       delete tp;
       throw;
@@ -182,10 +183,10 @@ int pd_evolve_backward_units(pd_plan* p, void* stream, pd_tape* tape, const void
                              void* grad_state0_dev) {
   return guarded_on(p, [&] {
     need(p && tape && states_dev && !tape->units.empty(), "pd_evolve_backward_units: bad argument");
-    p->eng.states_for_fallback_ = (const pd::cplx*)states_dev;
+    p->eng.states_for_fallback_ = (const pd::amp_t*)states_dev;
     try {
-      p->eng.backward_units(tape->units, det_values_host, amp_values_host, (const pd::cplx*)grad_states_dev,
-                            grad_det_host, grad_amp_host, (pd::cplx*)grad_state0_dev, stream);
+      p->eng.backward_units(tape->units, det_values_host, amp_values_host, (const pd::amp_t*)grad_states_dev,
+                            grad_det_host, grad_amp_host, (pd::amp_t*)grad_state0_dev, stream);
     } catch (...) {
       p->eng.states_for_fallback_ = nullptr;
       throw;
@@ -218,7 +219,7 @@ int pd_expect_diag(pd_plan* p, void* stream, const void* states_dev, int32_t n_t
                    const double* obs_dev, double* out_host) {
   return guarded_on(p, [&] {
     need(p && states_dev && obs_dev && out_host && n_t >= 1, "pd_expect_diag: bad argument");
-    p->eng.expect_diag((const pd::cplx*)states_dev, n_t, obs_dev, out_host, stream);
+    p->eng.expect_diag((const pd::amp_t*)states_dev, n_t, obs_dev, out_host, stream);
   });
 }
 int pd_rhs_vjp(pd_plan* p, void* stream, double t, const void* state_dev, const void* cot_dev,
@@ -226,8 +227,8 @@ int pd_rhs_vjp(pd_plan* p, void* stream, double t, const void* state_dev, const 
                double* grad_pair_host, double* grad_t_host, int32_t defer_pair) {
   return guarded_on(p, [&] {
     need(p && state_dev && cot_dev, "pd_rhs_vjp: NULL argument");
-    double tb = p->eng.rhs_vjp(t, (const pd::cplx*)state_dev, (const pd::cplx*)cot_dev,
-                               (pd::cplx*)grad_state_dev, grad_det_host, grad_amp_host,
+    double tb = p->eng.rhs_vjp(t, (const pd::amp_t*)state_dev, (const pd::amp_t*)cot_dev,
+                               (pd::amp_t*)grad_state_dev, grad_det_host, grad_amp_host,
                                grad_pair_host, defer_pair != 0, stream);
     if (grad_t_host) *grad_t_host = tb;
   });
@@ -243,7 +244,7 @@ int pd_lincomb(pd_plan* p, void* stream, void* out_dev, int32_t n_in, const void
   return guarded_on(p, [&] {
     need(p && out_dev && ins_dev && w_host && n_in >= 1 && n_in <= 8, "pd_lincomb: bad argument");
     for (int j = 0; j < n_in; ++j) need(ins_dev[j] != nullptr, "pd_lincomb: NULL input");
-    p->eng.lincomb((pd::cplx*)out_dev, n_in, (const pd::cplx* const*)ins_dev, w_host, stream);
+    p->eng.lincomb((pd::amp_t*)out_dev, n_in, (const pd::amp_t* const*)ins_dev, w_host, stream);
   });
 }
 int pd_dp5_error_sumsq(pd_plan* p, void* stream, const void* const* k_dev, const double* ew_host,
@@ -253,9 +254,9 @@ int pd_dp5_error_sumsq(pd_plan* p, void* stream, const void* const* k_dev, const
     need(p && k_dev && ew_host && y0_dev && y1_dev && sumsq_host, "pd_dp5_error_sumsq: NULL argument");
     for (int j = 0; j < 7; ++j)
       need(k_dev[j] != nullptr || ew_host[j] == 0.0, "pd_dp5_error_sumsq: NULL slope with a non-zero weight");
-    const pd::cplx* k[7];
-    for (int j = 0; j < 7; ++j) k[j] = k_dev[j] ? (const pd::cplx*)k_dev[j] : (const pd::cplx*)y0_dev;
-    p->eng.error_sumsq(k, ew_host, (const pd::cplx*)y0_dev, (const pd::cplx*)y1_dev, atol, rtol,
+    const pd::amp_t* k[7];
+    for (int j = 0; j < 7; ++j) k[j] = k_dev[j] ? (const pd::amp_t*)k_dev[j] : (const pd::amp_t*)y0_dev;
+    p->eng.error_sumsq(k, ew_host, (const pd::amp_t*)y0_dev, (const pd::amp_t*)y1_dev, atol, rtol,
                        sumsq_host, stream);
   });
 }
@@ -267,8 +268,8 @@ int pd_sharded_accumulate(pd_plan* p, void* stream, void* out_dev, const void* p
     need(n_peers == 0 || (peer_slices && coef_host), "pd_sharded_accumulate: NULL peer list");
     for (int k = 0; k < n_peers; ++k)
       need(peer_slices[k] != nullptr, "pd_sharded_accumulate: NULL peer slice");
-    p->eng.sharded_accumulate((pd::cplx*)out_dev, (const pd::cplx*)psi_dev, shift, n_peers,
-                              (const pd::cplx* const*)peer_slices, (const pd::cplx*)coef_host, stream);
+    p->eng.sharded_accumulate((pd::amp_t*)out_dev, (const pd::amp_t*)psi_dev, shift, n_peers,
+                              (const pd::amp_t* const*)peer_slices, (const pd::cplx*)coef_host, stream);
   });
 }
 int pd_sharded_accumulate_range(pd_plan* p, void* stream, void* out_dev, const void* psi_dev, double shift,
@@ -280,8 +281,8 @@ int pd_sharded_accumulate_range(pd_plan* p, void* stream, void* out_dev, const v
     need(n_peers == 0 || (peer_slices && coef_host), "pd_sharded_accumulate_range: NULL peer list");
     for (int k = 0; k < n_peers; ++k)
       need(peer_slices[k] != nullptr, "pd_sharded_accumulate_range: NULL peer slice");
-    p->eng.sharded_accumulate_n((pd::cplx*)out_dev, (const pd::cplx*)psi_dev, shift, n_peers,
-                                (const pd::cplx* const*)peer_slices, (const pd::cplx*)coef_host, (size_t)n_amp,
+    p->eng.sharded_accumulate_n((pd::amp_t*)out_dev, (const pd::amp_t*)psi_dev, shift, n_peers,
+                                (const pd::amp_t* const*)peer_slices, (const pd::cplx*)coef_host, (size_t)n_amp,
                                 stream);
   });
 }
@@ -289,14 +290,14 @@ int pd_bench_hpsi(pd_plan* p, void* stream, double t, int32_t reps, const void* 
                   void* out_dev, double* ms_per_apply_host) {
   return guarded_on(p, [&] {
     need(p && in_dev && out_dev && ms_per_apply_host && reps > 0, "pd_bench_hpsi: bad argument");
-    *ms_per_apply_host = p->eng.bench_apply((const pd::cplx*)in_dev, (pd::cplx*)out_dev, t, reps, stream);
+    *ms_per_apply_host = p->eng.bench_apply((const pd::amp_t*)in_dev, (pd::amp_t*)out_dev, t, reps, stream);
   });
 }
 int pd_bench_dp5_steps(pd_plan* p, void* stream, double t0, double dt, int32_t steps, void* y_dev,
                        double* ms_per_step_host) {
   return guarded_on(p, [&] {
     need(p && y_dev && ms_per_step_host && steps > 0, "pd_bench_dp5_steps: bad argument");
-    *ms_per_step_host = p->eng.bench_dp5((pd::cplx*)y_dev, t0, dt, steps, stream);
+    *ms_per_step_host = p->eng.bench_dp5((pd::amp_t*)y_dev, t0, dt, steps, stream);
   });
 }
 int pd_transfer_counters(int64_t* h2d_bytes, int64_t* d2h_bytes, int32_t reset) {

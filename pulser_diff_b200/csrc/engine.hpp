@@ -49,7 +49,7 @@ struct Tape {
 template <class BK>
 class Engine {
  public:
-  using vec = cplx*;
+  using vec = amp_t*;
   BK bk;
   Program prog;
   Geometry geo{};
@@ -118,7 +118,7 @@ class Engine {
 
   // ---- one generator application -------------------------------------------------------
   // out = G(t) (sum_j w_j in_j);  comb (nullable) receives the combined input.
-  void stage(vec out, vec comb, int n_in, const cplx* const* ins, const double* w, double t,
+  void stage(vec out, vec comb, int n_in, const amp_t* const* ins, const double* w, double t,
              int mode, void* stream) {
     if (prog.kind == PD_KET) {
       SiteOps so;
@@ -131,15 +131,15 @@ class Engine {
       launches += bk.stage_density(geo, out, comb, n_in, ins, w, so, scratch(stream), stream);
     }
   }
-  void apply(vec out, const cplx* in, double t, int mode, void* stream) {
-    const cplx* ins[1] = {in};
+  void apply(vec out, const amp_t* in, double t, int mode, void* stream) {
+    const amp_t* ins[1] = {in};
     double w[1] = {1.0};
     stage(out, nullptr, 1, ins, w, t, mode, stream);
   }
 
   // ---- forward ---------------------------------------------------------------------------
-  void forward(int solver, const pd_options& opt, const cplx* state0, const double* tsave, int n_t,
-               cplx* states, Tape* tape, void* stream) {
+  void forward(int solver, const pd_options& opt, const amp_t* state0, const double* tsave, int n_t,
+               amp_t* states, Tape* tape, void* stream) {
     if (n_t < 1) throw Error(PD_ERR_INVALID, "tsave must hold at least one time");
     for (int k = 1; k < n_t; ++k)
       if (tsave[k] < tsave[k - 1]) throw Error(PD_ERR_INVALID, "tsave must be sorted");
@@ -163,8 +163,8 @@ class Engine {
   }
 
   // ---- backward --------------------------------------------------------------------------
-  void backward(Tape& tape, const cplx* states, const cplx* gstates, double* g_det, double* g_amp,
-                double* g_pair, double* g_tsave, cplx* g_state0, void* stream) {
+  void backward(Tape& tape, const amp_t* states, const amp_t* gstates, double* g_det, double* g_amp,
+                double* g_pair, double* g_tsave, amp_t* g_state0, void* stream) {
     int n_t = (int)tape.tsave.size();
     int n_det = prog.n_det(), n_amp = prog.n_amp(), ns = prog.n_samples;
     if (g_det) std::fill(g_det, g_det + (size_t)n_det * ns, 0.0);
@@ -184,8 +184,8 @@ class Engine {
   // Same register, masks, time grid and options; unit u has its own coefficient tables
   // dv[u] ([n_det][n_samples]) / av[u] ([n_amp][n_samples] complex) and initial state.  One launch
   // evolves all units (one CTA per unit, small_ket*.cu); states: [U][n_t][batch][dim].
-  void forward_units(const pd_options& o, int n_units, const cplx* state0, const double* tsave, int n_t,
-                     const double* dv, const double* av, cplx* states, std::vector<Tape>* tapes,
+  void forward_units(const pd_options& o, int n_units, const amp_t* state0, const double* tsave, int n_t,
+                     const double* dv, const double* av, amp_t* states, std::vector<Tape>* tapes,
                      uint64_t* gen_out, void* stream) {
     if (n_t < 1) throw Error(PD_ERR_INVALID, "tsave must hold at least one time");
     for (int k = 1; k < n_t; ++k)
@@ -232,9 +232,9 @@ class Engine {
     }
   }
   // g_det: [U][n_det][n_samples], g_amp: [U][n_amp][n_samples][2], g_state0: [U][batch][dim] (device)
-  const cplx* states_for_fallback_ = nullptr;   // set by the C ABI around backward_units
-  void backward_units(std::vector<Tape>& tapes, const double* dv, const double* av, const cplx* gstates,
-                      double* g_det, double* g_amp, cplx* g_state0, void* stream) {
+  const amp_t* states_for_fallback_ = nullptr;   // set by the C ABI around backward_units
+  void backward_units(std::vector<Tape>& tapes, const double* dv, const double* av, const amp_t* gstates,
+                      double* g_det, double* g_amp, amp_t* g_state0, void* stream) {
     int n_units = (int)tapes.size();
     if (n_units == 0) return;
     int ns = prog.n_samples, n_det = prog.n_det(), n_amp = prog.n_amp();
@@ -242,7 +242,7 @@ class Engine {
     std::vector<std::vector<SkStepHost>> st(n_units);
     for (int u = 0; u < n_units; ++u)
       for (const auto& a : tapes[u].steps) st[u].push_back({a.t, a.dt, a.interval, a.clipped});
-    cplx* lam = (cplx*)buf("lam_units", sizeof(cplx) * L * (size_t)n_units);
+    amp_t* lam = (amp_t*)buf("lam_units", sizeof(amp_t) * L * (size_t)n_units);
     std::vector<std::vector<double>> sums;
     int nl = 0;
     bool want_coef = g_det || g_amp;
@@ -252,7 +252,7 @@ class Engine {
                                    lam, g_det, g_amp, stream);
       if (nl > 0) {
         launches += nl;
-        if (g_state0) bk.d2d(g_state0, lam, sizeof(cplx) * L * (size_t)n_units, stream);
+        if (g_state0) bk.d2d(g_state0, lam, sizeof(amp_t) * L * (size_t)n_units, stream);
         bk.sync(stream);
         return;
       }
@@ -285,7 +285,7 @@ class Engine {
       return;
     }
     launches += nl;
-    if (g_state0) bk.d2d(g_state0, lam, sizeof(cplx) * L * (size_t)n_units, stream);
+    if (g_state0) bk.d2d(g_state0, lam, sizeof(amp_t) * L * (size_t)n_units, stream);
     if (g_det) std::fill(g_det, g_det + (size_t)n_units * n_det * ns, 0.0);
     if (g_amp) std::fill(g_amp, g_amp + (size_t)n_units * n_amp * ns * 2, 0.0);
     if (want_coef)
@@ -303,19 +303,19 @@ class Engine {
   }
 
   // ---- measurement hooks ------------------------------------------------------------------
-  double bench_apply(const cplx* in, cplx* out, double t, int reps, void* stream) {
+  double bench_apply(const amp_t* in, amp_t* out, double t, int reps, void* stream) {
     apply(out, in, t, 2, stream);
     bk.sync(stream);
     bk.timer_start(stream);
     for (int r = 0; r < reps; ++r) apply(out, in, t, 2, stream);
     return bk.timer_stop_ms(stream) / std::max(1, reps);
   }
-  double bench_dp5(cplx* y_io, double t0, double dt, int steps, void* stream) {
+  double bench_dp5(amp_t* y_io, double t0, double dt, int steps, void* stream) {
     vec y = vbuf("y"), ynew = vbuf("ynew");
     vec k[7];
     for (int i = 0; i < 7; ++i) k[i] = vbuf("k" + std::to_string(i));
     double* d_err = (double*)buf("norm_out", sizeof(double) * geo.batch);
-    bk.d2d(y, y_io, sizeof(cplx) * L, stream);
+    bk.d2d(y, y_io, sizeof(amp_t) * L, stream);
     double t = t0;
     apply(k[0], y, t, 0, stream);
     auto one = [&]() {
@@ -329,13 +329,13 @@ class Engine {
     bk.timer_start(stream);
     for (int s = 0; s < steps; ++s) one();
     double ms = bk.timer_stop_ms(stream) / std::max(1, steps);
-    bk.d2d(y_io, y, sizeof(cplx) * L, stream);
+    bk.d2d(y_io, y, sizeof(amp_t) * L, stream);
     bk.sync(stream);
     return ms;
   }
 
   // ---- diagonal expectation --------------------------------------------------------------
-  void expect_diag(const cplx* states, int n_t, const double* obs, double* out_host, void* stream) {
+  void expect_diag(const amp_t* states, int n_t, const double* obs, double* out_host, void* stream) {
     cplx* d_out = (cplx*)buf("expect", sizeof(cplx) * (size_t)n_t);
     launches += bk.expect_diag(geo, states, n_t, obs, d_out, reduce_scratch(), stream);
     bk.d2h(out_host, d_out, sizeof(cplx) * (size_t)n_t, stream);
@@ -347,7 +347,7 @@ class Engine {
   // are ADDED into g_det / g_amp, g_pair is overwritten; returns dL/dt.  Same reductions as one
   // stage of the DP5 adjoint (adjoint_step), exposed so host-side integrators (the sharded
   // register, user-written steppers) are differentiable too.
-  double rhs_vjp(double t, const cplx* y, const cplx* kbar, cplx* grad_y, double* g_det,
+  double rhs_vjp(double t, const amp_t* y, const amp_t* kbar, amp_t* grad_y, double* g_det,
                  double* g_amp, double* g_pair, bool defer_pair, void* stream) {
     if (grad_y) apply(grad_y, kbar, t, 1, stream);
     int cs = corr_stride();
@@ -362,7 +362,7 @@ class Engine {
       d_wacc = (double*)buf("wacc", wbytes);
       bk.zero(d_wacc, wbytes, stream);
     }
-    const cplx* yi[1] = {y};
+    const amp_t* yi[1] = {y};
     double yw[1] = {1.0};
     launches += bk.corr_combo(geo, d_corr, d_wacc, 1.0, kbar, 1, yi, yw, vbuf("ystage"),
                               reduce_scratch(), stream);
@@ -392,11 +392,11 @@ class Engine {
 
   // ---- building blocks of a host-driven DP5 step (the sharded register) --------------------
   // out = sum_j w_j in_j (one pass)
-  void lincomb(cplx* out, int n_in, const cplx* const* ins, const double* w, void* stream) {
+  void lincomb(amp_t* out, int n_in, const amp_t* const* ins, const double* w, void* stream) {
     launches += bk.lincomb(geo, out, n_in, ins, w, stream);
   }
   // per-column sum over this plan's amplitudes of |sum_j ew_j k_j / (atol + rtol max(|y0|,|y1|))|^2
-  void error_sumsq(const cplx* const* k, const double* ew, const cplx* y0, const cplx* y1,
+  void error_sumsq(const amp_t* const* k, const double* ew, const amp_t* y0, const amp_t* y1,
                    double atol, double rtol, double* out_host, void* stream) {
     double* d_err = (double*)buf("norm_out", sizeof(double) * geo.batch);
     launches += bk.err_sumsq(geo, d_err, k, ew, y0, y1, atol, rtol, reduce_scratch(), stream);
@@ -406,11 +406,11 @@ class Engine {
 
   // ---- sharded register: flips of the qubits that index the rank -----------
   // out += shift*psi + sum_k coef_k * peers[k]; peers[k] may be peer-mapped device memory.
-  void sharded_accumulate(cplx* out, const cplx* psi, double shift, int n_peers,
-                          const cplx* const* peers, const cplx* coef, void* stream) {
+  void sharded_accumulate(amp_t* out, const amp_t* psi, double shift, int n_peers,
+                          const amp_t* const* peers, const cplx* coef, void* stream) {
     launches += bk.sharded_accumulate(geo, out, psi, shift, n_peers, peers, coef, stream);
   }
-  void sharded_accumulate_n(cplx* out, const cplx* psi, double shift, int n_peers, const cplx* const* peers,
+  void sharded_accumulate_n(amp_t* out, const amp_t* psi, double shift, int n_peers, const amp_t* const* peers,
                             const cplx* coef, size_t n_amp, void* stream) {
     if (n_amp > geo.dim * (size_t)geo.batch) throw Error(PD_ERR_INVALID, "range longer than the slice");
     Geometry g1 = geo;
@@ -446,7 +446,7 @@ class Engine {
         return;
       }
   }
-  vec vbuf(const std::string& name) { return (vec)buf(name, sizeof(cplx) * L); }
+  vec vbuf(const std::string& name) { return (vec)buf(name, sizeof(amp_t) * L); }
   vec scratch(void*) { return vbuf("scratch"); }
   double* reduce_scratch() { return (double*)buf("reduce", bk.reduce_scratch_bytes(geo)); }
 
@@ -455,7 +455,7 @@ class Engine {
     for (int b = 0; b < geo.batch; ++b) m = std::max(m, std::sqrt(sumsq[b] / (double)geo.dim));
     return m;
   }
-  double scaled_norm(const cplx* x, const cplx* xsub, const cplx* ref, double atol, double rtol,
+  double scaled_norm(const amp_t* x, const amp_t* xsub, const amp_t* ref, double atol, double rtol,
                      void* stream) {
     double* d = (double*)buf("norm_out", sizeof(double) * geo.batch);
     std::vector<double> h(geo.batch);
@@ -466,12 +466,12 @@ class Engine {
   }
 
   // Hairer's initial step heuristic
-  double init_tstep(double t0, const cplx* y0, const cplx* f0, const pd_options& o, void* stream) {
+  double init_tstep(double t0, const amp_t* y0, const amp_t* f0, const pd_options& o, void* stream) {
     double d0 = scaled_norm(y0, nullptr, y0, o.atol, o.rtol, stream);
     double d1 = scaled_norm(f0, nullptr, y0, o.atol, o.rtol, stream);
     double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     vec y1 = vbuf("ynew"), f1 = vbuf("k1");
-    const cplx* ins[2] = {y0, f0};
+    const amp_t* ins[2] = {y0, f0};
     double w[2] = {1.0, h0};
     stage(f1, y1, 2, ins, w, t0 + h0, 0, stream);
     double d2 = scaled_norm(f1, f0, y0, o.atol, o.rtol, stream) / h0;
@@ -487,9 +487,9 @@ class Engine {
   }
 
   // stages 2..(last) of one DP5 step from (t, y, k[0]); fills k[1..last-1]; ynew if last == 7
-  void dp5_stages(double t, double dt, const cplx* y, vec* k, vec ynew, int last, void* stream) {
+  void dp5_stages(double t, double dt, const amp_t* y, vec* k, vec ynew, int last, void* stream) {
     for (int i = 1; i < last; ++i) {
-      const cplx* ins[8];
+      const amp_t* ins[8];
       double w[8];
       int n = 0;
       ins[n] = y; w[n++] = 1.0;
@@ -503,7 +503,7 @@ class Engine {
 
   // stages 2..7, y_{n+1} and the per-column error sums of one step; fused tiled path if the
   // backend offers one for this shape, stage by stage otherwise
-  void dp5_step_with_error(double t, double dt, const cplx* y, vec* k, vec ynew, double atol,
+  void dp5_step_with_error(double t, double dt, const amp_t* y, vec* k, vec ynew, double atol,
                            double rtol, double* d_err, void* stream) {
     double ew[7];
     for (int j = 0; j < 7; ++j) ew[j] = dt * (tab.b5[j] - tab.b4[j]);
@@ -515,12 +515,12 @@ class Engine {
       if (nl > 0) { launches += nl; return; }
     }
     dp5_stages(t, dt, y, k, ynew, 7, stream);
-    launches += bk.err_sumsq(geo, d_err, (const cplx* const*)k, ew, y, ynew, atol, rtol,
+    launches += bk.err_sumsq(geo, d_err, (const amp_t* const*)k, ew, y, ynew, atol, rtol,
                              reduce_scratch(), stream);
   }
 
-  void forward_dp5(const pd_options& o, const cplx* state0, const double* tsave, int n_t,
-                   cplx* states, Tape* tape, void* stream) {
+  void forward_dp5(const pd_options& o, const amp_t* state0, const double* tsave, int n_t,
+                   amp_t* states, Tape* tape, void* stream) {
     vec y = vbuf("y"), ynew = vbuf("ynew");
     vec k[7];
     for (int i = 0; i < 7; ++i) k[i] = vbuf("k" + std::to_string(i));
@@ -539,7 +539,7 @@ class Engine {
       }
       return;
     }
-    bk.d2d(y, state0, sizeof(cplx) * L, stream);
+    bk.d2d(y, state0, sizeof(amp_t) * L, stream);
     double t = tsave[0];
     apply(k[0], y, t, 0, stream);
     bool replay = o.n_replay > 0;
@@ -582,7 +582,7 @@ class Engine {
         if (++steps >= o.max_steps) throw Error(PD_ERR_MAX_STEPS, "max_steps reached");
       }
       dt = cache_dt; error = cache_err;
-      bk.d2d(states + (size_t)kk * L, y, sizeof(cplx) * L, stream);
+      bk.d2d(states + (size_t)kk * L, y, sizeof(amp_t) * L, stream);
     }
     bk.sync(stream);
   }
@@ -590,8 +590,8 @@ class Engine {
   // ---- DP5 adjoint -------------------------------------------------------------------------
   int corr_stride() const { return geo.nq * (prog.kind == PD_KET ? 4 : 16); }
 
-  void backward_dp5(Tape& tape, const cplx* states, const cplx* gstates, double* g_det,
-                    double* g_amp, double* g_pair, double* g_tsave, cplx* g_state0, bool want_coef,
+  void backward_dp5(Tape& tape, const amp_t* states, const amp_t* gstates, double* g_det,
+                    double* g_amp, double* g_pair, double* g_tsave, amp_t* g_state0, bool want_coef,
                     void* stream) {
     int n_t = (int)tape.tsave.size();
     size_t n_steps = tape.steps.size();
@@ -605,8 +605,8 @@ class Engine {
     auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
     auto t_begin = now();
     double ms_alloc = 0, ms_recompute = 0, ms_sweep = 0;
-    if (gstates) bk.d2d(lam, gstates + (size_t)(n_t - 1) * L, sizeof(cplx) * L, stream);
-    else bk.zero(lam, sizeof(cplx) * L, stream);
+    if (gstates) bk.d2d(lam, gstates + (size_t)(n_t - 1) * L, sizeof(amp_t) * L, stream);
+    else bk.zero(lam, sizeof(amp_t) * L, stream);
     vec k[6], yb[6];
     for (int i = 0; i < 6; ++i) { k[i] = vbuf("k" + std::to_string(i)); yb[i] = vbuf("yb" + std::to_string(i)); }
     vec kbar = vbuf("kbar"), ystage = vbuf("ystage");
@@ -624,7 +624,7 @@ class Engine {
     std::vector<SlotInfo> slots(n_slots);
 
     // segment buffer for recomputed step-start states
-    size_t vec_bytes = sizeof(cplx) * L;
+    size_t vec_bytes = sizeof(amp_t) * L;
     size_t cap = std::max<size_t>(1, bk.segment_budget_bytes() / vec_bytes);
     auto t_setup = now();
 
@@ -634,7 +634,7 @@ class Engine {
       while (lo > 0 && tape.steps[lo - 1].interval == kk) --lo;
       size_t ns = hi - lo;
       if (ns > 0) {
-        const cplx* y_start = states + (size_t)(kk - 1) * L;
+        const amp_t* y_start = states + (size_t)(kk - 1) * L;
         // process the interval's steps in chunks of <= cap, last chunk first
         size_t done_hi = ns;
         while (done_hi > 0) {
@@ -644,7 +644,7 @@ class Engine {
           auto t0 = now();
           vec seg = (vec)buf("seg", vec_bytes * cn);
           vec ycur = vbuf("y"), ynext = vbuf("ynew");
-          const cplx* ysrc = y_start;
+          const amp_t* ysrc = y_start;
           for (size_t s = 0; s < c_lo; ++s) {
             const AcceptedStep& st = tape.steps[lo + s];
             advance(ysrc, ynext, st, k, stream);
@@ -682,7 +682,7 @@ class Engine {
       }
       hi = lo;
       if (gstates) {
-        const cplx* ins[2] = {lam, gstates + (size_t)(kk - 1) * L};
+        const amp_t* ins[2] = {lam, gstates + (size_t)(kk - 1) * L};
         double w[2] = {1.0, 1.0};
         launches += bk.lincomb(geo, lam, 2, ins, w, stream);
       }
@@ -729,8 +729,8 @@ class Engine {
     if (bk.path == 3 && !ok) throw Error(PD_ERR_INVALID, "path 3 (small-register kernels) does not fit this plan");
     return ok;
   }
-  bool backward_dp5_small(Tape& tape, const cplx* states, const cplx* gstates, double* g_det,
-                          double* g_amp, double* g_pair, double* g_tsave, cplx* g_state0,
+  bool backward_dp5_small(Tape& tape, const amp_t* states, const amp_t* gstates, double* g_det,
+                          double* g_amp, double* g_pair, double* g_tsave, amp_t* g_state0,
                           bool want_coef, void* stream) {
     int n_t = (int)tape.tsave.size();
     int n_steps = (int)tape.steps.size();
@@ -747,7 +747,7 @@ class Engine {
                                want_coef, d_wacc, lam, sums_u, stream);
     if (nl == 0) return false;
     launches += nl;
-    if (g_state0) bk.d2d(g_state0, lam, sizeof(cplx) * L, stream);
+    if (g_state0) bk.d2d(g_state0, lam, sizeof(amp_t) * L, stream);
     if (want_coef && n_steps > 0) {
       const std::vector<double>& sums = sums_u[0];
       size_t nred = (size_t)prog.n_det() + 2 * (size_t)prog.n_amp() + 1;
@@ -809,10 +809,10 @@ class Engine {
   }
 
   // y_out = DP5 step from y_in (no error estimate); leaves k[0..5] filled
-  void advance(const cplx* y_in, vec y_out, const AcceptedStep& st, vec* k, void* stream) {
+  void advance(const amp_t* y_in, vec y_out, const AcceptedStep& st, vec* k, void* stream) {
     apply(k[0], y_in, st.t, 0, stream);
     dp5_stages(st.t, st.dt, y_in, k, nullptr, 6, stream);
-    const cplx* ins[8];
+    const amp_t* ins[8];
     double w[8];
     int n = 0;
     ins[n] = y_in; w[n++] = 1.0;
@@ -821,7 +821,7 @@ class Engine {
     launches += bk.lincomb(geo, y_out, n, ins, w, stream);
   }
 
-  void adjoint_step(const AcceptedStep& st, int step_index, const cplx* y_n, vec lam, vec* k,
+  void adjoint_step(const AcceptedStep& st, int step_index, const amp_t* y_n, vec lam, vec* k,
                     vec* yb, vec kbar, vec ystage, cplx* d_corr, double* d_hdot, double* d_wacc,
                     std::vector<SlotInfo>& slots, bool want_coef, void* stream, bool have_k = false) {
     double t = st.t, h = st.dt;
@@ -831,7 +831,7 @@ class Engine {
     }
     int cs = corr_stride();
     for (int i = 5; i >= 0; --i) {
-      const cplx* ins[8];
+      const amp_t* ins[8];
       double w[8];
       int n = 0;
       if (tab.b5[i] != 0.0) { ins[n] = lam; w[n++] = h * tab.b5[i]; }
@@ -846,7 +846,7 @@ class Engine {
       slots[slot] = {ts, alpha, st.interval, step_index};
       if (want_coef || d_wacc) {
         // stage input Y_i = y_n + h sum_j beta_ij k_j, formed by the correlation launch itself
-        const cplx* yi[8];
+        const amp_t* yi[8];
         double yw[8];
         int m = 0;
         yi[m] = y_n; yw[m++] = 1.0;
@@ -860,7 +860,7 @@ class Engine {
       if (d_hdot && st.clipped)
         launches += bk.re_dot(geo, d_hdot + slot, kbar, k[i], reduce_scratch(), stream);
     }
-    const cplx* ins[7];
+    const amp_t* ins[7];
     double w[7];
     ins[0] = lam; w[0] = 1.0;
     for (int i = 0; i < 6; ++i) { ins[i + 1] = yb[i]; w[i + 1] = 1.0; }
@@ -933,7 +933,7 @@ class Engine {
   };
   // Builds the Krylov basis of (H(t_eval), v0) in `basis` (m vectors of length dim), returns the
   // small-matrix data; out (nullable) = exp(-i*delta*H) v0 (sign=+1) or exp(+i*delta*H) v0 (-1).
-  Lanczos lanczos_exp(const cplx* v0, vec out, vec basis, int max_m, double t_eval, double delta,
+  Lanczos lanczos_exp(const amp_t* v0, vec out, vec basis, int max_m, double t_eval, double delta,
                       double sign, const pd_options& o, void* stream) {
     size_t n = geo.dim;
     Lanczos lz;
@@ -952,7 +952,7 @@ class Engine {
         launches += bk.small_lanczos(g1, prog, v0, basis, max_m, t_eval, done, j1, done > 0 ? be[done - 1] : 0.0,
                                      al.data(), be.data(), &lz.nrm, stream);
         if (done == 0 && lz.nrm == 0.0) {
-          if (out) bk.zero(out, sizeof(cplx) * n, stream);
+          if (out) bk.zero(out, sizeof(amp_t) * n, stream);
           return lz;
         }
         for (int j = done; j < j1 && !stop; ++j) {
@@ -982,11 +982,11 @@ class Engine {
     bk.sync(stream);
     lz.nrm = std::sqrt(hs[0]);
     if (lz.nrm == 0.0) {
-      if (out) bk.zero(out, sizeof(cplx) * n, stream);
+      if (out) bk.zero(out, sizeof(amp_t) * n, stream);
       return lz;
     }
     {
-      const cplx* ins[1] = {v0};
+      const amp_t* ins[1] = {v0};
       double w[1] = {1.0 / lz.nrm};
       launches += bk.lincomb(g1, basis, 1, ins, w, stream);
     }
@@ -995,7 +995,7 @@ class Engine {
     prog.site_ops_ket(t_eval, 2, so);
     for (int j = 0; j < max_m; ++j) {
       vec vj = basis + (size_t)j * n;
-      const cplx* ins1[1] = {vj};
+      const amp_t* ins1[1] = {vj};
       double w1[1] = {1.0};
       launches += bk.stage_ket(g1, r, nullptr, 1, ins1, w1, so, scratch(stream), stream);
       launches += bk.re_dot(g1, d_s, vj, r, reduce_scratch(), stream);
@@ -1003,7 +1003,7 @@ class Engine {
       bk.sync(stream);
       lz.alpha.push_back(hs[0]);
       {
-        const cplx* ins[3] = {r, vj, j > 0 ? basis + (size_t)(j - 1) * n : vj};
+        const amp_t* ins[3] = {r, vj, j > 0 ? basis + (size_t)(j - 1) * n : vj};
         double w[3] = {1.0, -lz.alpha.back(), j > 0 ? -lz.beta.back() : 0.0};
         launches += bk.lincomb(g1, r, j > 0 ? 3 : 2, ins, w, stream);
       }
@@ -1022,7 +1022,7 @@ class Engine {
       }
       if (j + 1 == max_m) break;
       lz.beta.push_back(beta);
-      const cplx* ins[1] = {r};
+      const amp_t* ins[1] = {r};
       double w[1] = {1.0 / beta};
       launches += bk.lincomb(g1, basis + (size_t)(j + 1) * n, 1, ins, w, stream);
     }
@@ -1030,7 +1030,7 @@ class Engine {
     return lz;
   }
   // out = scale * sum_j w_j basis_j  (complex weights)
-  void combine_basis(vec out, const cplx* basis, const std::vector<cplx>& w, int m, double scale,
+  void combine_basis(vec out, const amp_t* basis, const std::vector<cplx>& w, int m, double scale,
                      void* stream) {
     Geometry g1 = geo;
     g1.batch = 1;
@@ -1039,18 +1039,18 @@ class Engine {
     launches += bk.lincomb_c(g1, out, m, basis, geo.dim, ws.data(), stream);
   }
 
-  void forward_krylov(const pd_options& o, const cplx* state0, const double* tsave, int n_t,
-                      cplx* states, Tape* tape, void* stream) {
+  void forward_krylov(const pd_options& o, const amp_t* state0, const double* tsave, int n_t,
+                      amp_t* states, Tape* tape, void* stream) {
     if (prog.kind != PD_KET) throw Error(PD_ERR_INVALID, "KRYLOV_SE needs a ket plan");
     size_t n = geo.dim;
     int max_m = std::max(2, (int)o.max_krylov);
-    vec basis = (vec)buf("kry_basis", sizeof(cplx) * n * (size_t)max_m);
-    bk.d2d(states, state0, sizeof(cplx) * L, stream);
+    vec basis = (vec)buf("kry_basis", sizeof(amp_t) * n * (size_t)max_m);
+    bk.d2d(states, state0, sizeof(amp_t) * L, stream);
     for (int kk = 1; kk < n_t; ++kk) {
       double delta = tsave[kk] - tsave[kk - 1];
-      cplx* dst = states + (size_t)kk * L;
-      const cplx* src = states + (size_t)(kk - 1) * L;
-      if (!(delta > 0.0)) { bk.d2d(dst, src, sizeof(cplx) * L, stream); continue; }
+      amp_t* dst = states + (size_t)kk * L;
+      const amp_t* src = states + (size_t)(kk - 1) * L;
+      if (!(delta > 0.0)) { bk.d2d(dst, src, sizeof(amp_t) * L, stream); continue; }
       for (int b = 0; b < geo.batch; ++b)
         lanczos_exp(src + (size_t)b * n, dst + (size_t)b * n, basis, max_m, tsave[kk], delta, 1.0, o, stream);
       if (tape) tape->ksegs.push_back({kk, delta, tsave[kk]});
@@ -1065,8 +1065,8 @@ class Engine {
   //   psi(s) = exp(-i s D H) psi_{k-1},  lam(s) = exp(+i (1-s) D H) lam_k,
   // with both curves evaluated inside their Krylov subspaces and the integral by
   // Gauss-Legendre quadrature.  Matches tape autograd through Lanczos to the Krylov tolerance.
-  void backward_krylov(Tape& tape, const cplx* states, const cplx* gstates, double* g_det,
-                       double* g_amp, double* g_pair, double* g_tsave, cplx* g_state0,
+  void backward_krylov(Tape& tape, const amp_t* states, const amp_t* gstates, double* g_det,
+                       double* g_amp, double* g_pair, double* g_tsave, amp_t* g_state0,
                        bool want_coef, void* stream) {
     static const double gx[12] = {-0.9815606342467192, -0.9041172563704749, -0.7699026741943047,
                                   -0.5873179542866175, -0.3678314989981802, -0.1252334085114689,
@@ -1084,10 +1084,10 @@ class Engine {
     Geometry g1 = geo;
     g1.batch = 1;
     vec lam = vbuf("lam");
-    if (gstates) bk.d2d(lam, gstates + (size_t)(n_t - 1) * L, sizeof(cplx) * L, stream);
-    else bk.zero(lam, sizeof(cplx) * L, stream);
-    vec basisV = (vec)buf("kry_basis", sizeof(cplx) * n * (size_t)max_m);
-    vec basisW = (vec)buf("kry_basis2", sizeof(cplx) * n * (size_t)max_m);
+    if (gstates) bk.d2d(lam, gstates + (size_t)(n_t - 1) * L, sizeof(amp_t) * L, stream);
+    else bk.zero(lam, sizeof(amp_t) * L, stream);
+    vec basisV = (vec)buf("kry_basis", sizeof(amp_t) * n * (size_t)max_m);
+    vec basisW = (vec)buf("kry_basis2", sizeof(amp_t) * n * (size_t)max_m);
     vec ps = vbuf("kry_ps"), ls = vbuf("kry_ls"), lnew = vbuf("kry_lnew");
     int cs = corr_stride();
     double* d_wacc = nullptr;
@@ -1110,12 +1110,12 @@ class Engine {
         SiteOps so_rhs;
         prog.site_ops_ket(sg.t_eval, 0, so_rhs);
         for (int b = 0; b < geo.batch; ++b) {
-          const cplx* psi_prev = states + (size_t)(kk - 1) * L + (size_t)b * n;
-          const cplx* psi_k = states + (size_t)kk * L + (size_t)b * n;
+          const amp_t* psi_prev = states + (size_t)(kk - 1) * L + (size_t)b * n;
+          const amp_t* psi_k = states + (size_t)kk * L + (size_t)b * n;
           vec lam_b = lam + (size_t)b * n;
           if (g_tsave) {
             // through delta = t_k - t_{k-1}:  Re<lam_k, -i H psi_k>
-            const cplx* ins1[1] = {psi_k};
+            const amp_t* ins1[1] = {psi_k};
             double w1[1] = {1.0};
             launches += bk.stage_ket(g1, ps, nullptr, 1, ins1, w1, so_rhs, scratch(stream), stream);
             launches += bk.re_dot(g1, d_h, lam_b, ps, reduce_scratch(), stream);
@@ -1138,16 +1138,16 @@ class Engine {
             launches += bk.corr(g1, d_corr + slot * cs, d_wacc, wq, ls, ps, reduce_scratch(), stream);
             kslots[slot] = {sg.t_eval, wq, kk};
           }
-          bk.d2d(lam_b, lnew, sizeof(cplx) * n, stream);
+          bk.d2d(lam_b, lnew, sizeof(amp_t) * n, stream);
         }
       }
       if (gstates) {
-        const cplx* ins[2] = {lam, gstates + (size_t)(kk - 1) * L};
+        const amp_t* ins[2] = {lam, gstates + (size_t)(kk - 1) * L};
         double w[2] = {1.0, 1.0};
         launches += bk.lincomb(geo, lam, 2, ins, w, stream);
       }
     }
-    if (g_state0) bk.d2d(g_state0, lam, sizeof(cplx) * L, stream);
+    if (g_state0) bk.d2d(g_state0, lam, sizeof(amp_t) * L, stream);
     if (want_coef && n_slots > 0) {
       std::vector<cplx> h_corr(n_slots * cs);
       bk.d2h(h_corr.data(), d_corr, sizeof(cplx) * n_slots * cs, stream);

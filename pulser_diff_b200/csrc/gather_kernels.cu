@@ -10,7 +10,7 @@ namespace pd {
 namespace {
 
 struct PtrW {
-  const cplx* p[8];
+  const amp_t* p[8];
   double w[8];
   int n;
 };
@@ -79,7 +79,7 @@ int rgrid_for(size_t n, int R, int ny) {
   return (int)std::max<size_t>(1, std::min(b, cap));
 }
 
-__global__ void __launch_bounds__(kThreads) k_lincomb(cplx* out, PtrW a, size_t n) {
+__global__ void __launch_bounds__(kThreads) k_lincomb(amp_t* out, PtrW a, size_t n) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     double re = 0.0, im = 0.0;
@@ -90,11 +90,11 @@ __global__ void __launch_bounds__(kThreads) k_lincomb(cplx* out, PtrW a, size_t 
         re = fma(a.w[j], v.re, re);
         im = fma(a.w[j], v.im, im);
       }
-    out[i] = {re, im};
+    out[i] = cplx{re, im};
   }
 }
 
-__global__ void __launch_bounds__(kThreads) k_lincomb_c(cplx* out, const cplx* basis, size_t stride_v,
+__global__ void __launch_bounds__(kThreads) k_lincomb_c(amp_t* out, const amp_t* basis, size_t stride_v,
                                                         const __grid_constant__ CW cw, size_t n) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kThreads) k_lincomb_c(cplx* out, const cplx* b
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_apply_ket(cplx* __restrict__ out, const cplx* __restrict__ in, const double* __restrict__ diag,
+k_apply_ket(amp_t* __restrict__ out, const amp_t* __restrict__ in, const double* __restrict__ diag,
             const __grid_constant__ SiteOps so, int nq, size_t dim, size_t total) {
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
@@ -128,7 +128,7 @@ k_apply_ket(cplx* __restrict__ out, const cplx* __restrict__ in, const double* _
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_apply_density(cplx* __restrict__ out, const cplx* __restrict__ in, const double* __restrict__ diag,
+k_apply_density(amp_t* __restrict__ out, const amp_t* __restrict__ in, const double* __restrict__ diag,
                 const __grid_constant__ SiteOpsDensity so, int nq, size_t total, int need_both) {
   __shared__ cplx T[kMaxSitesDensity * 16];
   for (int i = threadIdx.x; i < nq * 16; i += blockDim.x) T[i] = so.T[i];
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(kThreads) k_build_diag(double* diag, int nq, c
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_scaled_sumsq(const cplx* __restrict__ x, const cplx* __restrict__ xsub, const cplx* __restrict__ ref,
+k_scaled_sumsq(const amp_t* __restrict__ x, const amp_t* __restrict__ xsub, const amp_t* __restrict__ ref,
                double atol, double rtol, size_t dim, double* partial) {
   size_t base = (size_t)blockIdx.y * dim;
   double acc[1] = {0.0};
@@ -191,11 +191,11 @@ k_scaled_sumsq(const cplx* __restrict__ x, const cplx* __restrict__ xsub, const 
 }
 
 struct KPtr7 {
-  const cplx* k[7];
+  const amp_t* k[7];
   double ew[7];
 };
 __global__ void __launch_bounds__(kThreads)
-k_err_sumsq(KPtr7 kp, const cplx* __restrict__ y0, const cplx* __restrict__ y1, double atol,
+k_err_sumsq(KPtr7 kp, const amp_t* __restrict__ y0, const amp_t* __restrict__ y1, double atol,
             double rtol, size_t dim, double* partial) {
   size_t base = (size_t)blockIdx.y * dim;
   double acc[1] = {0.0};
@@ -218,7 +218,7 @@ k_err_sumsq(KPtr7 kp, const cplx* __restrict__ y0, const cplx* __restrict__ y1, 
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_re_dot(const cplx* __restrict__ a, const cplx* __restrict__ b, size_t n, double* partial) {
+k_re_dot(const amp_t* __restrict__ a, const amp_t* __restrict__ b, size_t n, double* partial) {
   double acc[1] = {0.0};
   size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -232,7 +232,7 @@ k_re_dot(const cplx* __restrict__ a, const cplx* __restrict__ b, size_t n, doubl
 //   C_q[a][a'] = sum_{b, s: bit_q(s)=a} conj(kbar[b,s]) * y[b, s with bit_q := a']
 constexpr int kQC = 4;
 __global__ void __launch_bounds__(kThreads)
-k_corr_ket(const cplx* __restrict__ kbar, const cplx* __restrict__ y, int nq, size_t dim, int batch,
+k_corr_ket(const amp_t* __restrict__ kbar, const amp_t* __restrict__ y, int nq, size_t dim, int batch,
            double* partial, double* wacc, double wscale) {
   int q0 = blockIdx.y * kQC;
   double acc[kQC * 8];
@@ -280,7 +280,7 @@ k_corr_ket(const cplx* __restrict__ kbar, const cplx* __restrict__ y, int nq, si
 // pass over the 4^N vector per site.)
 constexpr int kDF = 3 * kMaxSitesDensity;
 __global__ void __launch_bounds__(kThreads)
-k_corr_density_fused(const cplx* __restrict__ kbar, const cplx* __restrict__ y, int nq, size_t total,
+k_corr_density_fused(const amp_t* __restrict__ kbar, const amp_t* __restrict__ y, int nq, size_t total,
                      double* partial, double* wacc, double wscale) {
   size_t S = (size_t)1 << nq, dim = S * S;
   double acc[kDF];
@@ -348,7 +348,7 @@ k_pair_reduce(const double* __restrict__ wacc, int nq, double* out) {
 
 // blockIdx.y = time index.  ket: sum_{b,s} obs[s] |psi|^2.  density: sum_r obs[r] rho[r][r].
 __global__ void __launch_bounds__(kThreads)
-k_expect_diag(const cplx* __restrict__ states, const double* __restrict__ obs, int kind, int nq,
+k_expect_diag(const amp_t* __restrict__ states, const double* __restrict__ obs, int kind, int nq,
               size_t dim, int batch, double* partial) {
   double acc[2] = {0.0, 0.0};
   size_t base = (size_t)blockIdx.y * dim * batch;
@@ -372,7 +372,7 @@ k_expect_diag(const cplx* __restrict__ states, const double* __restrict__ obs, i
 
 }  // namespace
 
-int launch_lincomb(const Geometry& g, cplx* out, int n_in, const cplx* const* ins, const double* w,
+int launch_lincomb(const Geometry& g, amp_t* out, int n_in, const amp_t* const* ins, const double* w,
                    cudaStream_t s) {
   if (n_in < 1 || n_in > 8) throw Error(PD_ERR_INVALID, "lincomb takes 1..8 inputs");
   PtrW a{};
@@ -384,7 +384,7 @@ int launch_lincomb(const Geometry& g, cplx* out, int n_in, const cplx* const* in
   return 1;
 }
 
-int launch_lincomb_c(size_t n, cplx* out, int m, const cplx* basis, size_t stride, const cplx* ws,
+int launch_lincomb_c(size_t n, amp_t* out, int m, const amp_t* basis, size_t stride, const cplx* ws,
                      cudaStream_t s) {
   if (m < 1 || m > 128) throw Error(PD_ERR_INVALID, "lincomb_c takes 1..128 vectors");
   CW cw{};
@@ -395,14 +395,14 @@ int launch_lincomb_c(size_t n, cplx* out, int m, const cplx* basis, size_t strid
   return 1;
 }
 
-int launch_apply_ket(const Geometry& g, cplx* out, const cplx* in, const SiteOps& so, cudaStream_t s) {
+int launch_apply_ket(const Geometry& g, amp_t* out, const amp_t* in, const SiteOps& so, cudaStream_t s) {
   size_t total = g.dim * g.batch;
   k_apply_ket<<<grid_for(total), kThreads, 0, s>>>(out, in, g.diag, so, g.nq, g.dim, total);
   PD_CUDA_CHECK(cudaGetLastError());
   return 1;
 }
 
-int launch_apply_density(const Geometry& g, cplx* out, const cplx* in, const SiteOpsDensity& so,
+int launch_apply_density(const Geometry& g, amp_t* out, const amp_t* in, const SiteOpsDensity& so,
                          cudaStream_t s) {
   size_t total = g.dim * g.batch;
   int need_both = 0;
@@ -442,8 +442,8 @@ int launch_build_diag(double* diag, int nq, const double* d_pair_u, cudaStream_t
   return 1;
 }
 
-int launch_scaled_sumsq(const Geometry& g, double* out, const cplx* x, const cplx* xsub,
-                        const cplx* ref, double atol, double rtol, double* scratch, cudaStream_t s) {
+int launch_scaled_sumsq(const Geometry& g, double* out, const amp_t* x, const amp_t* xsub,
+                        const amp_t* ref, double atol, double rtol, double* scratch, cudaStream_t s) {
   int gx = rgrid_for(g.dim, 1, g.batch);
   k_scaled_sumsq<<<dim3(gx, g.batch), kThreads, 0, s>>>(x, xsub, ref, atol, rtol, g.dim, scratch);
   PD_CUDA_CHECK(cudaGetLastError());
@@ -452,8 +452,8 @@ int launch_scaled_sumsq(const Geometry& g, double* out, const cplx* x, const cpl
   return n;
 }
 
-int launch_err_sumsq(const Geometry& g, double* out, const cplx* const* k, const double* ew,
-                     const cplx* y0, const cplx* y1, double atol, double rtol, double* scratch,
+int launch_err_sumsq(const Geometry& g, double* out, const amp_t* const* k, const double* ew,
+                     const amp_t* y0, const amp_t* y1, double atol, double rtol, double* scratch,
                      cudaStream_t s) {
   KPtr7 kp{};
   for (int j = 0; j < 7; ++j) { kp.k[j] = k[j]; kp.ew[j] = ew[j]; }
@@ -465,7 +465,7 @@ int launch_err_sumsq(const Geometry& g, double* out, const cplx* const* k, const
   return n;
 }
 
-int launch_re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, double* scratch,
+int launch_re_dot(const Geometry& g, double* out, const amp_t* a, const amp_t* b, double* scratch,
                   cudaStream_t s) {
   size_t n = g.dim * g.batch;
   int gx = rgrid_for(n, 1, 1);
@@ -474,8 +474,8 @@ int launch_re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, 
   return 1 + finalize(scratch, gx, 1, out, 1, 1.0, 0, s);
 }
 
-int launch_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar,
-                const cplx* y, double* scratch, cudaStream_t s) {
+int launch_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const amp_t* kbar,
+                const amp_t* y, double* scratch, cudaStream_t s) {
   int n = 0;
   if (g.kind == PD_KET) {
     int ny = (g.nq + kQC - 1) / kQC;
@@ -511,7 +511,7 @@ int launch_pair_reduce(const Geometry& g, double* d_pair, const double* d_wacc, 
   return 1;
 }
 
-int launch_expect_diag(const Geometry& g, const cplx* states, int n_t, const double* obs, cplx* out,
+int launch_expect_diag(const Geometry& g, const amp_t* states, int n_t, const double* obs, cplx* out,
                        double* scratch, cudaStream_t s) {
   size_t work = g.kind == PD_KET ? g.dim * g.batch : ((size_t)1 << g.nq) * g.batch;
   int n = 0;

@@ -40,6 +40,27 @@ PD_HD inline void fma_acc(cplx& acc, cplx a, cplx b) {
   acc.im = fma(a.re, b.im, fma(a.im, b.re, acc.im));
 }
 
+// Storage type of state-vector amplitudes in device memory.  The default build keeps complex128 (amp_t is
+// cplx itself); the complex64 build (-DPD_C64 -> libpulser_diff_b200_c64.so, north_star's optional 1e-5 tier)
+// stores {float re, im}: half the bytes per vector pass.  Coefficients, reductions, gradients, times and the
+// step controller stay double in both builds.  The gather kernels convert on load/store and compute in
+// double; the stream kernels compute in the storage precision (areal).
+#if defined(PD_C64)
+using areal = float;
+struct alignas(8) amp_t {
+  float re, im;
+  amp_t() = default;
+  PD_HD amp_t(float r, float i) : re(r), im(i) {}
+  PD_HD amp_t(cplx c) : re((float)c.re), im((float)c.im) {}
+  PD_HD operator cplx() const { return cplx{(double)re, (double)im}; }
+};
+constexpr bool kC64 = true;
+#else
+using areal = double;
+using amp_t = cplx;
+constexpr bool kC64 = false;
+#endif
+
 struct Error : std::runtime_error {
   int code;
   Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}

@@ -20,30 +20,39 @@ constexpr int kPeersPerLaunch = 4;
 constexpr int kAmpsPerThread = 4;
 constexpr int kAccThreads = 256;
 
+// amplitudes travel in the storage precision of the build (pd_common.hpp amp_t); the sums run in double
+#if defined(PD_C64)
+using avec = float2;
+__device__ __forceinline__ avec make_avec(double re, double im) { return make_float2((float)re, (float)im); }
+#else
+using avec = double2;
+__device__ __forceinline__ avec make_avec(double re, double im) { return make_double2(re, im); }
+#endif
+
 struct PeerSet {
-  const double2* src[kPeersPerLaunch];
+  const avec* src[kPeersPerLaunch];
   double2 coef[kPeersPerLaunch];
 };
 
 template <int NP>
 __global__ void __launch_bounds__(kAccThreads)
-k_sharded_accumulate(double2* __restrict__ out, const double2* __restrict__ psi, double shift,
+k_sharded_accumulate(avec* __restrict__ out, const avec* __restrict__ psi, double shift,
                      PeerSet ps, size_t n_amp) {
   const size_t chunk = (size_t)kAccThreads * kAmpsPerThread;
   for (size_t base = (size_t)blockIdx.x * chunk; base < n_amp; base += (size_t)gridDim.x * chunk) {
-    double2 r[NP > 0 ? NP : 1][kAmpsPerThread], o[kAmpsPerThread], y[kAmpsPerThread];
+    avec r[NP > 0 ? NP : 1][kAmpsPerThread], o[kAmpsPerThread], y[kAmpsPerThread];
 #pragma unroll
     for (int k = 0; k < NP; ++k)
 #pragma unroll
       for (int j = 0; j < kAmpsPerThread; ++j) {
         size_t i = base + (size_t)j * kAccThreads + threadIdx.x;
-        r[k][j] = i < n_amp ? __ldcs(ps.src[k] + i) : make_double2(0.0, 0.0);
+        r[k][j] = i < n_amp ? __ldcs(ps.src[k] + i) : make_avec(0.0, 0.0);
       }
 #pragma unroll
     for (int j = 0; j < kAmpsPerThread; ++j) {
       size_t i = base + (size_t)j * kAccThreads + threadIdx.x;
-      o[j] = i < n_amp ? out[i] : make_double2(0.0, 0.0);
-      y[j] = (i < n_amp && psi) ? __ldg(psi + i) : make_double2(0.0, 0.0);
+      o[j] = i < n_amp ? out[i] : make_avec(0.0, 0.0);
+      y[j] = (i < n_amp && psi) ? __ldg(psi + i) : make_avec(0.0, 0.0);
     }
 #pragma unroll
     for (int j = 0; j < kAmpsPerThread; ++j) {
@@ -54,15 +63,15 @@ k_sharded_accumulate(double2* __restrict__ out, const double2* __restrict__ psi,
         re += ps.coef[k].x * r[k][j].x - ps.coef[k].y * r[k][j].y;
         im += ps.coef[k].x * r[k][j].y + ps.coef[k].y * r[k][j].x;
       }
-      if (i < n_amp) out[i] = make_double2(re, im);
+      if (i < n_amp) out[i] = make_avec(re, im);
     }
   }
 }
 
 }  // namespace
 
-int launch_sharded_accumulate(size_t n_amp, cplx* out, const cplx* psi, double shift, int n_peers,
-                              const cplx* const* peers, const cplx* coef, cudaStream_t s) {
+int launch_sharded_accumulate(size_t n_amp, amp_t* out, const amp_t* psi, double shift, int n_peers,
+                              const amp_t* const* peers, const cplx* coef, cudaStream_t s) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -75,11 +84,11 @@ int launch_sharded_accumulate(size_t n_amp, cplx* out, const cplx* psi, double s
     int np = std::min(kPeersPerLaunch, n_peers - done);
     PeerSet ps{};
     for (int k = 0; k < np; ++k) {
-      ps.src[k] = (const double2*)peers[done + k];
+      ps.src[k] = (const avec*)peers[done + k];
       ps.coef[k] = make_double2(coef[done + k].re, coef[done + k].im);
     }
-    double2* o = (double2*)out;
-    const double2* y = done == 0 ? (const double2*)psi : nullptr;
+    avec* o = (avec*)out;
+    const avec* y = done == 0 ? (const avec*)psi : nullptr;
     double sh = done == 0 ? shift : 0.0;
     switch (np) {
       case 0: k_sharded_accumulate<0><<<grid, kAccThreads, 0, s>>>(o, y, sh, ps, n_amp); break;

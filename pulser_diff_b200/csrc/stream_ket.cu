@@ -35,6 +35,26 @@ namespace pd {
 
 namespace {
 
+// Tile / register complex type: the storage precision of the build (complex128, or {float, float} in the
+// complex64 build, where the whole tile arithmetic runs in float and only reductions stay double).
+#if defined(PD_C64)
+using treal = float;
+struct alignas(8) tcplx { float re, im; };
+__host__ __device__ inline tcplx operator*(tcplx a, tcplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__host__ __device__ inline void fma_acc(tcplx& acc, tcplx a, tcplx b) {
+  acc.re = fmaf(a.re, b.re, fmaf(-a.im, b.im, acc.re));
+  acc.im = fmaf(a.re, b.im, fmaf(a.im, b.re, acc.im));
+}
+#else
+using treal = double;
+using tcplx = cplx;
+#endif
+static_assert(sizeof(tcplx) == sizeof(amp_t), "tile type and storage type share one layout");
+__host__ __device__ inline const tcplx* tc(const amp_t* p) { return reinterpret_cast<const tcplx*>(p); }
+__host__ __device__ inline tcplx* tc(amp_t* p) { return reinterpret_cast<tcplx*>(p); }
+constexpr int kAmpBytes = (int)sizeof(tcplx);
+constexpr int kMinCtas = kC64 ? 4 : 3;   // resident CTAs per SM the REAL-drive kernels are compiled for
+
 constexpr int TB = 12;
 constexpr int TILE = 1 << TB;
 constexpr int NT = 256;
@@ -46,10 +66,10 @@ constexpr int kMaxGroupBits = 8;
 // site_ops_ket), so the tiles accumulate h = H Y with a REAL diagonal and conjugate-paired flips and scale
 // once: per flip 2 FMAs when the drive has no phase (REAL), 4 otherwise.
 struct StreamCoef {
-  cplx kappa;
-  double d[kMaxQubits];       // per GLOBAL bit position p: diagonal entry of H for bit value 0 (|r>)
-  double gre[kMaxQubits];     // flip entry of H, row bit 1 <- partner bit 0: g = gre + i gim;
-  double gim[kMaxQubits];     //                  row bit 0 <- partner bit 1: conj(g)
+  tcplx kappa;
+  treal d[kMaxQubits];        // per GLOBAL bit position p: diagonal entry of H for bit value 0 (|r>)
+  treal gre[kMaxQubits];      // flip entry of H, row bit 1 <- partner bit 0: g = gre + i gim;
+  treal gim[kMaxQubits];      //                  row bit 0 <- partner bit 1: conj(g)
 };
 
 struct StreamParams {
@@ -57,17 +77,17 @@ struct StreamParams {
   int lo, nb, C;              // strided groups: row bits [lo, lo+nb), C = TB - nb column bits
   int n_in;
   size_t dim;
-  const cplx* v[kMaxIn];
-  double w[kMaxIn];
-  cplx* ymat;                 // A launch: combined input written here (nullable)
-  cplx* out;
+  const tcplx* v[kMaxIn];
+  treal w[kMaxIn];
+  tcplx* ymat;                 // A launch: combined input written here (nullable)
+  tcplx* out;
   const double* diag;         // Dint split for tiles (Geometry::diag_parts): no 8 B/amplitude stream from HBM
   // embedded error estimate of the Dormand-Prince step (last stage only):
   //   A launch:      aux = sum_j w2_j v_j                  (partial error vector, w2 = dt*(b5-b4))
   //   last g launch: err = aux + werr*out;  sum |err / (atol + rtol*max(|y0|,|Ymat|))|^2 per CTA
-  double w2[kMaxIn];
-  cplx* aux;                  // A: written (nullable);  g: read when err_partial != null
-  const cplx* y0;
+  treal w2[kMaxIn];
+  tcplx* aux;                  // A: written (nullable);  g: read when err_partial != null
+  const tcplx* y0;
   double werr, atol, rtol;
   double* err_partial;        // [n_tiles] (g launch, nullable)
   int pol_st, pol_ld;         // L2 policy kinds (l2_policy) of this launch's result stores / tile loads
@@ -76,10 +96,17 @@ struct StreamParams {
   int via_ring;               // pipelined group items: tile data arrives as TMA boxes through the ring (else: loads)
 };
 
-__device__ __forceinline__ cplx ldcs(const cplx* p) {
+#if defined(PD_C64)
+__device__ __forceinline__ tcplx ldcs(const tcplx* p) {
+  float2 v = __ldcs(reinterpret_cast<const float2*>(p));
+  return {v.x, v.y};
+}
+#else
+__device__ __forceinline__ tcplx ldcs(const tcplx* p) {
   double2 v = __ldcs(reinterpret_cast<const double2*>(p));
   return {v.x, v.y};
 }
+#endif
 
 // L2 residency control of the dataflow launch (k_stream_ag): what an A tile writes (Ymat, partial result) is
 // re-read by a group tile a few chunks later and should outlive the input vectors streaming through L2; what
@@ -91,14 +118,42 @@ __device__ __forceinline__ unsigned long long l2_policy(int kind) {   // 0 norma
   else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-__device__ __forceinline__ void st_pol(cplx* p, cplx v, unsigned long long pol) {
+#if defined(PD_C64)
+__device__ __forceinline__ void st_pol(tcplx* p, tcplx v, unsigned long long pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.re), "f"(v.im), "l"(pol) : "memory");
+}
+__device__ __forceinline__ tcplx ld_pol(const tcplx* p, unsigned long long pol) {
+  tcplx v;
+  asm volatile("ld.global.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v.re), "=f"(v.im) : "l"(p), "l"(pol));
+  return v;
+}
+// one amplitude, global -> shared, asynchronously (LDGSTS): 8-byte copies exist only with .ca
+__device__ __forceinline__ void cp_async_amp(tcplx* smem_dst, const tcplx* src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_amp_pol(tcplx* smem_dst, const tcplx* src, unsigned long long pol) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+#else
+__device__ __forceinline__ void st_pol(tcplx* p, tcplx v, unsigned long long pol) {
   asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.re), "d"(v.im), "l"(pol) : "memory");
 }
-__device__ __forceinline__ cplx ld_pol(const cplx* p, unsigned long long pol) {
-  cplx v;
+__device__ __forceinline__ tcplx ld_pol(const tcplx* p, unsigned long long pol) {
+  tcplx v;
   asm volatile("ld.global.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.re), "=d"(v.im) : "l"(p), "l"(pol));
   return v;
 }
+__device__ __forceinline__ void cp_async_amp(tcplx* smem_dst, const tcplx* src) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_amp_pol(tcplx* smem_dst, const tcplx* src, unsigned long long pol) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(pol) : "memory");
+}
+#endif
 
 // CTA barrier of a tile routine: every thread of the CTA (NBAR = 0), or the NBAR consumer threads of the
 // persistent kernel (named barrier 1; its producer warp does not take part).
@@ -110,7 +165,7 @@ __device__ __forceinline__ void tile_sync() {
 
 // h += (gre + i*s) * pv  (REAL: s == 0)
 template <bool REAL>
-__device__ __forceinline__ void flip_acc(cplx& h, double gre, double s, cplx pv) {
+__device__ __forceinline__ void flip_acc(tcplx& h, treal gre, treal s, tcplx pv) {
   h.re = fma(gre, pv.re, h.re);
   h.im = fma(gre, pv.im, h.im);
   if (!REAL) {
@@ -126,31 +181,31 @@ __device__ __forceinline__ void flip_acc(cplx& h, double gre, double s, cplx pv)
 // (lb < 8) or a compile-time constant (lb >= 8): no per-element index arithmetic or selects.
 // second phase of an A tile: T holds the combined input Y of the tile (written by this CTA, not yet synced)
 template <bool REAL, int NBAR>
-__device__ __forceinline__ void a_tile_flips(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t tile,
+__device__ __forceinline__ void a_tile_flips(const StreamParams& P, const StreamCoef& cf, tcplx* T, size_t tile,
                                              size_t base) {
   const int t = threadIdx.x;
   const int nq = P.nq;
   // per-thread constants of the second phase (computed while the loads above drain)
-  const cplx* Tt = T + t;
-  const cplx* Tp[8];
-  double sg[8];
+  const tcplx* Tt = T + t;
+  const tcplx* Tp[8];
+  treal sg[8];
   // Diagonal = detunings + interaction.  The interaction of an occupied low bit p with the occupied bits above
   // the tile, ch[tile][p], acts like one more detuning on p: 13 doubles per tile from a small table instead of
   // 8 B per amplitude from HBM; the pairs inside the low 12 bits come from a 32 KiB table that lives in L1.
   const size_t n_tiles = P.dim >> TB;
   const double* ch = P.diag + TILE + n_tiles + tile * 12;
-  double dthr = __ldg(P.diag + TILE + tile);   // bits this thread's elements share: tile bits 0-7, bits above the tile
+  treal dthr = (treal)__ldg(P.diag + TILE + tile);   // bits this thread's elements share: tile bits 0-7, bits above the tile
 #pragma unroll
   for (int lb = 0; lb < 8; ++lb) {
     const bool a = (t >> lb) & 1;
     Tp[lb] = T + (t ^ (1 << lb));
     sg[lb] = a ? cf.gim[lb] : -cf.gim[lb];
-    dthr += a ? 0.0 : (cf.d[lb] + __ldg(ch + lb));
+    dthr += a ? (treal)0 : (cf.d[lb] + (treal)__ldg(ch + lb));
   }
-  double d8[4];
+  treal d8[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) d8[k] = cf.d[8 + k] + __ldg(ch + 8 + k);
-  for (int gb = TB; gb < nq; ++gb) dthr += ((tile >> (gb - TB)) & 1) ? 0.0 : cf.d[gb];
+  for (int k = 0; k < 4; ++k) d8[k] = cf.d[8 + k] + (treal)__ldg(ch + 8 + k);
+  for (int gb = TB; gb < nq; ++gb) dthr += ((tile >> (gb - TB)) & 1) ? (treal)0 : cf.d[gb];
   const double* dg_ptr = P.diag + t;
   const unsigned long long pol = l2_policy(P.pol_st);
   tile_sync<NBAR>();
@@ -158,8 +213,8 @@ __device__ __forceinline__ void a_tile_flips(const StreamParams& P, const Stream
   // ---- out = kappa * ( (Dint + detuning diagonal) Y + low-bit flips )
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
-    const double dg = __ldg(dg_ptr + NT * i);
-    cplx h{0.0, 0.0};
+    const treal dg = (treal)__ldg(dg_ptr + NT * i);
+    tcplx h{0.0, 0.0};
 #pragma unroll
     for (int lb = 0; lb < 8; ++lb) flip_acc<REAL>(h, cf.gre[lb], sg[lb], Tp[lb][NT * i]);
 #pragma unroll
@@ -167,11 +222,11 @@ __device__ __forceinline__ void a_tile_flips(const StreamParams& P, const Stream
       const bool a = (i >> k) & 1;
       flip_acc<REAL>(h, cf.gre[8 + k], a ? cf.gim[8 + k] : -cf.gim[8 + k], Tt[NT * (i ^ (1 << k))]);
     }
-    double dd = dthr + dg;
+    treal dd = dthr + dg;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
       if (!((i >> k) & 1)) dd += d8[k];
-    const cplx own = Tt[NT * i];
+    const tcplx own = Tt[NT * i];
     h.re = fma(dd, own.re, h.re);
     h.im = fma(dd, own.im, h.im);
     st_pol(P.out + base + t + NT * i, cf.kappa * h, pol);
@@ -179,7 +234,7 @@ __device__ __forceinline__ void a_tile_flips(const StreamParams& P, const Stream
 }
 
 template <bool REAL, bool AUX>
-__device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t lin_tile) {
+__device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& cf, tcplx* T, size_t lin_tile) {
   const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
   const size_t tile = lin_tile % tiles_per_vec;
@@ -188,15 +243,14 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
   // ---- plain application (one input, weight 1, nothing to materialise): the tile goes straight to shared
   // memory with 16 asynchronous 16-byte copies per thread in flight -- one memory latency instead of four
   // rounds of register loads
-  if (!AUX && P.n_in == 1 && P.w[0] == 1.0 && P.ymat == nullptr) {
+  if (!AUX && P.n_in == 1 && P.w[0] == (treal)1 && P.ymat == nullptr) {
     // (no L2 cache hint here: with the three-way policy select feeding these copies ptxas 12.9 emitted LDGSTS
     // reading uniform registers it had not set -- "illegal instruction" at run time; the input of a plain
     // application wants the normal policy anyway, the group tiles read it again)
-    const cplx* v0 = P.v[0] + base + t;
+    const tcplx* v0 = P.v[0] + base + t;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(T + t + NT * i);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(v0 + NT * i) : "memory");
+      cp_async_amp(T + t + NT * i, v0 + NT * i);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -209,19 +263,19 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
   const unsigned long long pol = l2_policy(P.pol_st), pol_in = l2_policy(P.pol_in);
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += QP) {
-    cplx y[QP], z[QP];
+    tcplx y[QP], z[QP];
 #pragma unroll
     for (int i = 0; i < QP; ++i) { y[i] = {0.0, 0.0}; z[i] = {0.0, 0.0}; }
     for (int j = 0; j < P.n_in; j += 2) {
       const bool two = j + 1 < P.n_in;               // uniform
-      const cplx* v0 = P.v[j] + base;
-      const double w0 = P.w[j];
-      cplx x0[QP], x1[QP];
+      const tcplx* v0 = P.v[j] + base;
+      const treal w0 = P.w[j];
+      tcplx x0[QP], x1[QP];
 #pragma unroll
       for (int i = 0; i < QP; ++i) x0[i] = ld_pol(v0 + t + NT * (q0 + i), pol_in);
       if (two) {
-        const cplx* v1 = P.v[j + 1] + base;
-        const double w1 = P.w[j + 1];
+        const tcplx* v1 = P.v[j + 1] + base;
+        const treal w1 = P.w[j + 1];
 #pragma unroll
         for (int i = 0; i < QP; ++i) x1[i] = ld_pol(v1 + t + NT * (q0 + i), pol_in);
 #pragma unroll
@@ -229,7 +283,7 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
           y[i].re = fma(w1, x1[i].re, y[i].re); y[i].im = fma(w1, x1[i].im, y[i].im);
         }
         if (want_aux) {
-          const double u1 = P.w2[j + 1];
+          const treal u1 = P.w2[j + 1];
 #pragma unroll
           for (int i = 0; i < QP; ++i) {
             z[i].re = fma(u1, x1[i].re, z[i].re); z[i].im = fma(u1, x1[i].im, z[i].im);
@@ -241,7 +295,7 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
         y[i].re = fma(w0, x0[i].re, y[i].re); y[i].im = fma(w0, x0[i].im, y[i].im);
       }
       if (want_aux) {
-        const double u0 = P.w2[j];
+        const treal u0 = P.w2[j];
 #pragma unroll
         for (int i = 0; i < QP; ++i) {
           z[i].re = fma(u0, x0[i].re, z[i].re); z[i].im = fma(u0, x0[i].im, z[i].im);
@@ -259,10 +313,10 @@ __device__ __forceinline__ void a_tile(const StreamParams& P, const StreamCoef& 
 }
 
 template <bool REAL, bool AUX>
-__global__ void __launch_bounds__(NT, REAL ? 3 : 2)
+__global__ void __launch_bounds__(NT, REAL ? kMinCtas : 2)
 k_stream_a(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  a_tile<REAL, AUX>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
+  a_tile<REAL, AUX>(P, cf, reinterpret_cast<tcplx*>(smem_raw), blockIdx.x);
 }
 
 // ---- group tile: strided tile (2^nb rows x 2^C columns), out += kappa * H_g Ymat ------------------------
@@ -278,7 +332,7 @@ __device__ __forceinline__ size_t gindex(const StreamParams& P, size_t tile, int
 }
 
 template <bool REAL, int NBAR>
-__device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& cf, cplx* T, size_t lin_tile) {
+__device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& cf, tcplx* T, size_t lin_tile) {
   const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
   const size_t tile = lin_tile % tiles_per_vec;
@@ -286,25 +340,24 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
   const int C = P.C;
   const size_t g0 = boff + gindex(P, tile, t);
   const size_t stride = (size_t)1 << (P.lo + 8 - C);
-  const cplx* ym = P.v[0] + g0;
-  cplx* out = P.out + g0;
+  const tcplx* ym = P.v[0] + g0;
+  tcplx* out = P.out + g0;
   const unsigned long long pol_ld = l2_policy(P.pol_ld), pol_st = l2_policy(P.pol_st);
 
   // Ymat tile -> shared memory with 16-byte asynchronous copies (LDGSTS): 16 in flight per thread, no
   // registers; the first round of the partial result is fetched while they land
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(T + t + NT * i);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(ym + (size_t)i * stride), "l"(pol_ld) : "memory");
+    cp_async_amp_pol(T + t + NT * i, ym + (size_t)i * stride, pol_ld);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  const cplx* Tt = T + t;
+  const tcplx* Tt = T + t;
   const int n_cross = 8 - C;                       // 0..4 row bits that live in t
   const int p8 = P.lo + n_cross;                   // global bit position of tile bit 8
-  double gre8[4], gim8[4];
+  treal gre8[4], gim8[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) { gre8[k] = cf.gre[p8 + k]; gim8[k] = cf.gim[p8 + k]; }
-  cplx nxt[4];
+  tcplx nxt[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) nxt[j] = ld_pol(out + (size_t)j * stride, pol_ld);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -312,7 +365,7 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
   double err_acc = 0.0;
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += 4) {
-    cplx acc[4], h[4];
+    tcplx acc[4], h[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       acc[j] = nxt[j];
@@ -325,9 +378,9 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
     for (int b = 0; b < n_cross; ++b) {
       const int lb = C + b;
       const bool a = (t >> lb) & 1;
-      const cplx* Tq = T + (t ^ (1 << lb));
-      const double gr = cf.gre[P.lo + b];
-      const double s = a ? cf.gim[P.lo + b] : -cf.gim[P.lo + b];
+      const tcplx* Tq = T + (t ^ (1 << lb));
+      const treal gr = cf.gre[P.lo + b];
+      const treal s = a ? cf.gim[P.lo + b] : -cf.gim[P.lo + b];
 #pragma unroll
       for (int j = 0; j < 4; ++j) flip_acc<REAL>(h[j], gr, s, Tq[NT * (q0 + j)]);
     }
@@ -347,14 +400,14 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const size_t gi = g0 + (size_t)(q0 + j) * stride;
-        const cplx ep = ldcs(P.aux + gi);
-        const cplx y0 = ldcs(P.y0 + gi);
-        const cplx y1 = Tt[NT * (q0 + j)];
+        const tcplx ep = ldcs(P.aux + gi);
+        const tcplx y0 = ldcs(P.y0 + gi);
+        const tcplx y1 = Tt[NT * (q0 + j)];
         // |err / (atol + rtol max(|y0|, |y1|))|^2 with one square root and one division (amplitudes are <= 1:
         // the squares neither overflow nor matter when they underflow)
-        const double m2 = fmax(fma(y0.re, y0.re, y0.im * y0.im), fma(y1.re, y1.re, y1.im * y1.im));
+        const double m2 = (double)fmax(fma(y0.re, y0.re, y0.im * y0.im), fma(y1.re, y1.re, y1.im * y1.im));
         const double sc = fma(P.rtol, sqrt(m2), P.atol);
-        const double er = fma(P.werr, acc[j].re, ep.re), ei = fma(P.werr, acc[j].im, ep.im);
+        const double er = fma(P.werr, (double)acc[j].re, (double)ep.re), ei = fma(P.werr, (double)acc[j].im, (double)ep.im);
         err_acc += fma(er, er, ei * ei) / (sc * sc);
       }
     }
@@ -374,10 +427,10 @@ __device__ __forceinline__ void g_tile(const StreamParams& P, const StreamCoef& 
 }
 
 template <bool REAL>
-__global__ void __launch_bounds__(NT, REAL ? 3 : 2)
+__global__ void __launch_bounds__(NT, REAL ? kMinCtas : 2)
 k_stream_g(const __grid_constant__ StreamParams P, const __grid_constant__ StreamCoef cf) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  g_tile<REAL, 0>(P, cf, reinterpret_cast<cplx*>(smem_raw), blockIdx.x);
+  g_tile<REAL, 0>(P, cf, reinterpret_cast<tcplx*>(smem_raw), blockIdx.x);
 }
 
 // ---- dataflow launch: A tiles and the first group's tiles, chunk by chunk through L2 --------------------
@@ -401,11 +454,11 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 
 template <bool REAL, bool AUX>
-__global__ void __launch_bounds__(NT, REAL ? 3 : 2)
+__global__ void __launch_bounds__(NT, REAL ? kMinCtas : 2)
 k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ StreamParams PG,
             const __grid_constant__ StreamCoef cf, const AgCtl ctl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  tcplx* T = reinterpret_cast<tcplx*>(smem_raw);
   __shared__ unsigned s_item;
   if (threadIdx.x == 0) s_item = atomicAdd(ctl.sync, 1u);
   __syncthreads();
@@ -439,6 +492,7 @@ k_stream_ag(const __grid_constant__ StreamParams PA, const __grid_constant__ Str
   }
 }
 
+#if !defined(PD_C64)   // the experimental TMA pipeline exists for complex128 only
 // ---- persistent dataflow launch with an asynchronous input pipeline (round 2) ----------------------------
 // Same work items, ticket order and chunk counters as k_stream_ag, but the CTAs are persistent (one per SM, 16
 // consumer warps + a producer warp) and warp-specialised:
@@ -464,8 +518,8 @@ constexpr int kPipeSlots = 10;
 constexpr int kItemQ = 4;
 constexpr unsigned kSlotBytes = kSub * 16;
 struct PipeShared {
-  cplx T[TILE];
-  cplx ring[kPipeSlots][kSub];
+  tcplx T[TILE];
+  tcplx ring[kPipeSlots][kSub];
   unsigned long long full[kPipeSlots], empty[kPipeSlots], item_full[kItemQ], item_empty[kItemQ];
   unsigned item_kind[kItemQ], item_tile[kItemQ];
   double red[kPipeCons / 32];
@@ -532,10 +586,10 @@ __device__ __forceinline__ PipeItem decode_item(const AgCtl& ctl, unsigned item,
 }
 
 // one ring slot -> this thread's SPT elements of sub-block `q` (waits for the copy, frees the slot)
-__device__ __forceinline__ void ring_take(PipeShared& S, unsigned& step, cplx (&x)[SPT]) {
+__device__ __forceinline__ void ring_take(PipeShared& S, unsigned& step, tcplx (&x)[SPT]) {
   const unsigned sl = step % kPipeSlots;
   mbar_wait(&S.full[sl], (step / kPipeSlots) & 1u);
-  const cplx* src = S.ring[sl] + threadIdx.x;
+  const tcplx* src = S.ring[sl] + threadIdx.x;
 #pragma unroll
   for (int ii = 0; ii < SPT; ++ii) x[ii] = src[kPipeCons * ii];
   __syncwarp();
@@ -553,14 +607,14 @@ __device__ __forceinline__ void pipe_a_item(const StreamParams& P, const StreamC
   const size_t tile = lin_tile % tiles_per_vec;
   const size_t base = (lin_tile / tiles_per_vec) * P.dim + (tile << TB);
   const unsigned long long pol = l2_policy(P.pol_st);
-  cplx y[PEPT];
+  tcplx y[PEPT];
 #pragma unroll
   for (int q = 0; q < NSUB; ++q) {
-    cplx z[SPT];
+    tcplx z[SPT];
 #pragma unroll
     for (int ii = 0; ii < SPT; ++ii) { y[SPT * q + ii] = {0.0, 0.0}; z[ii] = {0.0, 0.0}; }
     for (int j = 0; j < P.n_in; ++j) {
-      cplx x[SPT];
+      tcplx x[SPT];
       ring_take(S, step, x);
       const double w = P.w[j];
 #pragma unroll
@@ -579,8 +633,8 @@ __device__ __forceinline__ void pipe_a_item(const StreamParams& P, const StreamC
       for (int ii = 0; ii < SPT; ++ii) P.aux[base + t + kPipeCons * (SPT * q + ii)] = z[ii];
     }
   }
-  cplx* T = S.T;
-  const cplx* Tp[PXB];
+  tcplx* T = S.T;
+  const tcplx* Tp[PXB];
   double sg[PXB];
   double dthr = 0.0;          // diagonal of the bits this thread's elements share: tile bits 0-8 and the bits above the tile
 #pragma unroll
@@ -612,7 +666,7 @@ __device__ __forceinline__ void pipe_a_item(const StreamParams& P, const StreamC
   cons_sync();
 #pragma unroll
   for (int i = 0; i < PEPT; ++i) {
-    cplx h{0.0, 0.0};
+    tcplx h{0.0, 0.0};
 #pragma unroll
     for (int lb = 0; lb < PXB; ++lb) flip_acc<REAL>(h, cf.gre[lb], sg[lb], Tp[lb][kPipeCons * i]);
 #pragma unroll
@@ -644,32 +698,32 @@ __device__ __forceinline__ void pipe_g_item(const StreamParams& P, const StreamC
   const int C = P.C;
   const size_t g0 = boff + gindex(P, tile, t);
   const size_t stride = (size_t)1 << (P.lo + PXB - C);
-  cplx* out = P.out + g0;
+  tcplx* out = P.out + g0;
   const unsigned long long pol_st = l2_policy(P.pol_st);
-  cplx y[PEPT];
+  tcplx y[PEPT];
   const bool ring = P.via_ring != 0;                 // uniform
   if (ring) {
 #pragma unroll
     for (int q = 0; q < NSUB; ++q) {
-      cplx x[SPT];
+      tcplx x[SPT];
       ring_take(S, step, x);
 #pragma unroll
       for (int ii = 0; ii < SPT; ++ii) y[SPT * q + ii] = x[ii];
     }
   } else {
     const unsigned long long pol_ld = l2_policy(P.pol_ld);
-    const cplx* ym = P.v[0] + g0;
+    const tcplx* ym = P.v[0] + g0;
 #pragma unroll
     for (int i = 0; i < PEPT; ++i) y[i] = ld_pol(ym + (size_t)i * stride, pol_ld);
   }
-  cplx* T = S.T;
+  tcplx* T = S.T;
   const int n_cross = PXB - C;                       // row bits that live in t
   const int p9 = P.lo + n_cross;                     // global bit position of tile bit 9
   double gre9[PRB], gim9[PRB];
 #pragma unroll
   for (int k = 0; k < PRB; ++k) { gre9[k] = cf.gre[p9 + k]; gim9[k] = cf.gim[p9 + k]; }
   // without the ring the partial result is fetched now, so that its latency hides behind the tile exchange
-  cplx accg[PEPT];
+  tcplx accg[PEPT];
   if (!ring) {
     const unsigned long long pol_ld = l2_policy(P.pol_ld);
 #pragma unroll
@@ -682,7 +736,7 @@ __device__ __forceinline__ void pipe_g_item(const StreamParams& P, const StreamC
   double err_acc = 0.0;
 #pragma unroll
   for (int q = 0; q < NSUB; ++q) {
-    cplx acc[SPT], h[SPT];
+    tcplx acc[SPT], h[SPT];
     if (ring) ring_take(S, step, acc);
     else {
 #pragma unroll
@@ -693,7 +747,7 @@ __device__ __forceinline__ void pipe_g_item(const StreamParams& P, const StreamC
     for (int b = 0; b < n_cross; ++b) {
       const int lb = C + b;
       const bool a = (t >> lb) & 1;
-      const cplx* Tq = T + (t ^ (1 << lb));
+      const tcplx* Tq = T + (t ^ (1 << lb));
       const double gr = cf.gre[P.lo + b];
       const double sgn = a ? cf.gim[P.lo + b] : -cf.gim[P.lo + b];
 #pragma unroll
@@ -715,8 +769,8 @@ __device__ __forceinline__ void pipe_g_item(const StreamParams& P, const StreamC
       for (int ii = 0; ii < SPT; ++ii) {
         const int i = SPT * q + ii;
         const size_t gi = g0 + (size_t)i * stride;
-        const cplx ep = ldcs(P.aux + gi);
-        const cplx y0 = ldcs(P.y0 + gi);
+        const tcplx ep = ldcs(P.aux + gi);
+        const tcplx y0 = ldcs(P.y0 + gi);
         const double m2 = fmax(fma(y0.re, y0.re, y0.im * y0.im), fma(y[i].re, y[i].re, y[i].im * y[i].im));
         const double sc = fma(P.rtol, sqrt(m2), P.atol);
         const double er = fma(P.werr, acc[ii].re, ep.re), ei = fma(P.werr, acc[ii].im, ep.im);
@@ -838,10 +892,12 @@ k_stream_pipe(const __grid_constant__ StreamParams PA, const __grid_constant__ S
   }
 }
 
+#endif  // !PD_C64
+
 // SiteOps holds kappa * H per qubit (pd_common.hpp site_ops_ket): recover the Hermitian entries.  kappa is
 // 1 or +-i, so multiplying by conj(kappa) is exact.
 void fill_coef(const SiteOps& so, int nq, StreamCoef& c) {
-  c.kappa = so.kappa;
+  c.kappa = {(treal)so.kappa.re, (treal)so.kappa.im};
   const cplx kc = conj(so.kappa);
   const double k2 = so.kappa.re * so.kappa.re + so.kappa.im * so.kappa.im;
   if (k2 != 1.0) throw Error(PD_ERR_STATE, "stream kernels expect a unit-modulus generator scale");
@@ -850,9 +906,9 @@ void fill_coef(const SiteOps& so, int nq, StreamCoef& c) {
     const cplx d = kc * so.T[q * 4 + 0], g = kc * so.T[q * 4 + 2], gc = kc * so.T[q * 4 + 1];
     if (d.im != 0.0 || g.re != gc.re || g.im != -gc.im || so.T[q * 4 + 3].re != 0.0 || so.T[q * 4 + 3].im != 0.0)
       throw Error(PD_ERR_STATE, "stream kernels expect kappa * (Hermitian site operators)");
-    c.d[p] = d.re;
-    c.gre[p] = g.re;
-    c.gim[p] = g.im;
+    c.d[p] = (treal)d.re;
+    c.gre[p] = (treal)g.re;
+    c.gim[p] = (treal)g.im;
   }
 }
 bool real_drive(const StreamCoef& a, int nq) {
@@ -868,10 +924,11 @@ int current_device() {
   if (dev < 0 || dev >= 64) throw Error(PD_ERR_STATE, "device index out of range");
   return dev;
 }
+#if !defined(PD_C64)
 // 3-D view of a vector for the strided tiles of the group on bits [lo, lo + nb), in doubles (2 per amplitude):
 // dim0 = 2^(lo+1) contiguous, dim1 = 2^nb rows (stride 2^lo amplitudes), dim2 = the slabs above (and the
 // batch columns, which continue the same stride); box = one ring slot = 2^(10-C) rows x 2^C amplitudes.
-CUtensorMap make_group_map(const cplx* base, size_t dim, int batch, int lo, int nb) {
+CUtensorMap make_group_map(const tcplx* base, size_t dim, int batch, int lo, int nb) {
   using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -888,13 +945,14 @@ CUtensorMap make_group_map(const cplx* base, size_t dim, int batch, int lo, int 
   const cuuint64_t gstride[2] = {(cuuint64_t)16 << lo, (cuuint64_t)16 << (lo + nb)};
   const cuuint32_t box[3] = {(cuuint32_t)2 << C, (cuuint32_t)1 << (10 - C), 1u};
   const cuuint32_t estr[3] = {1u, 1u, 1u};
-  const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<cplx*>(base), gdim, gstride, box, estr,
+  const CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<tcplx*>(base), gdim, gstride, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw Error(PD_ERR_STATE, "cuTensorMapEncodeTiled failed for a group tile view");
   return tm;
 }
 
+#endif  // !PD_C64
 int sm_count() {
   static int n[64] = {};
   const int dev = current_device();
@@ -904,13 +962,15 @@ int sm_count() {
 void set_attrs() {
   const int dev = current_device();
   if (g_attr_set[dev]) return;
-  auto big = [](auto* f) { PD_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16)); };
+  auto big = [](auto* f) { PD_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * kAmpBytes)); };
   big(k_stream_a<false, false>); big(k_stream_a<false, true>); big(k_stream_a<true, false>); big(k_stream_a<true, true>);
   big(k_stream_ag<false, false>); big(k_stream_ag<false, true>); big(k_stream_ag<true, false>); big(k_stream_ag<true, true>);
   big(k_stream_g<false>); big(k_stream_g<true>);
+#if !defined(PD_C64)
   auto pipe_attr = [](auto* f) { PD_CUDA_CHECK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmem)); };
   pipe_attr(k_stream_pipe<false, false>); pipe_attr(k_stream_pipe<false, true>);
   pipe_attr(k_stream_pipe<true, false>); pipe_attr(k_stream_pipe<true, true>);
+#endif
   g_attr_set[dev] = true;
 }
 
@@ -937,7 +997,8 @@ unsigned env_unsigned(const char* name, unsigned dflt) {
 int fuse_mode() {
   static const int mode = [] {
     const char* e = std::getenv("PD_STREAM_FUSE");
-    return e ? (e[0] - '0') : 1;                    // 0: separate launches, 1: k_stream_ag, 2: k_stream_pipe
+    const int m = e ? (e[0] - '0') : 1;             // 0: separate launches, 1: k_stream_ag, 2: k_stream_pipe
+    return (kC64 && m == 2) ? 1 : m;                // (the pipeline is a complex128 experiment)
   }();
   return mode;
 }
@@ -969,15 +1030,15 @@ Groups make_groups(int nq) {
 }
 
 struct ErrTail {   // embedded error estimate, finished by the LAST group launch of stage 7
-  cplx* aux;
-  const cplx* y0;
+  tcplx* aux;
+  const tcplx* y0;
   double werr, atol, rtol;
   double* err_partial;
 };
 
 // One stage: out = H_A Y (A launch; Y formed from A.v / written to A.ymat) then out += H_g ysrc per group.
 // The A launch and the first group launch go out as one dataflow launch (see k_stream_ag).
-int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf, bool uni, const cplx* ysrc,
+int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf, bool uni, const tcplx* ysrc,
                  const ErrTail* tail, cudaStream_t s) {
   const size_t n_tiles = (g.dim >> TB) * (size_t)g.batch;
   const unsigned grid = (unsigned)n_tiles;
@@ -1010,7 +1071,7 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
     // the pipelined launch moves group tiles as TMA boxes: inner extent 2^(C+1) doubles <= 256, i.e. nb >= 5
     const bool pipe = fuse_mode() == 2 && gr.nb[0] >= 5;
     static const unsigned dbg = env_unsigned("PD_STREAM_DBG", 0);
-    AgCtl ctl{ag_sync_buffer(s), chunk_log2, (unsigned)n_chunks, std::max(1u, lag), mix, pipe ? (unsigned)(kPipeCons / 32) : 1u, dbg};
+    AgCtl ctl{ag_sync_buffer(s), chunk_log2, (unsigned)n_chunks, std::max(1u, lag), mix, pipe ? 16u : 1u, dbg};
     StreamParams Af = A;
     Af.pol_st = hints & 1 ? 1 : 0;                   // keep Ymat and the partial result in L2 for the group tiles
     static const unsigned plain_in = env_unsigned("PD_STREAM_PLAIN_IN", 0);
@@ -1018,6 +1079,7 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
     PD_CUDA_CHECK(cudaMemsetAsync(ctl.sync, 0, sizeof(unsigned) * (n_chunks + 1), s));
     const unsigned ag_grid = (unsigned)(2 * (n_tiles + ((size_t)ctl.lag << chunk_log2)));
     const bool aux = A.aux != nullptr;
+#if !defined(PD_C64)
     if (pipe) {
       const unsigned pgrid = (unsigned)std::min<size_t>((size_t)sm_count(), n_tiles);
       // Group tiles of the dataflow launch read what A tiles of the SAME launch wrote a moment earlier.  Moving
@@ -1031,8 +1093,10 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
       auto go = [&](auto* f) { f<<<pgrid, kPipeThreads, kPipeSmem, s>>>(Af, B[0], cf, ctl, ag_grid, tm_y, tm_out); };
       if (uni) { if (aux) go(k_stream_pipe<true, true>); else go(k_stream_pipe<true, false>); }
       else { if (aux) go(k_stream_pipe<false, true>); else go(k_stream_pipe<false, false>); }
-    } else {
-      auto go = [&](auto* f) { f<<<ag_grid, NT, TILE * 16, s>>>(Af, B[0], cf, ctl); };
+    } else
+#endif
+    {
+      auto go = [&](auto* f) { f<<<ag_grid, NT, TILE * kAmpBytes, s>>>(Af, B[0], cf, ctl); };
       if (uni) { if (aux) go(k_stream_ag<true, true>); else go(k_stream_ag<true, false>); }
       else { if (aux) go(k_stream_ag<false, true>); else go(k_stream_ag<false, false>); }
     }
@@ -1042,7 +1106,7 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
     const bool aux = A.aux != nullptr;
     StreamParams An = A;
     An.pol_in = 2;
-    auto go = [&](auto* f) { f<<<grid, NT, TILE * 16, s>>>(An, cf); };
+    auto go = [&](auto* f) { f<<<grid, NT, TILE * kAmpBytes, s>>>(An, cf); };
     if (uni) { if (aux) go(k_stream_a<true, true>); else go(k_stream_a<true, false>); }
     else { if (aux) go(k_stream_a<false, true>); else go(k_stream_a<false, false>); }
     n = 1;
@@ -1051,6 +1115,7 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
   // persistent pipeline (every ticket is a group item; PD_STREAM_GPIPE=0 keeps the plain kernel)
   static const unsigned gpipe = env_unsigned("PD_STREAM_GPIPE", 1);
   for (int gi = first; gi < gr.G; ++gi) {
+#if !defined(PD_C64)
     if (gpipe && fuse_mode() == 2 && gr.nb[gi] >= 5 && n_tiles >= 2 * (size_t)sm_count()) {
       AgCtl gctl{ag_sync_buffer(s), 0u, 0u, 0u, 0u, 0u, 0u};   // chunk = 1 tile, no A items, nothing to wait for
       PD_CUDA_CHECK(cudaMemsetAsync(gctl.sync, 0, sizeof(unsigned) * 2, s));
@@ -1060,8 +1125,10 @@ int launch_stage(const Geometry& g, const StreamParams& A, const StreamCoef& cf,
       const unsigned total = (unsigned)(2 * n_tiles);
       if (uni) k_stream_pipe<true, false><<<pgrid, kPipeThreads, kPipeSmem, s>>>(B[gi], B[gi], cf, gctl, total, tm_y, tm_out);
       else k_stream_pipe<false, false><<<pgrid, kPipeThreads, kPipeSmem, s>>>(B[gi], B[gi], cf, gctl, total, tm_y, tm_out);
-    } else if (uni) k_stream_g<true><<<grid, NT, TILE * 16, s>>>(B[gi], cf);
-    else k_stream_g<false><<<grid, NT, TILE * 16, s>>>(B[gi], cf);
+    } else
+#endif
+    if (uni) k_stream_g<true><<<grid, NT, TILE * kAmpBytes, s>>>(B[gi], cf);
+    else k_stream_g<false><<<grid, NT, TILE * kAmpBytes, s>>>(B[gi], cf);
     ++n;
   }
   return n;
@@ -1078,8 +1145,11 @@ bool stream_ket_supported(const Geometry& g) {
 }
 
 // out = G (sum_j w_j in_j); ymat receives the combined input (required: the group launches read it).
-int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, const cplx* const* ins,
+int launch_stream_stage_ket(const Geometry& g, amp_t* out_, amp_t* ymat_, int n_in, const amp_t* const* ins_,
                             const double* w, const SiteOps& so, cudaStream_t s) {
+  tcplx* out = tc(out_);
+  tcplx* ymat = tc(ymat_);
+  const tcplx* const* ins = reinterpret_cast<const tcplx* const*>(ins_);
   if (n_in > kMaxIn) throw Error(PD_ERR_INVALID, "stream stage takes at most 8 inputs");
   set_attrs();
   StreamCoef cf;
@@ -1087,11 +1157,11 @@ int launch_stream_stage_ket(const Geometry& g, cplx* out, cplx* ymat, int n_in, 
   const bool uni = real_drive(cf, g.nq);
   // a plain application (one input, weight 1) needs no materialised combination
   const bool plain = n_in == 1 && w[0] == 1.0 && ymat == nullptr;
-  const cplx* ysrc = plain ? ins[0] : ymat;
+  const tcplx* ysrc = plain ? ins[0] : ymat;
   if (!plain && ymat == nullptr) throw Error(PD_ERR_STATE, "stream stage needs a buffer for the combined input");
   StreamParams A{};
   A.nq = g.nq; A.dim = g.dim; A.n_in = n_in; A.diag = g.diag_parts; A.ymat = plain ? nullptr : ymat; A.out = out;
-  for (int j = 0; j < n_in; ++j) { A.v[j] = ins[j]; A.w[j] = w[j]; }
+  for (int j = 0; j < n_in; ++j) { A.v[j] = ins[j]; A.w[j] = (treal)w[j]; }
   const int n = launch_stage(g, A, cf, uni, ysrc, nullptr, s);
   PD_CUDA_CHECK(cudaGetLastError());
   return n;
@@ -1131,23 +1201,23 @@ constexpr int kCG = 2 * kMaxGroupBits;   // per-CTA partial sums of a group laun
 struct CorrParams {
   int nq, lo, nb, C, n_in;
   size_t dim;
-  const cplx* v[kMaxIn];
-  double w[kMaxIn];
-  cplx* ymat;              // contiguous launch: combined stage input written here (nullable)
-  const cplx* ysrc;        // group launches
-  const cplx* kbar;
+  const tcplx* v[kMaxIn];
+  treal w[kMaxIn];
+  tcplx* ymat;              // contiguous launch: combined stage input written here (nullable)
+  const tcplx* ysrc;        // group launches
+  const tcplx* kbar;
   double* wacc;            // [2^nq] += wscale * Im(conj(kbar) y)   (nullable; contiguous launch)
   double wscale;
   double* partial;         // [gridDim.x][kCA or kCG]
 };
 
-template <int R>
-__device__ __forceinline__ void corr_block_reduce(double (&acc)[R], double* partial) {
+template <int R, class AccT>
+__device__ __forceinline__ void corr_block_reduce(AccT (&acc)[R], double* partial) {
   __shared__ double sh[NT / 32][R];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    double v = acc[r];
+    double v = (double)acc[r];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) sh[warp][r] = v;
@@ -1167,7 +1237,7 @@ __device__ __forceinline__ void corr_block_reduce(double (&acc)[R], double* part
 // straight into the two accumulators (ga += Im(conj(kb) y'), gb_raw += Re(conj(kb) y')).
 __global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__ CorrParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  tcplx* T = reinterpret_cast<tcplx*>(smem_raw);
   const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
   const size_t tile = blockIdx.x % tiles_per_vec;
@@ -1175,13 +1245,13 @@ __global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__
   constexpr int QP = 4;
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += QP) {
-    cplx y[QP];
+    tcplx y[QP];
 #pragma unroll
     for (int i = 0; i < QP; ++i) y[i] = {0.0, 0.0};
     for (int j = 0; j < P.n_in; ++j) {
-      const cplx* vj = P.v[j] + base;
-      const double wj = P.w[j];
-      cplx x[QP];
+      const tcplx* vj = P.v[j] + base;
+      const treal wj = P.w[j];
+      tcplx x[QP];
 #pragma unroll
       for (int i = 0; i < QP; ++i) x[i] = ldcs(vj + t + NT * (q0 + i));
 #pragma unroll
@@ -1193,51 +1263,51 @@ __global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__
       if (P.ymat) P.ymat[base + t + NT * (q0 + i)] = y[i];
     }
   }
-  const cplx* Tt = T + t;
-  const cplx* Tp[8];
+  const tcplx* Tt = T + t;
+  const tcplx* Tp[8];
 #pragma unroll
   for (int lb = 0; lb < 8; ++lb) Tp[lb] = T + (t ^ (1 << lb));
   __syncthreads();
-  double ga[TB], gb[TB], self_lo[4] = {0.0, 0.0, 0.0, 0.0}, self_all = 0.0;
+  treal ga[TB], gb[TB], self_lo[4] = {0, 0, 0, 0}, self_all = 0;
 #pragma unroll
-  for (int lb = 0; lb < TB; ++lb) { ga[lb] = 0.0; gb[lb] = 0.0; }
+  for (int lb = 0; lb < TB; ++lb) { ga[lb] = 0; gb[lb] = 0; }
   // four elements at a time (i = 4 io + ii): bounds the loads in flight / registers; tile bits 8, 9 are
   // compile-time inside the group, bits 10, 11 are uniform per group
 #pragma unroll 1
   for (int io = 0; io < 4; ++io) {
-    cplx kb4[4];
+    tcplx kb4[4];
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) kb4[ii] = ldcs(P.kbar + base + t + NT * (4 * io + ii));
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
       const int i = 4 * io + ii;
-      const cplx kbv = kb4[ii];                                // conj(kbar) = (kbv.re, -kbv.im)
-      const cplx own = Tt[NT * i];
-      const double self_im = fma(kbv.re, own.im, -kbv.im * own.re);
+      const tcplx kbv = kb4[ii];                                // conj(kbar) = (kbv.re, -kbv.im)
+      const tcplx own = Tt[NT * i];
+      const treal self_im = fma(kbv.re, own.im, -kbv.im * own.re);
       self_all += self_im;
-      if (P.wacc) atomicAdd(P.wacc + (tile << TB) + t + NT * i, P.wscale * self_im);
+      if (P.wacc) atomicAdd(P.wacc + (tile << TB) + t + NT * i, P.wscale * (double)self_im);
 #pragma unroll
       for (int lb = 0; lb < 8; ++lb) {
-        const cplx pv = Tp[lb][NT * i];
+        const tcplx pv = Tp[lb][NT * i];
         ga[lb] = fma(kbv.re, pv.im, fma(-kbv.im, pv.re, ga[lb]));
         gb[lb] = fma(kbv.re, pv.re, fma(kbv.im, pv.im, gb[lb]));
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const bool a = k < 2 ? ((ii >> k) & 1) : ((io >> (k - 2)) & 1);
-        const cplx pv = Tt[NT * (i ^ (1 << k))];
-        const double re = fma(kbv.re, pv.re, kbv.im * pv.im);
+        const tcplx pv = Tt[NT * (i ^ (1 << k))];
+        const treal re = fma(kbv.re, pv.re, kbv.im * pv.im);
         ga[8 + k] = fma(kbv.re, pv.im, fma(-kbv.im, pv.re, ga[8 + k]));
         gb[8 + k] += a ? re : -re;
-        self_lo[k] += a ? 0.0 : self_im;
+        self_lo[k] += a ? (treal)0 : self_im;
       }
     }
   }
-  double acc[kCA];
+  treal acc[kCA];
 #pragma unroll
   for (int lb = 0; lb < 8; ++lb) {
     const bool a = (t >> lb) & 1;
-    acc[lb * 3 + 0] = a ? 0.0 : self_all;
+    acc[lb * 3 + 0] = a ? (treal)0 : self_all;
     acc[lb * 3 + 1] = ga[lb];
     acc[lb * 3 + 2] = a ? gb[lb] : -gb[lb];
   }
@@ -1262,7 +1332,7 @@ __device__ __forceinline__ size_t cindex(const CorrParams& P, size_t tile, int e
 // (runtime count 8 - C <= 4), row bits 8-11 in i.
 __global__ void __launch_bounds__(NT, 2) k_stream_corr_g(const __grid_constant__ CorrParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  cplx* T = reinterpret_cast<cplx*>(smem_raw);
+  tcplx* T = reinterpret_cast<tcplx*>(smem_raw);
   const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
   const size_t tile = blockIdx.x % tiles_per_vec;
@@ -1272,26 +1342,25 @@ __global__ void __launch_bounds__(NT, 2) k_stream_corr_g(const __grid_constant__
   const size_t stride = (size_t)1 << (P.lo + 8 - C);
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(T + t + NT * i);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(P.ysrc + g0 + (size_t)i * stride) : "memory");
+    cp_async_amp(T + t + NT * i, P.ysrc + g0 + (size_t)i * stride);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
-  cplx kb[EPT];
+  tcplx kb[EPT];
 #pragma unroll
   for (int i = 0; i < EPT; ++i) kb[i] = ldcs(P.kbar + g0 + (size_t)i * stride);
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
-  const cplx* Tt = T + t;
+  const tcplx* Tt = T + t;
   const int n_cross = 8 - C;
-  double acc[kCG];
+  treal acc[kCG];
 #pragma unroll
-  for (int r = 0; r < kCG; ++r) acc[r] = 0.0;
+  for (int r = 0; r < kCG; ++r) acc[r] = 0;
   for (int b = 0; b < n_cross; ++b) {
-    const cplx* Tq = T + (t ^ (1 << (C + b)));
-    double a_im = 0.0, a_re = 0.0;
+    const tcplx* Tq = T + (t ^ (1 << (C + b)));
+    treal a_im = 0, a_re = 0;
 #pragma unroll
     for (int i = 0; i < EPT; ++i) {
-      const cplx pv = Tq[NT * i];
+      const tcplx pv = Tq[NT * i];
       a_im = fma(kb[i].re, pv.im, fma(-kb[i].im, pv.re, a_im));
       a_re = fma(kb[i].re, pv.re, fma(kb[i].im, pv.im, a_re));
     }
@@ -1302,13 +1371,13 @@ __global__ void __launch_bounds__(NT, 2) k_stream_corr_g(const __grid_constant__
       if (bb == b) { acc[bb * 2 + 0] = a_im; acc[bb * 2 + 1] = a ? a_re : -a_re; }
   }
   // tile bits 8-11 are group bits n_cross .. n_cross + 3
-  double ga8[4] = {0.0, 0.0, 0.0, 0.0}, gb8[4] = {0.0, 0.0, 0.0, 0.0};
+  treal ga8[4] = {0, 0, 0, 0}, gb8[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int i = 0; i < EPT; ++i) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const cplx pv = Tt[NT * (i ^ (1 << k))];
-      const double re = fma(kb[i].re, pv.re, kb[i].im * pv.im);
+      const tcplx pv = Tt[NT * (i ^ (1 << k))];
+      const treal re = fma(kb[i].re, pv.re, kb[i].im * pv.im);
       ga8[k] = fma(kb[i].re, pv.im, fma(-kb[i].im, pv.re, ga8[k]));
       gb8[k] += ((i >> k) & 1) ? re : -re;
     }
@@ -1379,14 +1448,17 @@ __global__ void __launch_bounds__(256) k_stream_corr_final(const __grid_constant
 
 // Site correlations of kbar with the stage input y = sum_j w_j in_j (ymat: buffer for y, required unless the
 // input is plain).  d_corr (nullable): [nq][4] complex; d_wacc (nullable): [2^nq] += wscale * Im(conj(kbar) y).
-int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar, int n_in,
-                       const cplx* const* ins, const double* w, cplx* ymat, cudaStream_t s) {
+int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const amp_t* kbar_, int n_in,
+                       const amp_t* const* ins_, const double* w, amp_t* ymat_, cudaStream_t s) {
+  const tcplx* kbar = tc(kbar_);
+  tcplx* ymat = tc(ymat_);
+  const tcplx* const* ins = reinterpret_cast<const tcplx* const*>(ins_);
   if (n_in > kMaxIn) throw Error(PD_ERR_INVALID, "stream corr takes at most 8 inputs");
   static bool attr_set[64] = {};
   const int dev = current_device();
   if (!attr_set[dev]) {
-    PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_a, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
-    PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_g, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * 16));
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_a, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * kAmpBytes));
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_g, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * kAmpBytes));
     attr_set[dev] = true;
   }
   const unsigned grid = (unsigned)((g.dim >> TB) * (size_t)g.batch);
@@ -1403,13 +1475,13 @@ int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double w
   }
   double* d_part = parts[dev];
   const bool plain = n_in == 1 && w[0] == 1.0;
-  const cplx* ysrc = plain ? ins[0] : ymat;
+  const tcplx* ysrc = plain ? ins[0] : ymat;
   if (!plain && G > 0 && ymat == nullptr) throw Error(PD_ERR_STATE, "stream corr needs a buffer for the stage input");
   CorrParams A{};
   A.nq = g.nq; A.dim = g.dim; A.n_in = n_in; A.kbar = kbar; A.wacc = d_wacc; A.wscale = wscale; A.partial = d_part;
-  for (int j = 0; j < n_in; ++j) { A.v[j] = ins[j]; A.w[j] = w[j]; }
+  for (int j = 0; j < n_in; ++j) { A.v[j] = ins[j]; A.w[j] = (treal)w[j]; }
   A.ymat = (plain || G == 0) ? nullptr : ymat;
-  k_stream_corr_a<<<grid, NT, TILE * 16, s>>>(A);
+  k_stream_corr_a<<<grid, NT, TILE * kAmpBytes, s>>>(A);
   int n = 1;
   if (d_corr) {
     CorrFinal F{};
@@ -1421,7 +1493,7 @@ int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double w
       CorrParams B{};
       B.nq = g.nq; B.dim = g.dim; B.ysrc = ysrc; B.kbar = kbar; B.lo = lo; B.nb = nb; B.C = TB - nb;
       B.partial = d_part + (size_t)grid * (kCA + (size_t)gi * kCG);
-      k_stream_corr_g<<<grid, NT, TILE * 16, s>>>(B);
+      k_stream_corr_g<<<grid, NT, TILE * kAmpBytes, s>>>(B);
       F.lo[gi] = lo; F.nb[gi] = nb; F.part_g[gi] = B.partial;
       lo += nb;
       ++n;
@@ -1439,10 +1511,15 @@ size_t stream_err_partial_count(const Geometry& g) { return (g.dim >> TB) * (siz
 // ynew = y_{n+1}, and the embedded error estimate folded into the stage-7 launches (the A launch
 // forms the partial error vector from the slopes it reads anyway, the last group launch finishes
 // it): err_out[b] = sum |err/scale|^2 per batch column.  aux: scratch vector.
-int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cplx* ynew, cplx* ymat, cplx* aux,
+int launch_stream_dp5_step(const Geometry& g, const amp_t* y_, amp_t* const* k_, amp_t* ynew_, amp_t* ymat_, amp_t* aux_,
                            const SiteOps* stage_ops /* [7], index i = stage i+1 */, const double* beta,
                            const double* ew, double dt, double atol, double rtol, double* err_partial,
                            double* err_out, cudaStream_t s) {
+  const tcplx* y = tc(y_);
+  tcplx* const* k = reinterpret_cast<tcplx* const*>(k_);
+  tcplx* ynew = tc(ynew_);
+  tcplx* ymat = tc(ymat_);
+  tcplx* aux = tc(aux_);
   set_attrs();
   int n = 0;
   for (int i = 1; i < 7; ++i) {
@@ -1450,14 +1527,14 @@ int launch_stream_dp5_step(const Geometry& g, const cplx* y, cplx* const* k, cpl
     fill_coef(stage_ops[i], g.nq, cf);
     const bool uni = real_drive(cf, g.nq);
     const bool last = i == 6;
-    cplx* ym = last ? ynew : ymat;
+    tcplx* ym = last ? ynew : ymat;
     StreamParams A{};
     A.nq = g.nq; A.dim = g.dim; A.diag = g.diag_parts; A.ymat = ym; A.out = k[i];
     int m = 0;
-    A.v[m] = y; A.w[m] = 1.0; A.w2[m] = 0.0; ++m;
+    A.v[m] = y; A.w[m] = (treal)1; A.w2[m] = (treal)0; ++m;
     for (int j = 0; j < i; ++j) {
       const double b = beta[(i - 1) * 6 + j];
-      if (b != 0.0 || (last && ew[j] != 0.0)) { A.v[m] = k[j]; A.w[m] = dt * b; A.w2[m] = last ? ew[j] : 0.0; ++m; }
+      if (b != 0.0 || (last && ew[j] != 0.0)) { A.v[m] = k[j]; A.w[m] = (treal)(dt * b); A.w2[m] = (treal)(last ? ew[j] : 0.0); ++m; }
     }
     A.n_in = m;
     A.aux = last ? aux : nullptr;

@@ -16,6 +16,13 @@
 
 Internal state layout is batch-major ``(batch, dim)``; the reference layout ``(dim, batch)``
 is converted in :mod:`pulser_diff_b200.solvers`.
+
+Precision.  State tensors are complex128 (what the reference computes in, backend.py:271, 280) or -- north_star's
+optional 1e-5 tier -- complex64: every operator here takes the precision from the dtype of the state it is given.
+complex64 states of the bandwidth-bound shapes (kets of N >= 15, every density matrix) run in the complex64
+build of the library (half the bytes per vector pass); kets of N <= 14 live in registers / L2 where nothing is
+bandwidth-bound, so they are computed by the complex128 kernels and only cast at the boundary
+(:func:`compute_dtype`).  Coefficients, times and every gradient w.r.t. them stay float64 / complex128.
 """
 from __future__ import annotations
 
@@ -57,11 +64,26 @@ def clear_plan_cache() -> None:
     _UNIT_PROGRAMS.clear()
 
 
-def get_plan(n_qubits: int, batch: int, kind: int, device: torch.device) -> Plan:
+C64_MIN_KET_QUBITS = 15     # kets below this are served by the complex128 small-register kernels
+
+
+def compute_dtype(state_dtype: torch.dtype, n_qubits: int, kind: int) -> torch.dtype:
+    """Precision the library computes in for states of ``state_dtype`` (see the module docstring)."""
+    if state_dtype == torch.complex64 and (kind == PD_DENSITY or n_qubits >= C64_MIN_KET_QUBITS):
+        return torch.complex64
+    if state_dtype in (torch.complex64, torch.complex128):
+        return torch.complex128
+    raise TypeError(f"state vectors must be complex128 or complex64, got {state_dtype}")
+
+
+def get_plan(n_qubits: int, batch: int, kind: int, device: torch.device,
+             dtype: torch.dtype = torch.complex128) -> Plan:
     device = torch.device(device)
     if device.type == "cuda" and device.index is None:
         device = torch.device("cuda", torch.cuda.current_device())
-    key = (n_qubits, batch, kind, str(device), _cabi._lib_path or _cabi.DEFAULT_LIBRARY)
+    c64 = dtype == torch.complex64
+    key = (n_qubits, batch, kind, str(device), c64,
+           _cabi._lib_paths[c64] or (_cabi.DEFAULT_LIBRARY_C64 if c64 else _cabi.DEFAULT_LIBRARY))
     plan = _PLAN_CACHE.pop(key, None)
     if plan is None:
         # bounded, least recently used first out: a plan pins its whole workspace (tens of GiB at N >= 26),
@@ -72,7 +94,7 @@ def get_plan(n_qubits: int, batch: int, kind: int, device: torch.device) -> Plan
             kept += _PLAN_CACHE[k].dim * _PLAN_CACHE[k].batch
             if kept > budget or len(_PLAN_CACHE) >= _PLAN_CACHE_MAX_PLANS:
                 del _PLAN_CACHE[k]
-        plan = Plan(n_qubits, batch, kind, device)
+        plan = Plan(n_qubits, batch, kind, device, dtype)
     _PLAN_CACHE[key] = plan          # most recently used last
     return plan
 
@@ -107,19 +129,21 @@ class _EvolveFn(torch.autograd.Function):
                 pair_u: Tensor, n_qubits: int, kind: int, dt: float, det_masks, amp_masks,
                 collapse, solver: int, opt: Options):
         batch = int(state0.shape[0])
-        plan = get_plan(n_qubits, batch, kind, state0.device)
+        cd = compute_dtype(state0.dtype, n_qubits, kind)
+        plan = get_plan(n_qubits, batch, kind, state0.device, cd)
         prog = make_program(n_qubits, kind, dt, det_masks, det_values, amp_masks, amp_values,
                             pair_u, collapse)
         configure(plan, prog)
         need = any(ctx.needs_input_grad[:5])
-        states, tape = plan.evolve_forward(solver, opt, state0.detach(), tsave, want_tape=need)
+        states, tape = plan.evolve_forward(solver, opt, state0.detach().to(cd), tsave, want_tape=need)
         ctx.plan, ctx.prog, ctx.tape = plan, prog, tape
+        ctx.state_dtype = state0.dtype
         ctx.meta = (tsave.device, tsave.dtype, det_values.device, det_values.dtype,
                     amp_values.device, amp_values.dtype, pair_u.device, pair_u.dtype,
                     tuple(det_values.shape), tuple(amp_values.shape))
         ctx.save_for_backward(states)
         ctx.set_materialize_grads(False)
-        return states
+        return states if cd == state0.dtype else states.to(state0.dtype)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -132,8 +156,10 @@ class _EvolveFn(torch.autograd.Function):
         configure(plan, prog)
         w_s0, w_ts, w_det, w_amp, w_pair = ctx.needs_input_grad[:5]
         g_det, g_amp, g_pair, g_ts, g_s0 = plan.evolve_backward(
-            ctx.tape, states, grad_states.to(torch.complex128).contiguous(),
+            ctx.tape, states, grad_states.to(plan.cdtype).contiguous(),
             want_det=w_det, want_amp=w_amp, want_pair=w_pair, want_tsave=w_ts, want_state0=w_s0)
+        if g_s0 is not None:
+            g_s0 = g_s0.to(ctx.state_dtype)
         (ts_dev, ts_dt, det_dev, det_dt, amp_dev, amp_dt, pu_dev, pu_dt, det_shape, amp_shape) = ctx.meta
         if g_ts is not None:
             g_ts = g_ts.to(device=ts_dev, dtype=ts_dt)
@@ -156,7 +182,7 @@ def evolve(state0: Tensor, tsave: Tensor, det_values: Tensor, amp_values: Tensor
            n_qubits: int, kind: int, dt: float, det_masks: Sequence[int], amp_masks: Sequence[int],
            collapse: Optional[Tensor] = None, solver: int = _cabi.SOLVER_DP5_SE,
            options: Optional[Options] = None) -> Tensor:
-    """states[k] = state at tsave[k]; shape (n_t, batch, dim), complex128, on state0's device."""
+    """states[k] = state at tsave[k]; shape (n_t, batch, dim), state0's dtype (complex128 / complex64) and device."""
     opt = options or Options()
     return _EvolveFn.apply(state0, tsave, det_values, amp_values, pair_u, int(n_qubits), int(kind),
                            float(dt), list(det_masks), list(amp_masks), collapse, int(solver), opt)
@@ -171,7 +197,8 @@ class _EvolveUnitsFn(torch.autograd.Function):
     def forward(ctx, state0: Tensor, tsave: Tensor, det_values: Tensor, amp_values: Tensor,
                 pair_u: Tensor, n_qubits: int, dt: float, det_masks, amp_masks, opt: Options):
         n_units, batch = int(state0.shape[0]), int(state0.shape[1])
-        plan = get_plan(n_qubits, batch, PD_KET, state0.device)
+        cd = compute_dtype(state0.dtype, n_qubits, PD_KET)
+        plan = get_plan(n_qubits, batch, PD_KET, state0.device, cd)
         # the plan carries the register, masks, dt and sample count; every unit brings its own tables, so
         # the plan's own are placeholders and one Program serves every call with the same structure
         # (no per-call reconfiguration, no device->host copy of a table)
@@ -188,14 +215,15 @@ class _EvolveUnitsFn(torch.autograd.Function):
             _UNIT_PROGRAMS[key] = prog
         configure(plan, prog)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
-        states, tape = plan.evolve_forward_units(opt, state0.detach(), tsave, det_values, amp_values,
+        states, tape = plan.evolve_forward_units(opt, state0.detach().to(cd), tsave, det_values, amp_values,
                                                  want_tape=need)
         ctx.plan, ctx.prog, ctx.tape = plan, prog, tape
+        ctx.state_dtype = state0.dtype
         ctx.tables = (det_values.detach(), amp_values.detach())
         ctx.meta = (det_values.device, det_values.dtype, amp_values.device, amp_values.dtype)
         ctx.save_for_backward(states)
         ctx.set_materialize_grads(False)
-        return states
+        return states if cd == state0.dtype else states.to(state0.dtype)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
@@ -207,8 +235,10 @@ class _EvolveUnitsFn(torch.autograd.Function):
         configure(ctx.plan, ctx.prog)
         dv, av = ctx.tables
         g_det, g_amp, g_s0 = ctx.plan.evolve_backward_units(
-            ctx.tape, states, grad_states.to(torch.complex128).contiguous(), dv, av,
+            ctx.tape, states, grad_states.to(ctx.plan.cdtype).contiguous(), dv, av,
             want_state0=ctx.needs_input_grad[0])
+        if g_s0 is not None:
+            g_s0 = g_s0.to(ctx.state_dtype)
         det_dev, det_dt, amp_dev, amp_dt = ctx.meta
         if g_det is not None:
             g_det = g_det.to(device=det_dev, dtype=det_dt)
@@ -256,10 +286,11 @@ def hpsi(psi: Tensor, t: float, det_values: Tensor, amp_values: Tensor, pair_u: 
          det_masks: List[int], amp_masks: List[int], dt: float) -> Tensor:
     """H(t) @ psi for psi of shape (batch, 2**N)."""
     n = int(pair_u.shape[0])
-    plan = get_plan(n, int(psi.shape[0]), PD_KET, psi.device)
+    cd = compute_dtype(psi.dtype, n, PD_KET)
+    plan = get_plan(n, int(psi.shape[0]), PD_KET, psi.device, cd)
     configure(plan, _prog_from_args(n, PD_KET, dt, det_masks, det_values, amp_masks, amp_values,
                                     pair_u, None))
-    return plan.hpsi(t, psi)
+    return plan.hpsi(t, psi.to(cd)).to(psi.dtype)
 
 
 @hpsi.register_fake
@@ -271,13 +302,16 @@ def _vjp_common(ctx, cot: Tensor, kind: int, collapse):
     """Shared reverse mode of one generator application (C ABI pd_rhs_vjp)."""
     state, det_values, amp_values, pair_u = ctx.saved_tensors
     n = int(pair_u.shape[0])
-    plan = get_plan(n, int(state.shape[0]), kind, state.device)
+    cd = compute_dtype(state.dtype, n, kind)
+    plan = get_plan(n, int(state.shape[0]), kind, state.device, cd)
     configure(plan, _prog_from_args(n, kind, ctx.dt, ctx.det_masks, det_values, ctx.amp_masks,
                                     amp_values, pair_u, collapse))
     w_state, _, w_det, w_amp, w_pair = ctx.needs_input_grad[:5]
-    g_state, g_det, g_amp, g_pair, _ = plan.rhs_vjp(ctx.t, state, cot.to(torch.complex128).contiguous(),
+    g_state, g_det, g_amp, g_pair, _ = plan.rhs_vjp(ctx.t, state.to(cd), cot.to(cd).contiguous(),
                                                     want_state=w_state, want_det=w_det, want_amp=w_amp,
                                                     want_pair=w_pair)
+    if g_state is not None:
+        g_state = g_state.to(state.dtype)
     if w_det:
         g_det = (g_det if g_det is not None else torch.zeros(det_values.shape, dtype=torch.float64))
         g_det = g_det.to(device=det_values.device, dtype=det_values.dtype)
@@ -310,10 +344,11 @@ def rhs(state: Tensor, t: float, det_values: Tensor, amp_values: Tensor, pair_u:
         collapse: Tensor, det_masks: List[int], amp_masks: List[int], dt: float, kind: int) -> Tensor:
     """-i H(t) psi (kind 0) or the Lindblad right-hand side on vec(rho) (kind 1)."""
     n = int(pair_u.shape[0])
-    plan = get_plan(n, int(state.shape[0]), kind, state.device)
+    cd = compute_dtype(state.dtype, n, kind)
+    plan = get_plan(n, int(state.shape[0]), kind, state.device, cd)
     configure(plan, _prog_from_args(n, kind, dt, det_masks, det_values, amp_masks, amp_values,
                                     pair_u, collapse))
-    return plan.hpsi(t, state, rhs=True)
+    return plan.hpsi(t, state.to(cd), rhs=True).to(state.dtype)
 
 
 @rhs.register_fake
@@ -342,11 +377,12 @@ def evolve_states(state0: Tensor, tsave: Tensor, det_values: Tensor, amp_values:
                   dt: float, kind: int, solver: int, atol: float, rtol: float) -> Tensor:
     """Forward-only evolution; returns (n_t, batch, dim)."""
     n = int(pair_u.shape[0])
-    plan = get_plan(n, int(state0.shape[0]), kind, state0.device)
+    cd = compute_dtype(state0.dtype, n, kind)
+    plan = get_plan(n, int(state0.shape[0]), kind, state0.device, cd)
     configure(plan, _prog_from_args(n, kind, dt, det_masks, det_values, amp_masks, amp_values,
                                     pair_u, collapse))
-    states, _ = plan.evolve_forward(solver, Options(atol=atol, rtol=rtol), state0, tsave, False)
-    return states
+    states, _ = plan.evolve_forward(solver, Options(atol=atol, rtol=rtol), state0.to(cd), tsave, False)
+    return states.to(state0.dtype)
 
 
 @evolve_states.register_fake
@@ -359,8 +395,9 @@ def _(state0, tsave, det_values, amp_values, pair_u, collapse, det_masks, amp_ma
 def expect_diag(states: Tensor, obs_diag: Tensor, kind: int) -> Tensor:
     """sum over batch of <psi|diag(obs)|psi> (kind 0) or tr(diag(obs) rho) (kind 1), per time."""
     n = int(obs_diag.numel()).bit_length() - 1
-    plan = get_plan(n, int(states.shape[1]), kind, states.device)
-    return plan.expect_diag(states, obs_diag)
+    cd = compute_dtype(states.dtype, n, kind)
+    plan = get_plan(n, int(states.shape[1]), kind, states.device, cd)
+    return plan.expect_diag(states.to(cd), obs_diag)
 
 
 @expect_diag.register_fake

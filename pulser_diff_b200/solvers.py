@@ -69,7 +69,7 @@ def sesolve(H, psi0: Tensor, tsave: Tensor, solver: SolverType = SolverType.DP5_
     if psi0.dim() != 2 or psi0.shape[0] != 2 ** H.n_qubits:
         raise ValueError(f"Incompatible shape of initial state. Expected ({2 ** H.n_qubits}, B), "
                          f"got {tuple(psi0.shape)}.")
-    state0 = psi0.to(device=H.device, dtype=C128).transpose(0, 1).contiguous()
+    state0 = psi0.to(device=H.device, dtype=_cabi.Options.from_dict(options).state_dtype).transpose(0, 1).contiguous()
     internal = _run(H, state0, tsave, _cabi.PD_KET, solver, options, None)
     return Result(internal.permute(0, 2, 1), internal)
 
@@ -96,7 +96,7 @@ def mesolve(H, rho0: Tensor, L, tsave: Tensor, solver: SolverType = SolverType.D
             "Hamiltonian (single-qubit structure); dense 2^N x 2^N jump operators are not "
             "applied on the device.")
     b = rho0.shape[2]
-    state0 = rho0.to(device=H.device, dtype=C128).permute(2, 0, 1).reshape(b, s * s).contiguous()
+    state0 = rho0.to(device=H.device, dtype=_cabi.Options.from_dict(options).state_dtype).permute(2, 0, 1).reshape(b, s * s).contiguous()
     internal = _run(H, state0, tsave, _cabi.PD_DENSITY, solver, options, collapse)
     n_t = internal.shape[0]
     return Result(internal.reshape(n_t, b, s, s).permute(0, 2, 3, 1), internal)

@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 EMU_DIR = os.path.join(ROOT, "tests", "emu")
 EMU_LIB = os.path.join(EMU_DIR, "libpd_emu.so")
+EMU_LIB_C64 = os.path.join(EMU_DIR, "libpd_emu_c64.so")     # same stand-in compiled with -DPD_C64
 
 
 def pytest_configure(config):
@@ -35,7 +36,7 @@ def engine_device(request, emu_library):
     from pulser_diff_b200 import _cabi, ops
     ops.clear_plan_cache()
     if request.param == "emu":
-        _cabi.use_library(emu_library)
+        _cabi.use_library(emu_library, EMU_LIB_C64)
         dev = torch.device("cpu")
     else:
         if not torch.cuda.is_available():

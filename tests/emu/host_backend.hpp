@@ -41,23 +41,23 @@ class HostBackend {
   // the small-register cooperative kernels exist only in the CUDA build
   bool small_supported(const Geometry&, const Program&) { return false; }
   bool small_units_supported(const Geometry&, const Program&) { return false; }
-  int small_lanczos(const Geometry&, const Program&, const cplx*, cplx*, int, double, int, int, double, double*,
+  int small_lanczos(const Geometry&, const Program&, const amp_t*, amp_t*, int, double, int, int, double, double*,
                     double*, double*, void*) {
     throw Error(PD_ERR_STATE, "small-register kernels need the CUDA build");
   }
-  int small_forward(const Geometry&, const Program&, const Tableau&, const pd_options&, int, const cplx*,
-                    const double*, const double*, const double*, int, cplx*,
+  int small_forward(const Geometry&, const Program&, const Tableau&, const pd_options&, int, const amp_t*,
+                    const double*, const double*, const double*, int, amp_t*,
                     std::vector<std::vector<pd_step_record>>&, bool, uint64_t*, void*) {
     throw Error(PD_ERR_STATE, "small-register kernels need the CUDA build");
   }
   int small_backward_units(const Geometry&, const Program&, const Tableau&, const std::vector<double>&, int,
-                           const double*, const double*, uint64_t, const cplx*, cplx*, double*, double*, void*) {
+                           const double*, const double*, uint64_t, const amp_t*, amp_t*, double*, double*, void*) {
     return 0;
   }
   void small_unit_counts(uint64_t, int, int* acc, int* att) { *acc = *att = -1; }
   int small_backward(const Geometry&, const Program&, const Tableau&, const std::vector<double>&, int,
                      const double*, const double*, const std::vector<std::vector<SkStepHost>>&, uint64_t,
-                     const cplx*, bool, double*, cplx*, std::vector<std::vector<double>>&, void*) {
+                     const amp_t*, bool, double*, amp_t*, std::vector<std::vector<double>>&, void*) {
     return 0;
   }
   size_t segment_budget_bytes() { return segment_budget; }
@@ -84,16 +84,16 @@ class HostBackend {
       diag[s] = acc;
     }
   }
-  int lincomb(const Geometry& g, cplx* out, int n_in, const cplx* const* ins, const double* w, void*) {
+  int lincomb(const Geometry& g, amp_t* out, int n_in, const amp_t* const* ins, const double* w, void*) {
     size_t n = g.dim * g.batch;
     for (size_t i = 0; i < n; ++i) {
       double re = 0, im = 0;
       for (int j = 0; j < n_in; ++j) { re += w[j] * ins[j][i].re; im += w[j] * ins[j][i].im; }
-      out[i] = {re, im};
+      out[i] = cplx{re, im};
     }
     return 1;
   }
-  int lincomb_c(const Geometry& g, cplx* out, int m, const cplx* basis, size_t stride, const cplx* ws, void*) {
+  int lincomb_c(const Geometry& g, amp_t* out, int m, const amp_t* basis, size_t stride, const cplx* ws, void*) {
     size_t n = g.dim * g.batch;
     for (size_t i = 0; i < n; ++i) {
       cplx acc{0, 0};
@@ -102,19 +102,19 @@ class HostBackend {
     }
     return 1;
   }
-  const cplx* combine(const Geometry& g, cplx* comb, int n_in, const cplx* const* ins, const double* w,
-                      cplx* scratch) {
+  const amp_t* combine(const Geometry& g, amp_t* comb, int n_in, const amp_t* const* ins, const double* w,
+                      amp_t* scratch) {
     if (n_in > 1 || w[0] != 1.0) {
-      cplx* dst = comb ? comb : scratch;
+      amp_t* dst = comb ? comb : scratch;
       lincomb(g, dst, n_in, ins, w, nullptr);
       return dst;
     }
-    if (comb) std::memmove(comb, ins[0], sizeof(cplx) * g.dim * g.batch);
+    if (comb) std::memmove(comb, ins[0], sizeof(amp_t) * g.dim * g.batch);
     return ins[0];
   }
-  int stage_ket(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
-                const double* w, const SiteOps& so, cplx* scratch, void*) {
-    const cplx* in = combine(g, comb, n_in, ins, w, scratch);
+  int stage_ket(const Geometry& g, amp_t* out, amp_t* comb, int n_in, const amp_t* const* ins,
+                const double* w, const SiteOps& so, amp_t* scratch, void*) {
+    const amp_t* in = combine(g, comb, n_in, ins, w, scratch);
     int nq = g.nq;
     for (size_t idx = 0; idx < g.dim * g.batch; ++idx) {
       size_t s = idx & (g.dim - 1);
@@ -128,13 +128,13 @@ class HostBackend {
     }
     return 1;
   }
-  int dp5_step_ket(const Geometry&, const cplx*, cplx* const*, cplx*, const SiteOps*, const Tableau&,
-                   const double*, double, double, double, cplx*, cplx*, double*, double*, void*) {
+  int dp5_step_ket(const Geometry&, const amp_t*, amp_t* const*, amp_t*, const SiteOps*, const Tableau&,
+                   const double*, double, double, double, amp_t*, amp_t*, double*, double*, void*) {
     return 0;   // no fused path in the stand-in: the engine falls back to stage-by-stage
   }
-  int stage_density(const Geometry& g, cplx* out, cplx* comb, int n_in, const cplx* const* ins,
-                    const double* w, const SiteOpsDensity& so, cplx* scratch, void*) {
-    const cplx* in = combine(g, comb, n_in, ins, w, scratch);
+  int stage_density(const Geometry& g, amp_t* out, amp_t* comb, int n_in, const amp_t* const* ins,
+                    const double* w, const SiteOpsDensity& so, amp_t* scratch, void*) {
+    const amp_t* in = combine(g, comb, n_in, ins, w, scratch);
     int nq = g.nq;
     size_t S = (size_t)1 << nq;
     for (size_t idx = 0; idx < g.dim * g.batch; ++idx) {
@@ -151,13 +151,13 @@ class HostBackend {
     }
     return 1;
   }
-  int scaled_sumsq(const Geometry& g, double* out, const cplx* x, const cplx* xsub, const cplx* ref,
+  int scaled_sumsq(const Geometry& g, double* out, const amp_t* x, const amp_t* xsub, const amp_t* ref,
                    double atol, double rtol, double*, void*) {
     for (int b = 0; b < g.batch; ++b) {
       double acc = 0;
       for (size_t i = 0; i < g.dim; ++i) {
         size_t k = (size_t)b * g.dim + i;
-        cplx v = xsub ? x[k] - xsub[k] : x[k];
+        cplx v = xsub ? cplx(x[k]) - cplx(xsub[k]) : cplx(x[k]);
         double sc = atol + rtol * std::hypot(ref[k].re, ref[k].im);
         acc += (v.re / sc) * (v.re / sc) + (v.im / sc) * (v.im / sc);
       }
@@ -165,8 +165,8 @@ class HostBackend {
     }
     return 1;
   }
-  int err_sumsq(const Geometry& g, double* out, const cplx* const* k, const double* ew,
-                const cplx* y0, const cplx* y1, double atol, double rtol, double*, void*) {
+  int err_sumsq(const Geometry& g, double* out, const amp_t* const* k, const double* ew,
+                const amp_t* y0, const amp_t* y1, double atol, double rtol, double*, void*) {
     for (int b = 0; b < g.batch; ++b) {
       double acc = 0;
       for (size_t i = 0; i < g.dim; ++i) {
@@ -181,8 +181,8 @@ class HostBackend {
     }
     return 1;
   }
-  int corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar,
-           const cplx* y, double*, void*) {
+  int corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const amp_t* kbar,
+           const amp_t* y, double*, void*) {
     int nq = g.nq;
     size_t S = (size_t)1 << nq;
     int per = g.kind == PD_KET ? 4 : 16;
@@ -215,17 +215,17 @@ class HostBackend {
     }
     return 1;
   }
-  int corr_combo(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const cplx* kbar, int n_in,
-                 const cplx* const* ins, const double* w, cplx* ybuf, double* scratch, void* s) {
+  int corr_combo(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, const amp_t* kbar, int n_in,
+                 const amp_t* const* ins, const double* w, amp_t* ybuf, double* scratch, void* s) {
     int n = 0;
-    const cplx* ysrc = ins[0];
+    const amp_t* ysrc = ins[0];
     if (n_in > 1 || w[0] != 1.0) {
       n += lincomb(g, ybuf, n_in, ins, w, s);
       ysrc = ybuf;
     }
     return n + corr(g, d_corr, d_wacc, wscale, kbar, ysrc, scratch, s);
   }
-  int re_dot(const Geometry& g, double* out, const cplx* a, const cplx* b, double*, void*) {
+  int re_dot(const Geometry& g, double* out, const amp_t* a, const amp_t* b, double*, void*) {
     double acc = 0;
     for (size_t i = 0; i < g.dim * g.batch; ++i) acc += a[i].re * b[i].re + a[i].im * b[i].im;
     *out = acc;
@@ -244,8 +244,8 @@ class HostBackend {
       }
     return 1;
   }
-  int sharded_accumulate(const Geometry& g, cplx* out, const cplx* psi, double shift, int n_peers,
-                         const cplx* const* peers, const cplx* coef, void*) {
+  int sharded_accumulate(const Geometry& g, amp_t* out, const amp_t* psi, double shift, int n_peers,
+                         const amp_t* const* peers, const cplx* coef, void*) {
     size_t L = g.dim * g.batch;
     for (size_t i = 0; i < L; ++i) {
       double re = out[i].re + shift * psi[i].re, im = out[i].im + shift * psi[i].im;
@@ -257,12 +257,12 @@ class HostBackend {
     }
     return 1;
   }
-  int expect_diag(const Geometry& g, const cplx* states, int n_t, const double* obs, cplx* out,
+  int expect_diag(const Geometry& g, const amp_t* states, int n_t, const double* obs, cplx* out,
                   double*, void*) {
     size_t S = (size_t)1 << g.nq;
     for (int t = 0; t < n_t; ++t) {
       cplx acc{0, 0};
-      const cplx* st = states + (size_t)t * g.dim * g.batch;
+      const amp_t* st = states + (size_t)t * g.dim * g.batch;
       for (int b = 0; b < g.batch; ++b)
         if (g.kind == PD_KET)
           for (size_t s = 0; s < g.dim; ++s) {
