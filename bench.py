@@ -147,7 +147,7 @@ def measured_peak():
 
 
 # ------------------------------------------------------------------------------------------------
-def fwd_grad_large(dev, n, n_steps, peak):
+def fwd_grad_large(dev, n, n_steps, peak, cdtype=torch.complex128):
     """Forward + adjoint-gradient wall time of n_steps fixed DP5 steps at n qubits (BASELINE metric
     "fwd+grad wall time at N qubits"), full-register global drive.  Algorithmic bytes of the adjoint of one
     step: 576 B/amplitude to recompute the stage inputs + 576 B for the six
@@ -165,7 +165,7 @@ def fwd_grad_large(dev, n, n_steps, peak):
         for j in range(i + 1, n):
             u[i, j] = C6 / (SPACING * (j - i)) ** 6
     full = (1 << n) - 1
-    psi0 = torch.zeros(1, 2 ** n, dtype=torch.complex128, device=dev)
+    psi0 = torch.zeros(1, 2 ** n, dtype=cdtype, device=dev)
     psi0[0, -1] = 1.0
     tsave = torch.tensor([0.0, 0.001 * n_steps], dtype=torch.float64)
     replay = [(0.001, False)] * (n_steps - 1) + [(0.001, True)]
@@ -189,8 +189,9 @@ def fwd_grad_large(dev, n, n_steps, peak):
         t2 = time.perf_counter()
         torch.cuda.nvtx.range_pop()
         fwd, bwd = (t1 - t0) * 1e3 / n_steps, (t2 - t1) * 1e3 / n_steps
-        amps = 2.0 ** n
+        amps = 2.0 ** n * (1.0 if cdtype == torch.complex128 else 0.5)     # bytes scale with the amplitude size
         out = {"workload": f"chain_n{n}: {n_steps} fixed DP5 steps forward + adjoint gradient w.r.t. all samples",
+               "state_dtype": str(cdtype).replace("torch.", ""),
                "fwd_ms_per_step": fwd, "adjoint_ms_per_step": bwd, "fwd_grad_ms_per_step": fwd + bwd,
                "adjoint_over_forward": bwd / fwd,
                "roofline_adjoint": {"bound": "hbm", "achieved": 1344.0 * amps / (bwd * 1e-3) / 1e9, "peak": peak,

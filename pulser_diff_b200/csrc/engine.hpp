@@ -437,6 +437,11 @@ class Engine {
     buf_sizes_.push_back({name, bytes});
     return p;
   }
+  size_t buf_bytes(const std::string& name) const {
+    for (size_t i = 0; i < bufs_.size(); ++i)
+      if (bufs_[i].first == name) return buf_sizes_[i].second;
+    return 0;
+  }
   void drop(const std::string& name) {
     for (size_t i = 0; i < bufs_.size(); ++i)
       if (bufs_[i].first == name) {
@@ -486,8 +491,12 @@ class Engine {
     return dt * std::min(0.9, std::max(o.min_factor, fac));
   }
 
-  // stages 2..(last) of one DP5 step from (t, y, k[0]); fills k[1..last-1]; ynew if last == 7
-  void dp5_stages(double t, double dt, const amp_t* y, vec* k, vec ynew, int last, void* stream) {
+  // stages 2..(last) of one DP5 step from (t, y, k[0]); fills k[1..last-1]; ynew if last == 7.
+  // ysave (nullable): ysave[i] receives the input of stage i+1, Y_i = y + dt sum_j beta_ij k_j, i = 1..5 --
+  // the launch that applies the generator forms and writes it anyway; the adjoint sweep reads it back for the
+  // site correlations instead of re-forming it from the slopes.
+  void dp5_stages(double t, double dt, const amp_t* y, vec* k, vec ynew, int last, void* stream,
+                  vec* ysave = nullptr) {
     for (int i = 1; i < last; ++i) {
       const amp_t* ins[8];
       double w[8];
@@ -497,7 +506,7 @@ class Engine {
         double b = tab.beta[i - 1][j];
         if (b != 0.0) { ins[n] = k[j]; w[n++] = dt * b; }
       }
-      stage(k[i], i == 6 ? ynew : nullptr, n, ins, w, t + dt * tab.alpha[i - 1], 0, stream);
+      stage(k[i], i == 6 ? ynew : (ysave ? ysave[i] : nullptr), n, ins, w, t + dt * tab.alpha[i - 1], 0, stream);
     }
   }
 
@@ -607,8 +616,10 @@ class Engine {
     double ms_alloc = 0, ms_recompute = 0, ms_sweep = 0;
     if (gstates) bk.d2d(lam, gstates + (size_t)(n_t - 1) * L, sizeof(amp_t) * L, stream);
     else bk.zero(lam, sizeof(amp_t) * L, stream);
-    vec k[6], yb[6];
+    vec k[6], yb[6], ys[6];
     for (int i = 0; i < 6; ++i) { k[i] = vbuf("k" + std::to_string(i)); yb[i] = vbuf("yb" + std::to_string(i)); }
+    ys[0] = nullptr;
+    for (int i = 1; i < 6; ++i) ys[i] = vbuf("ys" + std::to_string(i));
     vec kbar = vbuf("kbar"), ystage = vbuf("ystage");
     // per-slot reduction results
     size_t n_slots = n_steps * 6;
@@ -625,7 +636,10 @@ class Engine {
 
     // segment buffer for recomputed step-start states
     size_t vec_bytes = sizeof(amp_t) * L;
-    size_t cap = std::max<size_t>(1, bk.segment_budget_bytes() / vec_bytes);
+    // a third of the memory that is free or already held by this plan's segment buffers (a sweep that grew
+    // them must not shrink its own budget on the next call)
+    const size_t held = buf_bytes("seg") + buf_bytes("segk");
+    size_t cap = std::max<size_t>(1, (bk.segment_budget_bytes() + held / 3) / vec_bytes);
     auto t_setup = now();
 
     size_t hi = n_steps;  // steps [lo, hi) belong to the interval being processed
@@ -652,28 +666,34 @@ class Engine {
             ysrc = ycur;
           }
           bk.d2d(seg, ysrc, vec_bytes, stream);
-          // Spare segment budget keeps the slopes of the recomputation pass (6 vectors per step) for
-          // as many steps as fit, so the sweep does not recompute them.  Allocating that cache costs
+          // Spare segment budget keeps the slopes and stage inputs of the recomputation pass (6 + 5 vectors per
+          // step) for as many steps as fit, so the sweep does not recompute them.  Allocating that cache costs
           // more than one sweep saves (cudaMalloc ~50 ms/GiB against ~3 ms/GiB of recomputation), so
           // it is only set up once a plan is differentiated repeatedly (optimisation loops).
-          const size_t nk = (n_backward_ >= 1 && cap > cn) ? std::min(cn - 1, (cap - cn) / 6) : 0;
-          vec segk = nk ? (vec)buf("segk", vec_bytes * 6 * nk) : nullptr;
+          constexpr size_t kPerStep = 11;
+          const size_t nk = (n_backward_ >= 1 && cap > cn) ? std::min(cn - 1, (cap - cn) / kPerStep) : 0;
+          vec segk = nk ? (vec)buf("segk", vec_bytes * kPerStep * nk) : nullptr;
+          auto cache_ptrs = [&](size_t s, vec* ks, vec* yss) {
+            for (int i = 0; i < 6; ++i) ks[i] = s < nk ? segk + (s * kPerStep + i) * L : k[i];
+            yss[0] = nullptr;
+            for (int i = 1; i < 6; ++i) yss[i] = s < nk ? segk + (s * kPerStep + 5 + i) * L : ys[i];
+          };
           auto t1 = now();
           ms_alloc += ms(t0, t1);
           for (size_t s = 0; s + 1 < cn; ++s) {
             const AcceptedStep& st = tape.steps[lo + c_lo + s];
-            vec ks[6];
-            for (int i = 0; i < 6; ++i) ks[i] = s < nk ? segk + (s * 6 + i) * L : k[i];
-            advance(seg + s * L, seg + (s + 1) * L, st, ks, stream);
+            vec ks[6], yss[6];
+            cache_ptrs(s, ks, yss);
+            advance(seg + s * L, seg + (s + 1) * L, st, ks, stream, s < nk ? yss : nullptr);
           }
           auto t2 = now();
           ms_recompute += ms(t1, t2);
           for (size_t s = cn; s-- > 0;) {
             size_t gi = lo + c_lo + s;
             const bool cached = s < nk;
-            vec ks[6];
-            for (int i = 0; i < 6; ++i) ks[i] = cached ? segk + (s * 6 + i) * L : k[i];
-            adjoint_step(tape.steps[gi], (int)gi, seg + s * L, lam, ks, yb, kbar, ystage, d_corr,
+            vec ks[6], yss[6];
+            cache_ptrs(s, ks, yss);
+            adjoint_step(tape.steps[gi], (int)gi, seg + s * L, lam, ks, yss, yb, kbar, ystage, d_corr,
                          d_hdot, d_wacc, slots, want_coef, stream, cached);
           }
           ms_sweep += ms(t2, now());
@@ -809,9 +829,9 @@ class Engine {
   }
 
   // y_out = DP5 step from y_in (no error estimate); leaves k[0..5] filled
-  void advance(const amp_t* y_in, vec y_out, const AcceptedStep& st, vec* k, void* stream) {
+  void advance(const amp_t* y_in, vec y_out, const AcceptedStep& st, vec* k, void* stream, vec* ysave = nullptr) {
     apply(k[0], y_in, st.t, 0, stream);
-    dp5_stages(st.t, st.dt, y_in, k, nullptr, 6, stream);
+    dp5_stages(st.t, st.dt, y_in, k, nullptr, 6, stream, ysave);
     const amp_t* ins[8];
     double w[8];
     int n = 0;
@@ -821,13 +841,15 @@ class Engine {
     launches += bk.lincomb(geo, y_out, n, ins, w, stream);
   }
 
-  void adjoint_step(const AcceptedStep& st, int step_index, const amp_t* y_n, vec lam, vec* k,
+  // ys[1..5]: the stage inputs Y_i of this step (filled here unless the recomputation pass cached them with
+  // the slopes, have_k)
+  void adjoint_step(const AcceptedStep& st, int step_index, const amp_t* y_n, vec lam, vec* k, vec* ys,
                     vec* yb, vec kbar, vec ystage, cplx* d_corr, double* d_hdot, double* d_wacc,
                     std::vector<SlotInfo>& slots, bool want_coef, void* stream, bool have_k = false) {
     double t = st.t, h = st.dt;
     if (!have_k) {
       apply(k[0], y_n, t, 0, stream);
-      dp5_stages(t, h, y_n, k, nullptr, 6, stream);
+      dp5_stages(t, h, y_n, k, nullptr, 6, stream, ys);
     }
     int cs = corr_stride();
     for (int i = 5; i >= 0; --i) {
@@ -845,16 +867,10 @@ class Engine {
       size_t slot = (size_t)step_index * 6 + i;
       slots[slot] = {ts, alpha, st.interval, step_index};
       if (want_coef || d_wacc) {
-        // stage input Y_i = y_n + h sum_j beta_ij k_j, formed by the correlation launch itself
-        const amp_t* yi[8];
-        double yw[8];
-        int m = 0;
-        yi[m] = y_n; yw[m++] = 1.0;
-        for (int j = 0; j < i; ++j) {
-          double b = tab.beta[i - 1][j];
-          if (b != 0.0) { yi[m] = k[j]; yw[m++] = h * b; }
-        }
-        launches += bk.corr_combo(geo, want_coef ? d_corr + slot * cs : nullptr, d_wacc, 1.0, kbar, m, yi, yw,
+        // stage input Y_i = y_n + h sum_j beta_ij k_j as the forward stage launch wrote it (Y_0 = y_n)
+        const amp_t* yi[1] = {i == 0 ? y_n : ys[i]};
+        const double yw[1] = {1.0};
+        launches += bk.corr_combo(geo, want_coef ? d_corr + slot * cs : nullptr, d_wacc, 1.0, kbar, 1, yi, yw,
                                   ystage, reduce_scratch(), stream);
       }
       if (d_hdot && st.clipped)

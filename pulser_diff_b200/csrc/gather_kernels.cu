@@ -3,6 +3,8 @@
 //   H(t) psi = 2*int_mat psi + sum(det terms) + sum(amp terms)      (reference hamiltonian.py:536-544)
 // and of the Lindblad right-hand side, written as
 //   out[idx] = kappa*Dstat(idx)*v[idx] + sum_q sum_p' T_q[p(idx)][p'] v[idx with site q := p'].
+#include <cstdlib>
+
 #include "cuda_backend.cuh"
 
 namespace pd {
@@ -153,6 +155,63 @@ k_apply_density(amp_t* __restrict__ out, const amp_t* __restrict__ in, const dou
     }
     fma_acc(acc, dsum, v);
     out[idx] = acc;
+  }
+}
+
+// Column-tile variant of k_apply_density, OPT-IN (PD_DENSITY_CT=1; measured slower, profiles/r02_lindblad.md).
+// A CTA stages 2^10 CONTIGUOUS entries in shared memory: every flip whose mask lies inside the tile -- the column
+// bits of the last 10 sites (and, for small registers, low row bits) -- is served from shared memory, only the
+// remaining partners travel through L2, and the (row, column) double flip is fetched only where its coefficient
+// is non-zero: N = 12 with dephasing + relaxation fetches 1 + 17 entries per entry through L2 instead of 37.
+// On B200 it runs 0.86 ms per application against 0.67 ms for the plain kernel: the plain kernel's low column
+// partners already hit L1 (38 % L1 hit rate), both kernels wait on long-scoreboard stalls with ~50 % issue
+// utilisation at half occupancy (54 registers), and the tile adds two barriers per 1024 entries.
+constexpr int kDTB = 10;
+constexpr int kDTile = 1 << kDTB;
+constexpr int kDEpt = kDTile / kThreads;
+__global__ void __launch_bounds__(kThreads)
+k_apply_density_ct(amp_t* __restrict__ out, const amp_t* __restrict__ in, const double* __restrict__ diag,
+                   const __grid_constant__ SiteOpsDensity so, int nq, size_t n_tiles) {
+  __shared__ cplx T[kMaxSitesDensity * 16];
+  __shared__ amp_t tile[kDTile];
+  for (int i = threadIdx.x; i < nq * 16; i += blockDim.x) T[i] = so.T[i];
+  const size_t S = (size_t)1 << nq, dim = S * S;
+  const int t = threadIdx.x;
+  for (size_t ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+    const size_t base = ti << kDTB;
+    __syncthreads();                              // the previous tile's readers are done (and T is in place)
+#pragma unroll
+    for (int i = 0; i < kDEpt; ++i) tile[t + kThreads * i] = in[base + t + kThreads * i];
+    __syncthreads();
+#pragma unroll 2
+    for (int i = 0; i < kDEpt; ++i) {
+      const int el = t + kThreads * i;
+      const size_t idx = base + el;
+      const size_t e = idx & (dim - 1);
+      const size_t r = e >> nq, c = e & (S - 1);
+      const cplx v = tile[el];
+      const double dg = diag[r] - diag[c];
+      cplx dsum{so.kappa.re * dg, so.kappa.im * dg};
+      cplx acc{0.0, 0.0};
+#pragma unroll 4
+      for (int q = 0; q < nq; ++q) {
+        const size_t mc = (size_t)1 << (nq - 1 - q), mr = mc << nq;
+        const int p = ((e & mr) ? 2 : 0) | ((e & mc) ? 1 : 0);
+        const cplx* Tp = &T[q * 16 + p * 4];
+        dsum = dsum + Tp[p];
+        const cplx prow = mr < (size_t)kDTile ? (cplx)tile[el ^ (int)mr] : (cplx)in[idx ^ mr];
+        const cplx pcol = mc < (size_t)kDTile ? (cplx)tile[el ^ (int)mc] : (cplx)in[idx ^ mc];
+        fma_acc(acc, Tp[p ^ 2], prow);
+        fma_acc(acc, Tp[p ^ 1], pcol);
+        if ((so.nzmask[q] >> (p * 4 + (p ^ 3))) & 1u) {
+          const size_t mb = mr | mc;
+          const cplx pboth = mb < (size_t)kDTile ? (cplx)tile[el ^ (int)mb] : (cplx)in[idx ^ mb];
+          fma_acc(acc, Tp[p ^ 3], pboth);
+        }
+      }
+      fma_acc(acc, dsum, v);
+      out[idx] = acc;
+    }
   }
 }
 
@@ -310,6 +369,52 @@ k_corr_density_fused(const amp_t* __restrict__ kbar, const amp_t* __restrict__ y
   }
   block_reduce_write<kDF>(acc, partial);
 }
+// Column-tile variant (same sums, same partial layout): the y tile of 2^10 contiguous entries sits in shared
+// memory, so the column-bit partners of the last 10 sites never go through L2 (N = 12: 2 + 14 fetches per entry
+// instead of 2 + 24).
+__global__ void __launch_bounds__(kThreads)
+k_corr_density_ct(const amp_t* __restrict__ kbar, const amp_t* __restrict__ y, int nq, size_t n_tiles,
+                  double* partial, double* wacc, double wscale) {
+  __shared__ amp_t tile[kDTile];
+  const size_t S = (size_t)1 << nq, dim = S * S;
+  const int t = threadIdx.x;
+  double acc[kDF];
+#pragma unroll
+  for (int i = 0; i < kDF; ++i) acc[i] = 0.0;
+  for (size_t ti = blockIdx.x; ti < n_tiles; ti += gridDim.x) {
+    const size_t base = ti << kDTB;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kDEpt; ++i) tile[t + kThreads * i] = y[base + t + kThreads * i];
+    __syncthreads();
+    for (int i = 0; i < kDEpt; ++i) {
+      const int el = t + kThreads * i;
+      const size_t idx = base + el;
+      const size_t e = idx & (dim - 1);
+      const cplx kb = conj(kbar[idx]);
+      const cplx self = kb * (cplx)tile[el];
+#pragma unroll
+      for (int q = 0; q < kMaxSitesDensity; ++q) {
+        if (q < nq) {
+          const size_t mc = (size_t)1 << (nq - 1 - q), mr = mc << nq;
+          const bool a = (e & mr) != 0, b = (e & mc) != 0;
+          const cplx yr = mr < (size_t)kDTile ? (cplx)tile[el ^ (int)mr] : (cplx)y[idx ^ mr];
+          const cplx yc = mc < (size_t)kDTile ? (cplx)tile[el ^ (int)mc] : (cplx)y[idx ^ mc];
+          const cplx frow = kb * yr, fcol = kb * yc;
+          acc[q * 3 + 0] += ((a ? 0.0 : 1.0) - (b ? 0.0 : 1.0)) * self.im;
+          acc[q * 3 + 1] += frow.im - fcol.im;
+          acc[q * 3 + 2] += (a ? frow.re : -frow.re) + (b ? fcol.re : -fcol.re);
+        }
+      }
+      if (wacc) {
+        const double w = wscale * self.im;
+        atomicAdd(&wacc[e >> nq], w);
+        atomicAdd(&wacc[e & (S - 1)], -w);
+      }
+    }
+  }
+  block_reduce_write<kDF>(acc, partial);
+}
 // d_corr[q][16]: zero except the three entries engine.hpp::distribute turns back into (gd, ga, gb)
 __global__ void k_corr_density_scatter(const double* __restrict__ partial, int nblocks, int nq, cplx* d_corr) {
   int q = blockIdx.x, lane = threadIdx.x;   // one warp per site
@@ -409,6 +514,15 @@ int launch_apply_density(const Geometry& g, amp_t* out, const amp_t* in, const S
   for (int q = 0; q < so.nsites; ++q)
     for (int p = 0; p < 4; ++p)
       if (so.nzmask[q] >> (p * 4 + (p ^ 3)) & 1) need_both = 1;
+  // PD_DENSITY_CT=1 selects the column-tile kernel (A/B measurements; slower on B200)
+  static const bool use_ct = [] { const char* e = std::getenv("PD_DENSITY_CT"); return e && e[0] == '1'; }();
+  if (use_ct && total >= (size_t)kDTile && total % kDTile == 0) {
+    const size_t n_tiles = total >> kDTB;
+    const int grid = (int)std::min<size_t>(n_tiles, (size_t)148 * 8);
+    k_apply_density_ct<<<grid, kThreads, 0, s>>>(out, in, g.diag, so, g.nq, n_tiles);
+    PD_CUDA_CHECK(cudaGetLastError());
+    return 1;
+  }
   k_apply_density<<<grid_for(total), kThreads, 0, s>>>(out, in, g.diag, so, g.nq, total, need_both);
   PD_CUDA_CHECK(cudaGetLastError());
   return 1;
@@ -493,7 +607,14 @@ int launch_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, 
   } else {
     size_t total = g.dim * g.batch;
     int gx = rgrid_for(total, kDF, 1);
-    k_corr_density_fused<<<gx, kThreads, 0, s>>>(kbar, y, g.nq, total, scratch, d_wacc, wscale);
+    static const bool use_ct = [] { const char* e = std::getenv("PD_DENSITY_CT"); return e && e[0] == '1'; }();
+    if (use_ct && total >= (size_t)kDTile && total % kDTile == 0) {
+      const size_t n_tiles = total >> kDTB;
+      gx = (int)std::min<size_t>(n_tiles, (size_t)gx);
+      k_corr_density_ct<<<gx, kThreads, 0, s>>>(kbar, y, g.nq, n_tiles, scratch, d_wacc, wscale);
+    } else {
+      k_corr_density_fused<<<gx, kThreads, 0, s>>>(kbar, y, g.nq, total, scratch, d_wacc, wscale);
+    }
     PD_CUDA_CHECK(cudaGetLastError());
     ++n;
     if (d_corr) {

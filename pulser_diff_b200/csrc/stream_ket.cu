@@ -1212,7 +1212,7 @@ struct CorrParams {
 };
 
 template <int R, class AccT>
-__device__ __forceinline__ void corr_block_reduce(AccT (&acc)[R], double* partial) {
+__device__ __forceinline__ void corr_block_reduce(AccT (&acc)[R], double* partial, size_t block, size_t n_blocks) {
   __shared__ double sh[NT / 32][R];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -1227,7 +1227,7 @@ __device__ __forceinline__ void corr_block_reduce(AccT (&acc)[R], double* partia
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < NT / 32; ++w) s += sh[w][threadIdx.x];
-    partial[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = s;   // [R][n_blocks]: the final pass reads rows
+    partial[(size_t)threadIdx.x * n_blocks + block] = s;   // [R][n_blocks]: the final pass reads rows
   }
 }
 
@@ -1235,13 +1235,20 @@ __device__ __forceinline__ void corr_block_reduce(AccT (&acc)[R], double* partia
 // of the thread, so the sign of gb and the "bit clear" condition of gd are applied ONCE per thread after the
 // element loop; for lb >= 8 they are compile-time constants.  Per flip and element: one LDS.128 and four FMAs
 // straight into the two accumulators (ga += Im(conj(kb) y'), gb_raw += Re(conj(kb) y')).
-__global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__ CorrParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  tcplx* T = reinterpret_cast<tcplx*>(smem_raw);
+// KEEP: the tile's lines stay in L2 (normal policy instead of streaming loads) for the first group's tile of
+// the same chunk, which the interleaved launch k_stream_corr_ag schedules right behind it.
+template <bool KEEP>
+__device__ __forceinline__ tcplx corr_ld(const tcplx* p, unsigned long long pol) {
+  if (KEEP) return ld_pol(p, pol);
+  return ldcs(p);
+}
+template <bool KEEP>
+__device__ __forceinline__ void corr_a_tile(const CorrParams& P, tcplx* T, size_t lin_tile, size_t n_blocks) {
   const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
-  const size_t tile = blockIdx.x % tiles_per_vec;
-  const size_t base = (blockIdx.x / tiles_per_vec) * P.dim + (tile << TB);
+  const size_t tile = lin_tile % tiles_per_vec;
+  const size_t base = (lin_tile / tiles_per_vec) * P.dim + (tile << TB);
+  const unsigned long long pol_keep = KEEP ? l2_policy(1) : 0ull;
   constexpr int QP = 4;
 #pragma unroll
   for (int q0 = 0; q0 < EPT; q0 += QP) {
@@ -1253,7 +1260,7 @@ __global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__
       const treal wj = P.w[j];
       tcplx x[QP];
 #pragma unroll
-      for (int i = 0; i < QP; ++i) x[i] = ldcs(vj + t + NT * (q0 + i));
+      for (int i = 0; i < QP; ++i) x[i] = corr_ld<KEEP>(vj + t + NT * (q0 + i), pol_keep);
 #pragma unroll
       for (int i = 0; i < QP; ++i) { y[i].re = fma(wj, x[i].re, y[i].re); y[i].im = fma(wj, x[i].im, y[i].im); }
     }
@@ -1277,7 +1284,7 @@ __global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__
   for (int io = 0; io < 4; ++io) {
     tcplx kb4[4];
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii) kb4[ii] = ldcs(P.kbar + base + t + NT * (4 * io + ii));
+    for (int ii = 0; ii < 4; ++ii) kb4[ii] = corr_ld<KEEP>(P.kbar + base + t + NT * (4 * io + ii), pol_keep);
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
       const int i = 4 * io + ii;
@@ -1318,7 +1325,11 @@ __global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__
     acc[(8 + k) * 3 + 2] = gb[8 + k];
   }
   acc[kCA - 1] = self_all;
-  corr_block_reduce<kCA>(acc, P.partial);
+  corr_block_reduce<kCA>(acc, P.partial, lin_tile, n_blocks);
+}
+__global__ void __launch_bounds__(NT, 2) k_stream_corr_a(const __grid_constant__ CorrParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  corr_a_tile<false>(P, reinterpret_cast<tcplx*>(smem_raw), blockIdx.x, gridDim.x);
 }
 
 __device__ __forceinline__ size_t cindex(const CorrParams& P, size_t tile, int e) {
@@ -1330,13 +1341,11 @@ __device__ __forceinline__ size_t cindex(const CorrParams& P, size_t tile, int e
 
 // group tile: element e = t + 256 i at global index g0 + i * stride (see g_tile); row bits [C, 8) live in t
 // (runtime count 8 - C <= 4), row bits 8-11 in i.
-__global__ void __launch_bounds__(NT, 2) k_stream_corr_g(const __grid_constant__ CorrParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  tcplx* T = reinterpret_cast<tcplx*>(smem_raw);
+__device__ __forceinline__ void corr_g_tile(const CorrParams& P, tcplx* T, size_t lin_tile, size_t n_blocks) {
   const int t = threadIdx.x;
   const size_t tiles_per_vec = P.dim >> TB;
-  const size_t tile = blockIdx.x % tiles_per_vec;
-  const size_t boff = (blockIdx.x / tiles_per_vec) * P.dim;
+  const size_t tile = lin_tile % tiles_per_vec;
+  const size_t boff = (lin_tile / tiles_per_vec) * P.dim;
   const int C = P.C;
   const size_t g0 = boff + cindex(P, tile, t);
   const size_t stride = (size_t)1 << (P.lo + 8 - C);
@@ -1388,7 +1397,33 @@ __global__ void __launch_bounds__(NT, 2) k_stream_corr_g(const __grid_constant__
     for (int bb = 0; bb < kMaxGroupBits; ++bb)
       if (bb == n_cross + k) { acc[bb * 2 + 0] = ga8[k]; acc[bb * 2 + 1] = gb8[k]; }
   }
-  corr_block_reduce<kCG>(acc, P.partial);
+  corr_block_reduce<kCG>(acc, P.partial, lin_tile, n_blocks);
+}
+__global__ void __launch_bounds__(NT, 2) k_stream_corr_g(const __grid_constant__ CorrParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  corr_g_tile(P, reinterpret_cast<tcplx*>(smem_raw), blockIdx.x, gridDim.x);
+}
+// Contiguous tiles and the FIRST group's tiles of a plain stage input in one launch, chunk by chunk (a chunk =
+// 2^chunk_log2 tiles, closed under the first group's bits): the group tiles of chunk c - lag alternate with the
+// contiguous tiles of chunk c, so they find kbar and Y -- both only read here, no ordering needed -- in L2
+// instead of fetching them from HBM a second time (6 -> 4 vector passes per stage with two groups).
+__global__ void __launch_bounds__(NT, 2)
+k_stream_corr_ag(const __grid_constant__ CorrParams PA, const __grid_constant__ CorrParams PG, const unsigned chunk_log2,
+                 const unsigned n_chunks, const unsigned n_tiles, const unsigned lag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  tcplx* T = reinterpret_cast<tcplx*>(smem_raw);
+  const unsigned CT = 1u << chunk_log2;
+  const unsigned item = blockIdx.x;
+  const unsigned blk = item >> (chunk_log2 + 1);
+  const unsigned r = item & (2 * CT - 1);
+  const bool is_a = !(r & 1u);
+  if (is_a) {
+    if (blk >= n_chunks) return;
+    corr_a_tile<true>(PA, T, (size_t)blk * CT + (r >> 1), n_tiles);
+  } else {
+    if (blk < lag) return;
+    corr_g_tile(PG, T, (size_t)(blk - lag) * CT + (r >> 1), n_tiles);
+  }
 }
 
 // One warp per qubit bit position p: sums the per-CTA partials in a fixed order and writes the 2x2 block
@@ -1459,11 +1494,12 @@ int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double w
   if (!attr_set[dev]) {
     PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_a, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * kAmpBytes));
     PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_g, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * kAmpBytes));
+    PD_CUDA_CHECK(cudaFuncSetAttribute(k_stream_corr_ag, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE * kAmpBytes));
     attr_set[dev] = true;
   }
   const unsigned grid = (unsigned)((g.dim >> TB) * (size_t)g.batch);
-  const int rest = g.nq - TB;
-  const int G = d_corr ? (rest + kMaxGroupBits - 1) / kMaxGroupBits : 0;
+  const Groups gr = make_groups(g.nq);
+  const int G = d_corr ? gr.G : 0;
   // per-device scratch for the per-CTA partial sums (a process may drive several devices)
   static double* parts[64] = {};
   static size_t caps[64] = {};
@@ -1481,21 +1517,38 @@ int launch_stream_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double w
   A.nq = g.nq; A.dim = g.dim; A.n_in = n_in; A.kbar = kbar; A.wacc = d_wacc; A.wscale = wscale; A.partial = d_part;
   for (int j = 0; j < n_in; ++j) { A.v[j] = ins[j]; A.w[j] = (treal)w[j]; }
   A.ymat = (plain || G == 0) ? nullptr : ymat;
-  k_stream_corr_a<<<grid, NT, TILE * kAmpBytes, s>>>(A);
-  int n = 1;
+  CorrParams B[8];
+  CorrFinal F{};
+  F.nq = g.nq; F.n_groups = G; F.part_a = d_part; F.nblocks = grid; F.tiles_per_vec = (unsigned)(g.dim >> TB);
+  F.d_corr = d_corr;
+  for (int gi = 0; gi < G; ++gi) {
+    B[gi] = CorrParams{};
+    B[gi].nq = g.nq; B[gi].dim = g.dim; B[gi].ysrc = ysrc; B[gi].kbar = kbar;
+    B[gi].lo = gr.lo[gi]; B[gi].nb = gr.nb[gi]; B[gi].C = TB - gr.nb[gi];
+    B[gi].partial = d_part + (size_t)grid * (kCA + (size_t)gi * kCG);
+    F.lo[gi] = gr.lo[gi]; F.nb[gi] = gr.nb[gi]; F.part_g[gi] = B[gi].partial;
+  }
+  // a plain stage input (the adjoint sweep hands over the stage inputs the forward launches wrote): contiguous
+  // tiles + first group in one L2-blocked launch; PD_CORR_FUSE=0 keeps them separate (A/B measurements)
+  static const unsigned fuse = env_unsigned("PD_CORR_FUSE", 1), chunk_env = env_unsigned("PD_CORR_CHUNK", 6),
+                        lag = std::max(1u, env_unsigned("PD_CORR_LAG", 4));
+  const unsigned tiles_per_vec = (unsigned)(g.dim >> TB);
+  unsigned chunk_log2 = 0;
+  while ((1u << (chunk_log2 + 1)) <= tiles_per_vec && chunk_log2 < std::max<unsigned>(chunk_env, G ? gr.nb[0] : 0)) ++chunk_log2;
+  const size_t n_chunks = (size_t)grid >> chunk_log2;
+  int n = 0, first = 0;
+  if (fuse && plain && G >= 1 && (unsigned)gr.nb[0] <= chunk_log2 && n_chunks >= 16) {
+    const unsigned ag_grid = (unsigned)(2 * ((size_t)grid + ((size_t)lag << chunk_log2)));
+    k_stream_corr_ag<<<ag_grid, NT, TILE * kAmpBytes, s>>>(A, B[0], chunk_log2, (unsigned)n_chunks, grid, lag);
+    n = 1;
+    first = 1;
+  } else {
+    k_stream_corr_a<<<grid, NT, TILE * kAmpBytes, s>>>(A);
+    n = 1;
+  }
   if (d_corr) {
-    CorrFinal F{};
-    F.nq = g.nq; F.n_groups = G; F.part_a = d_part; F.nblocks = grid; F.tiles_per_vec = (unsigned)(g.dim >> TB);
-    F.d_corr = d_corr;
-    int lo = TB;
-    for (int gi = 0; gi < G; ++gi) {
-      const int nb = rest / G + (gi < rest % G ? 1 : 0);
-      CorrParams B{};
-      B.nq = g.nq; B.dim = g.dim; B.ysrc = ysrc; B.kbar = kbar; B.lo = lo; B.nb = nb; B.C = TB - nb;
-      B.partial = d_part + (size_t)grid * (kCA + (size_t)gi * kCG);
-      k_stream_corr_g<<<grid, NT, TILE * kAmpBytes, s>>>(B);
-      F.lo[gi] = lo; F.nb[gi] = nb; F.part_g[gi] = B.partial;
-      lo += nb;
+    for (int gi = first; gi < G; ++gi) {
+      k_stream_corr_g<<<grid, NT, TILE * kAmpBytes, s>>>(B[gi]);
       ++n;
     }
     k_stream_corr_final<<<g.nq, 256, 0, s>>>(F);
