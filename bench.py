@@ -575,13 +575,21 @@ def run_b200(args):
                 print(json.dumps(line), flush=True)
             os._exit(0)
 
-        timer = threading.Timer(300.0, give_up)
+        timer = threading.Timer(420.0, give_up)
         timer.daemon = True
         timer.start()
         try:
             sharded = sharded_measure(dev, rank, world, args.sharded_local_qubits, 6, 1)
         except Exception as exc:
             sharded = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        # the same leg one qubit larger in the complex64 tier: 2^30 amplitudes per GPU = the N = 33 register of
+        # configs[4] on eight GPUs, in the bytes the complex128 leg needs for N = 32
+        if "error" not in sharded and not args.no_sharded_c64:
+            try:
+                sharded["complex64"] = sharded_measure(dev, rank, world, args.sharded_local_qubits + 1, 4, 1,
+                                                       torch.complex64, parity=False)
+            except Exception as exc:
+                sharded["complex64"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         done.set()
         timer.cancel()
         if rank == 0:
@@ -739,7 +747,7 @@ def sharded_parity(dev, rank, world, n=20):
             "ok": bool(e[0] < 1e-10 and max(e[1:]) < 1e-8)}
 
 
-def sharded_measure(dev, rank, world, local_qubits, steps, warmup):
+def sharded_measure(dev, rank, world, local_qubits, steps, warmup, cdtype=torch.complex128, parity=True):
     """configs[4]-style leg: ONE register of local_qubits + log2(world) atoms sharded over the
     ranks by its top qubits (NVLink peer memory).  Times H.psi and fixed-size DP5 steps with CUDA
     events (max over ranks) and sets them against max(HBM, NVLink) rooflines; the NVLink rate is the
@@ -747,12 +755,13 @@ def sharded_measure(dev, rank, world, local_qubits, steps, warmup):
     import torch.distributed as dist
     from pulser_diff_b200 import parallel
     g = world.bit_length() - 1
-    parity = sharded_parity(dev, rank, world)
+    parity = sharded_parity(dev, rank, world) if parity else None
+    ab = 16.0 if cdtype == torch.complex128 else 8.0          # bytes per amplitude
     # largest slice that fits: the forward evolution holds y, 7 slopes, the next state, the peer-visible
     # buffer, g receive buffers, 2 saved states and ~2 transients (16 B/amplitude each) + the 8 B diagonal
     free = torch.tensor([torch.cuda.mem_get_info(dev)[0]], dtype=torch.float64, device=dev)
     dist.all_reduce(free, op=dist.ReduceOp.MIN)
-    need = lambda nl: ((14 + g) * 16 + 8) * 2.0 ** nl * 1.12
+    need = lambda nl: ((14 + g) * ab + 8) * 2.0 ** nl * 1.12
     while local_qubits > 20 and need(local_qubits) > free.item():
         local_qubits -= 1
     n = local_qubits + g
@@ -765,7 +774,7 @@ def sharded_measure(dev, rank, world, local_qubits, steps, warmup):
         for j in range(i + 1, n):
             u[i, j] = C6 / (SPACING * (j - i)) ** 6
     full = (1 << n) - 1
-    sk = parallel.ShardedKet(n, u, 0.02, [full], dv, [full], av, dev, peer_memory=True)
+    sk = parallel.ShardedKet(n, u, 0.02, [full], dv, [full], av, dev, peer_memory=True, dtype=cdtype)
     psi = sk.state_buffer()
     psi.zero_()
     if rank == world - 1:
@@ -791,9 +800,9 @@ def sharded_measure(dev, rank, world, local_qubits, steps, warmup):
             sk._recv[k].copy_(sk._peer_bufs[rank ^ (1 << k)])
     pull()
     ms_pull = timed(pull, 3)
-    nvlink = g * 16.0 * 2 ** local_qubits / (ms_pull * 1e-3) / 1e9
+    nvlink = g * ab * 2 ** local_qubits / (ms_pull * 1e-3) / 1e9
     ms_h = timed(lambda: sk.hpsi(0.3, psi), max(steps, 3))
-    y0 = torch.zeros(1, 2 ** local_qubits, dtype=torch.complex128, device=dev)
+    y0 = torch.zeros(1, 2 ** local_qubits, dtype=cdtype, device=dev)
     if rank == world - 1:
         y0[0, -1] = 1.0                                  # all-ground register
     h = 1e-3
@@ -808,16 +817,22 @@ def sharded_measure(dev, rank, world, local_qubits, steps, warmup):
         return {"bound": "nvlink" if link_t > hbm_t else "hbm", "hbm_s": hbm_t, "nvlink_s": link_t,
                 "frac": max(hbm_t, link_t) / (ms * 1e-3)}
 
-    return {"workload": f"single register N={n} sharded by its {g} top qubits (2^{local_qubits} amplitudes per GPU)",
+    del sk
+    from pulser_diff_b200 import ops as _ops
+    _ops.clear_plan_cache()
+    torch.cuda.empty_cache()
+    return {"workload": f"single register N={n} sharded by its {g} top qubits (2^{local_qubits} amplitudes per GPU, "
+                        f"{str(cdtype).replace('torch.', '')})",
             "exchange": "partner slices pulled by the copy engines from NVLink peer memory beside the local kernels; "
                         "one accumulate kernel (pd_sharded_accumulate)",
-            "local_qubits": local_qubits, "bytes_per_vector_per_gpu": 16 * amps,
-            "ms_per_hpsi": ms_h, "hpsi_per_s": 1e3 / ms_h, "roofline_hpsi": roof(40.0 * amps, g * 16.0 * amps, ms_h),
+            "local_qubits": local_qubits, "bytes_per_vector_per_gpu": ab * amps,
+            "ms_per_hpsi": ms_h, "hpsi_per_s": 1e3 / ms_h,
+            "roofline_hpsi": roof((2 * ab + 8) * amps, g * ab * amps, ms_h),
             "ms_per_dp5_step": ms_e, "dp5_steps_per_s": 1e3 / ms_e,
-            "roofline_dp5_step": roof(576.0 * amps, 6 * g * 16.0 * amps, ms_e),
+            "roofline_dp5_step": roof((33 * ab + 48) * amps, 6 * g * ab * amps, ms_e),
             "peak_hbm_GBs": peak,
             "nvlink_measured": {"GBs_per_direction_per_gpu": nvlink, "how": f"{g} concurrent peer copies of one "
-                                f"{16 * amps / 2 ** 30:.2f} GiB slice per rank, CUDA events, max over ranks",
+                                f"{ab * amps / 2 ** 30:.2f} GiB slice per rank, CUDA events, max over ranks",
                                 "ms": ms_pull},
             "parity_vs_single_gpu": parity}
 
@@ -857,6 +872,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--workload", default="c2", choices=["c2", "sharded"])
     ap.add_argument("--local-qubits", type=int, default=26)
+    ap.add_argument("--no-sharded-c64", action="store_true", help="N > 1: skip the complex64 sharded leg")
     ap.add_argument("--sharded-local-qubits", type=int, default=29,
                     help="N > 1: also time one register of this many + log2(N) qubits sharded over the ranks (0 = skip)")
     args = ap.parse_args()

@@ -41,6 +41,8 @@ _PLAN_CACHE: dict[tuple, Plan] = {}
 _PLAN_CACHE_MAX_PLANS = 16                 # small registers: cheap to keep
 _PLAN_CACHE_MAX_AMPLITUDES = 1 << 27       # plans kept beside a new one hold at most this many amplitudes in total
 _UNIT_PROGRAMS: dict[tuple, "Program"] = {}
+_PROGRAMS: dict[tuple, "Program"] = {}     # content -> Program: unchanged coefficient tables keep their identity
+_PROGRAMS_MAX = 32
 
 
 @dataclass
@@ -62,6 +64,7 @@ def clear_plan_cache() -> None:
     """Drop cached plans (frees their device workspace)."""
     _PLAN_CACHE.clear()
     _UNIT_PROGRAMS.clear()
+    _PROGRAMS.clear()
 
 
 C64_MIN_KET_QUBITS = 15     # kets below this are served by the complex128 small-register kernels
@@ -114,13 +117,24 @@ def make_program(n_qubits: int, kind: int, dt: float, det_masks: Sequence[int], 
                  collapse: Optional[Tensor]) -> Program:
     # a program may have no detuning (or no drive) term at all: keep the sample axis explicit
     n_s = int(det_values.shape[-1]) if len(det_masks) else (int(amp_values.shape[-1]) if len(amp_masks) else 0)
-    return Program(
-        n_qubits, kind, float(dt), [int(m) for m in det_masks],
-        det_values.detach().to("cpu", torch.float64).reshape(len(det_masks), n_s).contiguous(),
-        [int(m) for m in amp_masks],
-        amp_values.detach().to("cpu", torch.complex128).reshape(len(amp_masks), n_s).contiguous(),
-        pair_u.detach().to("cpu", torch.float64).contiguous(),
-        None if collapse is None else collapse.detach().to("cpu", torch.complex128).contiguous())
+    dm, am = [int(m) for m in det_masks], [int(m) for m in amp_masks]
+    dv = det_values.detach().to("cpu", torch.float64).reshape(len(dm), n_s).contiguous()
+    av = amp_values.detach().to("cpu", torch.complex128).reshape(len(am), n_s).contiguous()
+    pu = pair_u.detach().to("cpu", torch.float64).contiguous()
+    co = None if collapse is None else collapse.detach().to("cpu", torch.complex128).contiguous()
+    # Programs are identified by CONTENT (the tables are a few KiB): a stepper written on the hpsi / rhs ops calls
+    # this once per generator application with the same tables, and a plan that sees the same Program id skips
+    # its reconfiguration (diagonal rebuild + stream synchronisation + table copies, see configure)
+    key = (n_qubits, kind, float(dt), tuple(dm), tuple(am), n_s, dv.numpy().tobytes(),
+           torch.view_as_real(av).numpy().tobytes(), pu.numpy().tobytes(),
+           None if co is None else torch.view_as_real(co).numpy().tobytes())
+    prog = _PROGRAMS.pop(key, None)
+    if prog is None:
+        if len(_PROGRAMS) >= _PROGRAMS_MAX:
+            del _PROGRAMS[next(iter(_PROGRAMS))]        # least recently used first
+        prog = Program(n_qubits, kind, float(dt), dm, dv, am, av, pu, co)
+    _PROGRAMS[key] = prog
+    return prog
 
 
 class _EvolveFn(torch.autograd.Function):
@@ -219,6 +233,7 @@ class _EvolveUnitsFn(torch.autograd.Function):
                                                  want_tape=need)
         ctx.plan, ctx.prog, ctx.tape = plan, prog, tape
         ctx.state_dtype = state0.dtype
+        ctx.opt, ctx.state0, ctx.tsave = opt, state0.detach().to(cd), tsave.detach()
         ctx.tables = (det_values.detach(), amp_values.detach())
         ctx.meta = (det_values.device, det_values.dtype, amp_values.device, amp_values.dtype)
         ctx.save_for_backward(states)
@@ -234,9 +249,19 @@ class _EvolveUnitsFn(torch.autograd.Function):
         (states,) = ctx.saved_tensors
         configure(ctx.plan, ctx.prog)
         dv, av = ctx.tables
-        g_det, g_amp, g_s0 = ctx.plan.evolve_backward_units(
-            ctx.tape, states, grad_states.to(ctx.plan.cdtype).contiguous(), dv, av,
-            want_state0=ctx.needs_input_grad[0])
+        gs = grad_states.to(ctx.plan.cdtype).contiguous()
+        try:
+            g_det, g_amp, g_s0 = ctx.plan.evolve_backward_units(ctx.tape, states, gs, dv, av,
+                                                                want_state0=ctx.needs_input_grad[0])
+        except (RuntimeError, ValueError) as exc:
+            # The stage tape of a batch lives in plan-owned device memory; another evolution on the same plan
+            # (a second live graph of the same shape) has overwritten it.  The forward sweep is deterministic:
+            # run it again from the saved inputs and differentiate the fresh tape.
+            if "overwritten" not in str(exc) and "still current" not in str(exc):
+                raise
+            _, ctx.tape = ctx.plan.evolve_forward_units(ctx.opt, ctx.state0, ctx.tsave, dv, av, want_tape=True)
+            g_det, g_amp, g_s0 = ctx.plan.evolve_backward_units(ctx.tape, states, gs, dv, av,
+                                                                want_state0=ctx.needs_input_grad[0])
         if g_s0 is not None:
             g_s0 = g_s0.to(ctx.state_dtype)
         det_dev, det_dt, amp_dev, amp_dt = ctx.meta

@@ -95,12 +95,21 @@ class ShardedKet:
         peer_memory: ``True``/``"copy"``: partner slices come through NVLink peer memory (CUDA
                   ranks of one node), pulled by the copy engines beside the local kernels;
                   ``"read"``: read in place by the accumulation kernel; ``False``: send/recv.
+        dtype:    ``torch.complex128`` (default) or ``torch.complex64`` -- the optional 1e-5 tier: slices,
+                  exchange buffers and every stage vector in complex64 (the complex64 build of the library),
+                  which halves the HBM and the NVLink bytes and fits one more qubit per GPU (2^30 amplitudes
+                  = N = 33 on eight 180 GB GPUs).
     """
 
     def __init__(self, n_qubits: int, pair_u: Tensor, dt: float, det_masks: Sequence[int],
                  det_values: Tensor, amp_masks: Sequence[int], amp_values: Tensor,
-                 device: torch.device, group=None, peer_memory: bool | str = False) -> None:
+                 device: torch.device, group=None, peer_memory: bool | str = False,
+                 dtype: torch.dtype = torch.complex128) -> None:
         self.group = group
+        if dtype not in (torch.complex128, torch.complex64):
+            raise TypeError("sharded registers are complex128 or complex64")
+        self.cdtype = dtype
+        self._amp_bytes = 16 if dtype == torch.complex128 else 8
         # without a process group: one rank owning the whole register (no global qubits)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -122,7 +131,7 @@ class ShardedKet:
         self.r_glob = [1 - ((self.rank >> (g - 1 - q)) & 1) for q in range(g)]
         # local plan on the N-g low qubits (register qubits g..N-1 keep their order)
         loc = slice(g, n_qubits)
-        self.plan = ops.get_plan(self.nl, 1, _cabi.PD_KET, self.device)
+        self.plan = ops.get_plan(self.nl, 1, _cabi.PD_KET, self.device, dtype)
         low = (1 << self.nl) - 1
         dm = [(m >> g) & low for m in self.det_masks]          # mask bit q -> local bit q-g
         am = [(m >> g) & low for m in self.amp_masks]
@@ -155,8 +164,9 @@ class ShardedKet:
             if self.device.type != "cuda":
                 raise ValueError("peer_memory needs CUDA ranks")
             import torch.distributed._symmetric_memory as symm_mem
-            # float64 view of the complex slice: (re, im) pairs, the layout the kernels read
-            self._sym = symm_mem.empty((1, 2 << self.nl), dtype=torch.float64, device=self.device)
+            # real view of the complex slice: (re, im) pairs, the layout the kernels read
+            self._sym = symm_mem.empty((1, 2 << self.nl), device=self.device,
+                                       dtype=torch.float64 if dtype == torch.complex128 else torch.float32)
             self._hdl = symm_mem.rendezvous(self._sym, group if group is not None else dist.group.WORLD)
             self._peer_ptrs = [int(p) for p in self._hdl.buffer_ptrs]
 
@@ -252,7 +262,7 @@ class ShardedKet:
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 for c_ in range(n_ch):
-                    a_, b_ = 2 * c_ * ch, 2 * (c_ + 1) * ch          # float64 view: (re, im) pairs
+                    a_, b_ = 2 * c_ * ch, 2 * (c_ + 1) * ch          # real view: (re, im) pairs
                     for k, r in enumerate(peers):
                         self._recv[k][:, a_:b_].copy_(self._peer_bufs[r][:, a_:b_])
                     self._events[c_].record(self._side)
@@ -264,7 +274,7 @@ class ShardedKet:
         if copy and n_ch > 1:
             for c_ in range(n_ch):
                 main.wait_event(self._events[c_])
-                off = 16 * c_ * ch
+                off = self._amp_bytes * c_ * ch
                 self.plan.sharded_accumulate_range(out.data_ptr() + off, buf.data_ptr() + off, 0.0,
                                                    [buf.data_ptr() + off] + [p_ + off for p_ in ptrs], coefs, ch)
         else:

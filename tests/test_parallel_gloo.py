@@ -14,6 +14,7 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu", "libpd_emu.so")
+EMU_C64 = os.path.join(ROOT, "tests", "emu", "libpd_emu_c64.so")
 
 
 def _free_port():
@@ -90,7 +91,7 @@ def test_sharded_paths_gloo(world, emu_library, tmp_path):
     assert sorted(seen) == list(range(7))
 
 
-def _evolve_worker(rank, world, port, n, out_dir):
+def _evolve_worker(rank, world, port, n, out_dir, c64=False):
     """configs[4] on the CPU tier: sharded DP5 evolution + discrete adjoint vs the single-process
     engine on the full register (same library, so the comparison isolates the sharding)."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -98,8 +99,9 @@ def _evolve_worker(rank, world, port, n, out_dir):
     import sys
     sys.path.insert(0, ROOT)
     from pulser_diff_b200 import _cabi, ops, parallel
-    _cabi.use_library(EMU)
+    _cabi.use_library(EMU, EMU_C64)
     dev = torch.device("cpu")
+    cd = torch.complex64 if c64 else torch.complex128
     pr = _program(n, T=40)
     gen = torch.Generator().manual_seed(9)
     psi0 = torch.randn(1, 2 ** n, dtype=torch.complex128, generator=gen)
@@ -119,10 +121,11 @@ def _evolve_worker(rank, world, port, n, out_dir):
     log = [r for r in ops.last_step_log(st_full) if r["accepted"]]
 
     sk = parallel.ShardedKet(n, pr["pair_u"], pr["dt"], pr["det_masks"], pr["det_values"],
-                             pr["amp_masks"], pr["amp_values"], dev)
+                             pr["amp_masks"], pr["amp_values"], dev, dtype=cd)
     n_loc = 2 ** sk.nl
     sl = slice(rank * n_loc, (rank + 1) * n_loc)
     res = {}
+    psi0 = psi0.to(cd)
     # free-running controller: the same first steps (the all-reduced error norm differs from the
     # engine's by rounding, which the controller amplifies until an accept/reject decision
     # flips -- hence the shared-step protocol below for the tight comparison)
@@ -134,12 +137,13 @@ def _evolve_worker(rank, world, port, n, out_dir):
     replay = [(r["t"], r["dt"], r["interval"], bool(r["clipped"])) for r in log]
     st, steps = sk.evolve(sk.local_slice(psi0), tsave.tolist(), replay=replay)
     res["state_err"] = (st - st_full.detach()[:, :, sl]).abs().max().item()
+    res["state_dtype"] = str(st.dtype)
     st_leaf = st.clone().requires_grad_(True)
     # this rank's share of the loss: its slices only
     l_loc = (w[:, :, sl] * st_leaf.abs() ** 2).sum() + (v[:, :, sl].conj() * st_leaf).real.sum()
     (g_st,) = torch.autograd.grad(l_loc, st_leaf)
     out = sk.evolve_backward(st, g_st, steps)
-    relerr = lambda a, b: ((a - b).abs().max() / b.abs().max()).item()
+    relerr = lambda a, b: ((a.to(b.dtype) - b).abs().max() / b.abs().max()).item()
     res["g_det"] = relerr(out["det"], g_full[1])
     res["g_amp"] = relerr(out["amp"], g_full[2])
     res["g_pair"] = relerr(out["pair"], g_full[3])
@@ -161,3 +165,15 @@ def test_sharded_evolution_and_gradient_gloo(world, emu_library, tmp_path):
         assert res["state_err"] < 1e-12, res
         for key in ("g_det", "g_amp", "g_pair", "g_psi0"):
             assert res[key] < 1e-8, (key, res)
+
+
+def test_sharded_complex64_gloo(emu_library, tmp_path):
+    """The sharded register in the complex64 tier (slices, exchange and stage vectors in complex64) against
+    the unsharded complex128 engine on its accepted steps: states 1e-5, gradients 2e-5 of their scale."""
+    n, world = 6, 2
+    mp.spawn(_evolve_worker, args=(world, _free_port(), n, str(tmp_path), True), nprocs=world, join=True)
+    for r in range(world):
+        res = torch.load(os.path.join(tmp_path, f"e{r}.pt"))
+        assert res["state_dtype"] == "torch.complex64"
+        assert res["state_err"] < 1e-5, res
+        assert max(res["g_det"], res["g_amp"], res["g_pair"], res["g_psi0"]) < 2e-5, res

@@ -367,6 +367,43 @@ def test_parameter_set_batches(engine_device, n, batch):
             assert (a - b[u]).abs().max() < 1e-10 * max(1.0, a.abs().max().item())
 
 
+def test_two_live_batch_graphs(engine_device):
+    """Two forward batches of the same shape before either backward (a normal autograd pattern): the second
+    evolution overwrites the plan-owned stage tape of the first, whose backward then regenerates it; both
+    gradients equal those of the batches differentiated one after the other."""
+    from pulser_diff_b200 import ops
+    dev = engine_device
+    n, U, T = 2, 6, 20
+    g = torch.Generator().manual_seed(21)
+    pu = torch.zeros(n, n, dtype=torch.float64)
+    pu[0, 1] = 3.1
+    psi0 = torch.eye(4, dtype=torch.complex128)[:1].repeat(U, 1, 1).to(dev)
+    tsave = torch.tensor([0.0, 0.004, 0.011], dtype=torch.float64)
+    w = torch.arange(4, dtype=torch.float64, device=dev) + 0.5
+
+    def tables():
+        dv = (torch.rand(U, 1, T, dtype=torch.float64, generator=g) - 0.5) * 3
+        av = torch.complex(torch.rand(U, 1, T, dtype=torch.float64, generator=g) * 4, torch.zeros(U, 1, T, dtype=torch.float64))
+        return dv.to(dev), av.to(dev)
+
+    def run(dv, av):
+        dv, av = dv.clone().requires_grad_(True), av.clone().requires_grad_(True)
+        st = ops.evolve_units(psi0, tsave, dv, av, pu, n_qubits=n, dt=0.001, det_masks=[3], amp_masks=[3])
+        return (w * st[:, -1].abs() ** 2).sum(), dv, av
+
+    ta, tb = tables(), tables()
+    one_by_one = []
+    for t in (ta, tb):
+        loss, dv, av = run(*t)
+        one_by_one.append(torch.autograd.grad(loss, [dv, av]))
+    la, dva, ava = run(*ta)
+    lb, dvb, avb = run(*tb)                      # overwrites the device-side tape of the first batch
+    interleaved = [torch.autograd.grad(la, [dva, ava]), torch.autograd.grad(lb, [dvb, avb])]
+    for want, got in zip(one_by_one, interleaved):
+        for a, b in zip(want, got):
+            assert (a - b).abs().max() <= 1e-12 * max(1.0, a.abs().max().item())
+
+
 @pytest.mark.parametrize("n,batch,n_peers", [(3, 1, 0), (5, 1, 1), (11, 1, 3), (12, 2, 6)])
 def test_sharded_accumulate(engine_device, n, batch, n_peers):
     """pd_sharded_accumulate: out += shift*psi + sum_k coef_k * slice_k, the kernel the sharded
