@@ -849,7 +849,22 @@ class Engine {
     double t = st.t, h = st.dt;
     if (!have_k) {
       apply(k[0], y_n, t, 0, stream);
-      dp5_stages(t, h, y_n, k, nullptr, 6, stream, ys);
+      // the sweep reads the stage inputs Y_1..Y_5 and, for a clipped step whose end time is differentiated, the
+      // slopes (re_dot below): otherwise the sixth slope is never used and its application is skipped --
+      // Y_5 is then formed by a plain combination
+      const bool need_k5 = d_hdot && st.clipped;
+      dp5_stages(t, h, y_n, k, nullptr, need_k5 ? 6 : 5, stream, ys);
+      if (!need_k5) {
+        const amp_t* ins[8];
+        double w[8];
+        int n = 0;
+        ins[n] = y_n; w[n++] = 1.0;
+        for (int j = 0; j < 5; ++j) {
+          double b = tab.beta[4][j];
+          if (b != 0.0) { ins[n] = k[j]; w[n++] = h * b; }
+        }
+        launches += bk.lincomb(geo, ys[5], n, ins, w, stream);
+      }
     }
     int cs = corr_stride();
     for (int i = 5; i >= 0; --i) {

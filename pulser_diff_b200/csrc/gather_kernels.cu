@@ -158,6 +158,70 @@ k_apply_density(amp_t* __restrict__ out, const amp_t* __restrict__ in, const dou
   }
 }
 
+// Generator-specific Lindblad application (the default for density plans): same result as k_apply_density from the
+// pieces of the super-operator (pd_common.hpp LindbladForm) instead of a general 4x4 matrix per site.
+// k_apply_density issues ~760 thread instructions per entry (per site: four coefficient LDS.128 with a data-dependent
+// address, three partner loads -- the double flip whether or not its coefficient is zero -- and twelve DFMA) and is
+// bound by that, not by bytes (profiles/r02_lindblad.md).  Here per site: two partner loads and 2 DADD + 2 DFMA for a
+// phase-free drive (coefficients from the constant bank, uniform index), the dissipator's diagonal from four popcounts,
+// its off-diagonal entries only at the sites that feed them (bit scan over the matching sites).
+template <bool REAL>
+__global__ void __launch_bounds__(kThreads)
+k_apply_lindblad(amp_t* __restrict__ out, const amp_t* __restrict__ in, const double* __restrict__ diag,
+                 const __grid_constant__ LindbladForm lf, size_t total, int chunk_log2) {
+  const int nq = lf.nq;
+  const size_t S = (size_t)1 << nq, dim = S * S;
+  const unsigned smask = (unsigned)(S - 1);
+  // a CTA walks chunks of 2^chunk_log2 consecutive entries (kThreads at a time), so the column-bit partners inside
+  // the chunk are lines the same CTA touches a moment earlier or later (L1) instead of L2 round trips
+  const size_t n_items = total >> 8;                       // groups of kThreads = 256 entries (total is 4^N * batch)
+  const size_t per_chunk = (size_t)1 << (chunk_log2 - 8);
+  for (size_t it = (size_t)blockIdx.x * per_chunk; it < n_items; it += (size_t)gridDim.x * per_chunk)
+   for (size_t sub = 0; sub < per_chunk && it + sub < n_items; ++sub) {
+    const size_t idx = ((it + sub) << 8) + threadIdx.x;
+    const size_t e = idx & (dim - 1);
+    const unsigned r = (unsigned)(e >> nq), c = (unsigned)(e & (S - 1));
+    const cplx v = in[idx];
+    double dg = diag[r] - diag[c];
+    double sre = 0.0, sim = 0.0;
+#pragma unroll 4
+    for (int b = 0; b < nq; ++b) {
+      const size_t mc = (size_t)1 << b, mr = mc << nq;
+      const bool a = (r >> b) & 1u, cb = (c >> b) & 1u;
+      const cplx pr = in[idx ^ mr], pc = in[idx ^ mc];
+      const double db = lf.d[b], gr = lf.gre[b];
+      dg += (a ? 0.0 : db) - (cb ? 0.0 : db);
+      sre = fma(gr, pr.re - pc.re, sre);
+      sim = fma(gr, pr.im - pc.im, sim);
+      if (!REAL) {
+        const double gi = lf.gim[b];
+        const double tr = (a ? pr.re : -pr.re) + (cb ? pc.re : -pc.re);
+        const double ti = (a ? pr.im : -pr.im) + (cb ? pc.im : -pc.im);
+        sre = fma(-gi, ti, sre);
+        sim = fma(gi, tr, sim);
+      }
+    }
+    const cplx h{fma(dg, v.re, sre), fma(dg, v.im, sim)};
+    cplx acc = lf.kappa * h;
+    const int n3 = __popc(r & c), n2 = __popc(r & ~c & smask), n1 = __popc(~r & c & smask), n0 = nq - n1 - n2 - n3;
+    const cplx dsum{n0 * lf.dd[0].re + n1 * lf.dd[1].re + n2 * lf.dd[2].re + n3 * lf.dd[3].re,
+                    n0 * lf.dd[0].im + n1 * lf.dd[1].im + n2 * lf.dd[2].im + n3 * lf.dd[3].im};
+    fma_acc(acc, dsum, v);
+    for (int k = 0; k < lf.n_off; ++k) {
+      const int p = lf.off_p[k], x = p ^ lf.off_pp[k];
+      unsigned sel = ((p & 2) ? r : ~r) & ((p & 1) ? c : ~c) & smask;     // sites whose (a, c) pair is p
+      const cplx coef = lf.off_c[k];
+      while (sel) {
+        const int b = __ffs((int)sel) - 1;
+        sel &= sel - 1;
+        const size_t m = ((x & 2) ? ((size_t)1 << (b + nq)) : 0) | ((x & 1) ? ((size_t)1 << b) : 0);
+        fma_acc(acc, coef, in[idx ^ m]);
+      }
+    }
+    out[idx] = acc;
+   }
+}
+
 // Column-tile variant of k_apply_density, OPT-IN (PD_DENSITY_CT=1; measured slower, profiles/r02_lindblad.md).
 // A CTA stages 2^10 CONTIGUOUS entries in shared memory: every flip whose mask lies inside the tile -- the column
 // bits of the last 10 sites (and, for small registers, low row bits) -- is served from shared memory, only the
@@ -355,10 +419,15 @@ k_corr_density_fused(const amp_t* __restrict__ kbar, const amp_t* __restrict__ y
       if (q < nq) {
         size_t mc = (size_t)1 << (nq - 1 - q), mr = mc << nq;
         bool a = (e & mr) != 0, b = (e & mc) != 0;
-        cplx frow = kb * y[idx ^ mr], fcol = kb * y[idx ^ mc];
-        acc[q * 3 + 0] += ((a ? 0.0 : 1.0) - (b ? 0.0 : 1.0)) * self.im;
-        acc[q * 3 + 1] += frow.im - fcol.im;
-        acc[q * 3 + 2] += (a ? frow.re : -frow.re) + (b ? fcol.re : -fcol.re);
+        // Im(kb (yr - yc)) and Re(kb (sa yr + sb yc)) from the combined partners: 4 additions + 4 FMAs per site
+        // instead of two complex products
+        const cplx yr = y[idx ^ mr], yc = y[idx ^ mc];
+        const double dre = yr.re - yc.re, dim_ = yr.im - yc.im;
+        const double tre = (a ? yr.re : -yr.re) + (b ? yc.re : -yc.re);
+        const double tim = (a ? yr.im : -yr.im) + (b ? yc.im : -yc.im);
+        acc[q * 3 + 0] += (a == b) ? 0.0 : (a ? -self.im : self.im);
+        acc[q * 3 + 1] = fma(kb.re, dim_, fma(kb.im, dre, acc[q * 3 + 1]));
+        acc[q * 3 + 2] = fma(kb.re, tre, fma(-kb.im, tim, acc[q * 3 + 2]));
       }
     }
     if (wacc) {
@@ -514,6 +583,18 @@ int launch_apply_density(const Geometry& g, amp_t* out, const amp_t* in, const S
   for (int q = 0; q < so.nsites; ++q)
     for (int p = 0; p < 4; ++p)
       if (so.nzmask[q] >> (p * 4 + (p ^ 3)) & 1) need_both = 1;
+  // PD_LINDBLAD_FORM=0 keeps the general 4x4 kernels (A/B measurements)
+  static const bool use_form = [] { const char* e = std::getenv("PD_LINDBLAD_FORM"); return !e || e[0] != '0'; }();
+  if (use_form && so.form.ok && so.form.nq == g.nq && total >= 256) {
+    static const int chunk_env = [] { const char* e = std::getenv("PD_LINDBLAD_CHUNK"); return e ? std::atoi(e) : 12; }();
+    int chunk_log2 = std::max(8, std::min(chunk_env, 2 * g.nq));
+    while (chunk_log2 > 8 && (total >> chunk_log2) < (size_t)148 * 6) --chunk_log2;   // keep every SM busy
+    const int grid = (int)std::min<size_t>(total >> chunk_log2, (size_t)148 * 16);
+    if (so.form.real_drive) k_apply_lindblad<true><<<grid, kThreads, 0, s>>>(out, in, g.diag, so.form, total, chunk_log2);
+    else k_apply_lindblad<false><<<grid, kThreads, 0, s>>>(out, in, g.diag, so.form, total, chunk_log2);
+    PD_CUDA_CHECK(cudaGetLastError());
+    return 1;
+  }
   // PD_DENSITY_CT=1 selects the column-tile kernel (A/B measurements; slower on B200)
   static const bool use_ct = [] { const char* e = std::getenv("PD_DENSITY_CT"); return e && e[0] == '1'; }();
   if (use_ct && total >= (size_t)kDTile && total % kDTile == 0) {

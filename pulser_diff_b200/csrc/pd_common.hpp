@@ -91,11 +91,27 @@ struct SiteOps {
   cplx kappa;
   cplx T[kMaxQubits * 4];  // ket layout [q][a][a']; density uses SiteOpsDensity below
 };
+// The same super-operator in its generator-specific form (gather_kernels.cu k_apply_lindblad): instead of a
+// general 4x4 matrix per site, the pieces it is made of --
+//   out[e] = kappa * [ (Dint[r] - Dint[c] + sum_b d_b ((a_b == 0) - (c_b == 0))) rho[e]
+//                      + sum_b ( h_b(a_b) rho[e ^ row bit b] - conj(h_b(c_b)) rho[e ^ column bit b] ) ]
+//            + sum_b dd[p_b] rho[e] + sum over the dissipator's off-diagonal entries (p <- p') and the sites b with
+//              p_b = p of off_c * rho[e with site b set to p'],
+// h_b(x) = x ? g_b : conj(g_b), p_b = 2 a_b + c_b; arrays indexed by BIT position b (site q = nq - 1 - b).
+struct LindbladForm {
+  int ok = 0, nq = 0, real_drive = 0, n_off = 0;
+  cplx kappa{0, 0};
+  double d[kMaxSitesDensity], gre[kMaxSitesDensity], gim[kMaxSitesDensity];
+  cplx dd[4];
+  int off_p[12], off_pp[12];
+  cplx off_c[12];
+};
 struct SiteOpsDensity {
   int nsites;
   cplx kappa;
   unsigned nzmask[kMaxSitesDensity];  // bit (p*4+p') set <=> T[q][p][p'] != 0 for some use
   cplx T[kMaxSitesDensity * 16];      // [q][p][p']
+  LindbladForm form;
 };
 
 struct Geometry {
@@ -225,6 +241,25 @@ struct Program {
     coefficients(t, d, g);
     so.nsites = nq;
     so.kappa = mode == 0 ? cplx{0, -1} : cplx{0, 1};
+    {
+      LindbladForm& lf = so.form;
+      lf = LindbladForm{};
+      lf.ok = 1; lf.nq = nq; lf.kappa = so.kappa; lf.real_drive = 1;
+      for (int q = 0; q < nq; ++q) {
+        const int b = nq - 1 - q;
+        lf.d[b] = d[q]; lf.gre[b] = g[q].re; lf.gim[b] = g[q].im;
+        if (g[q].im != 0.0) lf.real_drive = 0;
+      }
+      for (int p = 0; p < 4; ++p)
+        for (int pp = 0; pp < 4; ++pp) {
+          cplx z = !has_dsup ? cplx{0, 0} : (mode == 0 ? dsup[p * 4 + pp] : conj(dsup[pp * 4 + p]));
+          if (p == pp) lf.dd[p] = z;
+          else if (z.re != 0.0 || z.im != 0.0) {
+            lf.off_p[lf.n_off] = p; lf.off_pp[lf.n_off] = pp; lf.off_c[lf.n_off] = z;
+            ++lf.n_off;
+          }
+        }
+    }
     const cplx mi{0, -1}, pi{0, 1};
     for (int q = 0; q < nq; ++q) {
       cplx F[16];

@@ -30,6 +30,6 @@ for cd in (torch.complex128, torch.complex64):
     ms = plan.bench_dp5_steps(0.3, 1e-3, 3, y.clone())
     ab = 16 if cd == torch.complex128 else 8
     alg = (33 * ab) * 4 ** n
-    print(json.dumps({"n": n, "dtype": str(cd), "ct": os.environ.get("PD_DENSITY_CT", "1"), "ms_apply": ms_apply,
+    print(json.dumps({"n": n, "dtype": str(cd), "ct": os.environ.get("PD_DENSITY_CT", "0"), "form": os.environ.get("PD_LINDBLAD_FORM", "1"), "ms_apply": ms_apply,
                       "ms_dp5_me_step": ms, "frac": alg / ms / 1e6 / 6548.2, "checksum": float(out.abs().sum())}))
     del plan
