@@ -758,10 +758,11 @@ def sharded_measure(dev, rank, world, local_qubits, steps, warmup, cdtype=torch.
     parity = sharded_parity(dev, rank, world) if parity else None
     ab = 16.0 if cdtype == torch.complex128 else 8.0          # bytes per amplitude
     # largest slice that fits: the forward evolution holds y, 7 slopes, the next state, the peer-visible
-    # buffer, g receive buffers, 2 saved states and ~2 transients (16 B/amplitude each) + the 8 B diagonal
+    # buffer, g receive buffers, 2 saved states, the bench's own initial state and the plan's two scratch
+    # vectors (one amplitude each) + the 8 B diagonal
     free = torch.tensor([torch.cuda.mem_get_info(dev)[0]], dtype=torch.float64, device=dev)
     dist.all_reduce(free, op=dist.ReduceOp.MIN)
-    need = lambda nl: ((14 + g) * ab + 8) * 2.0 ** nl * 1.12
+    need = lambda nl: ((15 + g) * ab + 8) * 2.0 ** nl * 1.05
     while local_qubits > 20 and need(local_qubits) > free.item():
         local_qubits -= 1
     n = local_qubits + g

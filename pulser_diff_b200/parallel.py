@@ -356,7 +356,9 @@ class ShardedKet:
         slopes = [torch.empty_like(y) for _ in range(7)]
         y_next = torch.empty_like(y)
         k0 = self.rhs(t, y, out=slopes[0])
-        steps, states = [], []
+        steps = []
+        # the saved states go straight into the result (no list + stack: two more vectors at the peak)
+        states = torch.empty((len(ts),) + tuple(y.shape), dtype=y.dtype, device=y.device)
         if replay is None:
             d0 = self._scaled_norm(y, y.abs(), atol, rtol)
             d1 = self._scaled_norm(k0, y.abs(), atol, rtol)
@@ -400,8 +402,8 @@ class ShardedKet:
                 if n_att >= max_steps:
                     raise RuntimeError("max_steps reached")
             dt, error = cache_dt, cache_err
-            states.append(y.clone())
-        return torch.stack(states), steps
+            states[kk].copy_(y)
+        return states, steps
 
     def _vjp(self, t: float, Y: Tensor, kbar: Tensor, acc: dict) -> Tensor:
         """Reverse mode of k = -i H(t) Y on the sharded register: returns this rank's slice of
