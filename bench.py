@@ -246,7 +246,7 @@ def c3_setup(dev):
     return idx, tsave, pair_u, torch.kron(had, had)
 
 
-def c3_batch(dev, rank, world, reps, barrier):
+def c3_batch(dev, rank, world, reps, barrier, weak=False):
     """BASELINE configs[2]: 4096 parameter sets of the 2-atom gate workload (8 constant pulses x 131 ns,
     psi0 = eye(4), rate 0.05, Hadamard x Hadamard infidelity, gradient w.r.t. the 24 parameters of every
     set), dealt over the ranks; tables, evolution, loss and gradients stay on the device."""
@@ -255,8 +255,10 @@ def c3_batch(dev, rank, world, reps, barrier):
     idx, tsave, pair_u, target = c3_setup(dev)
     target = target.to(dev)
     g = torch.Generator().manual_seed(0)
-    params_all = torch.rand(C3["n_sets"], 3, C3["pulses"], dtype=torch.float64, generator=g) * 4 * math.pi
-    mine = parallel.shard_units(C3["n_sets"], rank, world) if world > 1 else list(range(C3["n_sets"]))
+    # weak: every rank brings a full batch of its own (n_sets x world sets in total)
+    n_total = C3["n_sets"] * (world if weak else 1)
+    params_all = torch.rand(n_total, 3, C3["pulses"], dtype=torch.float64, generator=g) * 4 * math.pi
+    mine = parallel.shard_units(n_total, rank, world) if world > 1 else list(range(n_total))
     params = params_all[mine].to(dev).requires_grad_(True)
     idx_d = idx.to(dev)
     psi0 = torch.eye(4, dtype=torch.complex128, device=dev).repeat(len(mine), 1, 1)
@@ -504,6 +506,15 @@ def run_b200(args):
                   "seconds_per_sweep": tt.item(), "sets_per_s": C3["n_sets"] / tt.item(),
                   "sum_loss": chk[0].item(), "sum_abs_grad": chk[1].item(),
                   "tables": "built on the device from the parameters (no host tables cross the ABI)"}
+            if world > 1:
+                # one sweep of 4096/world sets is a fraction of ONE wave of per-set latency chains (16 one-warp
+                # units per SM), so the strong-scaling time is bounded below by a single set's forward + adjoint
+                # chain; with a full batch per GPU the same kernels scale with the device count:
+                w_s, _, _, w_mine = c3_batch(dev, rank, world, 3, barrier, weak=True)
+                wt = torch.tensor([w_s], dtype=torch.float64, device=dev)
+                dist.all_reduce(wt, op=dist.ReduceOp.MAX)
+                c3["weak"] = {"n_sets": C3["n_sets"] * world, "sets_per_rank": w_mine, "seconds_per_sweep": wt.item(),
+                              "sets_per_s": C3["n_sets"] * world / wt.item()}
         except Exception as exc:
             c3 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
