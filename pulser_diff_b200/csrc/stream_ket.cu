@@ -53,7 +53,11 @@ static_assert(sizeof(tcplx) == sizeof(amp_t), "tile type and storage type share 
 __host__ __device__ inline const tcplx* tc(const amp_t* p) { return reinterpret_cast<const tcplx*>(p); }
 __host__ __device__ inline tcplx* tc(amp_t* p) { return reinterpret_cast<tcplx*>(p); }
 constexpr int kAmpBytes = (int)sizeof(tcplx);
+#if defined(PD_MINCTAS)
+constexpr int kMinCtas = PD_MINCTAS;     // (A/B builds)
+#else
 constexpr int kMinCtas = kC64 ? 4 : 3;   // resident CTAs per SM the REAL-drive kernels are compiled for
+#endif
 
 constexpr int TB = 12;
 constexpr int TILE = 1 << TB;

@@ -1,5 +1,5 @@
 """complex64 vs complex128: fused DP5 step and H.psi at N qubits (device time from the C ABI's CUDA events),
-plus the adjoint per step.  Usage: python scripts/c64_bench.py [N ...]"""
+plus the adjoint per step.  Usage: python scripts/c64_bench.py [N ...] [c64only] [--lib=PATH_TO_A_C64_BUILD]"""
 import os, sys, time
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -7,6 +7,10 @@ sys.path.insert(0, ROOT)
 from pulser_diff_b200 import _cabi
 
 dev = torch.device("cuda", 0)
+libs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--lib=")]
+if libs:
+    _cabi.use_library(None, os.path.abspath(libs[0]))      # A/B builds of the complex64 library
+only64 = "c64only" in sys.argv
 
 
 def plan_for(n, cd):
@@ -20,8 +24,8 @@ def plan_for(n, cd):
     return plan
 
 
-for n in [int(a) for a in sys.argv[1:]] or [26]:
-    for cd in (torch.complex128, torch.complex64):
+for n in [int(a) for a in sys.argv[1:] if a.isdigit()] or [26]:
+    for cd in ((torch.complex64,) if only64 else (torch.complex128, torch.complex64)):
         plan = plan_for(n, cd)
         y = torch.zeros(1, 2 ** n, dtype=cd, device=dev)
         y[0, -1] = 1.0
