@@ -434,9 +434,9 @@ def run_b200(args):
     if rank == 0 and args.roofline_n > 0:
         def measure(nr, cdtype=torch.complex128):
             # algorithmic bytes per amplitude: DP5 step = (26 reads + 7 writes) amplitudes + 6
-            # diagonal doubles; H.psi = read + write + one diagonal double
+            # diagonal reals = 576 (complex128) / 288 (complex64); H.psi = read + write + one diagonal real = 40 / 20
             ab = 16.0 if cdtype == torch.complex128 else 8.0
-            b_step, b_h = 33.0 * ab + 48.0, 2.0 * ab + 8.0
+            b_step, b_h = 33.0 * ab + 3.0 * ab, 2.0 * ab + 0.5 * ab
             ops.clear_plan_cache()
             big = _cabi.Plan(nr, 1, _cabi.PD_KET, dev, cdtype)
             cu = torch.zeros(nr, nr, dtype=torch.float64)
@@ -839,9 +839,9 @@ def sharded_measure(dev, rank, world, local_qubits, steps, warmup, cdtype=torch.
                         "one accumulate kernel (pd_sharded_accumulate)",
             "local_qubits": local_qubits, "bytes_per_vector_per_gpu": ab * amps,
             "ms_per_hpsi": ms_h, "hpsi_per_s": 1e3 / ms_h,
-            "roofline_hpsi": roof((2 * ab + 8) * amps, g * ab * amps, ms_h),
+            "roofline_hpsi": roof(2.5 * ab * amps, g * ab * amps, ms_h),
             "ms_per_dp5_step": ms_e, "dp5_steps_per_s": 1e3 / ms_e,
-            "roofline_dp5_step": roof((33 * ab + 48) * amps, 6 * g * ab * amps, ms_e),
+            "roofline_dp5_step": roof(36 * ab * amps, 6 * g * ab * amps, ms_e),
             "peak_hbm_GBs": peak,
             "nvlink_measured": {"GBs_per_direction_per_gpu": nvlink, "how": f"{g} concurrent peer copies of one "
                                 f"{ab * amps / 2 ** 30:.2f} GiB slice per rank, CUDA events, max over ranks",

@@ -36,7 +36,7 @@ for n in [int(a) for a in sys.argv[1:] if a.isdigit()] or [26]:
         mh = plan.bench_hpsi(0.3, psi, 12)
         ab = 16.0 if cd == torch.complex128 else 8.0
         amps = 2.0 ** n
-        print(f"N={n} {str(cd):18s} dp5 step {ms:8.3f} ms ({(33 * ab + 48) * amps / ms / 1e6:7.0f} GB/s algorithmic)   "
+        print(f"N={n} {str(cd):18s} dp5 step {ms:8.3f} ms ({36 * ab * amps / ms / 1e6:7.0f} GB/s algorithmic)   "
               f"hpsi {mh:7.3f} ms ({(2 * ab + 8) * amps / mh / 1e6:7.0f} GB/s)  |y|={float(y.norm()):.6f}", flush=True)
         del plan, y, psi
         torch.cuda.empty_cache()
