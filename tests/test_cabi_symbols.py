@@ -32,6 +32,12 @@ def test_cuda_library_exports_every_symbol():
     lib.pd_abi_version.restype = ctypes.c_int
     assert lib.pd_abi_version() == 1
     assert lib.pd_is_cuda() == 1
+    assert lib.pd_amplitude_bytes() == 16
+    # the complex64 build of the same ABI (north_star's optional tier): same symbols, 8-byte amplitudes
+    lib64 = ctypes.CDLL(g.LIB_C64)
+    for name in declared_symbols():
+        assert hasattr(lib64, name), name
+    assert lib64.pd_abi_version() == 1 and lib64.pd_is_cuda() == 1 and lib64.pd_amplitude_bytes() == 8
 
 
 def test_product_refuses_cpu(emu_library):
