@@ -165,12 +165,14 @@ k_apply_density(amp_t* __restrict__ out, const amp_t* __restrict__ in, const dou
 // bound by that, not by bytes (profiles/r02_lindblad.md).  Here per site: two partner loads and 2 DADD + 2 DFMA for a
 // phase-free drive (coefficients from the constant bank, uniform index), the dissipator's diagonal from four popcounts,
 // its off-diagonal entries only at the sites that feed them (bit scan over the matching sites).
-template <bool REAL>
+// UD: every site has the same detuning coefficient (a global channel): its diagonal comes from two popcounts.
+// IdxT: 32-bit entry indices while 4^N * batch < 2^31 (one IMAD.WIDE per partner address).
+template <bool REAL, bool UD, class IdxT>
 __global__ void __launch_bounds__(kThreads)
 k_apply_lindblad(amp_t* __restrict__ out, const amp_t* __restrict__ in, const double* __restrict__ diag,
                  const __grid_constant__ LindbladForm lf, size_t total, int chunk_log2) {
   const int nq = lf.nq;
-  const size_t S = (size_t)1 << nq, dim = S * S;
+  const IdxT S = (IdxT)1 << nq, dim = S * S;
   const unsigned smask = (unsigned)(S - 1);
   // a CTA walks chunks of 2^chunk_log2 consecutive entries (kThreads at a time), so the column-bit partners inside
   // the chunk are lines the same CTA touches a moment earlier or later (L1) instead of L2 round trips
@@ -178,19 +180,23 @@ k_apply_lindblad(amp_t* __restrict__ out, const amp_t* __restrict__ in, const do
   const size_t per_chunk = (size_t)1 << (chunk_log2 - 8);
   for (size_t it = (size_t)blockIdx.x * per_chunk; it < n_items; it += (size_t)gridDim.x * per_chunk)
    for (size_t sub = 0; sub < per_chunk && it + sub < n_items; ++sub) {
-    const size_t idx = ((it + sub) << 8) + threadIdx.x;
-    const size_t e = idx & (dim - 1);
+    const IdxT idx = (IdxT)(((it + sub) << 8) + threadIdx.x);
+    const IdxT e = idx & (dim - 1);
     const unsigned r = (unsigned)(e >> nq), c = (unsigned)(e & (S - 1));
     const cplx v = in[idx];
     double dg = diag[r] - diag[c];
+    if (UD) dg += lf.d[0] * (double)(__popc(~r & smask) - __popc(~c & smask));
     double sre = 0.0, sim = 0.0;
 #pragma unroll 4
     for (int b = 0; b < nq; ++b) {
-      const size_t mc = (size_t)1 << b, mr = mc << nq;
+      const IdxT mc = (IdxT)1 << b, mr = mc << nq;
       const bool a = (r >> b) & 1u, cb = (c >> b) & 1u;
       const cplx pr = in[idx ^ mr], pc = in[idx ^ mc];
-      const double db = lf.d[b], gr = lf.gre[b];
-      dg += (a ? 0.0 : db) - (cb ? 0.0 : db);
+      const double gr = lf.gre[b];
+      if (!UD) {
+        const double db = lf.d[b];
+        dg += (a ? 0.0 : db) - (cb ? 0.0 : db);
+      }
       sre = fma(gr, pr.re - pc.re, sre);
       sim = fma(gr, pr.im - pc.im, sim);
       if (!REAL) {
@@ -214,7 +220,7 @@ k_apply_lindblad(amp_t* __restrict__ out, const amp_t* __restrict__ in, const do
       while (sel) {
         const int b = __ffs((int)sel) - 1;
         sel &= sel - 1;
-        const size_t m = ((x & 2) ? ((size_t)1 << (b + nq)) : 0) | ((x & 1) ? ((size_t)1 << b) : 0);
+        const IdxT m = ((x & 2) ? ((IdxT)1 << (b + nq)) : 0) | ((x & 1) ? ((IdxT)1 << b) : 0);
         fma_acc(acc, coef, in[idx ^ m]);
       }
     }
@@ -402,20 +408,31 @@ k_corr_ket(const amp_t* __restrict__ kbar, const amp_t* __restrict__ y, int nq, 
 // with the row / column bit flipped.  (A per-site 4x4 correlation kernel, the first version, cost one
 // pass over the 4^N vector per site.)
 constexpr int kDF = 3 * kMaxSitesDensity;
-__global__ void __launch_bounds__(kThreads)
+// MAXQ: sites the instantiation keeps accumulators for (3 per site, in registers); two CTAs per SM (128 registers:
+// three CTAs spill, one more register than 128 halves the occupancy).  Partial layout [block][3 * MAXQ].
+template <int MAXQ>
+__global__ void __launch_bounds__(kThreads, 2)
 k_corr_density_fused(const amp_t* __restrict__ kbar, const amp_t* __restrict__ y, int nq, size_t total,
-                     double* partial, double* wacc, double wscale) {
+                     double* partial, double* wacc, double wscale, int chunk_log2) {
+  constexpr int kAcc = 3 * MAXQ;
   size_t S = (size_t)1 << nq, dim = S * S;
-  double acc[kDF];
+  double acc[kAcc];
 #pragma unroll
-  for (int i = 0; i < kDF; ++i) acc[i] = 0.0;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+  for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+  // chunk_log2 >= 8 (total is a multiple of 256): a CTA walks 2^chunk_log2 consecutive entries, kThreads at a time
+  // (column partners inside the chunk are lines it touches anyway); chunk_log2 == 0: plain grid-stride walk
+  const size_t n_items = chunk_log2 ? total >> 8 : 0;
+  const size_t per_chunk = chunk_log2 ? (size_t)1 << (chunk_log2 - 8) : 1;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t it = chunk_log2 ? (size_t)blockIdx.x * per_chunk : (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+       it < (chunk_log2 ? n_items : total); it += chunk_log2 ? (size_t)gridDim.x * per_chunk : stride)
+   for (size_t sub = 0; sub < per_chunk && (!chunk_log2 || it + sub < n_items); ++sub) {
+    const size_t idx = chunk_log2 ? ((it + sub) << 8) + threadIdx.x : it;
     size_t e = idx & (dim - 1);
     cplx kb = conj(kbar[idx]);
     cplx self = kb * y[idx];
 #pragma unroll
-    for (int q = 0; q < kMaxSitesDensity; ++q) {
+    for (int q = 0; q < MAXQ; ++q) {
       if (q < nq) {
         size_t mc = (size_t)1 << (nq - 1 - q), mr = mc << nq;
         bool a = (e & mr) != 0, b = (e & mc) != 0;
@@ -435,10 +452,10 @@ k_corr_density_fused(const amp_t* __restrict__ kbar, const amp_t* __restrict__ y
       atomicAdd(&wacc[e >> nq], w);
       atomicAdd(&wacc[e & (S - 1)], -w);
     }
-  }
-  block_reduce_write<kDF>(acc, partial);
+   }
+  block_reduce_write<kAcc>(acc, partial);
 }
-// Column-tile variant (same sums, same partial layout): the y tile of 2^10 contiguous entries sits in shared
+// Column-tile variant (same sums, partial layout [block][3 * 16]): the y tile of 2^10 contiguous entries sits in shared
 // memory, so the column-bit partners of the last 10 sites never go through L2 (N = 12: 2 + 14 fetches per entry
 // instead of 2 + 24).
 __global__ void __launch_bounds__(kThreads)
@@ -485,11 +502,12 @@ k_corr_density_ct(const amp_t* __restrict__ kbar, const amp_t* __restrict__ y, i
   block_reduce_write<kDF>(acc, partial);
 }
 // d_corr[q][16]: zero except the three entries engine.hpp::distribute turns back into (gd, ga, gb)
-__global__ void k_corr_density_scatter(const double* __restrict__ partial, int nblocks, int nq, cplx* d_corr) {
+__global__ void k_corr_density_scatter(const double* __restrict__ partial, int nblocks, int nq, cplx* d_corr,
+                                       int pstride) {
   int q = blockIdx.x, lane = threadIdx.x;   // one warp per site
   double v[3] = {0.0, 0.0, 0.0};
   for (int b = lane; b < nblocks; b += 32)
-    for (int k = 0; k < 3; ++k) v[k] += partial[(size_t)b * kDF + q * 3 + k];
+    for (int k = 0; k < 3; ++k) v[k] += partial[(size_t)b * pstride + q * 3 + k];
   for (int k = 0; k < 3; ++k) v[k] = warp_sum(v[k]);
   if (lane < 16) d_corr[q * 16 + lane] = cplx{0.0, 0.0};
   __syncwarp();
@@ -590,8 +608,18 @@ int launch_apply_density(const Geometry& g, amp_t* out, const amp_t* in, const S
     int chunk_log2 = std::max(8, std::min(chunk_env, 2 * g.nq));
     while (chunk_log2 > 8 && (total >> chunk_log2) < (size_t)148 * 6) --chunk_log2;   // keep every SM busy
     const int grid = (int)std::min<size_t>(total >> chunk_log2, (size_t)148 * 16);
-    if (so.form.real_drive) k_apply_lindblad<true><<<grid, kThreads, 0, s>>>(out, in, g.diag, so.form, total, chunk_log2);
-    else k_apply_lindblad<false><<<grid, kThreads, 0, s>>>(out, in, g.diag, so.form, total, chunk_log2);
+    bool ud = true;
+    for (int b = 1; b < g.nq; ++b) ud = ud && so.form.d[b] == so.form.d[0];
+    static const bool narrow_ok = [] { const char* e = std::getenv("PD_LINDBLAD_IDX32"); return !e || e[0] != '0'; }();
+    const bool narrow = narrow_ok && total < ((size_t)1 << 31);
+    auto go = [&](auto* f) { f<<<grid, kThreads, 0, s>>>(out, in, g.diag, so.form, total, chunk_log2); };
+    if (narrow) {
+      if (so.form.real_drive) { if (ud) go(k_apply_lindblad<true, true, unsigned>); else go(k_apply_lindblad<true, false, unsigned>); }
+      else { if (ud) go(k_apply_lindblad<false, true, unsigned>); else go(k_apply_lindblad<false, false, unsigned>); }
+    } else {
+      if (so.form.real_drive) { if (ud) go(k_apply_lindblad<true, true, size_t>); else go(k_apply_lindblad<true, false, size_t>); }
+      else { if (ud) go(k_apply_lindblad<false, true, size_t>); else go(k_apply_lindblad<false, false, size_t>); }
+    }
     PD_CUDA_CHECK(cudaGetLastError());
     return 1;
   }
@@ -688,18 +716,27 @@ int launch_corr(const Geometry& g, cplx* d_corr, double* d_wacc, double wscale, 
   } else {
     size_t total = g.dim * g.batch;
     int gx = rgrid_for(total, kDF, 1);
+    int pstride = kDF;
     static const bool use_ct = [] { const char* e = std::getenv("PD_DENSITY_CT"); return e && e[0] == '1'; }();
     if (use_ct && total >= (size_t)kDTile && total % kDTile == 0) {
       const size_t n_tiles = total >> kDTB;
       gx = (int)std::min<size_t>(n_tiles, (size_t)gx);
       k_corr_density_ct<<<gx, kThreads, 0, s>>>(kbar, y, g.nq, n_tiles, scratch, d_wacc, wscale);
     } else {
-      k_corr_density_fused<<<gx, kThreads, 0, s>>>(kbar, y, g.nq, total, scratch, d_wacc, wscale);
+      static const int chunk_env = [] { const char* e = std::getenv("PD_LINDBLAD_CHUNK"); return e ? std::atoi(e) : 12; }();
+      int chunk_log2 = (chunk_env > 0 && total % 256 == 0 && total >= 256) ? std::max(8, std::min(chunk_env, 2 * g.nq)) : 0;
+      while (chunk_log2 > 8 && (total >> chunk_log2) < (size_t)gx) --chunk_log2;
+      if (g.nq <= 12) {
+        pstride = 36;
+        k_corr_density_fused<12><<<gx, kThreads, 0, s>>>(kbar, y, g.nq, total, scratch, d_wacc, wscale, chunk_log2);
+      } else {
+        k_corr_density_fused<16><<<gx, kThreads, 0, s>>>(kbar, y, g.nq, total, scratch, d_wacc, wscale, chunk_log2);
+      }
     }
     PD_CUDA_CHECK(cudaGetLastError());
     ++n;
     if (d_corr) {
-      k_corr_density_scatter<<<g.nq, 32, 0, s>>>(scratch, gx, g.nq, d_corr);
+      k_corr_density_scatter<<<g.nq, 32, 0, s>>>(scratch, gx, g.nq, d_corr, pstride);
       PD_CUDA_CHECK(cudaGetLastError());
       ++n;
     }
