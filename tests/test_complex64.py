@@ -97,10 +97,10 @@ def test_density_computed_in_complex64(engine_device):
         assert _close(g, r, 2e-5)
 
 
-def _chain_plan(n, dev, dtype, path=0):
+def _chain_plan(n, dev, dtype, path=0, batch=1):
     """A plan of the N-atom chain with a global drive (phase != 0: the general flip arithmetic) and one
     local detuning, as the large-register tests of test_gpu_scale.py build it."""
-    plan = _cabi.Plan(n, 1, _cabi.PD_KET, dev, dtype)
+    plan = _cabi.Plan(n, batch, _cabi.PD_KET, dev, dtype)
     x = torch.arange(n, dtype=torch.float64) * 6.0
     r = (x[:, None] - x[None, :]).abs() + torch.eye(n, dtype=torch.float64)
     u = torch.triu(865723.02 / r ** 6, diagonal=1)
@@ -116,15 +116,15 @@ def _chain_plan(n, dev, dtype, path=0):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,path", [(15, 0), (17, 1), (17, 4), (19, 0), (21, 0)])
-def test_hpsi_complex64_families(cuda_device, n, path):
+@pytest.mark.parametrize("n,path,batch", [(15, 0, 1), (17, 1, 3), (17, 4, 1), (19, 0, 2), (21, 0, 1)])
+def test_hpsi_complex64_families(cuda_device, n, path, batch):
     """One H(t) psi per kernel family of the complex64 library (gather: N = 15, 17; stream: N = 17 on request,
-    19 and 21 by default) against the complex128 library on the same vector."""
+    19 and 21 by default; batches of columns on both) against the complex128 library on the same vectors."""
     g = torch.Generator(device="cpu").manual_seed(n)
-    psi = torch.randn(1, 2 ** n, dtype=C128, generator=g)
+    psi = torch.randn(batch, 2 ** n, dtype=C128, generator=g)
     psi = (psi / psi.norm()).to(cuda_device)
-    ref = _chain_plan(n, cuda_device, C128).hpsi(0.11, psi)
-    got = _chain_plan(n, cuda_device, C64, path).hpsi(0.11, psi.to(C64))
+    ref = _chain_plan(n, cuda_device, C128, 0, batch).hpsi(0.11, psi)
+    got = _chain_plan(n, cuda_device, C64, path, batch).hpsi(0.11, psi.to(C64))
     assert got.dtype == C64
     assert _close(got, ref, 2e-6)           # one application: float round-off of ~N terms
 
