@@ -1025,7 +1025,13 @@ Groups make_groups(int nq) {
   // the even split by 3-4 %.
   static const unsigned g1_env = env_unsigned("PD_STREAM_G1BITS", 0);
   if (gr.G == 2) {
-    const int nb0 = g1_env ? (int)g1_env : (rest >= 12 ? std::max(rest - kMaxGroupBits, 6) : gr.nb[0]);
+    // complex64: a 7-bit second group keeps its strided pieces at 256 B (32 amplitudes of 8 B); measured at N = 26:
+    // 6 + 8 bits 6.48 ms, 7 + 7 bits 6.06 ms, 8 + 6 bits 7.07 ms per DP5 step; N = 27: 7 + 8 bits 12.9 ms, 8 + 7 bits
+    // 14.3 ms (profiles/r02_c64.md)
+    constexpr int kSecondGroupBits = kC64 ? 7 : kMaxGroupBits;
+    int nb0 = rest >= 12 ? std::max(rest - kSecondGroupBits, 6) : gr.nb[0];
+    if (nb0 > 7) nb0 = std::max(rest - kMaxGroupBits, 6);      // (an 8-bit FIRST group is the slower trade: N = 27)
+    if (g1_env) nb0 = (int)g1_env;
     const int nb1 = rest - nb0;
     if (nb0 >= 4 && nb0 <= kMaxGroupBits && nb1 >= 4 && nb1 <= kMaxGroupBits) { gr.nb[0] = nb0; gr.nb[1] = nb1; }
   }
